@@ -1,0 +1,100 @@
+"""ctypes binding of libsarnet_sm100.so (the C ABI declared in include/sarnet.h).
+
+PyTorch is plumbing here: it owns device memory and streams; every tensor crosses the
+boundary as a raw device pointer + sizes.  There is NO fallback: if the library is missing,
+cannot be loaded, or no CUDA device is present, the product path raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libsarnet_sm100.so")
+
+_lib = None
+
+c_fp = C.c_void_p      # const float* / float* (device)
+c_ip = C.c_void_p
+c_int = C.c_int
+c_f = C.c_float
+c_ll = C.c_longlong
+c_sz = C.c_size_t
+
+# name -> (restype, argtypes); MUST list every symbol include/sarnet.h declares
+SIGNATURES = {
+    "sar_version": (c_int, []),
+    "sar_last_error": (C.c_char_p, []),
+    "sar_compiled_arch": (c_int, []),
+    "sar_conv2d_fwd": (c_int, [c_fp] * 9 + [c_int] * 13 + [C.c_void_p]),
+    "sar_maxpool2d_fwd": (c_int, [c_fp, c_fp] + [c_int] * 10 + [C.c_void_p]),
+    "sar_affine_relu_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_ll, c_int, c_int, C.c_void_p]),
+    "sar_layernorm_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_ll, c_int, c_f, C.c_void_p]),
+    "sar_bigru_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, C.c_void_p]),
+    "sar_vlad_fwd": (c_int, [c_fp] * 6 + [c_int] * 5 + [C.c_void_p]),
+    "sar_avgpool_fwd": (c_int, [c_fp, c_fp, c_int, c_int, c_int, C.c_void_p]),
+    "sar_gemm_splitk_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
+    "sar_gemm_splitk_fwd": (c_int, [c_fp] * 4 + [c_int] * 3 + [C.c_void_p, c_sz, C.c_void_p]),
+    "sar_head_fwd": (c_int, [c_fp, c_int, c_fp, c_fp, c_int, c_fp, c_fp, c_int, c_fp, c_fp,
+                             c_fp, c_int, c_fp, c_fp, c_int, c_int, c_f, c_f, c_f,
+                             c_fp, c_fp, c_fp, c_fp, c_fp, c_int, C.c_void_p]),
+    "sar_ctc_fwd": (c_int, [c_fp, c_fp, c_ip, c_ip, c_fp, c_fp, c_ip, c_int, c_int, c_int, c_int, C.c_void_p]),
+    "sar_loss_reduce_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, C.c_void_p]),
+    "sar_fbank_fwd": (c_int, [c_fp, c_ip, c_fp, c_fp, c_fp, c_int, c_int, c_int, C.c_void_p]),
+}
+
+
+class SarnetError(RuntimeError):
+    pass
+
+
+def load_library(path: Optional[str] = None):
+    """dlopen the C-ABI library and attach prototypes.  Loading does not need a GPU."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise SarnetError(
+            "libsarnet_sm100.so not found at %s -- build it with `python -m aesrc2020_b200.csrc.build` "
+            "(or __graft_entry__.build()); there is no CPU/PyTorch fallback for this path" % p)
+    lib = C.CDLL(p)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def lib():
+    """Library handle for compute calls: requires a CUDA device (no fallback)."""
+    l = load_library()
+    if not torch.cuda.is_available():
+        raise SarnetError("aesrc2020_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return l
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load_library().sar_last_error()
+        raise SarnetError("%s failed (rc=%d): %s" % (what or "sarnet call", rc, msg.decode() if msg else ""))
+
+
+def ptr(t: Optional[torch.Tensor]):
+    """Raw device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise SarnetError("expected a CUDA tensor at the C-ABI boundary, got %s" % t.device)
+    if not t.is_contiguous():
+        raise SarnetError("tensor crossing the C-ABI boundary must be contiguous")
+    return t.data_ptr()
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream

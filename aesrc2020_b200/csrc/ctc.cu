@@ -1,0 +1,127 @@
+// ctc.cu -- ctc_pred softmax + K.ctc_batch_cost fused (model.py:268-269, 62-71).
+//
+// Reference data flow: Dense(softmax) on the GPU -> B*S*1000 fp32 probabilities copied to the
+// HOST -> tf.nn.ctc_loss CPU kernel (TF 1.13 has no GPU CTC).  Here one CTA per utterance
+//   1. per frame t (one warp per frame): row max / sum-exp of the 1000 logits, then
+//      Z = sum_c (p_c + 1e-7)  (K.ctc_batch_cost takes log(p + eps) and tf.nn.ctc_loss
+//      re-applies softmax, i.e. q = (p + 1e-7) / Z);
+//   2. gathers only the <= 2L+1 log q[t, ext[s]] values the lattice needs into shared memory;
+//   3. runs the alpha recursion in log space (blank = C-1, repeated labels need a blank),
+//      one thread per lattice state, double-buffered, S sequential steps;
+//   4. loss = -logsumexp(alpha[last], alpha[last-1]).
+// The probabilities never leave the chip unless the caller asks for them (`probs`).
+#include "common.cuh"
+
+namespace sar {
+
+constexpr int CTC_THREADS = 256;
+constexpr float CTC_EPS = 1e-7f;
+
+__device__ __forceinline__ float lse2(float a, float b) {
+  float m = fmaxf(a, b);
+  if (m == -INFINITY) return -INFINITY;
+  return m + logf(expf(a - m) + expf(b - m));
+}
+__device__ __forceinline__ float lse3(float a, float b, float c) {
+  float m = fmaxf(a, fmaxf(b, c));
+  if (m == -INFINITY) return -INFINITY;
+  return m + logf(expf(a - m) + expf(b - m) + expf(c - m));
+}
+
+__global__ void __launch_bounds__(CTC_THREADS) ctc_kernel(const float* __restrict__ logits, const float* __restrict__ labels,
+                                                           const int* __restrict__ in_len, const int* __restrict__ lab_len,
+                                                           float* __restrict__ loss, float* __restrict__ probs,
+                                                           int* __restrict__ status, int S, int C, int Lmax) {
+  extern __shared__ __align__(16) float sm[];
+  const int NE = 2 * Lmax + 1;
+  float* lq = sm;                               // [S][NE]
+  float* alpha = lq + (size_t)S * NE;           // [2][NE]
+  int* ext = reinterpret_cast<int*>(alpha + 2 * NE);   // [NE]
+  __shared__ int bad;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int b = blockIdx.x;
+  int T = in_len[b];
+  int L = lab_len[b];
+  if (t == 0) bad = 0;
+  __syncthreads();
+  if (T < 0 || T > S || L < 0 || L > Lmax) {   // malformed lengths
+    if (t == 0) { loss[b] = INFINITY; if (status) status[b] = 2; }
+    return;
+  }
+  const int blank = C - 1;
+  const int n = 2 * L + 1;
+  for (int s = t; s < n; s += CTC_THREADS) {
+    int v = blank;
+    if (s & 1) {
+      v = (int)labels[(size_t)b * Lmax + (s >> 1)];   // K.ctc_batch_cost casts float labels to int32
+      if (v < 0 || v >= blank) { bad = 1; v = 0; }
+    }
+    ext[s] = v;
+  }
+  __syncthreads();
+
+  // ---- per-frame normalisers and gathered log q
+  for (int f = warp; f < S; f += CTC_THREADS / 32) {
+    const float* row = logits + ((size_t)b * S + f) * C;
+    float m = -INFINITY;
+    for (int c = lane; c < C; c += 32) m = fmaxf(m, __ldg(row + c));
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int c = lane; c < C; c += 32) sum += expf(__ldg(row + c) - m);
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    float z = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      float pc = expf(__ldg(row + c) - m) * inv;
+      if (probs) probs[((size_t)b * S + f) * C + c] = pc;
+      z += pc + CTC_EPS;
+    }
+    z = warp_sum(z);
+    const float logz = logf(z);
+    if (f < T) {
+      for (int s = lane; s < n; s += 32) {
+        float pc = expf(__ldg(row + ext[s]) - m) * inv;
+        lq[(size_t)f * NE + s] = logf(pc + CTC_EPS) - logz;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- alpha recursion
+  float* a0 = alpha;
+  float* a1 = alpha + NE;
+  for (int s = t; s < n; s += CTC_THREADS) a0[s] = (s < 2 && T > 0) ? lq[s] : -INFINITY;
+  __syncthreads();
+  for (int f = 1; f < T; ++f) {
+    for (int s = t; s < n; s += CTC_THREADS) {
+      float x0 = a0[s];
+      float x1 = (s >= 1) ? a0[s - 1] : -INFINITY;
+      float x2 = (s >= 2 && (s & 1) && ext[s] != ext[s - 2]) ? a0[s - 2] : -INFINITY;
+      a1[s] = lse3(x0, x1, x2) + lq[(size_t)f * NE + s];
+    }
+    __syncthreads();
+    float* tmp = a0; a0 = a1; a1 = tmp;
+  }
+  if (t == 0) {
+    float ll = (T > 0) ? ((n > 1) ? lse2(a0[n - 1], a0[n - 2]) : a0[0]) : -INFINITY;
+    int st = bad ? 2 : ((ll == -INFINITY) ? 1 : 0);
+    loss[b] = -ll;
+    if (status) status[b] = st;
+  }
+}
+
+}  // namespace sar
+
+extern "C" int sar_ctc_fwd(const float* logits, const float* labels, const int* in_len, const int* lab_len,
+                           float* loss, float* probs, int* status, int B, int S, int C, int Lmax, void* stream) {
+  using namespace sar;
+  SAR_REQUIRE(logits && labels && in_len && lab_len && loss, SAR_ERR_BAD_ARG, "sar_ctc_fwd: null pointer");
+  SAR_REQUIRE(B > 0 && S > 0 && C > 1 && Lmax > 0, SAR_ERR_BAD_ARG, "sar_ctc_fwd: bad dimension");
+  const int NE = 2 * Lmax + 1;
+  size_t smem = sizeof(float) * ((size_t)S * NE + 2 * NE) + sizeof(int) * NE;
+  SAR_REQUIRE(smem <= 227 * 1024, SAR_ERR_UNSUPPORTED, "sar_ctc_fwd: S*(2*Lmax+1) too large for shared memory (%zu B)", smem);
+  cudaError_t e = cudaFuncSetAttribute(ctc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { set_error("sar_ctc_fwd: %s", cudaGetErrorString(e)); return (int)e; }
+  ctc_kernel<<<B, CTC_THREADS, smem, (cudaStream_t)stream>>>(logits, labels, in_len, lab_len, loss, probs, status, S, C, Lmax);
+  return check_launch("sar_ctc_fwd");
+}

@@ -1,0 +1,199 @@
+// elementwise.cu -- HBM-bound helper kernels: max-pool, BN-affine+ReLU, LayerNorm,
+// global average pool, batch loss reduction.  All fp32, vectorised where shapes allow.
+#include "common.cuh"
+
+namespace sar {
+
+// MaxPooling2D 'same' (resnet.py:174,192): one thread per (pixel, 4 channels)
+__global__ void maxpool_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int H, int W, int C,
+                               int Ho, int Wo, int k, int stride, int pad_t, int pad_l) {
+  const int C4 = C >> 2;
+  long long total = (long long)B * Ho * Wo * C4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c4 = (int)(i % C4);
+    long long pix = i / C4;
+    int wo = (int)(pix % Wo);
+    long long r = pix / Wo;
+    int ho = (int)(r % Ho);
+    int n = (int)(r / Ho);
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int dh = 0; dh < k; ++dh) {
+      int hi = ho * stride - pad_t + dh;
+      if (hi < 0 || hi >= H) continue;
+      for (int dw = 0; dw < k; ++dw) {
+        int wi = wo * stride - pad_l + dw;
+        if (wi < 0 || wi >= W) continue;
+        float4 v = __ldg(reinterpret_cast<const float4*>(x + (((size_t)n * H + hi) * W + wi) * C) + c4);
+        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+      }
+    }
+    reinterpret_cast<float4*>(out + (size_t)pix * C)[c4] = m;
+  }
+}
+
+__global__ void affine_relu_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                                   const float* __restrict__ shift, float* __restrict__ out,
+                                   long long rows, int C, int relu) {
+  const int C4 = C >> 2;
+  long long total = rows * C4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c4 = (int)(i % C4);
+    float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    float4 s = __ldg(reinterpret_cast<const float4*>(scale) + c4);
+    float4 b = __ldg(reinterpret_cast<const float4*>(shift) + c4);
+    v.x = fmaf(v.x, s.x, b.x); v.y = fmaf(v.y, s.y, b.y); v.z = fmaf(v.z, s.z, b.z); v.w = fmaf(v.w, s.w, b.w);
+    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    reinterpret_cast<float4*>(out)[i] = v;
+  }
+}
+
+// LayerNormalization (model.py:32-33): one warp per row, values held in registers,
+// two-pass mean / biased variance in fp32 (eps = 1e-14 amplifies a sloppy variance).
+template <int MAXV>   // MAXV float4 per lane => C <= 128*MAXV
+__global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, float* __restrict__ out,
+                                 long long rows, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int C4 = C >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * C);
+  float4 v[MAXV];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int c4 = lane + 32 * i;
+    if (c4 < C4) {
+      v[i] = __ldg(xr + c4);
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mean = warp_sum(sum) / (float)C;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int c4 = lane + 32 * i;
+    if (c4 < C4) {
+      float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      sq += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float var = warp_sum(sq) / (float)C;
+  const float rstd = 1.0f / sqrtf(var + eps);
+  float4* orow = reinterpret_cast<float4*>(out + row * C);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int c4 = lane + 32 * i;
+    if (c4 < C4) {
+      float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+      float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * g.x + b.x;
+      o.y = (v[i].y - mean) * rstd * g.y + b.y;
+      o.z = (v[i].z - mean) * rstd * g.z + b.z;
+      o.w = (v[i].w - mean) * rstd * g.w + b.w;
+      orow[c4] = o;
+    }
+  }
+}
+
+// GlobalAveragePooling1D (model.py:125): block per utterance, thread per feature
+__global__ void avgpool_kernel(const float* __restrict__ x, float* __restrict__ out, int S, int D) {
+  const int b = blockIdx.x;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float acc = 0.f;
+    for (int s = 0; s < S; ++s) acc += __ldg(x + ((size_t)b * S + s) * D + d);
+    out[(size_t)b * D + d] = acc / (float)S;
+  }
+}
+
+// one block, fixed reduction order => bitwise reproducible sums for a given B
+__global__ void loss_reduce_kernel(const float* __restrict__ stats, const float* __restrict__ ctc,
+                                   const float* __restrict__ bn, float* __restrict__ out8, int B) {
+  __shared__ float scratch[32];
+  float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    if (stats) { a[0] += stats[4 * b]; a[1] += stats[4 * b + 1]; a[4] += stats[4 * b + 2]; a[5] += stats[4 * b + 3]; }
+    if (ctc) a[2] += ctc[b];
+    if (bn) { a[3] += bn[4 * b + 1]; a[7] += bn[4 * b + 3]; }
+    a[6] += 1.f;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float r = block_sum(a[i], scratch);
+    if (threadIdx.x == 0) out8[i] = r;
+  }
+}
+
+static inline unsigned grid_for(long long total, int threads) {
+  long long g = (total + threads - 1) / threads;
+  long long cap = 148ll * 16;
+  return (unsigned)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+}  // namespace sar
+
+extern "C" {
+
+int sar_maxpool2d_fwd(const float* x, float* out, int B, int H, int W, int C, int Ho, int Wo,
+                      int k, int stride, int pad_t, int pad_l, void* stream) {
+  using namespace sar;
+  SAR_REQUIRE(x && out, SAR_ERR_BAD_ARG, "sar_maxpool2d_fwd: null pointer");
+  SAR_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && Ho > 0 && Wo > 0 && k > 0 && stride > 0, SAR_ERR_BAD_ARG,
+              "sar_maxpool2d_fwd: non-positive dimension");
+  SAR_REQUIRE(C % 4 == 0, SAR_ERR_UNSUPPORTED, "sar_maxpool2d_fwd: C must be a multiple of 4");
+  SAR_REQUIRE(aligned16(x) && aligned16(out), SAR_ERR_ALIGN, "sar_maxpool2d_fwd: unaligned pointer");
+  long long total = (long long)B * Ho * Wo * (C / 4);
+  maxpool_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, out, B, H, W, C, Ho, Wo, k, stride, pad_t, pad_l);
+  return check_launch("sar_maxpool2d_fwd");
+}
+
+int sar_affine_relu_fwd(const float* x, const float* scale, const float* shift, float* out,
+                        long long rows, int C, int relu, void* stream) {
+  using namespace sar;
+  SAR_REQUIRE(x && scale && shift && out, SAR_ERR_BAD_ARG, "sar_affine_relu_fwd: null pointer");
+  SAR_REQUIRE(rows > 0 && C > 0, SAR_ERR_BAD_ARG, "sar_affine_relu_fwd: non-positive dimension");
+  SAR_REQUIRE(C % 4 == 0, SAR_ERR_UNSUPPORTED, "sar_affine_relu_fwd: C must be a multiple of 4");
+  SAR_REQUIRE(aligned16(x) && aligned16(out) && aligned16(scale) && aligned16(shift), SAR_ERR_ALIGN,
+              "sar_affine_relu_fwd: unaligned pointer");
+  affine_relu_kernel<<<grid_for(rows * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(x, scale, shift, out, rows, C, relu);
+  return check_launch("sar_affine_relu_fwd");
+}
+
+int sar_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* out,
+                      long long rows, int C, float eps, void* stream) {
+  using namespace sar;
+  SAR_REQUIRE(x && gamma && beta && out, SAR_ERR_BAD_ARG, "sar_layernorm_fwd: null pointer");
+  SAR_REQUIRE(rows > 0 && C > 0, SAR_ERR_BAD_ARG, "sar_layernorm_fwd: non-positive dimension");
+  SAR_REQUIRE(C % 4 == 0 && C <= 1024, SAR_ERR_UNSUPPORTED, "sar_layernorm_fwd: C must be a multiple of 4, <= 1024");
+  SAR_REQUIRE(aligned16(x) && aligned16(out) && aligned16(gamma) && aligned16(beta), SAR_ERR_ALIGN,
+              "sar_layernorm_fwd: unaligned pointer");
+  const int warps = 8;
+  unsigned grid = (unsigned)((rows + warps - 1) / warps);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C <= 256) layernorm_kernel<2><<<grid, warps * 32, 0, st>>>(x, gamma, beta, out, rows, C, eps);
+  else if (C <= 512) layernorm_kernel<4><<<grid, warps * 32, 0, st>>>(x, gamma, beta, out, rows, C, eps);
+  else layernorm_kernel<8><<<grid, warps * 32, 0, st>>>(x, gamma, beta, out, rows, C, eps);
+  return check_launch("sar_layernorm_fwd");
+}
+
+int sar_avgpool_fwd(const float* x, float* out, int B, int S, int D, void* stream) {
+  using namespace sar;
+  SAR_REQUIRE(x && out, SAR_ERR_BAD_ARG, "sar_avgpool_fwd: null pointer");
+  SAR_REQUIRE(B > 0 && S > 0 && D > 0, SAR_ERR_BAD_ARG, "sar_avgpool_fwd: non-positive dimension");
+  avgpool_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(x, out, S, D);
+  return check_launch("sar_avgpool_fwd");
+}
+
+int sar_loss_reduce_fwd(const float* sample_stats, const float* ctc_loss, const float* bn_stats,
+                        float* out8, int B, void* stream) {
+  using namespace sar;
+  SAR_REQUIRE(out8, SAR_ERR_BAD_ARG, "sar_loss_reduce_fwd: null out8");
+  SAR_REQUIRE(B > 0, SAR_ERR_BAD_ARG, "sar_loss_reduce_fwd: B must be positive");
+  loss_reduce_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(sample_stats, ctc_loss, bn_stats, out8, B);
+  return check_launch("sar_loss_reduce_fwd");
+}
+
+}  // extern "C"

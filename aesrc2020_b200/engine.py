@@ -1,0 +1,232 @@
+"""Device-side execution plan of the SAR-Net forward (model.predict, model.py:229-339).
+
+`SARNetEngine` owns the device copies of the weights in kernel-native form (inference BN
+folded to per-channel affines, GRU kernels of both directions concatenated, AR_BN1/AR_BN2
+folded into AR_EMBEDDING) and launches the C-ABI kernels in order on the current stream.
+No PyTorch math is on the path: torch only allocates buffers.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import ops
+from .config import SARConfig, ResNetPlan
+
+BN_EPS = 1e-3      # Keras BatchNormalization default epsilon (resnet.py:25, model.py:29-30)
+
+
+def fold_bn(w: Dict[str, np.ndarray], name: str):
+    """Inference BN -> (scale, shift) in float64."""
+    g = w[name + "/gamma"].astype(np.float64)
+    b = w[name + "/beta"].astype(np.float64)
+    m = w[name + "/moving_mean"].astype(np.float64)
+    v = w[name + "/moving_variance"].astype(np.float64)
+    scale = g / np.sqrt(v + BN_EPS)
+    return scale, b - m * scale
+
+
+class ResNetDevice:
+    """ResNet-18/34 front-end (resnet.py:170-201) on device buffers."""
+
+    def __init__(self, plan: ResNetPlan, weights: Dict[str, np.ndarray], device):
+        self.plan = plan
+        self.device = device
+        self.p: Dict[str, torch.Tensor] = {}
+
+        def put(name, arr):
+            self.p[name] = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32)).to(device)
+
+        for c in plan.convs():
+            put(c.name + "/kernel", weights[c.name + "/kernel"])
+            put(c.name + "/bias", weights[c.name + "/bias"])
+        bns = [plan.stem.post_bn, plan.final_bn]
+        for b in plan.blocks:
+            bns += [x for x in (b.conv1.pre_bn, b.conv2.pre_bn) if x]
+        for name in bns:
+            s, t = fold_bn(weights, name)
+            put(name + "/scale", s)
+            put(name + "/shift", t)
+
+    def bn(self, name):
+        return (self.p[name + "/scale"], self.p[name + "/shift"]) if name else None
+
+    def conv(self, x, c, residual=None, act=None):
+        return ops.conv2d(x, self.p[c.name + "/kernel"], self.p[c.name + "/bias"], stride=c.stride,
+                          pad_t=c.pad_t, pad_l=c.pad_l, out_hw=(c.hout, c.wout), pre=self.bn(c.pre_bn),
+                          post=self.bn(c.post_bn), residual=residual, act=act)
+
+    def forward_raw(self, x: torch.Tensor) -> torch.Tensor:
+        """x (B,T,80,1) -> the residual stream BEFORE the final BN->ReLU (B,H',W',C)."""
+        pl = self.plan
+        a = self.conv(x, pl.stem, act="relu")                                   # resnet.py:173/191
+        a = ops.maxpool2d(a, k=3, stride=2, pad_t=pl.pool_pad_t, pad_l=pl.pool_pad_l,
+                          out_hw=(pl.pool_hout, pl.pool_wout))                  # resnet.py:174/192
+        for b in pl.blocks:                                                     # resnet.py:105-125
+            c1 = self.conv(a, b.conv1)
+            sc = self.conv(a, b.short) if b.short else a                       # resnet.py:67-89
+            a = self.conv(c1, b.conv2, residual=sc)
+        return a
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        a = self.forward_raw(x)
+        s, t = self.bn(self.plan.final_bn)
+        return ops.affine_relu(a, s, t, relu=True)                             # resnet.py:178/196
+
+
+class SARNetEngine:
+    def __init__(self, cfg: SARConfig, weights: Dict[str, np.ndarray], device="cuda"):
+        if cfg.ar_enable and cfg.mto not in ("avg", "bigru", "vlad", "gvlad"):
+            raise ValueError("Please specify avg/bigru/vlad/gvlad ..")          # model.py:136-138
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.plan = cfg.plan()
+        self.resnet = ResNetDevice(self.plan, weights, self.device)
+        self.p: Dict[str, torch.Tensor] = {}
+        self._prepare(weights)
+
+    # ------------------------------------------------------------------ weight preparation
+    def _put(self, name, arr):
+        self.p[name] = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32)).to(self.device)
+
+    def _dense(self, w, name, bias=True):
+        self._put(name + "/kernel", w[name + "/kernel"])
+        if bias:
+            self._put(name + "/bias", w[name + "/bias"])
+
+    def _ln(self, w, name):
+        self._put(name + "/gamma", w[name + "/gamma"])
+        self._put(name + "/beta", w[name + "/beta"])
+
+    def _bigru(self, w, name):
+        u = w[name + "/forward/recurrent_kernel"].shape[0]
+        kf, kb = w[name + "/forward/kernel"], w[name + "/backward/kernel"]
+        bf, bb = w[name + "/forward/bias"], w[name + "/backward/bias"]
+        self._put(name + "/kernel_cat", np.concatenate([kf, kb], axis=1))                 # (Din, 6u)
+        self._put(name + "/ibias_cat", np.concatenate([bf[:3 * u], bb[:3 * u]]))          # (6u,)
+        self._put(name + "/rec", np.stack([w[name + "/forward/recurrent_kernel"],
+                                           w[name + "/backward/recurrent_kernel"]]))      # (2,u,3u)
+        self._put(name + "/rbias", np.stack([bf[3 * u:], bb[3 * u:]]))                    # (2,3u)
+
+    def _prepare(self, w):
+        cfg = self.cfg
+        self._dense(w, "CNN_LIN"); self._ln(w, "CNN_LIN_LN")
+        self._bigru(w, "CRNN"); self._ln(w, "CRNN_LN")
+        if cfg.ctc_enable:
+            self._bigru(w, "CTC_BIGRU"); self._ln(w, "CTC_BIGRU_LN")
+            self._dense(w, "CTC_DS"); self._ln(w, "CTC_DS_LN")
+            self._dense(w, "ctc_pred")
+        if cfg.ar_enable:
+            self._dense(w, "AR_DS"); self._ln(w, "AR_DS_LN")
+            if cfg.mto == "bigru":
+                self._bigru(w, "AR_MERGE")
+            elif cfg.mto in ("vlad", "gvlad"):
+                pre = cfg.mto
+                k = w[pre + "_center_assignment/kernel"]
+                self._put(pre + "/w_assign", k.reshape(k.shape[2], k.shape[3]))
+                self._put(pre + "/b_assign", w[pre + "_center_assignment/bias"])
+                self._put(pre + "/centers", w[pre + "_pool/centers"])
+            # AR_BN1 -> AR_EMBEDDING -> AR_BN2 folded into one affine map (float64 on the host)
+            s1, t1 = fold_bn(w, "AR_BN1")
+            s2, t2 = fold_bn(w, "AR_BN2")
+            W = w["AR_EMBEDDING/kernel"].astype(np.float64)
+            b = w["AR_EMBEDDING/bias"].astype(np.float64)
+            self._put("AR_EMBEDDING/kernel_folded", (s1[:, None] * W) * s2[None, :])
+            self._put("AR_EMBEDDING/bias_folded", (t1 @ W + b) * s2 + t2)
+            for n in ("AR_CF_DS1", "AR_CF_DS2", "y_accent"):
+                self._dense(w, n)
+            if cfg.disc_enable:
+                key = "y_disc/W" if cfg.metric_loss in ("sphereface", "cosface", "arcface") else "y_disc/kernel"
+                self._put("y_disc/w", w[key])
+            if cfg.disc_enable and cfg.bn_dim:
+                self._dense(w, "AR_BN_DS")
+                s3, t3 = fold_bn(w, "AR_BN3")
+                s4, t4 = fold_bn(w, "AR_BN4")
+                Wb = w["bottleneck/kernel"].astype(np.float64)
+                bb = w["bottleneck/bias"].astype(np.float64)
+                self._put("bottleneck/kernel_folded", (s3[:, None] * Wb) * s4[None, :])
+                self._put("bottleneck/bias_folded", (t3 @ Wb + bb) * s4 + t4)
+                key = "y_disc_bn/W" if cfg.metric_loss in ("sphereface", "cosface", "arcface") else "y_disc_bn/kernel"
+                self._put("y_disc_bn/w", w[key])
+
+    # ------------------------------------------------------------------ building blocks
+    def dense_ln(self, x, name, ln_name, act="tanh", pre=None):
+        p = self.p
+        y = ops.dense(x, p[name + "/kernel"], p[name + "/bias"], act=act, pre=pre)
+        return ops.layernorm(y, p[ln_name + "/gamma"], p[ln_name + "/beta"])
+
+    def bigru(self, x, name, seq=True):
+        p = self.p
+        B, S, _ = x.shape
+        xp = ops.dense(x, p[name + "/kernel_cat"], p[name + "/ibias_cat"])       # (B,S,6u) = (B,S,2,3u)
+        return ops.bigru(xp.reshape(B, S, 2, -1), p[name + "/rec"], p[name + "/rbias"], seq=seq)
+
+    def embed(self, x):
+        p = self.p
+        W, b = p["AR_EMBEDDING/kernel_folded"], p["AR_EMBEDDING/bias_folded"]
+        if W.shape[0] >= 2048:
+            return ops.gemm_splitk(x, W, b)
+        return ops.dense(x, W, b)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, inputs: Dict[str, torch.Tensor], want_intermediates: bool = False) -> Dict[str, torch.Tensor]:
+        cfg, p = self.cfg, self.p
+        x = inputs["x_data"]
+        if x.dim() == 3:
+            x = x.unsqueeze(-1)
+        B = x.shape[0]
+        out: Dict[str, torch.Tensor] = {}
+        raw = self.resnet.forward_raw(x)
+        S, Cc = self.plan.seq_len, self.plan.cout
+        seq = raw.reshape(B, S, Cc)                                             # CNN2SEQ, model.py:252
+        # final ResNet BN->ReLU (resnet.py:178/196) fused as the input op of CNN_LIN
+        cnn = self.dense_ln(seq, "CNN_LIN", "CNN_LIN_LN", pre=self.resnet.bn(self.plan.final_bn))
+        crnn = ops.layernorm(self.bigru(cnn, "CRNN"), p["CRNN_LN/gamma"], p["CRNN_LN/beta"])
+        if want_intermediates:
+            out["resnet_raw"], out["cnn_lin"], out["crnn"] = raw, cnn, crnn
+        stats = None
+        ctc_loss = None
+        bn_stats = None
+        if cfg.ctc_enable:                                                      # model.py:261-269
+            asr = ops.layernorm(self.bigru(crnn, "CTC_BIGRU"), p["CTC_BIGRU_LN/gamma"], p["CTC_BIGRU_LN/beta"])
+            asr = self.dense_ln(asr, "CTC_DS", "CTC_DS_LN")
+            logits = ops.dense(asr, p["ctc_pred/kernel"], p["ctc_pred/bias"])
+            ctc_loss, status, probs = ops.ctc(logits, inputs["x_ctc_label"], inputs["x_ctc_in_len"],
+                                              inputs["x_ctc_out_len"], want_probs=want_intermediates)
+            out["y_ctc_loss"] = ctc_loss.reshape(B, 1)
+            out["ctc_status"] = status
+            if want_intermediates:
+                out["ctc_pred"] = probs
+        if cfg.ar_enable:                                                       # model.py:275-322
+            ar = self.dense_ln(crnn, "AR_DS", "AR_DS_LN")
+            if cfg.mto == "avg":
+                integ = ops.avgpool(ar)
+            elif cfg.mto == "bigru":
+                integ = self.bigru(ar, "AR_MERGE", seq=False)
+            else:
+                G = cfg.ghost_clusters if cfg.mto == "gvlad" else 0
+                integ = ops.vlad(ar, p[cfg.mto + "/w_assign"], p[cfg.mto + "/b_assign"], p[cfg.mto + "/centers"],
+                                 cfg.vlad_clusters, G)
+            emb = self.embed(integ)
+            if want_intermediates:
+                out["ar_ds"], out["integration"] = ar, integ
+            out["embedding"] = emb
+            onehot = inputs.get("x_accent") if cfg.disc_enable else inputs.get("y_true")
+            cls = tuple(p[k] for k in ("AR_CF_DS1/kernel", "AR_CF_DS1/bias", "AR_CF_DS2/kernel", "AR_CF_DS2/bias",
+                                       "y_accent/kernel", "y_accent/bias"))
+            h = ops.head(emb, cls, wd=p.get("y_disc/w") if cfg.disc_enable else None, onehot=onehot,
+                         n_classes=cfg.accent_classes, head_kind=cfg.metric_loss if cfg.disc_enable else None,
+                         margin=cfg.margin)
+            stats = h.pop("sample_stats")
+            out.update(h)
+            if cfg.disc_enable and cfg.bn_dim:
+                bn = ops.dense(emb, p["AR_BN_DS/kernel"], p["AR_BN_DS/bias"], act="relu")
+                bn = ops.dense(bn, p["bottleneck/kernel_folded"], p["bottleneck/bias_folded"])
+                hb = ops.head(None, None, emb_d=bn, wd=p["y_disc_bn/w"], onehot=onehot, n_classes=cfg.accent_classes,
+                              head_kind=cfg.metric_loss, margin=cfg.margin)
+                bn_stats = hb["sample_stats"]
+                out["y_disc_bn"] = hb["y_disc"]
+        out["loss_vector"] = ops.loss_reduce(stats, ctc_loss, bn_stats, B=B)
+        return out

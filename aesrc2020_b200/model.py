@@ -1,0 +1,478 @@
+"""Mirror of the reference's model.py call surface, executing on B200 through the C ABI.
+
+Kept verbatim from the reference: `SAR_Net(...)` keyword set and `(model, train_model)`
+return (model.py:204-224,371); the returned model's `predict / get_layer / load_weights /
+save_weights / summary`; helper names `build, compile, integration, vlad, disc_loss,
+ctc_module, ctc_lambda_func, sub_model, ctc_pred` and the layer factories `SQUEEZE, EXPAND,
+BN, LN, DS, BIGRU, DP` (model.py:23-53).  Forward-only: `lr` is accepted and ignored, and
+`compile` wires the data-parallel wrapper instead of an optimiser.
+
+Tensors at this surface: numpy arrays (host, as in Keras) or CUDA torch tensors.  predict()
+with host arrays does the H2D copy from pinned memory, runs the kernels, and copies the
+outputs back; with device tensors it is zero-copy.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from . import ops, weights as _weights
+from . import losses as ls
+from . import VLAD as vd
+from .config import SARConfig
+from .engine import SARNetEngine, fold_bn
+from ._shim import SarnetError
+
+ArrayLike = Union[np.ndarray, torch.Tensor]
+
+
+# =========================
+#         Layers            (model.py:23-53) -- eager, device tensors in/out
+# =========================
+class _Lambda:
+    def __init__(self, fn, name=None):
+        self.fn, self.name = fn, name
+
+    def __call__(self, x):
+        return self.fn(x)
+
+
+def SQUEEZE(axis=3, name=None):
+    return _Lambda(lambda x: x.squeeze(axis), name=name)
+
+
+def EXPAND(axis=3, name=None):
+    return _Lambda(lambda x: x.unsqueeze(axis), name=name)
+
+
+def DP(rate, name=None):
+    return _Lambda(lambda x: x, name=name)          # Dropout is the identity at inference
+
+
+class _Layer:
+    def __init__(self, name=None):
+        self.name = name
+        self.weights: Dict[str, np.ndarray] = {}
+        self._dev: Dict[str, torch.Tensor] = {}
+
+    def set_weights_dict(self, w: Dict[str, np.ndarray]):
+        self.weights = {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in w.items()}
+        self._dev = {}
+
+    def get_weights(self):
+        return list(self.weights.values())
+
+    def d(self, key, device, value=None):
+        if key not in self._dev or self._dev[key].device != device:
+            src = self.weights[key] if value is None else value
+            self._dev[key] = torch.from_numpy(np.ascontiguousarray(src, dtype=np.float32)).to(device)
+        return self._dev[key]
+
+
+class _BN(_Layer):
+    def __call__(self, x):
+        if not self.weights:
+            c = x.shape[-1]
+            self.set_weights_dict({"gamma": np.ones(c), "beta": np.zeros(c), "moving_mean": np.zeros(c),
+                                   "moving_variance": np.ones(c)})
+        s, t = fold_bn({"bn/" + k: v for k, v in self.weights.items()}, "bn")
+        return ops.affine_relu(x.contiguous(), self.d("s", x.device, s), self.d("t", x.device, t), relu=False)
+
+
+def BN(name=None):
+    return _BN(name)
+
+
+class _LN(_Layer):
+    def __call__(self, x):
+        if not self.weights:
+            c = x.shape[-1]
+            self.set_weights_dict({"gamma": np.ones(c), "beta": np.zeros(c)})
+        return ops.layernorm(x.contiguous(), self.d("gamma", x.device), self.d("beta", x.device))
+
+
+def LN(name=None):
+    return _LN(name)
+
+
+class _DS(_Layer):
+    def __init__(self, hidden, activation, use_bias=True, name=None):
+        super().__init__(name)
+        self.hidden, self.activation, self.use_bias = hidden, activation, use_bias
+
+    def __call__(self, x):
+        if not self.weights:
+            din = x.shape[-1]
+            rng = np.random.RandomState(1234)
+            w = {"kernel": rng.randn(din, self.hidden) * np.sqrt(2.0 / din)}
+            if self.use_bias:
+                w["bias"] = np.zeros(self.hidden)
+            self.set_weights_dict(w)
+        act = self.activation if self.activation in ("relu", "tanh") else None
+        y = ops.dense(x.contiguous(), self.d("kernel", x.device),
+                      self.d("bias", x.device) if self.use_bias else None, act=act)
+        if self.activation == "softmax":
+            n = y.shape[-1]
+            eye = torch.eye(n, device=y.device)
+            y = ops.head(None, None, emb_d=y.reshape(-1, n).contiguous(), wd=eye, n_classes=n,
+                         head_kind="softmax")["y_disc"].reshape(y.shape)
+        return y
+
+
+def DS(hidden, activation, rgr=None, use_bias=True, name=None):
+    return _DS(hidden, activation, use_bias=use_bias, name=name)
+
+
+class _BIGRU(_Layer):
+    def __init__(self, hidden, seq=True, name=None):
+        super().__init__(name)
+        self.hidden, self.seq = hidden, seq
+
+    def __call__(self, x):
+        u = self.hidden
+        if not self.weights:
+            din = x.shape[-1]
+            rng = np.random.RandomState(1234)
+            w = {}
+            for d in ("forward", "backward"):
+                lim = np.sqrt(6.0 / (din + 3 * u))
+                w[d + "/kernel"] = rng.uniform(-lim, lim, (din, 3 * u))
+                w[d + "/recurrent_kernel"] = rng.randn(u, 3 * u) / np.sqrt(u)
+                w[d + "/bias"] = np.zeros(6 * u)
+            self.set_weights_dict(w)
+        w = self.weights
+        kcat = np.concatenate([w["forward/kernel"], w["backward/kernel"]], axis=1)
+        bcat = np.concatenate([w["forward/bias"][:3 * u], w["backward/bias"][:3 * u]])
+        rec = np.stack([w["forward/recurrent_kernel"], w["backward/recurrent_kernel"]])
+        rb = np.stack([w["forward/bias"][3 * u:], w["backward/bias"][3 * u:]])
+        B, S, _ = x.shape
+        xp = ops.dense(x.contiguous(), self.d("kcat", x.device, kcat), self.d("bcat", x.device, bcat))
+        return ops.bigru(xp.reshape(B, S, 2, 3 * u), self.d("rec", x.device, rec), self.d("rb", x.device, rb),
+                         seq=self.seq)
+
+
+def BIGRU(hidden, seq=True, rgr=None, name=None):
+    return _BIGRU(hidden, seq=seq, name=name)
+
+
+# =========================
+#     ctc constructors      (model.py:62-73)
+# =========================
+def ctc_lambda_func(args):
+    """K.ctc_batch_cost(labels, y_pred, input_length, label_length) on device.  `y_pred` are the
+    ctc_pred softmax PROBABILITIES as in the reference; the kernel takes logits, and
+    softmax(log p) == p, so log-probabilities are passed (zeros map to -inf safely)."""
+    y_pred, labels, input_length, label_length = args
+    loss, status, _ = ops.ctc(torch.log(y_pred).contiguous(), labels, input_length, label_length)
+    if bool((status == 1).any()):
+        raise SarnetError("Not enough time for target transition sequence (infeasible CTC label)")
+    return loss.reshape(-1, 1)
+
+
+def ctc_module(ctc_pred, max_label_len):
+    raise SarnetError("ctc_module builds Keras Input placeholders (model.py:66-73); the device path takes the "
+                      "x_ctc_label/x_ctc_in_len/x_ctc_out_len tensors through SAR_Net(...).predict")
+
+
+# =========================
+#          NetVLAD          (model.py:82-109)
+# =========================
+def vlad(x, aggregation, vlad_clusters, ghost_clusters, weights: Optional[Dict[str, np.ndarray]] = None):
+    """x (B,1,S,D) -> (B, K*D): fused 1x1 assignment conv + VladPooling (one launch)."""
+    if aggregation not in ("vlad", "gvlad"):
+        return x
+    G = ghost_clusters if aggregation == "gvlad" else 0
+    D = x.shape[-1]
+    kg = vlad_clusters + G
+    if weights is None:
+        rng = np.random.RandomState(1234)
+        weights = {aggregation + "_center_assignment/kernel": rng.randn(1, 1, D, kg) / np.sqrt(D),
+                   aggregation + "_center_assignment/bias": np.zeros(kg),
+                   aggregation + "_pool/centers": rng.randn(kg, D) / np.sqrt(D)}
+    dev = x.device
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+    return ops.vlad(x.reshape(x.shape[0], -1, D).contiguous(),
+                    t(weights[aggregation + "_center_assignment/kernel"].reshape(D, kg)),
+                    t(weights[aggregation + "_center_assignment/bias"]),
+                    t(weights[aggregation + "_pool/centers"]), vlad_clusters, G)
+
+
+# =========================
+#         AR Module         (model.py:118-167)
+# =========================
+def integration(x, hidden_dim=256, mto="avg", vlad_clusters=8, ghost_clusters=2, weights=None):
+    if mto == "avg":
+        return ops.avgpool(x.contiguous())
+    if mto == "bigru":
+        layer = BIGRU(hidden_dim, seq=False, name="AR_MERGE")
+        if weights:
+            layer.set_weights_dict({k[len("AR_MERGE/"):]: v for k, v in weights.items() if k.startswith("AR_MERGE/")})
+        return layer(x)
+    if mto in ("vlad", "gvlad"):
+        return vlad(EXPAND(axis=1)(x), aggregation=mto, vlad_clusters=vlad_clusters, ghost_clusters=ghost_clusters,
+                    weights=weights)
+    print("Please specify avg/bigru/vlad/gvlad ..")
+    raise SystemExit(1)
+
+
+def disc_loss(x, accent_label, accent_classes, loss, margin, name, W: Optional[np.ndarray] = None):
+    """model.py:142-167 on device tensors; returns the layer output (probabilities, or raw
+    cosines for 'circleloss'), or None for an unknown loss (as the reference does)."""
+    if loss not in ops.HEAD or loss in (None, "none", "circle_raw"):
+        return None
+    if W is None:
+        lim = np.sqrt(6.0 / (x.shape[1] + accent_classes))
+        W = np.random.RandomState(1234).uniform(-lim, lim, (x.shape[1], accent_classes))
+    wd = torch.from_numpy(np.ascontiguousarray(W, dtype=np.float32)).to(x.device)
+    y = None if accent_label is None else accent_label.contiguous().float()
+    return ops.head(None, None, emb_d=x.contiguous(), wd=wd, onehot=y, n_classes=accent_classes,
+                    head_kind=loss, margin=margin)["y_disc"]
+
+
+# =========================
+#           Model           (model.py:175-371)
+# =========================
+class LayerView:
+    """What `model.get_layer(name)` returns: named access to one layer's weights."""
+
+    def __init__(self, model: "SARModel", name: str):
+        self.model, self.name = model, name
+        keys = [k for k in model.weights if k == name or k.startswith(name + "/")]
+        if not keys and name not in model.config.input_names() + model.config.output_names():
+            raise ValueError("No such layer: " + name)
+        self.keys = keys
+
+    def get_weights(self):
+        return [self.model.weights[k] for k in self.keys]
+
+    def set_weights(self, ws):
+        for k, v in zip(self.keys, ws):
+            if tuple(v.shape) != tuple(self.model.weights[k].shape):
+                raise ValueError("shape mismatch for %s" % k)
+            self.model.weights[k] = np.ascontiguousarray(v, dtype=np.float32)
+        self.model._engine = None
+
+
+class SARModel:
+    """The object SAR_Net returns (stands in for keras.models.Model on this path)."""
+
+    def __init__(self, config: SARConfig, weights: Dict[str, np.ndarray], name=None, device="cuda",
+                 outputs: Optional[List[str]] = None, gpus: int = 1):
+        self.config, self.weights, self.name = config, weights, name or "model"
+        self.device = device
+        self.gpus = gpus
+        self._outputs = outputs or config.output_names()
+        self._engine: Optional[SARNetEngine] = None
+        self._pinned: Dict[str, torch.Tensor] = {}
+
+    # -- Keras-like surface
+    @property
+    def input_names(self):
+        return self.config.input_names()
+
+    @property
+    def output_names(self):
+        return list(self._outputs)
+
+    def engine(self) -> SARNetEngine:
+        if self._engine is None:
+            self._engine = SARNetEngine(self.config, self.weights, self.device)
+        return self._engine
+
+    def summary(self, print_fn=print):
+        tot = 0
+        print_fn('Model: "%s"' % self.name)
+        for k, v in self.weights.items():
+            print_fn("%-48s %-22s %10d" % (k, tuple(v.shape), v.size))
+            tot += v.size
+        print_fn("Total params: %d" % tot)
+
+    def get_layer(self, name):
+        return LayerView(self, name)
+
+    def save_weights(self, path):
+        _weights.save_weights(path, self.weights)
+
+    def load_weights(self, path, by_name=True, skip_mismatch=True):
+        """model.py:181-183 semantics: load by name, silently skip shape mismatches."""
+        loaded = _weights.load_weights(path)
+        for k, v in loaded.items():
+            if k in self.weights and tuple(self.weights[k].shape) == tuple(v.shape):
+                self.weights[k] = np.ascontiguousarray(v, dtype=np.float32)
+            elif k in self.weights and not skip_mismatch:
+                raise ValueError("shape mismatch for %s" % k)
+        self._engine = None
+
+    # -- execution
+    def _to_device(self, key: str, v: ArrayLike) -> torch.Tensor:
+        if isinstance(v, torch.Tensor):
+            t = v.to(self.device, non_blocking=True)
+        else:
+            a = np.ascontiguousarray(v)
+            if key in ("x_ctc_in_len", "x_ctc_out_len"):
+                a = a.astype(np.int32, copy=False)
+            else:
+                a = a.astype(np.float32, copy=False)
+            pin = self._pinned.get(key)
+            if pin is None or pin.shape != a.shape or pin.dtype != torch.from_numpy(a).dtype:
+                pin = torch.empty(a.shape, dtype=torch.from_numpy(a).dtype, pin_memory=True)
+                self._pinned[key] = pin
+            pin.copy_(torch.from_numpy(a))
+            t = pin.to(self.device, non_blocking=True)
+        if key in ("x_ctc_in_len", "x_ctc_out_len"):
+            return t.to(torch.int32)
+        return t.float() if t.dtype != torch.float32 else t
+
+    def _as_dict(self, x) -> Dict[str, ArrayLike]:
+        if isinstance(x, dict):
+            return x
+        if isinstance(x, (list, tuple)):
+            return dict(zip(self.config.input_names(), x))
+        return {"x_data": x}
+
+    def forward_device(self, x, want_intermediates=False) -> Dict[str, torch.Tensor]:
+        xd = self._as_dict(x)
+        missing = [k for k in self.config.input_names() if k not in xd]
+        if missing:
+            raise ValueError("missing model inputs: %s" % missing)
+        dev_in = {k: self._to_device(k, v) for k, v in xd.items()}
+        out = self.engine().forward(dev_in, want_intermediates=want_intermediates)
+        if self.config.ctc_enable and bool((out["ctc_status"] != 0).any()):
+            # tf.nn.ctc_loss raises on infeasible / out-of-range labels
+            raise SarnetError("CTC: infeasible or out-of-range label sequence in batch "
+                              "(Not enough time for target transition sequence)")
+        return out
+
+    def predict(self, x, batch_size=32, verbose=0):
+        """Keras Model.predict: list of host arrays in output order (single array if one output).
+        Device-tensor inputs return device tensors (no host round trip)."""
+        xd = self._as_dict(x)
+        n = len(xd["x_data"])
+        on_device = isinstance(xd["x_data"], torch.Tensor) and xd["x_data"].is_cuda
+        chunks: List[List] = [[] for _ in self._outputs]
+        for b0 in range(0, n, batch_size):
+            sl = {k: v[b0:b0 + batch_size] for k, v in xd.items()}
+            out = self.forward_device(sl)
+            for i, name in enumerate(self._outputs):
+                chunks[i].append(out[name] if on_device else out[name].cpu().numpy())
+        cat = (lambda c: torch.cat(c, 0)) if on_device else (lambda c: np.concatenate(c, 0))
+        res = [cat(c) for c in chunks]
+        return res[0] if len(res) == 1 else res
+
+    def evaluate(self, x, y: Optional[Dict[str, ArrayLike]] = None, batch_size=32, group=None):
+        """Keras-style evaluate: batch-mean losses, accuracies and the weighted total
+        (model.py:344-367).  With torch.distributed initialised the 8-float loss vector is
+        all-reduced (SUM) across ranks -- the single collective of this path."""
+        from . import dist as _dist
+        xd = dict(self._as_dict(x))
+        if y is not None and "y_accent" in y and "x_accent" not in xd:
+            xd["y_true"] = y["y_accent"]
+        n = len(xd["x_data"])
+        total = None
+        for b0 in range(0, n, batch_size):
+            sl = {k: v[b0:b0 + batch_size] for k, v in xd.items()}
+            if "y_true" in sl:
+                sl["y_true"] = self._to_device("y_true", sl["y_true"])
+            vec = self.forward_device(sl)["loss_vector"]
+            total = vec if total is None else total + vec
+        total = _dist.all_reduce_loss_vector(total, group)
+        return _dist.loss_vector_to_metrics(total.cpu().numpy(), self.config)
+
+
+def build(inputs, outputs, raw=None, name="model"):
+    """model.py:175-184.  `inputs` = SARConfig, `outputs` = weights dict on this path."""
+    model = SARModel(inputs, outputs, name=name)
+    if raw:
+        print("===== init weights from:%s =====" % raw)
+        model.load_weights(raw, by_name=True, skip_mismatch=True)
+    return model
+
+
+def compile(model, gpus, lr=None, loss=None, loss_weights=None, metrics=None):
+    """model.py:187-201.  Forward-only: no optimiser.  gpus>1 returns the data-parallel view
+    (one process per GPU under torchrun; batch sharded by rank; loss vector all-reduced)."""
+    if gpus > 1:
+        from .dist import DataParallelModel
+        return DataParallelModel(model, gpus)
+    return model
+
+
+def SAR_Net(input_shape, ctc_enable=False, ar_enable=True, disc_enable=False, res_type="res18",
+            res_filters=64, hidden_dim=256, bn_dim=0, bpe_classes=1000, accent_classes=8, max_ctc_len=72,
+            mto=None, vlad_clusters=8, ghost_clusters=2, metric_loss="cosface", margin=0.3, raw_model=None,
+            lr=0.01, gpus=1, mode="train", name=None, weights: Optional[Dict[str, np.ndarray]] = None,
+            seed: int = 1234, device="cuda"):
+    """Signature of model.py:204-224 (+ `weights`/`seed`/`device` extensions, keyword-only in
+    practice).  Returns (model, train_model); `train_model is model` when gpus == 1."""
+    if mode != "train":
+        # model.py:229-232 builds Input([None, D, 1]) here, which _shortcut cannot handle
+        # (resnet.py:75 divides None) -- the reference cannot build this graph either.
+        raise SarnetError("mode != 'train' (variable-length Input) cannot be built by the reference either "
+                          "(resnet.py:75 on a None dimension); use fixed-T zero-padded inputs")
+    cfg = SARConfig(tuple(int(v) for v in input_shape), ctc_enable, ar_enable, disc_enable, res_type, res_filters,
+                    hidden_dim, bn_dim, bpe_classes, accent_classes, max_ctc_len, mto, vlad_clusters,
+                    ghost_clusters, metric_loss, margin)
+    if res_type not in ("res18", "res34", "res50", "res101", "res152"):
+        print("======= ERROR: please specify cnn in res-[18,34,50,101,152] ======")
+        raise ValueError(res_type)
+    cfg.plan()                                   # raises NotImplementedError for res50/101/152 (Q1)
+    if ar_enable and mto not in ("avg", "bigru", "vlad", "gvlad"):
+        print("Please specify avg/bigru/vlad/gvlad ..")      # model.py:136-138
+        raise SystemExit(1)
+    if hidden_dim != 256:
+        raise SarnetError("this build's Bi-GRU kernel supports hidden_dim=256 only")
+    w = weights if weights is not None else _weights.init_weights(cfg, seed)
+    expect = _weights.weight_shapes(cfg)
+    for k, shp in expect.items():
+        if k not in w or tuple(w[k].shape) != tuple(shp):
+            raise ValueError("weights: %s missing or wrong shape (want %s)" % (k, shp))
+    model = SARModel(cfg, {k: np.ascontiguousarray(w[k], dtype=np.float32) for k in expect}, name=name,
+                     device=device, gpus=gpus)
+    if raw_model:
+        print("===== init weights from:%s =====" % raw_model)
+        model.load_weights(raw_model, by_name=True, skip_mismatch=True)
+    train_model = compile(model, gpus, lr=lr, loss_weights=cfg.loss_weights())
+    print(cfg.loss_weights())                    # model.py:370
+    return model, train_model
+
+
+# ======================
+#         OTHER            (model.py:380-389)
+# ======================
+def sub_model(model: SARModel, input_name, output_name):
+    """Model(inputs=get_layer(input_name).input, outputs=get_layer(output_name).output)."""
+    valid = model.config.output_names() + ["embedding", "y_accent_logits", "y_disc_logits"]
+    if output_name == "AR_BN2":
+        output_name = "embedding"
+    if output_name not in valid:
+        raise ValueError("sub_model: output %s is not exposed (have %s)" % (output_name, valid))
+    sm = SARModel(model.config, model.weights, name=model.name, device=model.device, outputs=[output_name])
+    sm._engine = model._engine
+    return sm
+
+
+def ctc_pred(model: SARModel, x, batch_size, input_len):
+    """model.py:385-389: greedy CTC decode of the ctc_pred posteriors (blank = C-1, merge
+    repeats).  Inference post-processing ('next' row): argmax on device, collapse on host."""
+    outs = []
+    xd = model._as_dict(x)
+    n = len(xd["x_data"])
+    for b0 in range(0, n, batch_size):
+        sl = {k: v[b0:b0 + batch_size] for k, v in xd.items()}
+        o = model.forward_device(sl, want_intermediates=True)
+        best = o["ctc_pred"][:, :input_len].argmax(-1).cpu().numpy()
+        blank = model.config.bpe_classes - 1
+        for row in best:
+            prev, seq = -1, []
+            for v in row:
+                if v != prev and v != blank:
+                    seq.append(int(v))
+                prev = v
+            outs.append(seq)
+    L = max([len(s) for s in outs] + [1])
+    dec = -np.ones((len(outs), L), dtype=np.int64)       # K.ctc_decode pads with -1
+    for i, s in enumerate(outs):
+        dec[i, :len(s)] = s
+    return dec

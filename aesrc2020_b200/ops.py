@@ -1,0 +1,216 @@
+"""One thin Python wrapper per C-ABI entry point (include/sarnet.h).  Tensors in, tensors out;
+outputs are allocated here with torch (caller-owned device memory at the boundary)."""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _shim
+from ._shim import check, ptr, stream_ptr
+
+ACT = {None: 0, "none": 0, "linear": 0, "relu": 1, "tanh": 2}
+HEAD = {None: 0, "none": 0, "softmax": 1, "sphereface": 2, "cosface": 3, "arcface": 4, "circleloss": 5,
+        "circle_raw": 6}
+FACE_S = 30.0            # losses.py:13,59,106
+CIRCLE_GAMMA = 256.0     # model.py:355
+LN_EPS = 1e-14           # keras_layer_normalization default (K.epsilon()**2)
+
+# kernels launched through the C ABI since import (bench.py reports the delta as gpu_launches)
+LAUNCHES = {"n": 0}
+
+
+def _count(k: int = 1):
+    LAUNCHES["n"] += k
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise _shim.SarnetError("expected float32 tensor, got %s" % t.dtype)
+    return t.contiguous()
+
+
+def conv2d(x, w_hwio, bias=None, *, stride=1, pad_t=0, pad_l=0, out_hw: Tuple[int, int],
+           pre=None, post=None, residual=None, act=None, out=None):
+    """sar_conv2d_fwd.  x (B,H,W,Cin) NHWC, w (kh,kw,Cin,Cout); pre/post = (scale, shift)."""
+    x = _f32(x)
+    B, H, W, Cin = x.shape
+    kh, kw, cin2, Cout = w_hwio.shape
+    assert cin2 == Cin, (cin2, Cin)
+    Ho, Wo = out_hw
+    if out is None:
+        out = torch.empty((B, Ho, Wo, Cout), device=x.device, dtype=torch.float32)
+    ps, pt = pre if pre is not None else (None, None)
+    qs, qt = post if post is not None else (None, None)
+    check(_shim.lib().sar_conv2d_fwd(ptr(x), ptr(w_hwio), ptr(bias), ptr(ps), ptr(pt), ptr(qs), ptr(qt),
+                                     ptr(residual), ptr(out), B, H, W, Cin, Ho, Wo, Cout, kh, kw,
+                                     stride, pad_t, pad_l, ACT[act], stream_ptr()), "sar_conv2d_fwd")
+    _count(1)
+    return out
+
+
+def dense(x, kernel, bias=None, *, act=None, pre=None, post=None, out=None):
+    """Dense on the last axis as a 1x1 convolution: x (..., Din) @ kernel (Din, Dout)."""
+    x = _f32(x)
+    lead = x.shape[:-1]
+    M = 1
+    for d in lead:
+        M *= int(d)
+    Din, Dout = kernel.shape
+    y = conv2d(x.reshape(1, M, 1, Din), kernel.reshape(1, 1, Din, Dout), bias, out_hw=(M, 1),
+               pre=pre, post=post, act=act,
+               out=None if out is None else out.reshape(1, M, 1, Dout))
+    return y.reshape(*lead, Dout)
+
+
+def maxpool2d(x, *, k=3, stride=2, pad_t=0, pad_l=0, out_hw: Tuple[int, int]):
+    x = _f32(x)
+    B, H, W, Cc = x.shape
+    Ho, Wo = out_hw
+    out = torch.empty((B, Ho, Wo, Cc), device=x.device, dtype=torch.float32)
+    check(_shim.lib().sar_maxpool2d_fwd(ptr(x), ptr(out), B, H, W, Cc, Ho, Wo, k, stride, pad_t, pad_l,
+                                        stream_ptr()), "sar_maxpool2d_fwd")
+    _count(1)
+    return out
+
+
+def affine_relu(x, scale, shift, relu=True):
+    x = _f32(x)
+    Cc = x.shape[-1]
+    out = torch.empty_like(x)
+    check(_shim.lib().sar_affine_relu_fwd(ptr(x), ptr(scale), ptr(shift), ptr(out), x.numel() // Cc, Cc,
+                                          1 if relu else 0, stream_ptr()), "sar_affine_relu_fwd")
+    _count(1)
+    return out
+
+
+def layernorm(x, gamma, beta, eps: float = LN_EPS):
+    x = _f32(x)
+    Cc = x.shape[-1]
+    out = torch.empty_like(x)
+    check(_shim.lib().sar_layernorm_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(out), x.numel() // Cc, Cc,
+                                        float(eps), stream_ptr()), "sar_layernorm_fwd")
+    _count(1)
+    return out
+
+
+def bigru(xp, rec, rbias, *, seq=True):
+    """xp (B,S,2,3u) input projections; rec (2,u,3u); rbias (2,3u)."""
+    xp = _f32(xp)
+    B, S = xp.shape[0], xp.shape[1]
+    u = rec.shape[1]
+    out = torch.empty((B, S, 2 * u) if seq else (B, 2 * u), device=xp.device, dtype=torch.float32)
+    check(_shim.lib().sar_bigru_fwd(ptr(xp), ptr(rec), ptr(rbias), ptr(out), B, S, u, 1 if seq else 0,
+                                    stream_ptr()), "sar_bigru_fwd")
+    _count(1)
+    return out
+
+
+def vlad(feat, w_assign, b_assign, centers, K: int, G: int, score=None):
+    """feat (B,S,D) -> (B, K*D).  Scores from (w_assign, b_assign) or a given `score` (B,S,K+G)."""
+    feat = _f32(feat)
+    B, S, D = feat.shape
+    assert centers.shape == (K + G, D)
+    if score is None:
+        assert w_assign.shape == (D, K + G)
+    else:
+        score = _f32(score)
+        assert tuple(score.shape) == (B, S, K + G) and w_assign is None and b_assign is None
+    out = torch.empty((B, K * D), device=feat.device, dtype=torch.float32)
+    check(_shim.lib().sar_vlad_fwd(ptr(feat), ptr(w_assign), ptr(b_assign), ptr(score), ptr(centers), ptr(out),
+                                   B, S, D, K, G, stream_ptr()), "sar_vlad_fwd")
+    _count(1)
+    return out
+
+
+def avgpool(x):
+    x = _f32(x)
+    B, S, D = x.shape
+    out = torch.empty((B, D), device=x.device, dtype=torch.float32)
+    check(_shim.lib().sar_avgpool_fwd(ptr(x), ptr(out), B, S, D, stream_ptr()), "sar_avgpool_fwd")
+    _count(1)
+    return out
+
+
+def gemm_splitk(a, w, bias=None):
+    a = _f32(a)
+    M, K = a.shape
+    N = w.shape[1]
+    l = _shim.lib()
+    nbytes = l.sar_gemm_splitk_workspace_bytes(M, K, N)
+    ws = torch.empty((nbytes // 4,), device=a.device, dtype=torch.float32)
+    out = torch.empty((M, N), device=a.device, dtype=torch.float32)
+    check(l.sar_gemm_splitk_fwd(ptr(a), ptr(w), ptr(bias), ptr(out), M, K, N, ptr(ws), nbytes, stream_ptr()),
+          "sar_gemm_splitk_fwd")
+    _count(2)
+    return out
+
+
+def head(emb, cls_w=None, *, emb_d=None, wd=None, onehot=None, n_classes=8, head_kind=None,
+         margin=0.3, s=FACE_S, gamma=CIRCLE_GAMMA, want_logits=True):
+    """sar_head_fwd.  cls_w = (w1,b1,w2,b2,w3,b3) or None.  Returns a dict of tensors."""
+    B = (emb if emb is not None else emb_d).shape[0]
+    dev = (emb if emb is not None else emb_d).device
+    D = emb.shape[1] if emb is not None else 0
+    n = n_classes
+    hk = HEAD[head_kind]
+    res = {}
+    w1 = b1 = w2 = b2 = w3 = b3 = None
+    H1 = H2 = 0
+    if cls_w is not None:
+        w1, b1, w2, b2, w3, b3 = cls_w
+        H1, H2 = w1.shape[1], w2.shape[1]
+        res["y_accent"] = torch.empty((B, n), device=dev, dtype=torch.float32)
+        if want_logits:
+            res["y_accent_logits"] = torch.empty((B, n), device=dev, dtype=torch.float32)
+    if hk:
+        res["y_disc"] = torch.empty((B, n), device=dev, dtype=torch.float32)
+        if want_logits:
+            res["y_disc_logits"] = torch.empty((B, n), device=dev, dtype=torch.float32)
+    res["sample_stats"] = torch.empty((B, 4), device=dev, dtype=torch.float32)
+    check(_shim.lib().sar_head_fwd(ptr(emb), D, ptr(w1), ptr(b1), H1, ptr(w2), ptr(b2), H2, ptr(w3), ptr(b3),
+                                   ptr(emb_d), emb_d.shape[1] if emb_d is not None else 0, ptr(wd),
+                                   ptr(onehot), n, hk, float(margin), float(s), float(gamma),
+                                   ptr(res.get("y_accent")), ptr(res.get("y_accent_logits")),
+                                   ptr(res.get("y_disc")), ptr(res.get("y_disc_logits")),
+                                   ptr(res["sample_stats"]), B, stream_ptr()), "sar_head_fwd")
+    _count(1)
+    return res
+
+
+def ctc(logits, labels, in_len, lab_len, *, want_probs=False):
+    """logits (B,S,C) pre-softmax; labels (B,Lmax) float32; lens (B,) or (B,1) int32."""
+    logits = _f32(logits)
+    labels = _f32(labels)
+    B, S, Cc = logits.shape
+    in_len = in_len.reshape(-1).to(torch.int32).contiguous()
+    lab_len = lab_len.reshape(-1).to(torch.int32).contiguous()
+    loss = torch.empty((B,), device=logits.device, dtype=torch.float32)
+    status = torch.empty((B,), device=logits.device, dtype=torch.int32)
+    probs = torch.empty_like(logits) if want_probs else None
+    check(_shim.lib().sar_ctc_fwd(ptr(logits), ptr(labels), ptr(in_len), ptr(lab_len), ptr(loss), ptr(probs),
+                                  ptr(status), B, S, Cc, labels.shape[1], stream_ptr()), "sar_ctc_fwd")
+    _count(1)
+    return loss, status, probs
+
+
+def loss_reduce(sample_stats=None, ctc_loss=None, bn_stats=None, B: Optional[int] = None):
+    ref = sample_stats if sample_stats is not None else (ctc_loss if ctc_loss is not None else bn_stats)
+    B = B or ref.shape[0]
+    out8 = torch.empty((8,), device=ref.device, dtype=torch.float32)
+    check(_shim.lib().sar_loss_reduce_fwd(ptr(sample_stats), ptr(ctc_loss), ptr(bn_stats), ptr(out8), B,
+                                          stream_ptr()), "sar_loss_reduce_fwd")
+    _count(1)
+    return out8
+
+
+def fbank(wav, offsets, melfb_t, Fmax: int, T: int):
+    """wav (N,) float32 concatenated utterances, offsets (B+1,) int64 -> x_data (B,T,80)."""
+    wav = _f32(wav)
+    B = offsets.numel() - 1
+    feat = torch.empty((B, Fmax, 80), device=wav.device, dtype=torch.float32)
+    x = torch.empty((B, T, 80), device=wav.device, dtype=torch.float32)
+    check(_shim.lib().sar_fbank_fwd(ptr(wav), ptr(offsets), ptr(melfb_t), ptr(feat), ptr(x), B, Fmax, T,
+                                    stream_ptr()), "sar_fbank_fwd")
+    _count(2)
+    return x, feat

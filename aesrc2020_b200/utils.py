@@ -1,0 +1,86 @@
+"""Mirror of the parts of the reference's utils.py that sit on the hot path's boundary:
+the input dict contract (utils.py:102-116), label padding (utils.py:57-63) and the shape
+known-answer `cal_descriptors` (utils.py:156-159).  Pickle/scp file handling and the
+shuffling generator are data preparation and stay out of scope; `synthetic_batch` provides
+the seeded synthetic inputs the benchmarks and tests use instead.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+
+from .config import SARConfig
+
+UNK_ID, SOS_ID, EOS_ID = 0, 1, 2          # utils.py:53-55
+
+
+def text_ids_norm(ids, max_len):
+    """utils.py:57-63: truncate to max_len, pad with EOS_ID."""
+    ids = list(ids)[:max_len]
+    return ids + [EOS_ID] * (max_len - len(ids))
+
+
+def feat_reshape(feat: np.ndarray, max_len: int = 1200) -> np.ndarray:
+    """utils.py:39-46."""
+    h, w = feat.shape
+    if h >= max_len:
+        return feat[:max_len]
+    out = np.zeros((max_len, w), dtype=feat.dtype)
+    out[:h] = feat
+    return out
+
+
+def cal_descriptors(T, D):
+    """utils.py:156-159 (prints 114 for (1200, 80), utils.py:193)."""
+    def pool(x):
+        return np.ceil(x / 2)
+    return int(pool(pool(pool(pool(pool(T))))) * pool(pool(pool(pool(pool(D))))))
+
+
+def to_categorical(y, num_classes):
+    out = np.zeros((len(y), num_classes), dtype=np.float32)
+    out[np.arange(len(y)), np.asarray(y, dtype=np.int64)] = 1.0
+    return out
+
+
+def synthetic_batch(cfg: SARConfig, B: int, seed: int = 2020, lengths: Optional[np.ndarray] = None,
+                    label_len_range: Tuple[int, int] = (4, 20)) -> Tuple[Dict[str, np.ndarray], Dict[str, np.ndarray]]:
+    """Seeded synthetic (inputs, targets) with the dict keys / dtypes / shapes of
+    data_loader (utils.py:102-116).  x_data ~ U[0,1) (the range feat_norm guarantees); rows
+    beyond `lengths[i]` are zero (utils.py:39-46 padding, no masking downstream -- Q4);
+    CTC labels in [0, C-2] (blank = C-1), feasible for the encoder length."""
+    rng = np.random.RandomState(seed)
+    T, D, _ = cfg.input_shape
+    x = rng.rand(B, T, D, 1).astype(np.float32)
+    if lengths is not None:
+        for i, n in enumerate(lengths):
+            x[i, int(n):] = 0.0
+    inputs: Dict[str, np.ndarray] = {"x_data": x}
+    targets: Dict[str, np.ndarray] = {}
+    acc = rng.randint(0, cfg.accent_classes, size=B)
+    onehot = to_categorical(acc, cfg.accent_classes)
+    if cfg.ar_enable:
+        targets["y_accent"] = onehot
+    if cfg.disc_enable:
+        inputs["x_accent"] = onehot
+        targets["y_disc"] = onehot
+    if cfg.ctc_enable:
+        S = cfg.plan().seq_len
+        lo, hi = label_len_range
+        labels = np.full((B, cfg.max_ctc_len), EOS_ID, dtype=np.float32)
+        lab_len = np.zeros((B, 1), dtype=np.int32)
+        for i in range(B):
+            L = int(rng.randint(lo, hi + 1))
+            L = max(1, min(L, cfg.max_ctc_len, S // 2))
+            ids = rng.randint(0, cfg.bpe_classes - 1, size=L)
+            # feasibility (tf.nn.ctc_loss raises otherwise): L + #adjacent repeats <= S
+            while L + int(np.sum(ids[1:] == ids[:-1])) > S:
+                ids = rng.randint(0, cfg.bpe_classes - 1, size=L)
+            labels[i, :L] = ids
+            lab_len[i, 0] = L
+        inputs["x_ctc_label"] = labels
+        inputs["x_ctc_in_len"] = np.full((B, 1), S, dtype=np.int32)      # utils.py:96: constant encoder_len
+        inputs["x_ctc_out_len"] = lab_len
+        targets["y_ctc_loss"] = np.zeros([B])
+    return inputs, targets

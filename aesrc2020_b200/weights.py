@@ -1,0 +1,159 @@
+"""Canonical-name weight container for the SAR-Net hot path.
+
+Layouts are the reference's Keras layouts: conv kernels HWIO,
+Dense kernels (in, out), CuDNNGRU kernel (Din, 3u) / recurrent_kernel (u, 3u) /
+bias (6u,) in gate order z|r|h, BN gamma/beta/moving_mean/moving_variance,
+LayerNormalization gamma/beta, VladPooling `centers` (K+G, D) (VLAD.py:16-19),
+margin-head `W` (D, n_classes) (losses.py:22-26).
+
+Model-level layer names are the reference's explicit Keras names (model.py:252-322,
+95-106).  ResNet layers have no stable Keras names (resnet.py passes no `name=`), so
+they get canonical names resnet/s{stage}b{block}/{bn1,conv1,bn2,conv2,short}.
+
+Files are `.npz` (h5py is not available in this image; the .h5 importer is a
+"next" row).
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Dict, Tuple
+
+import numpy as np
+
+from .config import SARConfig
+
+
+def weight_shapes(cfg: SARConfig) -> "OrderedDict[str, Tuple[int, ...]]":
+    """Every weight tensor of the forward graph SAR_Net(cfg) builds, in creation order."""
+    s: "OrderedDict[str, Tuple[int, ...]]" = OrderedDict()
+
+    def bn(name, c):
+        for k in ("gamma", "beta", "moving_mean", "moving_variance"):
+            s["%s/%s" % (name, k)] = (c,)
+
+    def dense(name, i, o, bias=True):
+        s[name + "/kernel"] = (i, o)
+        if bias:
+            s[name + "/bias"] = (o,)
+
+    def ln(name, c):
+        s[name + "/gamma"] = (c,)
+        s[name + "/beta"] = (c,)
+
+    def bigru(name, din, u):
+        for d in ("forward", "backward"):
+            s["%s/%s/kernel" % (name, d)] = (din, 3 * u)
+            s["%s/%s/recurrent_kernel" % (name, d)] = (u, 3 * u)
+            s["%s/%s/bias" % (name, d)] = (6 * u,)
+
+    def conv(c):
+        s[c.name + "/kernel"] = (c.kh, c.kw, c.cin, c.cout)
+        s[c.name + "/bias"] = (c.cout,)
+
+    plan = cfg.plan()
+    conv(plan.stem)
+    bn("resnet/stem_bn", plan.stem.cout)
+    for b in plan.blocks:
+        if b.conv1.pre_bn:
+            bn(b.conv1.pre_bn, b.conv1.cin)
+        conv(b.conv1)
+        bn(b.conv2.pre_bn, b.conv2.cin)
+        conv(b.conv2)
+        if b.short:
+            conv(b.short)
+    bn(plan.final_bn, plan.cout)
+
+    H = cfg.hidden_dim
+    dense("CNN_LIN", plan.cout, H)
+    ln("CNN_LIN_LN", H)
+    bigru("CRNN", H, H)
+    ln("CRNN_LN", 2 * H)
+    if cfg.ctc_enable:
+        bigru("CTC_BIGRU", 2 * H, H)
+        ln("CTC_BIGRU_LN", 2 * H)
+        dense("CTC_DS", 2 * H, H)
+        ln("CTC_DS_LN", H)
+        dense("ctc_pred", H, cfg.bpe_classes)
+    if cfg.ar_enable:
+        dense("AR_DS", 2 * H, H)
+        ln("AR_DS_LN", H)
+        if cfg.mto == "bigru":
+            bigru("AR_MERGE", H, H)
+        elif cfg.mto in ("vlad", "gvlad"):
+            kg = cfg.vlad_clusters + (cfg.ghost_clusters if cfg.mto == "gvlad" else 0)
+            s[cfg.mto + "_center_assignment/kernel"] = (1, 1, H, kg)
+            s[cfg.mto + "_center_assignment/bias"] = (kg,)
+            s[cfg.mto + "_pool/centers"] = (kg, H)
+        d_int = cfg.integration_dim()
+        bn("AR_BN1", d_int)
+        dense("AR_EMBEDDING", d_int, H)
+        bn("AR_BN2", H)
+        dense("AR_CF_DS1", H, 64)
+        dense("AR_CF_DS2", 64, 64)
+        dense("y_accent", 64, cfg.accent_classes)
+
+        def disc(name, din):
+            if cfg.metric_loss in ("sphereface", "cosface", "arcface"):
+                s[name + "/W"] = (din, cfg.accent_classes)
+            elif cfg.metric_loss in ("softmax", "circleloss"):
+                s[name + "/kernel"] = (din, cfg.accent_classes)
+
+        if cfg.disc_enable:
+            disc("y_disc", H)
+        if cfg.disc_enable and cfg.bn_dim:
+            dense("AR_BN_DS", H, 64)
+            bn("AR_BN3", 64)
+            dense("bottleneck", 64, cfg.bn_dim)
+            bn("AR_BN4", cfg.bn_dim)
+            disc("y_disc_bn", cfg.bn_dim)
+    return s
+
+
+def init_weights(cfg: SARConfig, seed: int = 1234, degenerate: bool = False) -> Dict[str, np.ndarray]:
+    """Seeded synthetic weights.  With degenerate=False (default) BN statistics, affine
+    terms and biases are random so that no term of the forward is hidden by a Keras
+    zero/one initialiser; scales follow the reference's initialisers (he_normal convs and
+    Dense, glorot/orthogonal-scale GRU) so activations stay O(1) through the network."""
+    rng = np.random.RandomState(seed)
+    out: Dict[str, np.ndarray] = {}
+    for name, shp in weight_shapes(cfg).items():
+        leaf = name.rsplit("/", 1)[1]
+        if leaf == "kernel" and len(shp) == 4:
+            fan_in = shp[0] * shp[1] * shp[2]
+            w = rng.randn(*shp) * np.sqrt(2.0 / fan_in)
+        elif leaf == "kernel":
+            if "/forward/" in name or "/backward/" in name:
+                lim = np.sqrt(6.0 / (shp[0] + shp[1]))
+                w = rng.uniform(-lim, lim, size=shp)
+            else:
+                w = rng.randn(*shp) * np.sqrt(2.0 / shp[0])
+        elif leaf == "recurrent_kernel":
+            w = rng.randn(*shp) / np.sqrt(shp[0])
+        elif leaf == "W":
+            lim = np.sqrt(6.0 / (shp[0] + shp[1]))
+            w = rng.uniform(-lim, lim, size=shp)
+        elif leaf == "centers":
+            w = rng.randn(*shp) / np.sqrt(shp[1])
+        elif leaf == "bias":
+            w = np.zeros(shp) if degenerate else rng.randn(*shp) * 0.1
+        elif leaf == "gamma":
+            w = np.ones(shp) if degenerate else rng.uniform(0.7, 1.3, size=shp)
+        elif leaf == "beta":
+            w = np.zeros(shp) if degenerate else rng.randn(*shp) * 0.1
+        elif leaf == "moving_mean":
+            w = np.zeros(shp) if degenerate else rng.randn(*shp) * 0.1
+        elif leaf == "moving_variance":
+            w = np.ones(shp) if degenerate else rng.uniform(0.6, 1.4, size=shp)
+        else:
+            raise KeyError(name)
+        out[name] = np.ascontiguousarray(w, dtype=np.float32)
+    return out
+
+
+def save_weights(path: str, weights: Dict[str, np.ndarray]) -> None:
+    np.savez(path, **{k.replace("/", "|"): np.asarray(v) for k, v in weights.items()})
+
+
+def load_weights(path: str) -> Dict[str, np.ndarray]:
+    with np.load(path) as z:
+        return {k.replace("|", "/"): z[k] for k in z.files}

@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- utterances/sec of the SAR-Net forward path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg2]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one forward of the hot path over one per-GPU batch of synthetic fbank input
+(BASELINE.json configs[1] by default: B=64 x 500 frames x 80 mel, thin ResNet-34 + Bi-GRU +
+GhostVLAD(64c/8g) + ArcFace).  Weak scaling: every rank processes its own B utterances; the
+step ends with the path's single collective, an all-reduce(SUM) of the 8-float loss vector.
+
+Printed JSON (rank 0, one line):
+  value      whole-job utterances/s with inputs resident in HBM (CUDA events, max over ranks)
+  e2e        same metric through model.predict() with HOST numpy inputs: pinned H2D copy of the
+             step's inputs and D2H of the outputs inside the timed region
+  roofline   the ResNet residual-block convolution kernel (the dominant kernel): algorithmic
+             FLOPs / bytes per step over its measured device time inside the timed region
+  cpu_baseline  the oracle's torch-CPU fp32 restatement of the Keras forward on the host cores
+`--impl reference` times that CPU restatement as the reference arm (the literal Keras/TF
+graph cannot run here: no tensorflow/keras in the image and CuDNNGRU has no CPU kernel).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+METRIC = "utterances/sec (fbank->ResNet->GhostVLAD->margin-softmax fwd)"
+UNIT = "utt/s"
+
+CONFIGS = {
+    # BASELINE.json configs[1]
+    "cfg2": dict(B=64, T=500, kw=dict(ctc_enable=False, ar_enable=True, disc_enable=True, res_type="res34",
+                                      res_filters=32, mto="gvlad", vlad_clusters=64, ghost_clusters=8,
+                                      metric_loss="arcface", margin=0.3),
+                 workload="configs[1]: B=64/GPU x 500 frames x 80 mel, thin-ResNet34+BiGRU+GhostVLAD(64c/8g)+ArcFace fwd"),
+    # BASELINE.json configs[4] per-GPU shard (512 utt/GPU), for manual sweeps
+    "cfg5": dict(B=512, T=500, kw=dict(ctc_enable=True, ar_enable=True, disc_enable=True, res_type="res34",
+                                       res_filters=32, mto="gvlad", vlad_clusters=64, ghost_clusters=8,
+                                       metric_loss="circleloss", margin=0.2),
+                 workload="configs[4] shard: B=512/GPU x 500 frames, CRNN+GhostVLAD+Circle-Loss+CTC fwd"),
+    "cfg3": dict(B=256, T=800, kw=dict(ctc_enable=True, ar_enable=True, disc_enable=True, res_type="res34",
+                                       res_filters=32, mto="bigru", metric_loss="circleloss", margin=0.2),
+                 workload="configs[2]: B=256 x 200-800 frames padded to 800, CTC+Circle-Loss fwd"),
+}
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "tflops": float(p["bf16_tflops_sustained"]),
+                "tflops_burst": float(p["bf16_tflops"]), "source": "measured (MEASURED_PEAKS.json)"}
+    except Exception:
+        return {"hbm_gbs": 6650.0, "tflops": 1400.0, "tflops_burst": 1590.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def conv_algorithmic_work(plan, B, act_bytes):
+    """per-layer F = 2*B*Ho*Wo*Cout*Cin*kh*kw; Bytes = e*B*(in + out [+ residual]) + weights.
+    Returns (flops, bytes, launches) per step for the residual-block convolutions (stem excluded)."""
+    F = 0.0
+    Bt = 0.0
+    n = 0
+    for blk in plan.blocks:
+        for c, has_res in ((blk.conv1, False), (blk.conv2, True), (blk.short, False)):
+            if c is None:
+                continue
+            F += 2.0 * B * c.hout * c.wout * c.cout * c.cin * c.kh * c.kw
+            Bt += act_bytes * B * (c.hin * c.win * c.cin + c.hout * c.wout * c.cout * (2 if has_res else 1))
+            Bt += 4.0 * (c.kh * c.kw * c.cin * c.cout + c.cout)
+            n += 1
+    return F, Bt, n
+
+
+def run_reference(args, cfgd):
+    """Reference arm: the oracle's torch-CPU fp32 restatement of the Keras forward, all host threads."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from aesrc2020_b200.config import SARConfig
+    from aesrc2020_b200 import weights as W, utils as us
+    from oracle import sarnet_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = SARConfig(input_shape=(cfgd["T"], 80, 1), **cfgd["kw"])
+    w = W.init_weights(cfg, 1234)
+    Bs = min(args.ref_batch, cfgd["B"])
+    x, _ = us.synthetic_batch(cfg, Bs, seed=2020)
+    fwd = lambda: O.sar_net_forward(w, x, **cfg.model_kwargs(), dtype=torch.float32)
+    for _ in range(args.warmup):
+        fwd()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fwd()
+    dt = (time.perf_counter() - t0) / args.steps
+    v = Bs / dt
+    sample = "%d of the %d utterances of one step per timed step (torch-CPU fp32, %d threads)" % (Bs, cfgd["B"], cores)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfgd["workload"], "note": "reference arm = torch-CPU restatement of the Keras forward "
+                   "(oracle port); the literal Keras/TF graph is not runnable in this image"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=list(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
+    ap.add_argument("--ref-batch", type=int, default=32, help="utterances per step of the CPU reference sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rotate", type=int, default=16, help="distinct input batches rotated through (L2 hygiene)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    cfgd = dict(CONFIGS[args.config])
+    if args.batch:
+        cfgd["B"] = args.batch
+    if args.impl == "reference":
+        return run_reference(args, cfgd)
+
+    from aesrc2020_b200 import dist as sdist, model as mdl, utils as us, ops
+    import torch.distributed as tdist
+    env = sdist.init_from_env()
+    rank, world, local = env["rank"], env["world_size"], env["local_rank"]
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    dev = torch.device("cuda", local)
+    B, T = cfgd["B"], cfgd["T"]
+    import io, contextlib
+    with contextlib.redirect_stdout(io.StringIO()):
+        model, _ = mdl.SAR_Net((T, 80, 1), device=dev, **cfgd["kw"])
+    cfg = model.config
+    eng = model.engine()
+    plan = cfg.plan()
+
+    # ---- synthetic inputs: `rotate` distinct batches, resident in HBM (value) and in pinned host memory (e2e)
+    host_batches, dev_batches = [], []
+    lengths = None
+    for i in range(args.rotate):
+        if args.config == "cfg3":
+            lengths = np.random.RandomState(100 + i + 1000 * rank).randint(200, 801, size=B)
+        x, _ = us.synthetic_batch(cfg, B, seed=2020 + i + 1000 * rank, lengths=lengths)
+        host_batches.append(x)
+        dev_batches.append({k: model._to_device(k, v).clone() for k, v in x.items()})
+    torch.cuda.synchronize()
+    in_bytes = sum(v.nbytes for v in host_batches[0].values())
+
+    def step_device(i):
+        out = eng.forward(dev_batches[i % args.rotate])
+        vec = out["loss_vector"]
+        if world > 1:
+            tdist.all_reduce(vec)
+        return out
+
+    def barrier():
+        if world > 1:
+            tdist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    for i in range(args.warmup):
+        step_device(i)
+    barrier()
+
+    # ---- timed region (device-resident inputs); conv segment timed with its own events
+    conv_ev = []
+    orig_raw = eng.resnet.forward_raw
+
+    def timed_raw(x):
+        # events bracket the residual-block convolutions only (stem + pool run before e0)
+        pl = eng.resnet.plan
+        a = eng.resnet.conv(x, pl.stem, act="relu")
+        a = ops.maxpool2d(a, k=3, stride=2, pad_t=pl.pool_pad_t, pad_l=pl.pool_pad_l, out_hw=(pl.pool_hout, pl.pool_wout))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for b in pl.blocks:
+            c1 = eng.resnet.conv(a, b.conv1)
+            sc = eng.resnet.conv(a, b.short) if b.short else a
+            a = eng.resnet.conv(c1, b.conv2, residual=sc)
+        e1.record()
+        conv_ev.append((e0, e1))
+        return a
+
+    eng.resnet.forward_raw = timed_raw
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ops.LAUNCHES["n"]
+    barrier()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for i in range(args.steps):
+        step_device(args.warmup + i)
+    t_end.record()
+    barrier()
+    launches = ops.LAUNCHES["n"] - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    eng.resnet.forward_raw = orig_raw
+    ms = t_start.elapsed_time(t_end)
+    conv_ms = sum(a.elapsed_time(b) for a, b in conv_ev) / max(len(conv_ev), 1)
+    if world > 1:
+        tt = torch.tensor([ms], device=dev)
+        tdist.all_reduce(tt, op=tdist.ReduceOp.MAX)
+        ms = float(tt.item())
+    ms_per_step = ms / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+
+    # ---- e2e: model.predict with HOST inputs (pinned H2D + D2H of outputs inside the timed region)
+    def step_e2e(i):
+        outs = model.predict(host_batches[i % args.rotate], batch_size=B)
+        return outs
+    for i in range(3):
+        outs = step_e2e(i)
+    out_bytes = sum(o.nbytes for o in (outs if isinstance(outs, list) else [outs]))
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_e2e(3 + i)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([e2e_s], device=dev)
+        tdist.all_reduce(tt, op=tdist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    e2e_value = world * B * args.steps / e2e_s
+
+    if rank != 0:
+        if world > 1:
+            tdist.barrier()
+        return
+
+    # ---- roofline of the residual-block convolution kernel
+    peaks = load_peaks()
+    act_bytes = 4.0            # activations as stored by this build (fp32 NHWC)
+    F, Bt, nconv = conv_algorithmic_work(plan, B, act_bytes)
+    t_conv = conv_ms * 1e-3
+    tensor_time = F / (peaks["tflops"] * 1e12)
+    hbm_time = Bt / (peaks["hbm_gbs"] * 1e9)
+    if hbm_time >= tensor_time:
+        roof = {"bound": "hbm", "achieved": Bt / t_conv / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s"}
+    else:
+        roof = {"bound": "tensor", "achieved": F / t_conv / 1e12, "peak": peaks["tflops"], "unit": "TFLOP/s"}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    roof.update({"traffic": None, "kernel": "residual-block conv (36 launches/step for thin-ResNet34)",
+                 "launches_per_step": nconv, "avg_launch_us": conv_ms * 1e3 / nconv, "conv_ms_per_step": conv_ms,
+                 "share_of_step": conv_ms / ms_per_step, "algorithmic_gflop_per_step": F / 1e9,
+                 "algorithmic_mb_per_step": Bt / 1e6, "tflops_achieved": F / t_conv / 1e12,
+                 "peak_source": peaks["source"] + ", sustained bf16 for a kernel timed inside a long step"})
+
+    # ---- CPU baseline (oracle port, bounded sample) on rank 0, N=1 only
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import sarnet_oracle as O
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        Bs = min(args.ref_batch, B)
+        xs = {k: v[:Bs] for k, v in host_batches[0].items()}
+        fwd = lambda: O.sar_net_forward(model.weights, xs, **cfg.model_kwargs(), dtype=torch.float32)
+        fwd()
+        t0 = time.perf_counter()
+        reps = 0
+        while reps < 3 or (time.perf_counter() - t0 < 10.0 and reps < 50):
+            fwd()
+            reps += 1
+        dt = (time.perf_counter() - t0) / reps
+        cpu = {"value": Bs / dt, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "%d utterances of step 0 x %d repeats, torch-CPU fp32 restatement of the Keras forward" % (Bs, reps)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfgd["workload"], "per_gpu_batch": B, "frames": T, "seq_len": plan.seq_len,
+                   "l2": "inputs rotate over %d distinct batches (%.0f MB > 126 MB L2); activations %.0f MB/step"
+                         % (args.rotate, args.rotate * in_bytes / 1e6, 2 * Bt / 1e6 / 3),
+                   "parallelism": "dp%d (batch-sharded, 1 all-reduce of 8 floats/step)" % world},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes},
+        "gpu_launches": launches, "roofline": roof, "clocks": clocks,
+    }
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    if world > 1:
+        tdist.barrier()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,179 @@
+/* sarnet.h -- C ABI of libsarnet_sm100.so, the B200 (sm_100a) forward engine for the
+ * speech-accent-recognition network of pika-online/AESRC2020.
+ *
+ * The reference has NO native/FFI interface (it is Keras-on-TensorFlow Python); its
+ * boundary for this path is the Python call surface of model.py / resnet.py / VLAD.py /
+ * losses.py.  Each entry point below therefore cites the reference *function* whose
+ * arithmetic it replaces (file:line under the reference tree); the Python mirror in
+ * aesrc2020_b200/ binds them with ctypes (see INTEGRATION.md for the stub a reference
+ * maintainer would add).
+ *
+ * Conventions
+ *  - every pointer is CALLER-OWNED DEVICE memory unless the name ends in `_host`;
+ *    the library never allocates, frees or synchronises (stream-ordered);
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *  - tensors are dense, row-major, channels-last (NHWC) exactly like the reference
+ *    (resnet.py:12-14); fp32 unless stated; 16-byte aligned base pointers;
+ *  - return 0 on success, a negative sar_status for rejected arguments, the positive
+ *    cudaError_t for a launch failure; sar_last_error() returns a thread-local message;
+ *  - re-entrant across streams/devices: the caller sets the device; no global state.
+ */
+#ifndef SARNET_H_
+#define SARNET_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  SAR_OK = 0,
+  SAR_ERR_BAD_ARG = -1,      /* null pointer, non-positive size, inconsistent shape */
+  SAR_ERR_UNSUPPORTED = -2,  /* shape/option combination this build has no kernel for */
+  SAR_ERR_ALIGN = -3,        /* pointer or leading dimension not aligned as required */
+  SAR_ERR_WORKSPACE = -4     /* workspace too small (see the *_workspace_bytes helper) */
+} sar_status;
+
+/* activation selector for the fused epilogues */
+enum { SAR_ACT_NONE = 0, SAR_ACT_RELU = 1, SAR_ACT_TANH = 2 };
+
+/* margin-head selector: model.py:142-167 (disc_loss) */
+enum {
+  SAR_HEAD_NONE = 0,
+  SAR_HEAD_SOFTMAX = 1,     /* Dense(n, softmax, use_bias=False)            model.py:149-150 */
+  SAR_HEAD_SPHEREFACE = 2,  /* losses.py:12-50  */
+  SAR_HEAD_COSFACE = 3,     /* losses.py:58-94  */
+  SAR_HEAD_ARCFACE = 4,     /* losses.py:105-147 */
+  SAR_HEAD_CIRCLE = 5,      /* l2norm(x) @ W raw cosines + circle_loss      model.py:161-163, losses.py:157-172 */
+  SAR_HEAD_CIRCLE_RAW = 6   /* circle_loss on x @ W WITHOUT normalising x: with W = I this evaluates
+                               losses.circle_loss(y_true, y_pred) on given cosines (losses.py:157-172) */
+};
+
+int sar_version(void);
+const char* sar_last_error(void);
+/* compiled SM architecture of the embedded cubin (100 for sm_100a) */
+int sar_compiled_arch(void);
+
+/* ---- ResNet front-end -------------------------------------------------------------- */
+
+/* Generic NHWC convolution on CUDA cores (fp32 FFMA implicit GEMM), used for the 7x7/s2
+ * stem (Cin=1), and as the Dense/GEMM primitive (kh=kw=1, W=1).
+ * Replaces: Conv2D call sites resnet.py:39-42, 60-63, 82-87, 113-117; Dense model.py:35-42.
+ *   in' = pre_scale ? relu(pre_scale[ci]*x + pre_shift[ci]) : x     (_bn_relu on the conv INPUT,
+ *         applied to in-bounds cells only: TF-SAME zero padding pads the ACTIVATED tensor)
+ *   acc = conv(in', w_hwio) + bias + (residual ? residual : 0)     (Add(), resnet.py:89)
+ *   out = act( post_scale ? post_scale[co]*acc + post_shift[co] : acc )
+ * x (B,H,W,Cin); w (kh,kw,Cin,Cout) Keras HWIO; out/residual (B,Ho,Wo,Cout).
+ * pad_t/pad_l are the TF-SAME leading pads (trailing pads are implied by Ho/Wo). */
+int sar_conv2d_fwd(const float* x, const float* w_hwio, const float* bias,
+                   const float* pre_scale, const float* pre_shift,
+                   const float* post_scale, const float* post_shift,
+                   const float* residual, float* out,
+                   int B, int H, int W, int Cin, int Ho, int Wo, int Cout,
+                   int kh, int kw, int stride, int pad_t, int pad_l, int act, void* stream);
+
+/* MaxPooling2D(3x3, strides 2, 'same') -- resnet.py:174,192.  Padded cells never win. */
+int sar_maxpool2d_fwd(const float* x, float* out, int B, int H, int W, int C, int Ho, int Wo,
+                      int k, int stride, int pad_t, int pad_l, void* stream);
+
+/* y = relu(scale[c]*x + shift[c]) over the last axis: _bn_relu, resnet.py:22-26 (inference BN
+ * folded to an affine by the caller: scale=gamma/sqrt(var+1e-3), shift=beta-mean*scale). */
+int sar_affine_relu_fwd(const float* x, const float* scale, const float* shift, float* out,
+                        long long rows, int C, int relu, void* stream);
+
+/* ---- encoder tail ------------------------------------------------------------------ */
+
+/* LayerNormalization over the last axis (keras_layer_normalization, model.py:32-33):
+ * y = gamma*(x-mean)/sqrt(var+eps)+beta, biased variance, two-pass fp32.  C <= 1024. */
+int sar_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* out,
+                      long long rows, int C, float eps, void* stream);
+
+/* Recurrent part of Bidirectional(CuDNNGRU) -- model.py:44-50.
+ * xp (B,S,2,3u): input projections x*W + b_input for [forward | backward], gate order z|r|h
+ *   (computed by sar_conv2d_fwd as one GEMM against the concatenated kernels);
+ * rec (2,u,3u) recurrent kernels, rbias (2,3u) recurrent biases.
+ * seq!=0: out (B,S,2u) = concat(fwd[t], bwd[t]) in time order;
+ * seq==0: out (B,2u)   = concat(fwd final state, bwd final state).  u must be 256. */
+int sar_bigru_fwd(const float* xp, const float* rec, const float* rbias, float* out,
+                  int B, int S, int u, int seq, void* stream);
+
+/* ---- many-to-one integration ------------------------------------------------------- */
+
+/* NetVLAD / GhostVLAD: the 1x1 assignment conv (model.py:89-95 / 99-105) fused with
+ * VladPooling.call (VLAD.py:26-49).  feat (B,S,D); centers (K+G,D), ghosts are the LAST G
+ * rows; out (B,K*D), per-cluster L2-normalised.  Cluster scores come from EITHER the fused
+ * assignment conv (w_assign (D,K+G), b_assign (K+G); score = NULL) -- the model.vlad() path --
+ * OR a precomputed `score` (B,S,K+G) tensor (w_assign = b_assign = NULL) -- the bare
+ * VladPooling([feat, cluster_score]) call surface of VLAD.py:26-28.
+ * Requires D % 32 == 0, D <= 512, K+G <= 128. */
+int sar_vlad_fwd(const float* feat, const float* w_assign, const float* b_assign, const float* score,
+                 const float* centers, float* out, int B, int S, int D, int K, int G, void* stream);
+
+/* GlobalAveragePooling1D (model.py:125): out (B,D) = mean over S of x (B,S,D). */
+int sar_avgpool_fwd(const float* x, float* out, int B, int S, int D, void* stream);
+
+/* Split-K GEMM for the AR_EMBEDDING layer (model.py:286-289; AR_BN1/AR_BN2 folded into
+ * w/bias by the caller): out (M,N) = a (M,K) @ w (K,N) + bias.  Deterministic two-pass
+ * reduction through `workspace` (sar_gemm_splitk_workspace_bytes). */
+size_t sar_gemm_splitk_workspace_bytes(int M, int K, int N);
+int sar_gemm_splitk_fwd(const float* a, const float* w, const float* bias, float* out,
+                        int M, int K, int N, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- heads and losses -------------------------------------------------------------- */
+
+/* Classifier MLP + margin head + per-sample losses in one pass over the embedding row.
+ * Replaces: AR_CF_DS1/AR_CF_DS2/y_accent (model.py:294-296), disc_loss (model.py:142-167),
+ * SphereFace/CosFace/ArcFace.call (losses.py:28-47,74-91,121-144), circle_loss
+ * (losses.py:157-172), categorical_crossentropy + accuracy wiring (model.py:344-367).
+ * emb (B,D).  Classifier weights may be NULL (then y_accent outputs are skipped).
+ * wd (Dd,n) is the head weight applied to `emb_d` (B,Dd) (NULL -> emb, Dd=D).
+ * onehot (B,n) may be NULL when head is NONE/SOFTMAX/CIRCLE and no losses are wanted.
+ * Outputs (any may be NULL): y_accent (B,n) probs, y_accent_logits (B,n),
+ * y_disc (B,n) probs (raw cosines for CIRCLE), y_disc_logits (B,n) pre-softmax,
+ * sample_stats (B,4) = [loss_accent, loss_disc, correct_accent, correct_disc]. */
+int sar_head_fwd(const float* emb, int D,
+                 const float* w1, const float* b1, int H1,
+                 const float* w2, const float* b2, int H2,
+                 const float* w3, const float* b3,
+                 const float* emb_d, int Dd, const float* wd,
+                 const float* onehot, int n_classes, int head, float margin, float s, float gamma,
+                 float* y_accent, float* y_accent_logits, float* y_disc, float* y_disc_logits,
+                 float* sample_stats, int B, void* stream);
+
+/* CTC negative log-likelihood from PRE-softmax ctc_pred logits.
+ * Replaces: Dense(softmax) 'ctc_pred' activation + K.ctc_batch_cost (model.py:268-269,62-71):
+ * p = softmax(logits); q = (p+1e-7)/sum(p+1e-7); blank = C-1; merge_repeated.
+ * logits (B,S,C); labels (B,Lmax) FLOAT ids (utils.py:107); in_len/lab_len (B) int32.
+ * loss (B).  probs (B,S,C) optional output of the softmax (model.predict of ctc_pred).
+ * status (B) int32 optional: 0 ok, 1 infeasible label sequence (TF raises), 2 bad label. */
+int sar_ctc_fwd(const float* logits, const float* labels, const int* in_len, const int* lab_len,
+                float* loss, float* probs, int* status, int B, int S, int C, int Lmax, void* stream);
+
+/* Deterministic batch reduction of per-sample statistics into the 8-float vector that is
+ * all-reduced across GPUs (one ncclAllReduce(SUM), replaces multi_gpu_model, model.py:193-194):
+ * out8 = [sum loss_accent, sum loss_disc, sum loss_ctc, sum loss_disc_bn,
+ *         #correct_accent, #correct_disc, count, #correct_disc_bn].
+ * sample_stats (B,4) or NULL, ctc_loss (B) or NULL, bn_stats (B,4) or NULL. */
+int sar_loss_reduce_fwd(const float* sample_stats, const float* ctc_loss, const float* bn_stats,
+                        float* out8, int B, void* stream);
+
+/* ---- feature front-end ------------------------------------------------------------- */
+
+/* On-device restatement of psf.fbank(y, 16000, nfilt=80)[0] + feat_norm + feat_reshape
+ * (local/make_fbank.py:24-28, utils.py:35-46): preemphasis 0.97, 400/160 rectangular
+ * frames, 512-point power spectrum / 512, 80 triangular mel filters (linear energies, no
+ * log), per-utterance per-bin min-max to [0,1], truncate / zero-pad to T frames.
+ * wav (total samples) fp32 concatenated utterances; offsets (B+1) int64 sample offsets;
+ * melfb_t (257,80) BIN-MAJOR filterbank matrix (built by the caller,
+ * aesrc2020_b200.fbank.mel_filterbank(...).T); feat_ws (B,Fmax,80) workspace for the raw
+ * energies, Fmax >= the longest utterance's frame count 1+ceil((n-400)/160);
+ * x_data (B,T,80) output. */
+int sar_fbank_fwd(const float* wav, const long long* offsets, const float* melfb_t,
+                  float* feat_ws, float* x_data, int B, int Fmax, int T, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SARNET_H_ */

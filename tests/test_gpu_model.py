@@ -1,0 +1,144 @@
+"""GPU parity of the whole forward (SAR_Net(...).predict through the C ABI) against the float64
+CPU oracle, for the BASELINE.json configurations at oracle-sized batches, plus the
+size-independent properties used at full size (batch-split invariance, padding semantics)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import rel_err, norm_err, REL_TOL
+from oracle import sarnet_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+CONFIGS = {
+    # BASELINE.json configs[0]: single 300-frame utterance, res18/64 + AvgPool + Softmax
+    "cfg1_res18_avg_softmax": dict(T=300, B=1, kw=dict(res_type="res18", res_filters=64, mto="avg")),
+    # configs[1]: 500 frames, ResNet+Bi-GRU+GhostVLAD(64c/8g)+ArcFace
+    "cfg2_gvlad_arcface": dict(T=500, B=3, kw=dict(disc_enable=True, res_type="res34", res_filters=32, mto="gvlad",
+                                                   vlad_clusters=64, ghost_clusters=8, metric_loss="arcface", margin=0.3)),
+    # configs[2]: variable 200-800 frames zero-padded, CTC + Circle-Loss, bigru merge
+    "cfg3_ctc_circle_bigru": dict(T=800, B=3, lengths=[200, 517, 800],
+                                  kw=dict(ctc_enable=True, disc_enable=True, res_type="res34", res_filters=32, mto="bigru",
+                                          metric_loss="circleloss", margin=0.2)),
+    # configs[3]: NetVLAD(64c)+CosFace
+    "cfg4_vlad_cosface": dict(T=500, B=2, kw=dict(disc_enable=True, res_type="res34", res_filters=32, mto="vlad",
+                                                  vlad_clusters=64, metric_loss="cosface", margin=0.3)),
+    # configs[4]: full CRNN+GhostVLAD+Circle-Loss+CTC
+    "cfg5_gvlad_circle_ctc": dict(T=500, B=2, kw=dict(ctc_enable=True, disc_enable=True, res_type="res34", res_filters=32,
+                                                      mto="gvlad", vlad_clusters=64, ghost_clusters=8,
+                                                      metric_loss="circleloss", margin=0.2)),
+    # remaining heads / bottleneck branch / train.py's hard-coded 8c+2g (Q10) at the reference's T=1200 -> S=114
+    "sphereface_bn_T1200": dict(T=1200, B=1, kw=dict(ctc_enable=True, disc_enable=True, res_type="res34", res_filters=32,
+                                                     mto="gvlad", vlad_clusters=8, ghost_clusters=2, bn_dim=32,
+                                                     metric_loss="sphereface", margin=1.35)),
+    "softmax_head_res18_thin": dict(T=200, B=2, kw=dict(disc_enable=True, res_type="res18", res_filters=32, mto="avg",
+                                                        metric_loss="softmax")),
+}
+
+
+def build(name):
+    from aesrc2020_b200 import model as mdl, utils as us
+    c = CONFIGS[name]
+    model, train_model = mdl.SAR_Net((c["T"], 80, 1), **c["kw"])
+    assert train_model is model                        # gpus == 1 (model.py:195-196)
+    x, y = us.synthetic_batch(model.config, c["B"], seed=len(name), lengths=c.get("lengths"))
+    return model, x, y
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_forward_matches_oracle(cuda_device, name):
+    model, x, y = build(name)
+    cfg = model.config
+    ref = O.sar_net_forward(model.weights, x, **cfg.model_kwargs())
+    outs = model.predict(x, batch_size=CONFIGS[name]["B"])
+    outs = outs if isinstance(outs, list) else [outs]
+    assert [o.shape for o in outs] == [tuple(ref[n].shape) for n in cfg.output_names()]
+    for n, got in zip(cfg.output_names(), outs):
+        assert rel_err(got, ref[n]) < REL_TOL, n
+    # pre-softmax logits and the embedding, through the device dict
+    dev_out = model.forward_device(x)
+    assert norm_err(dev_out["embedding"], ref["embedding"]) < 1e-4
+    assert rel_err(dev_out["y_accent_logits"], ref["y_accent_logits"], floor=1e-2) < REL_TOL
+    if cfg.disc_enable:
+        assert rel_err(dev_out["y_disc_logits"], ref["y_disc_logits"], floor=1e-2) < REL_TOL
+    # Keras-style losses/metrics from the reduced 8-float vector
+    tgt = torch.as_tensor(y["y_accent"], dtype=torch.float64)
+    want = O.sar_net_losses(ref, tgt, ctc_enable=cfg.ctc_enable, ar_enable=cfg.ar_enable, disc_enable=cfg.disc_enable,
+                            bn_dim=cfg.bn_dim, metric_loss=cfg.metric_loss, margin=cfg.margin)
+    got = model.evaluate(x, y, batch_size=CONFIGS[name]["B"])
+    for k, v in want.items():
+        assert abs(got[k] - float(v)) <= REL_TOL * max(abs(float(v)), 1e-3), (k, got[k], float(v))
+
+
+def test_resnet_surface_and_intermediates(cuda_device):
+    """resnet34_(input, filters) call surface + stage-by-stage agreement of the encoder."""
+    from aesrc2020_b200 import resnet as rn, model as mdl, utils as us
+    model, x, _ = build("cfg5_gvlad_circle_ctc")
+    w64 = {k: torch.as_tensor(v, dtype=torch.float64) for k, v in model.weights.items()}
+    ref = O.sar_net_forward(model.weights, x, **model.config.model_kwargs(), return_intermediates=True)
+    fmap = rn.resnet34_(torch.from_numpy(x["x_data"]).cuda(), filters=32, weights=model.weights)
+    assert tuple(fmap.shape) == tuple(ref["resnet"].shape) == (2, 16, 3, 256)
+    assert norm_err(fmap, ref["resnet"]) < 1e-4
+    out = model.forward_device(x, want_intermediates=True)
+    for k in ("cnn_lin", "crnn", "ar_ds", "integration", "ctc_pred"):
+        assert norm_err(out[k], ref[k]) < 1e-4, k
+    with pytest.raises(NotImplementedError):
+        rn.resnet50_(torch.zeros(1, 200, 80, 1, device="cuda"))
+
+
+def test_batch_split_invariance_and_padding(cuda_device):
+    """Size-independent properties used at BASELINE sizes: per-utterance outputs do not depend
+    on batch composition (bitwise), and zero-padded frames are COMPUTED ON, not masked (Q4)."""
+    from aesrc2020_b200 import model as mdl, utils as us
+    kw = dict(ctc_enable=True, disc_enable=True, res_type="res34", res_filters=32, mto="gvlad", vlad_clusters=64,
+              ghost_clusters=8, metric_loss="arcface")
+    model, _ = mdl.SAR_Net((500, 80, 1), **kw)
+    x, _ = us.synthetic_batch(model.config, 64, seed=5)
+    full = model.predict(x, batch_size=64)
+    halves = model.predict(x, batch_size=32)
+    ragged = model.predict(x, batch_size=7)
+    for a, b, c in zip(full, halves, ragged):
+        assert np.array_equal(a, b) and np.array_equal(a, c)
+    assert all(np.isfinite(a).all() for a in full)
+    assert np.allclose(full[0].sum(-1), 1.0, atol=1e-5) and np.allclose(full[1].sum(-1), 1.0, atol=1e-5)
+    # padding semantics: zeroing the tail of an utterance changes its output (no masking) ...
+    x2 = {k: v.copy() for k, v in x.items()}
+    x2["x_data"][0, 300:] = 0.0
+    o2 = model.predict(x2, batch_size=64)
+    assert not np.array_equal(o2[0][0], full[0][0])
+    # ... but leaves every other utterance bit-identical (utterances are independent)
+    assert np.array_equal(o2[0][1:], full[0][1:])
+
+
+def test_weights_roundtrip_and_layers(cuda_device, tmp_path):
+    from aesrc2020_b200 import model as mdl, utils as us
+    model, x, _ = build("cfg4_vlad_cosface")
+    a = model.predict(x)
+    p = str(tmp_path / "demo.npz")
+    model.save_weights(p)                                  # model.py:416-417 round trip
+    other, _ = mdl.SAR_Net((500, 80, 1), **CONFIGS["cfg4_vlad_cosface"]["kw"], seed=99)
+    assert not np.array_equal(other.predict(x)[0], a[0])
+    other.load_weights(p)
+    assert all(np.array_equal(u, v) for u, v in zip(other.predict(x), a))
+    lay = model.get_layer("vlad_pool")
+    assert lay.get_weights()[0].shape == (64, 256)         # VLAD.py:17-19
+    sub = mdl.sub_model(model, "x_data", "y_accent")       # model.py:415
+    assert np.array_equal(sub.predict(x), a[0])
+
+
+def test_device_tensor_inputs_are_zero_copy(cuda_device):
+    model, x, _ = build("cfg2_gvlad_arcface")
+    xd = {k: torch.from_numpy(v).cuda() for k, v in x.items()}
+    outs = model.predict(xd, batch_size=8)
+    assert all(isinstance(o, torch.Tensor) and o.is_cuda for o in outs)
+    host = model.predict(x, batch_size=8)
+    assert all(np.array_equal(o.cpu().numpy(), h) for o, h in zip(outs, host))
+
+
+def test_ctc_infeasible_raises(cuda_device):
+    from aesrc2020_b200 import model as mdl, utils as us, _shim
+    model, x, _ = build("cfg5_gvlad_circle_ctc")
+    x["x_ctc_out_len"][:] = 40                             # 40 labels cannot fit in S=48 with repeats forced below
+    x["x_ctc_label"][:, :40] = 7.0
+    with pytest.raises(_shim.SarnetError):
+        model.predict(x)
