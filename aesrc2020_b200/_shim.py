@@ -30,6 +30,11 @@ SIGNATURES = {
     "sar_last_error": (C.c_char_p, []),
     "sar_compiled_arch": (c_int, []),
     "sar_conv2d_fwd": (c_int, [c_fp] * 9 + [c_int] * 13 + [C.c_void_p]),
+    "sar_planes_bytes": (c_sz, [c_int] * 5),
+    "sar_planes_pack_fwd": (c_int, [c_fp, c_fp, c_fp, c_int, c_fp] + [c_int] * 5 + [C.c_void_p]),
+    "sar_planes_unpack_fwd": (c_int, [c_fp, c_fp] + [c_int] * 5 + [C.c_void_p]),
+    "sar_maxpool_planes_fwd": (c_int, [c_fp, c_fp] + [c_int] * 10 + [C.c_void_p]),
+    "sar_conv_tc_fwd": (c_int, [C.c_void_p, C.c_void_p]),
     "sar_maxpool2d_fwd": (c_int, [c_fp, c_fp] + [c_int] * 10 + [C.c_void_p]),
     "sar_affine_relu_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_ll, c_int, c_int, C.c_void_p]),
     "sar_layernorm_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_ll, c_int, c_f, C.c_void_p]),

@@ -1,0 +1,473 @@
+// conv_tc.cu -- residual-block convolutions of resnet.py on the 5th-gen tensor cores.
+//
+// Replaces _bn_relu_conv / basic_block / _shortcut (resnet.py:47-65, 105-125, 67-89): every 3x3
+// convolution of the body (stride 1 and 2), with the 1x1 projection shortcut folded into the
+// same accumulator and bias / identity-shortcut add / next-layer BN->ReLU fused in the epilogue.
+//
+// Formulation (implicit GEMM without im2col):
+//  * Activations live in HBM as "flat-pad planes": an (H,W,C) map is stored as rows
+//    q = n*(H+1)*(W+1) + h*(W+1) + w of C fp16 channels with ONE shared zero pad column / pad row
+//    (the right pad of a row is the left pad of the next, the bottom pad row of an image is the top
+//    pad row of the next).  A 3x3/s1 tap (kh,kw) of output row q then reads input row
+//    q + (kh-1)*(W+1) + (kw-1): the A tile of tap t for 128 consecutive output rows is ONE 2-D TMA
+//    box at a shifted row coordinate; rows before the tensor start are TMA zero fill.  Outputs
+//    computed at pad positions are discarded by the epilogue (pads stay zero).
+//  * A tensor that feeds a stride-2 block is stored phase-split (4 planes by (h&1, w&1), each a
+//    flat-pad map with the OUTPUT geometry), which turns the stride-2 taps into stride-1 row
+//    shifts on one phase plane each -- TF-SAME's asymmetric padding becomes a choice of phase and
+//    shift per tap (computed on the host).
+//  * fp32 accuracy on fp16 tensor cores: every tensor is a pair of fp16 planes, hi = fp16(x) and
+//    lo = fp16((x - hi) * 2^11).  D = Ah*Wh accumulates in one TMEM accumulator and the cross
+//    terms Al*Wh + Ah*Wl in a second one; the epilogue combines acc0 + 2^-11 * acc1 (the dropped
+//    Al*Wl term is 2^-22 relative).  3 tcgen05.mma per k-step instead of 1.
+//
+// Kernel: persistent, one CTA per SM, 192 threads = TMA producer warp, MMA issuer warp (one
+// elected lane issues tcgen05.mma, accumulators in TMEM, double buffered across tiles), and four
+// epilogue warps (tcgen05.ld -> registers -> bias/residual/BN/ReLU -> hi/lo planes in HBM).
+// 3-stage TMA->SMEM ring with mbarrier full/empty pairs, 128B/64B hardware swizzle.
+#include <cuda.h>
+#include "common.cuh"
+
+namespace sar {
+
+constexpr int TC_BM = 128;            // output rows per tile (TMEM lanes)
+constexpr int TC_STAGES = 3;
+constexpr int TC_PLANE_BYTES = 16384; // 128 rows x 128 B (kc = 64) per operand plane
+constexpr int TC_STAGE_BYTES = 4 * TC_PLANE_BYTES;
+constexpr int TC_THREADS = 192;
+constexpr float TC_LO_SCALE = 2048.f;
+constexpr float TC_LO_INV = 1.f / 2048.f;
+
+struct TcParams {
+  // K loop
+  int ntaps, chunks_main, kc_main;       // main operand: ntaps * chunks_main k-steps of kc_main channels
+  int chunks_sc, kc_sc, sc_plane;        // projection-shortcut operand: chunks_sc k-steps of kc_sc channels
+  int tap_row_off[9], tap_plane[9];
+  // tiles
+  long long R;                           // flat output rows (incl. pads)
+  int m_tiles, n_tiles, BN, Cout;
+  // output geometry
+  int B, H, W, P, Rimg;                  // P = W+1, Rimg = (H+1)*P
+  int split, P2, Rimg2;                  // phase-split output geometry (consumer is a stride-2 block)
+  long long R2;
+  // epilogue
+  const float* bias; const float* act_scale; const float* act_shift;
+  const __half* res;                     // identity shortcut planes [2][R][Cout] or null
+  __half* out_raw; __half* out_act; float* out_dense;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 2000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t dst, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major shared-memory matrix descriptor (sm_100 format: version=1 at bit 46).
+// rows are kc*2 bytes (128 -> SWIZZLE_128B, 64 -> SWIZZLE_64B), 8-row groups are SBO apart.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int row_bytes) {
+  const uint64_t layout = (row_bytes == 128) ? 2ull : 4ull;      // SWIZZLE_128B : SWIZZLE_64B
+  const uint64_t sbo = (uint64_t)(8 * row_bytes) >> 4;
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// ------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapS,
+               const __grid_constant__ CUtensorMap mapWm, const __grid_constant__ CUtensorMap mapWs,
+               const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + TC_STAGES;
+  uint64_t* tfull_bar = empty_bar + TC_STAGES;      // [2] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;             // [2] accumulator drained
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_bias = reinterpret_cast<float*>(tmem_base_slot + 2);   // [Cout]
+  float* s_scale = s_bias + p.Cout;
+  float* s_shift = s_scale + p.Cout;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int BN = p.BN;
+  const uint32_t tmem_cols = (4 * BN <= 128) ? 128u : (4 * BN <= 256 ? 256u : 512u);   // 2 stages x (acc0, acc1)
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  for (int i = threadIdx.x; i < p.Cout; i += TC_THREADS) {
+    s_bias[i] = p.bias ? p.bias[i] : 0.f;
+    s_scale[i] = p.act_scale ? p.act_scale[i] : 1.f;
+    s_shift[i] = p.act_shift ? p.act_shift[i] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  const int n_main = p.ntaps * p.chunks_main;
+  const int n_ksteps = n_main + p.chunks_sc;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == 0) {
+    // ===================== TMA producer (one lane) =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+        const long long q0 = (long long)mt * TC_BM;
+        const int n0 = nt * BN;
+        for (int ks = 0; ks < n_ksteps; ++ks) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = smem + stage * TC_STAGE_BYTES;
+          const uint32_t a_hi = smem_u32(st), a_lo = a_hi + TC_PLANE_BYTES, b_hi = a_lo + TC_PLANE_BYTES, b_lo = b_hi + TC_PLANE_BYTES;
+          if (ks < n_main) {
+            const int tap = ks / p.chunks_main, ch = ks - tap * p.chunks_main;
+            const int kc = p.kc_main;
+            mbar_expect_tx(&full_bar[stage], (uint32_t)(2 * (TC_BM + BN) * kc * 2));
+            const int row = (int)(q0 + p.tap_row_off[tap]);
+            tma_load_3d(&mapA, a_hi, &full_bar[stage], ch * kc, row, p.tap_plane[tap]);
+            tma_load_3d(&mapA, a_lo, &full_bar[stage], ch * kc, row, p.tap_plane[tap] + 1);
+            const int kofs = ks * kc;
+            tma_load_3d(&mapWm, b_hi, &full_bar[stage], kofs, n0, 0);
+            tma_load_3d(&mapWm, b_lo, &full_bar[stage], kofs, n0, 1);
+          } else {
+            const int ch = ks - n_main;
+            const int kc = p.kc_sc;
+            mbar_expect_tx(&full_bar[stage], (uint32_t)(2 * (TC_BM + BN) * kc * 2));
+            tma_load_3d(&mapS, a_hi, &full_bar[stage], ch * kc, (int)q0, p.sc_plane);
+            tma_load_3d(&mapS, a_lo, &full_bar[stage], ch * kc, (int)q0, p.sc_plane + 1);
+            const int kofs = n_main * p.kc_main + ch * kc;
+            tma_load_3d(&mapWs, b_hi, &full_bar[stage], kofs, n0, 0);
+            tma_load_3d(&mapWs, b_lo, &full_bar[stage], kofs, n0, 1);
+          }
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one lane) =====================
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=f16, K-major both, N=BN, M=128
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(&tempty_bar[as], aphase ^ 1);            // epilogue drained this accumulator pair
+        tc_fence_after();
+        const uint32_t acc0 = tmem_base + (uint32_t)(as * 2 * BN);
+        const uint32_t acc1 = acc0 + (uint32_t)BN;
+        for (int ks = 0; ks < n_ksteps; ++ks) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const int kc = (ks < n_main) ? p.kc_main : p.kc_sc;
+          const int row_bytes = kc * 2;
+          uint8_t* st = smem + stage * TC_STAGE_BYTES;
+          const uint32_t a_hi = smem_u32(st), a_lo = a_hi + TC_PLANE_BYTES, b_hi = a_lo + TC_PLANE_BYTES, b_lo = b_hi + TC_PLANE_BYTES;
+          const uint64_t dah = make_desc(a_hi, row_bytes), dal = make_desc(a_lo, row_bytes);
+          const uint64_t dbh = make_desc(b_hi, row_bytes), dbl = make_desc(b_lo, row_bytes);
+          for (int kk = 0; kk < kc / 16; ++kk) {
+            const uint64_t adv = (uint64_t)(kk * 2);       // 32 bytes per UMMA_K=16 halves, in 16-byte units
+            const uint32_t first = (ks | kk) ? 1u : 0u;
+            umma_f16(acc0, dah + adv, dbh + adv, idesc, first);
+            umma_f16(acc1, dal + adv, dbh + adv, idesc, first);
+            umma_f16(acc1, dah + adv, dbl + adv, idesc, 1u);
+          }
+          umma_commit(&empty_bar[stage]);                  // frees the smem stage when these MMAs retire
+          if (ks == n_ksteps - 1) umma_commit(&tfull_bar[as]);
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (TMEM lane quadrant = warp % 4) =====================
+    const int quad = warp & 3;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+      const int n0 = nt * BN;
+      const long long q = (long long)mt * TC_BM + quad * 32 + lane;
+      // decode flat row -> (n, h, w)
+      bool valid = q < p.R;
+      int n = 0, h = 0, w = 0;
+      if (valid) {
+        n = (int)(q / p.Rimg);
+        const int rem = (int)(q - (long long)n * p.Rimg);
+        h = rem / p.P; w = rem - h * p.P;
+        valid = (h < p.H) && (w < p.W);
+      }
+      long long qo = q; long long Ro = p.R; int plane0 = 0;
+      if (p.split) {
+        qo = (long long)n * p.Rimg2 + (h >> 1) * p.P2 + (w >> 1);
+        Ro = p.R2;
+        plane0 = 2 * ((h & 1) * 2 + (w & 1));
+      }
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 2 * BN);
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r0[32], r1[32];
+        tmem_ld32(tbase + (uint32_t)c0, r0);
+        tmem_ld32(tbase + (uint32_t)(BN + c0), r1);
+        tmem_ld_wait();
+        if (valid) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            v[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]) * TC_LO_INV + s_bias[n0 + c0 + j];
+          if (p.res) {
+            const uint4* rh = reinterpret_cast<const uint4*>(p.res + (size_t)q * p.Cout + n0 + c0);
+            const uint4* rl = reinterpret_cast<const uint4*>(p.res + ((size_t)p.R + q) * p.Cout + n0 + c0);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 a = __ldg(rh + g), b = __ldg(rl + g);
+              const __half2* ah = reinterpret_cast<const __half2*>(&a);
+              const __half2* bl = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float2 fh = __half22float2(ah[e]), fl = __half22float2(bl[e]);
+                v[g * 8 + e * 2] += fh.x + fl.x * TC_LO_INV;
+                v[g * 8 + e * 2 + 1] += fh.y + fl.y * TC_LO_INV;
+              }
+            }
+          }
+          if (p.out_raw) {
+            uint4* oh = reinterpret_cast<uint4*>(p.out_raw + ((size_t)plane0 * Ro + qo) * p.Cout + n0 + c0);
+            uint4* ol = reinterpret_cast<uint4*>(p.out_raw + ((size_t)(plane0 + 1) * Ro + qo) * p.Cout + n0 + c0);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint32_t hh[4], ll[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float x0 = v[g * 8 + e * 2], x1 = v[g * 8 + e * 2 + 1];
+                __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+                hh[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                ll[e] = pack_half2((x0 - __half2float(h0)) * TC_LO_SCALE, (x1 - __half2float(h1)) * TC_LO_SCALE);
+              }
+              oh[g] = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+              ol[g] = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+            }
+          }
+          if (p.out_act || p.out_dense) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              v[j] = fmaxf(fmaf(v[j], s_scale[n0 + c0 + j], s_shift[n0 + c0 + j]), 0.f);
+          }
+          if (p.out_act) {
+            uint4* oh = reinterpret_cast<uint4*>(p.out_act + ((size_t)plane0 * Ro + qo) * p.Cout + n0 + c0);
+            uint4* ol = reinterpret_cast<uint4*>(p.out_act + ((size_t)(plane0 + 1) * Ro + qo) * p.Cout + n0 + c0);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint32_t hh[4], ll[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float x0 = v[g * 8 + e * 2], x1 = v[g * 8 + e * 2 + 1];
+                __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+                hh[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                ll[e] = pack_half2((x0 - __half2float(h0)) * TC_LO_SCALE, (x1 - __half2float(h1)) * TC_LO_SCALE);
+              }
+              oh[g] = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+              ol[g] = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+            }
+          }
+          if (p.out_dense) {
+            float4* od = reinterpret_cast<float4*>(p.out_dense + (((size_t)n * p.H + h) * p.W + w) * p.Cout + n0 + c0);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) od[g] = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  }
+  return fn;
+}
+
+// planes tensor [planes][rows][ch] fp16, box = (kc, box_rows, 1)
+static int make_map(CUtensorMap* map, const void* base, long long rows, int ch, int planes, int kc, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return SAR_ERR_UNSUPPORTED; }
+  cuuint64_t dims[3] = {(cuuint64_t)ch, (cuuint64_t)rows, (cuuint64_t)planes};
+  cuuint64_t strides[2] = {(cuuint64_t)ch * 2, (cuuint64_t)rows * ch * 2};
+  cuuint32_t box[3] = {(cuuint32_t)kc, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMapSwizzle sw = (kc * 2 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d): rows=%lld ch=%d planes=%d kc=%d box_rows=%d", (int)r, rows, ch, planes, kc, box_rows); return SAR_ERR_BAD_ARG; }
+  return SAR_OK;
+}
+
+static int pick_kc(int ch) { return (ch % 64 == 0) ? 64 : 32; }
+
+}  // namespace sar
+
+extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
+  using namespace sar;
+  SAR_REQUIRE(d, SAR_ERR_BAD_ARG, "sar_conv_tc_fwd: null descriptor");
+  SAR_REQUIRE(d->a && d->w && d->bias, SAR_ERR_BAD_ARG, "sar_conv_tc_fwd: null a/w/bias");
+  SAR_REQUIRE(d->ntaps >= 1 && d->ntaps <= 9, SAR_ERR_BAD_ARG, "sar_conv_tc_fwd: ntaps must be 1..9");
+  SAR_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->cout > 0 && d->a_ch > 0 && d->a_rows > 0, SAR_ERR_BAD_ARG,
+              "sar_conv_tc_fwd: non-positive dimension");
+  SAR_REQUIRE(d->a_ch % 32 == 0 && d->cout % 32 == 0 && (!d->s || d->s_ch % 32 == 0), SAR_ERR_UNSUPPORTED,
+              "sar_conv_tc_fwd: channel counts must be multiples of 32 (a_ch=%d s_ch=%d cout=%d)", d->a_ch, d->s_ch, d->cout);
+  SAR_REQUIRE(d->out_raw || d->out_act || d->out_dense, SAR_ERR_BAD_ARG, "sar_conv_tc_fwd: no output requested");
+  SAR_REQUIRE(!(d->out_act || d->out_dense) || (d->act_scale && d->act_shift), SAR_ERR_BAD_ARG,
+              "sar_conv_tc_fwd: activated outputs need act_scale/act_shift");
+  SAR_REQUIRE(aligned16(d->a) && aligned16(d->w) && (!d->s || aligned16(d->s)) && (!d->res || aligned16(d->res)) &&
+                  (!d->out_raw || aligned16(d->out_raw)) && (!d->out_act || aligned16(d->out_act)) &&
+                  (!d->out_dense || aligned16(d->out_dense)),
+              SAR_ERR_ALIGN, "sar_conv_tc_fwd: pointers must be 16-byte aligned");
+
+  TcParams p{};
+  p.ntaps = d->ntaps;
+  p.kc_main = pick_kc(d->a_ch);
+  p.chunks_main = d->a_ch / p.kc_main;
+  p.kc_sc = d->s ? pick_kc(d->s_ch) : 32;
+  p.chunks_sc = d->s ? d->s_ch / p.kc_sc : 0;
+  p.sc_plane = d->s_plane;
+  for (int t = 0; t < d->ntaps; ++t) {
+    p.tap_row_off[t] = d->tap_row_off[t];
+    p.tap_plane[t] = d->tap_plane[t];
+    SAR_REQUIRE(d->tap_plane[t] >= 0 && d->tap_plane[t] + 1 < d->a_planes, SAR_ERR_BAD_ARG, "sar_conv_tc_fwd: tap plane out of range");
+  }
+  p.B = d->B; p.H = d->H; p.W = d->W;
+  p.P = d->W + 1; p.Rimg = (d->H + 1) * p.P;
+  p.R = (long long)d->B * p.Rimg;
+  SAR_REQUIRE(p.R < (1ll << 31) - 4096, SAR_ERR_UNSUPPORTED, "sar_conv_tc_fwd: too many rows");
+  p.split = d->out_split ? 1 : 0;
+  p.P2 = (d->W + 1) / 2 + 1;
+  p.Rimg2 = ((d->H + 1) / 2 + 1) * p.P2;
+  p.R2 = (long long)d->B * p.Rimg2;
+  p.Cout = d->cout;
+  p.BN = (d->cout % 128 == 0) ? 128 : (d->cout % 64 == 0 ? 64 : 32);
+  p.m_tiles = (int)((p.R + TC_BM - 1) / TC_BM);
+  p.n_tiles = d->cout / p.BN;
+  p.bias = d->bias; p.act_scale = d->act_scale; p.act_shift = d->act_shift;
+  p.res = reinterpret_cast<const __half*>(d->res);
+  p.out_raw = reinterpret_cast<__half*>(d->out_raw);
+  p.out_act = reinterpret_cast<__half*>(d->out_act);
+  p.out_dense = d->out_dense;
+  SAR_REQUIRE(!(p.split && p.out_dense), SAR_ERR_BAD_ARG, "sar_conv_tc_fwd: dense output cannot be phase-split");
+
+  const int ktot = d->ntaps * d->a_ch + (d->s ? d->s_ch : 0);
+  CUtensorMap mapA, mapS, mapWm, mapWs;
+  int rc;
+  if ((rc = make_map(&mapA, d->a, d->a_rows, d->a_ch, d->a_planes, p.kc_main, TC_BM))) return rc;
+  if ((rc = make_map(&mapWm, d->w, d->cout, ktot, 2, p.kc_main, p.BN))) return rc;
+  if (d->s) {
+    SAR_REQUIRE(d->s_rows > 0 && d->s_planes >= 2 && d->s_plane >= 0 && d->s_plane + 1 < d->s_planes, SAR_ERR_BAD_ARG,
+                "sar_conv_tc_fwd: bad shortcut operand");
+    if ((rc = make_map(&mapS, d->s, d->s_rows, d->s_ch, d->s_planes, p.kc_sc, TC_BM))) return rc;
+    if ((rc = make_map(&mapWs, d->w, d->cout, ktot, 2, p.kc_sc, p.BN))) return rc;
+  } else {
+    mapS = mapA; mapWs = mapWm;
+  }
+  const size_t smem = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + 256 + 3 * (size_t)d->cout * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { set_error("sar_conv_tc_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int grid = tiles < sms ? tiles : sms;
+  conv_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(mapA, mapS, mapWm, mapWs, p);
+  return check_launch("sar_conv_tc_fwd");
+}

@@ -76,14 +76,119 @@ class ResNetDevice:
         return ops.affine_relu(a, s, t, relu=True)                             # resnet.py:178/196
 
 
+class ResNetTC:
+    """ResNet-18/34 front-end with the residual blocks on tcgen05 tensor cores.
+
+    stem 7x7/s2 (+BN+ReLU) : CUDA-core direct conv (Cin=1, K=49 is not GEMM-shaped)
+    max-pool 3x3/s2        : writes flat-pad hi/lo planes directly
+    every block conv       : csrc/conv_tc.cu; conv2 carries the shortcut (identity add or the 1x1
+                             projection as extra K-steps) and writes the NEXT block's inputs: the raw
+                             sum (its shortcut operand) and relu(bn1_next(.)) (its conv1 operand),
+                             phase-split when the next block is strided.  The last conv2 writes the
+                             final BN->ReLU map as dense fp32 (B,H',W',C) for CNN_LIN.
+    """
+
+    def __init__(self, plan: ResNetPlan, weights: Dict[str, np.ndarray], device):
+        from . import tc
+        self.tc = tc
+        self.plan = plan
+        self.device = device
+        self.p: Dict[str, torch.Tensor] = {}
+        self._bufs: Dict[tuple, list] = {}
+        self._rot: Dict[tuple, int] = {}
+        self.record_events = None
+
+        def put(name, arr, dtype=np.float32):
+            self.p[name] = torch.from_numpy(np.ascontiguousarray(arr, dtype=dtype)).to(device)
+
+        put("stem/kernel", weights[plan.stem.name + "/kernel"])
+        put("stem/bias", weights[plan.stem.name + "/bias"])
+        bns = [plan.stem.post_bn, plan.final_bn]
+        for b in plan.blocks:
+            bns += [x for x in (b.conv1.pre_bn, b.conv2.pre_bn) if x]
+            put(b.name + "/w1", tc.pack_weights(weights[b.conv1.name + "/kernel"]), np.float16)
+            put(b.name + "/b1", weights[b.conv1.name + "/bias"])
+            if b.short:
+                put(b.name + "/w2", tc.pack_weights(weights[b.conv2.name + "/kernel"], weights[b.short.name + "/kernel"]),
+                    np.float16)
+                put(b.name + "/b2", weights[b.conv2.name + "/bias"].astype(np.float64)
+                    + weights[b.short.name + "/bias"].astype(np.float64))
+            else:
+                put(b.name + "/w2", tc.pack_weights(weights[b.conv2.name + "/kernel"]), np.float16)
+                put(b.name + "/b2", weights[b.conv2.name + "/bias"])
+        for name in bns:
+            s, t = fold_bn(weights, name)
+            put(name + "/scale", s)
+            put(name + "/shift", t)
+
+    def bn(self, name):
+        return (self.p[name + "/scale"], self.p[name + "/shift"]) if name else None
+
+    def _buf(self, B, H, W, C, split, role):
+        """2-slot rotation of zero-initialised plane buffers per (geometry, role)."""
+        key = (B, H, W, C, bool(split), role)
+        if key not in self._bufs:
+            self._bufs[key] = [self.tc.alloc_planes(B, H, W, C, split, self.device) for _ in range(2)]
+            self._rot[key] = 0
+        self._rot[key] ^= 1
+        return self._bufs[key][self._rot[key]]
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """x (B,T,80,1) fp32 -> (B,H',W',C) fp32 after the final BN->ReLU."""
+        tc, pl, p = self.tc, self.plan, self.p
+        B = x.shape[0]
+        st = pl.stem
+        a = ops.conv2d(x, p["stem/kernel"], p["stem/bias"], stride=st.stride, pad_t=st.pad_t, pad_l=st.pad_l,
+                       out_hw=(st.hout, st.wout), post=self.bn(st.post_bn), act="relu")
+        first = pl.blocks[0]
+        cur = self._buf(B, pl.pool_hout, pl.pool_wout, st.cout, first.conv1.stride == 2, "raw")
+        assert not cur.split, "the first block is never strided"
+        tc.maxpool_planes(a, cur, 3, 2, pl.pool_pad_t, pl.pool_pad_l)
+        cur_act = cur_raw = cur
+        out_dense = None
+        ev = None
+        if self.record_events is not None:       # bench.py: device time of the block convolutions only
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+        for i, b in enumerate(pl.blocks):
+            nxt = pl.blocks[i + 1] if i + 1 < len(pl.blocks) else None
+            c1, c2 = b.conv1, b.conv2
+            c1_act = self._buf(B, c1.hout, c1.wout, c1.cout, False, "c1")
+            tc.conv_tc(cur_act, p[b.name + "/w1"], p[b.name + "/b1"], out_hw=(c1.hout, c1.wout),
+                       taps=tc.tap_table(3, 3, c1.stride, c1.pad_t, c1.pad_l, c1.wout), cout=c1.cout,
+                       out_act=c1_act, act=self.bn(c2.pre_bn))
+            taps2 = tc.tap_table(3, 3, 1, 1, 1, c2.wout)
+            if nxt is not None:
+                ns = nxt.conv1.stride == 2
+                nraw = self._buf(B, c2.hout, c2.wout, c2.cout, ns, "raw")
+                nact = self._buf(B, c2.hout, c2.wout, c2.cout, ns, "act")
+                tc.conv_tc(c1_act, p[b.name + "/w2"], p[b.name + "/b2"], out_hw=(c2.hout, c2.wout), taps=taps2,
+                           cout=c2.cout, short=cur_raw if b.short else None, res=None if b.short else cur_raw,
+                           out_raw=nraw, out_act=nact, act=self.bn(nxt.conv1.pre_bn))
+                cur_raw, cur_act = nraw, nact
+            else:
+                out_dense = torch.empty((B, c2.hout, c2.wout, c2.cout), device=self.device, dtype=torch.float32)
+                tc.conv_tc(c1_act, p[b.name + "/w2"], p[b.name + "/b2"], out_hw=(c2.hout, c2.wout), taps=taps2,
+                           cout=c2.cout, short=cur_raw if b.short else None, res=None if b.short else cur_raw,
+                           act=self.bn(pl.final_bn), out_dense=out_dense)
+        if ev is not None:
+            ev[1].record()
+            self.record_events.append(ev)
+        return out_dense
+
+
 class SARNetEngine:
-    def __init__(self, cfg: SARConfig, weights: Dict[str, np.ndarray], device="cuda"):
+    def __init__(self, cfg: SARConfig, weights: Dict[str, np.ndarray], device="cuda", conv_path: str = "tc"):
         if cfg.ar_enable and cfg.mto not in ("avg", "bigru", "vlad", "gvlad"):
             raise ValueError("Please specify avg/bigru/vlad/gvlad ..")          # model.py:136-138
         self.cfg = cfg
         self.device = torch.device(device)
         self.plan = cfg.plan()
-        self.resnet = ResNetDevice(self.plan, weights, self.device)
+        self.conv_path = conv_path
+        tc_ok = all(c.cin % 32 == 0 and c.cout % 32 == 0 for c in self.plan.convs()[1:])
+        if conv_path == "tc" and not tc_ok:
+            conv_path = self.conv_path = "ffma"   # channel counts not multiples of 32: CUDA-core kernel
+        self.resnet = (ResNetTC if conv_path == "tc" else ResNetDevice)(self.plan, weights, self.device)
         self.p: Dict[str, torch.Tensor] = {}
         self._prepare(weights)
 
@@ -178,11 +283,15 @@ class SARNetEngine:
             x = x.unsqueeze(-1)
         B = x.shape[0]
         out: Dict[str, torch.Tensor] = {}
-        raw = self.resnet.forward_raw(x)
         S, Cc = self.plan.seq_len, self.plan.cout
-        seq = raw.reshape(B, S, Cc)                                             # CNN2SEQ, model.py:252
-        # final ResNet BN->ReLU (resnet.py:178/196) fused as the input op of CNN_LIN
-        cnn = self.dense_ln(seq, "CNN_LIN", "CNN_LIN_LN", pre=self.resnet.bn(self.plan.final_bn))
+        if self.conv_path == "tc":
+            raw = self.resnet.forward(x)                                        # final BN->ReLU already applied
+            cnn = self.dense_ln(raw.reshape(B, S, Cc), "CNN_LIN", "CNN_LIN_LN")   # CNN2SEQ, model.py:252
+        else:
+            raw = self.resnet.forward_raw(x)
+            # final ResNet BN->ReLU (resnet.py:178/196) fused as the input op of CNN_LIN
+            cnn = self.dense_ln(raw.reshape(B, S, Cc), "CNN_LIN", "CNN_LIN_LN",
+                                pre=self.resnet.bn(self.plan.final_bn))
         crnn = ops.layernorm(self.bigru(cnn, "CRNN"), p["CRNN_LN/gamma"], p["CRNN_LN/beta"])
         if want_intermediates:
             out["resnet_raw"], out["cnn_lin"], out["crnn"] = raw, cnn, crnn

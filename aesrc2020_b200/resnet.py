@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from .config import SARConfig, resnet_plan
-from .engine import ResNetDevice
+from .engine import ResNetDevice, ResNetTC
 from . import weights as _w
 
 
@@ -32,7 +32,8 @@ def _run(res_type: str, input: torch.Tensor, filters: int, weights: Optional[Dic
     if weights is None:
         cfg = SARConfig(input_shape=(T, D, 1), res_type=res_type, res_filters=filters, mto="avg")
         weights = {k: v for k, v in _w.init_weights(cfg, seed).items() if k.startswith("resnet/")}
-    dev = ResNetDevice(plan, weights, input.device)
+    tc_ok = all(c.cin % 32 == 0 and c.cout % 32 == 0 for c in plan.convs()[1:])
+    dev = (ResNetTC if tc_ok else ResNetDevice)(plan, weights, input.device)
     return dev.forward(input.contiguous())
 
 

@@ -1,0 +1,166 @@
+"""Host side of the tensor-core residual-block path (csrc/conv_tc.cu, csrc/planes.cu):
+flat-pad hi/lo plane buffers, tap tables for TF-SAME stride-1/stride-2 3x3 convolutions,
+fp16 hi/lo weight packing, and the ctypes mirror of `sar_tc_conv` (include/sarnet.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _shim, ops
+from ._shim import check, ptr, stream_ptr
+
+LO_SCALE = 2048.0
+
+
+class sar_tc_conv(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p), ("a_rows", C.c_longlong), ("a_ch", C.c_int), ("a_planes", C.c_int),
+        ("ntaps", C.c_int), ("tap_row_off", C.c_int * 9), ("tap_plane", C.c_int * 9),
+        ("s", C.c_void_p), ("s_rows", C.c_longlong), ("s_ch", C.c_int), ("s_planes", C.c_int), ("s_plane", C.c_int),
+        ("w", C.c_void_p), ("cout", C.c_int),
+        ("bias", C.c_void_p),
+        ("res", C.c_void_p),
+        ("out_raw", C.c_void_p), ("out_act", C.c_void_p),
+        ("act_scale", C.c_void_p), ("act_shift", C.c_void_p),
+        ("out_dense", C.c_void_p),
+        ("out_split", C.c_int),
+        ("B", C.c_int), ("H", C.c_int), ("W", C.c_int),
+    ]
+
+
+@dataclass
+class Planes:
+    """A flat-pad hi/lo planes buffer (see include/sarnet.h) and its geometry."""
+    t: torch.Tensor          # (nplanes, rows, C) float16
+    B: int
+    H: int
+    W: int
+    C: int
+    split: bool
+
+    @property
+    def rows(self) -> int:
+        return int(self.t.shape[1])
+
+    @property
+    def nplanes(self) -> int:
+        return int(self.t.shape[0])
+
+
+def plane_rows(B: int, H: int, W: int, split: bool) -> int:
+    if split:
+        return B * ((H + 1) // 2 + 1) * ((W + 1) // 2 + 1)
+    return B * (H + 1) * (W + 1)
+
+
+def alloc_planes(B, H, W, Cc, split, device) -> Planes:
+    """Zero-initialised (pads must stay zero; kernels never write them)."""
+    n = 8 if split else 2
+    t = torch.zeros((n, plane_rows(B, H, W, split), Cc), device=device, dtype=torch.float16)
+    return Planes(t, B, H, W, Cc, bool(split))
+
+
+def pack(x: torch.Tensor, split=False, affine=None, relu=False, out: Optional[Planes] = None) -> Planes:
+    """dense fp32 NHWC (B,H,W,C) -> planes (sar_planes_pack_fwd)."""
+    x = x.contiguous()
+    B, H, W, Cc = x.shape
+    if out is None:
+        out = alloc_planes(B, H, W, Cc, split, x.device)
+    s, t = affine if affine is not None else (None, None)
+    check(_shim.lib().sar_planes_pack_fwd(ptr(x), ptr(s), ptr(t), 1 if relu else 0, ptr(out.t), B, H, W, Cc,
+                                          1 if out.split else 0, stream_ptr()), "sar_planes_pack_fwd")
+    ops._count(1)
+    return out
+
+
+def unpack(p: Planes) -> torch.Tensor:
+    x = torch.empty((p.B, p.H, p.W, p.C), device=p.t.device, dtype=torch.float32)
+    check(_shim.lib().sar_planes_unpack_fwd(ptr(p.t), ptr(x), p.B, p.H, p.W, p.C, 1 if p.split else 0, stream_ptr()),
+          "sar_planes_unpack_fwd")
+    ops._count(1)
+    return x
+
+
+def maxpool_planes(x: torch.Tensor, out: Planes, k, stride, pad_t, pad_l) -> Planes:
+    x = x.contiguous()
+    B, H, W, Cc = x.shape
+    check(_shim.lib().sar_maxpool_planes_fwd(ptr(x), ptr(out.t), B, H, W, Cc, out.H, out.W, k, stride, pad_t, pad_l,
+                                             stream_ptr()), "sar_maxpool_planes_fwd")
+    ops._count(1)
+    return out
+
+
+def pack_weights(kernel_hwio: np.ndarray, short_kernel: Optional[np.ndarray] = None) -> np.ndarray:
+    """Keras HWIO kernel (+ optional 1x1 projection kernel) -> [2][Cout][Ktot] fp16 hi/lo,
+    K-major with k = tap*Cin + ci and the shortcut's Cin_s rows appended."""
+    kh, kw, cin, cout = kernel_hwio.shape
+    wk = np.asarray(kernel_hwio, dtype=np.float32).reshape(kh * kw * cin, cout)
+    if short_kernel is not None:
+        wk = np.concatenate([wk, np.asarray(short_kernel, dtype=np.float32).reshape(-1, cout)], axis=0)
+    wt = np.ascontiguousarray(wk.T)                                  # (Cout, Ktot)
+    hi = wt.astype(np.float16)
+    lo = ((wt - hi.astype(np.float32)) * LO_SCALE).astype(np.float16)
+    return np.stack([hi, lo])
+
+
+def tap_table(kh: int, kw: int, stride: int, pad_t: int, pad_l: int, W_out: int) -> Tuple[list, list]:
+    """(row offsets, plane bases) per tap for a TF-SAME convolution on flat-pad planes.
+    stride 1: input is a plain planes tensor with the output geometry, tap (r,s) reads row
+              q + (r-pad_t)*(W+1) + (s-pad_l) of plane pair 0.
+    stride 2: input is phase-split; input row 2*ho + r - pad_t has parity a&1 and half-index
+              ho + (a>>1) with a = r - pad_t (same along w): plane pair (a_h&1)*2 + (a_w&1), row
+              offset (a_h>>1)*(W_out+1) + (a_w>>1)."""
+    P = W_out + 1
+    offs, planes = [], []
+    for r in range(kh):
+        for s in range(kw):
+            ah, aw = r - pad_t, s - pad_l
+            if stride == 1:
+                offs.append(ah * P + aw)
+                planes.append(0)
+            else:
+                assert stride == 2
+                offs.append((ah >> 1) * P + (aw >> 1))
+                planes.append(2 * ((ah & 1) * 2 + (aw & 1)))
+    return offs, planes
+
+
+def conv_tc(a: Planes, w_packed: torch.Tensor, bias: torch.Tensor, *, out_hw: Tuple[int, int], taps, cout: int,
+            short: Optional[Planes] = None, res: Optional[Planes] = None, out_raw: Optional[Planes] = None,
+            out_act: Optional[Planes] = None, act=None, out_dense: Optional[torch.Tensor] = None):
+    """sar_conv_tc_fwd.  taps = (row_offsets, plane_bases)."""
+    d = sar_tc_conv()
+    d.a, d.a_rows, d.a_ch, d.a_planes = ptr(a.t), a.rows, a.C, a.nplanes
+    offs, planes = taps
+    d.ntaps = len(offs)
+    for i, (o, pl) in enumerate(zip(offs, planes)):
+        d.tap_row_off[i] = int(o)
+        d.tap_plane[i] = int(pl)
+    if short is not None:
+        d.s, d.s_rows, d.s_ch, d.s_planes, d.s_plane = ptr(short.t), short.rows, short.C, short.nplanes, 0
+    d.w, d.cout = ptr(w_packed), cout
+    d.bias = ptr(bias)
+    H, W = out_hw
+    if res is not None:
+        assert not res.split and (res.H, res.W, res.C) == (H, W, cout)
+        d.res = ptr(res.t)
+    split = None
+    for o in (out_raw, out_act):
+        if o is not None:
+            assert (o.H, o.W, o.C) == (H, W, cout), ((o.H, o.W, o.C), (H, W, cout))
+            assert split is None or split == o.split
+            split = o.split
+    d.out_raw = ptr(out_raw.t) if out_raw is not None else None
+    d.out_act = ptr(out_act.t) if out_act is not None else None
+    if act is not None:
+        d.act_scale, d.act_shift = ptr(act[0]), ptr(act[1])
+    d.out_dense = ptr(out_dense) if out_dense is not None else None
+    d.out_split = 1 if split else 0
+    d.B, d.H, d.W = a.B, H, W
+    check(_shim.lib().sar_conv_tc_fwd(C.byref(d), stream_ptr()), "sar_conv_tc_fwd")
+    ops._count(1)

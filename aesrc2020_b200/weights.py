@@ -116,8 +116,18 @@ def init_weights(cfg: SARConfig, seed: int = 1234, degenerate: bool = False) -> 
     Dense, glorot/orthogonal-scale GRU) so activations stay O(1) through the network."""
     rng = np.random.RandomState(seed)
     out: Dict[str, np.ndarray] = {}
+    # A trained network's BN moving statistics track its activations.  The un-normalised
+    # residual stream of a pre-activation ResNet gains roughly one unit of variance per block, so
+    # the statistics of block j's leading BN (and of the final BN) are centred on that estimate --
+    # otherwise the synthetic stream grows ~2x per block and every downstream tanh saturates.
+    stream_var = {}
+    for j, b in enumerate(cfg.plan().blocks):
+        if b.conv1.pre_bn:
+            stream_var[b.conv1.pre_bn] = 1.0 + 0.6 * j
+    stream_var[cfg.plan().final_bn] = 1.0 + 0.6 * len(cfg.plan().blocks)
     for name, shp in weight_shapes(cfg).items():
         leaf = name.rsplit("/", 1)[1]
+        base_var = stream_var.get(name.rsplit("/", 1)[0], 1.0)
         if leaf == "kernel" and len(shp) == 4:
             fan_in = shp[0] * shp[1] * shp[2]
             w = rng.randn(*shp) * np.sqrt(2.0 / fan_in)
@@ -141,9 +151,9 @@ def init_weights(cfg: SARConfig, seed: int = 1234, degenerate: bool = False) -> 
         elif leaf == "beta":
             w = np.zeros(shp) if degenerate else rng.randn(*shp) * 0.1
         elif leaf == "moving_mean":
-            w = np.zeros(shp) if degenerate else rng.randn(*shp) * 0.1
+            w = np.zeros(shp) if degenerate else rng.randn(*shp) * 0.1 * np.sqrt(base_var)
         elif leaf == "moving_variance":
-            w = np.ones(shp) if degenerate else rng.uniform(0.6, 1.4, size=shp)
+            w = np.ones(shp) if degenerate else rng.uniform(0.6, 1.4, size=shp) * base_var
         else:
             raise KeyError(name)
         out[name] = np.ascontiguousarray(w, dtype=np.float32)

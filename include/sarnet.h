@@ -74,6 +74,54 @@ int sar_conv2d_fwd(const float* x, const float* w_hwio, const float* bias,
                    int B, int H, int W, int Cin, int Ho, int Wo, int Cout,
                    int kh, int kw, int stride, int pad_t, int pad_l, int act, void* stream);
 
+/* ---- tensor-core path of the residual blocks --------------------------------------------
+ * Activation layout "flat-pad hi/lo planes" (fp16): an (H,W,C) map of a batch of B is
+ *   planes[plane][q][c],  q = n*(H+1)*(W+1) + h*(W+1) + w,  R = B*(H+1)*(W+1) rows per plane,
+ * with ONE shared zero pad column (w == W) and pad row (h == H) per image; plane 0 = hi =
+ * fp16(x), plane 1 = lo = fp16((x - hi) * 2^11) (x == hi + lo/2048 to ~2^-22).  A tensor that
+ * feeds a stride-2 block is phase-split: 4 such pairs, plane = 2*((h&1)*2 + (w&1)) + {0,1},
+ * each over the geometry H2 = ceil(H/2), W2 = ceil(W/2).  Buffers must be zero-initialised once
+ * by the caller: kernels never write pad positions (that is what makes TF-SAME zero padding,
+ * including its asymmetric stride-2 form, a pure row shift). */
+size_t sar_planes_bytes(int B, int H, int W, int C, int split);
+
+/* dense fp32 NHWC -> planes, optionally y = relu?(scale[c]*x + shift[c]) first (_bn_relu,
+ * resnet.py:22-26).  C % 8 == 0. */
+int sar_planes_pack_fwd(const float* x, const float* scale, const float* shift, int relu, void* planes,
+                        int B, int H, int W, int C, int split, void* stream);
+/* planes -> dense fp32 NHWC (debug / tests / API boundary). */
+int sar_planes_unpack_fwd(const void* planes, float* x, int B, int H, int W, int C, int split, void* stream);
+/* MaxPooling2D(3x3, strides 2, 'same') (resnet.py:174,192) from dense fp32 NHWC into planes. */
+int sar_maxpool_planes_fwd(const float* x, void* planes, int B, int H, int W, int C, int Ho, int Wo,
+                           int k, int stride, int pad_t, int pad_l, void* stream);
+
+/* One residual-block convolution on tcgen05 tensor cores (csrc/conv_tc.cu).
+ * Replaces _bn_relu_conv / basic_block / _shortcut: resnet.py:47-65, 105-125, 67-89.
+ *   acc = sum_taps A[q + tap_row_off[t], plane tap_plane[t]] @ W_t  (+ S[q, s_plane] @ W_s)
+ *   v   = acc + bias (+ res[q])                         (Add(), resnet.py:89)
+ *   out_raw = v ; out_act / out_dense = relu(act_scale*v + act_shift)   (next layer's _bn_relu)
+ * a: planes of the ALREADY ACTIVATED conv input ([a_planes][a_rows][a_ch]); for a stride-2 conv
+ *    it is phase-split and tap_plane/tap_row_off select phase and shift per tap.
+ * s: planes of the RAW block input for the 1x1 projection shortcut (NULL = none).
+ * w: [2][cout][ntaps*a_ch + s_ch] fp16 hi/lo, K-major, k = tap*a_ch + ci (shortcut rows last).
+ * bias: conv bias (+ shortcut conv bias).  res: identity-shortcut planes [2][R][cout] or NULL.
+ * Outputs (any subset): out_raw / out_act planes (phase-split when out_split), out_dense fp32
+ * (B,H,W,cout).  All channel counts are multiples of 32. */
+typedef struct sar_tc_conv {
+  const void* a; long long a_rows; int a_ch; int a_planes;
+  int ntaps; int tap_row_off[9]; int tap_plane[9];
+  const void* s; long long s_rows; int s_ch; int s_planes; int s_plane;
+  const void* w; int cout;
+  const float* bias;
+  const void* res;
+  void* out_raw; void* out_act;
+  const float* act_scale; const float* act_shift;
+  float* out_dense;
+  int out_split;
+  int B, H, W;          /* output map geometry */
+} sar_tc_conv;
+int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream);
+
 /* MaxPooling2D(3x3, strides 2, 'same') -- resnet.py:174,192.  Padded cells never win. */
 int sar_maxpool2d_fwd(const float* x, float* out, int B, int H, int W, int C, int Ho, int Wo,
                       int k, int stride, int pad_t, int pad_l, void* stream);

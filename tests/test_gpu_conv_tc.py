@@ -1,0 +1,128 @@
+"""GPU parity of the tcgen05 residual-block convolution (csrc/conv_tc.cu) and the flat-pad
+hi/lo planes layout (csrc/planes.cu) against the float64 oracle's TF-SAME Conv2D."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import norm_err, t64, dev
+from oracle import sarnet_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _f32(a):
+    return np.asarray(a, dtype=np.float32).astype(np.float64)
+
+
+def test_planes_roundtrip_is_22_bits(cuda_device):
+    from aesrc2020_b200 import tc
+    rng = np.random.RandomState(0)
+    for split in (False, True):
+        for (H, W) in ((5, 4), (6, 3), (7, 7)):
+            x = dev(rng.randn(2, H, W, 32) * np.exp(rng.randn(2, H, W, 32) * 2))
+            p = tc.pack(x, split=split)
+            y = tc.unpack(p)
+            # 2^-22 relative for fp16-normal magnitudes (below ~1e-3 the lo plane goes subnormal:
+            # absolute error stays < 2^-25)
+            assert float(((y - x).abs() / x.abs().clamp_min(1e-3)).max()) < 2.0 ** -21
+            # pads and never-written phase rows stay exactly zero
+            assert float(p.t.float().abs().sum()) > 0
+    x = dev(rng.randn(1, 3, 3, 8))
+    s, t = dev(rng.rand(8) + 0.5), dev(rng.randn(8))
+    y = tc.unpack(tc.pack(x, affine=(s, t), relu=True))
+    assert norm_err(y, torch.relu(x * s + t)) < 1e-6
+
+
+def _case(B, H, W, Cin, Cout, stride, *, residual=False, proj=None, out_split=False, dense=False, seed=0):
+    """One conv_tc launch vs oracle.  proj = Cin_s: add a 1x1 projection shortcut (stride `proj_stride`
+    given by the geometry of the raw tensor) folded into the same accumulator."""
+    from aesrc2020_b200 import tc
+    from aesrc2020_b200.config import same_pad
+    rng = np.random.RandomState(seed + H * 7 + Cin)
+    x = _f32(rng.randn(B, H, W, Cin))                       # activated conv input
+    w = _f32(rng.randn(3, 3, Cin, Cout) * np.sqrt(2.0 / (9 * Cin)))
+    b = _f32(rng.randn(Cout) * 0.1)
+    Ho, pt, _ = same_pad(H, 3, stride)
+    Wo, pl, _ = same_pad(W, 3, stride)
+    want = O.conv2d(t64(x), t64(w), t64(b), stride, "same")
+    a = tc.pack(dev(x), split=(stride == 2))
+    short = None
+    wk = None
+    bias = b.copy()
+    if proj is not None:
+        cs, s_stride = proj
+        Hs, Ws = (Ho, Wo) if s_stride == 1 else (2 * Ho - (rng.randint(0, 2)), 2 * Wo - (rng.randint(0, 2)))
+        xs = _f32(rng.randn(B, Hs, Ws, cs))                 # RAW block input of the projection shortcut
+        wk = _f32(rng.randn(1, 1, cs, Cout) * np.sqrt(2.0 / cs))
+        bs = _f32(rng.randn(Cout) * 0.1)
+        sc = O.conv2d(t64(xs), t64(wk), t64(bs), s_stride, "valid")
+        assert tuple(sc.shape) == tuple(want.shape)
+        want = want + sc
+        bias = bias + bs
+        short = tc.pack(dev(xs), split=(s_stride == 2))
+    res = None
+    if residual:
+        r = _f32(rng.randn(B, Ho, Wo, Cout))
+        want = want + t64(r)
+        res = tc.pack(dev(r))
+    qs, qt = _f32(rng.rand(Cout) + 0.5), _f32(rng.randn(Cout) * 0.3)
+    want_act = torch.relu(want * t64(qs) + t64(qt))
+    out_raw = tc.alloc_planes(B, Ho, Wo, Cout, out_split, "cuda")
+    out_act = tc.alloc_planes(B, Ho, Wo, Cout, out_split, "cuda")
+    od = torch.zeros((B, Ho, Wo, Cout), device="cuda") if dense else None
+    tc.conv_tc(a, torch.from_numpy(tc.pack_weights(w, wk)).cuda(), dev(bias), out_hw=(Ho, Wo),
+               taps=tc.tap_table(3, 3, stride, pt, pl, Wo), cout=Cout, short=short, res=res,
+               out_raw=out_raw, out_act=out_act, act=(dev(qs), dev(qt)), out_dense=None if out_split else od)
+    torch.cuda.synchronize()
+    e_raw = norm_err(tc.unpack(out_raw), want)
+    e_act = norm_err(tc.unpack(out_act), want_act)
+    # tensor-core fp32 accumulation truncates: error grows ~1.2e-9 * K (K = 9*Cin up to 2304)
+    assert e_raw < 1e-5 and e_act < 1e-5, (e_raw, e_act)
+    if dense and not out_split:
+        assert norm_err(od, want_act) < 1e-5
+    # pad positions were never written (they are the zero padding of the next convolution)
+    if not out_split:
+        P, Rimg = Wo + 1, (Ho + 1) * (Wo + 1)
+        q = torch.arange(out_act.rows, device="cuda")
+        pad = ((q % Rimg) // P == Ho) | (q % P == Wo)
+        assert float(out_act.t[:, pad].float().abs().max()) == 0.0
+        assert float(out_raw.t[:, pad].float().abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [
+    (2, 13, 20, 32, 32),      # thin stage 1: kc=32 (SWIZZLE_64B), BN=32
+    (3, 9, 10, 64, 64),       # stage 2: kc=64 (SWIZZLE_128B), BN=64
+    (2, 7, 5, 128, 128),      # stage 3: BN=128
+    (2, 5, 3, 256, 256),      # stage 4: two N tiles
+    (1, 25, 20, 64, 32),      # s1b1.conv1 of thin res34 (Cin=64 -> 32)
+])
+def test_conv3x3_stride1(cuda_device, B, H, W, Cin, Cout):
+    _case(B, H, W, Cin, Cout, 1, dense=True)
+
+
+def test_conv3x3_identity_residual(cuda_device):
+    _case(2, 11, 10, 64, 64, 1, residual=True)
+    _case(2, 6, 3, 256, 256, 1, residual=True, dense=True)
+
+
+@pytest.mark.parametrize("H,W", [(25, 20), (26, 11), (13, 5), (8, 6)])
+def test_conv3x3_stride2_phase_split(cuda_device, H, W):
+    """TF-SAME stride 2: even sizes pad (0,1), odd sizes pad (1,1) -- both through phase planes."""
+    _case(2, H, W, 32, 64, 2)
+    _case(1, H, W, 64, 128, 2)
+
+
+def test_projection_shortcut_folded_into_accumulator(cuda_device):
+    _case(2, 13, 10, 64, 64, 1, proj=(32, 2))        # s2b1: conv2 (kc=64) + 1x1/s2 shortcut on 32 ch (kc=32)
+    _case(2, 7, 5, 128, 128, 1, proj=(64, 2))        # s3b1
+    _case(2, 25, 20, 32, 32, 1, proj=(64, 1))        # s1b1 of thin res34: 1x1/s1 projection 64 -> 32
+
+
+def test_outputs_phase_split_for_a_strided_consumer(cuda_device):
+    _case(2, 13, 10, 64, 64, 1, residual=True, out_split=True)
+    _case(2, 12, 7, 32, 32, 1, out_split=True)
+
+
+def test_many_tiles_persistent_loop(cuda_device):
+    """More tiles than SMs: every CTA loops, the TMEM accumulator pair double-buffers."""
+    _case(48, 125, 20, 32, 32, 1)                     # 48*126*21/128 = 993 tiles

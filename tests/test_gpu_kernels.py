@@ -61,7 +61,7 @@ def test_maxpool_same(cuda_device):
     from aesrc2020_b200.config import same_pad
     rng = np.random.RandomState(1)
     for H, W in ((150, 40), (11, 7)):
-        x = rng.randn(2, H, W, 8) - 2.0          # negative values: padded cells must never win
+        x = (rng.randn(2, H, W, 8) - 2.0).astype(np.float32).astype(np.float64)   # negative: padded cells must never win
         want = O.maxpool_same(t64(x))
         Ho, pt, _ = same_pad(H, 3, 2)
         Wo, pl, _ = same_pad(W, 3, 2)
@@ -225,7 +225,7 @@ def test_ctc_vs_oracle(cuda_device, S, C, Lmax):
     lab_len[2] = min(Lmax, S // 2)
     labels[2, :lab_len[2]] = rng.randint(0, C - 1, lab_len[2])
     in_len = np.full(B, S, np.int32)
-    in_len[3] = max(S - 3, 2 * int(lab_len[3]) + 1)  # shorter input_length (API allows it)
+    in_len[3] = min(S, max(S - 3, 2 * int(lab_len[3]) + 1))  # shorter input_length (API allows it)
     probs = torch.softmax(t64(logits), -1)
     want = O.ctc_batch_cost(t64(labels), probs, in_len, lab_len)
     loss, status, p = ops.ctc(dev(logits), dev(labels), torch.from_numpy(in_len).cuda(), torch.from_numpy(lab_len).cuda(),
