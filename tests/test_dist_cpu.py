@@ -1,0 +1,54 @@
+"""The N>1 host logic on CPU: world_size-2 gloo run of the loss-vector all-reduce and the
+multi_gpu_model split rule (model.py:193-194)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from aesrc2020_b200 import dist as sdist
+from aesrc2020_b200.config import SARConfig
+
+
+def test_shard_slice_is_multi_gpu_model_rule():
+    for n, g in ((64, 2), (65, 4), (7, 8), (4096, 8)):
+        parts = [sdist.shard_slice(n, r, g) for r in range(g)]
+        idx = np.concatenate([np.arange(n)[s] for s in parts])
+        assert np.array_equal(idx, np.arange(n))
+        sizes = [len(np.arange(n)[s]) for s in parts]
+        assert all(s == n // g for s in sizes[:-1]) and sizes[-1] == n - (g - 1) * (n // g)
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    env = sdist.init_from_env(backend="gloo")
+    assert env["world_size"] == world
+    rng = np.random.RandomState(0)
+    stats = rng.rand(10, 8).astype(np.float32)               # per-utterance contributions of a global batch of 10
+    stats[:, 6] = 1.0
+    sl = sdist.shard_slice(10, rank, world)
+    vec = torch.from_numpy(stats[sl].sum(0))
+    vec = sdist.all_reduce_loss_vector(vec)
+    if rank == 0:
+        np.save(out, vec.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_loss_vector_allreduce_gloo_world2(tmp_path):
+    out = str(tmp_path / "v.npy")
+    port = 29500 + (os.getpid() % 2000)
+    mp.start_processes(_worker, args=(2, port, out), nprocs=2, join=True, start_method="spawn")
+    got = np.load(out)
+    rng = np.random.RandomState(0)
+    stats = rng.rand(10, 8).astype(np.float32)
+    stats[:, 6] = 1.0
+    assert np.allclose(got, stats.sum(0), rtol=1e-6)
+    cfg = SARConfig(ctc_enable=True, disc_enable=True, mto="gvlad", metric_loss="circleloss")
+    m = sdist.loss_vector_to_metrics(got, cfg)
+    assert m["count"] == 10 and abs(m["y_ctc_loss_loss"] - stats[:, 2].mean()) < 1e-6
+    want_total = 0.01 * stats[:, 0].mean() + 0.6 * stats[:, 1].mean() + 0.01 * stats[:, 2].mean()
+    assert abs(m["loss"] - want_total) < 1e-6                # model.py:344-367 weights (Q5)
