@@ -1,77 +1,207 @@
 // bigru.cu -- recurrent step loop of Bidirectional(CuDNNGRU) (model.py:44-50).
 //
-// The input projections x*W + b_input of all S steps and both directions are one GEMM done
-// by the caller (sar_conv2d_fwd against the concatenated [forward | backward] kernels); this
-// kernel runs the S strictly sequential steps
+// The input projections x*W + b_input of all S steps and both directions are one GEMM done by
+// the caller (sar_conv2d_fwd against the concatenated [forward | backward] kernels); this kernel
+// runs the S strictly sequential steps
 //     hp = h @ U + b_rec                                   (u x 3u, gate order z|r|h)
 //     z = sigmoid(xz + hpz)   r = sigmoid(xr + hpr)   hh = tanh(xh + r * hph)
 //     h' = z*h + (1-z)*hh                                  (reset_after / cuDNN form)
-// as ONE persistent launch: a CTA owns BG utterances of one direction for the whole sequence,
-// h stays in shared memory, thread c owns recurrent column c (3u = 768 threads), the
-// recurrent kernel is streamed from L2 each step (coalesced rows).  Both directions run
-// concurrently (blockIdx.y).
+// as ONE persistent launch.  A thread-block CLUSTER of 8 CTAs owns 8 utterances of one direction
+// for the whole sequence:
+//   * the recurrent kernel U (256 x 768 fp32 = 786 KB) is split by hidden unit: CTA r owns units
+//     [32r, 32r+32) = 96 columns (z, r and h of each unit) and keeps its 256 x 96 slice in
+//     REGISTERS for all S steps (thread = 4 columns x 16 k's = 64 registers), so no weight byte
+//     moves after the prologue;
+//   * h (8 x 256) lives in every CTA's shared memory, double buffered, laid out so that the 16
+//     k-slices of a warp read conflict-free 128-bit rows; a thread reads 16 rows x 8 utterances
+//     (512 B) per step for 512 FMAs -- shared-memory and FMA pipes are balanced;
+//   * the 16 k-slice partials are combined by a recursive-halving shuffle reduction (30 shuffles
+//     for 32 values, each lane ends owning 2 complete sums);
+//   * after the gates each CTA pushes its 32 new units into all 8 CTAs' next h buffer through
+//     distributed shared memory; a split cluster barrier (arrive.release ... wait.acquire)
+//     publishes the step while the x-projections of step t+2 are being prefetched;
+//   * outputs are staged in shared memory and written to HBM once, coalesced, after the loop (no
+//     global store sits in front of the per-step release).
+// Both directions and all utterance groups run concurrently (grid = 8 * groups * 2 CTAs).
+#include <cooperative_groups.h>
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace sar {
 
 constexpr int GRU_U = 256;
-constexpr int GRU_BG = 4;      // utterances per CTA
+constexpr int GRU_BG = 8;                        // utterances per cluster
+constexpr int GRU_CL = 8;                        // CTAs per cluster
+constexpr int GRU_UPC = GRU_U / GRU_CL;          // 32 hidden units per CTA
+constexpr int GRU_COLS = 3 * GRU_UPC;            // 96 recurrent columns per CTA
+constexpr int GRU_CPT = 4;                       // columns per thread
+constexpr int GRU_KQ = 16;                       // k-slices
+constexpr int GRU_KPT = GRU_U / GRU_KQ;          // 16 k's per thread
+constexpr int GRU_THREADS = (GRU_COLS / GRU_CPT) * GRU_KQ;   // 384
+constexpr int GRU_HSTRIDE = GRU_KPT * GRU_BG + 4;            // 132 floats: +4 banks per k-slice
+constexpr int GRU_HBUF = GRU_KQ * GRU_HSTRIDE;               // floats per h buffer
 
-__global__ void __launch_bounds__(3 * GRU_U) bigru_kernel(const float* __restrict__ xp, const float* __restrict__ rec,
-                                                           const float* __restrict__ rbias, float* __restrict__ out,
-                                                           int B, int S, int seq) {
-  constexpr int U = GRU_U, U3 = 3 * GRU_U, BG = GRU_BG;
-  __shared__ __align__(16) float hs[BG][U];
-  __shared__ float hp[BG][U3];
+__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
-  const int c = threadIdx.x;            // recurrent column 0..767
-  const int dir = blockIdx.y;           // 0 forward, 1 backward
-  const int b0 = blockIdx.x * BG;
+__global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1)
+bigru_kernel(const float* __restrict__ xp, const float* __restrict__ rec, const float* __restrict__ rbias,
+             float* __restrict__ out, int B, int S, int seq, int stage_out) {
+  constexpr int U = GRU_U, U3 = 3 * GRU_U;
+  __shared__ __align__(16) float h_s[2 * GRU_HBUF];                 // [buf][kq][i][b]
+  __shared__ __align__(16) float hp_s[GRU_COLS][GRU_BG];
+  extern __shared__ __align__(16) float out_s[];                    // [S][gb][gj] when stage_out
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int cid = blockIdx.x / GRU_CL;
+  const int dir = cid & 1;
+  const int b0 = (cid >> 1) * GRU_BG;
+  const int t = threadIdx.x, lane = t & 31;
+  const int j0 = rank * GRU_UPC;
+
+  // ---- prologue: my 4 columns x 16 k's of the recurrent kernel -> registers
+  const int kq = lane & 15;                               // k-slice
+  const int cgp = (t >> 5) * 2 + (lane >> 4);             // column group 0..23
   const float* Ud = rec + (size_t)dir * U * U3;
-  const float rb = __ldg(rbias + dir * U3 + c);
+  float u[GRU_CPT][GRU_KPT];
+#pragma unroll
+  for (int c = 0; c < GRU_CPT; ++c) {
+    const int cc = cgp * GRU_CPT + c;                     // column within CTA: gate = cc/32, unit = cc%32
+    const int col = (cc / GRU_UPC) * U + j0 + (cc % GRU_UPC);
+#pragma unroll
+    for (int i = 0; i < GRU_KPT; ++i) u[c][i] = __ldg(Ud + (size_t)(kq * GRU_KPT + i) * U3 + col);
+  }
+  // after the reduction this lane owns column cgp*4 + (kq>>2), utterances (kq&3)*2 + {0,1}
+  const int red_col = cgp * GRU_CPT + (kq >> 2);
+  const int red_b = (kq & 3) * 2;
 
-  for (int i = c; i < BG * U; i += U3) (&hs[0][0])[i] = 0.f;
-  __syncthreads();
+  // gate-phase role: thread -> (unit gj, utterance gb)
+  const bool gate_thread = t < GRU_UPC * GRU_BG;          // 256 threads
+  const int gj = t >> 3, gb = t & 7;                     // gb fastest: a warp's DSMEM push is one 128 B row
+  const int unit = j0 + gj;
+  const bool bvalid = gate_thread && (b0 + gb) < B;
+  float rbz = 0.f, rbr = 0.f, rbh = 0.f;
+  if (gate_thread) {
+    rbz = __ldg(rbias + dir * U3 + unit);
+    rbr = __ldg(rbias + dir * U3 + U + unit);
+    rbh = __ldg(rbias + dir * U3 + 2 * U + unit);
+  }
+  const int hpos = (unit / GRU_KPT) * GRU_HSTRIDE + (unit % GRU_KPT) * GRU_BG + gb;
 
+  for (int i = t; i < 2 * GRU_HBUF; i += GRU_THREADS) h_s[i] = 0.f;
+  float* remote[GRU_CL];
+#pragma unroll
+  for (int r = 0; r < GRU_CL; ++r) remote[r] = cluster.map_shared_rank(h_s, r);
+
+  auto xrow = [&](int step) {
+    const int tt = dir ? (S - 1 - step) : step;
+    return xp + (((size_t)(b0 + gb) * S + tt) * 2 + dir) * U3 + unit;
+  };
+  // x-projection operands of steps `step` (x0) and `step+1` (x1) live in registers
+  float x0z = 0.f, x0r = 0.f, x0h = 0.f, x1z = 0.f, x1r = 0.f, x1h = 0.f;
+  if (bvalid) {
+    const float* p = xrow(0); x0z = __ldg(p); x0r = __ldg(p + U); x0h = __ldg(p + 2 * U);
+    if (S > 1) { const float* q = xrow(1); x1z = __ldg(q); x1r = __ldg(q + U); x1h = __ldg(q + 2 * U); }
+  }
+  cluster.sync();
+
+  int cur = 0;
   for (int step = 0; step < S; ++step) {
-    const int t = dir ? (S - 1 - step) : step;
-    // ---- hp[b][c] = sum_k h[b][k] * U[k][c] + b_rec[c]
-    float acc[BG];
+    // ---- partial dot products: 4 columns x 16 k's x 8 utterances
+    float v[GRU_CPT * GRU_BG];
 #pragma unroll
-    for (int b = 0; b < BG; ++b) acc[b] = 0.f;
-#pragma unroll 8
-    for (int k = 0; k < U; k += 4) {
-      float u0 = __ldg(Ud + (size_t)(k + 0) * U3 + c);
-      float u1 = __ldg(Ud + (size_t)(k + 1) * U3 + c);
-      float u2 = __ldg(Ud + (size_t)(k + 2) * U3 + c);
-      float u3 = __ldg(Ud + (size_t)(k + 3) * U3 + c);
+    for (int i = 0; i < GRU_CPT * GRU_BG; ++i) v[i] = 0.f;
+    const float* hq = h_s + cur * GRU_HBUF + kq * GRU_HSTRIDE;
 #pragma unroll
-      for (int b = 0; b < BG; ++b) {
-        float4 h4 = *reinterpret_cast<const float4*>(&hs[b][k]);
-        acc[b] = fmaf(h4.x, u0, acc[b]);
-        acc[b] = fmaf(h4.y, u1, acc[b]);
-        acc[b] = fmaf(h4.z, u2, acc[b]);
-        acc[b] = fmaf(h4.w, u3, acc[b]);
+    for (int i = 0; i < GRU_KPT; ++i) {
+      const float4 ha = *reinterpret_cast<const float4*>(hq + i * GRU_BG);
+      const float4 hb = *reinterpret_cast<const float4*>(hq + i * GRU_BG + 4);
+      const float hv[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+#pragma unroll
+      for (int c = 0; c < GRU_CPT; ++c)
+#pragma unroll
+        for (int b = 0; b < GRU_BG; ++b) v[c * GRU_BG + b] = fmaf(u[c][i], hv[b], v[c * GRU_BG + b]);
+    }
+    // ---- recursive-halving reduction over the 16 k-slices (lanes kq = lane & 15)
+    float w1[16], w2[8], w3[4], w4[2];
+    {
+      const bool up = (kq & 8) != 0;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float send = up ? v[i] : v[i + 16], keep = up ? v[i + 16] : v[i];
+        w1[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
       }
     }
+    {
+      const bool up = (kq & 4) != 0;
 #pragma unroll
-    for (int b = 0; b < BG; ++b) hp[b][c] = acc[b] + rb;
-    __syncthreads();
-    // ---- gates: BG*U items over 768 threads
-    for (int i = c; i < BG * U; i += U3) {
-      const int b = i / U, j = i - b * U;
-      if (b0 + b < B) {
-        const float* xrow = xp + (((size_t)(b0 + b) * S + t) * 2 + dir) * U3;
-        float z = sigmoidf_(__ldg(xrow + j) + hp[b][j]);
-        float r = sigmoidf_(__ldg(xrow + U + j) + hp[b][U + j]);
-        float hh = tanhf(__ldg(xrow + 2 * U + j) + r * hp[b][2 * U + j]);
-        float hn = z * hs[b][j] + (1.f - z) * hh;
-        hs[b][j] = hn;
-        if (seq) out[((size_t)(b0 + b) * S + t) * (2 * U) + dir * U + j] = hn;
-        else if (step == S - 1) out[(size_t)(b0 + b) * (2 * U) + dir * U + j] = hn;
+      for (int i = 0; i < 8; ++i) {
+        const float send = up ? w1[i] : w1[i + 8], keep = up ? w1[i + 8] : w1[i];
+        w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
       }
     }
+    {
+      const bool up = (kq & 2) != 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float send = up ? w2[i] : w2[i + 4], keep = up ? w2[i + 4] : w2[i];
+        w3[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+      }
+    }
+    {
+      const bool up = (kq & 1) != 0;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float send = up ? w3[i] : w3[i + 2], keep = up ? w3[i + 2] : w3[i];
+        w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+      }
+    }
+    *reinterpret_cast<float2*>(&hp_s[red_col][red_b]) = make_float2(w4[0], w4[1]);
     __syncthreads();
+
+    // ---- gates for my 32 units x 8 utterances, push h' to every CTA of the cluster
+    if (gate_thread) {
+      const float z = sigmoidf_(x0z + hp_s[gj][gb] + rbz);
+      const float r = sigmoidf_(x0r + hp_s[GRU_UPC + gj][gb] + rbr);
+      const float hh = tanhf(x0h + r * (hp_s[2 * GRU_UPC + gj][gb] + rbh));
+      const float hold = h_s[cur * GRU_HBUF + hpos];
+      const float hn = z * hold + (1.f - z) * hh;
+      const int nxt_off = (cur ^ 1) * GRU_HBUF + hpos;
+#pragma unroll
+      for (int r2 = 0; r2 < GRU_CL; ++r2) remote[r2][nxt_off] = hn;
+      if (stage_out) {
+        if (seq) out_s[(size_t)step * (GRU_UPC * GRU_BG) + t] = hn;
+        else if (step == S - 1) out_s[t] = hn;
+      } else if (bvalid) {
+        const int tt = dir ? (S - 1 - step) : step;
+        if (seq) out[((size_t)(b0 + gb) * S + tt) * (2 * U) + dir * U + unit] = hn;
+        else if (step == S - 1) out[(size_t)(b0 + gb) * (2 * U) + dir * U + unit] = hn;
+      }
+    }
+    cluster_arrive_release();            // publishes my DSMEM stores (no global store is pending)
+    // rotate the x-projection registers and prefetch step+2 while the barrier completes
+    x0z = x1z; x0r = x1r; x0h = x1h;
+    if (bvalid && step + 2 < S) { const float* p = xrow(step + 2); x1z = __ldg(p); x1r = __ldg(p + U); x1h = __ldg(p + 2 * U); }
+    cluster_wait_acquire();
+    cur ^= 1;
+  }
+
+  // ---- write the staged outputs: 32 consecutive units (128 B) per (step, utterance)
+  if (stage_out && gate_thread) {
+    const int oj = t & 31, ob = t >> 5;                    // unit fastest for coalesced global stores
+    if (b0 + ob < B) {
+      if (seq) {
+        for (int step = 0; step < S; ++step) {
+          const int tt = dir ? (S - 1 - step) : step;
+          out[((size_t)(b0 + ob) * S + tt) * (2 * U) + dir * U + j0 + oj] =
+              out_s[(size_t)step * (GRU_UPC * GRU_BG) + oj * GRU_BG + ob];
+        }
+      } else {
+        out[(size_t)(b0 + ob) * (2 * U) + dir * U + j0 + oj] = out_s[oj * GRU_BG + ob];
+      }
+    }
   }
 }
 
@@ -83,7 +213,13 @@ extern "C" int sar_bigru_fwd(const float* xp, const float* rec, const float* rbi
   SAR_REQUIRE(xp && rec && rbias && out, SAR_ERR_BAD_ARG, "sar_bigru_fwd: null pointer");
   SAR_REQUIRE(B > 0 && S > 0, SAR_ERR_BAD_ARG, "sar_bigru_fwd: non-positive dimension");
   SAR_REQUIRE(u == GRU_U, SAR_ERR_UNSUPPORTED, "sar_bigru_fwd: hidden size %d unsupported (this build: %d)", u, GRU_U);
-  dim3 grid((B + GRU_BG - 1) / GRU_BG, 2);
-  bigru_kernel<<<grid, 3 * GRU_U, 0, (cudaStream_t)stream>>>(xp, rec, rbias, out, B, S, seq);
+  const int groups = (B + GRU_BG - 1) / GRU_BG;
+  dim3 grid(GRU_CL * groups * 2);
+  size_t smem = seq ? (size_t)S * GRU_UPC * GRU_BG * sizeof(float) : (size_t)GRU_UPC * GRU_BG * sizeof(float);
+  int stage_out = 1;
+  if (smem > 180 * 1024) { smem = 0; stage_out = 0; }      // very long sequences: write through
+  cudaError_t e = cudaFuncSetAttribute(bigru_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(180 * 1024));
+  if (e != cudaSuccess) { set_error("sar_bigru_fwd: %s", cudaGetErrorString(e)); return (int)e; }
+  bigru_kernel<<<grid, GRU_THREADS, smem, (cudaStream_t)stream>>>(xp, rec, rbias, out, B, S, seq, stage_out);
   return check_launch("sar_bigru_fwd");
 }

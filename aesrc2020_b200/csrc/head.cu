@@ -55,8 +55,8 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(HeadP p) {
   extern __shared__ __align__(16) float sm[];
   float* x = sm;                         // [max(D,Dd)]
   float* h1 = x + max(p.D, p.Dd);        // [H1]
-  float* h2 = h1 + p.H1;                 // [H2]
-  float* la = h2 + p.H2;                 // [n] accent logits
+  float* h2 = h1 + p.H1;                 // [H2]   (h1|h2 region is at least HEAD_THREADS floats)
+  float* la = h1 + max(p.H1 + p.H2, HEAD_THREADS);   // [n] accent logits
   float* ld = la + HEAD_MAXC;            // [n] disc cos / logits
   float* wn = ld + HEAD_MAXC;            // [n] column norms^2
   float* scratch = wn + HEAD_MAXC;       // [32]
@@ -68,9 +68,15 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(HeadP p) {
     for (int d = t; d < p.D; d += HEAD_THREADS) x[d] = __ldg(p.emb + (size_t)b * p.D + d);
     __syncthreads();
     for (int j = t; j < p.H1; j += HEAD_THREADS) {
-      float acc = __ldg(p.b1 + j);
-      for (int d = 0; d < p.D; ++d) acc = fmaf(x[d], __ldg(p.w1 + (size_t)d * p.H1 + j), acc);
-      h1[j] = fmaxf(acc, 0.f);
+      float acc = __ldg(p.b1 + j), acc2 = 0.f;
+      int d = 0;
+#pragma unroll 8
+      for (; d + 1 < p.D; d += 2) {          // two chains, loads batched by the unroll
+        acc = fmaf(x[d], __ldg(p.w1 + (size_t)d * p.H1 + j), acc);
+        acc2 = fmaf(x[d + 1], __ldg(p.w1 + (size_t)(d + 1) * p.H1 + j), acc2);
+      }
+      if (d < p.D) acc = fmaf(x[d], __ldg(p.w1 + (size_t)d * p.H1 + j), acc);
+      h1[j] = fmaxf(acc + acc2, 0.f);
     }
     __syncthreads();
     for (int j = t; j < p.H2; j += HEAD_THREADS) {
@@ -112,13 +118,27 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(HeadP p) {
     ssq = block_sum(ssq, scratch);      // contains the barriers that publish x[]
     const bool normalise_x = p.head != SAR_HEAD_SOFTMAX && p.head != SAR_HEAD_CIRCLE_RAW;
     const float xinv = normalise_x ? 1.0f / sqrtf(fmaxf(ssq, 1e-12f)) : 1.f;
+    // x^ . W[:, c] and |W[:, c]|^2: classes x (HEAD_THREADS / n) d-slices, partials through smem
+    const int parts = HEAD_THREADS / n;
+    float* pacc = h1;                       // [parts][n]  (h1/h2 are free after the classifier)
+    float* pwss = wn + HEAD_MAXC + 32;      // placed after scratch: [parts][n]
+    if (t < parts * n) {
+      const int c = t % n, part = t / n;
+      const int dlo = (int)(((long long)Dd * part) / parts), dhi = (int)(((long long)Dd * (part + 1)) / parts);
+      float a = 0.f, w2 = 0.f;
+#pragma unroll 4
+      for (int d = dlo; d < dhi; ++d) {
+        const float wv = __ldg(p.wd + (size_t)d * n + c);
+        a = fmaf(x[d] * xinv, wv, a);
+        w2 = fmaf(wv, wv, w2);
+      }
+      pacc[part * n + c] = a;
+      pwss[part * n + c] = w2;
+    }
+    __syncthreads();
     if (t < n) {
       float acc = 0.f, wss = 0.f;
-      for (int d = 0; d < Dd; ++d) {
-        float wv = __ldg(p.wd + (size_t)d * n + t);
-        acc = fmaf(x[d] * xinv, wv, acc);
-        wss = fmaf(wv, wv, wss);
-      }
+      for (int part = 0; part < parts; ++part) { acc += pacc[part * n + t]; wss += pwss[part * n + t]; }
       const bool face = p.head == SAR_HEAD_SPHEREFACE || p.head == SAR_HEAD_COSFACE || p.head == SAR_HEAD_ARCFACE;
       if (face) acc *= 1.0f / sqrtf(fmaxf(wss, 1e-12f));      // W normalised per column, losses.py:34,80,127
       ld[t] = acc;
@@ -211,7 +231,7 @@ extern "C" int sar_head_fwd(const float* emb, int D,
   if (!emb) D = 0;
   int dmax = D > 0 ? D : 0;
   if (emb_d && Dd > dmax) dmax = Dd;
-  size_t smem = sizeof(float) * ((size_t)dmax + H1 + H2 + 3 * HEAD_MAXC + 32);
+  size_t smem = sizeof(float) * ((size_t)dmax + (H1 + H2 > HEAD_THREADS ? H1 + H2 : HEAD_THREADS) + 3 * HEAD_MAXC + 32 + HEAD_THREADS);
   SAR_REQUIRE(smem <= 200 * 1024, SAR_ERR_UNSUPPORTED, "sar_head_fwd: embedding too wide");
   HeadP p{emb, D, w1, b1, H1, w2, b2, H2, w3, b3, emb_d, emb_d ? Dd : D, wd, onehot, n_classes, head,
           margin, s, gamma, y_accent, y_accent_logits, y_disc, y_disc_logits, sample_stats};

@@ -7,57 +7,109 @@
 //     score = X @ Wa + ba ;  A = softmax_k(score)                      VLAD.py:33-35
 //     V[k] = sum_s A[s,k] * X[s] - (sum_s A[s,k]) * c[k]     k < K      VLAD.py:38-45
 //     out[k] = V[k] / sqrt(max(|V[k]|^2, 1e-12))                        VLAD.py:47-48
-// so HBM traffic is the algorithmic minimum: X read once, K*D written once (ghost
-// clusters only take part in the softmax and are never accumulated).
+// so HBM traffic is the algorithmic minimum: X read once, K*D written once (ghost clusters only
+// take part in the softmax and are never accumulated).
+//
+// Register tiling keeps the shared-memory pipe from being the limit:
+//   scores   : thread = 4 descriptors x 4 clusters, marching over d in float4 steps
+//              (8 LDS.128 per 64 FMA), Wa staged in shared memory when it fits;
+//   residual : warp = 8 clusters, lane = 8 feature columns -> 64 accumulators per thread,
+//              4 LDS.128 per 64 FMA; the per-cluster L2 norm is a warp reduction, so the
+//              normalised rows go straight from registers to HBM (32 B per lane, 1 KB per warp).
 #include "common.cuh"
 
 namespace sar {
 
 constexpr int VLAD_THREADS = 256;
-constexpr int VLAD_KC = 8;     // clusters accumulated per register block
 
-template <int DSL>   // columns per thread: D <= 256*DSL
 __global__ void __launch_bounds__(VLAD_THREADS) vlad_kernel(const float* __restrict__ feat, const float* __restrict__ wa,
                                                              const float* __restrict__ ba, const float* __restrict__ score,
-                                                             const float* __restrict__ centers,
-                                                             float* __restrict__ out, int S, int D, int K, int G) {
+                                                             const float* __restrict__ centers, float* __restrict__ out,
+                                                             int S, int D, int K, int G, int wa_smem) {
   extern __shared__ __align__(16) float smem[];
   const int KG = K + G;
-  const int KGP = (KG + 3) & ~3;                 // padded row of A for float4 reads
-  float* X = smem;                                // [S][D]
-  float* A = X + (size_t)S * D;                   // [S][KGP]
-  float* asum = A + (size_t)S * KGP;              // [KGP]
-  float* part = asum + KGP;                       // [VLAD_KC][8 warps]
+  const int KGP = (KG + 7) & ~7;                  // padded cluster count (A row, zero-filled)
+  const int XS = D + 4;                           // padded X row: +4 banks per descriptor
+  const int SP = (S + 3) & ~3;                    // descriptors padded to the 4-row score tile
+  float* X = smem;                                // [SP][XS]
+  float* A = X + (size_t)SP * XS;                 // [SP][KGP]
+  float* Ws = A + (size_t)SP * KGP;               // [D][KGP] (only when wa_smem)
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int b = blockIdx.x;
 
-  // ---- stage X (coalesced 16B loads)
+  // ---- stage X (coalesced 16B loads), zero the padded rows/columns
   {
     const float4* src = reinterpret_cast<const float4*>(feat + (size_t)b * S * D);
-    float4* dst = reinterpret_cast<float4*>(X);
-    const int n4 = S * D / 4;
-    for (int i = t; i < n4; i += VLAD_THREADS) dst[i] = __ldg(src + i);
-  }
-  for (int i = t; i < S * KGP; i += VLAD_THREADS) A[i] = 0.f;
-  __syncthreads();
-
-  // ---- scores: item (s,k); lanes run over k so Wa reads coalesce and X[s][d] broadcasts
-  for (int i = t; i < S * KG; i += VLAD_THREADS) {
-    const int s = i / KG, k = i - s * KG;
-    float acc;
-    if (score) {                                   // VladPooling called with external scores
-      acc = __ldg(score + ((size_t)b * S + s) * KG + k);
-    } else {                                       // fused 1x1 assignment conv
-      const float* xr = X + (size_t)s * D;
-      acc = __ldg(ba + k);
-#pragma unroll 8
-      for (int d = 0; d < D; ++d) acc = fmaf(xr[d], __ldg(wa + (size_t)d * KG + k), acc);
+    const int d4 = D >> 2;
+    for (int i = t; i < SP * d4; i += VLAD_THREADS) {
+      const int s = i / d4, c = i - s * d4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (s < S) v = __ldg(src + (size_t)s * d4 + c);
+      *reinterpret_cast<float4*>(X + (size_t)s * XS + 4 * c) = v;
     }
-    A[s * KGP + k] = acc;
+  }
+  for (int i = t; i < SP * KGP; i += VLAD_THREADS) A[i] = 0.f;
+  if (!score && wa_smem) {
+    for (int i = t; i < D * KGP; i += VLAD_THREADS) {
+      const int d = i / KGP, k = i - d * KGP;
+      Ws[i] = (k < KG) ? __ldg(wa + (size_t)d * KG + k) : 0.f;
+    }
   }
   __syncthreads();
 
-  // ---- softmax over clusters, one warp per descriptor row
+  // ---- scores
+  if (score) {                                     // VladPooling called with external scores
+    for (int i = t; i < S * KG; i += VLAD_THREADS) {
+      const int s = i / KG, k = i - s * KG;
+      A[s * KGP + k] = __ldg(score + ((size_t)b * S + s) * KG + k);
+    }
+  } else {                                         // fused 1x1 assignment conv, 4x4 register tiles
+    const int kt = KGP >> 2, tiles = (SP >> 2) * kt;
+    for (int tile = t; tile < tiles; tile += VLAD_THREADS) {
+      const int kg4 = tile % kt, sg4 = tile / kt;
+      const int k0 = 4 * kg4, s0 = 4 * sg4;
+      float acc[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+      for (int d = 0; d < D; d += 4) {
+        float4 xv[4], wv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xv[i] = *reinterpret_cast<const float4*>(X + (size_t)(s0 + i) * XS + d);
+        if (wa_smem) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) wv[e] = *reinterpret_cast<const float4*>(Ws + (size_t)(d + e) * KGP + k0);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float* wr = wa + (size_t)(d + e) * KG + k0;
+            wv[e] = make_float4(k0 < KG ? __ldg(wr) : 0.f, k0 + 1 < KG ? __ldg(wr + 1) : 0.f,
+                                k0 + 2 < KG ? __ldg(wr + 2) : 0.f, k0 + 3 < KG ? __ldg(wr + 3) : 0.f);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float xe[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            acc[i][0] = fmaf(xe[e], wv[e].x, acc[i][0]);
+            acc[i][1] = fmaf(xe[e], wv[e].y, acc[i][1]);
+            acc[i][2] = fmaf(xe[e], wv[e].z, acc[i][2]);
+            acc[i][3] = fmaf(xe[e], wv[e].w, acc[i][3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (s0 + i < S && k0 + j < KG) A[(s0 + i) * KGP + k0 + j] = acc[i][j] + __ldg(ba + k0 + j);
+    }
+  }
+  __syncthreads();
+
+  // ---- softmax over clusters, one warp per descriptor row (padded columns stay 0)
   for (int s = warp; s < S; s += VLAD_THREADS / 32) {
     float m = -INFINITY;
     for (int k = lane; k < KG; k += 32) m = fmaxf(m, A[s * KGP + k]);
@@ -72,75 +124,62 @@ __global__ void __launch_bounds__(VLAD_THREADS) vlad_kernel(const float* __restr
     for (int k = lane; k < KG; k += 32) A[s * KGP + k] = A[s * KGP + k] / sum;
   }
   __syncthreads();
-  for (int k = t; k < KGP; k += VLAD_THREADS) {
-    float a = 0.f;
-    if (k < KG) for (int s = 0; s < S; ++s) a += A[s * KGP + k];
-    asum[k] = a;
-  }
-  __syncthreads();
 
-  // ---- residual accumulation, VLAD_KC clusters at a time; thread owns columns d = t (+256)
-  for (int k0 = 0; k0 < K; k0 += VLAD_KC) {
-    float acc[DSL][VLAD_KC];
+  // ---- residual accumulation: warp <- 8 clusters, lane <- 8 columns (per 256-column slab)
+  const int kgroups = (K + 7) >> 3;
+  for (int kgp = warp; kgp < kgroups; kgp += VLAD_THREADS / 32) {
+    const int k0 = 8 * kgp;
+    {
+      const int d0 = 4 * lane, d1 = 128 + 4 * lane;  // D == 256: lane owns 2 x 4 columns (conflict-free LDS.128)
+      float acc[8][8];
+      float asum[8];
 #pragma unroll
-    for (int j = 0; j < DSL; ++j)
+      for (int i = 0; i < 8; ++i) {
+        asum[i] = 0.f;
 #pragma unroll
-      for (int q = 0; q < VLAD_KC; ++q) acc[j][q] = 0.f;
-    for (int s = 0; s < S; ++s) {
-      const float4 a0 = *reinterpret_cast<const float4*>(A + s * KGP + k0);
-      const float4 a1 = *reinterpret_cast<const float4*>(A + s * KGP + k0 + 4);
-      const float av[VLAD_KC] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-#pragma unroll
-      for (int j = 0; j < DSL; ++j) {
-        const int d = t + j * VLAD_THREADS;
-        const float xv = (d < D) ? X[(size_t)s * D + d] : 0.f;
-#pragma unroll
-        for (int q = 0; q < VLAD_KC; ++q) acc[j][q] = fmaf(av[q], xv, acc[j][q]);
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
       }
-    }
-    float ss[VLAD_KC];
+      for (int s = 0; s < S; ++s) {
+        const float4 a0 = *reinterpret_cast<const float4*>(A + s * KGP + k0);
+        const float4 a1 = *reinterpret_cast<const float4*>(A + s * KGP + k0 + 4);
+        const float4 x0 = *reinterpret_cast<const float4*>(X + (size_t)s * XS + d0);
+        const float4 x1 = *reinterpret_cast<const float4*>(X + (size_t)s * XS + d1);
+        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
-    for (int q = 0; q < VLAD_KC; ++q) {
-      ss[q] = 0.f;
-      const int k = k0 + q;
+        for (int i = 0; i < 8; ++i) {
+          asum[i] += av[i];
 #pragma unroll
-      for (int j = 0; j < DSL; ++j) {
-        const int d = t + j * VLAD_THREADS;
-        if (k < K && d < D) {
-          acc[j][q] -= asum[k] * __ldg(centers + (size_t)k * D + d);
-          ss[q] += acc[j][q] * acc[j][q];
-        } else {
-          acc[j][q] = 0.f;
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], xv[j], acc[i][j]);
         }
       }
-      ss[q] = warp_sum(ss[q]);
-    }
-    __syncthreads();                     // previous chunk's `part` readers are done
-    if (lane == 0) {
+      // the whole row is in this warp -> per-cluster L2 norm by warp reduction
 #pragma unroll
-      for (int q = 0; q < VLAD_KC; ++q) part[q * 8 + warp] = ss[q];
-    }
-    __syncthreads();
+      for (int i = 0; i < 8; ++i) {
+        const int k = k0 + i;
+        if (k >= K) continue;                               // warp-uniform
+        const float4 c0 = __ldg(reinterpret_cast<const float4*>(centers + (size_t)k * D + d0));
+        const float4 c1 = __ldg(reinterpret_cast<const float4*>(centers + (size_t)k * D + d1));
+        const float cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+        float ss = 0.f;
 #pragma unroll
-    for (int q = 0; q < VLAD_KC; ++q) {
-      const int k = k0 + q;
-      if (k >= K) continue;
-      float tot = 0.f;
-#pragma unroll
-      for (int w = 0; w < 8; ++w) tot += part[q * 8 + w];
-      const float inv = 1.0f / sqrtf(fmaxf(tot, 1e-12f));
-#pragma unroll
-      for (int j = 0; j < DSL; ++j) {
-        const int d = t + j * VLAD_THREADS;
-        if (d < D) out[((size_t)b * K + k) * D + d] = acc[j][q] * inv;
+        for (int j = 0; j < 8; ++j) {
+          acc[i][j] -= asum[i] * cv[j];
+          ss = fmaf(acc[i][j], acc[i][j], ss);
+        }
+        ss = warp_sum(ss);
+        float* orow = out + ((size_t)b * K + k) * D;
+        const float inv = 1.0f / sqrtf(fmaxf(ss, 1e-12f));
+        *reinterpret_cast<float4*>(orow + d0) = make_float4(acc[i][0] * inv, acc[i][1] * inv, acc[i][2] * inv, acc[i][3] * inv);
+        *reinterpret_cast<float4*>(orow + d1) = make_float4(acc[i][4] * inv, acc[i][5] * inv, acc[i][6] * inv, acc[i][7] * inv);
       }
     }
   }
 }
 
-static size_t vlad_smem_bytes(int S, int D, int KG) {
-  int KGP = (KG + 3) & ~3;
-  return sizeof(float) * ((size_t)S * D + (size_t)S * KGP + KGP + VLAD_KC * 8);
+static size_t vlad_smem_floats(int S, int D, int KG, bool with_w) {
+  const size_t KGP = (KG + 7) & ~7, XS = D + 4, SP = (S + 3) & ~3;
+  return SP * XS + SP * KGP + (with_w ? (size_t)D * KGP : 0);
 }
 
 }  // namespace sar
@@ -152,21 +191,15 @@ extern "C" int sar_vlad_fwd(const float* feat, const float* w_assign, const floa
   SAR_REQUIRE((score != nullptr) != (w_assign != nullptr && b_assign != nullptr), SAR_ERR_BAD_ARG,
               "sar_vlad_fwd: pass either (w_assign, b_assign) or score");
   SAR_REQUIRE(B > 0 && S > 0 && D > 0 && K > 0 && G >= 0, SAR_ERR_BAD_ARG, "sar_vlad_fwd: bad dimension");
-  SAR_REQUIRE(D % 32 == 0 && D <= 512 && K + G <= 128, SAR_ERR_UNSUPPORTED,
-              "sar_vlad_fwd: needs D %% 32 == 0, D <= 512, K+G <= 128 (got D=%d K+G=%d)", D, K + G);
-  SAR_REQUIRE(aligned16(feat) && aligned16(out), SAR_ERR_ALIGN, "sar_vlad_fwd: unaligned pointer");
-  // A rows are read VLAD_KC at a time: pad the cluster count so reads past K+G stay in the row
-  size_t smem = vlad_smem_bytes(S, D, K + G + VLAD_KC);
-  SAR_REQUIRE(smem <= 227 * 1024, SAR_ERR_UNSUPPORTED, "sar_vlad_fwd: S*D too large for shared memory (%zu B)", smem);
-  cudaStream_t st = (cudaStream_t)stream;
-  cudaError_t e;
-  if (D <= 256) {
-    e = cudaFuncSetAttribute(vlad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) vlad_kernel<1><<<B, VLAD_THREADS, smem, st>>>(feat, w_assign, b_assign, score, centers, out, S, D, K, G);
-  } else {
-    e = cudaFuncSetAttribute(vlad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) vlad_kernel<2><<<B, VLAD_THREADS, smem, st>>>(feat, w_assign, b_assign, score, centers, out, S, D, K, G);
-  }
+  SAR_REQUIRE(D == 256 && K + G <= 128, SAR_ERR_UNSUPPORTED,
+              "sar_vlad_fwd: this build supports D == 256 (hidden_dim) and K+G <= 128 (got D=%d K+G=%d)", D, K + G);
+  SAR_REQUIRE(aligned16(feat) && aligned16(out) && aligned16(centers), SAR_ERR_ALIGN, "sar_vlad_fwd: unaligned pointer");
+  const size_t limit = 227 * 1024;
+  int wa_smem = (!score && vlad_smem_floats(S, D, K + G, true) * sizeof(float) <= limit) ? 1 : 0;
+  size_t smem = vlad_smem_floats(S, D, K + G, wa_smem != 0) * sizeof(float);
+  SAR_REQUIRE(smem <= limit, SAR_ERR_UNSUPPORTED, "sar_vlad_fwd: S*D too large for shared memory (%zu B)", smem);
+  cudaError_t e = cudaFuncSetAttribute(vlad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("sar_vlad_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+  vlad_kernel<<<B, VLAD_THREADS, smem, (cudaStream_t)stream>>>(feat, w_assign, b_assign, score, centers, out, S, D, K, G, wa_smem);
   return check_launch("sar_vlad_fwd");
 }

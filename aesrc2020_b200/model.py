@@ -266,6 +266,7 @@ class SARModel:
         self._outputs = outputs or config.output_names()
         self._engine: Optional[SARNetEngine] = None
         self._pinned: Dict[str, torch.Tensor] = {}
+        self.use_graph = True          # replay a CUDA graph of the step (captured once per batch shape)
 
     # -- Keras-like surface
     @property
@@ -332,13 +333,19 @@ class SARModel:
             return dict(zip(self.config.input_names(), x))
         return {"x_data": x}
 
-    def forward_device(self, x, want_intermediates=False) -> Dict[str, torch.Tensor]:
+    def forward_device(self, x, want_intermediates=False, graph: bool = None) -> Dict[str, torch.Tensor]:
+        """One forward on the device.  `graph` (default: self.use_graph) replays a captured CUDA graph
+        of the step; the returned tensors are then the graph's static outputs."""
         xd = self._as_dict(x)
         missing = [k for k in self.config.input_names() if k not in xd]
         if missing:
             raise ValueError("missing model inputs: %s" % missing)
         dev_in = {k: self._to_device(k, v) for k, v in xd.items()}
-        out = self.engine().forward(dev_in, want_intermediates=want_intermediates)
+        use_graph = self.use_graph if graph is None else graph
+        if use_graph and not want_intermediates:
+            out = self.engine().forward_graphed(dev_in)
+        else:
+            out = self.engine().forward(dev_in, want_intermediates=want_intermediates)
         if self.config.ctc_enable and bool((out["ctc_status"] != 0).any()):
             # tf.nn.ctc_loss raises on infeasible / out-of-range labels
             raise SarnetError("CTC: infeasible or out-of-range label sequence in batch "
@@ -356,7 +363,7 @@ class SARModel:
             sl = {k: v[b0:b0 + batch_size] for k, v in xd.items()}
             out = self.forward_device(sl)
             for i, name in enumerate(self._outputs):
-                chunks[i].append(out[name] if on_device else out[name].cpu().numpy())
+                chunks[i].append(out[name].clone() if on_device else out[name].cpu().numpy())
         cat = (lambda c: torch.cat(c, 0)) if on_device else (lambda c: np.concatenate(c, 0))
         res = [cat(c) for c in chunks]
         return res[0] if len(res) == 1 else res
@@ -376,7 +383,7 @@ class SARModel:
             if "y_true" in sl:
                 sl["y_true"] = self._to_device("y_true", sl["y_true"])
             vec = self.forward_device(sl)["loss_vector"]
-            total = vec if total is None else total + vec
+            total = vec.clone() if total is None else total + vec     # vec may be a graph-static buffer
         total = _dist.all_reduce_loss_vector(total, group)
         return _dist.loss_vector_to_metrics(total.cpu().numpy(), self.config)
 

@@ -95,6 +95,16 @@ def maxpool_planes(x: torch.Tensor, out: Planes, k, stride, pad_t, pad_l) -> Pla
     return out
 
 
+def stem_pool(x: torch.Tensor, w, bias, scale, shift, out: Planes) -> Planes:
+    """sar_stem_pool_fwd: x (B,T,D[,1]) fp32 -> pooled stem map in planes `out`."""
+    x = x.contiguous()
+    B, T, D = int(x.shape[0]), int(x.shape[1]), int(x.shape[2])
+    check(_shim.lib().sar_stem_pool_fwd(ptr(x), ptr(w), ptr(bias), ptr(scale), ptr(shift), ptr(out.t), B, T, D, out.C,
+                                        stream_ptr()), "sar_stem_pool_fwd")
+    ops._count(1)
+    return out
+
+
 def pack_weights(kernel_hwio: np.ndarray, short_kernel: Optional[np.ndarray] = None) -> np.ndarray:
     """Keras HWIO kernel (+ optional 1x1 projection kernel) -> [2][Cout][Ktot] fp16 hi/lo,
     K-major with k = tap*Cin + ci and the shortcut's Cin_s rows appended."""

@@ -95,6 +95,14 @@ int sar_planes_unpack_fwd(const void* planes, float* x, int B, int H, int W, int
 int sar_maxpool_planes_fwd(const float* x, void* planes, int B, int H, int W, int C, int Ho, int Wo,
                            int k, int stride, int pad_t, int pad_l, void* stream);
 
+/* The whole ResNet stem in one kernel: Conv2D 7x7/s2 'same' (+bias) -> BatchNormalization -> ReLU ->
+ * MaxPooling2D 3x3/s2 'same' (resnet.py:28-45 via :173/:191, and :174/:192).  x (B,T,D) fp32 (the
+ * (B,T,D,1) x_data tensor), w (7,7,1,F0) Keras HWIO, scale/shift = folded inference BN; output: the
+ * pooled (B, ceil(ceil(T/2)/2), ceil(ceil(D/2)/2), F0) map as flat-pad hi/lo planes (non-split).
+ * TF-SAME pads are derived from T and D inside.  F0 in {16,32,48,64}; ceil(D/2) % 4 == 0. */
+int sar_stem_pool_fwd(const float* x, const float* w, const float* bias, const float* scale,
+                      const float* shift, void* planes, int B, int T, int D, int F0, void* stream);
+
 /* One residual-block convolution on tcgen05 tensor cores (csrc/conv_tc.cu).
  * Replaces _bn_relu_conv / basic_block / _shortcut: resnet.py:47-65, 105-125, 67-89.
  *   acc = sum_taps A[q + tap_row_off[t], plane tap_plane[t]] @ W_t  (+ S[q, s_plane] @ W_s)
@@ -155,7 +163,7 @@ int sar_bigru_fwd(const float* xp, const float* rec, const float* rbias, float* 
  * assignment conv (w_assign (D,K+G), b_assign (K+G); score = NULL) -- the model.vlad() path --
  * OR a precomputed `score` (B,S,K+G) tensor (w_assign = b_assign = NULL) -- the bare
  * VladPooling([feat, cluster_score]) call surface of VLAD.py:26-28.
- * Requires D % 32 == 0, D <= 512, K+G <= 128. */
+ * Requires D == 256 (hidden_dim of this build) and K+G <= 128. */
 int sar_vlad_fwd(const float* feat, const float* w_assign, const float* b_assign, const float* score,
                  const float* centers, float* out, int B, int S, int D, int K, int G, void* stream);
 

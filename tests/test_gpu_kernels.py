@@ -103,7 +103,7 @@ def test_bigru_vs_oracle(cuda_device, B, S, Din, seq):
 
 @pytest.mark.parametrize("mode,K,G,S,D", [("gvlad", 64, 8, 48, 256), ("vlad", 64, 0, 48, 256),
                                           ("gvlad", 8, 2, 21, 256), ("gvlad", 10, 3, 114, 256),
-                                          ("vlad", 4, 0, 5, 512)])
+                                          ("vlad", 4, 0, 5, 256), ("gvlad", 64, 8, 75, 256)])
 def test_vlad_vs_literal_5d_formula(cuda_device, mode, K, G, S, D):
     """Fused kernel vs the literal (B,1,S,K+G,D) broadcast of VLAD.py:33-48."""
     from aesrc2020_b200 import ops, VLAD
