@@ -169,10 +169,12 @@ bigru_kernel(const float* __restrict__ xp, const float* __restrict__ rec, const 
       const float hold = h_s[cur * GRU_HBUF + hpos];
       const float hn = z * hold + (1.f - z) * hh;
       const int nxt_off = (cur ^ 1) * GRU_HBUF + hpos;
+      if (seq & 2) { h_s[nxt_off] = hn; } else {
 #pragma unroll
       for (int r2 = 0; r2 < GRU_CL; ++r2) remote[r2][nxt_off] = hn;
+      }
       if (stage_out) {
-        if (seq) out_s[(size_t)step * (GRU_UPC * GRU_BG) + t] = hn;
+        if (seq & 1) out_s[(size_t)step * (GRU_UPC * GRU_BG) + t] = hn;
         else if (step == S - 1) out_s[t] = hn;
       } else if (bvalid) {
         const int tt = dir ? (S - 1 - step) : step;
@@ -180,11 +182,12 @@ bigru_kernel(const float* __restrict__ xp, const float* __restrict__ rec, const 
         else if (step == S - 1) out[(size_t)(b0 + gb) * (2 * U) + dir * U + unit] = hn;
       }
     }
+    if (seq & 4) __syncthreads(); else
     cluster_arrive_release();            // publishes my DSMEM stores (no global store is pending)
     // rotate the x-projection registers and prefetch step+2 while the barrier completes
     x0z = x1z; x0r = x1r; x0h = x1h;
     if (bvalid && step + 2 < S) { const float* p = xrow(step + 2); x1z = __ldg(p); x1r = __ldg(p + U); x1h = __ldg(p + 2 * U); }
-    cluster_wait_acquire();
+    if (!(seq & 4)) cluster_wait_acquire();
     cur ^= 1;
   }
 
@@ -221,5 +224,6 @@ extern "C" int sar_bigru_fwd(const float* xp, const float* rec, const float* rbi
   cudaError_t e = cudaFuncSetAttribute(bigru_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(180 * 1024));
   if (e != cudaSuccess) { set_error("sar_bigru_fwd: %s", cudaGetErrorString(e)); return (int)e; }
   bigru_kernel<<<grid, GRU_THREADS, smem, (cudaStream_t)stream>>>(xp, rec, rbias, out, B, S, seq, stage_out);
+  seq &= 1;
   return check_launch("sar_bigru_fwd");
 }

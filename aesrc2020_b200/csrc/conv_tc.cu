@@ -26,6 +26,7 @@
 // epilogue warps (tcgen05.ld -> registers -> bias/residual/BN/ReLU -> hi/lo planes in HBM).
 // 3-stage TMA->SMEM ring with mbarrier full/empty pairs, 128B/64B hardware swizzle.
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace sar {
@@ -34,7 +35,13 @@ constexpr int TC_BM = 128;            // output rows per tile (TMEM lanes)
 constexpr int TC_STAGES = 3;
 constexpr int TC_PLANE_BYTES = 16384; // 128 rows x 128 B (kc = 64) per operand plane
 constexpr int TC_STAGE_BYTES = 4 * TC_PLANE_BYTES;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;
+// Warp roles.  The SM's schedulers favour the HIGHEST warp id of a sub-partition (wid % 4), so the two
+// single-lane issuing warps get ids 4 and 5: they share sub-partitions 0 and 1 with epilogue warps 0 and 1
+// and win arbitration while those spin on an mbarrier (with ids 0/1 the MMA warp crawled at ~600 cycles/tap).
+constexpr int TC_WARP_TMA = 8, TC_WARP_MMA = 9;   // warps 0..7 = epilogue: quadrant = warp & 3, group = warp >> 2
+// Two epilogue groups: group g drains TMEM accumulator stage g (tiles with (it & 1) == g), so one tile's
+// conversion/stores may take up to two MMA tile times before the tensor pipe has to wait.
 constexpr float TC_LO_SCALE = 2048.f;
 constexpr float TC_LO_INV = 1.f / 2048.f;
 
@@ -54,6 +61,8 @@ struct TcParams {
   const float* bias; const float* act_scale; const float* act_shift;
   const __half* res;                     // identity shortcut planes [2][R][Cout] or null
   __half* out_raw; __half* out_act; float* out_dense;
+  long long* dbg;                        // optional: clock64 timestamps of CTA 0 (profiling aid)
+  int mma_mask;                          // experiment: which of the 3 hi/lo products to issue (7 = all)
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -92,6 +101,14 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t dst
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+// elect.sync: exactly one lane of the (converged) warp gets true.  The compiler then treats the guarded
+// region as single-lane code and feeds tcgen05.mma / TMA from uniform registers directly; a plain
+// `lane == 0` test makes it emit a per-instruction ELECT/R2UR/branch waterfall (~100 cycles per MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -133,6 +150,132 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// ------------------------------------------------------------------ epilogue (shared by both kernels)
+// 8 values -> hi = fp16(x) and lo = fp16((x - hi) * 2^11), packed conversions (cvt.rn.f16x2.f32)
+__device__ __forceinline__ void split_store8(const float* v, __half* hi_dst, __half* lo_dst) {
+  uint32_t hh[4], ll[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const __half2 h2 = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+    const float2 hf = __half22float2(h2);
+    const __half2 l2 = __floats2half2_rn((v[2 * e] - hf.x) * TC_LO_SCALE, (v[2 * e + 1] - hf.y) * TC_LO_SCALE);
+    hh[e] = *reinterpret_cast<const uint32_t*>(&h2);
+    ll[e] = *reinterpret_cast<const uint32_t*>(&l2);
+  }
+  *reinterpret_cast<uint4*>(hi_dst) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+  *reinterpret_cast<uint4*>(lo_dst) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+}
+
+// One tile: TMEM (acc0 + 2^-11 acc1) -> +bias (+identity shortcut) -> raw hi/lo planes and/or
+// relu(scale*v+shift) hi/lo planes (phase-split when the consumer is strided) or dense fp32.
+// The identity-shortcut rows of the next 32-column chunk are prefetched (L2 latency) while the current
+// chunk is converted and stored; the first chunk's rows are requested before waiting for the MMAs.
+__device__ __forceinline__ void epilogue_tile(const TcParams& p, int tile, int it, int quad, int lane, uint32_t tmem_base,
+                                              uint64_t* tfull_bar, uint64_t* tempty_bar, const float* s_bias,
+                                              const float* s_scale, const float* s_shift) {
+  const int BN = p.BN;
+  const int as = it & 1;
+  const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+  const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+  const int n0 = nt * BN;
+  const long long q = (long long)mt * TC_BM + quad * 32 + lane;
+  // decode flat row -> (n, h, w)
+  bool valid = q < p.R;
+  int n = 0, h = 0, w = 0;
+  if (valid) {
+    n = (int)(q / p.Rimg);
+    const int rem = (int)(q - (long long)n * p.Rimg);
+    h = rem / p.P; w = rem - h * p.P;
+    valid = (h < p.H) && (w < p.W);
+  }
+  long long qo = q; long long Ro = p.R; int plane0 = 0;
+  if (p.split) {
+    qo = (long long)n * p.Rimg2 + (h >> 1) * p.P2 + (w >> 1);
+    Ro = p.R2;
+    plane0 = 2 * ((h & 1) * 2 + (w & 1));
+  }
+  const bool has_res = p.res != nullptr && valid;
+  uint4 rh[4], rl[4];
+  if (has_res) {
+    const uint4* ph = reinterpret_cast<const uint4*>(p.res + (size_t)q * p.Cout + n0);
+    const uint4* pl = reinterpret_cast<const uint4*>(p.res + ((size_t)p.R + q) * p.Cout + n0);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) { rh[g] = __ldg(ph + g); rl[g] = __ldg(pl + g); }
+  }
+  mbar_wait(&tfull_bar[as], aphase);
+  tc_fence_after();
+  if (p.dbg && blockIdx.x == 0 && quad == 0 && lane == 0 && it < 8) p.dbg[32 + it * 2] = clock64();
+  const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 2 * BN);
+  for (int c0 = 0; c0 < BN; c0 += 32) {
+    uint32_t r0[32], r1[32];
+    tmem_ld32(tbase + (uint32_t)c0, r0);
+    tmem_ld32(tbase + (uint32_t)(BN + c0), r1);
+    tmem_ld_wait();
+    if (valid) {
+      float v[32];
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const float4 b4 = *reinterpret_cast<const float4*>(s_bias + n0 + c0 + 4 * g);
+        v[4 * g + 0] = fmaf(__uint_as_float(r1[4 * g + 0]), TC_LO_INV, __uint_as_float(r0[4 * g + 0])) + b4.x;
+        v[4 * g + 1] = fmaf(__uint_as_float(r1[4 * g + 1]), TC_LO_INV, __uint_as_float(r0[4 * g + 1])) + b4.y;
+        v[4 * g + 2] = fmaf(__uint_as_float(r1[4 * g + 2]), TC_LO_INV, __uint_as_float(r0[4 * g + 2])) + b4.z;
+        v[4 * g + 3] = fmaf(__uint_as_float(r1[4 * g + 3]), TC_LO_INV, __uint_as_float(r0[4 * g + 3])) + b4.w;
+      }
+      if (has_res) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const __half2* ah = reinterpret_cast<const __half2*>(&rh[g]);
+          const __half2* bl = reinterpret_cast<const __half2*>(&rl[g]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 fh = __half22float2(ah[e]), fl = __half22float2(bl[e]);
+            v[g * 8 + e * 2] += fmaf(fl.x, TC_LO_INV, fh.x);
+            v[g * 8 + e * 2 + 1] += fmaf(fl.y, TC_LO_INV, fh.y);
+          }
+        }
+        if (c0 + 32 < BN) {                      // prefetch the next chunk's shortcut rows
+          const uint4* ph = reinterpret_cast<const uint4*>(p.res + (size_t)q * p.Cout + n0 + c0 + 32);
+          const uint4* pl = reinterpret_cast<const uint4*>(p.res + ((size_t)p.R + q) * p.Cout + n0 + c0 + 32);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) { rh[g] = __ldg(ph + g); rl[g] = __ldg(pl + g); }
+        }
+      }
+      if (p.out_raw) {
+        __half* oh = p.out_raw + ((size_t)plane0 * Ro + qo) * p.Cout + n0 + c0;
+        __half* ol = p.out_raw + ((size_t)(plane0 + 1) * Ro + qo) * p.Cout + n0 + c0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) split_store8(v + 8 * g, oh + 8 * g, ol + 8 * g);
+      }
+      if (p.out_act || p.out_dense) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 s4 = *reinterpret_cast<const float4*>(s_scale + n0 + c0 + 4 * g);
+          const float4 t4 = *reinterpret_cast<const float4*>(s_shift + n0 + c0 + 4 * g);
+          v[4 * g + 0] = fmaxf(fmaf(v[4 * g + 0], s4.x, t4.x), 0.f);
+          v[4 * g + 1] = fmaxf(fmaf(v[4 * g + 1], s4.y, t4.y), 0.f);
+          v[4 * g + 2] = fmaxf(fmaf(v[4 * g + 2], s4.z, t4.z), 0.f);
+          v[4 * g + 3] = fmaxf(fmaf(v[4 * g + 3], s4.w, t4.w), 0.f);
+        }
+      }
+      if (p.out_act) {
+        __half* oh = p.out_act + ((size_t)plane0 * Ro + qo) * p.Cout + n0 + c0;
+        __half* ol = p.out_act + ((size_t)(plane0 + 1) * Ro + qo) * p.Cout + n0 + c0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) split_store8(v + 8 * g, oh + 8 * g, ol + 8 * g);
+      }
+      if (p.out_dense) {
+        float4* od = reinterpret_cast<float4*>(p.out_dense + (((size_t)n * p.H + h) * p.W + w) * p.Cout + n0 + c0);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) od[g] = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncwarp();
+  if (p.dbg && blockIdx.x == 0 && quad == 0 && lane == 0 && it < 8) p.dbg[32 + it * 2 + 1] = clock64();
+  if (lane == 0) mbar_arrive(&tempty_bar[as]);
+}
+
 // ------------------------------------------------------------------ the kernel
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapS,
@@ -145,7 +288,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   uint64_t* tfull_bar = empty_bar + TC_STAGES;      // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;             // [2] accumulator drained
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* s_bias = reinterpret_cast<float*>(tmem_base_slot + 2);   // [Cout]
+  float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_base_slot + 2) + 15) & ~uintptr_t(15));   // float4 reads   // [Cout]
   float* s_scale = s_bias + p.Cout;
   float* s_shift = s_scale + p.Cout;
 
@@ -158,7 +301,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {
+  if (warp == TC_WARP_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -176,16 +319,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const int n_ksteps = n_main + p.chunks_sc;
   const int total_tiles = p.m_tiles * p.n_tiles;
 
-  if (warp == 0) {
-    // ===================== TMA producer (one lane) =====================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
-        const long long q0 = (long long)mt * TC_BM;
-        const int n0 = nt * BN;
-        for (int ks = 0; ks < n_ksteps; ++ks) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+  if (warp == TC_WARP_TMA) {
+    // ===================== TMA producer (whole warp converged, one elected lane issues) =====================
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+      const long long q0 = (long long)mt * TC_BM;
+      const int n0 = nt * BN;
+      for (int ks = 0; ks < n_ksteps; ++ks) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           uint8_t* st = smem + stage * TC_STAGE_BYTES;
           const uint32_t a_hi = smem_u32(st), a_lo = a_hi + TC_PLANE_BYTES, b_hi = a_lo + TC_PLANE_BYTES, b_lo = b_hi + TC_PLANE_BYTES;
           if (ks < n_main) {
@@ -208,27 +351,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             tma_load_3d(&mapWs, b_hi, &full_bar[stage], kofs, n0, 0);
             tma_load_3d(&mapWs, b_lo, &full_bar[stage], kofs, n0, 1);
           }
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (one lane) =====================
-    if (lane == 0) {
-      // instruction descriptor: D=f32, A=B=f16, K-major both, N=BN, M=128
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      int stage = 0; uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int as = it & 1;
-        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-        mbar_wait(&tempty_bar[as], aphase ^ 1);            // epilogue drained this accumulator pair
+  } else if (warp == TC_WARP_MMA) {
+    // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
+    // instruction descriptor: D=f32, A=B=f16, K-major both, N=BN, M=128
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    int stage = 0; uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(&tempty_bar[as], aphase ^ 1);            // epilogue drained this accumulator pair
+      tc_fence_after();
+      const uint32_t acc0 = tmem_base + (uint32_t)(as * 2 * BN);
+      const uint32_t acc1 = acc0 + (uint32_t)BN;
+      for (int ks = 0; ks < n_ksteps; ++ks) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t acc0 = tmem_base + (uint32_t)(as * 2 * BN);
-        const uint32_t acc1 = acc0 + (uint32_t)BN;
-        for (int ks = 0; ks < n_ksteps; ++ks) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
+        if (elect_one()) {
           const int kc = (ks < n_main) ? p.kc_main : p.kc_sc;
           const int row_bytes = kc * 2;
           uint8_t* st = smem + stage * TC_STAGE_BYTES;
@@ -244,119 +388,286 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           }
           umma_commit(&empty_bar[stage]);                  // frees the smem stage when these MMAs retire
           if (ks == n_ksteps - 1) umma_commit(&tfull_bar[as]);
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else {
     // ===================== epilogue warps (TMEM lane quadrant = warp % 4) =====================
-    const int quad = warp & 3;
+    const int quad = warp & 3, group = warp >> 2;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int as = it & 1;
-      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-      const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
-      const int n0 = nt * BN;
-      const long long q = (long long)mt * TC_BM + quad * 32 + lane;
-      // decode flat row -> (n, h, w)
-      bool valid = q < p.R;
-      int n = 0, h = 0, w = 0;
-      if (valid) {
-        n = (int)(q / p.Rimg);
-        const int rem = (int)(q - (long long)n * p.Rimg);
-        h = rem / p.P; w = rem - h * p.P;
-        valid = (h < p.H) && (w < p.W);
-      }
-      long long qo = q; long long Ro = p.R; int plane0 = 0;
-      if (p.split) {
-        qo = (long long)n * p.Rimg2 + (h >> 1) * p.P2 + (w >> 1);
-        Ro = p.R2;
-        plane0 = 2 * ((h & 1) * 2 + (w & 1));
-      }
-      mbar_wait(&tfull_bar[as], aphase);
-      tc_fence_after();
-      const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 2 * BN);
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r0[32], r1[32];
-        tmem_ld32(tbase + (uint32_t)c0, r0);
-        tmem_ld32(tbase + (uint32_t)(BN + c0), r1);
-        tmem_ld_wait();
-        if (valid) {
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            v[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]) * TC_LO_INV + s_bias[n0 + c0 + j];
-          if (p.res) {
-            const uint4* rh = reinterpret_cast<const uint4*>(p.res + (size_t)q * p.Cout + n0 + c0);
-            const uint4* rl = reinterpret_cast<const uint4*>(p.res + ((size_t)p.R + q) * p.Cout + n0 + c0);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint4 a = __ldg(rh + g), b = __ldg(rl + g);
-              const __half2* ah = reinterpret_cast<const __half2*>(&a);
-              const __half2* bl = reinterpret_cast<const __half2*>(&b);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float2 fh = __half22float2(ah[e]), fl = __half22float2(bl[e]);
-                v[g * 8 + e * 2] += fh.x + fl.x * TC_LO_INV;
-                v[g * 8 + e * 2 + 1] += fh.y + fl.y * TC_LO_INV;
-              }
-            }
-          }
-          if (p.out_raw) {
-            uint4* oh = reinterpret_cast<uint4*>(p.out_raw + ((size_t)plane0 * Ro + qo) * p.Cout + n0 + c0);
-            uint4* ol = reinterpret_cast<uint4*>(p.out_raw + ((size_t)(plane0 + 1) * Ro + qo) * p.Cout + n0 + c0);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint32_t hh[4], ll[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float x0 = v[g * 8 + e * 2], x1 = v[g * 8 + e * 2 + 1];
-                __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
-                hh[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-                ll[e] = pack_half2((x0 - __half2float(h0)) * TC_LO_SCALE, (x1 - __half2float(h1)) * TC_LO_SCALE);
-              }
-              oh[g] = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-              ol[g] = make_uint4(ll[0], ll[1], ll[2], ll[3]);
-            }
-          }
-          if (p.out_act || p.out_dense) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              v[j] = fmaxf(fmaf(v[j], s_scale[n0 + c0 + j], s_shift[n0 + c0 + j]), 0.f);
-          }
-          if (p.out_act) {
-            uint4* oh = reinterpret_cast<uint4*>(p.out_act + ((size_t)plane0 * Ro + qo) * p.Cout + n0 + c0);
-            uint4* ol = reinterpret_cast<uint4*>(p.out_act + ((size_t)(plane0 + 1) * Ro + qo) * p.Cout + n0 + c0);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint32_t hh[4], ll[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float x0 = v[g * 8 + e * 2], x1 = v[g * 8 + e * 2 + 1];
-                __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
-                hh[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-                ll[e] = pack_half2((x0 - __half2float(h0)) * TC_LO_SCALE, (x1 - __half2float(h1)) * TC_LO_SCALE);
-              }
-              oh[g] = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-              ol[g] = make_uint4(ll[0], ll[1], ll[2], ll[3]);
-            }
-          }
-          if (p.out_dense) {
-            float4* od = reinterpret_cast<float4*>(p.out_dense + (((size_t)n * p.H + h) * p.W + w) * p.Cout + n0 + c0);
-#pragma unroll
-            for (int g = 0; g < 8; ++g) od[g] = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
-    }
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it)
+      if ((it & 1) == group)
+        epilogue_tile(p, tile, it, quad, lane, tmem_base, tfull_bar, tempty_bar, s_bias, s_scale, s_shift);
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == TC_WARP_MMA) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
+  }
+}
+
+// ------------------------------------------------------------------ the slab kernel (3x3 stride 1)
+// Same roles and epilogue as conv_tc_kernel, but
+//  * the A operand of a tile is loaded ONCE per 64-channel chunk as a halo'd slab of
+//    128 + 2(W+1) + 2 consecutive flat rows; the 9 taps are 9 shared-memory matrix descriptors into
+//    that slab, shifted by (kh-1)(W+1)+(kw-1) rows (the swizzle is a function of the absolute smem
+//    address, so a row-shifted start is just a different address);
+//  * weights are RESIDENT in shared memory for the whole kernel when the layer's packed kernel fits
+//    (thin stages), otherwise they stream through a ring whose depth is whatever shared memory is
+//    left (the k-step loop is TMA-latency bound, not bandwidth bound: depth is what matters);
+//  * the 1x1 projection shortcut rides along as extra chunks with one tap.
+constexpr int SL_MAX_RING = 16;
+constexpr int SL_MAX_SLABS = 4;
+
+struct SlabParams {
+  int slab_rows, lead;          // rows per main slab (multiple of 8), rows in front of q0 (= W + 2)
+  int slab_bytes;               // bytes per plane of one slab buffer (1024-aligned)
+  int nslab;                    // slab ring depth (2..4)
+  int resident;                 // 1: all weight tiles stay in smem; 0: ring of `nring` stages
+  int nring;
+  int bplane_bytes;             // bytes of one weight tile plane (BN x kc_max x 2, 1024-aligned)
+};
+
+// Start address on ANY row boundary of a swizzled slab: measured on B200, the tensor core applies the
+// 128B/64B XOR swizzle to the absolute shared-memory address bits (exactly like TMA wrote them), so a
+// row-shifted start needs no base-offset field (setting (addr>>7)&7 there gives wrong results).
+__device__ __forceinline__ uint64_t make_desc_shifted(uint32_t saddr, int row_bytes) { return make_desc(saddr, row_bytes); }
+
+template <int KC, bool RESIDENT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapS,
+                    const __grid_constant__ CUtensorMap mapWm, const __grid_constant__ CUtensorMap mapWs,
+                    const TcParams p, const SlabParams sp) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int n_main = p.ntaps * p.chunks_main;
+  const int n_ksteps = n_main + p.chunks_sc;
+  const int nb = sp.resident ? n_ksteps : sp.nring;                    // weight slots in smem
+  uint8_t* slab_base = smem;                                           // [nslab][2 planes][slab_bytes]
+  uint8_t* b_base = smem + (size_t)sp.nslab * 2 * sp.slab_bytes;       // [nb][2 planes][bplane_bytes]
+  uint64_t* sfull_bar = reinterpret_cast<uint64_t*>(b_base + (size_t)nb * 2 * sp.bplane_bytes);
+  uint64_t* sempty_bar = sfull_bar + SL_MAX_SLABS;
+  uint64_t* bfull_bar = sempty_bar + SL_MAX_SLABS;
+  uint64_t* bempty_bar = bfull_bar + SL_MAX_RING;
+  uint64_t* tfull_bar = bempty_bar + SL_MAX_RING;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_base_slot + 2) + 15) & ~uintptr_t(15));   // float4 reads
+  float* s_scale = s_bias + p.Cout;
+  float* s_shift = s_scale + p.Cout;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int BN = p.BN;
+  const uint32_t tmem_cols = (4 * BN <= 128) ? 128u : (4 * BN <= 256 ? 256u : 512u);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SL_MAX_SLABS; ++s) { mbar_init(&sfull_bar[s], 1); mbar_init(&sempty_bar[s], 1); }
+    for (int s = 0; s < SL_MAX_RING; ++s) { mbar_init(&bfull_bar[s], 1); mbar_init(&bempty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == TC_WARP_MMA) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  for (int i = threadIdx.x; i < p.Cout; i += TC_THREADS) {
+    s_bias[i] = p.bias ? p.bias[i] : 0.f;
+    s_scale[i] = p.act_scale ? p.act_scale[i] : 1.f;
+    s_shift[i] = p.act_shift ? p.act_shift[i] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  const int n_chunks = p.chunks_main + p.chunks_sc;       // slabs per tile
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  // weight k-step index of (chunk c, tap): main steps are tap-major in K (k = tap*Cin + ci)
+  auto kstep_of = [&](int c, int tap) { return c < p.chunks_main ? tap * p.chunks_main + c : n_main + (c - p.chunks_main); };
+  auto kofs_of = [&](int c, int tap) {
+    return c < p.chunks_main ? (tap * p.chunks_main + c) * p.kc_main : n_main * p.kc_main + (c - p.chunks_main) * p.kc_sc;
+  };
+
+  if (warp == TC_WARP_TMA) {
+    // ===================== TMA producer (whole warp converged, one elected lane issues) =====================
+    {
+      if (sp.resident) {
+        // all weight tiles of this CTA's N tile (n_tiles == 1 in resident mode) under one barrier
+        if (elect_one()) {
+          uint32_t bytes = 0;
+          for (int c = 0; c < n_chunks; ++c) bytes += (uint32_t)((c < p.chunks_main ? p.ntaps * p.kc_main : p.kc_sc) * 2 * BN * 2);
+          mbar_expect_tx(&bfull_bar[0], bytes);
+          for (int c = 0; c < n_chunks; ++c) {
+            const bool main = c < p.chunks_main;
+            const CUtensorMap* wm = main ? &mapWm : &mapWs;
+            for (int tap = 0; tap < (main ? p.ntaps : 1); ++tap) {
+              const uint32_t b_hi = smem_u32(b_base + (size_t)kstep_of(c, tap) * 2 * sp.bplane_bytes);
+              const uint32_t lo_off = (uint32_t)(BN * (main ? p.kc_main : p.kc_sc) * 2);   // lo tile right behind the hi tile
+              tma_load_3d(wm, b_hi, &bfull_bar[0], kofs_of(c, tap), 0, 0);
+              tma_load_3d(wm, b_hi + lo_off, &bfull_bar[0], kofs_of(c, tap), 0, 1);
+            }
+          }
+        }
+        __syncwarp();
+      }
+      int sb = 0; uint32_t sphase = 0;        // slab ring
+      int bs = 0; uint32_t bphase = 0;        // weight ring
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+        const long long q0 = (long long)mt * TC_BM;
+        const int n0 = nt * BN;
+        for (int c = 0; c < n_chunks; ++c) {
+          const bool main = c < p.chunks_main;
+          const int kc = main ? p.kc_main : p.kc_sc;
+          const int rows = main ? sp.slab_rows : TC_BM;
+          mbar_wait(&sempty_bar[sb], sphase ^ 1);
+          if (elect_one()) {
+            const uint32_t dst = smem_u32(slab_base + (size_t)sb * 2 * sp.slab_bytes);
+            mbar_expect_tx(&sfull_bar[sb], (uint32_t)(2 * rows * kc * 2));
+            if (main) {
+              const int row0 = (int)(q0 - sp.lead);
+              tma_load_3d(&mapA, dst, &sfull_bar[sb], c * kc, row0, 0);
+              tma_load_3d(&mapA, dst + sp.slab_bytes, &sfull_bar[sb], c * kc, row0, 1);
+            } else {
+              const int ch = c - p.chunks_main;
+              tma_load_3d(&mapS, dst, &sfull_bar[sb], ch * kc, (int)q0, p.sc_plane);
+              tma_load_3d(&mapS, dst + sp.slab_bytes, &sfull_bar[sb], ch * kc, (int)q0, p.sc_plane + 1);
+            }
+          }
+          __syncwarp();
+          if (++sb == sp.nslab) { sb = 0; sphase ^= 1; }
+          if (!sp.resident) {
+            const CUtensorMap* wm = main ? &mapWm : &mapWs;
+            for (int tap = 0; tap < (main ? p.ntaps : 1); ++tap) {
+              mbar_wait(&bempty_bar[bs], bphase ^ 1);
+              if (elect_one()) {
+                const uint32_t b_hi = smem_u32(b_base + (size_t)bs * 2 * sp.bplane_bytes);
+                mbar_expect_tx(&bfull_bar[bs], (uint32_t)(2 * BN * kc * 2));
+                tma_load_3d(wm, b_hi, &bfull_bar[bs], kofs_of(c, tap), n0, 0);
+                tma_load_3d(wm, b_hi + (uint32_t)(BN * kc * 2), &bfull_bar[bs], kofs_of(c, tap), n0, 1);   // [B_hi ; B_lo] adjacent
+              }
+              __syncwarp();
+              if (++bs == sp.nring) { bs = 0; bphase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == TC_WARP_MMA) {
+    // ===================== MMA issuer: ONE elected lane runs the whole loop =====================
+    // The loop is issue-bound (one thread, dependent uniform-datapath ops at ~8 cycles each), so the
+    // instruction count per tcgen05.mma is what sets the speed of the thin layers:
+    //  * taps and k16 steps fully unrolled, descriptors = constant hi word + ONE 32-bit add per operand;
+    //  * the hi/lo products need only TWO instructions per k16 step: B_hi and B_lo tiles are adjacent in
+    //    shared memory, so  [acc0 | acc1] (+)= A_hi x [B_hi ; B_lo]  is a single N = 2*BN MMA, followed by
+    //    acc1 += A_lo x B_hi (N = BN).
+    if (elect_one()) {
+      const uint32_t idesc_n = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      const uint32_t idesc_2n = (1u << 4) | ((uint32_t)(BN >> 2) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      constexpr uint32_t ROWB = KC * 2, ROW16 = ROWB >> 4;
+      constexpr uint32_t DHI = ((8 * ROWB) >> 4) | (1u << 14) | ((ROWB == 128 ? 2u : 4u) << 29);
+      const uint32_t a_base0 = ((smem_u32(slab_base) & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t a_slab16 = (uint32_t)(2 * sp.slab_bytes) >> 4, a_lo16 = (uint32_t)sp.slab_bytes >> 4;
+      const uint32_t b_base0 = ((smem_u32(b_base) & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t b_slot16 = (uint32_t)(2 * sp.bplane_bytes) >> 4;
+      const uint32_t p_row16 = (uint32_t)p.P * ROW16;
+      const uint32_t tap0_16 = (uint32_t)(sp.lead - p.P - 1) * ROW16;      // slab row of tap (0,0), in 16 B units
+      int sb = 0; uint32_t sphase = 0;
+      int bs = 0; uint32_t bphase = 0;
+      int it = 0;
+      if (RESIDENT) { mbar_wait(&bfull_bar[0], 0); tc_fence_after(); }
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        if (p.dbg && blockIdx.x == 0 && it < 8) p.dbg[it * 4] = clock64();
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        if (p.dbg && blockIdx.x == 0 && it < 8) p.dbg[it * 4 + 1] = clock64();
+        const uint32_t acc0 = tmem_base + (uint32_t)(as * 2 * BN);
+        const uint32_t acc1 = acc0 + (uint32_t)BN;
+        uint32_t acc_on = 0;
+        for (int c = 0; c < p.chunks_main; ++c) {
+          mbar_wait(&sfull_bar[sb], sphase);
+          tc_fence_after();
+          if (p.dbg && blockIdx.x == 0 && it < 8 && c == 0) p.dbg[it * 4 + 2] = clock64();
+          uint32_t a_row = a_base0 + (uint32_t)sb * a_slab16 + tap0_16;
+          uint32_t b_res = b_base0 + (uint32_t)c * b_slot16;               // resident: slot of (tap 0, chunk c)
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+              uint32_t b0;
+              if (RESIDENT) {
+                b0 = b_res;
+                b_res += (uint32_t)p.chunks_main * b_slot16;
+              } else {
+                mbar_wait(&bfull_bar[bs], bphase);
+                tc_fence_after();
+                b0 = b_base0 + (uint32_t)bs * b_slot16;
+              }
+              const uint32_t a0 = a_row + (uint32_t)kw * ROW16;
+#pragma unroll
+              for (int kk = 0; kk < KC / 16; ++kk) {
+                const uint64_t dah = ((uint64_t)DHI << 32) | (a0 + 2u * kk), dal = ((uint64_t)DHI << 32) | (a0 + a_lo16 + 2u * kk);
+                const uint64_t dbh = ((uint64_t)DHI << 32) | (b0 + 2u * kk);
+                umma_f16(acc0, dah, dbh, idesc_2n, acc_on);                  // [acc0|acc1] (+)= Ah x [Bh;Bl]
+                umma_f16(acc1, dal, dbh, idesc_n, 1u);                       // acc1 += Al x Bh
+                acc_on = 1u;
+              }
+              if (!RESIDENT) {
+                umma_commit(&bempty_bar[bs]);
+                if (++bs == sp.nring) { bs = 0; bphase ^= 1; }
+              }
+            }
+            a_row += p_row16;
+          }
+          umma_commit(&sempty_bar[sb]);                     // slab free once its 9 taps have retired
+          if (p.chunks_sc == 0 && c == p.chunks_main - 1) umma_commit(&tfull_bar[as]);
+          if (++sb == sp.nslab) { sb = 0; sphase ^= 1; }
+        }
+        // 1x1 projection shortcut: chunks of kc_sc channels, one tap, no shift
+        for (int c = 0; c < p.chunks_sc; ++c) {
+          const uint32_t rowb = (uint32_t)p.kc_sc * 2;
+          const uint32_t dhi_s = ((8 * rowb) >> 4) | (1u << 14) | ((rowb == 128 ? 2u : 4u) << 29);
+          mbar_wait(&sfull_bar[sb], sphase);
+          tc_fence_after();
+          const uint32_t a0 = a_base0 + (uint32_t)sb * a_slab16;
+          uint32_t b0;
+          if (RESIDENT) b0 = b_base0 + (uint32_t)(n_main + c) * b_slot16;
+          else { mbar_wait(&bfull_bar[bs], bphase); tc_fence_after(); b0 = b_base0 + (uint32_t)bs * b_slot16; }
+          for (int kk = 0; kk < p.kc_sc / 16; ++kk) {
+            const uint64_t dah = ((uint64_t)dhi_s << 32) | (a0 + 2u * kk), dal = ((uint64_t)dhi_s << 32) | (a0 + a_lo16 + 2u * kk);
+            const uint64_t dbh = ((uint64_t)dhi_s << 32) | (b0 + 2u * kk);
+            umma_f16(acc0, dah, dbh, idesc_2n, 1u);
+            umma_f16(acc1, dal, dbh, idesc_n, 1u);
+          }
+          if (!RESIDENT) {
+            umma_commit(&bempty_bar[bs]);
+            if (++bs == sp.nring) { bs = 0; bphase ^= 1; }
+          }
+          umma_commit(&sempty_bar[sb]);
+          if (c == p.chunks_sc - 1) umma_commit(&tfull_bar[as]);
+          if (++sb == sp.nslab) { sb = 0; sphase ^= 1; }
+        }
+        if (p.dbg && blockIdx.x == 0 && it < 8) p.dbg[it * 4 + 3] = clock64();
+      }
+    }
+    __syncwarp();
+  } else {
+    const int quad = warp & 3, group = warp >> 2;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it)
+      if ((it & 1) == group)
+        epilogue_tile(p, tile, it, quad, lane, tmem_base, tfull_bar, tempty_bar, s_bias, s_scale, s_shift);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TC_WARP_MMA) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
   }
@@ -445,12 +756,61 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
   p.out_raw = reinterpret_cast<__half*>(d->out_raw);
   p.out_act = reinterpret_cast<__half*>(d->out_act);
   p.out_dense = d->out_dense;
+  p.dbg = reinterpret_cast<long long*>(d->dbg);
+  p.mma_mask = getenv("SAR_TC_MMAMASK") ? atoi(getenv("SAR_TC_MMAMASK")) : 7;
   SAR_REQUIRE(!(p.split && p.out_dense), SAR_ERR_BAD_ARG, "sar_conv_tc_fwd: dense output cannot be phase-split");
 
   const int ktot = d->ntaps * d->a_ch + (d->s ? d->s_ch : 0);
+  // slab path: plain 3x3 stride-1 taps on a non-split tensor whose halo'd slab fits shared memory
+  bool slab = d->ntaps == 9 && d->a_planes == 2;
+  for (int t = 0; slab && t < 9; ++t)
+    slab = d->tap_plane[t] == 0 && d->tap_row_off[t] == (t / 3 - 1) * p.P + (t % 3 - 1);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // N tile: minimise (rounds over the SMs) x (per-tile cost ~ BN + fixed) -- late, small maps have fewer
+  // M tiles than SMs and want a narrower N tile so more SMs share the layer
+  {
+    int best = p.BN; long long best_cost = -1;
+    for (int bn = p.BN; bn >= 32; bn >>= 1) {
+      if (d->cout % bn) continue;
+      const long long tiles = (long long)p.m_tiles * (d->cout / bn);
+      const long long cost = ((tiles + sms - 1) / sms) * (bn + 32);
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
+    }
+    p.BN = best; p.n_tiles = d->cout / p.BN;
+  }
+  SlabParams sp{};
+  sp.lead = p.P + 1;
+  sp.slab_rows = (TC_BM + 2 * p.P + 2 + 7) & ~7;
+  const int kc_max = (d->s && p.kc_sc > p.kc_main) ? p.kc_sc : p.kc_main;
+  sp.slab_bytes = (sp.slab_rows * kc_max * 2 + 1023) & ~1023;
+  if (sp.slab_bytes < TC_BM * kc_max * 2) sp.slab_bytes = TC_BM * kc_max * 2;
+  sp.bplane_bytes = p.BN * kc_max * 2;       // hi and lo tiles adjacent: [B_hi ; B_lo] is one 2*BN-row operand
+  if (sp.slab_rows > 192) slab = false;
+  const size_t fixed = 1024 + 512 + 3 * (size_t)d->cout * sizeof(float);     // align slack + barriers + epilogue vectors
+  const size_t budget = 227 * 1024 - fixed;
+  if (slab) {
+    const int n_ksteps = p.ntaps * p.chunks_main + p.chunks_sc;
+    const size_t wres = (size_t)n_ksteps * 2 * sp.bplane_bytes;
+    const size_t slab1 = 2 * (size_t)sp.slab_bytes;
+    if (p.n_tiles == 1 && wres + 2 * slab1 <= budget) {
+      sp.resident = 1;
+      sp.nring = 0;
+      sp.nslab = (int)((budget - wres) / slab1);
+    } else {
+      sp.resident = 0;
+      sp.nslab = 2;
+      sp.nring = (int)((budget - 2 * slab1) / (2 * (size_t)sp.bplane_bytes));
+      if (sp.nring > SL_MAX_RING) sp.nring = SL_MAX_RING;
+      if (sp.nring < 2) slab = false;
+    }
+    if (sp.nslab > SL_MAX_SLABS) sp.nslab = SL_MAX_SLABS;
+  }
+
   CUtensorMap mapA, mapS, mapWm, mapWs;
   int rc;
-  if ((rc = make_map(&mapA, d->a, d->a_rows, d->a_ch, d->a_planes, p.kc_main, TC_BM))) return rc;
+  if ((rc = make_map(&mapA, d->a, d->a_rows, d->a_ch, d->a_planes, p.kc_main, slab ? sp.slab_rows : TC_BM))) return rc;
   if ((rc = make_map(&mapWm, d->w, d->cout, ktot, 2, p.kc_main, p.BN))) return rc;
   if (d->s) {
     SAR_REQUIRE(d->s_rows > 0 && d->s_planes >= 2 && d->s_plane >= 0 && d->s_plane + 1 < d->s_planes, SAR_ERR_BAD_ARG,
@@ -460,14 +820,26 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
   } else {
     mapS = mapA; mapWs = mapWm;
   }
-  const size_t smem = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + 256 + 3 * (size_t)d->cout * sizeof(float);
-  cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) { set_error("sar_conv_tc_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < sms ? tiles : sms;
-  conv_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(mapA, mapS, mapWm, mapWs, p);
+  if (slab) {
+    const int nb = sp.resident ? (p.ntaps * p.chunks_main + p.chunks_sc) : sp.nring;
+    const size_t smem = fixed + (size_t)sp.nslab * 2 * sp.slab_bytes + (size_t)nb * 2 * sp.bplane_bytes;
+    auto launch = [&](auto kern) -> int {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) { set_error("sar_conv_tc_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+      kern<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(mapA, mapS, mapWm, mapWs, p, sp);
+      return 0;
+    };
+    int lrc;
+    if (p.kc_main == 64) lrc = sp.resident ? launch(conv_tc_slab_kernel<64, true>) : launch(conv_tc_slab_kernel<64, false>);
+    else lrc = sp.resident ? launch(conv_tc_slab_kernel<32, true>) : launch(conv_tc_slab_kernel<32, false>);
+    if (lrc) return lrc;
+  } else {
+    const size_t smem = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + 256 + 3 * (size_t)d->cout * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("sar_conv_tc_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    conv_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(mapA, mapS, mapWm, mapWs, p);
+  }
   return check_launch("sar_conv_tc_fwd");
 }

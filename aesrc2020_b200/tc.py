@@ -30,6 +30,7 @@ class sar_tc_conv(C.Structure):
         ("out_dense", C.c_void_p),
         ("out_split", C.c_int),
         ("B", C.c_int), ("H", C.c_int), ("W", C.c_int),
+        ("dbg", C.c_void_p),
     ]
 
 
@@ -142,7 +143,7 @@ def tap_table(kh: int, kw: int, stride: int, pad_t: int, pad_l: int, W_out: int)
 
 def conv_tc(a: Planes, w_packed: torch.Tensor, bias: torch.Tensor, *, out_hw: Tuple[int, int], taps, cout: int,
             short: Optional[Planes] = None, res: Optional[Planes] = None, out_raw: Optional[Planes] = None,
-            out_act: Optional[Planes] = None, act=None, out_dense: Optional[torch.Tensor] = None):
+            out_act: Optional[Planes] = None, act=None, out_dense: Optional[torch.Tensor] = None, dbg=None):
     """sar_conv_tc_fwd.  taps = (row_offsets, plane_bases)."""
     d = sar_tc_conv()
     d.a, d.a_rows, d.a_ch, d.a_planes = ptr(a.t), a.rows, a.C, a.nplanes
@@ -172,5 +173,6 @@ def conv_tc(a: Planes, w_packed: torch.Tensor, bias: torch.Tensor, *, out_hw: Tu
     d.out_dense = ptr(out_dense) if out_dense is not None else None
     d.out_split = 1 if split else 0
     d.B, d.H, d.W = a.B, H, W
+    d.dbg = ptr(dbg) if dbg is not None else None
     check(_shim.lib().sar_conv_tc_fwd(C.byref(d), stream_ptr()), "sar_conv_tc_fwd")
     ops._count(1)

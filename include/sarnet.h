@@ -127,6 +127,7 @@ typedef struct sar_tc_conv {
   float* out_dense;
   int out_split;
   int B, H, W;          /* output map geometry */
+  void* dbg;            /* optional device buffer of >= 64 int64 clock64() stamps of CTA 0 (profiling aid); NULL */
 } sar_tc_conv;
 int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream);
 

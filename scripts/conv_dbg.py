@@ -1,0 +1,26 @@
+import os, sys, io, contextlib
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from aesrc2020_b200 import model as mdl, utils as us, tc
+B = 64
+with contextlib.redirect_stdout(io.StringIO()):
+    model, _ = mdl.SAR_Net((500, 80, 1), disc_enable=True, res_type="res34", res_filters=32, mto="gvlad", vlad_clusters=64, ghost_clusters=8, metric_loss="arcface")
+eng = model.engine(); rn = eng.resnet
+x, _ = us.synthetic_batch(model.config, B, seed=1)
+xd = model._to_device("x_data", x["x_data"])
+calls = []
+orig = tc.conv_tc
+dbgs = []
+def timed(*a, **k):
+    d = torch.zeros(64, dtype=torch.int64, device="cuda"); dbgs.append(d)
+    orig(*a, dbg=d, **k)
+rn.forward(xd); torch.cuda.synchronize()
+tc.conv_tc = timed
+rn.forward(xd); torch.cuda.synchronize()
+for li in (2, 3, 8, 16, 28):
+    d = dbgs[li].cpu().tolist()
+    t0 = d[0]
+    print("layer", li)
+    for it in range(6):
+        m = [d[it*4+j] - t0 for j in range(4)]; e = [d[32+it*2+j] - t0 for j in range(2)]
+        print("  tile %d: mma start %6d  tempty ok %6d  slab ok %6d  issued %6d | epi: tfull %6d done %6d (epi %5d)" % (it, m[0], m[1], m[2], m[3], e[0], e[1], e[1]-e[0]))
