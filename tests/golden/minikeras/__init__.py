@@ -1,0 +1,507 @@
+"""minikeras -- a minimal EAGER stand-in for the Keras 2.2 / TF 1.13 primitives the reference
+imports, so that the reference's OWN source files (model.py, resnet.py, VLAD.py, losses.py under
+/root/reference) can be executed in this container to generate golden vectors.
+
+TEST INFRASTRUCTURE ONLY (used by tests/golden/make_golden.py, which must run where /root/reference exists; never imported by the product).
+What it pins: the graph wiring and the arithmetic the reference itself writes (layer order, which
+BN feeds which conv, where the shortcut taps, VLAD / margin-head / circle-loss formulas, loss
+plumbing).  What it does NOT pin: the third-party primitives themselves -- Conv2D 'same' padding,
+BatchNormalization eps, CuDNNGRU equations, LayerNormalization eps, ctc_batch_cost are restated here
+from the libraries' documented behaviour ([KERAS-SEMANTICS] in SURVEY.md), in numpy, independently
+of oracle/sarnet_oracle.py (different code: explicit tap loops, numpy GRU, numpy CTC DP).
+
+Tensors are `KT` objects wrapping float64 numpy arrays; layers run when called.  `Input(name=...)`
+takes its value from `FEED[name]`.  Every layer instance is appended to `LAYERS` in creation
+order (the reference's ResNet layers are unnamed; creation order is their only identity).
+"""
+import sys
+import types
+
+import numpy as np
+
+FEED = {}
+LAYERS = []
+RNG = np.random.RandomState(0)
+QUEUE = None            # optional list of (canonical_name, array): weights handed out in creation order
+USED = []               # (canonical_name, owning layer) for every weight taken from QUEUE
+K_EPS = 1e-7
+
+
+def reset(seed=0, queue=None):
+    """queue: weights in the creation order of the reference graph.  Every weight a layer creates
+    pops the next entry; its shape must match and, when the layer carries an explicit Keras name,
+    the entry's canonical name must start with it -- so a wiring/order mismatch between the
+    reference source and the canonical container fails loudly instead of silently permuting."""
+    global QUEUE
+    FEED.clear()
+    del LAYERS[:]
+    del USED[:]
+    RNG.seed(seed)
+    QUEUE = list(queue) if queue is not None else None
+
+
+def _take(layer, shape, make):
+    shape = tuple(int(s) for s in shape)
+    if QUEUE is None:
+        return make()
+    if not QUEUE:
+        raise AssertionError("weight queue exhausted at layer %r shape %r" % (layer.name, shape))
+    name, arr = QUEUE.pop(0)
+    arr = np.asarray(arr, dtype=np.float64)
+    if arr.shape != shape:
+        raise AssertionError("creation-order mismatch: %s has shape %r, layer %r wants %r" % (name, arr.shape, layer.name, shape))
+    owner = getattr(layer, "owner_name", None) or layer.name
+    if owner is not None and not name.startswith(owner + "/"):
+        raise AssertionError("creation-order mismatch: %s handed to layer %r" % (name, owner))
+    USED.append((name, layer))
+    return arr
+
+
+class KT:
+    """Eager tensor."""
+
+    def __init__(self, v):
+        self.v = np.asarray(v, dtype=np.float64)
+
+    @property
+    def shape(self):
+        return tuple(int(s) for s in self.v.shape)
+
+    def _b(self, o):
+        return o.v if isinstance(o, KT) else o
+
+    def __add__(self, o): return KT(self.v + self._b(o))
+    def __radd__(self, o): return KT(self._b(o) + self.v)
+    def __sub__(self, o): return KT(self.v - self._b(o))
+    def __rsub__(self, o): return KT(self._b(o) - self.v)
+    def __mul__(self, o): return KT(self.v * self._b(o))
+    def __rmul__(self, o): return KT(self._b(o) * self.v)
+    def __truediv__(self, o): return KT(self.v / self._b(o))
+    def __matmul__(self, o): return KT(self.v @ self._b(o))
+    def __neg__(self): return KT(-self.v)
+    def __pow__(self, o): return KT(self.v ** o)
+    def __getitem__(self, idx): return KT(self.v[idx])
+
+
+def _f32(a):
+    """weights are generated at float32 precision (stored fixtures are float32)"""
+    return np.asarray(np.asarray(a, dtype=np.float32), dtype=np.float64)
+
+
+def _init(shape, kind):
+    shape = tuple(int(s) for s in shape)
+    if kind in ("he_normal",):
+        fan_in = int(np.prod(shape[:-1]))
+        return _f32(RNG.randn(*shape) * np.sqrt(2.0 / fan_in))
+    if kind in ("glorot_uniform",):
+        fan_in, fan_out = int(np.prod(shape[:-1])), shape[-1]
+        lim = np.sqrt(6.0 / (fan_in + fan_out))
+        return _f32(RNG.uniform(-lim, lim, shape))
+    if kind == "orthogonal":
+        return _f32(RNG.randn(*shape) / np.sqrt(shape[-1] if len(shape) == 2 else np.prod(shape[:-1])))
+    if kind == "bias":
+        return _f32(RNG.randn(*shape) * 0.1)
+    raise ValueError(kind)
+
+
+# ----------------------------------------------------------------------------- layer base
+class Layer:
+    def __init__(self, name=None, **kwargs):
+        self.name = name
+        self.weights = {}
+        self.built = False
+        LAYERS.append(self)
+
+    def add_weight(self, shape=None, name=None, initializer="glorot_uniform", trainable=True, regularizer=None, **kw):
+        w = KT(_take(self, shape, lambda: _init(shape, initializer if isinstance(initializer, str) else "glorot_uniform")))
+        self.weights[name] = w
+        return w
+
+    def build(self, input_shape):
+        self.built = True
+
+    def __call__(self, x):
+        if not self.built:
+            shp = [t.shape for t in x] if isinstance(x, (list, tuple)) else x.shape
+            self.build(shp)
+            self.built = True
+        self.input = x
+        self.output = self.call(x)
+        return self.output
+
+    def compute_output_shape(self, input_shape):
+        return input_shape
+
+
+def same_pad(n, k, s):
+    out = -(-n // s)
+    total = max((out - 1) * s + k - n, 0)
+    return out, total // 2, total - total // 2
+
+
+class Conv2D(Layer):
+    def __init__(self, filters, kernel_size, strides=(1, 1), padding="valid", kernel_initializer="glorot_uniform",
+                 use_bias=True, kernel_regularizer=None, bias_regularizer=None, trainable=True, name=None, **kw):
+        super().__init__(name)
+        self.filters, self.ks, self.strides, self.padding, self.use_bias = filters, tuple(kernel_size), tuple(strides), padding, use_bias
+        self.kinit = kernel_initializer
+
+    def build(self, shp):
+        kshape = self.ks + (shp[-1], self.filters)
+        self.weights["kernel"] = KT(_take(self, kshape, lambda: _init(kshape, self.kinit if self.kinit in ("he_normal", "orthogonal") else "glorot_uniform")))
+        if self.use_bias:
+            self.weights["bias"] = KT(_take(self, (self.filters,), lambda: _init((self.filters,), "bias")))
+
+    def call(self, x):
+        v = x.v
+        B, H, W, C = v.shape
+        kh, kw = self.ks
+        sh, sw = self.strides
+        if self.padding == "same":
+            Ho, pt, pb = same_pad(H, kh, sh)
+            Wo, pl, pr = same_pad(W, kw, sw)
+            v = np.pad(v, ((0, 0), (pt, pb), (pl, pr), (0, 0)))
+        else:
+            Ho, Wo = (H - kh) // sh + 1, (W - kw) // sw + 1
+        out = np.zeros((B, Ho, Wo, self.filters))
+        k = self.weights["kernel"].v
+        for r in range(kh):                      # explicit tap loop (cross-correlation, HWIO kernel)
+            for c in range(kw):
+                patch = v[:, r:r + (Ho - 1) * sh + 1:sh, c:c + (Wo - 1) * sw + 1:sw, :]
+                out += patch @ k[r, c]
+        if self.use_bias:
+            out += self.weights["bias"].v
+        return KT(out)
+
+
+class BatchNormalization(Layer):
+    def __init__(self, axis=-1, name=None, **kw):
+        super().__init__(name)
+
+    def build(self, shp):
+        c = shp[-1]
+        self.weights["gamma"] = KT(_take(self, (c,), lambda: _f32(RNG.uniform(0.7, 1.3, c))))
+        self.weights["beta"] = KT(_take(self, (c,), lambda: _f32(RNG.randn(c) * 0.1)))
+        self.weights["moving_mean"] = KT(_take(self, (c,), lambda: _f32(RNG.randn(c) * 0.1)))
+        self.weights["moving_variance"] = KT(_take(self, (c,), lambda: _f32(RNG.uniform(0.6, 1.4, c))))
+
+    def call(self, x):
+        w = self.weights
+        return KT(w["gamma"].v * (x.v - w["moving_mean"].v) / np.sqrt(w["moving_variance"].v + 1e-3) + w["beta"].v)
+
+
+class MaxPooling2D(Layer):
+    def __init__(self, pool_size=(2, 2), strides=None, padding="valid", name=None, **kw):
+        super().__init__(name)
+        self.ps, self.st, self.padding = tuple(pool_size), tuple(strides or pool_size), padding
+
+    def call(self, x):
+        v = x.v
+        B, H, W, C = v.shape
+        (kh, kw), (sh, sw) = self.ps, self.st
+        Ho, pt, pb = same_pad(H, kh, sh)
+        Wo, pl, pr = same_pad(W, kw, sw)
+        assert self.padding == "same"
+        v = np.pad(v, ((0, 0), (pt, pb), (pl, pr), (0, 0)), constant_values=-np.inf)
+        out = np.full((B, Ho, Wo, C), -np.inf)
+        for r in range(kh):
+            for c in range(kw):
+                out = np.maximum(out, v[:, r:r + (Ho - 1) * sh + 1:sh, c:c + (Wo - 1) * sw + 1:sw, :])
+        return KT(out)
+
+
+class Activation(Layer):
+    def __init__(self, activation, name=None, **kw):
+        super().__init__(name)
+        self.activation = activation
+
+    def call(self, x):
+        return KT(_act(x.v, self.activation))
+
+
+def _act(v, a):
+    if a is None or a == "linear":
+        return v
+    if a == "relu":
+        return np.maximum(v, 0.0)
+    if a == "tanh":
+        return np.tanh(v)
+    if a == "softmax":
+        e = np.exp(v - v.max(-1, keepdims=True))
+        return e / e.sum(-1, keepdims=True)
+    raise ValueError(a)
+
+
+class Add(Layer):
+    def call(self, xs):
+        return KT(xs[0].v + xs[1].v)
+
+
+class Dense(Layer):
+    def __init__(self, units, activation=None, use_bias=True, kernel_initializer="glorot_uniform", kernel_regularizer=None,
+                 bias_regularizer=None, kernel_constraint=None, name=None, **kw):
+        super().__init__(name)
+        self.units, self.activation, self.use_bias, self.kinit = units, activation, use_bias, kernel_initializer
+
+    def build(self, shp):
+        kshape = (shp[-1], self.units)
+        self.weights["kernel"] = KT(_take(self, kshape, lambda: _init(kshape, self.kinit if self.kinit == "he_normal" else "glorot_uniform")))
+        if self.use_bias:
+            self.weights["bias"] = KT(_take(self, (self.units,), lambda: _init((self.units,), "bias")))
+
+    def call(self, x):
+        y = x.v @ self.weights["kernel"].v
+        if self.use_bias:
+            y = y + self.weights["bias"].v
+        return KT(_act(y, self.activation))
+
+
+class Lambda(Layer):
+    def __init__(self, function, output_shape=None, name=None, **kw):
+        super().__init__(name)
+        self.function = function
+
+    def call(self, x):
+        return self.function(x)
+
+
+class Dropout(Layer):
+    def __init__(self, rate, name=None, **kw):
+        super().__init__(name)
+
+    def call(self, x):
+        return x
+
+
+class Reshape(Layer):
+    def __init__(self, target_shape, name=None, **kw):
+        super().__init__(name)
+        self.target = tuple(target_shape)
+
+    def call(self, x):
+        return KT(x.v.reshape((x.v.shape[0],) + self.target))
+
+
+class GlobalAveragePooling1D(Layer):
+    def call(self, x):
+        return KT(x.v.mean(axis=1))
+
+
+class Flatten(Layer):
+    def call(self, x):
+        return KT(x.v.reshape(x.v.shape[0], -1))
+
+
+class AveragePooling2D(Layer):
+    pass
+
+
+class CuDNNGRU(Layer):
+    """[KERAS-SEMANTICS] reset_after GRU, gate order z|r|h, bias (6u,) = [input biases | recurrent biases]."""
+
+    def __init__(self, units, return_sequences=False, kernel_regularizer=None, bias_regularizer=None, name=None, **kw):
+        super().__init__(name)
+        self.units, self.return_sequences = units, return_sequences
+
+    def build(self, shp):
+        u = self.units
+        self.weights["kernel"] = KT(_take(self, (shp[-1], 3 * u), lambda: _init((shp[-1], 3 * u), "glorot_uniform")))
+        self.weights["recurrent_kernel"] = KT(_take(self, (u, 3 * u), lambda: _f32(RNG.randn(u, 3 * u) / np.sqrt(u))))
+        self.weights["bias"] = KT(_take(self, (6 * u,), lambda: _f32(RNG.randn(6 * u) * 0.1)))
+
+    def run(self, v, reverse):
+        u = self.units
+        W, U, b = self.weights["kernel"].v, self.weights["recurrent_kernel"].v, self.weights["bias"].v
+        B, S, _ = v.shape
+        h = np.zeros((B, u))
+        outs = np.zeros((B, S, u))
+        sig = lambda a: 1.0 / (1.0 + np.exp(-a))
+        for t in (range(S - 1, -1, -1) if reverse else range(S)):
+            xi = v[:, t] @ W + b[:3 * u]
+            hr = h @ U + b[3 * u:]
+            z = sig(xi[:, :u] + hr[:, :u])
+            r = sig(xi[:, u:2 * u] + hr[:, u:2 * u])
+            hh = np.tanh(xi[:, 2 * u:] + r * hr[:, 2 * u:])
+            h = z * h + (1 - z) * hh
+            outs[:, t] = h
+        return outs, h
+
+
+CuDNNLSTM = CuDNNGRU
+
+
+class Bidirectional(Layer):
+    def __init__(self, layer, merge_mode="concat", name=None, **kw):
+        super().__init__(name)
+        LAYERS.remove(layer)                    # the wrapped layer is owned by this one
+        self.fwd = layer
+        self.bwd = CuDNNGRU(layer.units, return_sequences=layer.return_sequences)
+        LAYERS.remove(self.bwd)
+        self.merge_mode = merge_mode
+
+    def build(self, shp):
+        self.fwd.owner_name = "%s/forward" % self.name if self.name else None
+        self.bwd.owner_name = "%s/backward" % self.name if self.name else None
+        self.fwd.build(shp)
+        self.bwd.build(shp)
+        for d, l in (("forward", self.fwd), ("backward", self.bwd)):
+            for k, w in l.weights.items():
+                self.weights[d + "/" + k] = w
+
+    def call(self, x):
+        of, hf = self.fwd.run(x.v, False)
+        ob, hb = self.bwd.run(x.v, True)
+        if self.fwd.return_sequences:
+            return KT(np.concatenate([of, ob], -1))
+        return KT(np.concatenate([hf, hb], -1))
+
+
+class LayerNormalization(Layer):
+    """[KERAS-SEMANTICS] keras_layer_normalization: eps = K.epsilon()**2, biased variance."""
+
+    def __init__(self, name=None, **kw):
+        super().__init__(name)
+
+    def build(self, shp):
+        c = shp[-1]
+        self.weights["gamma"] = KT(_take(self, (c,), lambda: _f32(RNG.uniform(0.7, 1.3, c))))
+        self.weights["beta"] = KT(_take(self, (c,), lambda: _f32(RNG.randn(c) * 0.1)))
+
+    def call(self, x):
+        m = x.v.mean(-1, keepdims=True)
+        var = ((x.v - m) ** 2).mean(-1, keepdims=True)
+        return KT((x.v - m) / np.sqrt(var + K_EPS * K_EPS) * self.weights["gamma"].v + self.weights["beta"].v)
+
+
+def Input(shape=None, dtype=None, name=None, **kw):
+    return KT(FEED[name])
+
+
+class Model:
+    def __init__(self, inputs=None, outputs=None, name=None):
+        self.inputs, self.outputs, self.name = inputs, outputs, name
+
+    def summary(self):
+        pass
+
+    def load_weights(self, *a, **k):
+        raise RuntimeError("minikeras cannot load .h5")
+
+    def compile(self, **kw):
+        self.compiled = kw
+
+    def get_layer(self, name=None):
+        for l in LAYERS:
+            if l.name == name:
+                return l
+        raise ValueError(name)
+
+
+# ----------------------------------------------------------------------------- backend (K) and tf
+def _ctc_batch_cost(labels, y_pred, input_length, label_length):
+    """[KERAS-SEMANTICS] K.ctc_batch_cost: log(p + eps) -> tf.nn.ctc_loss (softmax again), blank = C-1."""
+    p = y_pred.v
+    B, S, C = p.shape
+    out = np.zeros((B, 1))
+    for b in range(B):
+        T, L = int(np.asarray(input_length.v)[b].reshape(-1)[0]), int(np.asarray(label_length.v)[b].reshape(-1)[0])
+        lab = [int(x) for x in labels.v[b, :L]]
+        lg = np.log(p[b, :T] + K_EPS)
+        q = np.exp(lg - lg.max(-1, keepdims=True))
+        q = q / q.sum(-1, keepdims=True)
+        ext = [C - 1]
+        for l in lab:
+            ext += [l, C - 1]
+        n = len(ext)
+        alpha = np.zeros(n)                       # plain-probability DP with per-step rescaling
+        alpha[0] = q[0, ext[0]]
+        if n > 1:
+            alpha[1] = q[0, ext[1]]
+        logscale = 0.0
+        for t in range(1, T):
+            new = np.zeros(n)
+            for s in range(n):
+                a = alpha[s] + (alpha[s - 1] if s >= 1 else 0.0)
+                if s >= 2 and ext[s] != C - 1 and ext[s] != ext[s - 2]:
+                    a += alpha[s - 2]
+                new[s] = a * q[t, ext[s]]
+            sc = new.sum()
+            if sc <= 0:
+                raise ValueError("Not enough time for target transition sequence")
+            alpha = new / sc
+            logscale += np.log(sc)
+        tot = alpha[-1] + (alpha[-2] if n > 1 else 0.0)
+        out[b, 0] = -(np.log(tot) + logscale)
+    return KT(out)
+
+
+def _l2n(x, axis):
+    v = x.v
+    return KT(v / np.sqrt(np.maximum((v * v).sum(axis=axis, keepdims=True), 1e-12)))
+
+
+def _install():
+    def mod(name):
+        m = types.ModuleType(name)
+        sys.modules[name] = m
+        return m
+
+    keras = mod("keras")
+    layers = mod("keras.layers")
+    for n in ("Input", "Conv2D", "BatchNormalization", "MaxPooling2D", "Flatten", "AveragePooling2D", "Activation", "Add",
+              "Dense", "Lambda", "Dropout", "Bidirectional", "GlobalAveragePooling1D", "Reshape", "Layer"):
+        setattr(layers, n, globals()[n])
+    cr = mod("keras.layers.cudnn_recurrent")
+    cr.CuDNNGRU, cr.CuDNNLSTM = CuDNNGRU, CuDNNLSTM
+    layers.cudnn_recurrent = cr
+    models = mod("keras.models")
+    models.Model = Model
+    K = mod("keras.backend")
+    K.int_shape = lambda x: x.shape
+    K.shape = lambda x: x.shape
+    K.squeeze = lambda x, axis: KT(np.squeeze(x.v, axis))
+    K.expand_dims = lambda x, axis=-1: KT(np.expand_dims(x.v, axis))
+    K.max = lambda x, axis=None, keepdims=False: KT(x.v.max(axis=axis, keepdims=keepdims))
+    K.exp = lambda x: KT(np.exp(x.v))
+    K.sum = lambda x, axis=None, keepdims=False: KT(x.v.sum(axis=tuple(axis) if isinstance(axis, list) else axis, keepdims=keepdims))
+    K.reshape = lambda x, shape: KT(x.v.reshape([int(s) for s in shape]))
+    K.clip = lambda x, lo, hi: KT(np.clip(x.v, lo, hi))
+    K.epsilon = lambda: K_EPS
+    K.l2_normalize = lambda x, axis=None: _l2n(x, axis)
+    K.ctc_batch_cost = _ctc_batch_cost
+    reg = mod("keras.regularizers")
+    reg.l2 = lambda *a, **k: None
+    reg.get = lambda x: x
+    con = mod("keras.constraints")
+    con.unit_norm = lambda *a, **k: None
+    utils = mod("keras.utils")
+    utils.multi_gpu_model = lambda m, gpus=1: m
+    opt = mod("keras.optimizers")
+    opt.Adam = lambda *a, **k: ("adam", a, k)
+    engine = mod("keras.engine")
+    engine.Layer = Layer
+    keras.layers, keras.models, keras.backend, keras.regularizers = layers, models, K, reg
+    keras.constraints, keras.utils, keras.optimizers, keras.engine = con, utils, opt, engine
+    kln = mod("keras_layer_normalization")
+    kln.LayerNormalization = LayerNormalization
+    tf = mod("tensorflow")
+    nn = types.SimpleNamespace()
+    nn.l2_normalize = lambda x, axis=None: _l2n(x, axis)
+    nn.softmax = lambda x: KT(_act(x.v, "softmax"))
+    nn.relu = lambda x: KT(np.maximum(x.v, 0.0))
+
+    def sce(labels=None, logits=None):
+        lg = logits.v
+        lse = np.log(np.exp(lg - lg.max(-1, keepdims=True)).sum(-1)) + lg.max(-1)
+        return KT(-(labels.v * (lg - lse[:, None])).sum(-1))
+    nn.softmax_cross_entropy_with_logits = sce
+    tf.nn = nn
+    tf.acos = lambda x: KT(np.arccos(x.v))
+    tf.cos = lambda x: KT(np.cos(x.v))
+    tf.multiply = lambda a, b: KT(a.v * b.v)
+    tf.stop_gradient = lambda x: x
+    tf.cast = lambda x, dt: x
+    tf.float32 = "float32"
+
+
+_install()

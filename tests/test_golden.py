@@ -1,0 +1,151 @@
+"""Golden-vector parity: tests/golden/*.npz hold outputs of the reference's OWN source
+(/root/reference model.py / resnet.py / VLAD.py / losses.py) executed on the minikeras eager
+stand-in by tests/golden/make_golden.py.  Nothing here reads /root/reference.
+
+ * not gpu: the float64 oracle must reproduce every fixture (pins the oracle's graph wiring and
+   its restatement of VladPooling / margin heads / circle loss / loss weights);
+ * gpu: the CUDA path through the C ABI must reproduce the same fixtures within north_star's
+   1e-3 relative tolerance (1e-6 floor).
+"""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import rel_err, norm_err, REL_TOL
+from oracle import sarnet_oracle as O
+from aesrc2020_b200.config import SARConfig
+from aesrc2020_b200 import weights as W, utils as us
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = sorted(os.path.basename(p)[len("sarnet_"):-4] for p in glob.glob(os.path.join(GOLD, "sarnet_*.npz")))
+
+
+def load_case(name):
+    with np.load(os.path.join(GOLD, "sarnet_%s.npz" % name)) as z:
+        g = {k.replace("|", "/"): z[k] for k in z.files}
+    meta = json.loads(str(g["meta"]))
+    cfg = SARConfig(input_shape=(meta["T"], 80, 1), **meta["kwargs"])
+    weights = W.init_weights(cfg, seed=meta["seed"])
+    l1 = sum(float(np.abs(v.astype(np.float64)).sum()) for v in weights.values())
+    assert abs(l1 - float(g["weights_l1"])) <= 1e-9 * l1, "init_weights drifted from the fixture generator"
+    x, y = us.synthetic_batch(cfg, meta["B"], seed=meta["input_seed"], lengths=meta["lengths"],
+                              label_len_range=tuple(meta["label_len_range"]))
+    assert abs(float(np.abs(x["x_data"].astype(np.float64)).sum()) - float(g["in_l1/x_data"])) < 1e-6
+    for k in x:
+        if k != "x_data":
+            assert np.array_equal(x[k], g["in/" + k]), k
+    return cfg, meta, weights, x, y, g
+
+
+def test_fixture_inventory():
+    assert len(CASES) == 8 and os.path.exists(os.path.join(GOLD, "layers.npz"))
+    assert {"cfg1_res18_avg_softmax", "cfg2_gvlad_arcface", "cfg3_ctc_circle_bigru", "cfg4_vlad_cosface",
+            "cfg5_gvlad_circle_ctc"} <= set(CASES)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_reproduces_reference_graph(name):
+    cfg, meta, weights, x, y, g = load_case(name)
+    ref = O.sar_net_forward(weights, x, **cfg.model_kwargs(), return_intermediates=True)
+    for n in cfg.output_names():
+        assert tuple(ref[n].shape) == g[n].shape
+        assert rel_err(ref[n], g[n], floor=1e-12) < 1e-8, n
+    B = meta["B"]
+    inter = {"resnet_seq": ref["resnet"].reshape(B, -1, ref["resnet"].shape[-1]), "cnn_lin": ref["cnn_lin"],
+             "crnn": ref["crnn"]}
+    for k in ("ar_ds", "integration", "embedding", "ctc_pred"):
+        if k in ref:
+            inter[k] = ref[k]
+    for k, v in inter.items():
+        assert k in g, k
+        assert norm_err(v, g[k]) < (1e-9 if g[k].dtype == np.float64 else 1e-6), k
+    # compile()'d losses, loss weights and accuracies as the reference's dicts define them
+    if cfg.ar_enable:
+        tgt = torch.as_tensor(y["y_accent"], dtype=torch.float64)
+        res = O.sar_net_losses(ref, tgt, ctc_enable=cfg.ctc_enable, ar_enable=cfg.ar_enable,
+                               disc_enable=cfg.disc_enable, bn_dim=cfg.bn_dim, metric_loss=cfg.metric_loss,
+                               margin=cfg.margin)
+        for n in cfg.output_names():
+            assert abs(float(res[n + "_loss"]) - float(g["loss/" + n])) <= 1e-8 * max(1.0, abs(float(g["loss/" + n]))), n
+            if "acc/" + n in g:
+                assert float(res[n + "_acc"]) == float(g["acc/" + n]) if n + "_acc" in res else True
+        assert abs(float(res["loss"]) - float(g["loss/total"])) <= 1e-8 * max(1.0, abs(float(g["loss/total"])))
+    lw = O.loss_weights(cfg.ctc_enable, cfg.ar_enable, cfg.disc_enable, cfg.bn_dim)
+    assert lw == cfg.loss_weights()
+    for n in cfg.output_names():
+        assert lw[n] == float(g["loss_weight/" + n]), n
+
+
+def _layers():
+    with np.load(os.path.join(GOLD, "layers.npz")) as z:
+        return {k.replace("|", "/"): z[k] for k in z.files}
+
+
+def test_oracle_layers_match_reference_source():
+    g = _layers()
+    t = lambda a: torch.as_tensor(a, dtype=torch.float64)
+    for mode, K in (("vlad", 5), ("gvlad", 6)):
+        got = O.vlad_pooling(t(g[mode + "/feat"]), t(g[mode + "/score"]), t(g[mode + "/centers"]), mode, K)
+        assert rel_err(got, g[mode + "/out"], floor=1e-12) < 1e-9, mode
+    for key, kind, m in (("SphereFace_1.35", "sphereface", 1.35), ("CosFace_0.35", "cosface", 0.35),
+                         ("ArcFace_0.5", "arcface", 0.5), ("ArcFace_0.3", "arcface", 0.3)):
+        logits = O.face_logits(t(g["face/x"]), t(g["face/%s/W" % key]), t(g["face/y"]), kind, m)
+        assert rel_err(torch.softmax(logits, -1), g["face/%s/out" % key], floor=1e-12) < 1e-9, key
+    for gm, m in ((256, 0.25), (256, 0.2), (64, 0.4)):
+        got = O.circle_loss(t(g["circle/y"]), t(g["circle/cos"]), float(gm), m)
+        assert rel_err(got, g["circle/g%d_m%g" % (gm, m)], floor=1e-9) < 1e-9
+
+
+# ------------------------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_cuda_path_reproduces_reference_graph(cuda_device, name):
+    from aesrc2020_b200 import model as mdl
+    cfg, meta, weights, x, y, g = load_case(name)
+    model, _ = mdl.SAR_Net((meta["T"], 80, 1), **meta["kwargs"], weights=weights)
+    outs = model.predict(x, batch_size=meta["B"])
+    outs = outs if isinstance(outs, list) else [outs]
+    for n, got in zip(cfg.output_names(), outs):
+        assert got.shape == g[n].shape
+        assert rel_err(got, g[n]) < REL_TOL, n
+    dev_out = model.forward_device(x, want_intermediates=True)
+    for k in ("cnn_lin", "crnn", "ar_ds", "integration", "embedding", "ctc_pred"):
+        if k in g and k in dev_out:
+            assert norm_err(dev_out[k], g[k]) < 1e-4, k
+    if cfg.ar_enable:
+        got = model.evaluate(x, y, batch_size=meta["B"])
+        for n in cfg.output_names():
+            want = float(g["loss/" + n])
+            assert abs(got[n + "_loss"] - want) <= REL_TOL * max(abs(want), 1e-3), (n, got[n + "_loss"], want)
+        want = float(g["loss/total"])
+        assert abs(got["loss"] - want) <= REL_TOL * max(abs(want), 1e-3)
+
+
+@pytest.mark.gpu
+def test_cuda_layers_match_reference_source(cuda_device):
+    """VladPooling / margin-head call surfaces of the mirror vs the reference source's outputs."""
+    from aesrc2020_b200 import VLAD as vd, losses as ls
+    g = _layers()
+    c = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float32)).cuda()
+    for mode, K, G in (("vlad", 5, 0), ("gvlad", 6, 3)):
+        lay = vd.VladPooling(mode=mode, k_centers=K, g_centers=G, name="p")
+        feat, score = c(g[mode + "/feat"]), c(g[mode + "/score"])
+        lay.build([tuple(feat.shape), tuple(score.shape)])
+        lay.set_weights([g[mode + "/centers"]])
+        got = lay([feat, score])
+        assert tuple(got.shape) == lay.compute_output_shape([tuple(feat.shape), tuple(score.shape)])
+        assert rel_err(got, g[mode + "/out"], floor=1e-4) < REL_TOL, mode
+    for key, cls, m in (("SphereFace_1.35", ls.SphereFace, 1.35), ("CosFace_0.35", ls.CosFace, 0.35),
+                        ("ArcFace_0.5", ls.ArcFace, 0.5), ("ArcFace_0.3", ls.ArcFace, 0.3)):
+        lay = cls(n_classes=8, m=m, name="h")
+        x, y = c(g["face/x"]), c(g["face/y"])
+        lay.build([tuple(x.shape), tuple(y.shape)])
+        lay.set_weights([g["face/%s/W" % key]])
+        assert rel_err(lay([x, y]), g["face/%s/out" % key]) < REL_TOL, key
+    for gm, m in ((256, 0.25), (256, 0.2), (64, 0.4)):
+        got = ls.circle_loss(c(g["circle/y"]), c(g["circle/cos"]), gamma=gm, margin=m)
+        assert rel_err(got, g["circle/g%d_m%g" % (gm, m)], floor=1e-3) < REL_TOL
