@@ -174,6 +174,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     ap.add_argument("--ref-batch", type=int, default=32, help="utterances per step of the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="no CUDA-graph replay (for ncu launch lists)")
     ap.add_argument("--rotate", type=int, default=16, help="distinct input batches rotated through (L2 hygiene)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
@@ -214,7 +215,7 @@ def main():
 
     def step_device(i, graphed=True):
         x = dev_batches[i % args.rotate]
-        out = eng.forward_graphed(x) if graphed else eng.forward(x)
+        out = eng.forward_graphed(x) if (graphed and not args.eager) else eng.forward(x)
         vec = out["loss_vector"]
         if world > 1:
             tdist.all_reduce(vec)

@@ -136,12 +136,13 @@ def layer_cases():
     """VladPooling / margin heads / circle_loss called directly at odd sizes (no SAR_Net)."""
     rng = np.random.RandomState(77)
     out = {}
-    for mode, K, G, S, D in (("vlad", 5, 0, 7, 12), ("gvlad", 6, 3, 9, 16)):
+    # *256: hidden_dim-wide descriptors (the width the CUDA kernel is built for) at odd K / G / S
+    for mode, K, G, S, D in (("vlad", 5, 0, 7, 12), ("gvlad", 6, 3, 9, 16), ("vlad256", 5, 0, 7, 256), ("gvlad256", 6, 3, 9, 256)):
         feat = rng.randn(3, 1, S, D)
         score = rng.randn(3, 1, S, K + G) * 2
         cen = rng.randn(K + G, D).astype(np.float32)
         mk.reset(queue=[("p/centers", cen)])
-        lay = ref_vlad.VladPooling(mode=mode, k_centers=K, g_centers=G, name="p")
+        lay = ref_vlad.VladPooling(mode=mode.replace("256", ""), k_centers=K, g_centers=G, name="p")
         res = lay([mk.KT(feat), mk.KT(score)])
         assert lay.compute_output_shape([feat.shape, score.shape]) == (3, K * D)
         out.update({"%s/feat" % mode: feat, "%s/score" % mode: score, "%s/centers" % mode: cen, "%s/out" % mode: res.v})

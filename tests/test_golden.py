@@ -88,8 +88,9 @@ def _layers():
 def test_oracle_layers_match_reference_source():
     g = _layers()
     t = lambda a: torch.as_tensor(a, dtype=torch.float64)
-    for mode, K in (("vlad", 5), ("gvlad", 6)):
-        got = O.vlad_pooling(t(g[mode + "/feat"]), t(g[mode + "/score"]), t(g[mode + "/centers"]), mode, K)
+    for mode, K in (("vlad", 5), ("gvlad", 6), ("vlad256", 5), ("gvlad256", 6)):
+        got = O.vlad_pooling(t(g[mode + "/feat"]), t(g[mode + "/score"]), t(g[mode + "/centers"]),
+                             mode.replace("256", ""), K)
         assert rel_err(got, g[mode + "/out"], floor=1e-12) < 1e-9, mode
     for key, kind, m in (("SphereFace_1.35", "sphereface", 1.35), ("CosFace_0.35", "cosface", 0.35),
                          ("ArcFace_0.5", "arcface", 0.5), ("ArcFace_0.3", "arcface", 0.3)):
@@ -131,8 +132,8 @@ def test_cuda_layers_match_reference_source(cuda_device):
     from aesrc2020_b200 import VLAD as vd, losses as ls
     g = _layers()
     c = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float32)).cuda()
-    for mode, K, G in (("vlad", 5, 0), ("gvlad", 6, 3)):
-        lay = vd.VladPooling(mode=mode, k_centers=K, g_centers=G, name="p")
+    for mode, K, G in (("vlad256", 5, 0), ("gvlad256", 6, 3)):      # vlad.cu is built for D == hidden_dim == 256
+        lay = vd.VladPooling(mode=mode.replace("256", ""), k_centers=K, g_centers=G, name="p")
         feat, score = c(g[mode + "/feat"]), c(g[mode + "/score"])
         lay.build([tuple(feat.shape), tuple(score.shape)])
         lay.set_weights([g[mode + "/centers"]])
