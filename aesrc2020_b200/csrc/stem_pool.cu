@@ -9,6 +9,7 @@
 // the (T/2)x40xF0 conv map (2.56 MB / utterance at T=500) never leaves shared memory.
 //
 // One CTA = one utterance x PH=4 pooled rows (9 conv rows, 23 input rows).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace sar {
@@ -147,6 +148,10 @@ __global__ void __launch_bounds__(SP_THREADS, 2) stem_pool_kernel(StemP p) {
   }
 }
 
+int stem_tc_launch(const float* x, const float* w, const float* bias, const float* scale, const float* shift,
+                   void* planes, int B, int T, int D, int F0, int Hc, int pt, int Wc, int pl, int Hp, int ppt,
+                   int Wp, int ppl, cudaStream_t stream);      // stem_tc.cu
+
 static inline void same_pad_host(int n_in, int k, int s, int* n_out, int* pad_before) {
   *n_out = (n_in + s - 1) / s;
   int total = (*n_out - 1) * s + k - n_in;
@@ -171,6 +176,12 @@ extern "C" int sar_stem_pool_fwd(const float* x, const float* w, const float* bi
   same_pad_host(D, 7, 2, &p.Wc, &p.pl);
   same_pad_host(p.Hc, 3, 2, &p.Hp, &p.ppt);
   same_pad_host(p.Wc, 3, 2, &p.Wp, &p.ppl);
+  // D == 80, F0 == 64 (every res34 stem, default res18): tensor-core kernel (stem_tc.cu); else CUDA-core FFMA below
+  if (!getenv("SAR_STEM_FFMA")) {
+    const int rc = stem_tc_launch(x, w, bias, scale, shift, planes, B, T, D, F0, p.Hc, p.pt, p.Wc, p.pl, p.Hp, p.ppt,
+                                  p.Wp, p.ppl, (cudaStream_t)stream);
+    if (rc != SAR_ERR_UNSUPPORTED) return rc;
+  }
   SAR_REQUIRE(p.Wc % 4 == 0, SAR_ERR_UNSUPPORTED, "sar_stem_pool_fwd: feature dim must give a conv width multiple of 4 (D=%d)", D);
   p.XW = ((8 * (p.Wc / 4 - 1) + 13) + 3) & ~3;      // widest column any thread touches, rounded to 4
   if (p.XW < D + p.pl + 4) p.XW = (D + p.pl + 7) & ~3;

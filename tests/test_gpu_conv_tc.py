@@ -126,3 +126,31 @@ def test_outputs_phase_split_for_a_strided_consumer(cuda_device):
 def test_many_tiles_persistent_loop(cuda_device):
     """More tiles than SMs: every CTA loops, the TMEM accumulator pair double-buffers."""
     _case(48, 125, 20, 32, 32, 1)                     # 48*126*21/128 = 993 tiles
+
+
+@pytest.mark.parametrize("T,B,F0", [(500, 3, 64), (300, 2, 64), (37, 1, 64), (7, 2, 64), (801, 1, 64), (200, 150, 64),
+                                    (200, 2, 32), (37, 1, 16)])
+def test_stem_pool_matches_oracle(cuda_device, T, B, F0):
+    """Fused stem (conv 7x7/s2 + bias + BN + ReLU + max-pool 3x3/s2) vs the oracle's three primitives:
+    F0 == 64 runs the tcgen05 kernel (stem_tc.cu), other widths the CUDA-core kernel (stem_pool.cu).
+    Odd conv heights (T=37 -> Hc=19, T=801) exercise the leading pool pad row; B=150 > #SMs the item loop."""
+    from aesrc2020_b200 import tc
+    from aesrc2020_b200.config import same_pad
+    rng = np.random.RandomState(T + F0)
+    x = _f32(rng.rand(B, T, 80, 1))
+    w = _f32(rng.randn(7, 7, 1, F0) * np.sqrt(2.0 / 49))
+    b = _f32(rng.randn(F0) * 0.1)
+    p = {"bn/gamma": t64(_f32(rng.uniform(0.7, 1.3, F0))), "bn/beta": t64(_f32(rng.randn(F0) * 0.1)),
+         "bn/moving_mean": t64(_f32(rng.randn(F0) * 0.1)), "bn/moving_variance": t64(_f32(rng.uniform(0.6, 1.4, F0)))}
+    want = O.maxpool_same(O.bn_relu(O.conv2d(t64(x), t64(w), t64(b), 2, "same"), p, "bn"))
+    scale = p["bn/gamma"] / torch.sqrt(p["bn/moving_variance"] + O.BN_EPS)
+    shift = p["bn/beta"] - p["bn/moving_mean"] * scale
+    Hp, Wp = want.shape[1], want.shape[2]
+    out = tc.alloc_planes(B, Hp, Wp, F0, False, "cuda")
+    tc.stem_pool(dev(x), dev(w), dev(b), dev(scale.numpy()), dev(shift.numpy()), out)
+    got = tc.unpack(out)
+    assert tuple(got.shape) == tuple(want.shape)
+    assert norm_err(got, want) < 2e-6
+    # pad rows / columns of the planes stay exactly zero
+    t = out.t.view(2, B, Hp + 1, Wp + 1, F0)
+    assert float(t[:, :, Hp].abs().sum()) == 0.0 and float(t[:, :, :, Wp].abs().sum()) == 0.0
