@@ -12,7 +12,7 @@ LIB = os.path.join(HERE, "libsarnet_sm100.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-DSAR_COMPILED_ARCH=100",
-         "-Xcompiler", "-fPIC", "-DSAR_BUILD"]
+         "-Xcompiler", "-fPIC", "-DSAR_BUILD"] + os.environ.get("SAR_NVCC_EXTRA", "").split()
 
 
 def sources():

@@ -21,6 +21,17 @@
 
 namespace sar {
 
+#ifdef SAR_STEM_PROFILE     // build with SAR_NVCC_EXTRA=-DSAR_STEM_PROFILE: CTA 0 prints per-role cycle counts
+#define ST_PROF_DECL long long pr_wait = 0, pr_work = 0, pr_pool = 0, pr_t = clock64(), pr_t0 = pr_t;
+#define ST_PROF(acc) { const long long _n = clock64(); acc += _n - pr_t; pr_t = _n; }
+#define ST_PROF_PRINT(role) if (blockIdx.x == 0 && lane == 0 && (warp & 7) == 0) \
+    printf("stem_tc %s: total %lld wait %lld work %lld pool %lld\n", role, clock64() - pr_t0, pr_wait, pr_work, pr_pool);
+#else
+#define ST_PROF_DECL
+#define ST_PROF(acc)
+#define ST_PROF_PRINT(role)
+#endif
+
 constexpr int ST_WC = 40;                 // conv width  (D = 80)
 constexpr int ST_WP = 20;                 // pooled width
 constexpr int ST_F0 = 64;
@@ -29,14 +40,20 @@ constexpr int ST_PL = 2;                  // TF-SAME left pad of the 7-wide kern
 constexpr int ST_PH = 4;                  // pooled rows per item
 constexpr int ST_CR = 2 * ST_PH + 1;      // conv rows per item (9)
 constexpr int ST_IR = 2 * (ST_CR - 1) + 7;   // input rows per item (23)
-constexpr int ST_XW = 88;                 // x_s row pitch in floats (2 + 80 + 6 zero columns)
+constexpr int ST_XW = 88;                 // x_s row pitch in halfs: 4 zero columns + 80 + 4 zero columns (input col c at c + 4)
+constexpr int ST_XPLANE = 23 * 88;        // halfs per hi (or lo) plane of one x buffer
 constexpr int ST_TROWS = 3;               // conv rows per MMA tile
 constexpr int ST_TILES = ST_CR / ST_TROWS;   // 3
 constexpr int ST_MROWS = ST_TROWS * ST_WC;   // 120 live rows of the M = 128 tile
-constexpr int ST_THREADS = 288;           // warps 0-3 epilogue (TMEM quadrant = warp), 4-7 builders, 8 MMA
+// Warp roles.  The SM's schedulers favour the HIGHEST warp id of a sub-partition, and a warp polling an mbarrier
+// still takes issue slots: the epilogue/pool warps (the critical path) get the high ids, the builders (which
+// mostly wait for a free A stage) the low ids and a sleeping wait.
+constexpr int ST_THREADS = 544;           // warps 0-7 builders, 8-15 epilogue (TMEM quadrant = warp & 3, column half = (warp >> 2) & 1), 16 MMA
+constexpr int ST_WARP_MMA = 16;
 constexpr int ST_APLANE = 16384;          // 128 rows x 128 B
 constexpr int ST_XBUF = 8192;             // >= 23 * 88 * 4
-constexpr int ST_CS_BYTES = ST_CR * ST_WC * 256;
+constexpr int ST_CPITCH = 272;              // conv-row buffer: 64 fp32 + 16 B pad per position (conflict-free STS.128 by position / LDS.128 by chunk)
+constexpr int ST_CS_BYTES = ST_CR * ST_WC * ST_CPITCH;
 
 struct StemTcP {
   const float* x; const float* w; const float* bias; const float* scale; const float* shift;
@@ -46,11 +63,12 @@ struct StemTcP {
 
 __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const StemTcP p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // offset arithmetic on the __shared__ array keeps the address space: LDS/STS instead of generic LD/ST
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* a_base = smem;                                   // [2 stages][hi, lo][16 KB]
   uint8_t* w_base = a_base + 4 * ST_APLANE;                 // [W_hi rows 0..63 ; W_lo rows 64..127] x 128 B
-  uint8_t* c_base = w_base + ST_APLANE;                     // conv rows: [360 positions][64 fp32], 16 B chunks XOR (pos & 15)
-  float* x_s = reinterpret_cast<float*>(c_base + ST_CS_BYTES);          // [2][23][88]
+  uint8_t* c_base = w_base + ST_APLANE;                     // conv rows: [360 positions][pitch 272 B]
+  __half* x_s = reinterpret_cast<__half*>(c_base + ST_CS_BYTES);        // [2 buffers][hi, lo][23][88] fp16
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(x_s) + 2 * ST_XBUF);
   uint64_t* empty_bar = full_bar + 2;
   uint64_t* tfull_bar = empty_bar + 2;
@@ -62,12 +80,12 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const StemTcP p)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&full_bar[s], 128); mbar_init(&empty_bar[s], 1);
-      mbar_init(&tfull_bar[s], 1);  mbar_init(&tempty_bar[s], 4);
+      mbar_init(&full_bar[s], 8); mbar_init(&empty_bar[s], 1);
+      mbar_init(&tfull_bar[s], 1);  mbar_init(&tempty_bar[s], 8);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) tmem_alloc(tmem_slot, 256);
+  if (warp == ST_WARP_MMA) tmem_alloc(tmem_slot, 256);
   if (threadIdx.x < ST_F0) {
     const float sc = __ldg(p.scale + threadIdx.x);
     s_sc[threadIdx.x] = sc;
@@ -84,10 +102,11 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const StemTcP p)
   const int Rimg = (p.Hp + 1) * (ST_WP + 1);
   const long long R = (long long)p.B * Rimg;
 
-  if (warp >= 4 && warp < 8) {
+  if (warp < 8) {
     // ===================== builders: weights once, then x rows -> A tiles =====================
-    const int b = threadIdx.x - 128;
-    for (int i = b; i < 49 * ST_F0; i += 128) {
+    // 256 threads: thread (m = b & 127, half = b >> 7) converts kernel rows 0..3 / 4..6 of A row m
+    const int b = threadIdx.x;
+    for (int i = b; i < 49 * ST_F0; i += 256) {
       const int f = i & 63, k = i >> 6;                     // HWIO (7,7,1,64): i = (kr*7 + kc)*64 + f
       const int kr = k / 7, kc = k - kr * 7;
       const float wv = __ldg(p.w + i);
@@ -97,13 +116,13 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const StemTcP p)
       *reinterpret_cast<__half*>(w_base + off) = h;
       *reinterpret_cast<__half*>(w_base + 8192 + off) = l;
     }
-    float4 xr[4];
+    float4 xr[2];
     auto load_x = [&](int item) {
       const int n = item / p.bands, band = item - n * p.bands;
       const int hi0 = 2 * (2 * band * ST_PH - p.ppt) - p.pt;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int idx = b + 128 * j;
+      for (int j = 0; j < 2; ++j) {
+        const int idx = b + 256 * j;
         const int r = idx / 20, c4 = idx - r * 20;
         const int hi = hi0 + r;
         xr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -111,67 +130,74 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const StemTcP p)
           xr[j] = __ldg(reinterpret_cast<const float4*>(p.x + ((size_t)n * p.T + hi) * ST_D) + c4);
       }
     };
-    auto store_x = [&](float* xb) {
+    // every input sample is split into fp16 hi/lo ONCE here (a sample is used by up to 28 A elements)
+    auto store_x = [&](__half* xb) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int idx = b + 128 * j;
+      for (int j = 0; j < 2; ++j) {
+        const int idx = b + 256 * j;
         const int r = idx / 20, c4 = idx - r * 20;
         if (idx < ST_IR * 20) {
-          float2* d = reinterpret_cast<float2*>(xb + r * ST_XW + ST_PL + 4 * c4);
-          d[0] = make_float2(xr[j].x, xr[j].y);
-          d[1] = make_float2(xr[j].z, xr[j].w);
+          const __half2 h01 = __floats2half2_rn(xr[j].x, xr[j].y), h23 = __floats2half2_rn(xr[j].z, xr[j].w);
+          const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+          const __half2 l01 = __floats2half2_rn((xr[j].x - f01.x) * 2048.f, (xr[j].y - f01.y) * 2048.f);
+          const __half2 l23 = __floats2half2_rn((xr[j].z - f23.x) * 2048.f, (xr[j].w - f23.y) * 2048.f);
+          __half* d = xb + r * ST_XW + 4 + 4 * c4;
+          *reinterpret_cast<uint2*>(d) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+          *reinterpret_cast<uint2*>(d + ST_XPLANE) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
         }
       }
     };
-    const int m = b;
+    const int m = b & 127;
+    const int kr0 = (b >> 7) ? 4 : 0, kr1 = (b >> 7) ? 7 : 4;
     const int mr = m / ST_WC, mw = m - mr * ST_WC;
     int g = 0, k = 0;
+    ST_PROF_DECL
     if ((int)blockIdx.x < p.n_items) load_x(blockIdx.x);
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++k) {
-      float* xb = x_s + (k & 1) * (ST_XBUF / 4);
+      __half* xb = x_s + (k & 1) * (ST_XBUF / 2);
       store_x(xb);
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 256);
       if (item + (int)gridDim.x < p.n_items) load_x(item + gridDim.x);
+      ST_PROF(pr_pool)
       for (int tile = 0; tile < ST_TILES; ++tile, ++g) {
         const int s = g & 1;
-        mbar_wait(&empty_bar[s], ((uint32_t)(g >> 1) & 1u) ^ 1u);
+        while (!mbar_try_wait(&empty_bar[s], ((uint32_t)(g >> 1) & 1u) ^ 1u)) __nanosleep(64);
+        ST_PROF(pr_wait)
         if (m < ST_MROWS) {
           uint8_t* arow = a_base + s * 2 * ST_APLANE + m * 128;
-          const float* src = xb + (2 * (ST_TROWS * tile + mr)) * ST_XW + 2 * mw;
-#pragma unroll
-          for (int kr = 0; kr < 7; ++kr) {
-            const float2* s2 = reinterpret_cast<const float2*>(src + kr * ST_XW);
-            uint32_t hh[4], ll[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 v = s2[e];
-              const __half2 h2 = __floats2half2_rn(v.x, v.y);
-              const float2 hf = __half22float2(h2);
-              const __half2 l2 = __floats2half2_rn((v.x - hf.x) * 2048.f, (v.y - hf.y) * 2048.f);
-              hh[e] = *reinterpret_cast<const uint32_t*>(&h2);
-              ll[e] = *reinterpret_cast<const uint32_t*>(&l2);
-            }
+          // chunk (m, kr) = 8 consecutive samples starting at input column 2*mw - 2 = storage column 2*mw + 2
+          const __half* src = xb + (2 * (ST_TROWS * tile + mr)) * ST_XW + 2 * mw + 2;
+#pragma unroll 4
+          for (int kr = kr0; kr < kr1; ++kr) {
+            const uint32_t* sh = reinterpret_cast<const uint32_t*>(src + kr * ST_XW);
+            const uint32_t* sl = reinterpret_cast<const uint32_t*>(src + kr * ST_XW + ST_XPLANE);
             const uint32_t co = (uint32_t)((kr ^ (m & 7)) << 4);
-            *reinterpret_cast<uint4*>(arow + co) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-            *reinterpret_cast<uint4*>(arow + ST_APLANE + co) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+            *reinterpret_cast<uint4*>(arow + co) = make_uint4(sh[0], sh[1], sh[2], sh[3]);
+            *reinterpret_cast<uint4*>(arow + ST_APLANE + co) = make_uint4(sl[0], sl[1], sl[2], sl[3]);
           }
         }
         fence_proxy_async();
-        mbar_arrive(&full_bar[s]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[s]);
+        ST_PROF(pr_work)
       }
     }
-  } else if (warp == 8) {
+    ST_PROF_PRINT("builder")
+  } else if (warp == ST_WARP_MMA) {
     // ===================== MMA issuer =====================
     const uint32_t idesc_128 = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t idesc_64 = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint64_t dbh = make_desc(smem_u32(w_base), 128);
     int g = 0;
+    ST_PROF_DECL
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       for (int tile = 0; tile < ST_TILES; ++tile, ++g) {
         const int s = g & 1;
         const uint32_t ph = (uint32_t)(g >> 1) & 1u;
         mbar_wait(&tempty_bar[s], ph ^ 1u);
+        ST_PROF(pr_wait)
         mbar_wait(&full_bar[s], ph);
+        ST_PROF(pr_pool)
         tc_fence_after();
         if (elect_one()) {
           const uint64_t dah = make_desc(smem_u32(a_base + s * 2 * ST_APLANE), 128);
@@ -186,90 +212,104 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const StemTcP p)
           umma_commit(&tfull_bar[s]);
         }
         __syncwarp();
+        ST_PROF(pr_work)
       }
     }
+    ST_PROF_PRINT("mma (wait=tempty pool=full)")
   } else {
     // ===================== epilogue warps: TMEM -> conv rows in smem -> max-pool -> planes =====================
-    const int m = threadIdx.x;                       // TMEM lane
+    const int quad = warp & 3, chalf = (warp >> 2) & 1;
+    const int et = threadIdx.x - 256;                // 0..255 within the epilogue group
+    const int m = quad * 32 + lane;                  // TMEM lane = A row
     const int P = ST_WP + 1;
+    const int pj = et & 15;                 // pool role: 4-channel chunk (constant per thread)
+    const float4 sc4 = *reinterpret_cast<const float4*>(s_sc + 4 * pj);
+    const float4 sh4 = *reinterpret_cast<const float4*>(s_sh + 4 * pj);
     int g = 0;
+    ST_PROF_DECL
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const int n = item / p.bands, band = item - n * p.bands;
       const int hp0 = band * ST_PH;
       const int hc0 = 2 * hp0 - p.ppt;
+      const int rlo = max(0, -hc0), rhi = min(ST_CR - 1, p.Hc - 1 - hc0);     // conv rows of this item inside the map
       for (int tile = 0; tile < ST_TILES; ++tile, ++g) {
         const int s = g & 1;
         mbar_wait(&tfull_bar[s], (uint32_t)(g >> 1) & 1u);
+        ST_PROF(pr_wait)
         tc_fence_after();
-        const int hc = hc0 + ST_TROWS * tile + m / ST_WC;
-        const bool live = m < ST_MROWS;
-        const bool inside = hc >= 0 && hc < p.Hc;
+        // raw conv sums acc0 + acc1/2048 of my 32 channels -> swizzled conv-row buffer (BN/ReLU happen in the pool)
         const int pos = tile * ST_MROWS + m;
-        uint8_t* crow = c_base + (size_t)pos * 256;
-        const uint32_t tb = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(s * 128);
+        uint8_t* crow = c_base + pos * ST_CPITCH;
+        const uint32_t tb = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * 128 + 32 * chalf);
+        uint32_t r0[32], r1[32];
+        tmem_ld32(tb, r0);
+        tmem_ld32(tb + 64u, r1);
+        tmem_ld_wait();
+        if (m < ST_MROWS) {
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t r0[32], r1[32];
-          tmem_ld32(tb + (uint32_t)(32 * half), r0);
-          tmem_ld32(tb + 64u + (uint32_t)(32 * half), r1);
-          tmem_ld_wait();
-          if (live) {
+          for (int q = 0; q < 8; ++q) {
+            float o[4];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              float o[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int f = 32 * half + 4 * q + e;
-                const float acc = fmaf(__uint_as_float(r1[4 * q + e]), 1.f / 2048.f, __uint_as_float(r0[4 * q + e]));
-                o[e] = inside ? fmaxf(fmaf(acc, s_sc[f], s_sh[f]), 0.f) : -INFINITY;
-              }
-              const int j = 8 * half + q;
-              *reinterpret_cast<float4*>(crow + ((j ^ (pos & 15)) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
-            }
+            for (int e = 0; e < 4; ++e)
+              o[e] = fmaf(__uint_as_float(r1[4 * q + e]), 1.f / 2048.f, __uint_as_float(r0[4 * q + e]));
+            const int j = 8 * chalf + q;
+            *reinterpret_cast<float4*>(crow + (j << 4)) = make_float4(o[0], o[1], o[2], o[3]);
           }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[s]);
+        ST_PROF(pr_work)
       }
-      named_bar_sync(2, 128);
-      // ---- 3x3/s2 max-pool of the 9 conv rows: (pooled position, 4-channel chunk) per thread-item
-#pragma unroll 2
-      for (int i = 0; i < (ST_PH * ST_WP * 16) / 128; ++i) {
-        const int idx = m + 128 * i;
-        const int j = idx & 15, pp = idx >> 4;
+      named_bar_sync(2, 256);
+      // ---- BN + ReLU + 3x3/s2 max-pool of the 9 conv rows: (pooled position, 4-channel chunk) per thread-item.
+      // relu(max(.)) = max(0, .): start from 0 and skip rows / columns outside the conv map.
+#pragma unroll 1
+      for (int i = 0; i < (ST_PH * ST_WP * 16) / 256; ++i) {
+        const int pp = (et >> 4) + 16 * i;
         const int dh = pp / ST_WP, wp = pp - dh * ST_WP;
         const int hp = hp0 + dh;
         if (hp >= p.Hp) continue;
-        float4 mx = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        // taps outside the conv map are CLAMPED onto a valid tap of the same window (a duplicate never changes
+        // a max), so there is no masking: 9 loads at row/column offsets, BN, max with 0 (= ReLU)
+        const uint8_t* cb = c_base + (pj << 4);
+        int ro[3], co[3];
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
+        for (int a = 0; a < 3; ++a) ro[a] = min(max(2 * dh + a, rlo), rhi) * (ST_WC * ST_CPITCH);
 #pragma unroll
-          for (int bb = 0; bb < 3; ++bb) {
-            const int wc = 2 * wp - p.ppl + bb;
-            if (wc < 0 || wc >= ST_WC) continue;
-            const int pos = (2 * dh + a) * ST_WC + wc;
-            const float4 v = *reinterpret_cast<const float4*>(c_base + (size_t)pos * 256 + ((j ^ (pos & 15)) << 4));
-            mx.x = fmaxf(mx.x, v.x); mx.y = fmaxf(mx.y, v.y); mx.z = fmaxf(mx.z, v.z); mx.w = fmaxf(mx.w, v.w);
-          }
+        for (int bb = 0; bb < 3; ++bb) co[bb] = min(max(2 * wp - p.ppl + bb, 0), ST_WC - 1) * ST_CPITCH;
+        float4 v[9];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int bb = 0; bb < 3; ++bb) v[3 * a + bb] = *reinterpret_cast<const float4*>(cb + ro[a] + co[bb]);
+        float4 mx = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          mx.x = fmaxf(mx.x, fmaf(v[k].x, sc4.x, sh4.x));
+          mx.y = fmaxf(mx.y, fmaf(v[k].y, sc4.y, sh4.y));
+          mx.z = fmaxf(mx.z, fmaf(v[k].z, sc4.z, sh4.z));
+          mx.w = fmaxf(mx.w, fmaf(v[k].w, sc4.w, sh4.w));
         }
         const __half2 h01 = __floats2half2_rn(mx.x, mx.y), h23 = __floats2half2_rn(mx.z, mx.w);
         const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
         const __half2 l01 = __floats2half2_rn((mx.x - f01.x) * 2048.f, (mx.y - f01.y) * 2048.f);
         const __half2 l23 = __floats2half2_rn((mx.z - f23.x) * 2048.f, (mx.w - f23.y) * 2048.f);
         const long long row = (long long)n * Rimg + (long long)hp * P + wp;
-        *reinterpret_cast<uint2*>(p.planes + (size_t)row * ST_F0 + 4 * j) =
+        *reinterpret_cast<uint2*>(p.planes + (size_t)row * ST_F0 + 4 * pj) =
             make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
-        *reinterpret_cast<uint2*>(p.planes + ((size_t)R + row) * ST_F0 + 4 * j) =
+        *reinterpret_cast<uint2*>(p.planes + ((size_t)R + row) * ST_F0 + 4 * pj) =
             make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
       }
-      named_bar_sync(2, 128);
+      named_bar_sync(2, 256);
+      ST_PROF(pr_pool)
     }
+    ST_PROF_PRINT("epilogue")
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == ST_WARP_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
   }
