@@ -39,6 +39,7 @@ SIGNATURES = {
     "sar_maxpool2d_fwd": (c_int, [c_fp, c_fp] + [c_int] * 10 + [C.c_void_p]),
     "sar_affine_relu_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_ll, c_int, c_int, C.c_void_p]),
     "sar_layernorm_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_ll, c_int, c_f, C.c_void_p]),
+    "sar_layernorm_planes_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_ll, c_int, c_ll, c_int, c_f, C.c_void_p]),
     "sar_bigru_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, C.c_void_p]),
     "sar_vlad_fwd": (c_int, [c_fp] * 6 + [c_int] * 5 + [C.c_void_p]),
     "sar_avgpool_fwd": (c_int, [c_fp, c_fp, c_int, c_int, c_int, C.c_void_p]),

@@ -1,4 +1,5 @@
 // api.cu -- error channel and library identification for libsarnet_sm100.so
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace sar {
@@ -8,6 +9,11 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("SAR_NO_PDL"); on = (e && e[0] && e[0] != '0') ? 0 : 1; }
+  return on != 0;
 }
 }  // namespace sar
 

@@ -95,6 +95,8 @@ bigru_kernel(const float* __restrict__ xp, const float* __restrict__ rec, const 
 #pragma unroll
   for (int r = 0; r < GRU_CL; ++r) remote[r] = cluster.map_shared_rank(h_s, r);
 
+  pdl_wait();            // everything above read only the recurrent weights
+  pdl_trigger();
   auto xrow = [&](int step) {
     const int tt = dir ? (S - 1 - step) : step;
     return xp + (((size_t)(b0 + gb) * S + tt) * 2 + dir) * U3 + unit;
@@ -223,7 +225,7 @@ extern "C" int sar_bigru_fwd(const float* xp, const float* rec, const float* rbi
   if (smem > 180 * 1024) { smem = 0; stage_out = 0; }      // very long sequences: write through
   cudaError_t e = cudaFuncSetAttribute(bigru_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(180 * 1024));
   if (e != cudaSuccess) { set_error("sar_bigru_fwd: %s", cudaGetErrorString(e)); return (int)e; }
-  bigru_kernel<<<grid, GRU_THREADS, smem, (cudaStream_t)stream>>>(xp, rec, rbias, out, B, S, seq, stage_out);
+  launch_k(bigru_kernel, dim3(grid), dim3(GRU_THREADS), smem, (cudaStream_t)stream, xp, rec, rbias, out, B, S, seq, stage_out);
   seq &= 1;
   return check_launch("sar_bigru_fwd");
 }

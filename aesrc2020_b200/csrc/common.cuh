@@ -28,6 +28,31 @@ inline int check_launch(const char* what) {
     }                                           \
   } while (0)
 
+// ---- programmatic dependent launch (PDL): every kernel of the step is launched with
+// programmaticStreamSerialization, so its CTAs may become resident (and run their prologue: barrier init, TMEM
+// allocation, constant weights -> shared memory) while the previous kernel of the stream drains.  Device side:
+// pdl_wait() before the first access to anything a previous kernel wrote (or that it may still read), then
+// pdl_trigger() so the NEXT kernel's prologue overlaps this kernel's body.  SAR_NO_PDL=1 disables the attribute
+// (the device instructions are no-ops then).
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -25,6 +25,8 @@ constexpr int BM = 128, BN = 64, BK = 16, TM = 8, TN = 4;
 
 template <bool VEC_A>
 __global__ void __launch_bounds__(256) conv_ffma_kernel(ConvP p) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN];
 
@@ -196,7 +198,7 @@ extern "C" int sar_conv2d_fwd(const float* x, const float* w_hwio, const float* 
           B, H, W, Cin, Ho, Wo, Cout, kh, kw, stride, pad_t, pad_l, act, (int)M, kh * kw * Cin};
   dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((Cout + BN - 1) / BN));
   cudaStream_t st = (cudaStream_t)stream;
-  if (Cin % 8 == 0) conv_ffma_kernel<true><<<grid, 256, 0, st>>>(p);
-  else conv_ffma_kernel<false><<<grid, 256, 0, st>>>(p);
+  if (Cin % 8 == 0) launch_k(conv_ffma_kernel<true>, dim3(grid), dim3(256), 0, st, p);
+  else launch_k(conv_ffma_kernel<false>, dim3(grid), dim3(256), 0, st, p);
   return check_launch("sar_conv2d_fwd");
 }

@@ -64,6 +64,7 @@ struct TcParams {
   __half* out_raw; __half* out_act; float* out_dense;
   long long* dbg;                        // optional: clock64 timestamps of CTA 0 (profiling aid)
   int mma_mask;                          // experiment: which of the 3 hi/lo products to issue (7 = all)
+  int act_kind;                          // activated outputs: 0 relu(scale*v+shift), 1 identity, 2 tanh(v)
 };
 
 // ------------------------------------------------------------------ epilogue (shared by both kernels)
@@ -162,7 +163,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, int tile, int i
 #pragma unroll
         for (int g = 0; g < 4; ++g) split_store8(v + 8 * g, oh + 8 * g, ol + 8 * g);
       }
-      if (p.out_act || p.out_dense) {
+      if ((p.out_act || p.out_dense) && p.act_kind == 0) {
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
           const float4 s4 = *reinterpret_cast<const float4*>(s_scale + n0 + c0 + 4 * g);
@@ -172,6 +173,9 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, int tile, int i
           v[4 * g + 2] = fmaxf(fmaf(v[4 * g + 2], s4.z, t4.z), 0.f);
           v[4 * g + 3] = fmaxf(fmaf(v[4 * g + 3], s4.w, t4.w), 0.f);
         }
+      } else if ((p.out_act || p.out_dense) && p.act_kind == 2) {      // Dense(..., activation='tanh'), model.py:35-42
+#pragma unroll
+        for (int g = 0; g < 32; ++g) v[g] = tanhf(v[g]);
       }
       if (p.out_act) {
         __half* oh = p.out_act + ((size_t)plane0 * Ro + qo) * p.Cout + n0 + c0;
@@ -234,6 +238,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const int n_main = p.ntaps * p.chunks_main;
   const int n_ksteps = n_main + p.chunks_sc;
   const int total_tiles = p.m_tiles * p.n_tiles;
+  pdl_wait();          // everything above touched only constants (bias / BN affines) and on-chip state
+  pdl_trigger();
 
   if (warp == TC_WARP_TMA) {
     // ===================== TMA producer (whole warp converged, one elected lane issues) =====================
@@ -360,6 +366,7 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     const TcParams p, const SlabParams sp) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const long long t_entry = p.dbg ? clock64() : 0;
   const int n_main = p.ntaps * p.chunks_main;
   const int n_ksteps = n_main + p.chunks_sc;
   const int nb = sp.resident ? n_ksteps : sp.nring;                    // weight slots in smem
@@ -399,6 +406,7 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[61] = clock64();     // prologue done
 
   const int n_chunks = p.chunks_main + p.chunks_sc;       // slabs per tile
   const int total_tiles = p.m_tiles * p.n_tiles;
@@ -430,6 +438,8 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         }
         __syncwarp();
       }
+      pdl_wait();                             // the resident weights (constants) are already in flight
+      pdl_trigger();
       int sb = 0; uint32_t sphase = 0;        // slab ring
       int bs = 0; uint32_t bphase = 0;        // weight ring
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -575,6 +585,7 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     __syncwarp();
   } else {
     const int quad = warp & 3, group = warp >> 2;
+    pdl_wait();                               // identity-shortcut rows and the output planes
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it)
       if ((it & 1) == group)
@@ -587,6 +598,7 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
   }
+  if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) { p.dbg[62] = t_entry; p.dbg[63] = clock64(); }
 }
 
 // ------------------------------------------------------------------ host side
@@ -636,8 +648,9 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
   SAR_REQUIRE(d->a_ch % 32 == 0 && d->cout % 32 == 0 && (!d->s || d->s_ch % 32 == 0), SAR_ERR_UNSUPPORTED,
               "sar_conv_tc_fwd: channel counts must be multiples of 32 (a_ch=%d s_ch=%d cout=%d)", d->a_ch, d->s_ch, d->cout);
   SAR_REQUIRE(d->out_raw || d->out_act || d->out_dense, SAR_ERR_BAD_ARG, "sar_conv_tc_fwd: no output requested");
-  SAR_REQUIRE(!(d->out_act || d->out_dense) || (d->act_scale && d->act_shift), SAR_ERR_BAD_ARG,
-              "sar_conv_tc_fwd: activated outputs need act_scale/act_shift");
+  SAR_REQUIRE(d->act_kind >= 0 && d->act_kind <= 2, SAR_ERR_BAD_ARG, "sar_conv_tc_fwd: act_kind must be 0, 1 or 2");
+  SAR_REQUIRE(!(d->out_act || d->out_dense) || d->act_kind != 0 || (d->act_scale && d->act_shift), SAR_ERR_BAD_ARG,
+              "sar_conv_tc_fwd: act_kind 0 (BN->ReLU) outputs need act_scale/act_shift");
   SAR_REQUIRE(aligned16(d->a) && aligned16(d->w) && (!d->s || aligned16(d->s)) && (!d->res || aligned16(d->res)) &&
                   (!d->out_raw || aligned16(d->out_raw)) && (!d->out_act || aligned16(d->out_act)) &&
                   (!d->out_dense || aligned16(d->out_dense)),
@@ -673,6 +686,7 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
   p.out_act = reinterpret_cast<__half*>(d->out_act);
   p.out_dense = d->out_dense;
   p.dbg = reinterpret_cast<long long*>(d->dbg);
+  p.act_kind = d->act_kind;
   p.mma_mask = getenv("SAR_TC_MMAMASK") ? atoi(getenv("SAR_TC_MMAMASK")) : 7;
   SAR_REQUIRE(!(p.split && p.out_dense), SAR_ERR_BAD_ARG, "sar_conv_tc_fwd: dense output cannot be phase-split");
 
@@ -744,7 +758,7 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
     auto launch = [&](auto kern) -> int {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) { set_error("sar_conv_tc_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-      kern<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(mapA, mapS, mapWm, mapWs, p, sp);
+      launch_k(kern, dim3(grid), dim3(TC_THREADS), smem, (cudaStream_t)stream, mapA, mapS, mapWm, mapWs, p, sp);
       return 0;
     };
     int lrc;
@@ -755,7 +769,7 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
     const size_t smem = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + 256 + 3 * (size_t)d->cout * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("sar_conv_tc_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-    conv_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(mapA, mapS, mapWm, mapWs, p);
+    launch_k(conv_tc_kernel, dim3(grid), dim3(TC_THREADS), smem, (cudaStream_t)stream, mapA, mapS, mapWm, mapWs, p);
   }
   return check_launch("sar_conv_tc_fwd");
 }

@@ -32,6 +32,8 @@ __global__ void __launch_bounds__(CTC_THREADS) ctc_kernel(const float* __restric
                                                            const int* __restrict__ in_len, const int* __restrict__ lab_len,
                                                            float* __restrict__ loss, float* __restrict__ probs,
                                                            int* __restrict__ status, int S, int C, int Lmax) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ __align__(16) float sm[];
   const int NE = 2 * Lmax + 1;
   float* lq = sm;                               // [S][NE]
@@ -122,6 +124,6 @@ extern "C" int sar_ctc_fwd(const float* logits, const float* labels, const int* 
   SAR_REQUIRE(smem <= 227 * 1024, SAR_ERR_UNSUPPORTED, "sar_ctc_fwd: S*(2*Lmax+1) too large for shared memory (%zu B)", smem);
   cudaError_t e = cudaFuncSetAttribute(ctc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("sar_ctc_fwd: %s", cudaGetErrorString(e)); return (int)e; }
-  ctc_kernel<<<B, CTC_THREADS, smem, (cudaStream_t)stream>>>(logits, labels, in_len, lab_len, loss, probs, status, S, C, Lmax);
+  launch_k(ctc_kernel, dim3(B), dim3(CTC_THREADS), smem, (cudaStream_t)stream, logits, labels, in_len, lab_len, loss, probs, status, S, C, Lmax);
   return check_launch("sar_ctc_fwd");
 }

@@ -7,6 +7,8 @@ namespace sar {
 // MaxPooling2D 'same' (resnet.py:174,192): one thread per (pixel, 4 channels)
 __global__ void maxpool_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int H, int W, int C,
                                int Ho, int Wo, int k, int stride, int pad_t, int pad_l) {
+  pdl_wait();
+  pdl_trigger();
   const int C4 = C >> 2;
   long long total = (long long)B * Ho * Wo * C4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -35,6 +37,8 @@ __global__ void maxpool_kernel(const float* __restrict__ x, float* __restrict__ 
 __global__ void affine_relu_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                                    const float* __restrict__ shift, float* __restrict__ out,
                                    long long rows, int C, int relu) {
+  pdl_wait();
+  pdl_trigger();
   const int C4 = C >> 2;
   long long total = rows * C4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -54,7 +58,10 @@ __global__ void affine_relu_kernel(const float* __restrict__ x, const float* __r
 template <int MAXV>   // MAXV float4 per lane => C <= 128*MAXV
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, float* __restrict__ out,
+                                 __half* __restrict__ planes, long long plane_rows, int seg,
                                  long long rows, int C, float eps) {
+  pdl_wait();
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -82,7 +89,10 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
   }
   const float var = warp_sum(sq) / (float)C;
   const float rstd = 1.0f / sqrtf(var + eps);
-  float4* orow = reinterpret_cast<float4*>(out + row * C);
+  float4* orow = out ? reinterpret_cast<float4*>(out + row * C) : nullptr;
+  const long long prow = seg > 0 ? row + row / seg : row;
+  __half* ph = planes ? planes + prow * C : nullptr;
+  __half* pl = planes ? planes + (plane_rows + prow) * C : nullptr;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     int c4 = lane + 32 * i;
@@ -94,13 +104,23 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
       o.y = (v[i].y - mean) * rstd * g.y + b.y;
       o.z = (v[i].z - mean) * rstd * g.z + b.z;
       o.w = (v[i].w - mean) * rstd * g.w + b.w;
-      orow[c4] = o;
+      if (orow) orow[c4] = o;
+      if (planes) {                       // x = hi + lo/2048 (conv_tc.cu operand format)
+        const __half2 h01 = __floats2half2_rn(o.x, o.y), h23 = __floats2half2_rn(o.z, o.w);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn((o.x - f01.x) * 2048.f, (o.y - f01.y) * 2048.f);
+        const __half2 l23 = __floats2half2_rn((o.z - f23.x) * 2048.f, (o.w - f23.y) * 2048.f);
+        *reinterpret_cast<uint2*>(ph + 4 * c4) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+        *reinterpret_cast<uint2*>(pl + 4 * c4) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+      }
     }
   }
 }
 
 // GlobalAveragePooling1D (model.py:125): block per utterance, thread per feature
 __global__ void avgpool_kernel(const float* __restrict__ x, float* __restrict__ out, int S, int D) {
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.x;
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
     float acc = 0.f;
@@ -112,6 +132,8 @@ __global__ void avgpool_kernel(const float* __restrict__ x, float* __restrict__ 
 // one block, fixed reduction order => bitwise reproducible sums for a given B
 __global__ void loss_reduce_kernel(const float* __restrict__ stats, const float* __restrict__ ctc,
                                    const float* __restrict__ bn, float* __restrict__ out8, int B) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float scratch[32];
   float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
@@ -146,7 +168,7 @@ int sar_maxpool2d_fwd(const float* x, float* out, int B, int H, int W, int C, in
   SAR_REQUIRE(C % 4 == 0, SAR_ERR_UNSUPPORTED, "sar_maxpool2d_fwd: C must be a multiple of 4");
   SAR_REQUIRE(aligned16(x) && aligned16(out), SAR_ERR_ALIGN, "sar_maxpool2d_fwd: unaligned pointer");
   long long total = (long long)B * Ho * Wo * (C / 4);
-  maxpool_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, out, B, H, W, C, Ho, Wo, k, stride, pad_t, pad_l);
+  launch_k(maxpool_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, x, out, B, H, W, C, Ho, Wo, k, stride, pad_t, pad_l);
   return check_launch("sar_maxpool2d_fwd");
 }
 
@@ -158,24 +180,33 @@ int sar_affine_relu_fwd(const float* x, const float* scale, const float* shift, 
   SAR_REQUIRE(C % 4 == 0, SAR_ERR_UNSUPPORTED, "sar_affine_relu_fwd: C must be a multiple of 4");
   SAR_REQUIRE(aligned16(x) && aligned16(out) && aligned16(scale) && aligned16(shift), SAR_ERR_ALIGN,
               "sar_affine_relu_fwd: unaligned pointer");
-  affine_relu_kernel<<<grid_for(rows * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(x, scale, shift, out, rows, C, relu);
+  launch_k(affine_relu_kernel, dim3(grid_for(rows * (C / 4), 256)), dim3(256), 0, (cudaStream_t)stream, x, scale, shift, out, rows, C, relu);
   return check_launch("sar_affine_relu_fwd");
 }
 
 int sar_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* out,
                       long long rows, int C, float eps, void* stream) {
+  SAR_REQUIRE(out, SAR_ERR_BAD_ARG, "sar_layernorm_fwd: null pointer");
+  return sar_layernorm_planes_fwd(x, gamma, beta, out, nullptr, 0, 0, rows, C, eps, stream);
+}
+
+int sar_layernorm_planes_fwd(const float* x, const float* gamma, const float* beta, float* out, void* planes_v,
+                             long long plane_rows, int seg, long long rows, int C, float eps, void* stream) {
   using namespace sar;
-  SAR_REQUIRE(x && gamma && beta && out, SAR_ERR_BAD_ARG, "sar_layernorm_fwd: null pointer");
+  __half* planes = reinterpret_cast<__half*>(planes_v);
+  SAR_REQUIRE(x && gamma && beta && (out || planes), SAR_ERR_BAD_ARG, "sar_layernorm_fwd: null pointer");
+  SAR_REQUIRE(!planes || (C % 8 == 0 && seg >= 0 && plane_rows >= rows + (seg > 0 ? (rows - 1) / seg : 0) && aligned16(planes)),
+              SAR_ERR_BAD_ARG, "sar_layernorm_planes_fwd: bad planes geometry (rows=%lld seg=%d plane_rows=%lld C=%d)", rows, seg, plane_rows, C);
   SAR_REQUIRE(rows > 0 && C > 0, SAR_ERR_BAD_ARG, "sar_layernorm_fwd: non-positive dimension");
   SAR_REQUIRE(C % 4 == 0 && C <= 1024, SAR_ERR_UNSUPPORTED, "sar_layernorm_fwd: C must be a multiple of 4, <= 1024");
-  SAR_REQUIRE(aligned16(x) && aligned16(out) && aligned16(gamma) && aligned16(beta), SAR_ERR_ALIGN,
+  SAR_REQUIRE(aligned16(x) && (!out || aligned16(out)) && aligned16(gamma) && aligned16(beta), SAR_ERR_ALIGN,
               "sar_layernorm_fwd: unaligned pointer");
   const int warps = 8;
   unsigned grid = (unsigned)((rows + warps - 1) / warps);
   cudaStream_t st = (cudaStream_t)stream;
-  if (C <= 256) layernorm_kernel<2><<<grid, warps * 32, 0, st>>>(x, gamma, beta, out, rows, C, eps);
-  else if (C <= 512) layernorm_kernel<4><<<grid, warps * 32, 0, st>>>(x, gamma, beta, out, rows, C, eps);
-  else layernorm_kernel<8><<<grid, warps * 32, 0, st>>>(x, gamma, beta, out, rows, C, eps);
+  if (C <= 256) launch_k(layernorm_kernel<2>, dim3(grid), dim3(warps * 32), 0, st, x, gamma, beta, out, planes, plane_rows, seg, rows, C, eps);
+  else if (C <= 512) launch_k(layernorm_kernel<4>, dim3(grid), dim3(warps * 32), 0, st, x, gamma, beta, out, planes, plane_rows, seg, rows, C, eps);
+  else launch_k(layernorm_kernel<8>, dim3(grid), dim3(warps * 32), 0, st, x, gamma, beta, out, planes, plane_rows, seg, rows, C, eps);
   return check_launch("sar_layernorm_fwd");
 }
 
@@ -183,7 +214,7 @@ int sar_avgpool_fwd(const float* x, float* out, int B, int S, int D, void* strea
   using namespace sar;
   SAR_REQUIRE(x && out, SAR_ERR_BAD_ARG, "sar_avgpool_fwd: null pointer");
   SAR_REQUIRE(B > 0 && S > 0 && D > 0, SAR_ERR_BAD_ARG, "sar_avgpool_fwd: non-positive dimension");
-  avgpool_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(x, out, S, D);
+  launch_k(avgpool_kernel, dim3(B), dim3(256), 0, (cudaStream_t)stream, x, out, S, D);
   return check_launch("sar_avgpool_fwd");
 }
 
@@ -192,7 +223,7 @@ int sar_loss_reduce_fwd(const float* sample_stats, const float* ctc_loss, const 
   using namespace sar;
   SAR_REQUIRE(out8, SAR_ERR_BAD_ARG, "sar_loss_reduce_fwd: null out8");
   SAR_REQUIRE(B > 0, SAR_ERR_BAD_ARG, "sar_loss_reduce_fwd: B must be positive");
-  loss_reduce_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(sample_stats, ctc_loss, bn_stats, out8, B);
+  launch_k(loss_reduce_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, sample_stats, ctc_loss, bn_stats, out8, B);
   return check_launch("sar_loss_reduce_fwd");
 }
 

@@ -26,6 +26,8 @@ __device__ __forceinline__ int fb_num_frames(long long n) {
 __global__ void __launch_bounds__(256) fbank_frame_kernel(const float* __restrict__ wav, const long long* __restrict__ offsets,
                                                            const float* __restrict__ melfb_t, float* __restrict__ feat,
                                                            int Fmax) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float re[FB_NFFT], im[FB_NFFT];
   __shared__ float pw[FB_NBIN + 3];
   const int f = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
@@ -67,6 +69,8 @@ __global__ void __launch_bounds__(256) fbank_frame_kernel(const float* __restric
 
 __global__ void __launch_bounds__(320) fbank_norm_kernel(const float* __restrict__ feat, const long long* __restrict__ offsets,
                                                           float* __restrict__ x_data, int Fmax, int T) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float smin[4][FB_NFILT], smax[4][FB_NFILT];
   const int b = blockIdx.x, m = threadIdx.x % FB_NFILT, q = threadIdx.x / FB_NFILT;   // 4 frame-phases
   const long long n = offsets[b + 1] - offsets[b];
@@ -102,9 +106,9 @@ extern "C" int sar_fbank_fwd(const float* wav, const long long* offsets, const f
   SAR_REQUIRE(B > 0 && Fmax > 0 && T > 0, SAR_ERR_BAD_ARG, "sar_fbank_fwd: non-positive dimension");
   SAR_REQUIRE(B <= 65535, SAR_ERR_UNSUPPORTED, "sar_fbank_fwd: B > 65535");
   cudaStream_t st = (cudaStream_t)stream;
-  fbank_frame_kernel<<<dim3(Fmax, B), 256, 0, st>>>(wav, offsets, melfb_t, feat_ws, Fmax);
+  launch_k(fbank_frame_kernel, dim3(dim3(Fmax, B)), dim3(256), 0, st, wav, offsets, melfb_t, feat_ws, Fmax);
   int rc = check_launch("sar_fbank_fwd(frames)");
   if (rc) return rc;
-  fbank_norm_kernel<<<B, 4 * FB_NFILT, 0, st>>>(feat_ws, offsets, x_data, Fmax, T);
+  launch_k(fbank_norm_kernel, dim3(B), dim3(4 * FB_NFILT), 0, st, feat_ws, offsets, x_data, Fmax, T);
   return check_launch("sar_fbank_fwd(norm)");
 }

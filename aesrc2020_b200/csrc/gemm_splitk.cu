@@ -12,6 +12,8 @@ constexpr int SK_BM = 64, SK_BN = 64, SK_BK = 16, SK_KSLAB = 512;
 
 __global__ void __launch_bounds__(256) gemm_splitk_kernel(const float* __restrict__ a, const float* __restrict__ w,
                                                           float* __restrict__ ws, int M, int K, int N) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ __align__(16) float As[SK_BK][SK_BM + 4];
   __shared__ __align__(16) float Bs[SK_BK][SK_BN];
   const int t = threadIdx.x;
@@ -75,6 +77,8 @@ __global__ void __launch_bounds__(256) gemm_splitk_kernel(const float* __restric
 
 __global__ void splitk_reduce_kernel(const float* __restrict__ ws, const float* __restrict__ bias,
                                      float* __restrict__ out, int M, int N, int splits) {
+  pdl_wait();
+  pdl_trigger();
   long long total = (long long)M * N;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -108,13 +112,13 @@ int sar_gemm_splitk_fwd(const float* a, const float* w, const float* bias, float
   int splits = (K + SK_KSLAB - 1) / SK_KSLAB;
   dim3 grid((M + SK_BM - 1) / SK_BM, (N + SK_BN - 1) / SK_BN, splits);
   cudaStream_t st = (cudaStream_t)stream;
-  gemm_splitk_kernel<<<grid, 256, 0, st>>>(a, w, (float*)workspace, M, K, N);
+  launch_k(gemm_splitk_kernel, dim3(grid), dim3(256), 0, st, a, w, (float*)workspace, M, K, N);
   int rc = check_launch("sar_gemm_splitk_fwd(partial)");
   if (rc) return rc;
   long long total = (long long)M * N;
   unsigned rg = (unsigned)((total + 255) / 256);
   if (rg > 148 * 8) rg = 148 * 8;
-  splitk_reduce_kernel<<<rg, 256, 0, st>>>((const float*)workspace, bias, out, M, N, splits);
+  launch_k(splitk_reduce_kernel, dim3(rg), dim3(256), 0, st, (const float*)workspace, bias, out, M, N, splits);
   return check_launch("sar_gemm_splitk_fwd(reduce)");
 }
 

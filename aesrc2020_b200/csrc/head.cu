@@ -61,6 +61,8 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(HeadP p) {
   float* wn = ld + HEAD_MAXC;            // [n] column norms^2
   float* scratch = wn + HEAD_MAXC;       // [32]
   const int t = threadIdx.x, b = blockIdx.x, n = p.n;
+  pdl_wait();
+  pdl_trigger();
   const float* y = p.onehot ? p.onehot + (size_t)b * n : nullptr;
   float loss_a = 0.f, loss_d = 0.f, corr_a = 0.f, corr_d = 0.f;
 
@@ -239,6 +241,6 @@ extern "C" int sar_head_fwd(const float* emb, int D,
     cudaError_t e = cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("sar_head_fwd: %s", cudaGetErrorString(e)); return (int)e; }
   }
-  head_kernel<<<B, HEAD_THREADS, smem, (cudaStream_t)stream>>>(p);
+  launch_k(head_kernel, dim3(B), dim3(HEAD_THREADS), smem, (cudaStream_t)stream, p);
   return check_launch("sar_head_fwd");
 }

@@ -45,6 +45,8 @@ __device__ __forceinline__ void store_hilo8(__half* planes, long long R, int pla
 // dense fp32 NHWC -> planes, optional per-channel affine + ReLU; one thread per (pixel, 8 channels)
 __global__ void planes_pack_kernel(const float* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
                                    int relu, __half* __restrict__ planes, PlaneGeom g) {
+  pdl_wait();
+  pdl_trigger();
   const int C8 = g.C >> 3;
   const long long total = (long long)g.B * g.H * g.W * C8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -72,6 +74,8 @@ __global__ void planes_pack_kernel(const float* __restrict__ x, const float* __r
 }
 
 __global__ void planes_unpack_kernel(const __half* __restrict__ planes, float* __restrict__ x, PlaneGeom g) {
+  pdl_wait();
+  pdl_trigger();
   const long long total = (long long)g.B * g.H * g.W * g.C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % g.C);
@@ -91,6 +95,8 @@ __global__ void planes_unpack_kernel(const __half* __restrict__ planes, float* _
 // MaxPooling2D 'same' from dense fp32 NHWC into planes (pool output geometry in g)
 __global__ void maxpool_planes_kernel(const float* __restrict__ x, __half* __restrict__ planes, int Hin, int Win,
                                       int k, int stride, int pad_t, int pad_l, PlaneGeom g) {
+  pdl_wait();
+  pdl_trigger();
   const int C8 = g.C >> 3;
   const long long total = (long long)g.B * g.H * g.W * C8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -149,8 +155,7 @@ int sar_planes_pack_fwd(const float* x, const float* scale, const float* shift, 
   SAR_REQUIRE(C % 8 == 0, SAR_ERR_UNSUPPORTED, "sar_planes_pack_fwd: C must be a multiple of 8");
   SAR_REQUIRE(aligned16(x) && aligned16(planes), SAR_ERR_ALIGN, "sar_planes_pack_fwd: unaligned pointer");
   PlaneGeom g{B, H, W, C, split ? 1 : 0};
-  planes_pack_kernel<<<pgrid((long long)B * H * W * (C / 8)), 256, 0, (cudaStream_t)stream>>>(
-      x, scale, shift, relu, reinterpret_cast<__half*>(planes), g);
+  launch_k(planes_pack_kernel, dim3(pgrid((long long)B * H * W * (C / 8))), dim3(256), 0, (cudaStream_t)stream, x, scale, shift, relu, reinterpret_cast<__half*>(planes), g);
   return check_launch("sar_planes_pack_fwd");
 }
 
@@ -159,8 +164,7 @@ int sar_planes_unpack_fwd(const void* planes, float* x, int B, int H, int W, int
   SAR_REQUIRE(x && planes, SAR_ERR_BAD_ARG, "sar_planes_unpack_fwd: null pointer");
   SAR_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0, SAR_ERR_BAD_ARG, "sar_planes_unpack_fwd: non-positive dimension");
   PlaneGeom g{B, H, W, C, split ? 1 : 0};
-  planes_unpack_kernel<<<pgrid((long long)B * H * W * C), 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const __half*>(planes), x, g);
+  launch_k(planes_unpack_kernel, dim3(pgrid((long long)B * H * W * C)), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<const __half*>(planes), x, g);
   return check_launch("sar_planes_unpack_fwd");
 }
 
@@ -173,8 +177,7 @@ int sar_maxpool_planes_fwd(const float* x, void* planes, int B, int H, int W, in
   SAR_REQUIRE(C % 8 == 0, SAR_ERR_UNSUPPORTED, "sar_maxpool_planes_fwd: C must be a multiple of 8");
   SAR_REQUIRE(aligned16(x) && aligned16(planes), SAR_ERR_ALIGN, "sar_maxpool_planes_fwd: unaligned pointer");
   PlaneGeom g{B, Ho, Wo, C, 0};
-  maxpool_planes_kernel<<<pgrid((long long)B * Ho * Wo * (C / 8)), 256, 0, (cudaStream_t)stream>>>(
-      x, reinterpret_cast<__half*>(planes), H, W, k, stride, pad_t, pad_l, g);
+  launch_k(maxpool_planes_kernel, dim3(pgrid((long long)B * Ho * Wo * (C / 8))), dim3(256), 0, (cudaStream_t)stream, x, reinterpret_cast<__half*>(planes), H, W, k, stride, pad_t, pad_l, g);
   return check_launch("sar_maxpool_planes_fwd");
 }
 

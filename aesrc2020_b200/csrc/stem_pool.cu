@@ -30,6 +30,8 @@ struct StemP {
 };
 
 __global__ void __launch_bounds__(SP_THREADS, 2) stem_pool_kernel(StemP p) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ __align__(16) float sm[];
   float* w_s = sm;                               // [49][F0]
   float* x_s = w_s + 49 * p.F0;                  // [SP_IR][XW]
@@ -190,6 +192,6 @@ extern "C" int sar_stem_pool_fwd(const float* x, const float* w, const float* bi
   cudaError_t e = cudaFuncSetAttribute(stem_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("sar_stem_pool_fwd: %s", cudaGetErrorString(e)); return (int)e; }
   dim3 grid((p.Hp + SP_PH - 1) / SP_PH, B);
-  stem_pool_kernel<<<grid, SP_THREADS, smem, (cudaStream_t)stream>>>(p);
+  launch_k(stem_pool_kernel, dim3(grid), dim3(SP_THREADS), smem, (cudaStream_t)stream, p);
   return check_launch("sar_stem_pool_fwd");
 }

@@ -98,6 +98,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const StemTcP p)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
 
   const int Rimg = (p.Hp + 1) * (ST_WP + 1);
   const long long R = (long long)p.B * Rimg;
@@ -332,7 +334,7 @@ int stem_tc_launch(const float* x, const float* w, const float* bias, const floa
   cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("sar_stem_pool_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
   const int grid = p.n_items < sms ? p.n_items : sms;
-  stem_tc_kernel<<<grid, ST_THREADS, smem, stream>>>(p);
+  launch_k(stem_tc_kernel, dim3(grid), dim3(ST_THREADS), smem, stream, p);
   return check_launch("sar_stem_pool_fwd(tc)");
 }
 

@@ -37,6 +37,16 @@ __global__ void __launch_bounds__(VLAD_THREADS) vlad_kernel(const float* __restr
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int b = blockIdx.x;
 
+  // ---- constants first (overlaps the previous kernel's tail under programmatic dependent launch)
+  for (int i = t; i < SP * KGP; i += VLAD_THREADS) A[i] = 0.f;
+  if (!score && wa_smem) {
+    for (int i = t; i < D * KGP; i += VLAD_THREADS) {
+      const int d = i / KGP, k = i - d * KGP;
+      Ws[i] = (k < KG) ? __ldg(wa + (size_t)d * KG + k) : 0.f;
+    }
+  }
+  pdl_wait();
+  pdl_trigger();
   // ---- stage X (coalesced 16B loads), zero the padded rows/columns
   {
     const float4* src = reinterpret_cast<const float4*>(feat + (size_t)b * S * D);
@@ -46,13 +56,6 @@ __global__ void __launch_bounds__(VLAD_THREADS) vlad_kernel(const float* __restr
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (s < S) v = __ldg(src + (size_t)s * d4 + c);
       *reinterpret_cast<float4*>(X + (size_t)s * XS + 4 * c) = v;
-    }
-  }
-  for (int i = t; i < SP * KGP; i += VLAD_THREADS) A[i] = 0.f;
-  if (!score && wa_smem) {
-    for (int i = t; i < D * KGP; i += VLAD_THREADS) {
-      const int d = i / KGP, k = i - d * KGP;
-      Ws[i] = (k < KG) ? __ldg(wa + (size_t)d * KG + k) : 0.f;
     }
   }
   __syncthreads();
@@ -200,6 +203,6 @@ extern "C" int sar_vlad_fwd(const float* feat, const float* w_assign, const floa
   SAR_REQUIRE(smem <= limit, SAR_ERR_UNSUPPORTED, "sar_vlad_fwd: S*D too large for shared memory (%zu B)", smem);
   cudaError_t e = cudaFuncSetAttribute(vlad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("sar_vlad_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-  vlad_kernel<<<B, VLAD_THREADS, smem, (cudaStream_t)stream>>>(feat, w_assign, b_assign, score, centers, out, S, D, K, G, wa_smem);
+  launch_k(vlad_kernel, dim3(B), dim3(VLAD_THREADS), smem, (cudaStream_t)stream, feat, w_assign, b_assign, score, centers, out, S, D, K, G, wa_smem);
   return check_launch("sar_vlad_fwd");
 }

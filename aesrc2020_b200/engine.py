@@ -133,8 +133,9 @@ class ResNetTC:
         self._rot[key] ^= 1
         return self._bufs[key][self._rot[key]]
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        """x (B,T,80,1) fp32 -> (B,H',W',C) fp32 after the final BN->ReLU."""
+    def forward(self, x: torch.Tensor, as_planes: bool = False):
+        """x (B,T,80,1) fp32 -> (B,H',W',C) after the final BN->ReLU: fp32 NHWC, or (as_planes) the hi/lo
+        planes a tensor-core Dense consumes directly."""
         tc, pl, p = self.tc, self.plan, self.p
         B = x.shape[0]
         st = pl.stem
@@ -150,7 +151,10 @@ class ResNetTC:
         out_dense = None
         ev = None
         if self.record_events is not None:       # bench.py: device time of the block convolutions only
-            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            # external events become event-record NODES when the step is being captured into a CUDA graph, so
+            # the segment can be timed inside a replay (ordinary events cannot be recorded during capture)
+            ext = torch.cuda.is_current_stream_capturing()
+            ev = (torch.cuda.Event(enable_timing=True, external=ext), torch.cuda.Event(enable_timing=True, external=ext))
             ev[0].record()
         for i, b in enumerate(pl.blocks):
             nxt = pl.blocks[i + 1] if i + 1 < len(pl.blocks) else None
@@ -168,6 +172,11 @@ class ResNetTC:
                            cout=c2.cout, short=cur_raw if b.short else None, res=None if b.short else cur_raw,
                            out_raw=nraw, out_act=nact, act=self.bn(nxt.conv1.pre_bn))
                 cur_raw, cur_act = nraw, nact
+            elif as_planes:
+                out_dense = self._buf(B, c2.hout, c2.wout, c2.cout, False, "final")
+                tc.conv_tc(c1_act, p[b.name + "/w2"], p[b.name + "/b2"], out_hw=(c2.hout, c2.wout), taps=taps2,
+                           cout=c2.cout, short=cur_raw if b.short else None, res=None if b.short else cur_raw,
+                           act=self.bn(pl.final_bn), out_act=out_dense)
             else:
                 out_dense = torch.empty((B, c2.hout, c2.wout, c2.cout), device=self.device, dtype=torch.float32)
                 tc.conv_tc(c1_act, p[b.name + "/w2"], p[b.name + "/b2"], out_hw=(c2.hout, c2.wout), taps=taps2,
@@ -193,16 +202,23 @@ class SARNetEngine:
         self.resnet = (ResNetTC if conv_path == "tc" else ResNetDevice)(self.plan, weights, self.device)
         self._graphs: Dict[tuple, tuple] = {}
         self.p: Dict[str, torch.Tensor] = {}
+        # Dense layers / GRU input projections on the tensor cores (1-tap conv_tc) when the residual blocks are
+        self.dense_tc = conv_path == "tc" and cfg.hidden_dim % 64 == 0 and self.plan.cout % 32 == 0
+        self._seq_bufs: Dict[tuple, object] = {}
         self._prepare(weights)
 
     # ------------------------------------------------------------------ weight preparation
     def _put(self, name, arr):
         self.p[name] = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32)).to(self.device)
 
-    def _dense(self, w, name, bias=True):
+    def _dense(self, w, name, bias=True, tc_ok=True):
         self._put(name + "/kernel", w[name + "/kernel"])
         if bias:
             self._put(name + "/bias", w[name + "/bias"])
+        k = w[name + "/kernel"]
+        if self.dense_tc and tc_ok and name in ("CNN_LIN", "CTC_DS", "AR_DS") and k.shape[0] % 32 == 0 and k.shape[1] % 32 == 0:
+            from . import tc
+            self.p[name + "/w_tc"] = torch.from_numpy(tc.pack_dense_weights(k)).to(self.device)
 
     def _ln(self, w, name):
         self._put(name + "/gamma", w[name + "/gamma"])
@@ -213,6 +229,9 @@ class SARNetEngine:
         kf, kb = w[name + "/forward/kernel"], w[name + "/backward/kernel"]
         bf, bb = w[name + "/forward/bias"], w[name + "/backward/bias"]
         self._put(name + "/kernel_cat", np.concatenate([kf, kb], axis=1))                 # (Din, 6u)
+        if self.dense_tc and kf.shape[0] % 32 == 0 and (6 * u) % 32 == 0:
+            from . import tc
+            self.p[name + "/w_tc"] = torch.from_numpy(tc.pack_dense_weights(np.concatenate([kf, kb], axis=1))).to(self.device)
         self._put(name + "/ibias_cat", np.concatenate([bf[:3 * u], bb[:3 * u]]))          # (6u,)
         self._put(name + "/rec", np.stack([w[name + "/forward/recurrent_kernel"],
                                            w[name + "/backward/recurrent_kernel"]]))      # (2,u,3u)
@@ -225,7 +244,7 @@ class SARNetEngine:
         if cfg.ctc_enable:
             self._bigru(w, "CTC_BIGRU"); self._ln(w, "CTC_BIGRU_LN")
             self._dense(w, "CTC_DS"); self._ln(w, "CTC_DS_LN")
-            self._dense(w, "ctc_pred")
+            self._dense(w, "ctc_pred", tc_ok=False)
         if cfg.ar_enable:
             self._dense(w, "AR_DS"); self._ln(w, "AR_DS_LN")
             if cfg.mto == "bigru":
@@ -271,6 +290,37 @@ class SARNetEngine:
         xp = ops.dense(x, p[name + "/kernel_cat"], p[name + "/ibias_cat"])       # (B,S,6u) = (B,S,2,3u)
         return ops.bigru(xp.reshape(B, S, 2, -1), p[name + "/rec"], p[name + "/rbias"], seq=seq)
 
+    # tensor-core variants: sequence activations travel as hi/lo planes of a (1, B, S) map
+    def _seq_planes(self, B, S, C, role):
+        from . import tc
+        key = (B, S, C, role)
+        if key not in self._seq_bufs:
+            self._seq_bufs[key] = tc.alloc_planes(1, B, S, C, False, self.device)
+        return self._seq_bufs[key]
+
+    def ln_planes(self, x, ln_name, role, want_dense=False):
+        """LayerNorm of x (B,S,C) -> (fp32 or None, planes)."""
+        p = self.p
+        B, S, C = x.shape
+        pl = self._seq_planes(B, S, C, role)
+        d = ops.layernorm(x, p[ln_name + "/gamma"], p[ln_name + "/beta"], planes=pl, want_dense=want_dense)
+        return d, pl
+
+    def dense_planes(self, planes, name, act=None, bias_name=None, seq_shape=None):
+        """Dense over the channels of a planes tensor -> fp32 (B, S, Dout): planes is either a (1, B, S)
+        sequence map or (seq_shape=(B, S)) the ResNet's (B, H', W') map read as CNN2SEQ does (model.py:252)."""
+        from . import tc
+        p = self.p
+        y = tc.dense_tc(planes, p[name + "/w_tc"], p[bias_name or (name + "/bias")], act=act)
+        B, S = seq_shape if seq_shape is not None else (planes.H, planes.W)
+        return y.reshape(B, S, -1)
+
+    def bigru_planes(self, planes, name, seq=True):
+        p = self.p
+        xp = self.dense_planes(planes, name, bias_name=name + "/ibias_cat")      # (B,S,6u)
+        B, S = xp.shape[0], xp.shape[1]
+        return ops.bigru(xp.reshape(B, S, 2, -1), p[name + "/rec"], p[name + "/rbias"], seq=seq)
+
     def embed(self, x):
         p = self.p
         W, b = p["AR_EMBEDDING/kernel_folded"], p["AR_EMBEDDING/bias_folded"]
@@ -280,12 +330,12 @@ class SARNetEngine:
 
     # ------------------------------------------------------------------ forward
     # ------------------------------------------------------------------ CUDA-graph replay
-    def forward_graphed(self, inputs: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    def forward_graphed(self, inputs: Dict[str, torch.Tensor], tag: str = "") -> Dict[str, torch.Tensor]:
         """Same as forward(), but the ~45 launches of a step are captured once per input signature
         into a CUDA graph and replayed (the step is launch-bound at small batches).  Inputs are
         copied into the graph's static buffers; the returned tensors are the graph's static outputs
         (valid until the next replay of the same signature)."""
-        key = tuple(sorted((k, tuple(v.shape), str(v.dtype)) for k, v in inputs.items()))
+        key = (tag,) + tuple(sorted((k, tuple(v.shape), str(v.dtype)) for k, v in inputs.items()))
         entry = self._graphs.get(key)
         if entry is None:
             static_in = {k: v.clone() for k, v in inputs.items()}
@@ -318,6 +368,8 @@ class SARNetEngine:
         B = x.shape[0]
         out: Dict[str, torch.Tensor] = {}
         S, Cc = self.plan.seq_len, self.plan.cout
+        if self.dense_tc:
+            return self._forward_tc(inputs, x, want_intermediates)
         if self.conv_path == "tc":
             raw = self.resnet.forward(x)                                        # final BN->ReLU already applied
             cnn = self.dense_ln(raw.reshape(B, S, Cc), "CNN_LIN", "CNN_LIN_LN")   # CNN2SEQ, model.py:252
@@ -329,12 +381,42 @@ class SARNetEngine:
         crnn = ops.layernorm(self.bigru(cnn, "CRNN"), p["CRNN_LN/gamma"], p["CRNN_LN/beta"])
         if want_intermediates:
             out["resnet_raw"], out["cnn_lin"], out["crnn"] = raw, cnn, crnn
+        return self._forward_tail(inputs, out, crnn, None, want_intermediates)
+
+    def _forward_tc(self, inputs, x, want_intermediates):
+        """Encoder with every Dense / GRU input projection on the tensor cores: activations between the
+        LayerNorms and the Dense layers travel as fp16 hi/lo planes (no fp32 round trip)."""
+        p = self.p
+        B = x.shape[0]
+        S = self.plan.seq_len
+        out: Dict[str, torch.Tensor] = {}
+        wi = want_intermediates
+        P0 = self.resnet.forward(x, as_planes=True)                             # relu(final BN), resnet.py:178/196
+        y = self.dense_planes(P0, "CNN_LIN", act="tanh", seq_shape=(B, S))      # CNN2SEQ + CNN_LIN, model.py:252-253
+        cnn, P1 = self.ln_planes(y, "CNN_LIN_LN", "cnn", want_dense=wi)
+        crnn, P2 = self.ln_planes(self.bigru_planes(P1, "CRNN"), "CRNN_LN", "crnn", want_dense=wi)
+        if wi:
+            out["resnet_raw"], out["cnn_lin"], out["crnn"] = self.tc_unpack(P0), cnn, crnn
+        return self._forward_tail(inputs, out, crnn, P2, want_intermediates)
+
+    def tc_unpack(self, planes):
+        from . import tc
+        return tc.unpack(planes)
+
+    def _forward_tail(self, inputs, out, crnn, crnn_planes, want_intermediates):
+        cfg, p = self.cfg, self.p
+        B = inputs["x_data"].shape[0]
+        use_tc = crnn_planes is not None
         stats = None
         ctc_loss = None
         bn_stats = None
         if cfg.ctc_enable:                                                      # model.py:261-269
-            asr = ops.layernorm(self.bigru(crnn, "CTC_BIGRU"), p["CTC_BIGRU_LN/gamma"], p["CTC_BIGRU_LN/beta"])
-            asr = self.dense_ln(asr, "CTC_DS", "CTC_DS_LN")
+            if use_tc:
+                _, P3 = self.ln_planes(self.bigru_planes(crnn_planes, "CTC_BIGRU"), "CTC_BIGRU_LN", "ctc_bigru")
+                asr = ops.layernorm(self.dense_planes(P3, "CTC_DS", act="tanh"), p["CTC_DS_LN/gamma"], p["CTC_DS_LN/beta"])
+            else:
+                asr = ops.layernorm(self.bigru(crnn, "CTC_BIGRU"), p["CTC_BIGRU_LN/gamma"], p["CTC_BIGRU_LN/beta"])
+                asr = self.dense_ln(asr, "CTC_DS", "CTC_DS_LN")
             logits = ops.dense(asr, p["ctc_pred/kernel"], p["ctc_pred/bias"])
             ctc_loss, status, probs = ops.ctc(logits, inputs["x_ctc_label"], inputs["x_ctc_in_len"],
                                               inputs["x_ctc_out_len"], want_probs=want_intermediates)
@@ -343,11 +425,19 @@ class SARNetEngine:
             if want_intermediates:
                 out["ctc_pred"] = probs
         if cfg.ar_enable:                                                       # model.py:275-322
-            ar = self.dense_ln(crnn, "AR_DS", "AR_DS_LN")
+            P4 = None
+            if use_tc:
+                y = self.dense_planes(crnn_planes, "AR_DS", act="tanh")
+                if cfg.mto == "bigru":
+                    ar, P4 = self.ln_planes(y, "AR_DS_LN", "ar", want_dense=want_intermediates)
+                else:
+                    ar = ops.layernorm(y, p["AR_DS_LN/gamma"], p["AR_DS_LN/beta"])
+            else:
+                ar = self.dense_ln(crnn, "AR_DS", "AR_DS_LN")
             if cfg.mto == "avg":
                 integ = ops.avgpool(ar)
             elif cfg.mto == "bigru":
-                integ = self.bigru(ar, "AR_MERGE", seq=False)
+                integ = self.bigru_planes(P4, "AR_MERGE", seq=False) if P4 is not None else self.bigru(ar, "AR_MERGE", seq=False)
             else:
                 G = cfg.ghost_clusters if cfg.mto == "gvlad" else 0
                 integ = ops.vlad(ar, p[cfg.mto + "/w_assign"], p[cfg.mto + "/b_assign"], p[cfg.mto + "/centers"],

@@ -84,12 +84,22 @@ def affine_relu(x, scale, shift, relu=True):
     return out
 
 
-def layernorm(x, gamma, beta, eps: float = LN_EPS):
+def layernorm(x, gamma, beta, eps: float = LN_EPS, *, planes=None, want_dense: bool = True):
+    """sar_layernorm_fwd / sar_layernorm_planes_fwd.  `planes` (tc.Planes of a (1, B, S) map, C channels): also
+    write the rows as fp16 hi/lo flat-pad planes for a following tensor-core Dense; want_dense=False skips the
+    fp32 output (returns None)."""
     x = _f32(x)
     Cc = x.shape[-1]
-    out = torch.empty_like(x)
-    check(_shim.lib().sar_layernorm_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(out), x.numel() // Cc, Cc,
-                                        float(eps), stream_ptr()), "sar_layernorm_fwd")
+    rows = x.numel() // Cc
+    out = torch.empty_like(x) if want_dense or planes is None else None
+    if planes is None:
+        check(_shim.lib().sar_layernorm_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(out), rows, Cc,
+                                            float(eps), stream_ptr()), "sar_layernorm_fwd")
+    else:
+        assert planes.C == Cc and planes.B == 1 and planes.H * planes.W == rows and not planes.split
+        check(_shim.lib().sar_layernorm_planes_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(out), ptr(planes.t), planes.rows,
+                                                   planes.W, rows, Cc, float(eps), stream_ptr()),
+              "sar_layernorm_planes_fwd")
     _count(1)
     return out
 

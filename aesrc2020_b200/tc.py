@@ -31,7 +31,10 @@ class sar_tc_conv(C.Structure):
         ("out_split", C.c_int),
         ("B", C.c_int), ("H", C.c_int), ("W", C.c_int),
         ("dbg", C.c_void_p),
+        ("act_kind", C.c_int),
     ]
+
+ACT_KIND = {"bn_relu": 0, None: 1, "none": 1, "linear": 1, "tanh": 2}
 
 
 @dataclass
@@ -143,7 +146,8 @@ def tap_table(kh: int, kw: int, stride: int, pad_t: int, pad_l: int, W_out: int)
 
 def conv_tc(a: Planes, w_packed: torch.Tensor, bias: torch.Tensor, *, out_hw: Tuple[int, int], taps, cout: int,
             short: Optional[Planes] = None, res: Optional[Planes] = None, out_raw: Optional[Planes] = None,
-            out_act: Optional[Planes] = None, act=None, out_dense: Optional[torch.Tensor] = None, dbg=None):
+            out_act: Optional[Planes] = None, act=None, out_dense: Optional[torch.Tensor] = None, dbg=None,
+            act_kind: int = 0):
     """sar_conv_tc_fwd.  taps = (row_offsets, plane_bases)."""
     d = sar_tc_conv()
     d.a, d.a_rows, d.a_ch, d.a_planes = ptr(a.t), a.rows, a.C, a.nplanes
@@ -174,5 +178,22 @@ def conv_tc(a: Planes, w_packed: torch.Tensor, bias: torch.Tensor, *, out_hw: Tu
     d.out_split = 1 if split else 0
     d.B, d.H, d.W = a.B, H, W
     d.dbg = ptr(dbg) if dbg is not None else None
+    d.act_kind = int(act_kind)
     check(_shim.lib().sar_conv_tc_fwd(C.byref(d), stream_ptr()), "sar_conv_tc_fwd")
     ops._count(1)
+
+
+def pack_dense_weights(kernel: np.ndarray) -> np.ndarray:
+    """Keras Dense kernel (Din, Dout) -> the 1-tap packed form [2][Dout][Din] fp16 hi/lo."""
+    din, dout = kernel.shape
+    return pack_weights(np.asarray(kernel).reshape(1, 1, din, dout))
+
+
+def dense_tc(a: Planes, w_packed: torch.Tensor, bias: torch.Tensor, *, act=None) -> torch.Tensor:
+    """Dense on the channel axis of a planes tensor as a 1-tap tensor-core "convolution"
+    (Dense of model.py:35-42 / the GRU input projections of model.py:44-50).
+    Returns fp32 (a.B, a.H, a.W, Dout) in the plain layout (pad rows are skipped)."""
+    dout = int(w_packed.shape[1])
+    out = torch.empty((a.B, a.H, a.W, dout), device=a.t.device, dtype=torch.float32)
+    conv_tc(a, w_packed, bias, out_hw=(a.H, a.W), taps=([0], [0]), cout=dout, out_dense=out, act_kind=ACT_KIND[act])
+    return out

@@ -128,6 +128,8 @@ typedef struct sar_tc_conv {
   int out_split;
   int B, H, W;          /* output map geometry */
   void* dbg;            /* optional device buffer of >= 64 int64 clock64() stamps of CTA 0 (profiling aid); NULL */
+  int act_kind;         /* out_act / out_dense activation: 0 relu(act_scale*v+act_shift) (the next layer's BN->ReLU),
+                           1 identity, 2 tanh(v) -- the Dense layers of model.py:35-42 run as 1-tap "convolutions" */
 } sar_tc_conv;
 int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream);
 
@@ -146,6 +148,12 @@ int sar_affine_relu_fwd(const float* x, const float* scale, const float* shift, 
  * y = gamma*(x-mean)/sqrt(var+eps)+beta, biased variance, two-pass fp32.  C <= 1024. */
 int sar_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* out,
                       long long rows, int C, float eps, void* stream);
+/* Same, writing the normalised rows as fp16 hi/lo planes [2][plane_rows][C] for a following tensor-core Dense
+ * (sar_conv_tc_fwd with one tap): input row r lands on plane row r + r/seg (one zero pad row after every `seg`
+ * rows: the flat-pad layout of a (1, rows/seg, seg) map; seg = 0: no pad rows).  `out` (fp32, optional) also
+ * receives the rows in the plain layout.  C % 8 == 0. */
+int sar_layernorm_planes_fwd(const float* x, const float* gamma, const float* beta, float* out, void* planes,
+                             long long plane_rows, int seg, long long rows, int C, float eps, void* stream);
 
 /* Recurrent part of Bidirectional(CuDNNGRU) -- model.py:44-50.
  * xp (B,S,2,3u): input projections x*W + b_input for [forward | backward], gate order z|r|h

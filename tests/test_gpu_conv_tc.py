@@ -154,3 +154,31 @@ def test_stem_pool_matches_oracle(cuda_device, T, B, F0):
     # pad rows / columns of the planes stay exactly zero
     t = out.t.view(2, B, Hp + 1, Wp + 1, F0)
     assert float(t[:, :, Hp].abs().sum()) == 0.0 and float(t[:, :, :, Wp].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("B,S,Din,Dout,act", [(3, 48, 256, 256, "tanh"), (5, 30, 512, 256, "tanh"),
+                                              (4, 48, 256, 1536, None), (2, 75, 512, 1536, None), (1, 7, 64, 96, None)])
+def test_dense_tc_after_layernorm_planes(cuda_device, B, S, Din, Dout, act):
+    """LayerNorm -> fp16 hi/lo planes of a (1,B,S) map -> 1-tap tensor-core Dense (model.py:32-42 and the GRU
+    input projections) vs the float64 oracle."""
+    from aesrc2020_b200 import tc, ops
+    rng = np.random.RandomState(B * 100 + S)
+    x = _f32(rng.randn(B, S, Din) * 3 + 1)
+    g, bt = _f32(rng.rand(Din) + 0.5), _f32(rng.randn(Din) * 0.2)
+    w = _f32(rng.randn(Din, Dout) / np.sqrt(Din))
+    b = _f32(rng.randn(Dout) * 0.1)
+    ln = O.layernorm(t64(x), {"ln/gamma": t64(g), "ln/beta": t64(bt)}, "ln")
+    want = ln @ t64(w) + t64(b)
+    if act == "tanh":
+        want = torch.tanh(want)
+    planes = tc.alloc_planes(1, B, S, Din, False, "cuda")
+    d = ops.layernorm(dev(x), dev(g), dev(bt), planes=planes, want_dense=True)
+    assert norm_err(d, ln) < 2e-6
+    assert norm_err(tc.unpack(planes).reshape(B, S, Din), ln) < 2e-6
+    # pad rows (one after every S rows) stay exactly zero
+    pt = planes.t.reshape(2, B + 1, S + 1, Din)
+    assert float(pt[:, :, S].abs().sum()) == 0 and float(pt[:, B].abs().sum()) == 0
+    wp = torch.from_numpy(tc.pack_dense_weights(w.astype(np.float32))).cuda()
+    y = tc.dense_tc(planes, wp, dev(b), act=act).reshape(B, S, Dout)
+    assert norm_err(y, want) < 5e-6
+    assert ops.layernorm(dev(x), dev(g), dev(bt), planes=planes, want_dense=False) is None
