@@ -30,8 +30,13 @@ namespace cg = cooperative_groups;
 
 namespace sar {
 
+#ifdef SAR_GRU_PROFILE       // SAR_NVCC_EXTRA=-DSAR_GRU_PROFILE: thread 0 of CTA 0 prints cycle stamps of steps 8..11
+#define GRU_STAMP(k) if (blockIdx.x == 0 && t == 0 && step >= 8 && step < 12) stamps[(step - 8) * 8 + (k)] = clock64();
+#else
+#define GRU_STAMP(k)
+#endif
+
 constexpr int GRU_U = 256;
-constexpr int GRU_BG = 8;                        // utterances per cluster
 constexpr int GRU_CL = 8;                        // CTAs per cluster
 constexpr int GRU_UPC = GRU_U / GRU_CL;          // 32 hidden units per CTA
 constexpr int GRU_COLS = 3 * GRU_UPC;            // 96 recurrent columns per CTA
@@ -39,20 +44,32 @@ constexpr int GRU_CPT = 4;                       // columns per thread
 constexpr int GRU_KQ = 16;                       // k-slices
 constexpr int GRU_KPT = GRU_U / GRU_KQ;          // 16 k's per thread
 constexpr int GRU_THREADS = (GRU_COLS / GRU_CPT) * GRU_KQ;   // 384
-constexpr int GRU_HSTRIDE = GRU_KPT * GRU_BG + 4;            // 132 floats: +4 banks per k-slice
-constexpr int GRU_HBUF = GRU_KQ * GRU_HSTRIDE;               // floats per h buffer
+// BG = utterances per cluster (template parameter: 8 or 12).  A B200 can keep only 15 clusters of 8 CTAs
+// resident (cudaOccupancyMaxActiveClusters), so B = 64 with BG = 8 (16 clusters) ran as TWO waves; BG = 12
+// gives 12 clusters in one wave at 1.5x the FMA work per step.
+constexpr int GRU_MAX_CLUSTERS = 15;
 
 __device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
+template <int GRU_BG>
 __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1)
 bigru_kernel(const float* __restrict__ xp, const float* __restrict__ rec, const float* __restrict__ rbias,
              float* __restrict__ out, int B, int S, int seq, int stage_out) {
   constexpr int U = GRU_U, U3 = 3 * GRU_U;
+  constexpr int GRU_HSTRIDE = GRU_KPT * GRU_BG + 4;            // +4 banks per k-slice: conflict-free LDS.128
+  constexpr int GRU_HBUF = GRU_KQ * GRU_HSTRIDE;               // floats per h buffer
+  constexpr int NV = GRU_CPT * GRU_BG;                         // partial sums per thread
+  constexpr int NOWN = NV / GRU_KQ;                            // complete sums a lane owns after the reduction
+  static_assert(GRU_BG % 4 == 0 && NV % GRU_KQ == 0 && GRU_UPC * GRU_BG <= GRU_THREADS, "unsupported utterance group");
   __shared__ __align__(16) float h_s[2 * GRU_HBUF];                 // [buf][kq][i][b]
   __shared__ __align__(16) float hp_s[GRU_COLS][GRU_BG];
   extern __shared__ __align__(16) float out_s[];                    // [S][gb][gj] when stage_out
 
+#ifdef SAR_GRU_PROFILE
+  const long long t_entry = clock64();
+  long long t_glob0; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_glob0));
+#endif
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int cid = blockIdx.x / GRU_CL;
@@ -73,13 +90,13 @@ bigru_kernel(const float* __restrict__ xp, const float* __restrict__ rec, const 
 #pragma unroll
     for (int i = 0; i < GRU_KPT; ++i) u[c][i] = __ldg(Ud + (size_t)(kq * GRU_KPT + i) * U3 + col);
   }
-  // after the reduction this lane owns column cgp*4 + (kq>>2), utterances (kq&3)*2 + {0,1}
-  const int red_col = cgp * GRU_CPT + (kq >> 2);
-  const int red_b = (kq & 3) * 2;
+  // after the reduction lane kq owns the NOWN sums with index kq*NOWN + j in the thread's [column][utterance] space
+  const int red_col = cgp * GRU_CPT + (kq * NOWN) / GRU_BG;
+  const int red_b = (kq * NOWN) % GRU_BG;
 
   // gate-phase role: thread -> (unit gj, utterance gb)
   const bool gate_thread = t < GRU_UPC * GRU_BG;          // 256 threads
-  const int gj = t >> 3, gb = t & 7;                     // gb fastest: a warp's DSMEM push is one 128 B row
+  const int gj = t / GRU_BG, gb = t % GRU_BG;            // gb fastest: a warp's DSMEM push covers whole h rows
   const int unit = j0 + gj;
   const bool bvalid = gate_thread && (b0 + gb) < B;
   float rbz = 0.f, rbr = 0.f, rbh = 0.f;
@@ -110,58 +127,71 @@ bigru_kernel(const float* __restrict__ xp, const float* __restrict__ rec, const 
   cluster.sync();
 
   int cur = 0;
+#ifdef SAR_GRU_PROFILE
+  long long stamps[32];
+  const long long t_loop = clock64();
+#endif
   for (int step = 0; step < S; ++step) {
+    GRU_STAMP(0)
     // ---- partial dot products: 4 columns x 16 k's x 8 utterances
-    float v[GRU_CPT * GRU_BG];
+    float v[NV];
 #pragma unroll
-    for (int i = 0; i < GRU_CPT * GRU_BG; ++i) v[i] = 0.f;
+    for (int i = 0; i < NV; ++i) v[i] = 0.f;
     const float* hq = h_s + cur * GRU_HBUF + kq * GRU_HSTRIDE;
 #pragma unroll
     for (int i = 0; i < GRU_KPT; ++i) {
-      const float4 ha = *reinterpret_cast<const float4*>(hq + i * GRU_BG);
-      const float4 hb = *reinterpret_cast<const float4*>(hq + i * GRU_BG + 4);
-      const float hv[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+      float hv[GRU_BG];
+#pragma unroll
+      for (int q = 0; q < GRU_BG / 4; ++q) {
+        const float4 h4 = *reinterpret_cast<const float4*>(hq + i * GRU_BG + 4 * q);
+        hv[4 * q] = h4.x; hv[4 * q + 1] = h4.y; hv[4 * q + 2] = h4.z; hv[4 * q + 3] = h4.w;
+      }
 #pragma unroll
       for (int c = 0; c < GRU_CPT; ++c)
 #pragma unroll
         for (int b = 0; b < GRU_BG; ++b) v[c * GRU_BG + b] = fmaf(u[c][i], hv[b], v[c * GRU_BG + b]);
     }
-    // ---- recursive-halving reduction over the 16 k-slices (lanes kq = lane & 15)
-    float w1[16], w2[8], w3[4], w4[2];
+    GRU_STAMP(1)
+    // ---- recursive-halving reduction over the 16 k-slices (lanes kq = lane & 15): at every level a lane keeps
+    // the half of its index range selected by the corresponding bit of kq and adds the partner's copy of it
+    float w1[NV / 2], w2[NV / 4], w3[NV / 8], w4[NV / 16];
     {
       const bool up = (kq & 8) != 0;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float send = up ? v[i] : v[i + 16], keep = up ? v[i + 16] : v[i];
+      for (int i = 0; i < NV / 2; ++i) {
+        const float send = up ? v[i] : v[i + NV / 2], keep = up ? v[i + NV / 2] : v[i];
         w1[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
       }
     }
     {
       const bool up = (kq & 4) != 0;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float send = up ? w1[i] : w1[i + 8], keep = up ? w1[i + 8] : w1[i];
+      for (int i = 0; i < NV / 4; ++i) {
+        const float send = up ? w1[i] : w1[i + NV / 4], keep = up ? w1[i + NV / 4] : w1[i];
         w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
       }
     }
     {
       const bool up = (kq & 2) != 0;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float send = up ? w2[i] : w2[i + 4], keep = up ? w2[i + 4] : w2[i];
+      for (int i = 0; i < NV / 8; ++i) {
+        const float send = up ? w2[i] : w2[i + NV / 8], keep = up ? w2[i + NV / 8] : w2[i];
         w3[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
       }
     }
     {
       const bool up = (kq & 1) != 0;
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const float send = up ? w3[i] : w3[i + 2], keep = up ? w3[i + 2] : w3[i];
+      for (int i = 0; i < NV / 16; ++i) {
+        const float send = up ? w3[i] : w3[i + NV / 16], keep = up ? w3[i + NV / 16] : w3[i];
         w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
       }
     }
-    *reinterpret_cast<float2*>(&hp_s[red_col][red_b]) = make_float2(w4[0], w4[1]);
+    GRU_STAMP(2)
+#pragma unroll
+    for (int j = 0; j < NOWN; ++j) hp_s[red_col][red_b + j] = w4[j];
     __syncthreads();
+    GRU_STAMP(3)
 
     // ---- gates for my 32 units x 8 utterances, push h' to every CTA of the cluster
     if (gate_thread) {
@@ -184,18 +214,32 @@ bigru_kernel(const float* __restrict__ xp, const float* __restrict__ rec, const 
         else if (step == S - 1) out[(size_t)(b0 + gb) * (2 * U) + dir * U + unit] = hn;
       }
     }
+    GRU_STAMP(4)
     if (seq & 4) __syncthreads(); else
     cluster_arrive_release();            // publishes my DSMEM stores (no global store is pending)
     // rotate the x-projection registers and prefetch step+2 while the barrier completes
     x0z = x1z; x0r = x1r; x0h = x1h;
     if (bvalid && step + 2 < S) { const float* p = xrow(step + 2); x1z = __ldg(p); x1r = __ldg(p + U); x1h = __ldg(p + 2 * U); }
+    GRU_STAMP(5)
     if (!(seq & 4)) cluster_wait_acquire();
+    GRU_STAMP(6)
     cur ^= 1;
   }
+#ifdef SAR_GRU_PROFILE
+  const long long t_loop_end = clock64();
+#endif
+#ifdef SAR_GRU_PROFILE
+  if (blockIdx.x == 0 && t == 0)
+    for (int i = 0; i < 4; ++i)
+      printf("gru step %d: fma %lld  reduce %lld  sts+bar %lld  gates+push %lld  arrive+prefetch %lld  wait %lld | total %lld\n", 8 + i,
+             stamps[i * 8 + 1] - stamps[i * 8], stamps[i * 8 + 2] - stamps[i * 8 + 1], stamps[i * 8 + 3] - stamps[i * 8 + 2],
+             stamps[i * 8 + 4] - stamps[i * 8 + 3], stamps[i * 8 + 5] - stamps[i * 8 + 4], stamps[i * 8 + 6] - stamps[i * 8 + 5],
+             stamps[i * 8 + 6] - stamps[i * 8]);
+#endif
 
   // ---- write the staged outputs: 32 consecutive units (128 B) per (step, utterance)
   if (stage_out && gate_thread) {
-    const int oj = t & 31, ob = t >> 5;                    // unit fastest for coalesced global stores
+    const int oj = t & 31, ob = t >> 5;                    // unit fastest for coalesced global stores (ob < GRU_BG)
     if (b0 + ob < B) {
       if (seq) {
         for (int step = 0; step < S; ++step) {
@@ -208,6 +252,13 @@ bigru_kernel(const float* __restrict__ xp, const float* __restrict__ rec, const 
       }
     }
   }
+#ifdef SAR_GRU_PROFILE
+  if ((blockIdx.x == 0 || blockIdx.x == 127) && t == 0) {
+    long long t_glob1; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_glob1));
+    printf("gru cta %d: prologue %lld  loop %lld  epilogue %lld cycles; globaltimer %lld ns\n", (int)blockIdx.x, t_loop - t_entry, t_loop_end - t_loop,
+           clock64() - t_loop_end, t_glob1 - t_glob0);
+  }
+#endif
 }
 
 }  // namespace sar
@@ -218,14 +269,38 @@ extern "C" int sar_bigru_fwd(const float* xp, const float* rec, const float* rbi
   SAR_REQUIRE(xp && rec && rbias && out, SAR_ERR_BAD_ARG, "sar_bigru_fwd: null pointer");
   SAR_REQUIRE(B > 0 && S > 0, SAR_ERR_BAD_ARG, "sar_bigru_fwd: non-positive dimension");
   SAR_REQUIRE(u == GRU_U, SAR_ERR_UNSUPPORTED, "sar_bigru_fwd: hidden size %d unsupported (this build: %d)", u, GRU_U);
-  const int groups = (B + GRU_BG - 1) / GRU_BG;
+  // utterances per cluster: fewest waves of at most GRU_MAX_CLUSTERS resident clusters, weighted by the measured
+  // step time of each variant (~3.9k cycles at 8 utterances, ~4.7k at 12)
+  auto waves = [](int B_, int bg) { const int cl = 2 * ((B_ + bg - 1) / bg); return (cl + GRU_MAX_CLUSTERS - 1) / GRU_MAX_CLUSTERS; };
+  const int bg = (waves(B, 8) * 39 <= waves(B, 12) * 47) ? 8 : 12;
+  const int groups = (B + bg - 1) / bg;
   dim3 grid(GRU_CL * groups * 2);
-  size_t smem = seq ? (size_t)S * GRU_UPC * GRU_BG * sizeof(float) : (size_t)GRU_UPC * GRU_BG * sizeof(float);
+  size_t smem = seq ? (size_t)S * GRU_UPC * bg * sizeof(float) : (size_t)GRU_UPC * bg * sizeof(float);
   int stage_out = 1;
-  if (smem > 180 * 1024) { smem = 0; stage_out = 0; }      // very long sequences: write through
-  cudaError_t e = cudaFuncSetAttribute(bigru_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(180 * 1024));
-  if (e != cudaSuccess) { set_error("sar_bigru_fwd: %s", cudaGetErrorString(e)); return (int)e; }
-  launch_k(bigru_kernel, dim3(grid), dim3(GRU_THREADS), smem, (cudaStream_t)stream, xp, rec, rbias, out, B, S, seq, stage_out);
+  if (smem > 160 * 1024) { smem = 0; stage_out = 0; }      // very long sequences: write through
+  auto launch = [&](auto kern) -> int {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(160 * 1024));
+    if (e != cudaSuccess) { set_error("sar_bigru_fwd: %s", cudaGetErrorString(e)); return (int)e; }
+    launch_k(kern, dim3(grid), dim3(GRU_THREADS), smem, (cudaStream_t)stream, xp, rec, rbias, out, B, S, seq, stage_out);
+    return 0;
+  };
+  const int lrc = bg == 8 ? launch(bigru_kernel<8>) : launch(bigru_kernel<12>);
+  if (lrc) return lrc;
   seq &= 1;
   return check_launch("sar_bigru_fwd");
+}
+
+// diagnostic (not part of include/sarnet.h): how many 8-CTA clusters of bigru_kernel can be resident at once
+extern "C" int sar_debug_bigru_max_clusters(int smem_bytes) {
+  using namespace sar;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(GRU_CL * 64); cfg.blockDim = dim3(GRU_THREADS); cfg.dynamicSmemBytes = (size_t)smem_bytes;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = GRU_CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaFuncSetAttribute(bigru_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(160 * 1024));
+  int n = -1;
+  cudaError_t e = cudaOccupancyMaxActiveClusters(&n, bigru_kernel<12>, &cfg);
+  return e == cudaSuccess ? n : -(int)e;
 }

@@ -13,8 +13,8 @@
 
 namespace sar {
 
-constexpr int HEAD_THREADS = 128;
-constexpr int HEAD_MAXC = 32;      // max classes
+constexpr int HEAD_THREADS = 256;
+constexpr int HEAD_MAXC = 32;      // max classes (one warp lane per class in the final stage)
 constexpr float K_EPS = 1e-7f;
 
 struct HeadP {
@@ -27,82 +27,119 @@ struct HeadP {
   float* y_accent; float* y_accent_logits; float* y_disc; float* y_disc_logits; float* stats;
 };
 
-__device__ __forceinline__ float ce_on_probs(const float* p, const float* y, int n) {
-  // keras categorical_crossentropy on probabilities
-  float sum = 0.f;
-  for (int c = 0; c < n; ++c) sum += p[c];
-  float l = 0.f;
-  for (int c = 0; c < n; ++c) {
-    float q = fminf(fmaxf(p[c] / sum, K_EPS), 1.f - K_EPS);
-    l -= y[c] * logf(q);
+// y[j] = sum_d x[d] * w[d*ldw + j] for j < nout, the d range cut into `parts` slices so that all HEAD_THREADS
+// threads carry independent load streams (the op is pure L2 latency: a 256 x 64 weight block is read once per
+// utterance); slice partials meet in shared memory and are summed in a fixed order (deterministic).
+// With SQ, wsq[j] = sum_d w[d][j]^2 as well (the column norms of the Face heads).  Ends with a barrier.
+template <bool SQ>
+__device__ __forceinline__ void matvec_parts(const float* x, int D, const float* __restrict__ w, int nout, float xscale,
+                                             float* pacc, float* psq, float* y, float* wsq, int t) {
+  if (nout <= HEAD_THREADS) {
+    const int parts = HEAD_THREADS / nout;
+    if (t < parts * nout) {
+      const int j = t % nout, part = t / nout;
+      const int dlo = (int)(((long long)D * part) / parts), dhi = (int)(((long long)D * (part + 1)) / parts);
+      float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
+      int d = dlo;
+#pragma unroll 8
+      for (; d + 1 < dhi; d += 2) {
+        const float w0 = __ldg(w + (size_t)d * nout + j), w1 = __ldg(w + (size_t)(d + 1) * nout + j);
+        a0 = fmaf(x[d] * xscale, w0, a0);
+        a1 = fmaf(x[d + 1] * xscale, w1, a1);
+        if (SQ) { q0 = fmaf(w0, w0, q0); q1 = fmaf(w1, w1, q1); }
+      }
+      if (d < dhi) {
+        const float w0 = __ldg(w + (size_t)d * nout + j);
+        a0 = fmaf(x[d] * xscale, w0, a0);
+        if (SQ) q0 = fmaf(w0, w0, q0);
+      }
+      pacc[part * nout + j] = a0 + a1;
+      if (SQ) psq[part * nout + j] = q0 + q1;
+    }
+    __syncthreads();
+    if (t < nout) {
+      float a = 0.f, q = 0.f;
+      for (int part = 0; part < parts; ++part) { a += pacc[part * nout + t]; if (SQ) q += psq[part * nout + t]; }
+      y[t] = a;
+      if (SQ) wsq[t] = q;
+    }
+  } else {                                   // wide layers: one output per thread per round
+    for (int j = t; j < nout; j += HEAD_THREADS) {
+      float a = 0.f, q = 0.f;
+      for (int d = 0; d < D; ++d) {
+        const float w0 = __ldg(w + (size_t)d * nout + j);
+        a = fmaf(x[d] * xscale, w0, a);
+        if (SQ) q = fmaf(w0, w0, q);
+      }
+      y[j] = a;
+      if (SQ) wsq[j] = q;
+    }
   }
-  return l;
+  __syncthreads();
 }
-__device__ __forceinline__ int argmax_first(const float* v, int n) {
-  int a = 0;
-  for (int c = 1; c < n; ++c) if (v[c] > v[a]) a = c;
-  return a;
+
+// lane c < n holds v; returns the index of the first maximum (np.argmax tie rule) on every lane
+__device__ __forceinline__ int warp_argmax_first(float v, int lane, int n) {
+  float bv = lane < n ? v : -INFINITY;
+  int bi = lane < n ? lane : 0x7fffffff;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  return bi;
 }
-__device__ __forceinline__ void softmax_small(const float* logit, float* p, int n) {
-  float m = logit[0];
-  for (int c = 1; c < n; ++c) m = fmaxf(m, logit[c]);
-  float sum = 0.f;
-  for (int c = 0; c < n; ++c) { p[c] = expf(logit[c] - m); sum += p[c]; }
-  for (int c = 0; c < n; ++c) p[c] /= sum;
+// softmax over the n live lanes
+__device__ __forceinline__ float warp_softmax(float logit, int lane, int n) {
+  const float m = warp_max(lane < n ? logit : -INFINITY);
+  const float e = lane < n ? expf(logit - m) : 0.f;
+  return e / warp_sum(e);
+}
+// keras categorical_crossentropy on probabilities: p /= sum p; clip(1e-7, 1-1e-7); -sum y log p
+__device__ __forceinline__ float warp_ce_on_probs(float pr, float y, int lane, int n) {
+  const float sum = warp_sum(lane < n ? pr : 0.f);
+  const float q = fminf(fmaxf(pr / sum, K_EPS), 1.f - K_EPS);
+  return warp_sum(lane < n ? -y * logf(q) : 0.f);
 }
 
 __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(HeadP p) {
   extern __shared__ __align__(16) float sm[];
-  float* x = sm;                         // [max(D,Dd)]
-  float* h1 = x + max(p.D, p.Dd);        // [H1]
-  float* h2 = h1 + p.H1;                 // [H2]   (h1|h2 region is at least HEAD_THREADS floats)
-  float* la = h1 + max(p.H1 + p.H2, HEAD_THREADS);   // [n] accent logits
-  float* ld = la + HEAD_MAXC;            // [n] disc cos / logits
-  float* wn = ld + HEAD_MAXC;            // [n] column norms^2
+  const int Dmax = max(p.D, p.Dd), Hmax = max(max(p.H1, p.H2), HEAD_MAXC);
+  float* x = sm;                         // [Dmax]
+  float* h1 = x + Dmax;                  // [Hmax]
+  float* h2 = h1 + Hmax;                 // [Hmax]
+  float* wn = h2 + Hmax;                 // [HEAD_MAXC] column norms^2
   float* scratch = wn + HEAD_MAXC;       // [32]
-  const int t = threadIdx.x, b = blockIdx.x, n = p.n;
+  float* pacc = scratch + 32;            // [HEAD_THREADS]
+  float* psq = pacc + HEAD_THREADS;      // [HEAD_THREADS]
+  const int t = threadIdx.x, lane = t & 31, b = blockIdx.x, n = p.n;
   pdl_wait();
   pdl_trigger();
-  const float* y = p.onehot ? p.onehot + (size_t)b * n : nullptr;
+  const float* yrow = p.onehot ? p.onehot + (size_t)b * n : nullptr;
+  const float yc = (yrow && t < n) ? __ldg(yrow + t) : 0.f;        // lane c of warp 0: one-hot entry of class c
   float loss_a = 0.f, loss_d = 0.f, corr_a = 0.f, corr_d = 0.f;
 
   if (p.w1) {
     for (int d = t; d < p.D; d += HEAD_THREADS) x[d] = __ldg(p.emb + (size_t)b * p.D + d);
     __syncthreads();
-    for (int j = t; j < p.H1; j += HEAD_THREADS) {
-      float acc = __ldg(p.b1 + j), acc2 = 0.f;
-      int d = 0;
-#pragma unroll 8
-      for (; d + 1 < p.D; d += 2) {          // two chains, loads batched by the unroll
-        acc = fmaf(x[d], __ldg(p.w1 + (size_t)d * p.H1 + j), acc);
-        acc2 = fmaf(x[d + 1], __ldg(p.w1 + (size_t)(d + 1) * p.H1 + j), acc2);
+    matvec_parts<false>(x, p.D, p.w1, p.H1, 1.f, pacc, psq, h1, nullptr, t);
+    for (int j = t; j < p.H1; j += HEAD_THREADS) h1[j] = fmaxf(h1[j] + __ldg(p.b1 + j), 0.f);
+    __syncthreads();
+    matvec_parts<false>(h1, p.H1, p.w2, p.H2, 1.f, pacc, psq, h2, nullptr, t);
+    for (int j = t; j < p.H2; j += HEAD_THREADS) h2[j] = fmaxf(h2[j] + __ldg(p.b2 + j), 0.f);
+    __syncthreads();
+    matvec_parts<false>(h2, p.H2, p.w3, n, 1.f, pacc, psq, h1, nullptr, t);      // h1[0..n) = logits - bias
+    if (t < 32) {
+      const float la = lane < n ? h1[lane] + __ldg(p.b3 + lane) : 0.f;
+      const float pr = warp_softmax(la, lane, n);
+      if (lane < n) {
+        if (p.y_accent) p.y_accent[(size_t)b * n + lane] = pr;
+        if (p.y_accent_logits) p.y_accent_logits[(size_t)b * n + lane] = la;
       }
-      if (d < p.D) acc = fmaf(x[d], __ldg(p.w1 + (size_t)d * p.H1 + j), acc);
-      h1[j] = fmaxf(acc + acc2, 0.f);
-    }
-    __syncthreads();
-    for (int j = t; j < p.H2; j += HEAD_THREADS) {
-      float acc = __ldg(p.b2 + j);
-      for (int d = 0; d < p.H1; ++d) acc = fmaf(h1[d], __ldg(p.w2 + (size_t)d * p.H2 + j), acc);
-      h2[j] = fmaxf(acc, 0.f);
-    }
-    __syncthreads();
-    if (t < n) {
-      float acc = __ldg(p.b3 + t);
-      for (int d = 0; d < p.H2; ++d) acc = fmaf(h2[d], __ldg(p.w3 + (size_t)d * n + t), acc);
-      la[t] = acc;
-    }
-    __syncthreads();
-    if (t == 0) {
-      float pr[HEAD_MAXC];
-      softmax_small(la, pr, n);
-      for (int c = 0; c < n; ++c) {
-        if (p.y_accent) p.y_accent[(size_t)b * n + c] = pr[c];
-        if (p.y_accent_logits) p.y_accent_logits[(size_t)b * n + c] = la[c];
-      }
-      if (y) {
-        loss_a = ce_on_probs(pr, y, n);
-        corr_a = (argmax_first(pr, n) == argmax_first(y, n)) ? 1.f : 0.f;
+      if (yrow) {
+        loss_a = warp_ce_on_probs(pr, yc, lane, n);
+        corr_a = (warp_argmax_first(pr, lane, n) == warp_argmax_first(yc, lane, n)) ? 1.f : 0.f;
       }
     }
     __syncthreads();
@@ -113,84 +150,52 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(HeadP p) {
     const int Dd = p.emb_d ? p.Dd : p.D;
     float ssq = 0.f;
     for (int d = t; d < Dd; d += HEAD_THREADS) {
-      float v = __ldg(e + (size_t)b * Dd + d);
+      const float v = __ldg(e + (size_t)b * Dd + d);
       x[d] = v;
       ssq += v * v;
     }
     ssq = block_sum(ssq, scratch);      // contains the barriers that publish x[]
     const bool normalise_x = p.head != SAR_HEAD_SOFTMAX && p.head != SAR_HEAD_CIRCLE_RAW;
     const float xinv = normalise_x ? 1.0f / sqrtf(fmaxf(ssq, 1e-12f)) : 1.f;
-    // x^ . W[:, c] and |W[:, c]|^2: classes x (HEAD_THREADS / n) d-slices, partials through smem
-    const int parts = HEAD_THREADS / n;
-    float* pacc = h1;                       // [parts][n]  (h1/h2 are free after the classifier)
-    float* pwss = wn + HEAD_MAXC + 32;      // placed after scratch: [parts][n]
-    if (t < parts * n) {
-      const int c = t % n, part = t / n;
-      const int dlo = (int)(((long long)Dd * part) / parts), dhi = (int)(((long long)Dd * (part + 1)) / parts);
-      float a = 0.f, w2 = 0.f;
-#pragma unroll 4
-      for (int d = dlo; d < dhi; ++d) {
-        const float wv = __ldg(p.wd + (size_t)d * n + c);
-        a = fmaf(x[d] * xinv, wv, a);
-        w2 = fmaf(wv, wv, w2);
-      }
-      pacc[part * n + c] = a;
-      pwss[part * n + c] = w2;
-    }
-    __syncthreads();
-    if (t < n) {
-      float acc = 0.f, wss = 0.f;
-      for (int part = 0; part < parts; ++part) { acc += pacc[part * n + t]; wss += pwss[part * n + t]; }
+    matvec_parts<true>(x, Dd, p.wd, n, xinv, pacc, psq, h2, wn, t);               // h2[c] = x^ . W[:, c]
+    if (t < 32) {
       const bool face = p.head == SAR_HEAD_SPHEREFACE || p.head == SAR_HEAD_COSFACE || p.head == SAR_HEAD_ARCFACE;
-      if (face) acc *= 1.0f / sqrtf(fmaxf(wss, 1e-12f));      // W normalised per column, losses.py:34,80,127
-      ld[t] = acc;
-    }
-    __syncthreads();
-    if (t == 0) {
-      float lg[HEAD_MAXC], pr[HEAD_MAXC];
+      float v = lane < n ? h2[lane] : 0.f;
+      if (face && lane < n) v *= 1.0f / sqrtf(fmaxf(wn[lane], 1e-12f));          // W normalised per column, losses.py:34,80,127
       if (p.head == SAR_HEAD_CIRCLE || p.head == SAR_HEAD_CIRCLE_RAW) {
-        for (int c = 0; c < n; ++c) {
-          if (p.y_disc) p.y_disc[(size_t)b * n + c] = ld[c];
-          if (p.y_disc_logits) p.y_disc_logits[(size_t)b * n + c] = ld[c];
+        if (lane < n) {
+          if (p.y_disc) p.y_disc[(size_t)b * n + lane] = v;
+          if (p.y_disc_logits) p.y_disc_logits[(size_t)b * n + lane] = v;
         }
-        if (y) {
+        if (yrow) {
           // circle_loss, losses.py:157-172
           const float m = p.margin;
-          for (int c = 0; c < n; ++c) {
-            float ap = fmaxf(1.f + m - ld[c], 0.f), an = fmaxf(ld[c] + m, 0.f);
-            lg[c] = (y[c] * (ap * (ld[c] - (1.f - m))) + (1.f - y[c]) * (an * (ld[c] - m))) * p.gamma;
-          }
-          float mx = lg[0];
-          for (int c = 1; c < n; ++c) mx = fmaxf(mx, lg[c]);
-          float sum = 0.f;
-          for (int c = 0; c < n; ++c) sum += expf(lg[c] - mx);
-          float lse = mx + logf(sum);
-          for (int c = 0; c < n; ++c) loss_d -= y[c] * (lg[c] - lse);
-          corr_d = (argmax_first(ld, n) == argmax_first(y, n)) ? 1.f : 0.f;
+          const float ap = fmaxf(1.f + m - v, 0.f), an = fmaxf(v + m, 0.f);
+          const float lg = (yc * (ap * (v - (1.f - m))) + (1.f - yc) * (an * (v - m))) * p.gamma;
+          const float mx = warp_max(lane < n ? lg : -INFINITY);
+          const float lse = mx + logf(warp_sum(lane < n ? expf(lg - mx) : 0.f));
+          loss_d = warp_sum(lane < n ? -yc * (lg - lse) : 0.f);
+          corr_d = (warp_argmax_first(v, lane, n) == warp_argmax_first(yc, lane, n)) ? 1.f : 0.f;
         }
       } else {
-        for (int c = 0; c < n; ++c) {
-          float v = ld[c];
-          if (p.head != SAR_HEAD_SOFTMAX) {
-            float yc = y ? y[c] : 0.f;
-            float target = v;
-            if (p.head == SAR_HEAD_COSFACE) target = v - p.margin;
-            else {
-              float th = acosf(fminf(fmaxf(v, -1.f + K_EPS), 1.f - K_EPS));
-              target = (p.head == SAR_HEAD_SPHEREFACE) ? cosf(p.margin * th) : cosf(th + p.margin);
-            }
-            v = (v * (1.f - yc) + target * yc) * p.s;
+        float lg = v;
+        if (p.head != SAR_HEAD_SOFTMAX) {
+          float target = v;
+          if (p.head == SAR_HEAD_COSFACE) target = v - p.margin;
+          else {
+            const float th = acosf(fminf(fmaxf(v, -1.f + K_EPS), 1.f - K_EPS));
+            target = (p.head == SAR_HEAD_SPHEREFACE) ? cosf(p.margin * th) : cosf(th + p.margin);
           }
-          lg[c] = v;
+          lg = (v * (1.f - yc) + target * yc) * p.s;
         }
-        softmax_small(lg, pr, n);
-        for (int c = 0; c < n; ++c) {
-          if (p.y_disc) p.y_disc[(size_t)b * n + c] = pr[c];
-          if (p.y_disc_logits) p.y_disc_logits[(size_t)b * n + c] = lg[c];
+        const float pr = warp_softmax(lg, lane, n);
+        if (lane < n) {
+          if (p.y_disc) p.y_disc[(size_t)b * n + lane] = pr;
+          if (p.y_disc_logits) p.y_disc_logits[(size_t)b * n + lane] = lg;
         }
-        if (y) {
-          loss_d = ce_on_probs(pr, y, n);
-          corr_d = (argmax_first(pr, n) == argmax_first(y, n)) ? 1.f : 0.f;
+        if (yrow) {
+          loss_d = warp_ce_on_probs(pr, yc, lane, n);
+          corr_d = (warp_argmax_first(pr, lane, n) == warp_argmax_first(yc, lane, n)) ? 1.f : 0.f;
         }
       }
     }
@@ -233,7 +238,9 @@ extern "C" int sar_head_fwd(const float* emb, int D,
   if (!emb) D = 0;
   int dmax = D > 0 ? D : 0;
   if (emb_d && Dd > dmax) dmax = Dd;
-  size_t smem = sizeof(float) * ((size_t)dmax + (H1 + H2 > HEAD_THREADS ? H1 + H2 : HEAD_THREADS) + 3 * HEAD_MAXC + 32 + HEAD_THREADS);
+  int hmax = H1 > H2 ? H1 : H2;
+  if (hmax < HEAD_MAXC) hmax = HEAD_MAXC;
+  size_t smem = sizeof(float) * ((size_t)dmax + 2 * (size_t)hmax + HEAD_MAXC + 32 + 2 * HEAD_THREADS);
   SAR_REQUIRE(smem <= 200 * 1024, SAR_ERR_UNSUPPORTED, "sar_head_fwd: embedding too wide");
   HeadP p{emb, D, w1, b1, H1, w2, b2, H2, w3, b3, emb_d, emb_d ? Dd : D, wd, onehot, n_classes, head,
           margin, s, gamma, y_accent, y_accent_logits, y_disc, y_disc_logits, sample_stats};

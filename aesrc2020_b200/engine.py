@@ -338,7 +338,7 @@ class SARNetEngine:
         key = (tag,) + tuple(sorted((k, tuple(v.shape), str(v.dtype)) for k, v in inputs.items()))
         entry = self._graphs.get(key)
         if entry is None:
-            static_in = {k: v.clone() for k, v in inputs.items()}
+            static_in = {k: torch.empty_like(v, device=self.device).copy_(v) for k, v in inputs.items()}   # inputs may be pinned host tensors
             cur = torch.cuda.current_stream()
             side = torch.cuda.Stream()
             side.wait_stream(cur)

@@ -266,6 +266,8 @@ class SARModel:
         self._outputs = outputs or config.output_names()
         self._engine: Optional[SARNetEngine] = None
         self._pinned: Dict[str, torch.Tensor] = {}
+        self._pin_events: Dict[str, torch.cuda.Event] = {}
+        self._pinned_out: Optional[torch.Tensor] = None
         self.use_graph = True          # replay a CUDA graph of the step (captured once per batch shape)
 
     # -- Keras-like surface
@@ -307,21 +309,41 @@ class SARModel:
         self._engine = None
 
     # -- execution
+    def _to_host_tensor(self, key: str, v) -> torch.Tensor:
+        """numpy input -> host tensor of the dtype the kernels take, in PAGE-LOCKED memory: arrays that already
+        live in pinned memory (utils.pinned_like -- what a loader's ring buffer would be) are used in place, any
+        other array is staged through a cached pinned buffer (guarded by an event: the previous asynchronous
+        H2D out of that buffer must have finished before it is overwritten)."""
+        a = np.ascontiguousarray(v)
+        want = np.int32 if key in ("x_ctc_in_len", "x_ctc_out_len") else np.float32
+        a = a.astype(want, copy=False)
+        th = torch.from_numpy(a)
+        if a.nbytes >= (1 << 16) and th.is_pinned():
+            return th
+        pin = self._pinned.get(key)
+        if pin is None or pin.shape != th.shape or pin.dtype != th.dtype:
+            pin = torch.empty(th.shape, dtype=th.dtype, pin_memory=True)
+            self._pinned[key] = pin
+        ev = self._pin_events.get(key)
+        if ev is not None:
+            ev.synchronize()
+        pin.copy_(th)
+        return pin
+
+    def _mark_h2d(self, keys):
+        for k in keys:
+            if k in self._pinned:
+                ev = self._pin_events.get(k)
+                if ev is None:
+                    ev = self._pin_events[k] = torch.cuda.Event()
+                ev.record()
+
     def _to_device(self, key: str, v: ArrayLike) -> torch.Tensor:
         if isinstance(v, torch.Tensor):
             t = v.to(self.device, non_blocking=True)
         else:
-            a = np.ascontiguousarray(v)
-            if key in ("x_ctc_in_len", "x_ctc_out_len"):
-                a = a.astype(np.int32, copy=False)
-            else:
-                a = a.astype(np.float32, copy=False)
-            pin = self._pinned.get(key)
-            if pin is None or pin.shape != a.shape or pin.dtype != torch.from_numpy(a).dtype:
-                pin = torch.empty(a.shape, dtype=torch.from_numpy(a).dtype, pin_memory=True)
-                self._pinned[key] = pin
-            pin.copy_(torch.from_numpy(a))
-            t = pin.to(self.device, non_blocking=True)
+            t = self._to_host_tensor(key, v).to(self.device, non_blocking=True)
+            self._mark_h2d([key])
         if key in ("x_ctc_in_len", "x_ctc_out_len"):
             return t.to(torch.int32)
         return t.float() if t.dtype != torch.float32 else t
@@ -340,11 +362,20 @@ class SARModel:
         missing = [k for k in self.config.input_names() if k not in xd]
         if missing:
             raise ValueError("missing model inputs: %s" % missing)
-        dev_in = {k: self._to_device(k, v) for k, v in xd.items()}
         use_graph = self.use_graph if graph is None else graph
         if use_graph and not want_intermediates:
-            out = self.engine().forward_graphed(dev_in)
+            # host inputs go from page-locked memory STRAIGHT into the captured graph's static input buffers
+            # (one asynchronous H2D per input, no intermediate device tensor)
+            src = {}
+            for k, v in xd.items():
+                if isinstance(v, torch.Tensor):
+                    src[k] = self._to_device(k, v)
+                else:
+                    src[k] = self._to_host_tensor(k, v)
+            out = self.engine().forward_graphed(src)
+            self._mark_h2d([k for k, v in xd.items() if not isinstance(v, torch.Tensor)])
         else:
+            dev_in = {k: self._to_device(k, v) for k, v in xd.items()}
             out = self.engine().forward(dev_in, want_intermediates=want_intermediates)
         if self.config.ctc_enable and bool((out["ctc_status"] != 0).any()):
             # tf.nn.ctc_loss raises on infeasible / out-of-range labels
@@ -362,8 +393,24 @@ class SARModel:
         for b0 in range(0, n, batch_size):
             sl = {k: v[b0:b0 + batch_size] for k, v in xd.items()}
             out = self.forward_device(sl)
-            for i, name in enumerate(self._outputs):
-                chunks[i].append(out[name].clone() if on_device else out[name].cpu().numpy())
+            if on_device:
+                for i, name in enumerate(self._outputs):
+                    chunks[i].append(out[name].clone())
+                continue
+            # all outputs of the chunk -> one pinned buffer, asynchronously, then ONE stream synchronisation
+            outs = [out[name] for name in self._outputs]
+            tot = sum(o.numel() for o in outs)
+            if self._pinned_out is None or self._pinned_out.numel() < tot:
+                self._pinned_out = torch.empty((max(tot, 4096),), dtype=torch.float32, pin_memory=True)
+            off = 0
+            for o in outs:
+                self._pinned_out[off:off + o.numel()].view(o.shape).copy_(o, non_blocking=True)
+                off += o.numel()
+            torch.cuda.current_stream().synchronize()
+            off = 0
+            for i, o in enumerate(outs):
+                chunks[i].append(self._pinned_out[off:off + o.numel()].view(o.shape).numpy().copy())
+                off += o.numel()
         cat = (lambda c: torch.cat(c, 0)) if on_device else (lambda c: np.concatenate(c, 0))
         res = [cat(c) for c in chunks]
         return res[0] if len(res) == 1 else res

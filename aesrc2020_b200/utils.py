@@ -84,3 +84,17 @@ def synthetic_batch(cfg: SARConfig, B: int, seed: int = 2020, lengths: Optional[
         inputs["x_ctc_out_len"] = lab_len
         targets["y_ctc_loss"] = np.zeros([B])
     return inputs, targets
+
+
+def pinned_like(arrays: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
+    """Copies of `arrays` in PAGE-LOCKED host memory (numpy views of pinned torch tensors) -- what a loader's
+    ring buffer would hand to model.predict(): such arrays are DMA'd to the device in place, pageable ones are
+    first staged through an internal pinned buffer."""
+    import torch
+    out = {}
+    for k, v in arrays.items():
+        a = np.ascontiguousarray(v)
+        t = torch.empty(a.shape, dtype=torch.from_numpy(a).dtype, pin_memory=True)
+        t.copy_(torch.from_numpy(a))
+        out[k] = t.numpy()          # the array keeps the tensor alive through its .base
+    return out

@@ -208,7 +208,7 @@ def main():
         if args.config == "cfg3":
             lengths = np.random.RandomState(100 + i + 1000 * rank).randint(200, 801, size=B)
         x, _ = us.synthetic_batch(cfg, B, seed=2020 + i + 1000 * rank, lengths=lengths)
-        host_batches.append(x)
+        host_batches.append(us.pinned_like(x))      # e2e: inputs start in pinned host memory (a loader's ring buffer)
         dev_batches.append({k: model._to_device(k, v).clone() for k, v in x.items()})
     torch.cuda.synchronize()
     in_bytes = sum(v.nbytes for v in host_batches[0].values())
