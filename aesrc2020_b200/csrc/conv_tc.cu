@@ -65,6 +65,7 @@ struct TcParams {
   long long* dbg;                        // optional: clock64 timestamps of CTA 0 (profiling aid)
   int mma_mask;                          // experiment: which of the 3 hi/lo products to issue (7 = all)
   int act_kind;                          // activated outputs: 0 relu(scale*v+shift), 1 identity, 2 tanh(v)
+  int epi_tma;                           // slab kernel: plane outputs (and the identity shortcut) move by TMA
 };
 
 // ------------------------------------------------------------------ epilogue (shared by both kernels)
@@ -194,6 +195,175 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, int tile, int i
   __syncwarp();
   if (p.dbg && blockIdx.x == 0 && quad == 0 && lane == 0 && it < 8) p.dbg[32 + it * 2 + 1] = clock64();
   if (lane == 0) mbar_arrive(&tempty_bar[as]);
+}
+
+// ------------------------------------------------------------------ TMA epilogue (slab kernel, plane outputs)
+// The row-per-thread global stores above touch 32 different cache lines per instruction (a row chunk is 64 B of a
+// Cout*2-byte pitch): measured 2-4k cycles per 32-column chunk, the critical path of every conv2.  Here a warp
+// stages its 32 rows x 32 channels per plane in shared memory in the 64B-swizzled layout of a TMA box (conflict
+// free: lane = row, 16 B piece j lands in slot j ^ ((row >> 1) & 3)) and one lane issues cp.async.bulk.tensor
+// stores; the identity-shortcut chunk arrives the same way (TMA load into the buffer the raw sum is then staged
+// in).  Pad rows are stored as zeros (they must stay zero), rows beyond the tensor are clipped by the tensor map.
+//
+// Work item = (tile, 32-column chunk).  The eight epilogue warps are two groups of four (one warp per TMEM lane
+// quadrant); group g takes the items with (it * nchunks + chunk) % 2 == g, so the chunks of a single-tile CTA
+// (late stages) drain in parallel and thin tiles (BN = 32) alternate between the groups.
+constexpr int EPI_PLANE_BYTES = 32 * 64;           // 32 rows x 32 fp16 channels
+constexpr int EPI_BUF_BYTES = 2 * EPI_PLANE_BYTES; // hi | lo
+constexpr int EPI_WARP_BYTES = 2 * EPI_BUF_BYTES;  // R (shortcut in, raw out in place), A (activated out)
+
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+  uint32_t hh[4], ll[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const __half2 h2 = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+    const float2 hf = __half22float2(h2);
+    const __half2 l2 = __floats2half2_rn((v[2 * e] - hf.x) * TC_LO_SCALE, (v[2 * e + 1] - hf.y) * TC_LO_SCALE);
+    hh[e] = *reinterpret_cast<const uint32_t*>(&h2);
+    ll[e] = *reinterpret_cast<const uint32_t*>(&l2);
+  }
+  hi = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+  lo = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+}
+
+// `alias`: the CTA owns a single tile, the staging buffers live in the (by then idle) operand region, so the
+// shortcut chunk can only be requested once the tile's MMAs have retired.
+__device__ __forceinline__ void epilogue_item_tma(const TcParams& p, const CUtensorMap* mapRes, const CUtensorMap* mapRaw,
+                                                  const CUtensorMap* mapAct, int tile, int c, int it, int quad, int lane,
+                                                  uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar,
+                                                  const float* s_bias, const float* s_scale, const float* s_shift,
+                                                  uint32_t stage_u, uint64_t* rbar, uint32_t n_item, bool alias) {
+  const int BN = p.BN;
+  const int as = it & 1;
+  const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+  const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+  const int n0 = nt * BN, c0 = c * 32;
+  const int row0 = mt * TC_BM + quad * 32;
+  const bool has_res = p.res != nullptr;
+  const uint32_t rb = stage_u, ab = stage_u + EPI_BUF_BYTES;
+  auto request_res = [&]() {
+    if (lane == 0) {
+      bulk_wait_read0();                             // this warp's previous stores have finished reading R and A
+      if (has_res) {
+        mbar_expect_tx(rbar, (uint32_t)EPI_BUF_BYTES);
+        tma_load_3d(mapRes, rb, rbar, n0 + c0, row0, 0);
+        tma_load_3d(mapRes, rb + EPI_PLANE_BYTES, rbar, n0 + c0, row0, 1);
+      }
+    }
+    __syncwarp();
+  };
+  if (!alias) request_res();
+  const long long q = (long long)row0 + lane;
+  bool valid = q < p.R;
+  if (valid) {
+    const int n = (int)(q / p.Rimg);
+    const int rem = (int)(q - (long long)n * p.Rimg);
+    const int h = rem / p.P, w = rem - h * p.P;
+    valid = (h < p.H) && (w < p.W);
+  }
+  const uint32_t sw = (uint32_t)((lane >> 1) & 3);                 // swizzle term of this lane's row
+  const uint32_t rowoff = (uint32_t)lane * 64u;
+  mbar_wait(&tfull_bar[as], aphase);
+  tc_fence_after();
+  if (alias) request_res();
+#define EPI_STAMP(j) if (p.dbg && blockIdx.x == 0 && quad == 0 && lane == 0 && it < 4 && c == 0) p.dbg[32 + it * 6 + (j)] = clock64();
+  EPI_STAMP(0)
+  const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 2 * BN);
+  uint32_t r0[32], r1[32];
+  tmem_ld32(tbase + (uint32_t)c0, r0);
+  tmem_ld32(tbase + (uint32_t)(BN + c0), r1);
+  tmem_ld_wait();
+  EPI_STAMP(1)
+  tc_fence_before();                                 // the chunk is in registers: hand the accumulator back
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&tempty_bar[as]);
+  float v[32];
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const float4 b4 = *reinterpret_cast<const float4*>(s_bias + n0 + c0 + 4 * g);
+    v[4 * g + 0] = fmaf(__uint_as_float(r1[4 * g + 0]), TC_LO_INV, __uint_as_float(r0[4 * g + 0])) + b4.x;
+    v[4 * g + 1] = fmaf(__uint_as_float(r1[4 * g + 1]), TC_LO_INV, __uint_as_float(r0[4 * g + 1])) + b4.y;
+    v[4 * g + 2] = fmaf(__uint_as_float(r1[4 * g + 2]), TC_LO_INV, __uint_as_float(r0[4 * g + 2])) + b4.z;
+    v[4 * g + 3] = fmaf(__uint_as_float(r1[4 * g + 3]), TC_LO_INV, __uint_as_float(r0[4 * g + 3])) + b4.w;
+  }
+  if (has_res) {
+    mbar_wait(rbar, n_item & 1u);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const uint32_t off = rowoff + (((uint32_t)g ^ sw) << 4);
+      uint4 rh, rl;
+      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rh.x), "=r"(rh.y), "=r"(rh.z), "=r"(rh.w) : "r"(rb + off));
+      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rl.x), "=r"(rl.y), "=r"(rl.z), "=r"(rl.w) : "r"(rb + EPI_PLANE_BYTES + off));
+      const __half2* ah = reinterpret_cast<const __half2*>(&rh);
+      const __half2* bl = reinterpret_cast<const __half2*>(&rl);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 fh = __half22float2(ah[e]), fl = __half22float2(bl[e]);
+        v[g * 8 + e * 2] += fmaf(fl.x, TC_LO_INV, fh.x);
+        v[g * 8 + e * 2 + 1] += fmaf(fl.y, TC_LO_INV, fh.y);
+      }
+    }
+  }
+  if (!valid) {
+#pragma unroll
+    for (int g = 0; g < 32; ++g) v[g] = 0.f;       // pad positions are stored as zeros
+  }
+  EPI_STAMP(2)
+  if (p.out_raw) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint4 hi, lo;
+      split8(v + 8 * g, hi, lo);
+      const uint32_t off = rowoff + (((uint32_t)g ^ sw) << 4);
+      asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(rb + off), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
+      asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(rb + EPI_PLANE_BYTES + off), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w) : "memory");
+    }
+  }
+  if (p.out_act) {
+    if (p.act_kind == 0) {
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const float4 s4 = *reinterpret_cast<const float4*>(s_scale + n0 + c0 + 4 * g);
+        const float4 t4 = *reinterpret_cast<const float4*>(s_shift + n0 + c0 + 4 * g);
+        v[4 * g + 0] = fmaxf(fmaf(v[4 * g + 0], s4.x, t4.x), 0.f);
+        v[4 * g + 1] = fmaxf(fmaf(v[4 * g + 1], s4.y, t4.y), 0.f);
+        v[4 * g + 2] = fmaxf(fmaf(v[4 * g + 2], s4.z, t4.z), 0.f);
+        v[4 * g + 3] = fmaxf(fmaf(v[4 * g + 3], s4.w, t4.w), 0.f);
+      }
+      if (!valid) {
+#pragma unroll
+        for (int g = 0; g < 32; ++g) v[g] = 0.f;   // relu(shift) of a pad position is not zero
+      }
+    } else if (p.act_kind == 2) {
+#pragma unroll
+      for (int g = 0; g < 32; ++g) v[g] = tanhf(v[g]);
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint4 hi, lo;
+      split8(v + 8 * g, hi, lo);
+      const uint32_t off = rowoff + (((uint32_t)g ^ sw) << 4);
+      asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ab + off), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
+      asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ab + EPI_PLANE_BYTES + off), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w) : "memory");
+    }
+  }
+  EPI_STAMP(3)
+  fence_proxy_async();
+  __syncwarp();
+  EPI_STAMP(4)
+  if (lane == 0) {
+    if (p.out_raw) {
+      tma_store_3d(mapRaw, rb, n0 + c0, row0, 0);
+      tma_store_3d(mapRaw, rb + EPI_PLANE_BYTES, n0 + c0, row0, 1);
+    }
+    if (p.out_act) {
+      tma_store_3d(mapAct, ab, n0 + c0, row0, 0);
+      tma_store_3d(mapAct, ab + EPI_PLANE_BYTES, n0 + c0, row0, 1);
+    }
+    bulk_commit();
+  }
+  EPI_STAMP(5)
+#undef EPI_STAMP
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -344,6 +514,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 //  * the 1x1 projection shortcut rides along as extra chunks with one tap.
 constexpr int SL_MAX_RING = 16;
 constexpr int SL_MAX_SLABS = 4;
+constexpr int SL_THREADS = TC_THREADS;             // warps 0..7 epilogue (quadrant = warp & 3, group = warp >> 2), 8 TMA, 9 MMA
+constexpr int SL_WARP_TMA = TC_WARP_TMA, SL_WARP_MMA = TC_WARP_MMA;
+constexpr int SL_EPI_BYTES = 8 * EPI_WARP_BYTES;   // staging of the TMA epilogue (64 KB)
 
 struct SlabParams {
   int slab_rows, lead;          // rows per main slab (multiple of 8), rows in front of q0 (= W + 2)
@@ -360,10 +533,11 @@ struct SlabParams {
 __device__ __forceinline__ uint64_t make_desc_shifted(uint32_t saddr, int row_bytes) { return make_desc(saddr, row_bytes); }
 
 template <int KC, bool RESIDENT>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(SL_THREADS, 1)
 conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapS,
                     const __grid_constant__ CUtensorMap mapWm, const __grid_constant__ CUtensorMap mapWs,
-                    const TcParams p, const SlabParams sp) {
+                    const __grid_constant__ CUtensorMap mapRes, const __grid_constant__ CUtensorMap mapRaw,
+                    const __grid_constant__ CUtensorMap mapAct, const TcParams p, const SlabParams sp) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const long long t_entry = p.dbg ? clock64() : 0;
@@ -372,13 +546,18 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   const int nb = sp.resident ? n_ksteps : sp.nring;                    // weight slots in smem
   uint8_t* slab_base = smem;                                           // [nslab][2 planes][slab_bytes]
   uint8_t* b_base = smem + (size_t)sp.nslab * 2 * sp.slab_bytes;       // [nb][2 planes][bplane_bytes]
-  uint64_t* sfull_bar = reinterpret_cast<uint64_t*>(b_base + (size_t)nb * 2 * sp.bplane_bytes);
+  // TMA-epilogue staging [8 warps][EPI_WARP_BYTES]: its own region, or (epi_tma == 2: one tile per CTA) on top of
+  // the operand region, which is idle once the tile's last MMA has retired
+  uint8_t* epi_own = b_base + (size_t)nb * 2 * sp.bplane_bytes;
+  uint8_t* epi_base = p.epi_tma == 2 ? smem : epi_own;
+  uint64_t* sfull_bar = reinterpret_cast<uint64_t*>(epi_own + (p.epi_tma == 1 ? SL_EPI_BYTES : 0));
   uint64_t* sempty_bar = sfull_bar + SL_MAX_SLABS;
   uint64_t* bfull_bar = sempty_bar + SL_MAX_SLABS;
   uint64_t* bempty_bar = bfull_bar + SL_MAX_RING;
   uint64_t* tfull_bar = bempty_bar + SL_MAX_RING;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* rbar = tempty_bar + 2;                                     // [8 warps] shortcut chunk landed
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(rbar + 8);
   float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_base_slot + 2) + 15) & ~uintptr_t(15));   // float4 reads
   float* s_scale = s_bias + p.Cout;
   float* s_shift = s_scale + p.Cout;
@@ -387,25 +566,42 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   const int BN = p.BN;
   const uint32_t tmem_cols = (4 * BN <= 128) ? 128u : (4 * BN <= 256 ? 256u : 512u);
 
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < SL_MAX_SLABS; ++s) { mbar_init(&sfull_bar[s], 1); mbar_init(&sempty_bar[s], 1); }
-    for (int s = 0; s < SL_MAX_RING; ++s) { mbar_init(&bfull_bar[s], 1); mbar_init(&bempty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+  // Short prologue (it is on the critical path of every layer: the previous kernel's CTA must leave the SM before
+  // this one starts): the 52 mbarriers are initialised one per lane, TMEM is allocated by the MMA warp, and only
+  // the epilogue warps wait for the bias / BN vectors (they are idle until the first accumulator is ready).
+  if (warp == SL_WARP_TMA) {
+    constexpr int NBAR = 2 * SL_MAX_SLABS + 2 * SL_MAX_RING + 2 + 2 + 8;       // contiguous from sfull_bar
+    for (int i = lane; i < NBAR; i += 32) {
+      const bool is_tempty = (i == 2 * SL_MAX_SLABS + 2 * SL_MAX_RING + 2) || (i == 2 * SL_MAX_SLABS + 2 * SL_MAX_RING + 3);
+      mbar_init(&sfull_bar[i], is_tempty ? (p.epi_tma ? 4u * (uint32_t)(p.BN >> 5) : 4u) : 1u);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (lane == 0) {
+      prefetch_tmap(&mapA); prefetch_tmap(&mapWm);
+      if (p.chunks_sc) { prefetch_tmap(&mapS); prefetch_tmap(&mapWs); }
+    }
   }
-  if (warp == TC_WARP_MMA) {
+  if (warp == SL_WARP_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  for (int i = threadIdx.x; i < p.Cout; i += TC_THREADS) {
-    s_bias[i] = p.bias ? p.bias[i] : 0.f;
-    s_scale[i] = p.act_scale ? p.act_scale[i] : 1.f;
-    s_shift[i] = p.act_shift ? p.act_shift[i] : 0.f;
+  if (p.epi_tma && warp == 0 && lane == 0) {
+    if (p.res) prefetch_tmap(&mapRes);
+    if (p.out_raw) prefetch_tmap(&mapRaw);
+    if (p.out_act) prefetch_tmap(&mapAct);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  if (warp < 8) {
+    for (int i = threadIdx.x; i < p.Cout; i += 256) {
+      s_bias[i] = p.bias ? p.bias[i] : 0.f;
+      s_scale[i] = p.act_scale ? p.act_scale[i] : 1.f;
+      s_shift[i] = p.act_shift ? p.act_shift[i] : 0.f;
+    }
+    named_bar_sync(1, 256);
+  }
   if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[61] = clock64();     // prologue done
 
   const int n_chunks = p.chunks_main + p.chunks_sc;       // slabs per tile
@@ -416,7 +612,7 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     return c < p.chunks_main ? (tap * p.chunks_main + c) * p.kc_main : n_main * p.kc_main + (c - p.chunks_main) * p.kc_sc;
   };
 
-  if (warp == TC_WARP_TMA) {
+  if (warp == SL_WARP_TMA) {
     // ===================== TMA producer (whole warp converged, one elected lane issues) =====================
     {
       if (sp.resident) {
@@ -483,7 +679,7 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         }
       }
     }
-  } else if (warp == TC_WARP_MMA) {
+  } else if (warp == SL_WARP_MMA) {
     // ===================== MMA issuer: ONE elected lane runs the whole loop =====================
     // The loop is issue-bound (one thread, dependent uniform-datapath ops at ~8 cycles each), so the
     // instruction count per tcgen05.mma is what sets the speed of the thin layers:
@@ -587,14 +783,29 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     const int quad = warp & 3, group = warp >> 2;
     pdl_wait();                               // identity-shortcut rows and the output planes
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it)
-      if ((it & 1) == group)
-        epilogue_tile(p, tile, it, quad, lane, tmem_base, tfull_bar, tempty_bar, s_bias, s_scale, s_shift);
+    if (p.epi_tma) {
+      const uint32_t stage_u = smem_u32(epi_base + (size_t)warp * EPI_WARP_BYTES);
+      const int nchunks = BN >> 5;
+      uint32_t n_item = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it)
+        for (int c = 0; c < nchunks; ++c)
+          if (((it * nchunks + c) & 1) == group) {
+            epilogue_item_tma(p, &mapRes, &mapRaw, &mapAct, tile, c, it, quad, lane, tmem_base, tfull_bar, tempty_bar,
+                              s_bias, s_scale, s_shift, stage_u, &rbar[warp], n_item, p.epi_tma == 2);
+            ++n_item;
+          }
+      if (lane == 0) bulk_wait0();             // all plane stores complete before the CTA retires
+      __syncwarp();
+    } else {
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it)
+        if ((it & 1) == group)
+          epilogue_tile(p, tile, it, quad, lane, tmem_base, tfull_bar, tempty_bar, s_bias, s_scale, s_shift);
+    }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == TC_WARP_MMA) {
+  if (warp == SL_WARP_MMA) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
   }
@@ -718,7 +929,11 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
   if (sp.slab_bytes < TC_BM * kc_max * 2) sp.slab_bytes = TC_BM * kc_max * 2;
   sp.bplane_bytes = p.BN * kc_max * 2;       // hi and lo tiles adjacent: [B_hi ; B_lo] is one 2*BN-row operand
   if (sp.slab_rows > 192) slab = false;
-  const size_t fixed = 1024 + 512 + 3 * (size_t)d->cout * sizeof(float);     // align slack + barriers + epilogue vectors
+  // TMA epilogue: plane outputs of an unsplit map (every conv1 and all but the three stage-ending conv2's)
+  // 1 = own staging region, 2 = staging aliased onto the operand region (every CTA owns a single tile)
+  p.epi_tma = (slab && !p.split && !d->out_dense && !getenv("SAR_TC_NO_EPI_TMA")) ? 1 : 0;
+  if (p.epi_tma && (long long)p.m_tiles * p.n_tiles <= sms) p.epi_tma = 2;
+  const size_t fixed = 1024 + 1024 + 640 + 3 * (size_t)d->cout * sizeof(float) + (p.epi_tma == 1 ? SL_EPI_BYTES : 0);   // align slack (x2) + barriers + epilogue vectors (+ staging)
   const size_t budget = 227 * 1024 - fixed;
   if (slab) {
     const int n_ksteps = p.ntaps * p.chunks_main + p.chunks_sc;
@@ -738,8 +953,9 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
     if (sp.nslab > SL_MAX_SLABS) sp.nslab = SL_MAX_SLABS;
   }
 
-  CUtensorMap mapA, mapS, mapWm, mapWs;
+  CUtensorMap mapA, mapS, mapWm, mapWs, mapRes, mapRaw, mapAct;
   int rc;
+  if (!slab) p.epi_tma = 0;
   if ((rc = make_map(&mapA, d->a, d->a_rows, d->a_ch, d->a_planes, p.kc_main, slab ? sp.slab_rows : TC_BM))) return rc;
   if ((rc = make_map(&mapWm, d->w, d->cout, ktot, 2, p.kc_main, p.BN))) return rc;
   if (d->s) {
@@ -754,11 +970,18 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
   const int grid = tiles < sms ? tiles : sms;
   if (slab) {
     const int nb = sp.resident ? (p.ntaps * p.chunks_main + p.chunks_sc) : sp.nring;
-    const size_t smem = fixed + (size_t)sp.nslab * 2 * sp.slab_bytes + (size_t)nb * 2 * sp.bplane_bytes;
+    size_t smem = fixed + (size_t)sp.nslab * 2 * sp.slab_bytes + (size_t)nb * 2 * sp.bplane_bytes;
+    if (p.epi_tma == 2 && smem - fixed < (size_t)SL_EPI_BYTES) smem = fixed + SL_EPI_BYTES;    // aliased staging needs 64 KB of operand region
+    mapRes = mapA; mapRaw = mapA; mapAct = mapA;
+    if (p.epi_tma) {        // 32-channel x 32-row boxes of the [2][R][Cout] plane tensors, 64B swizzle
+      if (d->res && (rc = make_map(&mapRes, d->res, p.R, d->cout, 2, 32, 32))) return rc;
+      if (d->out_raw && (rc = make_map(&mapRaw, d->out_raw, p.R, d->cout, 2, 32, 32))) return rc;
+      if (d->out_act && (rc = make_map(&mapAct, d->out_act, p.R, d->cout, 2, 32, 32))) return rc;
+    }
     auto launch = [&](auto kern) -> int {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) { set_error("sar_conv_tc_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-      launch_k(kern, dim3(grid), dim3(TC_THREADS), smem, (cudaStream_t)stream, mapA, mapS, mapWm, mapWs, p, sp);
+      launch_k(kern, dim3(grid), dim3(SL_THREADS), smem, (cudaStream_t)stream, mapA, mapS, mapWm, mapWs, mapRes, mapRaw, mapAct, p, sp);
       return 0;
     };
     int lrc;

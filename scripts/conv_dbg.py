@@ -17,10 +17,11 @@ def timed(*a, **k):
 rn.forward(xd); torch.cuda.synchronize()
 tc.conv_tc = timed
 rn.forward(xd); torch.cuda.synchronize()
-for li in (2, 3, 8, 9, 16, 17, 28, 31, 34, 35):
+for li in (2, 3, 9, 17, 31):
     d = dbgs[li].cpu().tolist()
     t0 = d[62]
     print("layer", li, "entry 0  prologue done %d  exit %d" % (d[61] - t0, d[63] - t0))
     for it in range(4):
-        m = [d[it*4+j] - t0 for j in range(4)]; e = [d[32+it*2+j] - t0 for j in range(2)]
-        print("  tile %d: mma start %6d  tempty ok %6d  slab ok %6d  issued %6d | epi: tfull %6d done %6d (epi %5d)" % (it, m[0], m[1], m[2], m[3], e[0], e[1], e[1]-e[0]))
+        m = [d[it*4+j] - t0 for j in range(4)]; e = [d[32+it*6+j] - t0 for j in range(6)]
+        if m[0] < 0: continue
+        print("  tile %d: mma start %6d  tempty ok %6d  slab ok %6d  issued %6d | epi chunk0: tfull %6d  +tmem %5d  +res/math %5d  +split/STS %5d  +fence %5d  +TMA issue %5d" % (it, m[0], m[1], m[2], m[3], e[0], e[1]-e[0], e[2]-e[1], e[3]-e[2], e[4]-e[3], e[5]-e[4]))
