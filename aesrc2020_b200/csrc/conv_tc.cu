@@ -65,152 +65,28 @@ struct TcParams {
   long long* dbg;                        // optional: clock64 timestamps of CTA 0 (profiling aid)
   int mma_mask;                          // experiment: which of the 3 hi/lo products to issue (7 = all)
   int act_kind;                          // activated outputs: 0 relu(scale*v+shift), 1 identity, 2 tanh(v)
-  int epi_tma;                           // slab kernel: plane outputs (and the identity shortcut) move by TMA
+  int epi_alias;                         // every CTA owns ONE tile: the epilogue staging lives on top of the (then idle) operand region
+  int stages;                            // generic kernel: depth of the TMA ring (2 or 3)
 };
 
 // ------------------------------------------------------------------ epilogue (shared by both kernels)
-// 8 values -> hi = fp16(x) and lo = fp16((x - hi) * 2^11), packed conversions (cvt.rn.f16x2.f32)
-__device__ __forceinline__ void split_store8(const float* v, __half* hi_dst, __half* lo_dst) {
-  uint32_t hh[4], ll[4];
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const __half2 h2 = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
-    const float2 hf = __half22float2(h2);
-    const __half2 l2 = __floats2half2_rn((v[2 * e] - hf.x) * TC_LO_SCALE, (v[2 * e + 1] - hf.y) * TC_LO_SCALE);
-    hh[e] = *reinterpret_cast<const uint32_t*>(&h2);
-    ll[e] = *reinterpret_cast<const uint32_t*>(&l2);
-  }
-  *reinterpret_cast<uint4*>(hi_dst) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-  *reinterpret_cast<uint4*>(lo_dst) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
-}
-
-// One tile: TMEM (acc0 + 2^-11 acc1) -> +bias (+identity shortcut) -> raw hi/lo planes and/or
-// relu(scale*v+shift) hi/lo planes (phase-split when the consumer is strided) or dense fp32.
-// The identity-shortcut rows of the next 32-column chunk are prefetched (L2 latency) while the current
-// chunk is converted and stored; the first chunk's rows are requested before waiting for the MMAs.
-__device__ __forceinline__ void epilogue_tile(const TcParams& p, int tile, int it, int quad, int lane, uint32_t tmem_base,
-                                              uint64_t* tfull_bar, uint64_t* tempty_bar, const float* s_bias,
-                                              const float* s_scale, const float* s_shift) {
-  const int BN = p.BN;
-  const int as = it & 1;
-  const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-  const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
-  const int n0 = nt * BN;
-  const long long q = (long long)mt * TC_BM + quad * 32 + lane;
-  // decode flat row -> (n, h, w)
-  bool valid = q < p.R;
-  int n = 0, h = 0, w = 0;
-  if (valid) {
-    n = (int)(q / p.Rimg);
-    const int rem = (int)(q - (long long)n * p.Rimg);
-    h = rem / p.P; w = rem - h * p.P;
-    valid = (h < p.H) && (w < p.W);
-  }
-  long long qo = q; long long Ro = p.R; int plane0 = 0;
-  if (p.split) {
-    qo = (long long)n * p.Rimg2 + (h >> 1) * p.P2 + (w >> 1);
-    Ro = p.R2;
-    plane0 = 2 * ((h & 1) * 2 + (w & 1));
-  }
-  const bool has_res = p.res != nullptr && valid;
-  uint4 rh[4], rl[4];
-  if (has_res) {
-    const uint4* ph = reinterpret_cast<const uint4*>(p.res + (size_t)q * p.Cout + n0);
-    const uint4* pl = reinterpret_cast<const uint4*>(p.res + ((size_t)p.R + q) * p.Cout + n0);
-#pragma unroll
-    for (int g = 0; g < 4; ++g) { rh[g] = __ldg(ph + g); rl[g] = __ldg(pl + g); }
-  }
-  mbar_wait(&tfull_bar[as], aphase);
-  tc_fence_after();
-  if (p.dbg && blockIdx.x == 0 && quad == 0 && lane == 0 && it < 8) p.dbg[32 + it * 2] = clock64();
-  const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 2 * BN);
-  for (int c0 = 0; c0 < BN; c0 += 32) {
-    uint32_t r0[32], r1[32];
-    tmem_ld32(tbase + (uint32_t)c0, r0);
-    tmem_ld32(tbase + (uint32_t)(BN + c0), r1);
-    tmem_ld_wait();
-    if (valid) {
-      float v[32];
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        const float4 b4 = *reinterpret_cast<const float4*>(s_bias + n0 + c0 + 4 * g);
-        v[4 * g + 0] = fmaf(__uint_as_float(r1[4 * g + 0]), TC_LO_INV, __uint_as_float(r0[4 * g + 0])) + b4.x;
-        v[4 * g + 1] = fmaf(__uint_as_float(r1[4 * g + 1]), TC_LO_INV, __uint_as_float(r0[4 * g + 1])) + b4.y;
-        v[4 * g + 2] = fmaf(__uint_as_float(r1[4 * g + 2]), TC_LO_INV, __uint_as_float(r0[4 * g + 2])) + b4.z;
-        v[4 * g + 3] = fmaf(__uint_as_float(r1[4 * g + 3]), TC_LO_INV, __uint_as_float(r0[4 * g + 3])) + b4.w;
-      }
-      if (has_res) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const __half2* ah = reinterpret_cast<const __half2*>(&rh[g]);
-          const __half2* bl = reinterpret_cast<const __half2*>(&rl[g]);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 fh = __half22float2(ah[e]), fl = __half22float2(bl[e]);
-            v[g * 8 + e * 2] += fmaf(fl.x, TC_LO_INV, fh.x);
-            v[g * 8 + e * 2 + 1] += fmaf(fl.y, TC_LO_INV, fh.y);
-          }
-        }
-        if (c0 + 32 < BN) {                      // prefetch the next chunk's shortcut rows
-          const uint4* ph = reinterpret_cast<const uint4*>(p.res + (size_t)q * p.Cout + n0 + c0 + 32);
-          const uint4* pl = reinterpret_cast<const uint4*>(p.res + ((size_t)p.R + q) * p.Cout + n0 + c0 + 32);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) { rh[g] = __ldg(ph + g); rl[g] = __ldg(pl + g); }
-        }
-      }
-      if (p.out_raw) {
-        __half* oh = p.out_raw + ((size_t)plane0 * Ro + qo) * p.Cout + n0 + c0;
-        __half* ol = p.out_raw + ((size_t)(plane0 + 1) * Ro + qo) * p.Cout + n0 + c0;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) split_store8(v + 8 * g, oh + 8 * g, ol + 8 * g);
-      }
-      if ((p.out_act || p.out_dense) && p.act_kind == 0) {
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const float4 s4 = *reinterpret_cast<const float4*>(s_scale + n0 + c0 + 4 * g);
-          const float4 t4 = *reinterpret_cast<const float4*>(s_shift + n0 + c0 + 4 * g);
-          v[4 * g + 0] = fmaxf(fmaf(v[4 * g + 0], s4.x, t4.x), 0.f);
-          v[4 * g + 1] = fmaxf(fmaf(v[4 * g + 1], s4.y, t4.y), 0.f);
-          v[4 * g + 2] = fmaxf(fmaf(v[4 * g + 2], s4.z, t4.z), 0.f);
-          v[4 * g + 3] = fmaxf(fmaf(v[4 * g + 3], s4.w, t4.w), 0.f);
-        }
-      } else if ((p.out_act || p.out_dense) && p.act_kind == 2) {      // Dense(..., activation='tanh'), model.py:35-42
-#pragma unroll
-        for (int g = 0; g < 32; ++g) v[g] = tanhf(v[g]);
-      }
-      if (p.out_act) {
-        __half* oh = p.out_act + ((size_t)plane0 * Ro + qo) * p.Cout + n0 + c0;
-        __half* ol = p.out_act + ((size_t)(plane0 + 1) * Ro + qo) * p.Cout + n0 + c0;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) split_store8(v + 8 * g, oh + 8 * g, ol + 8 * g);
-      }
-      if (p.out_dense) {
-        float4* od = reinterpret_cast<float4*>(p.out_dense + (((size_t)n * p.H + h) * p.W + w) * p.Cout + n0 + c0);
-#pragma unroll
-        for (int g = 0; g < 8; ++g) od[g] = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-      }
-    }
-  }
-  tc_fence_before();
-  __syncwarp();
-  if (p.dbg && blockIdx.x == 0 && quad == 0 && lane == 0 && it < 8) p.dbg[32 + it * 2 + 1] = clock64();
-  if (lane == 0) mbar_arrive(&tempty_bar[as]);
-}
-
-// ------------------------------------------------------------------ TMA epilogue (slab kernel, plane outputs)
-// The row-per-thread global stores above touch 32 different cache lines per instruction (a row chunk is 64 B of a
-// Cout*2-byte pitch): measured 2-4k cycles per 32-column chunk, the critical path of every conv2.  Here a warp
-// stages its 32 rows x 32 channels per plane in shared memory in the 64B-swizzled layout of a TMA box (conflict
-// free: lane = row, 16 B piece j lands in slot j ^ ((row >> 1) & 3)) and one lane issues cp.async.bulk.tensor
-// stores; the identity-shortcut chunk arrives the same way (TMA load into the buffer the raw sum is then staged
-// in).  Pad rows are stored as zeros (they must stay zero), rows beyond the tensor are clipped by the tensor map.
+// Work item = (tile, 32-column chunk) handled by ONE warp.  The eight epilogue warps are two groups of four (one
+// warp per TMEM lane quadrant); group g takes the items with (it * nchunks + chunk) % 2 == g, so the chunks of a
+// single-tile CTA (late stages) drain in parallel and thin tiles (BN = 32) alternate between the groups.
 //
-// Work item = (tile, 32-column chunk).  The eight epilogue warps are two groups of four (one warp per TMEM lane
-// quadrant); group g takes the items with (it * nchunks + chunk) % 2 == g, so the chunks of a single-tile CTA
-// (late stages) drain in parallel and thin tiles (BN = 32) alternate between the groups.
+// A row-per-thread global store touches 32 different cache lines per instruction (a row chunk is 64 B of a
+// Cout*2-byte pitch; measured 2-4k cycles per chunk), so the warp transposes through shared memory: lane = row on
+// the TMEM side (tcgen05.ld hands a lane one accumulator row), lane = (row, 16-byte piece) on the global side, so
+// every LDG/STG instruction covers whole 64-byte (planes) or 128-byte (fp32) row chunks.  Staging tiles are
+// XOR-swizzled by row, which makes both access patterns bank-conflict free.  The identity-shortcut chunk is
+// requested BEFORE waiting for the accumulator (it does not depend on the MMAs) and sits in registers until then.
+// Non-split plane outputs store zeros at pad positions (pads must stay zero); split planes and the dense output
+// skip them.  The code is kept compact on purpose (rolled loops over 8-column groups): a CTA of the late stages
+// runs it once or twice per warp, and the unrolled version was instruction-fetch bound (ncu: stall_no_inst).
 constexpr int EPI_PLANE_BYTES = 32 * 64;           // 32 rows x 32 fp16 channels
-constexpr int EPI_BUF_BYTES = 2 * EPI_PLANE_BYTES; // hi | lo
-constexpr int EPI_WARP_BYTES = 2 * EPI_BUF_BYTES;  // R (shortcut in, raw out in place), A (activated out)
+constexpr int EPI_BUF_BYTES = 2 * EPI_PLANE_BYTES; // hi | lo planes, or 32 rows x 32 fp32
+constexpr int EPI_WARP_BYTES = 2 * EPI_BUF_BYTES;  // R (shortcut in, raw out in place), A (activated planes or dense fp32)
+constexpr int EPI_BYTES = 8 * EPI_WARP_BYTES;      // 64 KB
 
 __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
   uint32_t hh[4], ll[4];
@@ -225,145 +101,191 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
   hi = make_uint4(hh[0], hh[1], hh[2], hh[3]);
   lo = make_uint4(ll[0], ll[1], ll[2], ll[3]);
 }
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
+  return r;
+}
+__device__ __forceinline__ void sts128(uint32_t a, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __noinline__ float tanh_precise(float x) { return tanhf(x); }
 
-// `alias`: the CTA owns a single tile, the staging buffers live in the (by then idle) operand region, so the
-// shortcut chunk can only be requested once the tile's MMAs have retired.
-__device__ __forceinline__ void epilogue_item_tma(const TcParams& p, const CUtensorMap* mapRes, const CUtensorMap* mapRaw,
-                                                  const CUtensorMap* mapAct, int tile, int c, int it, int quad, int lane,
-                                                  uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar,
-                                                  const float* s_bias, const float* s_scale, const float* s_shift,
-                                                  uint32_t stage_u, uint64_t* rbar, uint32_t n_item, bool alias) {
+__device__ __forceinline__ void epilogue_item(const TcParams& p, int tile, int c, int it, int quad, int lane,
+                                           uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar,
+                                           uint32_t s_bias_u, uint32_t stage_u) {
   const int BN = p.BN;
   const int as = it & 1;
   const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
   const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
   const int n0 = nt * BN, c0 = c * 32;
-  const int row0 = mt * TC_BM + quad * 32;
+  const long long row0 = (long long)mt * TC_BM + quad * 32;
   const bool has_res = p.res != nullptr;
   const uint32_t rb = stage_u, ab = stage_u + EPI_BUF_BYTES;
-  auto request_res = [&]() {
-    if (lane == 0) {
-      bulk_wait_read0();                             // this warp's previous stores have finished reading R and A
-      if (has_res) {
-        mbar_expect_tx(rbar, (uint32_t)EPI_BUF_BYTES);
-        tma_load_3d(mapRes, rb, rbar, n0 + c0, row0, 0);
-        tma_load_3d(mapRes, rb + EPI_PLANE_BYTES, rbar, n0 + c0, row0, 1);
+  // global side of the plane tiles: lane -> (row 8i + lane/4, 16-byte piece lane%4); slot = piece ^ ((row >> 1) & 3)
+  const int g_row = lane >> 2, g_piece = lane & 3;
+  const size_t g_col = (size_t)(n0 + c0 + 8 * g_piece);
+  uint4 res_h[4], res_l[4];
+  if (has_res) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long q = row0 + 8 * i + g_row;
+      res_h[i] = make_uint4(0, 0, 0, 0); res_l[i] = make_uint4(0, 0, 0, 0);
+      if (q < p.R) {
+        res_h[i] = __ldg(reinterpret_cast<const uint4*>(p.res + (size_t)q * p.Cout + g_col));
+        res_l[i] = __ldg(reinterpret_cast<const uint4*>(p.res + ((size_t)p.R + q) * p.Cout + g_col));
       }
     }
-    __syncwarp();
-  };
-  if (!alias) request_res();
-  const long long q = (long long)row0 + lane;
+  }
+  // TMEM side: lane -> row.  drow_p / drow_d: destination row of the plane / dense outputs (-1: not stored)
+  const long long q = row0 + lane;
   bool valid = q < p.R;
+  int drow_p = -1, drow_d = -1;
   if (valid) {
     const int n = (int)(q / p.Rimg);
     const int rem = (int)(q - (long long)n * p.Rimg);
     const int h = rem / p.P, w = rem - h * p.P;
+    drow_p = (int)q;
     valid = (h < p.H) && (w < p.W);
+    if (p.split) drow_p = valid ? (int)((long long)(2 * ((h & 1) * 2 + (w & 1))) * p.R2 + (long long)n * p.Rimg2 + (h >> 1) * p.P2 + (w >> 1)) : -1;
+    if (valid) drow_d = (n * p.H + h) * p.W + w;
   }
-  const uint32_t sw = (uint32_t)((lane >> 1) & 3);                 // swizzle term of this lane's row
+  const size_t lo_off = (size_t)(p.split ? p.R2 : p.R) * p.Cout;       // hi plane -> lo plane, in elements
+  const uint32_t sw = (uint32_t)((lane >> 1) & 3);
   const uint32_t rowoff = (uint32_t)lane * 64u;
   mbar_wait(&tfull_bar[as], aphase);
   tc_fence_after();
-  if (alias) request_res();
 #define EPI_STAMP(j) if (p.dbg && blockIdx.x == 0 && quad == 0 && lane == 0 && it < 4 && c == 0) p.dbg[32 + it * 6 + (j)] = clock64();
   EPI_STAMP(0)
-  const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 2 * BN);
-  uint32_t r0[32], r1[32];
-  tmem_ld32(tbase + (uint32_t)c0, r0);
-  tmem_ld32(tbase + (uint32_t)(BN + c0), r1);
-  tmem_ld_wait();
-  EPI_STAMP(1)
-  tc_fence_before();                                 // the chunk is in registers: hand the accumulator back
-  __syncwarp();
-  if (lane == 0) mbar_arrive(&tempty_bar[as]);
-  float v[32];
+  if (has_res) {                                     // shortcut pieces -> staging
 #pragma unroll
-  for (int g = 0; g < 8; ++g) {
-    const float4 b4 = *reinterpret_cast<const float4*>(s_bias + n0 + c0 + 4 * g);
-    v[4 * g + 0] = fmaf(__uint_as_float(r1[4 * g + 0]), TC_LO_INV, __uint_as_float(r0[4 * g + 0])) + b4.x;
-    v[4 * g + 1] = fmaf(__uint_as_float(r1[4 * g + 1]), TC_LO_INV, __uint_as_float(r0[4 * g + 1])) + b4.y;
-    v[4 * g + 2] = fmaf(__uint_as_float(r1[4 * g + 2]), TC_LO_INV, __uint_as_float(r0[4 * g + 2])) + b4.z;
-    v[4 * g + 3] = fmaf(__uint_as_float(r1[4 * g + 3]), TC_LO_INV, __uint_as_float(r0[4 * g + 3])) + b4.w;
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t off = (uint32_t)(8 * i + g_row) * 64u + (((uint32_t)g_piece ^ (uint32_t)(((8 * i + g_row) >> 1) & 3)) << 4);
+      sts128(rb + off, res_h[i]);
+      sts128(rb + EPI_PLANE_BYTES + off, res_l[i]);
+    }
+    __syncwarp();
   }
-  if (has_res) {
-    mbar_wait(rbar, n_item & 1u);
+  const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 2 * BN + c0);
+#pragma unroll 2
+  for (int g = 0; g < 4; ++g) {                      // 8 columns per round
+    uint32_t r0[8], r1[8];
+    tmem_ld8(tbase + (uint32_t)(8 * g), r0);
+    tmem_ld8(tbase + (uint32_t)(BN + 8 * g), r1);
+    tmem_ld_wait();
+    if (g == 3) {                                    // the chunk has left TMEM: hand the accumulator back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+    const uint32_t vec = s_bias_u + (uint32_t)(n0 + c0 + 8 * g) * 4u;   // bias | scale | shift, Cout floats apart
+    float v[8];
+    {
+      const uint4 b0 = lds128(vec), b1 = lds128(vec + 16);
+      const float bb[8] = {__uint_as_float(b0.x), __uint_as_float(b0.y), __uint_as_float(b0.z), __uint_as_float(b0.w),
+                           __uint_as_float(b1.x), __uint_as_float(b1.y), __uint_as_float(b1.z), __uint_as_float(b1.w)};
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const uint32_t off = rowoff + (((uint32_t)g ^ sw) << 4);
-      uint4 rh, rl;
-      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rh.x), "=r"(rh.y), "=r"(rh.z), "=r"(rh.w) : "r"(rb + off));
-      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rl.x), "=r"(rl.y), "=r"(rl.z), "=r"(rl.w) : "r"(rb + EPI_PLANE_BYTES + off));
+      for (int e = 0; e < 8; ++e) v[e] = fmaf(__uint_as_float(r1[e]), TC_LO_INV, __uint_as_float(r0[e])) + bb[e];
+    }
+    const uint32_t off = rowoff + (((uint32_t)g ^ sw) << 4);
+    if (has_res) {
+      const uint4 rh = lds128(rb + off), rl = lds128(rb + EPI_PLANE_BYTES + off);
       const __half2* ah = reinterpret_cast<const __half2*>(&rh);
       const __half2* bl = reinterpret_cast<const __half2*>(&rl);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float2 fh = __half22float2(ah[e]), fl = __half22float2(bl[e]);
-        v[g * 8 + e * 2] += fmaf(fl.x, TC_LO_INV, fh.x);
-        v[g * 8 + e * 2 + 1] += fmaf(fl.y, TC_LO_INV, fh.y);
+        v[e * 2] += fmaf(fl.x, TC_LO_INV, fh.x);
+        v[e * 2 + 1] += fmaf(fl.y, TC_LO_INV, fh.y);
       }
     }
-  }
-  if (!valid) {
+    if (!valid) {
 #pragma unroll
-    for (int g = 0; g < 32; ++g) v[g] = 0.f;       // pad positions are stored as zeros
-  }
-  EPI_STAMP(2)
-  if (p.out_raw) {
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
+      for (int e = 0; e < 8; ++e) v[e] = 0.f;        // pad positions of non-split planes are stored as zeros
+    }
+    if (p.out_raw) {                                 // in place: a lane only reads and writes its own row here
       uint4 hi, lo;
-      split8(v + 8 * g, hi, lo);
-      const uint32_t off = rowoff + (((uint32_t)g ^ sw) << 4);
-      asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(rb + off), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
-      asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(rb + EPI_PLANE_BYTES + off), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w) : "memory");
+      split8(v, hi, lo);
+      sts128(rb + off, hi);
+      sts128(rb + EPI_PLANE_BYTES + off, lo);
     }
-  }
-  if (p.out_act) {
-    if (p.act_kind == 0) {
+    if (p.out_act || p.out_dense) {
+      if (p.act_kind == 0) {
+        const uint4 s0 = lds128(vec + (uint32_t)p.Cout * 4u), s1 = lds128(vec + (uint32_t)p.Cout * 4u + 16);
+        const uint4 t0 = lds128(vec + (uint32_t)p.Cout * 8u), t1 = lds128(vec + (uint32_t)p.Cout * 8u + 16);
+        const float ss[8] = {__uint_as_float(s0.x), __uint_as_float(s0.y), __uint_as_float(s0.z), __uint_as_float(s0.w),
+                             __uint_as_float(s1.x), __uint_as_float(s1.y), __uint_as_float(s1.z), __uint_as_float(s1.w)};
+        const float tt[8] = {__uint_as_float(t0.x), __uint_as_float(t0.y), __uint_as_float(t0.z), __uint_as_float(t0.w),
+                             __uint_as_float(t1.x), __uint_as_float(t1.y), __uint_as_float(t1.z), __uint_as_float(t1.w)};
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        const float4 s4 = *reinterpret_cast<const float4*>(s_scale + n0 + c0 + 4 * g);
-        const float4 t4 = *reinterpret_cast<const float4*>(s_shift + n0 + c0 + 4 * g);
-        v[4 * g + 0] = fmaxf(fmaf(v[4 * g + 0], s4.x, t4.x), 0.f);
-        v[4 * g + 1] = fmaxf(fmaf(v[4 * g + 1], s4.y, t4.y), 0.f);
-        v[4 * g + 2] = fmaxf(fmaf(v[4 * g + 2], s4.z, t4.z), 0.f);
-        v[4 * g + 3] = fmaxf(fmaf(v[4 * g + 3], s4.w, t4.w), 0.f);
+        for (int e = 0; e < 8; ++e) v[e] = valid ? fmaxf(fmaf(v[e], ss[e], tt[e]), 0.f) : 0.f;   // relu(shift) of a pad is not zero
+      } else if (p.act_kind == 2) {                  // Dense(..., activation='tanh'), model.py:35-42
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = tanh_precise(v[e]);
       }
-      if (!valid) {
-#pragma unroll
-        for (int g = 0; g < 32; ++g) v[g] = 0.f;   // relu(shift) of a pad position is not zero
+      if (p.out_act) {
+        uint4 hi, lo;
+        split8(v, hi, lo);
+        sts128(ab + off, hi);
+        sts128(ab + EPI_PLANE_BYTES + off, lo);
+      } else {                                       // fp32 tile: 32 rows x 128 B, 16-byte piece j in slot j ^ (row & 7)
+        const uint32_t drow = ab + (uint32_t)lane * 128u;
+        const uint32_t x7 = (uint32_t)(lane & 7);
+        sts128(drow + ((((uint32_t)(2 * g)) ^ x7) << 4), make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])));
+        sts128(drow + ((((uint32_t)(2 * g + 1)) ^ x7) << 4), make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7])));
       }
-    } else if (p.act_kind == 2) {
-#pragma unroll
-      for (int g = 0; g < 32; ++g) v[g] = tanhf(v[g]);
-    }
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      uint4 hi, lo;
-      split8(v + 8 * g, hi, lo);
-      const uint32_t off = rowoff + (((uint32_t)g ^ sw) << 4);
-      asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ab + off), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
-      asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ab + EPI_PLANE_BYTES + off), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w) : "memory");
     }
   }
   EPI_STAMP(3)
-  fence_proxy_async();
   __syncwarp();
-  EPI_STAMP(4)
-  if (lane == 0) {
-    if (p.out_raw) {
-      tma_store_3d(mapRaw, rb, n0 + c0, row0, 0);
-      tma_store_3d(mapRaw, rb + EPI_PLANE_BYTES, n0 + c0, row0, 1);
+  // write-out of the plane tiles: every store instruction covers 8 rows x 64 B
+  if (p.out_raw || p.out_act) {
+#pragma unroll 1
+    for (int i = 0; i < 4; ++i) {
+      const int rl_ = 8 * i + g_row;
+      const int dr = __shfl_sync(0xffffffffu, drow_p, rl_);
+      const uint32_t off = (uint32_t)rl_ * 64u + (((uint32_t)g_piece ^ (uint32_t)((rl_ >> 1) & 3)) << 4);
+      if (dr >= 0) {
+        const size_t e0 = (size_t)dr * p.Cout + g_col;
+        if (p.out_raw) {
+          *reinterpret_cast<uint4*>(p.out_raw + e0) = lds128(rb + off);
+          *reinterpret_cast<uint4*>(p.out_raw + e0 + lo_off) = lds128(rb + EPI_PLANE_BYTES + off);
+        }
+        if (p.out_act) {
+          *reinterpret_cast<uint4*>(p.out_act + e0) = lds128(ab + off);
+          *reinterpret_cast<uint4*>(p.out_act + e0 + lo_off) = lds128(ab + EPI_PLANE_BYTES + off);
+        }
+      }
     }
-    if (p.out_act) {
-      tma_store_3d(mapAct, ab, n0 + c0, row0, 0);
-      tma_store_3d(mapAct, ab + EPI_PLANE_BYTES, n0 + c0, row0, 1);
-    }
-    bulk_commit();
   }
+  if (p.out_dense) {                                 // 4 rows x 128 B per store instruction
+    const int d_row = lane >> 3, d_piece = lane & 7;
+#pragma unroll 1
+    for (int i = 0; i < 8; ++i) {
+      const int rl_ = 4 * i + d_row;
+      const int dr = __shfl_sync(0xffffffffu, drow_d, rl_);
+      if (dr >= 0)
+        *reinterpret_cast<uint4*>(p.out_dense + (size_t)dr * p.Cout + n0 + c0 + 4 * d_piece) =
+            lds128(ab + (uint32_t)rl_ * 128u + ((((uint32_t)d_piece) ^ (uint32_t)(rl_ & 7)) << 4));
+    }
+  }
+  __syncwarp();                                      // staging is reused by this warp's next item
   EPI_STAMP(5)
 #undef EPI_STAMP
+}
+
+// all items of this CTA for one epilogue warp
+__device__ __forceinline__ void epilogue_warp(const TcParams& p, int total_tiles, int warp, int lane, uint32_t tmem_base,
+                                              uint64_t* tfull_bar, uint64_t* tempty_bar, const float* s_bias, uint8_t* epi_base) {
+  const int quad = warp & 3, group = warp >> 2;
+  const uint32_t stage_u = smem_u32(epi_base + (size_t)warp * EPI_WARP_BYTES);
+  const uint32_t s_bias_u = smem_u32(s_bias);
+  const int nchunks = p.BN >> 5;
+  int it = 0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it)
+    for (int c = 0; c < nchunks; ++c)
+      if (((it * nchunks + c) & 1) == group)
+        epilogue_item(p, tile, c, it, quad, lane, tmem_base, tfull_bar, tempty_bar, s_bias_u, stage_u);
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -373,12 +295,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
+  // [stages x 64 KB ring][epilogue staging 64 KB unless aliased onto the ring][barriers][bias | scale | shift]
+  uint8_t* epi_own = smem + (size_t)p.stages * TC_STAGE_BYTES;
+  uint8_t* epi_base = p.epi_alias ? smem : epi_own;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_own + (p.epi_alias ? 0 : EPI_BYTES));
   uint64_t* empty_bar = full_bar + TC_STAGES;
   uint64_t* tfull_bar = empty_bar + TC_STAGES;      // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;             // [2] accumulator drained
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_base_slot + 2) + 15) & ~uintptr_t(15));   // float4 reads   // [Cout]
+  float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_base_slot + 2) + 15) & ~uintptr_t(15));   // [Cout] x 3
   float* s_scale = s_bias + p.Cout;
   float* s_shift = s_scale + p.Cout;
 
@@ -386,24 +311,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const int BN = p.BN;
   const uint32_t tmem_cols = (4 * BN <= 128) ? 128u : (4 * BN <= 256 ? 256u : 512u);   // 2 stages x (acc0, acc1)
 
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+  // short prologue: see conv_tc_slab_kernel
+  if (warp == TC_WARP_TMA) {
+    if (lane < 2 * TC_STAGES + 4) {
+      const bool is_tempty = lane >= 2 * TC_STAGES + 2;
+      mbar_init(&full_bar[lane], is_tempty ? 4u * (uint32_t)(BN >> 5) : 1u);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (lane == 0) {
+      prefetch_tmap(&mapA); prefetch_tmap(&mapWm);
+      if (p.chunks_sc) { prefetch_tmap(&mapS); prefetch_tmap(&mapWs); }
+    }
   }
   if (warp == TC_WARP_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  for (int i = threadIdx.x; i < p.Cout; i += TC_THREADS) {
-    s_bias[i] = p.bias ? p.bias[i] : 0.f;
-    s_scale[i] = p.act_scale ? p.act_scale[i] : 1.f;
-    s_shift[i] = p.act_shift ? p.act_shift[i] : 0.f;
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  if (warp < 8) {
+    for (int i = threadIdx.x; i < p.Cout; i += 256) {
+      s_bias[i] = p.bias ? p.bias[i] : 0.f;
+      s_scale[i] = p.act_scale ? p.act_scale[i] : 1.f;
+      s_shift[i] = p.act_shift ? p.act_shift[i] : 0.f;
+    }
+    named_bar_sync(1, 256);
+  }
 
   const int n_main = p.ntaps * p.chunks_main;
   const int n_ksteps = n_main + p.chunks_sc;
@@ -445,7 +380,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           }
         }
         __syncwarp();
-        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == TC_WARP_MMA) {
@@ -482,16 +417,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           if (ks == n_ksteps - 1) umma_commit(&tfull_bar[as]);
         }
         __syncwarp();
-        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else {
     // ===================== epilogue warps (TMEM lane quadrant = warp % 4) =====================
-    const int quad = warp & 3, group = warp >> 2;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it)
-      if ((it & 1) == group)
-        epilogue_tile(p, tile, it, quad, lane, tmem_base, tfull_bar, tempty_bar, s_bias, s_scale, s_shift);
+    epilogue_warp(p, total_tiles, warp, lane, tmem_base, tfull_bar, tempty_bar, s_bias, epi_base);
   }
 
   tc_fence_before();
@@ -516,7 +447,6 @@ constexpr int SL_MAX_RING = 16;
 constexpr int SL_MAX_SLABS = 4;
 constexpr int SL_THREADS = TC_THREADS;             // warps 0..7 epilogue (quadrant = warp & 3, group = warp >> 2), 8 TMA, 9 MMA
 constexpr int SL_WARP_TMA = TC_WARP_TMA, SL_WARP_MMA = TC_WARP_MMA;
-constexpr int SL_EPI_BYTES = 8 * EPI_WARP_BYTES;   // staging of the TMA epilogue (64 KB)
 
 struct SlabParams {
   int slab_rows, lead;          // rows per main slab (multiple of 8), rows in front of q0 (= W + 2)
@@ -536,8 +466,7 @@ template <int KC, bool RESIDENT>
 __global__ void __launch_bounds__(SL_THREADS, 1)
 conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapS,
                     const __grid_constant__ CUtensorMap mapWm, const __grid_constant__ CUtensorMap mapWs,
-                    const __grid_constant__ CUtensorMap mapRes, const __grid_constant__ CUtensorMap mapRaw,
-                    const __grid_constant__ CUtensorMap mapAct, const TcParams p, const SlabParams sp) {
+                    const TcParams p, const SlabParams sp) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const long long t_entry = p.dbg ? clock64() : 0;
@@ -546,11 +475,11 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   const int nb = sp.resident ? n_ksteps : sp.nring;                    // weight slots in smem
   uint8_t* slab_base = smem;                                           // [nslab][2 planes][slab_bytes]
   uint8_t* b_base = smem + (size_t)sp.nslab * 2 * sp.slab_bytes;       // [nb][2 planes][bplane_bytes]
-  // TMA-epilogue staging [8 warps][EPI_WARP_BYTES]: its own region, or (epi_tma == 2: one tile per CTA) on top of
-  // the operand region, which is idle once the tile's last MMA has retired
+  // epilogue staging [8 warps][EPI_WARP_BYTES]: its own region, or (epi_alias: one tile per CTA) on top of the
+  // operand region, which is idle once the tile's last MMA has retired
   uint8_t* epi_own = b_base + (size_t)nb * 2 * sp.bplane_bytes;
-  uint8_t* epi_base = p.epi_tma == 2 ? smem : epi_own;
-  uint64_t* sfull_bar = reinterpret_cast<uint64_t*>(epi_own + (p.epi_tma == 1 ? SL_EPI_BYTES : 0));
+  uint8_t* epi_base = p.epi_alias ? smem : epi_own;
+  uint64_t* sfull_bar = reinterpret_cast<uint64_t*>(epi_own + (p.epi_alias ? 0 : EPI_BYTES));
   uint64_t* sempty_bar = sfull_bar + SL_MAX_SLABS;
   uint64_t* bfull_bar = sempty_bar + SL_MAX_SLABS;
   uint64_t* bempty_bar = bfull_bar + SL_MAX_RING;
@@ -573,7 +502,7 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     constexpr int NBAR = 2 * SL_MAX_SLABS + 2 * SL_MAX_RING + 2 + 2 + 8;       // contiguous from sfull_bar
     for (int i = lane; i < NBAR; i += 32) {
       const bool is_tempty = (i == 2 * SL_MAX_SLABS + 2 * SL_MAX_RING + 2) || (i == 2 * SL_MAX_SLABS + 2 * SL_MAX_RING + 3);
-      mbar_init(&sfull_bar[i], is_tempty ? (p.epi_tma ? 4u * (uint32_t)(p.BN >> 5) : 4u) : 1u);
+      mbar_init(&sfull_bar[i], is_tempty ? 4u * (uint32_t)(p.BN >> 5) : 1u);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (lane == 0) {
@@ -584,11 +513,6 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   if (warp == SL_WARP_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  if (p.epi_tma && warp == 0 && lane == 0) {
-    if (p.res) prefetch_tmap(&mapRes);
-    if (p.out_raw) prefetch_tmap(&mapRaw);
-    if (p.out_act) prefetch_tmap(&mapAct);
   }
   tc_fence_before();
   __syncthreads();
@@ -780,27 +704,8 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     }
     __syncwarp();
   } else {
-    const int quad = warp & 3, group = warp >> 2;
     pdl_wait();                               // identity-shortcut rows and the output planes
-    int it = 0;
-    if (p.epi_tma) {
-      const uint32_t stage_u = smem_u32(epi_base + (size_t)warp * EPI_WARP_BYTES);
-      const int nchunks = BN >> 5;
-      uint32_t n_item = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it)
-        for (int c = 0; c < nchunks; ++c)
-          if (((it * nchunks + c) & 1) == group) {
-            epilogue_item_tma(p, &mapRes, &mapRaw, &mapAct, tile, c, it, quad, lane, tmem_base, tfull_bar, tempty_bar,
-                              s_bias, s_scale, s_shift, stage_u, &rbar[warp], n_item, p.epi_tma == 2);
-            ++n_item;
-          }
-      if (lane == 0) bulk_wait0();             // all plane stores complete before the CTA retires
-      __syncwarp();
-    } else {
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it)
-        if ((it & 1) == group)
-          epilogue_tile(p, tile, it, quad, lane, tmem_base, tfull_bar, tempty_bar, s_bias, s_scale, s_shift);
-    }
+    epilogue_warp(p, total_tiles, warp, lane, tmem_base, tfull_bar, tempty_bar, s_bias, epi_base);
   }
 
   tc_fence_before();
@@ -900,6 +805,8 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
   p.act_kind = d->act_kind;
   p.mma_mask = getenv("SAR_TC_MMAMASK") ? atoi(getenv("SAR_TC_MMAMASK")) : 7;
   SAR_REQUIRE(!(p.split && p.out_dense), SAR_ERR_BAD_ARG, "sar_conv_tc_fwd: dense output cannot be phase-split");
+  SAR_REQUIRE(!(p.out_act && p.out_dense), SAR_ERR_BAD_ARG,
+              "sar_conv_tc_fwd: out_act and out_dense are the same activated values in two layouts -- request one of them");
 
   const int ktot = d->ntaps * d->a_ch + (d->s ? d->s_ch : 0);
   // slab path: plain 3x3 stride-1 taps on a non-split tensor whose halo'd slab fits shared memory
@@ -930,10 +837,9 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
   sp.bplane_bytes = p.BN * kc_max * 2;       // hi and lo tiles adjacent: [B_hi ; B_lo] is one 2*BN-row operand
   if (sp.slab_rows > 192) slab = false;
   // TMA epilogue: plane outputs of an unsplit map (every conv1 and all but the three stage-ending conv2's)
-  // 1 = own staging region, 2 = staging aliased onto the operand region (every CTA owns a single tile)
-  p.epi_tma = (slab && !p.split && !d->out_dense && !getenv("SAR_TC_NO_EPI_TMA")) ? 1 : 0;
-  if (p.epi_tma && (long long)p.m_tiles * p.n_tiles <= sms) p.epi_tma = 2;
-  const size_t fixed = 1024 + 1024 + 640 + 3 * (size_t)d->cout * sizeof(float) + (p.epi_tma == 1 ? SL_EPI_BYTES : 0);   // align slack (x2) + barriers + epilogue vectors (+ staging)
+  // epilogue staging (64 KB): aliased onto the operand region when every CTA owns a single tile
+  p.epi_alias = ((long long)p.m_tiles * p.n_tiles <= sms) ? 1 : 0;
+  const size_t fixed = 1024 + 1024 + 640 + 3 * (size_t)d->cout * sizeof(float) + (p.epi_alias ? 0 : EPI_BYTES);   // align slack (x2) + barriers + epilogue vectors (+ staging)
   const size_t budget = 227 * 1024 - fixed;
   if (slab) {
     const int n_ksteps = p.ntaps * p.chunks_main + p.chunks_sc;
@@ -953,9 +859,8 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
     if (sp.nslab > SL_MAX_SLABS) sp.nslab = SL_MAX_SLABS;
   }
 
-  CUtensorMap mapA, mapS, mapWm, mapWs, mapRes, mapRaw, mapAct;
+  CUtensorMap mapA, mapS, mapWm, mapWs;
   int rc;
-  if (!slab) p.epi_tma = 0;
   if ((rc = make_map(&mapA, d->a, d->a_rows, d->a_ch, d->a_planes, p.kc_main, slab ? sp.slab_rows : TC_BM))) return rc;
   if ((rc = make_map(&mapWm, d->w, d->cout, ktot, 2, p.kc_main, p.BN))) return rc;
   if (d->s) {
@@ -971,17 +876,11 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
   if (slab) {
     const int nb = sp.resident ? (p.ntaps * p.chunks_main + p.chunks_sc) : sp.nring;
     size_t smem = fixed + (size_t)sp.nslab * 2 * sp.slab_bytes + (size_t)nb * 2 * sp.bplane_bytes;
-    if (p.epi_tma == 2 && smem - fixed < (size_t)SL_EPI_BYTES) smem = fixed + SL_EPI_BYTES;    // aliased staging needs 64 KB of operand region
-    mapRes = mapA; mapRaw = mapA; mapAct = mapA;
-    if (p.epi_tma) {        // 32-channel x 32-row boxes of the [2][R][Cout] plane tensors, 64B swizzle
-      if (d->res && (rc = make_map(&mapRes, d->res, p.R, d->cout, 2, 32, 32))) return rc;
-      if (d->out_raw && (rc = make_map(&mapRaw, d->out_raw, p.R, d->cout, 2, 32, 32))) return rc;
-      if (d->out_act && (rc = make_map(&mapAct, d->out_act, p.R, d->cout, 2, 32, 32))) return rc;
-    }
+    if (p.epi_alias && smem - fixed < (size_t)EPI_BYTES) smem = fixed + EPI_BYTES;    // aliased staging needs 64 KB of operand region
     auto launch = [&](auto kern) -> int {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) { set_error("sar_conv_tc_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-      launch_k(kern, dim3(grid), dim3(SL_THREADS), smem, (cudaStream_t)stream, mapA, mapS, mapWm, mapWs, mapRes, mapRaw, mapAct, p, sp);
+      launch_k(kern, dim3(grid), dim3(SL_THREADS), smem, (cudaStream_t)stream, mapA, mapS, mapWm, mapWs, p, sp);
       return 0;
     };
     int lrc;
@@ -989,7 +888,8 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
     else lrc = sp.resident ? launch(conv_tc_slab_kernel<32, true>) : launch(conv_tc_slab_kernel<32, false>);
     if (lrc) return lrc;
   } else {
-    const size_t smem = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + 256 + 3 * (size_t)d->cout * sizeof(float);
+    p.stages = p.epi_alias ? 3 : 2;
+    const size_t smem = 1024 + (size_t)p.stages * TC_STAGE_BYTES + (p.epi_alias ? 0 : EPI_BYTES) + 256 + 3 * (size_t)d->cout * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("sar_conv_tc_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     launch_k(conv_tc_kernel, dim3(grid), dim3(TC_THREADS), smem, (cudaStream_t)stream, mapA, mapS, mapWm, mapWs, p);

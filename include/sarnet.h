@@ -113,8 +113,8 @@ int sar_stem_pool_fwd(const float* x, const float* w, const float* bias, const f
  * s: planes of the RAW block input for the 1x1 projection shortcut (NULL = none).
  * w: [2][cout][ntaps*a_ch + s_ch] fp16 hi/lo, K-major, k = tap*a_ch + ci (shortcut rows last).
  * bias: conv bias (+ shortcut conv bias).  res: identity-shortcut planes [2][R][cout] or NULL.
- * Outputs (any subset): out_raw / out_act planes (phase-split when out_split), out_dense fp32
- * (B,H,W,cout).  All channel counts are multiples of 32. */
+ * Outputs: out_raw and/or out_act planes (phase-split when out_split), or out_raw and/or out_dense fp32
+ * (B,H,W,cout) -- out_act and out_dense are the same activated values in two layouts, at most one of them.  All channel counts are multiples of 32. */
 typedef struct sar_tc_conv {
   const void* a; long long a_rows; int a_ch; int a_planes;
   int ntaps; int tap_row_off[9]; int tap_plane[9];

@@ -24,4 +24,4 @@ for li in (2, 3, 9, 17, 31):
     for it in range(4):
         m = [d[it*4+j] - t0 for j in range(4)]; e = [d[32+it*6+j] - t0 for j in range(6)]
         if m[0] < 0: continue
-        print("  tile %d: mma start %6d  tempty ok %6d  slab ok %6d  issued %6d | epi chunk0: tfull %6d  +tmem %5d  +res/math %5d  +split/STS %5d  +fence %5d  +TMA issue %5d" % (it, m[0], m[1], m[2], m[3], e[0], e[1]-e[0], e[2]-e[1], e[3]-e[2], e[4]-e[3], e[5]-e[4]))
+        print("  tile %d: mma start %6d  tempty ok %6d  slab ok %6d  issued %6d | epi chunk0: tfull %6d  +tmem %5d  +res/math %5d  +split/STS %5d  +write-out %5d" % (it, m[0], m[1], m[2], m[3], e[0], e[1]-e[0], e[2]-e[1], e[3]-e[2], e[5]-e[3]))

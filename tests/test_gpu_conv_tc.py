@@ -70,9 +70,12 @@ def _case(B, H, W, Cin, Cout, stride, *, residual=False, proj=None, out_split=Fa
     out_raw = tc.alloc_planes(B, Ho, Wo, Cout, out_split, "cuda")
     out_act = tc.alloc_planes(B, Ho, Wo, Cout, out_split, "cuda")
     od = torch.zeros((B, Ho, Wo, Cout), device="cuda") if dense else None
-    tc.conv_tc(a, torch.from_numpy(tc.pack_weights(w, wk)).cuda(), dev(bias), out_hw=(Ho, Wo),
-               taps=tc.tap_table(3, 3, stride, pt, pl, Wo), cout=Cout, short=short, res=res,
-               out_raw=out_raw, out_act=out_act, act=(dev(qs), dev(qt)), out_dense=None if out_split else od)
+    wp = torch.from_numpy(tc.pack_weights(w, wk)).cuda()
+    tc.conv_tc(a, wp, dev(bias), out_hw=(Ho, Wo), taps=tc.tap_table(3, 3, stride, pt, pl, Wo), cout=Cout, short=short,
+               res=res, out_raw=out_raw, out_act=out_act, act=(dev(qs), dev(qt)))
+    if dense and not out_split:      # the activated values as dense fp32 instead of planes (one layout per call)
+        tc.conv_tc(a, wp, dev(bias), out_hw=(Ho, Wo), taps=tc.tap_table(3, 3, stride, pt, pl, Wo), cout=Cout, short=short,
+                   res=res, act=(dev(qs), dev(qt)), out_dense=od)
     torch.cuda.synchronize()
     e_raw = norm_err(tc.unpack(out_raw), want)
     e_act = norm_err(tc.unpack(out_act), want_act)
