@@ -67,6 +67,8 @@ struct TcParams {
   int act_kind;                          // activated outputs: 0 relu(scale*v+shift), 1 identity, 2 tanh(v)
   int epi_alias;                         // every CTA owns ONE tile: the epilogue staging lives on top of the (then idle) operand region
   int stages;                            // generic kernel: depth of the TMA ring (2 or 3)
+  int ksplit, ksteps_split, mn_tiles;    // generic kernel, split-K (1-tap GEMMs with a long K): tile = z * mn_tiles + (mt, nt)
+  long long dense_zstride;               // elements between the fp32 partial outputs of consecutive K slices
 };
 
 // ------------------------------------------------------------------ epilogue (shared by both kernels)
@@ -117,7 +119,8 @@ __device__ __forceinline__ void epilogue_item(const TcParams& p, int tile, int c
   const int BN = p.BN;
   const int as = it & 1;
   const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-  const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+  const int z = tile / p.mn_tiles, tmn = tile - z * p.mn_tiles;         // K slice (split-K), tile within the M x N grid
+  const int mt = tmn / p.n_tiles, nt = tmn - mt * p.n_tiles;
   const int n0 = nt * BN, c0 = c * 32;
   const long long row0 = (long long)mt * TC_BM + quad * 32;
   const bool has_res = p.res != nullptr;
@@ -265,7 +268,7 @@ __device__ __forceinline__ void epilogue_item(const TcParams& p, int tile, int c
       const int rl_ = 4 * i + d_row;
       const int dr = __shfl_sync(0xffffffffu, drow_d, rl_);
       if (dr >= 0)
-        *reinterpret_cast<uint4*>(p.out_dense + (size_t)dr * p.Cout + n0 + c0 + 4 * d_piece) =
+        *reinterpret_cast<uint4*>(p.out_dense + (size_t)z * p.dense_zstride + (size_t)dr * p.Cout + n0 + c0 + 4 * d_piece) =
             lds128(ab + (uint32_t)rl_ * 128u + ((((uint32_t)d_piece) ^ (uint32_t)(rl_ & 7)) << 4));
     }
   }
@@ -340,9 +343,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     named_bar_sync(1, 256);
   }
 
-  const int n_main = p.ntaps * p.chunks_main;
+  const int n_main = p.ksplit > 1 ? p.ksteps_split : p.ntaps * p.chunks_main;      // split-K: one tap, a slice of the chunks
   const int n_ksteps = n_main + p.chunks_sc;
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int total_tiles = p.mn_tiles * p.ksplit;
   pdl_wait();          // everything above touched only constants (bias / BN affines) and on-chip state
   pdl_trigger();
 
@@ -350,22 +353,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // ===================== TMA producer (whole warp converged, one elected lane issues) =====================
     int stage = 0; uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+      const int z = tile / p.mn_tiles, tmn = tile - z * p.mn_tiles;
+      const int mt = tmn / p.n_tiles, nt = tmn - mt * p.n_tiles;
       const long long q0 = (long long)mt * TC_BM;
       const int n0 = nt * BN;
+      const int ch0 = z * p.ksteps_split;                  // first channel chunk of this K slice (0 without split-K)
       for (int ks = 0; ks < n_ksteps; ++ks) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one()) {
           uint8_t* st = smem + stage * TC_STAGE_BYTES;
           const uint32_t a_hi = smem_u32(st), a_lo = a_hi + TC_PLANE_BYTES, b_hi = a_lo + TC_PLANE_BYTES, b_lo = b_hi + TC_PLANE_BYTES;
           if (ks < n_main) {
-            const int tap = ks / p.chunks_main, ch = ks - tap * p.chunks_main;
+            const int tap = (ch0 + ks) / p.chunks_main, ch = (ch0 + ks) - tap * p.chunks_main;
             const int kc = p.kc_main;
             mbar_expect_tx(&full_bar[stage], (uint32_t)(2 * (TC_BM + BN) * kc * 2));
             const int row = (int)(q0 + p.tap_row_off[tap]);
             tma_load_3d(&mapA, a_hi, &full_bar[stage], ch * kc, row, p.tap_plane[tap]);
             tma_load_3d(&mapA, a_lo, &full_bar[stage], ch * kc, row, p.tap_plane[tap] + 1);
-            const int kofs = ks * kc;
+            const int kofs = (ch0 + ks) * kc;
             tma_load_3d(&mapWm, b_hi, &full_bar[stage], kofs, n0, 0);
             tma_load_3d(&mapWm, b_lo, &full_bar[stage], kofs, n0, 1);
           } else {
@@ -786,6 +791,7 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
   }
   p.B = d->B; p.H = d->H; p.W = d->W;
   p.P = d->W + 1; p.Rimg = (d->H + 1) * p.P;
+  if (d->nopad) { p.P = d->W; p.Rimg = d->H * d->W; }      // plain row-major operand (GEMM use): no pad row / column
   p.R = (long long)d->B * p.Rimg;
   SAR_REQUIRE(p.R < (1ll << 31) - 4096, SAR_ERR_UNSUPPORTED, "sar_conv_tc_fwd: too many rows");
   p.split = d->out_split ? 1 : 0;
@@ -808,6 +814,13 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
   SAR_REQUIRE(!(p.out_act && p.out_dense), SAR_ERR_BAD_ARG,
               "sar_conv_tc_fwd: out_act and out_dense are the same activated values in two layouts -- request one of them");
 
+  p.ksplit = d->ksplit > 1 ? d->ksplit : 1;
+  if (p.ksplit > 1) {
+    SAR_REQUIRE(d->ntaps == 1 && !d->s && !d->res && !d->out_raw && !d->out_act && d->out_dense && d->act_kind == 1,
+                SAR_ERR_BAD_ARG, "sar_conv_tc_fwd: split-K needs a 1-tap GEMM with only the (identity) dense output");
+    SAR_REQUIRE(p.chunks_main % p.ksplit == 0, SAR_ERR_BAD_ARG, "sar_conv_tc_fwd: ksplit must divide a_ch / %d", p.kc_main);
+  }
+  p.ksteps_split = p.ksplit > 1 ? p.chunks_main / p.ksplit : 0;
   const int ktot = d->ntaps * d->a_ch + (d->s ? d->s_ch : 0);
   // slab path: plain 3x3 stride-1 taps on a non-split tensor whose halo'd slab fits shared memory
   bool slab = d->ntaps == 9 && d->a_planes == 2;
@@ -822,7 +835,7 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
     int best = p.BN; long long best_cost = -1;
     for (int bn = p.BN; bn >= 32; bn >>= 1) {
       if (d->cout % bn) continue;
-      const long long tiles = (long long)p.m_tiles * (d->cout / bn);
+      const long long tiles = (long long)p.m_tiles * (d->cout / bn) * p.ksplit;
       const long long cost = ((tiles + sms - 1) / sms) * (bn + 32);
       if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
     }
@@ -838,7 +851,9 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
   if (sp.slab_rows > 192) slab = false;
   // TMA epilogue: plane outputs of an unsplit map (every conv1 and all but the three stage-ending conv2's)
   // epilogue staging (64 KB): aliased onto the operand region when every CTA owns a single tile
-  p.epi_alias = ((long long)p.m_tiles * p.n_tiles <= sms) ? 1 : 0;
+  p.mn_tiles = p.m_tiles * p.n_tiles;
+  p.dense_zstride = (long long)d->B * d->H * d->W * d->cout;
+  p.epi_alias = ((long long)p.mn_tiles * p.ksplit <= sms) ? 1 : 0;
   const size_t fixed = 1024 + 1024 + 640 + 3 * (size_t)d->cout * sizeof(float) + (p.epi_alias ? 0 : EPI_BYTES);   // align slack (x2) + barriers + epilogue vectors (+ staging)
   const size_t budget = 227 * 1024 - fixed;
   if (slab) {
@@ -871,7 +886,7 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
   } else {
     mapS = mapA; mapWs = mapWm;
   }
-  const int tiles = p.m_tiles * p.n_tiles;
+  const int tiles = p.mn_tiles * p.ksplit;
   const int grid = tiles < sms ? tiles : sms;
   if (slab) {
     const int nb = sp.resident ? (p.ntaps * p.chunks_main + p.chunks_sc) : sp.nring;

@@ -122,4 +122,14 @@ int sar_gemm_splitk_fwd(const float* a, const float* w, const float* bias, float
   return check_launch("sar_gemm_splitk_fwd(reduce)");
 }
 
+int sar_splitk_reduce_fwd(const float* ws, const float* bias, float* out, int M, int N, int splits, void* stream) {
+  using namespace sar;
+  SAR_REQUIRE(ws && out && M > 0 && N > 0 && splits > 0, SAR_ERR_BAD_ARG, "sar_splitk_reduce_fwd: bad argument");
+  long long total = (long long)M * N;
+  unsigned rg = (unsigned)((total + 255) / 256);
+  if (rg > 148 * 8) rg = 148 * 8;
+  launch_k(splitk_reduce_kernel, dim3(rg), dim3(256), 0, (cudaStream_t)stream, ws, bias, out, M, N, splits);
+  return check_launch("sar_splitk_reduce_fwd");
+}
+
 }  // extern "C"

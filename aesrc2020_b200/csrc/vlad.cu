@@ -25,7 +25,7 @@ constexpr int VLAD_THREADS = 256;
 __global__ void __launch_bounds__(VLAD_THREADS) vlad_kernel(const float* __restrict__ feat, const float* __restrict__ wa,
                                                              const float* __restrict__ ba, const float* __restrict__ score,
                                                              const float* __restrict__ centers, float* __restrict__ out,
-                                                             int S, int D, int K, int G, int wa_smem) {
+                                                             __half* __restrict__ out_planes, int S, int D, int K, int G, int wa_smem) {
   extern __shared__ __align__(16) float smem[];
   const int KG = K + G;
   const int KGP = (KG + 7) & ~7;                  // padded cluster count (A row, zero-filled)
@@ -171,10 +171,30 @@ __global__ void __launch_bounds__(VLAD_THREADS) vlad_kernel(const float* __restr
           ss = fmaf(acc[i][j], acc[i][j], ss);
         }
         ss = warp_sum(ss);
-        float* orow = out + ((size_t)b * K + k) * D;
         const float inv = 1.0f / sqrtf(fmaxf(ss, 1e-12f));
-        *reinterpret_cast<float4*>(orow + d0) = make_float4(acc[i][0] * inv, acc[i][1] * inv, acc[i][2] * inv, acc[i][3] * inv);
-        *reinterpret_cast<float4*>(orow + d1) = make_float4(acc[i][4] * inv, acc[i][5] * inv, acc[i][6] * inv, acc[i][7] * inv);
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = acc[i][j] * inv;
+        if (out) {
+          float* orow = out + ((size_t)b * K + k) * D;
+          *reinterpret_cast<float4*>(orow + d0) = make_float4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<float4*>(orow + d1) = make_float4(o[4], o[5], o[6], o[7]);
+        }
+        if (out_planes) {                 // fp16 hi/lo planes [2][B][K*D] for the tensor-core embedding GEMM
+          __half* ph = out_planes + ((size_t)b * K + k) * D;
+          __half* pl = ph + (size_t)gridDim.x * K * D;
+#pragma unroll
+          for (int hlf = 0; hlf < 2; ++hlf) {
+            const float* oo = o + 4 * hlf;
+            const __half2 h01 = __floats2half2_rn(oo[0], oo[1]), h23 = __floats2half2_rn(oo[2], oo[3]);
+            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+            const __half2 l01 = __floats2half2_rn((oo[0] - f01.x) * 2048.f, (oo[1] - f01.y) * 2048.f);
+            const __half2 l23 = __floats2half2_rn((oo[2] - f23.x) * 2048.f, (oo[3] - f23.y) * 2048.f);
+            const int dd = hlf ? d1 : d0;
+            *reinterpret_cast<uint2*>(ph + dd) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+            *reinterpret_cast<uint2*>(pl + dd) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+          }
+        }
       }
     }
   }
@@ -189,20 +209,28 @@ static size_t vlad_smem_floats(int S, int D, int KG, bool with_w) {
 
 extern "C" int sar_vlad_fwd(const float* feat, const float* w_assign, const float* b_assign, const float* score,
                             const float* centers, float* out, int B, int S, int D, int K, int G, void* stream) {
+  SAR_REQUIRE(out, SAR_ERR_BAD_ARG, "sar_vlad_fwd: null pointer");
+  return sar_vlad_planes_fwd(feat, w_assign, b_assign, score, centers, out, nullptr, B, S, D, K, G, stream);
+}
+
+extern "C" int sar_vlad_planes_fwd(const float* feat, const float* w_assign, const float* b_assign, const float* score,
+                                   const float* centers, float* out, void* out_planes, int B, int S, int D, int K, int G,
+                                   void* stream) {
   using namespace sar;
-  SAR_REQUIRE(feat && centers && out, SAR_ERR_BAD_ARG, "sar_vlad_fwd: null pointer");
+  SAR_REQUIRE(feat && centers && (out || out_planes), SAR_ERR_BAD_ARG, "sar_vlad_fwd: null pointer");
   SAR_REQUIRE((score != nullptr) != (w_assign != nullptr && b_assign != nullptr), SAR_ERR_BAD_ARG,
               "sar_vlad_fwd: pass either (w_assign, b_assign) or score");
   SAR_REQUIRE(B > 0 && S > 0 && D > 0 && K > 0 && G >= 0, SAR_ERR_BAD_ARG, "sar_vlad_fwd: bad dimension");
   SAR_REQUIRE(D == 256 && K + G <= 128, SAR_ERR_UNSUPPORTED,
               "sar_vlad_fwd: this build supports D == 256 (hidden_dim) and K+G <= 128 (got D=%d K+G=%d)", D, K + G);
-  SAR_REQUIRE(aligned16(feat) && aligned16(out) && aligned16(centers), SAR_ERR_ALIGN, "sar_vlad_fwd: unaligned pointer");
+  SAR_REQUIRE(aligned16(feat) && (!out || aligned16(out)) && (!out_planes || aligned16(out_planes)) && aligned16(centers), SAR_ERR_ALIGN,
+              "sar_vlad_fwd: unaligned pointer");
   const size_t limit = 227 * 1024;
   int wa_smem = (!score && vlad_smem_floats(S, D, K + G, true) * sizeof(float) <= limit) ? 1 : 0;
   size_t smem = vlad_smem_floats(S, D, K + G, wa_smem != 0) * sizeof(float);
   SAR_REQUIRE(smem <= limit, SAR_ERR_UNSUPPORTED, "sar_vlad_fwd: S*D too large for shared memory (%zu B)", smem);
   cudaError_t e = cudaFuncSetAttribute(vlad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("sar_vlad_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-  launch_k(vlad_kernel, dim3(B), dim3(VLAD_THREADS), smem, (cudaStream_t)stream, feat, w_assign, b_assign, score, centers, out, S, D, K, G, wa_smem);
+  launch_k(vlad_kernel, dim3(B), dim3(VLAD_THREADS), smem, (cudaStream_t)stream, feat, w_assign, b_assign, score, centers, out, reinterpret_cast<__half*>(out_planes), S, D, K, G, wa_smem);
   return check_launch("sar_vlad_fwd");
 }

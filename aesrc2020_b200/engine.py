@@ -262,6 +262,14 @@ class SARNetEngine:
             b = w["AR_EMBEDDING/bias"].astype(np.float64)
             self._put("AR_EMBEDDING/kernel_folded", (s1[:, None] * W) * s2[None, :])
             self._put("AR_EMBEDDING/bias_folded", (t1 @ W + b) * s2 + t2)
+            Wf = (s1[:, None] * W) * s2[None, :]
+            self.embed_ksplit = 0
+            if self.dense_tc and cfg.mto in ("vlad", "gvlad") and Wf.shape[0] % 2048 == 0 and Wf.shape[1] % 32 == 0:
+                from . import tc
+                # tensor-core split-K GEMM: K slices of 256 channels (4 k-steps), e.g. 64 slices at K = 16384
+                self.embed_ksplit = Wf.shape[0] // 256
+                self.p["AR_EMBEDDING/w_tc"] = torch.from_numpy(tc.pack_dense_weights(Wf.astype(np.float32))).to(self.device)
+                self.p["AR_EMBEDDING/zero_bias"] = torch.zeros(Wf.shape[1], device=self.device, dtype=torch.float32)
             for n in ("AR_CF_DS1", "AR_CF_DS2", "y_accent"):
                 self._dense(w, n)
             if cfg.disc_enable:
@@ -440,9 +448,21 @@ class SARNetEngine:
                 integ = self.bigru_planes(P4, "AR_MERGE", seq=False) if P4 is not None else self.bigru(ar, "AR_MERGE", seq=False)
             else:
                 G = cfg.ghost_clusters if cfg.mto == "gvlad" else 0
+                vplanes = None
+                if getattr(self, "embed_ksplit", 0):
+                    from . import tc
+                    key = (B, cfg.vlad_clusters * ar.shape[-1], "vlad")
+                    if key not in self._seq_bufs:
+                        self._seq_bufs[key] = tc.alloc_rows(B, key[1], self.device)
+                    vplanes = self._seq_bufs[key]
                 integ = ops.vlad(ar, p[cfg.mto + "/w_assign"], p[cfg.mto + "/b_assign"], p[cfg.mto + "/centers"],
-                                 cfg.vlad_clusters, G)
-            emb = self.embed(integ)
+                                 cfg.vlad_clusters, G, planes=vplanes, want_dense=want_intermediates or vplanes is None)
+            if cfg.mto in ("vlad", "gvlad") and getattr(self, "embed_ksplit", 0):
+                from . import tc
+                emb = tc.gemm_splitk_tc(vplanes, p["AR_EMBEDDING/w_tc"], p["AR_EMBEDDING/bias_folded"],
+                                        p["AR_EMBEDDING/zero_bias"], self.embed_ksplit)
+            else:
+                emb = self.embed(integ)
             if want_intermediates:
                 out["ar_ds"], out["integration"] = ar, integ
             out["embedding"] = emb

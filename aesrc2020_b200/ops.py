@@ -116,8 +116,10 @@ def bigru(xp, rec, rbias, *, seq=True):
     return out
 
 
-def vlad(feat, w_assign, b_assign, centers, K: int, G: int, score=None):
-    """feat (B,S,D) -> (B, K*D).  Scores from (w_assign, b_assign) or a given `score` (B,S,K+G)."""
+def vlad(feat, w_assign, b_assign, centers, K: int, G: int, score=None, *, planes=None, want_dense: bool = True):
+    """feat (B,S,D) -> (B, K*D).  Scores from (w_assign, b_assign) or a given `score` (B,S,K+G).
+    `planes` (tc.Planes of a (1, B, 1) map with K*D channels, see tc.alloc_rows): also write the descriptor as
+    fp16 hi/lo planes for the tensor-core embedding GEMM; want_dense=False skips the fp32 output."""
     feat = _f32(feat)
     B, S, D = feat.shape
     assert centers.shape == (K + G, D)
@@ -126,9 +128,12 @@ def vlad(feat, w_assign, b_assign, centers, K: int, G: int, score=None):
     else:
         score = _f32(score)
         assert tuple(score.shape) == (B, S, K + G) and w_assign is None and b_assign is None
-    out = torch.empty((B, K * D), device=feat.device, dtype=torch.float32)
-    check(_shim.lib().sar_vlad_fwd(ptr(feat), ptr(w_assign), ptr(b_assign), ptr(score), ptr(centers), ptr(out),
-                                   B, S, D, K, G, stream_ptr()), "sar_vlad_fwd")
+    out = torch.empty((B, K * D), device=feat.device, dtype=torch.float32) if (want_dense or planes is None) else None
+    if planes is not None:
+        assert tuple(planes.t.shape) == (2, B, K * D), (tuple(planes.t.shape), (2, B, K * D))
+    check(_shim.lib().sar_vlad_planes_fwd(ptr(feat), ptr(w_assign), ptr(b_assign), ptr(score), ptr(centers), ptr(out),
+                                          ptr(planes.t) if planes is not None else None,
+                                          B, S, D, K, G, stream_ptr()), "sar_vlad_fwd")
     _count(1)
     return out
 

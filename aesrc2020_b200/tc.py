@@ -32,6 +32,7 @@ class sar_tc_conv(C.Structure):
         ("B", C.c_int), ("H", C.c_int), ("W", C.c_int),
         ("dbg", C.c_void_p),
         ("act_kind", C.c_int),
+        ("nopad", C.c_int), ("ksplit", C.c_int),
     ]
 
 ACT_KIND = {"bn_relu": 0, None: 1, "none": 1, "linear": 1, "tanh": 2}
@@ -147,7 +148,7 @@ def tap_table(kh: int, kw: int, stride: int, pad_t: int, pad_l: int, W_out: int)
 def conv_tc(a: Planes, w_packed: torch.Tensor, bias: torch.Tensor, *, out_hw: Tuple[int, int], taps, cout: int,
             short: Optional[Planes] = None, res: Optional[Planes] = None, out_raw: Optional[Planes] = None,
             out_act: Optional[Planes] = None, act=None, out_dense: Optional[torch.Tensor] = None, dbg=None,
-            act_kind: int = 0):
+            act_kind: int = 0, nopad: bool = False, ksplit: int = 1):
     """sar_conv_tc_fwd.  taps = (row_offsets, plane_bases)."""
     d = sar_tc_conv()
     d.a, d.a_rows, d.a_ch, d.a_planes = ptr(a.t), a.rows, a.C, a.nplanes
@@ -179,6 +180,7 @@ def conv_tc(a: Planes, w_packed: torch.Tensor, bias: torch.Tensor, *, out_hw: Tu
     d.B, d.H, d.W = a.B, H, W
     d.dbg = ptr(dbg) if dbg is not None else None
     d.act_kind = int(act_kind)
+    d.nopad, d.ksplit = (1 if nopad else 0), int(ksplit)
     check(_shim.lib().sar_conv_tc_fwd(C.byref(d), stream_ptr()), "sar_conv_tc_fwd")
     ops._count(1)
 
@@ -196,4 +198,24 @@ def dense_tc(a: Planes, w_packed: torch.Tensor, bias: torch.Tensor, *, act=None)
     dout = int(w_packed.shape[1])
     out = torch.empty((a.B, a.H, a.W, dout), device=a.t.device, dtype=torch.float32)
     conv_tc(a, w_packed, bias, out_hw=(a.H, a.W), taps=([0], [0]), cout=dout, out_dense=out, act_kind=ACT_KIND[act])
+    return out
+
+
+def alloc_rows(M: int, Cc: int, device) -> Planes:
+    """hi/lo planes [2][M][C] of a plain row-major (M, C) matrix (no pad rows): the A operand of gemm_splitk_tc."""
+    t = torch.zeros((2, M, Cc), device=device, dtype=torch.float16)
+    return Planes(t, 1, M, 1, Cc, False)
+
+
+def gemm_splitk_tc(a: Planes, w_packed: torch.Tensor, bias: torch.Tensor, zero_bias: torch.Tensor, ksplit: int) -> torch.Tensor:
+    """out (M, N) = a (M, K) @ w (K, N) + bias on the tensor cores with the long K axis cut into `ksplit` slices
+    (AR_EMBEDDING, model.py:286-289: M = batch, K = clusters * hidden = 16384): slice z is one tile of the 1-tap
+    conv_tc kernel writing fp32 partial products, sar_splitk_reduce_fwd sums them in a fixed order and adds the bias."""
+    M, N = a.H, int(w_packed.shape[1])
+    ws = torch.empty((ksplit, M, N), device=a.t.device, dtype=torch.float32)
+    conv_tc(a, w_packed, zero_bias, out_hw=(a.H, a.W), taps=([0], [0]), cout=N, out_dense=ws, act_kind=ACT_KIND[None],
+            nopad=True, ksplit=ksplit)
+    out = torch.empty((M, N), device=a.t.device, dtype=torch.float32)
+    check(_shim.lib().sar_splitk_reduce_fwd(ptr(ws), ptr(bias), ptr(out), M, N, ksplit, stream_ptr()), "sar_splitk_reduce_fwd")
+    ops._count(1)
     return out

@@ -130,6 +130,9 @@ typedef struct sar_tc_conv {
   void* dbg;            /* optional device buffer of >= 64 int64 clock64() stamps of CTA 0 (profiling aid); NULL */
   int act_kind;         /* out_act / out_dense activation: 0 relu(act_scale*v+act_shift) (the next layer's BN->ReLU),
                            1 identity, 2 tanh(v) -- the Dense layers of model.py:35-42 run as 1-tap "convolutions" */
+  int nopad;            /* 1: the operand / output rows are plain row-major (B*H*W rows, no pad row or column): GEMM use */
+  int ksplit;           /* > 1: split-K for a 1-tap GEMM with a long K (a_ch): K slice z writes its fp32 partial products to
+                           out_dense + z*B*H*W*cout (identity activation, zero bias); sum them with sar_splitk_reduce_fwd */
 } sar_tc_conv;
 int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream);
 
@@ -175,6 +178,10 @@ int sar_bigru_fwd(const float* xp, const float* rec, const float* rbias, float* 
  * Requires D == 256 (hidden_dim of this build) and K+G <= 128. */
 int sar_vlad_fwd(const float* feat, const float* w_assign, const float* b_assign, const float* score,
                  const float* centers, float* out, int B, int S, int D, int K, int G, void* stream);
+/* Same, with the descriptor ALSO / INSTEAD written as fp16 hi/lo planes [2][B][K*D] (x = hi + lo/2048) for the
+ * tensor-core AR_EMBEDDING GEMM (sar_conv_tc_fwd with nopad + ksplit).  `out` and `out_planes` may each be NULL. */
+int sar_vlad_planes_fwd(const float* feat, const float* w_assign, const float* b_assign, const float* score,
+                        const float* centers, float* out, void* out_planes, int B, int S, int D, int K, int G, void* stream);
 
 /* GlobalAveragePooling1D (model.py:125): out (B,D) = mean over S of x (B,S,D). */
 int sar_avgpool_fwd(const float* x, float* out, int B, int S, int D, void* stream);
@@ -185,6 +192,9 @@ int sar_avgpool_fwd(const float* x, float* out, int B, int S, int D, void* strea
 size_t sar_gemm_splitk_workspace_bytes(int M, int K, int N);
 int sar_gemm_splitk_fwd(const float* a, const float* w, const float* bias, float* out,
                         int M, int K, int N, void* workspace, size_t workspace_bytes, void* stream);
+
+/* out (M,N) = bias + sum over `splits` partial (M,N) fp32 tiles of `ws`, in a fixed order (deterministic). */
+int sar_splitk_reduce_fwd(const float* ws, const float* bias, float* out, int M, int N, int splits, void* stream);
 
 /* ---- heads and losses -------------------------------------------------------------- */
 

@@ -185,3 +185,35 @@ def test_dense_tc_after_layernorm_planes(cuda_device, B, S, Din, Dout, act):
     y = tc.dense_tc(planes, wp, dev(b), act=act).reshape(B, S, Dout)
     assert norm_err(y, want) < 5e-6
     assert ops.layernorm(dev(x), dev(g), dev(bt), planes=planes, want_dense=False) is None
+
+
+@pytest.mark.parametrize("M,K,N,ksplit", [(64, 16384, 256, 64), (5, 2048, 64, 8), (130, 4096, 256, 16)])
+def test_gemm_splitk_tc(cuda_device, M, K, N, ksplit):
+    """AR_EMBEDDING as a tensor-core split-K GEMM over plain row-major hi/lo planes (nopad + ksplit) vs float64."""
+    from aesrc2020_b200 import tc
+    rng = np.random.RandomState(M + N)
+    a = _f32(rng.randn(M, K))
+    w = _f32(rng.randn(K, N) / np.sqrt(K))
+    b = _f32(rng.randn(N) * 0.1)
+    want = t64(a) @ t64(w) + t64(b)
+    planes = tc.alloc_rows(M, K, "cuda")
+    tc.pack(dev(a).reshape(1, M, 1, K), out=None)          # (exercise pack on this shape too)
+    hi = torch.from_numpy(a.astype(np.float32)).cuda().half()
+    planes.t[0] = hi
+    planes.t[1] = ((torch.from_numpy(a.astype(np.float32)).cuda() - hi.float()) * 2048.0).half()
+    wp = torch.from_numpy(tc.pack_dense_weights(w.astype(np.float32))).cuda()
+    got = tc.gemm_splitk_tc(planes, wp, dev(b), torch.zeros(N, device="cuda"), ksplit)
+    assert norm_err(got, want) < 5e-6
+
+
+def test_vlad_planes_output_matches_dense(cuda_device):
+    from aesrc2020_b200 import ops, tc
+    rng = np.random.RandomState(3)
+    B, S, D, K, G = 5, 48, 256, 64, 8
+    feat = dev(rng.randn(B, S, D))
+    wa, ba, cen = dev(rng.randn(D, K + G) / 16 * 3), dev(rng.randn(K + G) * 0.1), dev(rng.randn(K + G, D) / 16)
+    planes = tc.alloc_rows(B, K * D, "cuda")
+    dense = ops.vlad(feat, wa, ba, cen, K, G, planes=planes)
+    rebuilt = planes.t[0].float() + planes.t[1].float() / 2048.0
+    assert float((rebuilt - dense).abs().max()) < 2.0 ** -21
+    assert ops.vlad(feat, wa, ba, cen, K, G, planes=planes, want_dense=False) is None
