@@ -24,7 +24,7 @@
 //     global store sits in front of the per-step release).
 // Both directions and all utterance groups run concurrently (grid = 8 * groups * 2 CTAs).
 #include <cooperative_groups.h>
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -49,6 +49,18 @@ constexpr int GRU_THREADS = (GRU_COLS / GRU_CPT) * GRU_KQ;   // 384
 // gives 12 clusters in one wave at 1.5x the FMA work per step.
 constexpr int GRU_MAX_CLUSTERS = 15;
 
+// shared::cta address -> the same location in CTA `rank` of the cluster (shared::cluster window)
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+// asynchronous remote store that also counts 4 bytes on the destination CTA's mbarrier: the data and its
+// "arrived" signal travel together, so a step needs no cluster-wide barrier (arrive.release alone cost ~1300 cycles)
+__device__ __forceinline__ void st_async_f32(uint32_t raddr, float v, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+               ::"r"(raddr), "r"(__float_as_uint(v)), "r"(rbar) : "memory");
+}
 __device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
@@ -64,6 +76,7 @@ bigru_kernel(const float* __restrict__ xp, const float* __restrict__ rec, const 
   static_assert(GRU_BG % 4 == 0 && NV % GRU_KQ == 0 && GRU_UPC * GRU_BG <= GRU_THREADS, "unsupported utterance group");
   __shared__ __align__(16) float h_s[2 * GRU_HBUF];                 // [buf][kq][i][b]
   __shared__ __align__(16) float hp_s[GRU_COLS][GRU_BG];
+  __shared__ __align__(8) uint64_t hbar[2];                          // h buffer b has received all 8 CTAs' slices
   extern __shared__ __align__(16) float out_s[];                    // [S][gb][gj] when stage_out
 
 #ifdef SAR_GRU_PROFILE
@@ -108,9 +121,12 @@ bigru_kernel(const float* __restrict__ xp, const float* __restrict__ rec, const 
   const int hpos = (unit / GRU_KPT) * GRU_HSTRIDE + (unit % GRU_KPT) * GRU_BG + gb;
 
   for (int i = t; i < 2 * GRU_HBUF; i += GRU_THREADS) h_s[i] = 0.f;
-  float* remote[GRU_CL];
-#pragma unroll
-  for (int r = 0; r < GRU_CL; ++r) remote[r] = cluster.map_shared_rank(h_s, r);
+  if (t == 0) {
+    mbar_init(&hbar[0], 1); mbar_init(&hbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  const uint32_t h_u = smem_u32(h_s), hbar_u = smem_u32(hbar);
+  constexpr uint32_t STEP_BYTES = (uint32_t)(GRU_CL * GRU_UPC * GRU_BG * sizeof(float));   // one step's h' from all 8 CTAs
 
   pdl_wait();            // everything above read only the recurrent weights
   pdl_trigger();
@@ -132,6 +148,11 @@ bigru_kernel(const float* __restrict__ xp, const float* __restrict__ rec, const 
   const long long t_loop = clock64();
 #endif
   for (int step = 0; step < S; ++step) {
+    // h(step) is complete in my buffer `cur` once all 8 CTAs' step-1 gate threads have pushed (step 0 reads zeros);
+    // buffer cur^1 is then armed for h(step+1).  Double buffering + this data dependency make the h buffers race
+    // free: nobody can push h(step+1) before every CTA has pushed h(step), i.e. finished reading h(step-1).
+    if (step > 0) mbar_wait(&hbar[cur], (uint32_t)((step - 1) >> 1) & 1u);
+    if (t == 0 && step + 1 < S) mbar_expect_tx(&hbar[cur ^ 1], STEP_BYTES);
     GRU_STAMP(0)
     // ---- partial dot products: 4 columns x 16 k's x 8 utterances
     float v[NV];
@@ -200,10 +221,11 @@ bigru_kernel(const float* __restrict__ xp, const float* __restrict__ rec, const 
       const float hh = tanhf(x0h + r * (hp_s[2 * GRU_UPC + gj][gb] + rbh));
       const float hold = h_s[cur * GRU_HBUF + hpos];
       const float hn = z * hold + (1.f - z) * hh;
-      const int nxt_off = (cur ^ 1) * GRU_HBUF + hpos;
-      if (seq & 2) { h_s[nxt_off] = hn; } else {
+      if (step + 1 < S) {
+        const uint32_t dst = h_u + (uint32_t)(((cur ^ 1) * GRU_HBUF + hpos) * sizeof(float));
+        const uint32_t bar = hbar_u + (uint32_t)((cur ^ 1) * sizeof(uint64_t));
 #pragma unroll
-      for (int r2 = 0; r2 < GRU_CL; ++r2) remote[r2][nxt_off] = hn;
+        for (int r2 = 0; r2 < GRU_CL; ++r2) st_async_f32(mapa_u32(dst, (uint32_t)r2), hn, mapa_u32(bar, (uint32_t)r2));
       }
       if (stage_out) {
         if (seq & 1) out_s[(size_t)step * (GRU_UPC * GRU_BG) + t] = hn;
@@ -215,16 +237,14 @@ bigru_kernel(const float* __restrict__ xp, const float* __restrict__ rec, const 
       }
     }
     GRU_STAMP(4)
-    if (seq & 4) __syncthreads(); else
-    cluster_arrive_release();            // publishes my DSMEM stores (no global store is pending)
-    // rotate the x-projection registers and prefetch step+2 while the barrier completes
+    // rotate the x-projection registers and prefetch step+2 while the pushes are in flight
     x0z = x1z; x0r = x1r; x0h = x1h;
     if (bvalid && step + 2 < S) { const float* p = xrow(step + 2); x1z = __ldg(p); x1r = __ldg(p + U); x1h = __ldg(p + 2 * U); }
     GRU_STAMP(5)
-    if (!(seq & 4)) cluster_wait_acquire();
     GRU_STAMP(6)
     cur ^= 1;
   }
+  cluster.sync();                        // nobody leaves while a peer could still address its shared memory
 #ifdef SAR_GRU_PROFILE
   const long long t_loop_end = clock64();
 #endif
@@ -286,7 +306,6 @@ extern "C" int sar_bigru_fwd(const float* xp, const float* rec, const float* rbi
   };
   const int lrc = bg == 8 ? launch(bigru_kernel<8>) : launch(bigru_kernel<12>);
   if (lrc) return lrc;
-  seq &= 1;
   return check_launch("sar_bigru_fwd");
 }
 
