@@ -27,6 +27,7 @@
 // 3-stage TMA->SMEM ring with mbarrier full/empty pairs, 128B/64B hardware swizzle.
 #include <cuda.h>
 #include <stdlib.h>
+#include <type_traits>
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -65,6 +66,8 @@ struct TcParams {
   long long* dbg;                        // optional: clock64 timestamps of CTA 0 (profiling aid)
   int mma_mask;                          // experiment: which of the 3 hi/lo products to issue (7 = all)
   int act_kind;                          // activated outputs: 0 relu(scale*v+shift), 1 identity, 2 tanh(v)
+  unsigned div_rimg_m, div_p_m;          // floor(x / Rimg), floor(x / P) for x < 2^31 as __umulhi(x, m) >> sh (0: divisor is 1)
+  int div_rimg_sh, div_p_sh;
   int epi_alias;                         // every CTA owns ONE tile: the epilogue staging lives on top of the (then idle) operand region
   int stages;                            // generic kernel: depth of the TMA ring (2 or 3)
   int ksplit, ksteps_split, mn_tiles;    // generic kernel, split-K (1-tap GEMMs with a long K): tile = z * mn_tiles + (mt, nt)
@@ -113,6 +116,10 @@ __device__ __forceinline__ void sts128(uint32_t a, const uint4& v) {
 }
 __device__ __noinline__ float tanh_precise(float x) { return tanhf(x); }
 
+// MODE < 0: every output option is a run-time flag.  MODE >= 0 fixes the combination at compile time (the hot
+// residual-block cases; the per-round flag tests were ~25 % of the executed instructions):
+//   bit 0 = identity shortcut, bit 1 = raw planes out, the activated planes (BN->ReLU) are always written.
+template <int MODE>
 __device__ __forceinline__ void epilogue_item(const TcParams& p, int tile, int c, int it, int quad, int lane,
                                            uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar,
                                            uint32_t s_bias_u, uint32_t stage_u) {
@@ -123,7 +130,11 @@ __device__ __forceinline__ void epilogue_item(const TcParams& p, int tile, int c
   const int mt = tmn / p.n_tiles, nt = tmn - mt * p.n_tiles;
   const int n0 = nt * BN, c0 = c * 32;
   const long long row0 = (long long)mt * TC_BM + quad * 32;
-  const bool has_res = p.res != nullptr;
+  const bool has_res = MODE < 0 ? (p.res != nullptr) : ((MODE & 1) != 0);
+  const bool out_raw = MODE < 0 ? (p.out_raw != nullptr) : ((MODE & 2) != 0);
+  const bool out_act = MODE < 0 ? (p.out_act != nullptr) : true;
+  const bool out_dense = MODE < 0 ? (p.out_dense != nullptr) : false;
+  const int act_kind = MODE < 0 ? p.act_kind : 0;
   const uint32_t rb = stage_u, ab = stage_u + EPI_BUF_BYTES;
   // global side of the plane tiles: lane -> (row 8i + lane/4, 16-byte piece lane%4); slot = piece ^ ((row >> 1) & 3)
   const int g_row = lane >> 2, g_piece = lane & 3;
@@ -140,17 +151,19 @@ __device__ __forceinline__ void epilogue_item(const TcParams& p, int tile, int c
       }
     }
   }
-  // TMEM side: lane -> row.  drow_p / drow_d: destination row of the plane / dense outputs (-1: not stored)
+  // TMEM side: lane -> row.  drow_p / drow_d: destination row of the plane / dense outputs; -1: not stored;
+  // -2 - q: pad position of a non-split plane, row q is stored as zeros (pads must stay zero)
   const long long q = row0 + lane;
-  bool valid = q < p.R;
   int drow_p = -1, drow_d = -1;
-  if (valid) {
-    const int n = (int)(q / p.Rimg);
-    const int rem = (int)(q - (long long)n * p.Rimg);
-    const int h = rem / p.P, w = rem - h * p.P;
-    drow_p = (int)q;
-    valid = (h < p.H) && (w < p.W);
+  if (q < p.R) {
+    const uint32_t qu = (uint32_t)q;
+    const int n = p.div_rimg_m ? (int)(__umulhi(qu, p.div_rimg_m) >> p.div_rimg_sh) : (int)qu;
+    const uint32_t rem = qu - (uint32_t)n * (uint32_t)p.Rimg;
+    const int h = p.div_p_m ? (int)(__umulhi(rem, p.div_p_m) >> p.div_p_sh) : (int)rem;
+    const int w = (int)rem - h * p.P;
+    const bool valid = (h < p.H) && (w < p.W);
     if (p.split) drow_p = valid ? (int)((long long)(2 * ((h & 1) * 2 + (w & 1))) * p.R2 + (long long)n * p.Rimg2 + (h >> 1) * p.P2 + (w >> 1)) : -1;
+    else drow_p = valid ? (int)q : -2 - (int)q;
     if (valid) drow_d = (n * p.H + h) * p.W + w;
   }
   const size_t lo_off = (size_t)(p.split ? p.R2 : p.R) * p.Cout;       // hi plane -> lo plane, in elements
@@ -202,18 +215,14 @@ __device__ __forceinline__ void epilogue_item(const TcParams& p, int tile, int c
         v[e * 2 + 1] += fmaf(fl.y, TC_LO_INV, fh.y);
       }
     }
-    if (!valid) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = 0.f;        // pad positions of non-split planes are stored as zeros
-    }
-    if (p.out_raw) {                                 // in place: a lane only reads and writes its own row here
+    if (out_raw) {                                   // in place: a lane only reads and writes its own row here
       uint4 hi, lo;
       split8(v, hi, lo);
       sts128(rb + off, hi);
       sts128(rb + EPI_PLANE_BYTES + off, lo);
     }
-    if (p.out_act || p.out_dense) {
-      if (p.act_kind == 0) {
+    if (out_act || out_dense) {
+      if (act_kind == 0) {
         const uint4 s0 = lds128(vec + (uint32_t)p.Cout * 4u), s1 = lds128(vec + (uint32_t)p.Cout * 4u + 16);
         const uint4 t0 = lds128(vec + (uint32_t)p.Cout * 8u), t1 = lds128(vec + (uint32_t)p.Cout * 8u + 16);
         const float ss[8] = {__uint_as_float(s0.x), __uint_as_float(s0.y), __uint_as_float(s0.z), __uint_as_float(s0.w),
@@ -221,12 +230,12 @@ __device__ __forceinline__ void epilogue_item(const TcParams& p, int tile, int c
         const float tt[8] = {__uint_as_float(t0.x), __uint_as_float(t0.y), __uint_as_float(t0.z), __uint_as_float(t0.w),
                              __uint_as_float(t1.x), __uint_as_float(t1.y), __uint_as_float(t1.z), __uint_as_float(t1.w)};
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = valid ? fmaxf(fmaf(v[e], ss[e], tt[e]), 0.f) : 0.f;   // relu(shift) of a pad is not zero
-      } else if (p.act_kind == 2) {                  // Dense(..., activation='tanh'), model.py:35-42
+        for (int e = 0; e < 8; ++e) v[e] = fmaxf(fmaf(v[e], ss[e], tt[e]), 0.f);
+      } else if (act_kind == 2) {                  // Dense(..., activation='tanh'), model.py:35-42
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] = tanh_precise(v[e]);
       }
-      if (p.out_act) {
+      if (out_act) {
         uint4 hi, lo;
         split8(v, hi, lo);
         sts128(ab + off, hi);
@@ -242,26 +251,28 @@ __device__ __forceinline__ void epilogue_item(const TcParams& p, int tile, int c
   EPI_STAMP(3)
   __syncwarp();
   // write-out of the plane tiles: every store instruction covers 8 rows x 64 B
-  if (p.out_raw || p.out_act) {
+  if (out_raw || out_act) {
 #pragma unroll 1
     for (int i = 0; i < 4; ++i) {
       const int rl_ = 8 * i + g_row;
       const int dr = __shfl_sync(0xffffffffu, drow_p, rl_);
       const uint32_t off = (uint32_t)rl_ * 64u + (((uint32_t)g_piece ^ (uint32_t)((rl_ >> 1) & 3)) << 4);
-      if (dr >= 0) {
-        const size_t e0 = (size_t)dr * p.Cout + g_col;
-        if (p.out_raw) {
-          *reinterpret_cast<uint4*>(p.out_raw + e0) = lds128(rb + off);
-          *reinterpret_cast<uint4*>(p.out_raw + e0 + lo_off) = lds128(rb + EPI_PLANE_BYTES + off);
+      if (dr != -1) {
+        const bool zero = dr < 0;                       // pad position: the staged values are garbage, store zeros
+        const size_t e0 = (size_t)(zero ? -2 - dr : dr) * p.Cout + g_col;
+        const uint4 z4 = make_uint4(0, 0, 0, 0);
+        if (out_raw) {
+          *reinterpret_cast<uint4*>(p.out_raw + e0) = zero ? z4 : lds128(rb + off);
+          *reinterpret_cast<uint4*>(p.out_raw + e0 + lo_off) = zero ? z4 : lds128(rb + EPI_PLANE_BYTES + off);
         }
-        if (p.out_act) {
-          *reinterpret_cast<uint4*>(p.out_act + e0) = lds128(ab + off);
-          *reinterpret_cast<uint4*>(p.out_act + e0 + lo_off) = lds128(ab + EPI_PLANE_BYTES + off);
+        if (out_act) {
+          *reinterpret_cast<uint4*>(p.out_act + e0) = zero ? z4 : lds128(ab + off);
+          *reinterpret_cast<uint4*>(p.out_act + e0 + lo_off) = zero ? z4 : lds128(ab + EPI_PLANE_BYTES + off);
         }
       }
     }
   }
-  if (p.out_dense) {                                 // 4 rows x 128 B per store instruction
+  if (out_dense) {                                   // 4 rows x 128 B per store instruction
     const int d_row = lane >> 3, d_piece = lane & 7;
 #pragma unroll 1
     for (int i = 0; i < 8; ++i) {
@@ -278,6 +289,7 @@ __device__ __forceinline__ void epilogue_item(const TcParams& p, int tile, int c
 }
 
 // all items of this CTA for one epilogue warp
+template <int MODE>
 __device__ __forceinline__ void epilogue_warp(const TcParams& p, int total_tiles, int warp, int lane, uint32_t tmem_base,
                                               uint64_t* tfull_bar, uint64_t* tempty_bar, const float* s_bias, uint8_t* epi_base) {
   const int quad = warp & 3, group = warp >> 2;
@@ -288,7 +300,7 @@ __device__ __forceinline__ void epilogue_warp(const TcParams& p, int total_tiles
   for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it)
     for (int c = 0; c < nchunks; ++c)
       if (((it * nchunks + c) & 1) == group)
-        epilogue_item(p, tile, c, it, quad, lane, tmem_base, tfull_bar, tempty_bar, s_bias_u, stage_u);
+        epilogue_item<MODE>(p, tile, c, it, quad, lane, tmem_base, tfull_bar, tempty_bar, s_bias_u, stage_u);
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -427,7 +439,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
   } else {
     // ===================== epilogue warps (TMEM lane quadrant = warp % 4) =====================
-    epilogue_warp(p, total_tiles, warp, lane, tmem_base, tfull_bar, tempty_bar, s_bias, epi_base);
+    epilogue_warp<-1>(p, total_tiles, warp, lane, tmem_base, tfull_bar, tempty_bar, s_bias, epi_base);
   }
 
   tc_fence_before();
@@ -467,7 +479,7 @@ struct SlabParams {
 // row-shifted start needs no base-offset field (setting (addr>>7)&7 there gives wrong results).
 __device__ __forceinline__ uint64_t make_desc_shifted(uint32_t saddr, int row_bytes) { return make_desc(saddr, row_bytes); }
 
-template <int KC, bool RESIDENT>
+template <int KC, bool RESIDENT, int EPI_MODE>
 __global__ void __launch_bounds__(SL_THREADS, 1)
 conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapS,
                     const __grid_constant__ CUtensorMap mapWm, const __grid_constant__ CUtensorMap mapWs,
@@ -710,7 +722,7 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     __syncwarp();
   } else {
     pdl_wait();                               // identity-shortcut rows and the output planes
-    epilogue_warp(p, total_tiles, warp, lane, tmem_base, tfull_bar, tempty_bar, s_bias, epi_base);
+    epilogue_warp<EPI_MODE>(p, total_tiles, warp, lane, tmem_base, tfull_bar, tempty_bar, s_bias, epi_base);
   }
 
   tc_fence_before();
@@ -756,6 +768,15 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, int ch, 
 }
 
 static int pick_kc(int ch) { return (ch % 64 == 0) ? 64 : 32; }
+
+// floor(x / d) == __umulhi(x, m) >> sh for every x < 2^31 (d >= 2); m = 0 flags d == 1
+static void fast_div(unsigned d, unsigned* m, int* sh) {
+  if (d <= 1) { *m = 0; *sh = 0; return; }
+  int s = 0;
+  while ((1ull << s) < d) ++s;                       // s = ceil(log2 d) >= 1
+  *m = (unsigned)(((1ull << (31 + s)) / d) + 1);
+  *sh = s - 1;
+}
 
 }  // namespace sar
 
@@ -851,6 +872,8 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
   if (sp.slab_rows > 192) slab = false;
   // TMA epilogue: plane outputs of an unsplit map (every conv1 and all but the three stage-ending conv2's)
   // epilogue staging (64 KB): aliased onto the operand region when every CTA owns a single tile
+  fast_div((unsigned)p.Rimg, &p.div_rimg_m, &p.div_rimg_sh);
+  fast_div((unsigned)p.P, &p.div_p_m, &p.div_p_sh);
   p.mn_tiles = p.m_tiles * p.n_tiles;
   p.dense_zstride = (long long)d->B * d->H * d->W * d->cout;
   p.epi_alias = ((long long)p.mn_tiles * p.ksplit <= sms) ? 1 : 0;
@@ -898,9 +921,22 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
       launch_k(kern, dim3(grid), dim3(SL_THREADS), smem, (cudaStream_t)stream, mapA, mapS, mapWm, mapWs, p, sp);
       return 0;
     };
+    // epilogue mode: the residual-block combinations get compile-time flags (bit 0 identity shortcut, bit 1 raw out)
+    int mode = -1;
+    if (d->out_act && !d->out_dense && d->act_kind == 0 && !p.split) mode = (d->res ? 1 : 0) | (d->out_raw ? 2 : 0);
+    auto pick = [&](auto kc_tag, auto res_tag) -> int {
+      constexpr int KCv = decltype(kc_tag)::value;
+      constexpr bool RSv = decltype(res_tag)::value;
+      switch (mode) {
+        case 0: return launch(conv_tc_slab_kernel<KCv, RSv, 0>);
+        case 2: return launch(conv_tc_slab_kernel<KCv, RSv, 2>);
+        case 3: return launch(conv_tc_slab_kernel<KCv, RSv, 3>);
+        default: return launch(conv_tc_slab_kernel<KCv, RSv, -1>);
+      }
+    };
     int lrc;
-    if (p.kc_main == 64) lrc = sp.resident ? launch(conv_tc_slab_kernel<64, true>) : launch(conv_tc_slab_kernel<64, false>);
-    else lrc = sp.resident ? launch(conv_tc_slab_kernel<32, true>) : launch(conv_tc_slab_kernel<32, false>);
+    if (p.kc_main == 64) lrc = sp.resident ? pick(std::integral_constant<int, 64>{}, std::true_type{}) : pick(std::integral_constant<int, 64>{}, std::false_type{});
+    else lrc = sp.resident ? pick(std::integral_constant<int, 32>{}, std::true_type{}) : pick(std::integral_constant<int, 32>{}, std::false_type{});
     if (lrc) return lrc;
   } else {
     p.stages = p.epi_alias ? 3 : 2;
