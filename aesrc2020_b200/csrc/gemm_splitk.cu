@@ -83,7 +83,15 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, const float* 
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     float acc = bias ? __ldg(bias + (int)(i % N)) : 0.f;
-    for (int z = 0; z < splits; ++z) acc += ws[(size_t)z * total + i];
+    int z = 0;
+    for (; z + 8 <= splits; z += 8) {           // 8 independent loads in flight, summed in the fixed order z = 0, 1, 2, ...
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = ws[(size_t)(z + j) * total + i];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc += v[j];
+    }
+    for (; z < splits; ++z) acc += ws[(size_t)z * total + i];
     out[i] = acc;
   }
 }
