@@ -303,7 +303,7 @@ class SARNetEngine:
         from . import tc
         key = (B, S, C, role)
         if key not in self._seq_bufs:
-            self._seq_bufs[key] = tc.alloc_planes(1, B, S, C, False, self.device)
+            self._seq_bufs[key] = tc.alloc_rows(B * S, C, self.device)       # plain rows: a Dense has one tap, no halo
         return self._seq_bufs[key]
 
     def ln_planes(self, x, ln_name, role, want_dense=False):
@@ -314,19 +314,19 @@ class SARNetEngine:
         d = ops.layernorm(x, p[ln_name + "/gamma"], p[ln_name + "/beta"], planes=pl, want_dense=want_dense)
         return d, pl
 
-    def dense_planes(self, planes, name, act=None, bias_name=None, seq_shape=None):
-        """Dense over the channels of a planes tensor -> fp32 (B, S, Dout): planes is either a (1, B, S)
-        sequence map or (seq_shape=(B, S)) the ResNet's (B, H', W') map read as CNN2SEQ does (model.py:252)."""
+    def dense_planes(self, planes, name, seq_shape, act=None, bias_name=None, conv_map=False):
+        """Dense over the channels of a planes tensor -> fp32 (B, S, Dout): planes holds either plain rows
+        (B*S, C) or (conv_map) the ResNet's flat-pad (B, H', W') map read as CNN2SEQ does (model.py:252)."""
         from . import tc
         p = self.p
-        y = tc.dense_tc(planes, p[name + "/w_tc"], p[bias_name or (name + "/bias")], act=act)
-        B, S = seq_shape if seq_shape is not None else (planes.H, planes.W)
+        y = tc.dense_tc(planes, p[name + "/w_tc"], p[bias_name or (name + "/bias")], act=act, nopad=not conv_map)
+        B, S = seq_shape
         return y.reshape(B, S, -1)
 
-    def bigru_planes(self, planes, name, seq=True):
+    def bigru_planes(self, planes, name, seq_shape, seq=True):
         p = self.p
-        xp = self.dense_planes(planes, name, bias_name=name + "/ibias_cat")      # (B,S,6u)
-        B, S = xp.shape[0], xp.shape[1]
+        xp = self.dense_planes(planes, name, seq_shape, bias_name=name + "/ibias_cat")      # (B,S,6u)
+        B, S = seq_shape
         return ops.bigru(xp.reshape(B, S, 2, -1), p[name + "/rec"], p[name + "/rbias"], seq=seq)
 
     def embed(self, x):
@@ -400,9 +400,9 @@ class SARNetEngine:
         out: Dict[str, torch.Tensor] = {}
         wi = want_intermediates
         P0 = self.resnet.forward(x, as_planes=True)                             # relu(final BN), resnet.py:178/196
-        y = self.dense_planes(P0, "CNN_LIN", act="tanh", seq_shape=(B, S))      # CNN2SEQ + CNN_LIN, model.py:252-253
+        y = self.dense_planes(P0, "CNN_LIN", (B, S), act="tanh", conv_map=True)      # CNN2SEQ + CNN_LIN, model.py:252-253
         cnn, P1 = self.ln_planes(y, "CNN_LIN_LN", "cnn", want_dense=wi)
-        crnn, P2 = self.ln_planes(self.bigru_planes(P1, "CRNN"), "CRNN_LN", "crnn", want_dense=wi)
+        crnn, P2 = self.ln_planes(self.bigru_planes(P1, "CRNN", (B, S)), "CRNN_LN", "crnn", want_dense=wi)
         if wi:
             out["resnet_raw"], out["cnn_lin"], out["crnn"] = self.tc_unpack(P0), cnn, crnn
         return self._forward_tail(inputs, out, crnn, P2, want_intermediates)
@@ -420,8 +420,9 @@ class SARNetEngine:
         bn_stats = None
         if cfg.ctc_enable:                                                      # model.py:261-269
             if use_tc:
-                _, P3 = self.ln_planes(self.bigru_planes(crnn_planes, "CTC_BIGRU"), "CTC_BIGRU_LN", "ctc_bigru")
-                asr = ops.layernorm(self.dense_planes(P3, "CTC_DS", act="tanh"), p["CTC_DS_LN/gamma"], p["CTC_DS_LN/beta"])
+                S_ = self.plan.seq_len
+                _, P3 = self.ln_planes(self.bigru_planes(crnn_planes, "CTC_BIGRU", (B, S_)), "CTC_BIGRU_LN", "ctc_bigru")
+                asr = ops.layernorm(self.dense_planes(P3, "CTC_DS", (B, S_), act="tanh"), p["CTC_DS_LN/gamma"], p["CTC_DS_LN/beta"])
             else:
                 asr = ops.layernorm(self.bigru(crnn, "CTC_BIGRU"), p["CTC_BIGRU_LN/gamma"], p["CTC_BIGRU_LN/beta"])
                 asr = self.dense_ln(asr, "CTC_DS", "CTC_DS_LN")
@@ -435,7 +436,7 @@ class SARNetEngine:
         if cfg.ar_enable:                                                       # model.py:275-322
             P4 = None
             if use_tc:
-                y = self.dense_planes(crnn_planes, "AR_DS", act="tanh")
+                y = self.dense_planes(crnn_planes, "AR_DS", (B, self.plan.seq_len), act="tanh")
                 if cfg.mto == "bigru":
                     ar, P4 = self.ln_planes(y, "AR_DS_LN", "ar", want_dense=want_intermediates)
                 else:
@@ -445,7 +446,7 @@ class SARNetEngine:
             if cfg.mto == "avg":
                 integ = ops.avgpool(ar)
             elif cfg.mto == "bigru":
-                integ = self.bigru_planes(P4, "AR_MERGE", seq=False) if P4 is not None else self.bigru(ar, "AR_MERGE", seq=False)
+                integ = self.bigru_planes(P4, "AR_MERGE", (B, self.plan.seq_len), seq=False) if P4 is not None else self.bigru(ar, "AR_MERGE", seq=False)
             else:
                 G = cfg.ghost_clusters if cfg.mto == "gvlad" else 0
                 vplanes = None

@@ -97,8 +97,9 @@ def layernorm(x, gamma, beta, eps: float = LN_EPS, *, planes=None, want_dense: b
                                             float(eps), stream_ptr()), "sar_layernorm_fwd")
     else:
         assert planes.C == Cc and planes.B == 1 and planes.H * planes.W == rows and not planes.split
+        seg = planes.W if planes.rows != rows else 0       # flat-pad (1, B, S) map: a pad row per S rows; plain rows: none
         check(_shim.lib().sar_layernorm_planes_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(out), ptr(planes.t), planes.rows,
-                                                   planes.W, rows, Cc, float(eps), stream_ptr()),
+                                                   seg, rows, Cc, float(eps), stream_ptr()),
               "sar_layernorm_planes_fwd")
     _count(1)
     return out

@@ -191,13 +191,14 @@ def pack_dense_weights(kernel: np.ndarray) -> np.ndarray:
     return pack_weights(np.asarray(kernel).reshape(1, 1, din, dout))
 
 
-def dense_tc(a: Planes, w_packed: torch.Tensor, bias: torch.Tensor, *, act=None) -> torch.Tensor:
+def dense_tc(a: Planes, w_packed: torch.Tensor, bias: torch.Tensor, *, act=None, nopad: bool = False) -> torch.Tensor:
     """Dense on the channel axis of a planes tensor as a 1-tap tensor-core "convolution"
     (Dense of model.py:35-42 / the GRU input projections of model.py:44-50).
     Returns fp32 (a.B, a.H, a.W, Dout) in the plain layout (pad rows are skipped)."""
     dout = int(w_packed.shape[1])
     out = torch.empty((a.B, a.H, a.W, dout), device=a.t.device, dtype=torch.float32)
-    conv_tc(a, w_packed, bias, out_hw=(a.H, a.W), taps=([0], [0]), cout=dout, out_dense=out, act_kind=ACT_KIND[act])
+    conv_tc(a, w_packed, bias, out_hw=(a.H, a.W), taps=([0], [0]), cout=dout, out_dense=out, act_kind=ACT_KIND[act],
+            nopad=nopad)
     return out
 
 

@@ -315,7 +315,18 @@ def main():
     else:
         roof = {"bound": "tensor", "achieved": F / t_conv / 1e12, "peak": peaks["tflops"], "unit": "TFLOP/s"}
     roof["frac"] = roof["achieved"] / roof["peak"]
-    roof.update({"traffic": None, "kernel": "residual-block conv (36 launches/step for thin-ResNet34)",
+    # DRAM bytes per launch from the committed ncu pass of this workload (profiles/r1_conv_traffic_v6.json); ncu is
+    # never run inside the bench.  Only valid for the default workload it was captured on.
+    traffic = None
+    try:
+        if args.config == "cfg2" and B == 64:
+            with open(os.path.join(ROOT, "profiles", "r1_conv_traffic_v6.json")) as f:
+                traffic = json.load(f)["traffic_bytes_per_launch"]
+    except Exception:
+        traffic = None
+    roof.update({"traffic": traffic, "traffic_unit": "bytes/launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu, profiles/r1_conv_traffic_v6.json)",
+                 "algorithmic_bytes_per_launch": Bt / nconv,
+                 "kernel": "residual-block conv (36 launches/step for thin-ResNet34)",
                  "launches_per_step": nconv, "avg_launch_us": conv_ms * 1e3 / nconv, "conv_ms_per_step": conv_ms,
                  "share_of_step": conv_ms / eager_ms_per_step, "ms_per_step_region_b": eager_ms_per_step,
                  "timing": "external CUDA events (graph event-record nodes) around the 36 block-conv launches, read after each of K graph replays run right after the value region", "algorithmic_gflop_per_step": F / 1e9,
