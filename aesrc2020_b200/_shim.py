@@ -35,6 +35,8 @@ SIGNATURES = {
     "sar_planes_unpack_fwd": (c_int, [c_fp, c_fp] + [c_int] * 5 + [C.c_void_p]),
     "sar_maxpool_planes_fwd": (c_int, [c_fp, c_fp] + [c_int] * 10 + [C.c_void_p]),
     "sar_conv_tc_fwd": (c_int, [C.c_void_p, C.c_void_p]),
+    "sar_conv_tc_chain_workspace_bytes": (c_sz, [C.c_void_p, c_int]),
+    "sar_conv_tc_chain_fwd": (c_int, [C.c_void_p, c_int, C.c_void_p, c_sz, C.c_void_p]),
     "sar_stem_pool_fwd": (c_int, [c_fp] * 6 + [c_int] * 4 + [C.c_void_p]),
     "sar_maxpool2d_fwd": (c_int, [c_fp, c_fp] + [c_int] * 10 + [C.c_void_p]),
     "sar_affine_relu_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_ll, c_int, c_int, C.c_void_p]),

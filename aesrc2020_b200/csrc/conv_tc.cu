@@ -72,6 +72,11 @@ struct TcParams {
   int stages;                            // generic kernel: depth of the TMA ring (2 or 3)
   int ksplit, ksteps_split, mn_tiles;    // generic kernel, split-K (1-tap GEMMs with a long K): tile = z * mn_tiles + (mt, nt)
   long long dense_zstride;               // elements between the fp32 partial outputs of consecutive K slices
+  // chain kernel (several layers of one stage in ONE persistent launch, see conv_tc_chain_kernel)
+  int* flag_done;                        // [m_tiles] epilogue items finished per M tile of THIS layer (or null)
+  const int* flag_dep;                   // [m_tiles] the same counters of the layer this one reads (or null)
+  int flag_need;                         // items per M tile = 4 * Cout / 32
+  int epi_mode;                          // epilogue mode of this layer (-1, 0, 2, 3)
 };
 
 // ------------------------------------------------------------------ epilogue (shared by both kernels)
@@ -119,7 +124,10 @@ __device__ __noinline__ float tanh_precise(float x) { return tanhf(x); }
 // MODE < 0: every output option is a run-time flag.  MODE >= 0 fixes the combination at compile time (the hot
 // residual-block cases; the per-round flag tests were ~25 % of the executed instructions):
 //   bit 0 = identity shortcut, bit 1 = raw planes out, the activated planes (BN->ReLU) are always written.
-template <int MODE>
+// CHAIN (conv_tc_chain_kernel): the bias / BN vectors of the item's 32 columns are staged from global memory into a
+// per-warp area (s_bias_u, 32 floats apart), shortcut rows are read with ld.global.cg (another CTA wrote them
+// during this very kernel), and the finished item is published in the layer's per-M-tile counter.
+template <int MODE, bool CHAIN = false>
 __device__ __forceinline__ void epilogue_item(const TcParams& p, int tile, int c, int it, int quad, int lane,
                                            uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar,
                                            uint32_t s_bias_u, uint32_t stage_u) {
@@ -146,11 +154,27 @@ __device__ __forceinline__ void epilogue_item(const TcParams& p, int tile, int c
       const long long q = row0 + 8 * i + g_row;
       res_h[i] = make_uint4(0, 0, 0, 0); res_l[i] = make_uint4(0, 0, 0, 0);
       if (q < p.R) {
-        res_h[i] = __ldg(reinterpret_cast<const uint4*>(p.res + (size_t)q * p.Cout + g_col));
-        res_l[i] = __ldg(reinterpret_cast<const uint4*>(p.res + ((size_t)p.R + q) * p.Cout + g_col));
+        if (CHAIN) {
+          res_h[i] = __ldcg(reinterpret_cast<const uint4*>(p.res + (size_t)q * p.Cout + g_col));
+          res_l[i] = __ldcg(reinterpret_cast<const uint4*>(p.res + ((size_t)p.R + q) * p.Cout + g_col));
+        } else {
+          res_h[i] = __ldg(reinterpret_cast<const uint4*>(p.res + (size_t)q * p.Cout + g_col));
+          res_l[i] = __ldg(reinterpret_cast<const uint4*>(p.res + ((size_t)p.R + q) * p.Cout + g_col));
+        }
       }
     }
   }
+  if (CHAIN) {                                       // bias | scale | shift of columns n0+c0 .. +31 -> [3][32] floats
+    const int col = n0 + c0 + lane;
+    const float bv = p.bias ? __ldg(p.bias + col) : 0.f;
+    const float sv = p.act_scale ? __ldg(p.act_scale + col) : 1.f;
+    const float tv = p.act_shift ? __ldg(p.act_shift + col) : 0.f;
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_bias_u + (uint32_t)lane * 4u), "f"(bv) : "memory");
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_bias_u + 128u + (uint32_t)lane * 4u), "f"(sv) : "memory");
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_bias_u + 256u + (uint32_t)lane * 4u), "f"(tv) : "memory");
+    __syncwarp();
+  }
+  const uint32_t vstride = CHAIN ? 128u : (uint32_t)p.Cout * 4u;
   // TMEM side: lane -> row.  drow_p / drow_d: destination row of the plane / dense outputs; -1: not stored;
   // -2 - q: pad position of a non-split plane, row q is stored as zeros (pads must stay zero)
   const long long q = row0 + lane;
@@ -194,7 +218,7 @@ __device__ __forceinline__ void epilogue_item(const TcParams& p, int tile, int c
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
     }
-    const uint32_t vec = s_bias_u + (uint32_t)(n0 + c0 + 8 * g) * 4u;   // bias | scale | shift, Cout floats apart
+    const uint32_t vec = s_bias_u + (uint32_t)((CHAIN ? 0 : n0 + c0) + 8 * g) * 4u;   // bias | scale | shift, vstride bytes apart
     float v[8];
     {
       const uint4 b0 = lds128(vec), b1 = lds128(vec + 16);
@@ -223,8 +247,8 @@ __device__ __forceinline__ void epilogue_item(const TcParams& p, int tile, int c
     }
     if (out_act || out_dense) {
       if (act_kind == 0) {
-        const uint4 s0 = lds128(vec + (uint32_t)p.Cout * 4u), s1 = lds128(vec + (uint32_t)p.Cout * 4u + 16);
-        const uint4 t0 = lds128(vec + (uint32_t)p.Cout * 8u), t1 = lds128(vec + (uint32_t)p.Cout * 8u + 16);
+        const uint4 s0 = lds128(vec + vstride), s1 = lds128(vec + vstride + 16);
+        const uint4 t0 = lds128(vec + 2u * vstride), t1 = lds128(vec + 2u * vstride + 16);
         const float ss[8] = {__uint_as_float(s0.x), __uint_as_float(s0.y), __uint_as_float(s0.z), __uint_as_float(s0.w),
                              __uint_as_float(s1.x), __uint_as_float(s1.y), __uint_as_float(s1.z), __uint_as_float(s1.w)};
         const float tt[8] = {__uint_as_float(t0.x), __uint_as_float(t0.y), __uint_as_float(t0.z), __uint_as_float(t0.w),
@@ -284,6 +308,12 @@ __device__ __forceinline__ void epilogue_item(const TcParams& p, int tile, int c
     }
   }
   __syncwarp();                                      // staging is reused by this warp's next item
+  if (CHAIN && p.flag_done) {                        // publish: the rows this item wrote are visible GPU-wide
+    if (lane == 0) {
+      __threadfence();
+      atomicAdd(p.flag_done + mt, 1);
+    }
+  }
   EPI_STAMP(5)
 #undef EPI_STAMP
 }
@@ -734,6 +764,255 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) { p.dbg[62] = t_entry; p.dbg[63] = clock64(); }
 }
 
+// ------------------------------------------------------------------ the chain kernel
+// All stride-1 3x3 convolutions of one ResNet stage (conv2 of the first block, then conv1/conv2 of every further
+// block) as ONE persistent launch.  At small batches a stage-3/4 layer has fewer tiles than the chip has SMs and
+// pays its own launch, prologue and epilogue tail; here a CTA walks the layers ("phases") back to back, the
+// epilogue of one phase overlaps the mainloop of the next, and the M x N tiles of all phases fill all SMs.
+// There is no grid-wide barrier: a 3x3 tile of layer l reads the rows of M tiles m-1, m, m+1 of layer l-1, so the
+// TMA producer waits for those three per-M-tile counters (bumped by the epilogue warps with a release pattern:
+// stores, __syncwarp, __threadfence, atomicAdd; read with ld.acquire + fence.proxy.async before the TMA load).
+// Tiles are dealt to CTAs identically in every phase (tile = blockIdx.x + k * gridDim.x), all CTAs are resident
+// (grid <= #SMs), and dependencies only point to the previous phase: no deadlock.  Neighbouring tiles are never
+// more than one phase apart, which also makes the two-slot rotation of the activation buffers safe.
+// Weights stream through the TMA ring (non-resident form of conv_tc_slab_kernel), epilogue staging has its own
+// 64 KB, the per-item bias / BN vectors a 3 KB per-warp area.
+constexpr int CH_MAX = 12;
+struct ChainPhase { CUtensorMap mapA, mapS, mapWm, mapWs; TcParams p; };
+struct ChainParams {
+  int n_phases;
+  int* flags;                    // [n_phases][m_tiles] counters + [1] CTA exit counter (self-cleaning)
+  SlabParams sp;
+  ChainPhase ph[CH_MAX];
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <int KC>
+__global__ void __launch_bounds__(SL_THREADS, 1) conv_tc_chain_kernel(const __grid_constant__ ChainParams cp) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const SlabParams& sp = cp.sp;
+  const TcParams& g0 = cp.ph[0].p;                                     // geometry / tiling: identical in every phase
+  uint8_t* slab_base = smem;                                           // [nslab][2 planes][slab_bytes]
+  uint8_t* b_base = smem + (size_t)sp.nslab * 2 * sp.slab_bytes;       // [nring][2 planes][bplane_bytes]
+  uint8_t* epi_base = b_base + (size_t)sp.nring * 2 * sp.bplane_bytes; // [8 warps][EPI_WARP_BYTES]
+  uint8_t* vec_base = epi_base + EPI_BYTES;                            // [8 warps][3][32] floats
+  uint64_t* sfull_bar = reinterpret_cast<uint64_t*>(vec_base + 8 * 384);
+  uint64_t* sempty_bar = sfull_bar + SL_MAX_SLABS;
+  uint64_t* bfull_bar = sempty_bar + SL_MAX_SLABS;
+  uint64_t* bempty_bar = bfull_bar + SL_MAX_RING;
+  uint64_t* tfull_bar = bempty_bar + SL_MAX_RING;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int BN = g0.BN;
+  const uint32_t tmem_cols = (4 * BN <= 128) ? 128u : (4 * BN <= 256 ? 256u : 512u);
+  const int total_tiles = g0.m_tiles * g0.n_tiles;
+
+  if (warp == SL_WARP_TMA) {
+    constexpr int NBAR = 2 * SL_MAX_SLABS + 2 * SL_MAX_RING + 2 + 2;
+    for (int i = lane; i < NBAR; i += 32) {
+      const bool is_tempty = i >= NBAR - 2;
+      mbar_init(&sfull_bar[i], is_tempty ? 4u * (uint32_t)(BN >> 5) : 1u);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (lane == 0) { prefetch_tmap(&cp.ph[0].mapA); prefetch_tmap(&cp.ph[0].mapWm); }
+  }
+  if (warp == SL_WARP_MMA) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+  pdl_wait();
+  pdl_trigger();
+
+  if (warp == SL_WARP_TMA) {
+    // ===================== TMA producer =====================
+    int sb = 0; uint32_t sphase = 0;        // slab ring
+    int bs = 0; uint32_t bphase = 0;        // weight ring
+    for (int ph = 0; ph < cp.n_phases; ++ph) {
+      const ChainPhase& P = cp.ph[ph];
+      const TcParams& p = P.p;
+      const int n_main = p.ntaps * p.chunks_main;
+      const int n_chunks = p.chunks_main + p.chunks_sc;
+      if (lane == 0 && ph + 1 < cp.n_phases) { prefetch_tmap(&cp.ph[ph + 1].mapA); prefetch_tmap(&cp.ph[ph + 1].mapWm); }
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+        const long long q0 = (long long)mt * TC_BM;
+        const int n0 = nt * BN;
+        if (p.flag_dep) {                    // rows of M tiles mt-1 .. mt+1 of the previous layer must be complete
+          const int lo = mt > 0 ? mt - 1 : 0, hi = mt + 1 < p.m_tiles ? mt + 1 : p.m_tiles - 1;
+          const long long t0 = clock64();
+          for (int mm = lo; mm <= hi; ++mm)
+            while (ld_acquire_gpu(p.flag_dep + mm) < p.flag_need)
+              if (clock64() - t0 > 4000000000LL) __trap();     // a protocol bug traps instead of hanging the GPU
+          asm volatile("fence.proxy.async;" ::: "memory");
+          __syncwarp();
+        }
+        for (int c = 0; c < n_chunks; ++c) {
+          const bool main = c < p.chunks_main;
+          const int kc = main ? p.kc_main : p.kc_sc;
+          const int rows = main ? sp.slab_rows : TC_BM;
+          mbar_wait(&sempty_bar[sb], sphase ^ 1);
+          if (elect_one()) {
+            const uint32_t dst = smem_u32(slab_base + (size_t)sb * 2 * sp.slab_bytes);
+            mbar_expect_tx(&sfull_bar[sb], (uint32_t)(2 * rows * kc * 2));
+            if (main) {
+              const int row0 = (int)(q0 - sp.lead);
+              tma_load_3d(&P.mapA, dst, &sfull_bar[sb], c * kc, row0, 0);
+              tma_load_3d(&P.mapA, dst + sp.slab_bytes, &sfull_bar[sb], c * kc, row0, 1);
+            } else {
+              const int ch = c - p.chunks_main;
+              tma_load_3d(&P.mapS, dst, &sfull_bar[sb], ch * kc, (int)q0, p.sc_plane);
+              tma_load_3d(&P.mapS, dst + sp.slab_bytes, &sfull_bar[sb], ch * kc, (int)q0, p.sc_plane + 1);
+            }
+          }
+          __syncwarp();
+          if (++sb == sp.nslab) { sb = 0; sphase ^= 1; }
+          const CUtensorMap* wm = main ? &P.mapWm : &P.mapWs;
+          for (int tap = 0; tap < (main ? p.ntaps : 1); ++tap) {
+            const int kofs = main ? (tap * p.chunks_main + c) * p.kc_main : n_main * p.kc_main + (c - p.chunks_main) * p.kc_sc;
+            mbar_wait(&bempty_bar[bs], bphase ^ 1);
+            if (elect_one()) {
+              const uint32_t b_hi = smem_u32(b_base + (size_t)bs * 2 * sp.bplane_bytes);
+              mbar_expect_tx(&bfull_bar[bs], (uint32_t)(2 * BN * kc * 2));
+              tma_load_3d(wm, b_hi, &bfull_bar[bs], kofs, n0, 0);
+              tma_load_3d(wm, b_hi + (uint32_t)(BN * kc * 2), &bfull_bar[bs], kofs, n0, 1);
+            }
+            __syncwarp();
+            if (++bs == sp.nring) { bs = 0; bphase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == SL_WARP_MMA) {
+    // ===================== MMA issuer (see conv_tc_slab_kernel) =====================
+    if (elect_one()) {
+      const uint32_t idesc_n = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      const uint32_t idesc_2n = (1u << 4) | ((uint32_t)(BN >> 2) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      constexpr uint32_t ROWB = KC * 2, ROW16 = ROWB >> 4;
+      constexpr uint32_t DHI = ((8 * ROWB) >> 4) | (1u << 14) | ((ROWB == 128 ? 2u : 4u) << 29);
+      const uint32_t a_base0 = ((smem_u32(slab_base) & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t a_slab16 = (uint32_t)(2 * sp.slab_bytes) >> 4, a_lo16 = (uint32_t)sp.slab_bytes >> 4;
+      const uint32_t b_base0 = ((smem_u32(b_base) & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t b_slot16 = (uint32_t)(2 * sp.bplane_bytes) >> 4;
+      const uint32_t p_row16 = (uint32_t)g0.P * ROW16;
+      const uint32_t tap0_16 = (uint32_t)(sp.lead - g0.P - 1) * ROW16;
+      int sb = 0; uint32_t sphase = 0;
+      int bs = 0; uint32_t bphase = 0;
+      int it = 0;
+      for (int ph = 0; ph < cp.n_phases; ++ph) {
+        const TcParams& p = cp.ph[ph].p;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+          const int as = it & 1;
+          const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+          mbar_wait(&tempty_bar[as], aphase ^ 1);
+          tc_fence_after();
+          const uint32_t acc0 = tmem_base + (uint32_t)(as * 2 * BN);
+          const uint32_t acc1 = acc0 + (uint32_t)BN;
+          uint32_t acc_on = 0;
+          for (int c = 0; c < p.chunks_main; ++c) {
+            mbar_wait(&sfull_bar[sb], sphase);
+            tc_fence_after();
+            uint32_t a_row = a_base0 + (uint32_t)sb * a_slab16 + tap0_16;
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+              for (int kw = 0; kw < 3; ++kw) {
+                mbar_wait(&bfull_bar[bs], bphase);
+                tc_fence_after();
+                const uint32_t b0 = b_base0 + (uint32_t)bs * b_slot16;
+                const uint32_t a0 = a_row + (uint32_t)kw * ROW16;
+#pragma unroll
+                for (int kk = 0; kk < KC / 16; ++kk) {
+                  const uint64_t dah = ((uint64_t)DHI << 32) | (a0 + 2u * kk), dal = ((uint64_t)DHI << 32) | (a0 + a_lo16 + 2u * kk);
+                  const uint64_t dbh = ((uint64_t)DHI << 32) | (b0 + 2u * kk);
+                  umma_f16(acc0, dah, dbh, idesc_2n, acc_on);
+                  umma_f16(acc1, dal, dbh, idesc_n, 1u);
+                  acc_on = 1u;
+                }
+                umma_commit(&bempty_bar[bs]);
+                if (++bs == sp.nring) { bs = 0; bphase ^= 1; }
+              }
+              a_row += p_row16;
+            }
+            umma_commit(&sempty_bar[sb]);
+            if (p.chunks_sc == 0 && c == p.chunks_main - 1) umma_commit(&tfull_bar[as]);
+            if (++sb == sp.nslab) { sb = 0; sphase ^= 1; }
+          }
+          for (int c = 0; c < p.chunks_sc; ++c) {
+            const uint32_t rowb = (uint32_t)p.kc_sc * 2;
+            const uint32_t dhi_s = ((8 * rowb) >> 4) | (1u << 14) | ((rowb == 128 ? 2u : 4u) << 29);
+            mbar_wait(&sfull_bar[sb], sphase);
+            tc_fence_after();
+            const uint32_t a0 = a_base0 + (uint32_t)sb * a_slab16;
+            mbar_wait(&bfull_bar[bs], bphase);
+            tc_fence_after();
+            const uint32_t b0 = b_base0 + (uint32_t)bs * b_slot16;
+            for (int kk = 0; kk < p.kc_sc / 16; ++kk) {
+              const uint64_t dah = ((uint64_t)dhi_s << 32) | (a0 + 2u * kk), dal = ((uint64_t)dhi_s << 32) | (a0 + a_lo16 + 2u * kk);
+              const uint64_t dbh = ((uint64_t)dhi_s << 32) | (b0 + 2u * kk);
+              umma_f16(acc0, dah, dbh, idesc_2n, 1u);
+              umma_f16(acc1, dal, dbh, idesc_n, 1u);
+            }
+            umma_commit(&bempty_bar[bs]);
+            if (++bs == sp.nring) { bs = 0; bphase ^= 1; }
+            umma_commit(&sempty_bar[sb]);
+            if (c == p.chunks_sc - 1) umma_commit(&tfull_bar[as]);
+            if (++sb == sp.nslab) { sb = 0; sphase ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue warps =====================
+    const int quad = warp & 3, group = warp >> 2;
+    const uint32_t stage_u = smem_u32(epi_base + (size_t)warp * EPI_WARP_BYTES);
+    const uint32_t vec_u = smem_u32(vec_base + (size_t)warp * 384);
+    const int nchunks = BN >> 5;
+    int it = 0;
+    for (int ph = 0; ph < cp.n_phases; ++ph) {
+      const TcParams& p = cp.ph[ph].p;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it)
+        for (int c = 0; c < nchunks; ++c)
+          if (((it * nchunks + c) & 1) == group) {
+            switch (p.epi_mode) {
+              case 0: epilogue_item<0, true>(p, tile, c, it, quad, lane, tmem_base, tfull_bar, tempty_bar, vec_u, stage_u); break;
+              case 3: epilogue_item<3, true>(p, tile, c, it, quad, lane, tmem_base, tfull_bar, tempty_bar, vec_u, stage_u); break;
+              default: epilogue_item<-1, true>(p, tile, c, it, quad, lane, tmem_base, tfull_bar, tempty_bar, vec_u, stage_u); break;
+            }
+          }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == SL_WARP_MMA) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
+  }
+  // self-cleaning counters: the last CTA to leave zeroes them for the next launch
+  __shared__ int s_last;
+  const int nflags = cp.n_phases * g0.m_tiles;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(cp.flags + nflags, 1) == (int)gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last)
+    for (int i = threadIdx.x; i <= nflags; i += SL_THREADS) cp.flags[i] = 0;
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -780,8 +1059,9 @@ static void fast_div(unsigned d, unsigned* m, int* sh) {
 
 }  // namespace sar
 
-extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
-  using namespace sar;
+namespace sar {
+// argument checks + the layer description shared by sar_conv_tc_fwd and sar_conv_tc_chain_fwd
+static int fill_params(const sar_tc_conv* d, TcParams& p) {
   SAR_REQUIRE(d, SAR_ERR_BAD_ARG, "sar_conv_tc_fwd: null descriptor");
   SAR_REQUIRE(d->a && d->w && d->bias, SAR_ERR_BAD_ARG, "sar_conv_tc_fwd: null a/w/bias");
   SAR_REQUIRE(d->ntaps >= 1 && d->ntaps <= 9, SAR_ERR_BAD_ARG, "sar_conv_tc_fwd: ntaps must be 1..9");
@@ -798,7 +1078,6 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
                   (!d->out_dense || aligned16(d->out_dense)),
               SAR_ERR_ALIGN, "sar_conv_tc_fwd: pointers must be 16-byte aligned");
 
-  TcParams p{};
   p.ntaps = d->ntaps;
   p.kc_main = pick_kc(d->a_ch);
   p.chunks_main = d->a_ch / p.kc_main;
@@ -842,6 +1121,14 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
     SAR_REQUIRE(p.chunks_main % p.ksplit == 0, SAR_ERR_BAD_ARG, "sar_conv_tc_fwd: ksplit must divide a_ch / %d", p.kc_main);
   }
   p.ksteps_split = p.ksplit > 1 ? p.chunks_main / p.ksplit : 0;
+  return SAR_OK;
+}
+}  // namespace sar
+
+extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
+  using namespace sar;
+  TcParams p{};
+  { const int frc = fill_params(d, p); if (frc) return frc; }
   const int ktot = d->ntaps * d->a_ch + (d->s ? d->s_ch : 0);
   // slab path: plain 3x3 stride-1 taps on a non-split tensor whose halo'd slab fits shared memory
   bool slab = d->ntaps == 9 && d->a_planes == 2;
@@ -946,4 +1233,108 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
     launch_k(conv_tc_kernel, dim3(grid), dim3(TC_THREADS), smem, (cudaStream_t)stream, mapA, mapS, mapWm, mapWs, p);
   }
   return check_launch("sar_conv_tc_fwd");
+}
+
+extern "C" size_t sar_conv_tc_chain_workspace_bytes(const sar_tc_conv* first, int n) {
+  if (!first || n <= 0) return 0;
+  const long long R = (long long)first->B * (first->H + 1) * (first->W + 1);
+  const long long m_tiles = (R + sar::TC_BM - 1) / sar::TC_BM;
+  return (size_t)(n * m_tiles + 1) * sizeof(int);
+}
+
+extern "C" int sar_conv_tc_chain_fwd(const sar_tc_conv* descs, int n, void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace sar;
+  SAR_REQUIRE(descs && n >= 1 && n <= CH_MAX, SAR_ERR_BAD_ARG, "sar_conv_tc_chain_fwd: need 1..%d layers", CH_MAX);
+  SAR_REQUIRE(workspace && workspace_bytes >= sar_conv_tc_chain_workspace_bytes(descs, n), SAR_ERR_WORKSPACE,
+              "sar_conv_tc_chain_fwd: workspace too small");
+  static thread_local ChainParams cp;          // ~10 KB: kept off the stack
+  static_assert(sizeof(ChainParams) < 32000, "ChainParams must fit the kernel parameter space");
+  cp.n_phases = n;
+  cp.flags = reinterpret_cast<int*>(workspace);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int kc_max = 32;
+  for (int i = 0; i < n; ++i) {
+    const sar_tc_conv* d = descs + i;
+    TcParams& p = cp.ph[i].p;
+    p = TcParams{};
+    { const int frc = fill_params(d, p); if (frc) return frc; }
+    SAR_REQUIRE(d->ntaps == 9 && d->a_planes == 2 && !d->nopad && p.ksplit == 1 && !d->out_dense, SAR_ERR_UNSUPPORTED,
+                "sar_conv_tc_chain_fwd: layer %d is not a stride-1 3x3 convolution with plane outputs", i);
+    for (int t = 0; t < 9; ++t)
+      SAR_REQUIRE(d->tap_plane[t] == 0 && d->tap_row_off[t] == (t / 3 - 1) * p.P + (t % 3 - 1), SAR_ERR_UNSUPPORTED,
+                  "sar_conv_tc_chain_fwd: layer %d: not the stride-1 tap pattern", i);
+    SAR_REQUIRE(d->B == descs->B && d->H == descs->H && d->W == descs->W && d->cout == descs->cout && d->a_ch == descs->a_ch,
+                SAR_ERR_BAD_ARG, "sar_conv_tc_chain_fwd: layer %d: all layers of a chain share geometry and channel counts", i);
+    SAR_REQUIRE(!d->s || i == 0, SAR_ERR_UNSUPPORTED, "sar_conv_tc_chain_fwd: only the first layer may carry a projection shortcut");
+    if (p.kc_main > kc_max) kc_max = p.kc_main;
+    if (d->s && p.kc_sc > kc_max) kc_max = p.kc_sc;
+  }
+  TcParams& g0 = cp.ph[0].p;
+  const int cout = descs->cout;
+  // N tile: 64 columns when possible -- the weight ring shares shared memory with the epilogue staging, and the
+  // M x N tiles of consecutive phases pipeline, so narrow tiles fill the SMs without a round-quantisation loss
+  const int BN = (cout % 64 == 0) ? 64 : 32;
+  SlabParams sp{};
+  sp.lead = g0.P + 1;
+  sp.slab_rows = (TC_BM + 2 * g0.P + 2 + 7) & ~7;
+  SAR_REQUIRE(sp.slab_rows <= 192, SAR_ERR_UNSUPPORTED, "sar_conv_tc_chain_fwd: map too wide for the slab path (W=%d)", descs->W);
+  sp.slab_bytes = (sp.slab_rows * kc_max * 2 + 1023) & ~1023;
+  if (sp.slab_bytes < TC_BM * kc_max * 2) sp.slab_bytes = TC_BM * kc_max * 2;
+  sp.bplane_bytes = BN * kc_max * 2;
+  sp.resident = 0;
+  sp.nslab = 2;
+  const size_t fixed = 1024 + 1024 + 640 + EPI_BYTES + 8 * 384;
+  const size_t budget = 227 * 1024 - fixed;
+  const size_t slab1 = 2 * (size_t)sp.slab_bytes;
+  SAR_REQUIRE(budget > 2 * slab1 + 4 * (size_t)sp.bplane_bytes, SAR_ERR_UNSUPPORTED, "sar_conv_tc_chain_fwd: shared memory budget");
+  size_t left = budget - 2 * slab1;
+  if (g0.chunks_main >= 2 && left >= slab1 + 6 * 2 * (size_t)sp.bplane_bytes) { sp.nslab = 3; left -= slab1; }
+  sp.nring = (int)(left / (2 * (size_t)sp.bplane_bytes));
+  if (sp.nring > SL_MAX_RING) sp.nring = SL_MAX_RING;
+  cp.sp = sp;
+  const int m_tiles = g0.m_tiles;
+  for (int i = 0; i < n; ++i) {
+    const sar_tc_conv* d = descs + i;
+    ChainPhase& P = cp.ph[i];
+    TcParams& p = P.p;
+    p.BN = BN; p.n_tiles = cout / BN; p.mn_tiles = p.m_tiles * p.n_tiles;
+    fast_div((unsigned)p.Rimg, &p.div_rimg_m, &p.div_rimg_sh);
+    fast_div((unsigned)p.P, &p.div_p_m, &p.div_p_sh);
+    p.epi_alias = 0;
+    p.dbg = nullptr;
+    p.flag_done = cp.flags + (size_t)i * m_tiles;
+    p.flag_dep = i > 0 ? cp.flags + (size_t)(i - 1) * m_tiles : nullptr;
+    p.flag_need = 4 * (cout / 32);
+    p.epi_mode = -1;
+    if (d->out_act && d->act_kind == 0 && !p.split) {
+      const int m = (d->res ? 1 : 0) | (d->out_raw ? 2 : 0);
+      if (m == 0 || m == 3) p.epi_mode = m;
+    }
+    const int ktot = 9 * d->a_ch + (d->s ? d->s_ch : 0);
+    int rc;
+    if ((rc = make_map(&P.mapA, d->a, d->a_rows, d->a_ch, d->a_planes, p.kc_main, sp.slab_rows))) return rc;
+    if ((rc = make_map(&P.mapWm, d->w, cout, ktot, 2, p.kc_main, BN))) return rc;
+    if (d->s) {
+      SAR_REQUIRE(d->s_rows > 0 && d->s_planes >= 2 && d->s_plane >= 0 && d->s_plane + 1 < d->s_planes, SAR_ERR_BAD_ARG,
+                  "sar_conv_tc_chain_fwd: bad shortcut operand");
+      if ((rc = make_map(&P.mapS, d->s, d->s_rows, d->s_ch, d->s_planes, p.kc_sc, TC_BM))) return rc;
+      if ((rc = make_map(&P.mapWs, d->w, cout, ktot, 2, p.kc_sc, BN))) return rc;
+    } else {
+      P.mapS = P.mapA; P.mapWs = P.mapWm;
+    }
+  }
+  const int tiles = g0.m_tiles * (cout / BN);
+  const int grid = tiles < sms ? tiles : sms;
+  const size_t smem = fixed + (size_t)sp.nslab * slab1 + (size_t)sp.nring * 2 * sp.bplane_bytes;
+  auto launch = [&](auto kern) -> int {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("sar_conv_tc_chain_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    launch_k(kern, dim3(grid), dim3(SL_THREADS), smem, (cudaStream_t)stream, cp);
+    return 0;
+  };
+  const int lrc = g0.kc_main == 64 ? launch(conv_tc_chain_kernel<64>) : launch(conv_tc_chain_kernel<32>);
+  if (lrc) return lrc;
+  return check_launch("sar_conv_tc_chain_fwd");
 }

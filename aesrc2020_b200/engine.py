@@ -97,6 +97,9 @@ class ResNetTC:
         self._bufs: Dict[tuple, list] = {}
         self._rot: Dict[tuple, int] = {}
         self.record_events = None
+        import os as _os
+        # stages whose stride-1 layers run as one persistent chain launch (SAR_CHAIN_STAGES="" disables)
+        self.chain_stages = {int(x) for x in _os.environ.get("SAR_CHAIN_STAGES", "2,3,4").split(",") if x.strip()}
 
         def put(name, arr, dtype=np.float32):
             self.p[name] = torch.from_numpy(np.ascontiguousarray(arr, dtype=dtype)).to(device)
@@ -156,32 +159,61 @@ class ResNetTC:
             ext = torch.cuda.is_current_stream_capturing()
             ev = (torch.cuda.Event(enable_timing=True, external=ext), torch.cuda.Event(enable_timing=True, external=ext))
             ev[0].record()
+        # The stride-1 3x3 layers of a stage (conv2 of its first block, then conv1/conv2 of every further block)
+        # go out as ONE persistent launch (tc.conv_tc_chain) when the stage is in self.chain_stages; everything
+        # else (the stage's first conv1: strided, or 64 -> 32 channels in stage 1) is a launch of its own.
+        pending: list = []
+        stage = 0
+
+        def flush():
+            if not pending:
+                return
+            if len(pending) == 1:
+                tc.conv_launch(pending[0])
+            else:
+                key = ("chain", B, stage, len(pending))
+                if key not in self._bufs:
+                    self._bufs[key] = tc.chain_workspace(pending, self.device)
+                tc.conv_tc_chain(pending, self._bufs[key])
+            pending.clear()
+
+        def emit(desc, chainable):
+            if chainable and stage in self.chain_stages:
+                pending.append(desc)
+            else:
+                flush()
+                tc.conv_launch(desc)
+
         for i, b in enumerate(pl.blocks):
             nxt = pl.blocks[i + 1] if i + 1 < len(pl.blocks) else None
             c1, c2 = b.conv1, b.conv2
+            first = i == 0 or c1.stride == 2
+            if first:
+                flush()
+                stage += 1
             c1_act = self._buf(B, c1.hout, c1.wout, c1.cout, False, "c1")
-            tc.conv_tc(cur_act, p[b.name + "/w1"], p[b.name + "/b1"], out_hw=(c1.hout, c1.wout),
-                       taps=tc.tap_table(3, 3, c1.stride, c1.pad_t, c1.pad_l, c1.wout), cout=c1.cout,
-                       out_act=c1_act, act=self.bn(c2.pre_bn))
+            emit(tc.conv_desc(cur_act, p[b.name + "/w1"], p[b.name + "/b1"], out_hw=(c1.hout, c1.wout),
+                              taps=tc.tap_table(3, 3, c1.stride, c1.pad_t, c1.pad_l, c1.wout), cout=c1.cout,
+                              out_act=c1_act, act=self.bn(c2.pre_bn)), chainable=not first)
             taps2 = tc.tap_table(3, 3, 1, 1, 1, c2.wout)
+            common = dict(out_hw=(c2.hout, c2.wout), taps=taps2, cout=c2.cout, short=cur_raw if b.short else None,
+                          res=None if b.short else cur_raw)
             if nxt is not None:
                 ns = nxt.conv1.stride == 2
                 nraw = self._buf(B, c2.hout, c2.wout, c2.cout, ns, "raw")
                 nact = self._buf(B, c2.hout, c2.wout, c2.cout, ns, "act")
-                tc.conv_tc(c1_act, p[b.name + "/w2"], p[b.name + "/b2"], out_hw=(c2.hout, c2.wout), taps=taps2,
-                           cout=c2.cout, short=cur_raw if b.short else None, res=None if b.short else cur_raw,
-                           out_raw=nraw, out_act=nact, act=self.bn(nxt.conv1.pre_bn))
+                emit(tc.conv_desc(c1_act, p[b.name + "/w2"], p[b.name + "/b2"], out_raw=nraw, out_act=nact,
+                                  act=self.bn(nxt.conv1.pre_bn), **common), chainable=True)
                 cur_raw, cur_act = nraw, nact
             elif as_planes:
                 out_dense = self._buf(B, c2.hout, c2.wout, c2.cout, False, "final")
-                tc.conv_tc(c1_act, p[b.name + "/w2"], p[b.name + "/b2"], out_hw=(c2.hout, c2.wout), taps=taps2,
-                           cout=c2.cout, short=cur_raw if b.short else None, res=None if b.short else cur_raw,
-                           act=self.bn(pl.final_bn), out_act=out_dense)
+                emit(tc.conv_desc(c1_act, p[b.name + "/w2"], p[b.name + "/b2"], act=self.bn(pl.final_bn),
+                                  out_act=out_dense, **common), chainable=True)
             else:
                 out_dense = torch.empty((B, c2.hout, c2.wout, c2.cout), device=self.device, dtype=torch.float32)
-                tc.conv_tc(c1_act, p[b.name + "/w2"], p[b.name + "/b2"], out_hw=(c2.hout, c2.wout), taps=taps2,
-                           cout=c2.cout, short=cur_raw if b.short else None, res=None if b.short else cur_raw,
-                           act=self.bn(pl.final_bn), out_dense=out_dense)
+                emit(tc.conv_desc(c1_act, p[b.name + "/w2"], p[b.name + "/b2"], act=self.bn(pl.final_bn),
+                                  out_dense=out_dense, **common), chainable=False)
+        flush()
         if ev is not None:
             ev[1].record()
             self.record_events.append(ev)

@@ -145,11 +145,11 @@ def tap_table(kh: int, kw: int, stride: int, pad_t: int, pad_l: int, W_out: int)
     return offs, planes
 
 
-def conv_tc(a: Planes, w_packed: torch.Tensor, bias: torch.Tensor, *, out_hw: Tuple[int, int], taps, cout: int,
+def conv_desc(a: Planes, w_packed: torch.Tensor, bias: torch.Tensor, *, out_hw: Tuple[int, int], taps, cout: int,
             short: Optional[Planes] = None, res: Optional[Planes] = None, out_raw: Optional[Planes] = None,
             out_act: Optional[Planes] = None, act=None, out_dense: Optional[torch.Tensor] = None, dbg=None,
-            act_kind: int = 0, nopad: bool = False, ksplit: int = 1):
-    """sar_conv_tc_fwd.  taps = (row_offsets, plane_bases)."""
+            act_kind: int = 0, nopad: bool = False, ksplit: int = 1) -> sar_tc_conv:
+    """The `sar_tc_conv` descriptor of one layer.  taps = (row_offsets, plane_bases)."""
     d = sar_tc_conv()
     d.a, d.a_rows, d.a_ch, d.a_planes = ptr(a.t), a.rows, a.C, a.nplanes
     offs, planes = taps
@@ -181,7 +181,30 @@ def conv_tc(a: Planes, w_packed: torch.Tensor, bias: torch.Tensor, *, out_hw: Tu
     d.dbg = ptr(dbg) if dbg is not None else None
     d.act_kind = int(act_kind)
     d.nopad, d.ksplit = (1 if nopad else 0), int(ksplit)
+    return d
+
+
+def conv_launch(d: sar_tc_conv):
     check(_shim.lib().sar_conv_tc_fwd(C.byref(d), stream_ptr()), "sar_conv_tc_fwd")
+    ops._count(1)
+
+
+def conv_tc(*args, **kwargs):
+    """sar_conv_tc_fwd (arguments of conv_desc)."""
+    conv_launch(conv_desc(*args, **kwargs))
+
+
+def chain_workspace(descs, device) -> torch.Tensor:
+    arr = (sar_tc_conv * len(descs))(*descs)
+    n = _shim.lib().sar_conv_tc_chain_workspace_bytes(arr, len(descs))
+    return torch.zeros((n + 3) // 4, device=device, dtype=torch.int32)
+
+
+def conv_tc_chain(descs, workspace: torch.Tensor):
+    """sar_conv_tc_chain_fwd: the stride-1 3x3 layers of one stage in one persistent launch."""
+    arr = (sar_tc_conv * len(descs))(*descs)
+    check(_shim.lib().sar_conv_tc_chain_fwd(arr, len(descs), ptr(workspace), workspace.numel() * 4, stream_ptr()),
+          "sar_conv_tc_chain_fwd")
     ops._count(1)
 
 

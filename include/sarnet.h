@@ -136,6 +136,14 @@ typedef struct sar_tc_conv {
 } sar_tc_conv;
 int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream);
 
+/* Up to 12 stride-1 3x3 layers of ONE ResNet stage (same B, H, W, a_ch == cout; plane outputs; only descs[0] may
+ * carry a projection shortcut `s`) as a single persistent launch: layer i+1 reads what layer i wrote (its `a` is
+ * layer i's out_act), tiles synchronise through per-M-tile counters in `workspace` (device memory, zero-filled once
+ * by the caller, sar_conv_tc_chain_workspace_bytes(); the kernel leaves it zeroed) instead of kernel boundaries.
+ * Results are bitwise those of n sar_conv_tc_fwd calls. */
+size_t sar_conv_tc_chain_workspace_bytes(const sar_tc_conv* first, int n);
+int sar_conv_tc_chain_fwd(const sar_tc_conv* descs, int n, void* workspace, size_t workspace_bytes, void* stream);
+
 /* MaxPooling2D(3x3, strides 2, 'same') -- resnet.py:174,192.  Padded cells never win. */
 int sar_maxpool2d_fwd(const float* x, float* out, int B, int H, int W, int C, int Ho, int Wo,
                       int k, int stride, int pad_t, int pad_l, void* stream);

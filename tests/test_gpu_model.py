@@ -163,3 +163,24 @@ def test_predict_host_paths_agree_bitwise(cuda_device):
             assert np.array_equal(a, c.cpu().numpy())
             assert np.array_equal(a, d)
     assert all(np.array_equal(a, b) for a, b in zip(ref[0], model.predict(xs[0], batch_size=4)))
+
+
+def test_stage_chain_launch_is_bitwise_the_layer_by_layer_path(cuda_device):
+    """sar_conv_tc_chain_fwd (all stride-1 3x3 layers of a stage in one persistent launch, tiles synchronised by
+    per-M-tile counters) vs one sar_conv_tc_fwd launch per layer: identical bits, also on repeated calls (the
+    counters are self-cleaning) and with every stage chained."""
+    from aesrc2020_b200 import model as mdl, utils as us
+    kw = dict(disc_enable=True, res_type="res34", res_filters=32, mto="gvlad", vlad_clusters=8, ghost_clusters=2,
+              metric_loss="arcface", margin=0.3)
+    model, _ = mdl.SAR_Net((500, 80, 1), **kw)
+    model.use_graph = False
+    x, _ = us.synthetic_batch(model.config, 6, seed=11)
+    rn = model.engine().resnet
+    rn.chain_stages = set()
+    want = model.predict(x, batch_size=6)
+    for stages in ({2, 3, 4}, {1, 2, 3, 4}, {3}):
+        rn.chain_stages = stages
+        for _ in range(2):
+            got = model.predict(x, batch_size=6)
+            for a, b in zip(want, got):
+                assert np.array_equal(a, b), stages
