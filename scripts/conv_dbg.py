@@ -5,19 +5,19 @@ from aesrc2020_b200 import model as mdl, utils as us, tc
 B = 64
 with contextlib.redirect_stdout(io.StringIO()):
     model, _ = mdl.SAR_Net((500, 80, 1), disc_enable=True, res_type="res34", res_filters=32, mto="gvlad", vlad_clusters=64, ghost_clusters=8, metric_loss="arcface")
-eng = model.engine(); rn = eng.resnet
+eng = model.engine(); rn = eng.resnet; rn.chain_stages = set()
 x, _ = us.synthetic_batch(model.config, B, seed=1)
 xd = model._to_device("x_data", x["x_data"])
 calls = []
-orig = tc.conv_tc
+orig = tc.conv_desc
 dbgs = []
 def timed(*a, **k):
     d = torch.zeros(64, dtype=torch.int64, device="cuda"); dbgs.append(d)
-    orig(*a, dbg=d, **k)
+    return orig(*a, dbg=d, **k)
 rn.forward(xd); torch.cuda.synchronize()
-tc.conv_tc = timed
+tc.conv_desc = timed
 rn.forward(xd); torch.cuda.synchronize()
-for li in (2, 3, 9, 17, 31):
+for li in (16, 17, 31):
     d = dbgs[li].cpu().tolist()
     t0 = d[62]
     print("layer", li, "entry 0  prologue done %d  exit %d" % (d[61] - t0, d[63] - t0))
