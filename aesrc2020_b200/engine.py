@@ -97,6 +97,7 @@ class ResNetTC:
         self._bufs: Dict[tuple, list] = {}
         self._rot: Dict[tuple, int] = {}
         self.record_events = None
+        self.lane = 0            # buffer namespace: concurrent micro-batch lanes never share activation buffers
         import os as _os
         # stages whose stride-1 layers run as one persistent chain launch (SAR_CHAIN_STAGES="" disables)
         self.chain_stages = {int(x) for x in _os.environ.get("SAR_CHAIN_STAGES", "2,3,4").split(",") if x.strip()}
@@ -129,7 +130,7 @@ class ResNetTC:
 
     def _buf(self, B, H, W, C, split, role):
         """2-slot rotation of zero-initialised plane buffers per (geometry, role)."""
-        key = (B, H, W, C, bool(split), role)
+        key = (self.lane, B, H, W, C, bool(split), role)
         if key not in self._bufs:
             self._bufs[key] = [self.tc.alloc_planes(B, H, W, C, split, self.device) for _ in range(2)]
             self._rot[key] = 0
@@ -171,14 +172,16 @@ class ResNetTC:
             if len(pending) == 1:
                 tc.conv_launch(pending[0])
             else:
-                key = ("chain", B, stage, len(pending))
+                key = ("chain", self.lane, B, stage, len(pending))
                 if key not in self._bufs:
                     self._bufs[key] = tc.chain_workspace(pending, self.device)
                 tc.conv_tc_chain(pending, self._bufs[key])
             pending.clear()
 
         def emit(desc, chainable):
-            if chainable and stage in self.chain_stages:
+            # lanes run concurrently on separate streams: a chain launch (CTAs spinning on tile counters of CTAs of
+            # the SAME launch) needs its whole grid resident, which two lanes sharing the SMs cannot promise
+            if chainable and stage in self.chain_stages and self.lane == 0:
                 pending.append(desc)
             else:
                 flush()
@@ -237,6 +240,12 @@ class SARNetEngine:
         # Dense layers / GRU input projections on the tensor cores (1-tap conv_tc) when the residual blocks are
         self.dense_tc = conv_path == "tc" and cfg.hidden_dim % 64 == 0 and self.plan.cout % 32 == 0
         self._seq_bufs: Dict[tuple, object] = {}
+        self.lane = 0
+        self._lane_streams: List[torch.cuda.Stream] = []
+        self._lane_done: List[torch.cuda.Event] = []
+        self._lane_sinks: Dict[tuple, Dict[str, torch.Tensor]] = {}
+        self._lane_in: Optional[torch.cuda.Event] = None
+        self._sink = None
         self._prepare(weights)
 
     # ------------------------------------------------------------------ weight preparation
@@ -333,7 +342,7 @@ class SARNetEngine:
     # tensor-core variants: sequence activations travel as hi/lo planes of a (1, B, S) map
     def _seq_planes(self, B, S, C, role):
         from . import tc
-        key = (B, S, C, role)
+        key = (self.lane, B, S, C, role)
         if key not in self._seq_bufs:
             self._seq_bufs[key] = tc.alloc_rows(B * S, C, self.device)       # plain rows: a Dense has one tap, no halo
         return self._seq_bufs[key]
@@ -370,12 +379,12 @@ class SARNetEngine:
 
     # ------------------------------------------------------------------ forward
     # ------------------------------------------------------------------ CUDA-graph replay
-    def forward_graphed(self, inputs: Dict[str, torch.Tensor], tag: str = "") -> Dict[str, torch.Tensor]:
+    def forward_graphed(self, inputs: Dict[str, torch.Tensor], tag="", sink=None) -> Dict[str, torch.Tensor]:
         """Same as forward(), but the ~45 launches of a step are captured once per input signature
         into a CUDA graph and replayed (the step is launch-bound at small batches).  Inputs are
         copied into the graph's static buffers; the returned tensors are the graph's static outputs
         (valid until the next replay of the same signature)."""
-        key = (tag,) + tuple(sorted((k, tuple(v.shape), str(v.dtype)) for k, v in inputs.items()))
+        key = (tag, self.lane) + tuple(sorted((k, tuple(v.shape), str(v.dtype)) for k, v in inputs.items()))
         entry = self._graphs.get(key)
         if entry is None:
             static_in = {k: torch.empty_like(v, device=self.device).copy_(v) for k, v in inputs.items()}   # inputs may be pinned host tensors
@@ -384,14 +393,14 @@ class SARNetEngine:
             side.wait_stream(cur)
             with torch.cuda.stream(side):           # warm-up: allocates plane buffers, sets func attributes
                 for _ in range(2):
-                    self.forward(static_in)
+                    self.forward(static_in, sink=sink)
             cur.wait_stream(side)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                static_out = self.forward(static_in)
+                static_out = self.forward(static_in, sink=sink)
             entry = (graph, static_in, static_out)
-            if len(self._graphs) >= 8:
+            if len(self._graphs) >= 16:
                 self._graphs.pop(next(iter(self._graphs)))
             self._graphs[key] = entry
         graph, static_in, static_out = entry
@@ -400,7 +409,66 @@ class SARNetEngine:
         graph.replay()
         return static_out
 
-    def forward(self, inputs: Dict[str, torch.Tensor], want_intermediates: bool = False) -> Dict[str, torch.Tensor]:
+    # ------------------------------------------------------------------ concurrent micro-batch lanes
+    def forward_lanes(self, inputs: Dict[str, torch.Tensor], lanes: int, tag="") -> Dict[str, torch.Tensor]:
+        """One step as `lanes` contiguous micro-batches, each a captured CUDA graph replayed on a stream of its own.
+        Utterances are independent on this path (inference BN), so results are bitwise those of the unsplit step.
+        Why: at B=64 most kernels are latency-bound and leave SMs idle (stage 3-4 convs fill 68-99 of 148 SMs, the
+        Bi-GRU recurrence is 48 dependent steps); a second lane's kernels fill them, and with host inputs lane
+        k+1's H2D runs under lane k's compute.  Every lane writes its rows of shared per-sample output buffers
+        (`sink`); the batch loss vector is one sar_loss_reduce_fwd over all rows after the lanes join."""
+        B = int(inputs["x_data"].shape[0])
+        lanes = max(1, min(int(lanes), B))
+        if lanes == 1:
+            return self.forward_graphed(inputs, tag)
+        cur = torch.cuda.current_stream()
+        while len(self._lane_streams) < lanes:
+            self._lane_streams.append(torch.cuda.Stream(device=self.device))
+            self._lane_done.append(torch.cuda.Event())
+        if self._lane_in is None:
+            self._lane_in = torch.cuda.Event()
+        bounds = [(l * B // lanes, (l + 1) * B // lanes) for l in range(lanes)]
+        sink = self._lane_sinks.get((B, lanes))
+        self._lane_in.record(cur)
+        try:
+            for l, (b0, b1) in enumerate(bounds):
+                st = self._lane_streams[l]
+                st.wait_event(self._lane_in)
+                with torch.cuda.stream(st):
+                    self._set_lane(l + 1)                       # lane 0 is the unsplit path
+                    sl = {k: v[b0:b1] for k, v in inputs.items()}
+                    if sink is None:                             # first call: learn the per-sample outputs from an eager probe
+                        probe = self.forward({k: v.to(self.device) for k, v in sl.items()})
+                        st.synchronize()
+                        sink = {k: torch.zeros((B,) + tuple(v.shape[1:]), device=self.device, dtype=v.dtype)
+                                for k, v in probe.items() if k != "loss_vector"}
+                        if "_ctc_loss" in sink:                  # (B,1) model output = the kernel's (B,) vector
+                            sink["y_ctc_loss"] = sink["_ctc_loss"].view(B, 1)
+                        self._lane_sinks[(B, lanes)] = sink
+                    self.forward_graphed(sl, tag=(tag, "lanes", B, lanes), sink={k: t[b0:b1] for k, t in sink.items()})
+                    self._lane_done[l].record(st)
+        finally:
+            self._set_lane(0)
+        for l in range(lanes):
+            cur.wait_event(self._lane_done[l])
+        out = {k: v for k, v in sink.items() if not k.startswith("_")}
+        out["loss_vector"] = ops.loss_reduce(sink.get("_sample_stats"), sink.get("_ctc_loss"), sink.get("_bn_stats"), B=B)
+        return out
+
+    def _set_lane(self, lane: int):
+        self.lane = lane
+        self.resnet.lane = lane
+
+    def forward(self, inputs: Dict[str, torch.Tensor], want_intermediates: bool = False, sink=None) -> Dict[str, torch.Tensor]:
+        """`sink` (forward_lanes): per-sample outputs are written into these preallocated rows and the batch loss
+        vector is left to the caller."""
+        self._sink = sink
+        try:
+            return self._forward(inputs, want_intermediates)
+        finally:
+            self._sink = None
+
+    def _forward(self, inputs: Dict[str, torch.Tensor], want_intermediates: bool = False) -> Dict[str, torch.Tensor]:
         cfg, p = self.cfg, self.p
         x = inputs["x_data"]
         if x.dim() == 3:
@@ -447,6 +515,7 @@ class SARNetEngine:
         cfg, p = self.cfg, self.p
         B = inputs["x_data"].shape[0]
         use_tc = crnn_planes is not None
+        sink = self._sink or {}
         stats = None
         ctc_loss = None
         bn_stats = None
@@ -460,7 +529,9 @@ class SARNetEngine:
                 asr = self.dense_ln(asr, "CTC_DS", "CTC_DS_LN")
             logits = ops.dense(asr, p["ctc_pred/kernel"], p["ctc_pred/bias"])
             ctc_loss, status, probs = ops.ctc(logits, inputs["x_ctc_label"], inputs["x_ctc_in_len"],
-                                              inputs["x_ctc_out_len"], want_probs=want_intermediates)
+                                              inputs["x_ctc_out_len"], want_probs=want_intermediates,
+                                              loss=sink.get("_ctc_loss"), status=sink.get("ctc_status"))
+            out["_ctc_loss"] = ctc_loss
             out["y_ctc_loss"] = ctc_loss.reshape(B, 1)
             out["ctc_status"] = status
             if want_intermediates:
@@ -484,16 +555,16 @@ class SARNetEngine:
                 vplanes = None
                 if getattr(self, "embed_ksplit", 0):
                     from . import tc
-                    key = (B, cfg.vlad_clusters * ar.shape[-1], "vlad")
+                    key = (self.lane, B, cfg.vlad_clusters * ar.shape[-1], "vlad")
                     if key not in self._seq_bufs:
-                        self._seq_bufs[key] = tc.alloc_rows(B, key[1], self.device)
+                        self._seq_bufs[key] = tc.alloc_rows(B, key[2], self.device)
                     vplanes = self._seq_bufs[key]
                 integ = ops.vlad(ar, p[cfg.mto + "/w_assign"], p[cfg.mto + "/b_assign"], p[cfg.mto + "/centers"],
                                  cfg.vlad_clusters, G, planes=vplanes, want_dense=want_intermediates or vplanes is None)
             if cfg.mto in ("vlad", "gvlad") and getattr(self, "embed_ksplit", 0):
                 from . import tc
                 emb = tc.gemm_splitk_tc(vplanes, p["AR_EMBEDDING/w_tc"], p["AR_EMBEDDING/bias_folded"],
-                                        p["AR_EMBEDDING/zero_bias"], self.embed_ksplit)
+                                        p["AR_EMBEDDING/zero_bias"], self.embed_ksplit, out=sink.get("embedding"))
             else:
                 emb = self.embed(integ)
             if want_intermediates:
@@ -504,8 +575,12 @@ class SARNetEngine:
                                        "y_accent/kernel", "y_accent/bias"))
             h = ops.head(emb, cls, wd=p.get("y_disc/w") if cfg.disc_enable else None, onehot=onehot,
                          n_classes=cfg.accent_classes, head_kind=cfg.metric_loss if cfg.disc_enable else None,
-                         margin=cfg.margin)
+                         margin=cfg.margin,
+                         out={k: sink.get(n) for k, n in (("y_accent", "y_accent"), ("y_accent_logits", "y_accent_logits"),
+                                                          ("y_disc", "y_disc"), ("y_disc_logits", "y_disc_logits"),
+                                                          ("sample_stats", "_sample_stats"))})
             stats = h.pop("sample_stats")
+            out["_sample_stats"] = stats
             out.update(h)
             if cfg.disc_enable and cfg.bn_dim:
                 bn = ops.dense(emb, p["AR_BN_DS/kernel"], p["AR_BN_DS/bias"], act="relu")
@@ -513,6 +588,14 @@ class SARNetEngine:
                 hb = ops.head(None, None, emb_d=bn, wd=p["y_disc_bn/w"], onehot=onehot, n_classes=cfg.accent_classes,
                               head_kind=cfg.metric_loss, margin=cfg.margin)
                 bn_stats = hb["sample_stats"]
+                out["_bn_stats"] = bn_stats
                 out["y_disc_bn"] = hb["y_disc"]
+        if self._sink is not None:
+            # anything a kernel did not write in place (the views of y_ctc_loss share _ctc_loss's rows)
+            for k, dst in self._sink.items():
+                src = out.get(k)
+                if src is not None and src.data_ptr() != dst.data_ptr():
+                    dst.copy_(src)
+            return dict(self._sink)
         out["loss_vector"] = ops.loss_reduce(stats, ctc_loss, bn_stats, B=B)
         return out

@@ -13,6 +13,7 @@ outputs back; with device tensors it is zero-copy.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence, Union
 
 import numpy as np
@@ -26,6 +27,7 @@ from .engine import SARNetEngine, fold_bn
 from ._shim import SarnetError
 
 ArrayLike = Union[np.ndarray, torch.Tensor]
+AUTO_LANES = 1       # default micro-batch lanes for batches >= 32 (SARModel.lanes = 0)
 
 
 # =========================
@@ -269,6 +271,9 @@ class SARModel:
         self._pin_events: Dict[str, torch.cuda.Event] = {}
         self._pinned_out: Optional[torch.Tensor] = None
         self.use_graph = True          # replay a CUDA graph of the step (captured once per batch shape)
+        # concurrent micro-batch lanes per step (engine.forward_lanes); 0 = automatic (see _lanes_for)
+        self.lanes = int(os.environ.get("SAR_LANES", "0"))
+        self._pipe = None              # predict_generator's staging slots (see _pipe_state)
 
     # -- Keras-like surface
     @property
@@ -355,6 +360,13 @@ class SARModel:
             return dict(zip(self.config.input_names(), x))
         return {"x_data": x}
 
+    def _lanes_for(self, B: int) -> int:
+        """Micro-batch lanes of a graphed step: batches too small to fill the GPU with one kernel at a time are
+        split so that independent kernels of the lanes overlap (measured: profiles/r1_lanes.md)."""
+        if self.lanes > 0:
+            return min(self.lanes, B)
+        return AUTO_LANES if B >= 32 else 1
+
     def forward_device(self, x, want_intermediates=False, graph: bool = None) -> Dict[str, torch.Tensor]:
         """One forward on the device.  `graph` (default: self.use_graph) replays a captured CUDA graph
         of the step; the returned tensors are then the graph's static outputs."""
@@ -372,7 +384,7 @@ class SARModel:
                     src[k] = self._to_device(k, v)
                 else:
                     src[k] = self._to_host_tensor(k, v)
-            out = self.engine().forward_graphed(src)
+            out = self.engine().forward_lanes(src, self._lanes_for(len(xd["x_data"])))
             self._mark_h2d([k for k, v in xd.items() if not isinstance(v, torch.Tensor)])
         else:
             dev_in = {k: self._to_device(k, v) for k, v in xd.items()}
@@ -413,6 +425,118 @@ class SARModel:
                 off += o.numel()
         cat = (lambda c: torch.cat(c, 0)) if on_device else (lambda c: np.concatenate(c, 0))
         res = [cat(c) for c in chunks]
+        return res[0] if len(res) == 1 else res
+
+    # -- pipelined prediction over a batch generator
+    PIPE_DEPTH = 2
+
+    def _pipe_state(self):
+        if self._pipe is None:
+            dev = torch.device(self.device)
+            D = self.PIPE_DEPTH
+            self._pipe = {
+                "copy": torch.cuda.Stream(device=dev),
+                "h2d": [torch.cuda.Event() for _ in range(D)], "free": [None] * D,
+                "done": [torch.cuda.Event() for _ in range(D)],
+                "stage": [dict() for _ in range(D)], "pin_in": [dict() for _ in range(D)], "pin_out": [None] * D,
+            }
+        return self._pipe
+
+    def _submit(self, x, slot: int):
+        """Enqueue one batch without waiting for it: H2D on the copy stream into staging slot `slot`, the graphed
+        step and the D2H of its outputs on the compute stream.  Returns the handle _collect() waits on."""
+        ps = self._pipe_state()
+        xd = self._as_dict(x)
+        missing = [k for k in self.config.input_names() if k not in xd]
+        if missing:
+            raise ValueError("missing model inputs: %s" % missing)
+        B = len(xd["x_data"])
+        cur = torch.cuda.current_stream()
+        stage, pins = ps["stage"][slot], ps["pin_in"][slot]
+        with torch.cuda.stream(ps["copy"]):
+            if ps["free"][slot] is not None:
+                ps["copy"].wait_event(ps["free"][slot])      # the step that last read this slot has consumed it
+            for k, v in xd.items():
+                want = torch.int32 if k in ("x_ctc_in_len", "x_ctc_out_len") else torch.float32
+                if isinstance(v, torch.Tensor):
+                    src = v
+                else:
+                    a = np.ascontiguousarray(v).astype(np.int32 if want == torch.int32 else np.float32, copy=False)
+                    src = torch.from_numpy(a)
+                    if not src.is_pinned():                  # pageable: through this slot's own pinned buffer (the
+                        pin = pins.get(k)                    # wait on `free` above also covers its previous H2D)
+                        if pin is None or pin.shape != src.shape or pin.dtype != src.dtype:
+                            pin = pins[k] = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+                        if ps["free"][slot] is not None:
+                            ps["free"][slot].synchronize()
+                        pin.copy_(src)
+                        src = pin
+                dst = stage.get(k)
+                if dst is None or dst.shape != src.shape:
+                    dst = stage[k] = torch.empty(src.shape, dtype=want, device=self.device)
+                dst.copy_(src, non_blocking=True)
+            ps["h2d"][slot].record(ps["copy"])
+        cur.wait_event(ps["h2d"][slot])
+        out = self.engine().forward_lanes({k: stage[k] for k in xd}, self._lanes_for(B))
+        if ps["free"][slot] is None:
+            ps["free"][slot] = torch.cuda.Event()
+        ps["free"][slot].record(cur)
+        outs = [out[name] for name in self._outputs]
+        if self.config.ctc_enable:
+            outs.append(out["ctc_status"])
+        tot = sum(o.numel() for o in outs)
+        pin = ps["pin_out"][slot]
+        if pin is None or pin.numel() < tot:
+            pin = ps["pin_out"][slot] = torch.empty((max(tot, 4096),), dtype=torch.float32, pin_memory=True)
+        off = 0
+        views = []
+        for o in outs:
+            dst = pin[off:off + o.numel()]
+            dst = dst.view(torch.int32) if o.dtype == torch.int32 else dst
+            dst.view(o.shape).copy_(o, non_blocking=True)
+            views.append(dst.view(o.shape))
+            off += o.numel()
+        ps["done"][slot].record(cur)
+        return slot, views
+
+    def _collect(self, handle) -> List[np.ndarray]:
+        slot, views = handle
+        self._pipe_state()["done"][slot].synchronize()
+        if self.config.ctc_enable and bool((views[-1] != 0).any()):
+            raise SarnetError("CTC: infeasible or out-of-range label sequence in batch "
+                              "(Not enough time for target transition sequence)")
+        return [v.numpy().copy() for v in views[:len(self._outputs)]]
+
+    def predict_generator(self, generator, steps=None, max_queue_size=10, workers=1, use_multiprocessing=False, verbose=0):
+        """Keras `Model.predict_generator` (the forward-only twin of the `fit_generator(generator, max_queue_size=20)`
+        loop the reference trains with, train.py:38-44): `generator` yields one batch per step -- an input dict /
+        list as utils.data_loader builds it (utils.py:102-116), or the (inputs, targets) tuple data_generator
+        yields.  Batches are pipelined PIPE_DEPTH deep: while step i runs, step i+1's inputs are DMA'd from pinned
+        host memory by the copy engine and step i-1's outputs are read back, so the host<->device copies of every
+        step stay off the kernels' critical path.  Returns the outputs concatenated over steps, as predict() does."""
+        from collections import deque
+        it = iter(generator)
+        pending = deque()
+        chunks: List[List] = [[] for _ in self._outputs]
+
+        def drain():
+            for i, a in enumerate(self._collect(pending.popleft())):
+                chunks[i].append(a)
+        n = 0
+        while steps is None or n < steps:
+            try:
+                x = next(it)
+            except StopIteration:
+                break
+            if isinstance(x, tuple):
+                x = x[0]
+            if len(pending) >= self.PIPE_DEPTH:
+                drain()
+            pending.append(self._submit(x, n % self.PIPE_DEPTH))
+            n += 1
+        while pending:
+            drain()
+        res = [np.concatenate(c, 0) for c in chunks] if n else [np.zeros((0,), np.float32) for _ in chunks]
         return res[0] if len(res) == 1 else res
 
     def evaluate(self, x, y: Optional[Dict[str, ArrayLike]] = None, batch_size=32, group=None):

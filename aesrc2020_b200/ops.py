@@ -163,27 +163,36 @@ def gemm_splitk(a, w, bias=None):
 
 
 def head(emb, cls_w=None, *, emb_d=None, wd=None, onehot=None, n_classes=8, head_kind=None,
-         margin=0.3, s=FACE_S, gamma=CIRCLE_GAMMA, want_logits=True):
-    """sar_head_fwd.  cls_w = (w1,b1,w2,b2,w3,b3) or None.  Returns a dict of tensors."""
+         margin=0.3, s=FACE_S, gamma=CIRCLE_GAMMA, want_logits=True, out=None):
+    """sar_head_fwd.  cls_w = (w1,b1,w2,b2,w3,b3) or None.  Returns a dict of tensors; `out` may hold
+    preallocated (B, n) / (B, 4) tensors under the same names (rows of a larger batch buffer)."""
     B = (emb if emb is not None else emb_d).shape[0]
     dev = (emb if emb is not None else emb_d).device
     D = emb.shape[1] if emb is not None else 0
     n = n_classes
     hk = HEAD[head_kind]
     res = {}
+    out = out or {}
+
+    def new(name, cols):
+        t = out.get(name)
+        if t is None:
+            return torch.empty((B, cols), device=dev, dtype=torch.float32)
+        assert tuple(t.shape) == (B, cols) and t.is_contiguous() and t.dtype == torch.float32, name
+        return t
     w1 = b1 = w2 = b2 = w3 = b3 = None
     H1 = H2 = 0
     if cls_w is not None:
         w1, b1, w2, b2, w3, b3 = cls_w
         H1, H2 = w1.shape[1], w2.shape[1]
-        res["y_accent"] = torch.empty((B, n), device=dev, dtype=torch.float32)
+        res["y_accent"] = new("y_accent", n)
         if want_logits:
-            res["y_accent_logits"] = torch.empty((B, n), device=dev, dtype=torch.float32)
+            res["y_accent_logits"] = new("y_accent_logits", n)
     if hk:
-        res["y_disc"] = torch.empty((B, n), device=dev, dtype=torch.float32)
+        res["y_disc"] = new("y_disc", n)
         if want_logits:
-            res["y_disc_logits"] = torch.empty((B, n), device=dev, dtype=torch.float32)
-    res["sample_stats"] = torch.empty((B, 4), device=dev, dtype=torch.float32)
+            res["y_disc_logits"] = new("y_disc_logits", n)
+    res["sample_stats"] = new("sample_stats", 4)
     check(_shim.lib().sar_head_fwd(ptr(emb), D, ptr(w1), ptr(b1), H1, ptr(w2), ptr(b2), H2, ptr(w3), ptr(b3),
                                    ptr(emb_d), emb_d.shape[1] if emb_d is not None else 0, ptr(wd),
                                    ptr(onehot), n, hk, float(margin), float(s), float(gamma),
@@ -194,15 +203,18 @@ def head(emb, cls_w=None, *, emb_d=None, wd=None, onehot=None, n_classes=8, head
     return res
 
 
-def ctc(logits, labels, in_len, lab_len, *, want_probs=False):
+def ctc(logits, labels, in_len, lab_len, *, want_probs=False, loss=None, status=None):
     """logits (B,S,C) pre-softmax; labels (B,Lmax) float32; lens (B,) or (B,1) int32."""
     logits = _f32(logits)
     labels = _f32(labels)
     B, S, Cc = logits.shape
     in_len = in_len.reshape(-1).to(torch.int32).contiguous()
     lab_len = lab_len.reshape(-1).to(torch.int32).contiguous()
-    loss = torch.empty((B,), device=logits.device, dtype=torch.float32)
-    status = torch.empty((B,), device=logits.device, dtype=torch.int32)
+    if loss is None:
+        loss = torch.empty((B,), device=logits.device, dtype=torch.float32)
+    if status is None:
+        status = torch.empty((B,), device=logits.device, dtype=torch.int32)
+    assert loss.numel() == B and status.numel() == B and loss.is_contiguous() and status.is_contiguous()
     probs = torch.empty_like(logits) if want_probs else None
     check(_shim.lib().sar_ctc_fwd(ptr(logits), ptr(labels), ptr(in_len), ptr(lab_len), ptr(loss), ptr(probs),
                                   ptr(status), B, S, Cc, labels.shape[1], stream_ptr()), "sar_ctc_fwd")

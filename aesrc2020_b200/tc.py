@@ -231,7 +231,8 @@ def alloc_rows(M: int, Cc: int, device) -> Planes:
     return Planes(t, 1, M, 1, Cc, False)
 
 
-def gemm_splitk_tc(a: Planes, w_packed: torch.Tensor, bias: torch.Tensor, zero_bias: torch.Tensor, ksplit: int) -> torch.Tensor:
+def gemm_splitk_tc(a: Planes, w_packed: torch.Tensor, bias: torch.Tensor, zero_bias: torch.Tensor, ksplit: int,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out (M, N) = a (M, K) @ w (K, N) + bias on the tensor cores with the long K axis cut into `ksplit` slices
     (AR_EMBEDDING, model.py:286-289: M = batch, K = clusters * hidden = 16384): slice z is one tile of the 1-tap
     conv_tc kernel writing fp32 partial products, sar_splitk_reduce_fwd sums them in a fixed order and adds the bias."""
@@ -239,7 +240,9 @@ def gemm_splitk_tc(a: Planes, w_packed: torch.Tensor, bias: torch.Tensor, zero_b
     ws = torch.empty((ksplit, M, N), device=a.t.device, dtype=torch.float32)
     conv_tc(a, w_packed, zero_bias, out_hw=(a.H, a.W), taps=([0], [0]), cout=N, out_dense=ws, act_kind=ACT_KIND[None],
             nopad=True, ksplit=ksplit)
-    out = torch.empty((M, N), device=a.t.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty((M, N), device=a.t.device, dtype=torch.float32)
+    assert tuple(out.shape) == (M, N) and out.is_contiguous()
     check(_shim.lib().sar_splitk_reduce_fwd(ptr(ws), ptr(bias), ptr(out), M, N, ksplit, stream_ptr()), "sar_splitk_reduce_fwd")
     ops._count(1)
     return out

@@ -184,3 +184,68 @@ def test_stage_chain_launch_is_bitwise_the_layer_by_layer_path(cuda_device):
             got = model.predict(x, batch_size=6)
             for a, b in zip(want, got):
                 assert np.array_equal(a, b), stages
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ctc", [False, True])
+def test_micro_batch_lanes_are_bitwise_the_single_stream_step(cuda_device, ctc):
+    """engine.forward_lanes: the step as 2 / 3 / 4 concurrent micro-batch graphs on separate streams returns bitwise
+    the outputs AND the batch loss vector of the single-graph step (utterances are independent; the loss reduce runs
+    once over all rows after the lanes join), step after step with changing inputs, for host and device inputs."""
+    from aesrc2020_b200 import model as mdl, utils as us
+    kw = dict(ctc_enable=ctc, disc_enable=True, res_type="res34", res_filters=32, mto="gvlad", vlad_clusters=64,
+              ghost_clusters=8, metric_loss="circleloss" if ctc else "arcface")
+    model, _ = mdl.SAR_Net((500, 80, 1), **kw)
+    eng = model.engine()
+    batches = [us.synthetic_batch(model.config, 50, seed=40 + i)[0] for i in range(3)]   # 50: lanes of unequal size
+    model.lanes = 1
+    ref = [model.predict(x, batch_size=50) for x in batches]
+    dev = [{k: model._to_device(k, v).clone() for k, v in x.items()} for x in batches]
+    ref_vec = [eng.forward_graphed(d)["loss_vector"].cpu().numpy().copy() for d in dev]
+    for lanes in (2, 3, 4):
+        model.lanes = lanes
+        for rep in range(2):
+            for x, d, r, rv in zip(batches, dev, ref, ref_vec):
+                got = model.predict(x, batch_size=50)
+                assert all(np.array_equal(a, b) for a, b in zip(got, r)), (lanes, rep)
+                out = eng.forward_lanes(d, lanes)
+                assert np.array_equal(out["loss_vector"].cpu().numpy(), rv), (lanes, rep)
+                assert np.array_equal(out["y_accent"].cpu().numpy(), r[0])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["cfg2_gvlad_arcface", "cfg5_gvlad_circle_ctc"])
+def test_predict_generator_pipeline_is_bitwise_predict(cuda_device, name):
+    """Keras-style predict_generator (H2D of step i+1 and D2H of step i-1 under step i's kernels): bitwise the
+    per-batch predict() outputs, for (inputs, targets) tuples, plain dicts, pinned and pageable arrays, a ragged last
+    batch and `steps` shorter than the generator."""
+    from aesrc2020_b200 import utils as us
+    model, _, _ = build(name)
+    sizes = [8, 8, 8, 8, 5]
+    batches = [us.synthetic_batch(model.config, b, seed=70 + i) for i, b in enumerate(sizes)]
+    want = [model.predict(x, batch_size=len(x["x_data"])) for x, _ in batches]
+    want = [w if isinstance(w, list) else [w] for w in want]
+    cat = [np.concatenate([w[i] for w in want], 0) for i in range(len(want[0]))]
+
+    def gen(pinned, tuples):
+        for x, y in batches:
+            xx = us.pinned_like(x) if pinned else x
+            yield (xx, y) if tuples else xx
+    for pinned in (False, True):
+        got = model.predict_generator(gen(pinned, tuples=pinned))
+        got = got if isinstance(got, list) else [got]
+        assert all(np.array_equal(a, b) for a, b in zip(got, cat)), pinned
+    got = model.predict_generator(gen(True, True), steps=3)
+    got = got if isinstance(got, list) else [got]
+    assert all(np.array_equal(a, b[:24]) for a, b in zip(got, cat))
+
+
+def test_predict_generator_raises_on_infeasible_ctc(cuda_device):
+    from aesrc2020_b200 import _shim
+    model, x, _ = build("cfg5_gvlad_circle_ctc")
+    bad = {k: v.copy() for k, v in x.items()}
+    bad["x_ctc_out_len"][:] = 40
+    bad["x_ctc_label"][:, :40] = 7.0
+    with pytest.raises(_shim.SarnetError):
+        model.predict_generator(iter([x, bad, x]))
+    assert np.array_equal(model.predict_generator(iter([x]))[0], model.predict(x)[0])     # the pipeline survives the error
