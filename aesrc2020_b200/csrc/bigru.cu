@@ -24,6 +24,7 @@
 //     global store sits in front of the per-step release).
 // Both directions and all utterance groups run concurrently (grid = 8 * groups * 2 CTAs).
 #include <cooperative_groups.h>
+#include <stdlib.h>
 #include "tc_common.cuh"
 
 namespace cg = cooperative_groups;
@@ -283,12 +284,20 @@ bigru_kernel(const float* __restrict__ xp, const float* __restrict__ rec, const 
 
 }  // namespace sar
 
+namespace sar { int bigru_tc_launch(const float*, const float*, const float*, float*, int, int, int, cudaStream_t); }
+
 extern "C" int sar_bigru_fwd(const float* xp, const float* rec, const float* rbias, float* out,
                              int B, int S, int u, int seq, void* stream) {
   using namespace sar;
   SAR_REQUIRE(xp && rec && rbias && out, SAR_ERR_BAD_ARG, "sar_bigru_fwd: null pointer");
   SAR_REQUIRE(B > 0 && S > 0, SAR_ERR_BAD_ARG, "sar_bigru_fwd: non-positive dimension");
   SAR_REQUIRE(u == GRU_U, SAR_ERR_UNSUPPORTED, "sar_bigru_fwd: hidden size %d unsupported (this build: %d)", u, GRU_U);
+  // default: the tcgen05 recurrence (bigru_tc.cu); SAR_GRU_FFMA=1 selects the CUDA-core kernel below
+  static const bool use_ffma = getenv("SAR_GRU_FFMA") != nullptr;
+  if (!use_ffma) {
+    SAR_REQUIRE(aligned16(xp) && aligned16(rbias) && aligned16(out), SAR_ERR_BAD_ARG, "sar_bigru_fwd: pointers must be 16-byte aligned");
+    return bigru_tc_launch(xp, rec, rbias, out, B, S, seq, (cudaStream_t)stream);
+  }
   // utterances per cluster: fewest waves of at most GRU_MAX_CLUSTERS resident clusters, weighted by the measured
   // step time of each variant (~3.9k cycles at 8 utterances, ~4.7k at 12)
   auto waves = [](int B_, int bg) { const int cl = 2 * ((B_ + bg - 1) / bg); return (cl + GRU_MAX_CLUSTERS - 1) / GRU_MAX_CLUSTERS; };

@@ -83,7 +83,7 @@ def test_layernorm_eps_1e14(cuda_device):
 
 
 @pytest.mark.parametrize("seq", [True, False])
-@pytest.mark.parametrize("B,S,Din", [(5, 21, 256), (2, 7, 512), (61, 9, 256), (130, 4, 256)])   # 61, 130: the 12-utterance-per-cluster variant, ragged last group
+@pytest.mark.parametrize("B,S,Din", [(5, 21, 256), (2, 7, 512), (61, 9, 256), (130, 4, 256)])   # 61: 16 utterances per cluster, ragged last group; 130: the 32-utterance variant
 def test_bigru_vs_oracle(cuda_device, B, S, Din, seq):
     from aesrc2020_b200 import model as mdl
     rng = np.random.RandomState(B * 7 + S)
