@@ -477,7 +477,10 @@ class SARModel:
                 dst.copy_(src, non_blocking=True)
             ps["h2d"][slot].record(ps["copy"])
         cur.wait_event(ps["h2d"][slot])
-        out = self.engine().forward_lanes({k: stage[k] for k in xd}, self._lanes_for(B))
+        if self.use_graph:
+            out = self.engine().forward_lanes({k: stage[k] for k in xd}, self._lanes_for(B))
+        else:
+            out = self.engine().forward({k: stage[k] for k in xd})
         if ps["free"][slot] is None:
             ps["free"][slot] = torch.cuda.Event()
         ps["free"][slot].record(cur)

@@ -214,6 +214,8 @@ def main():
     torch.cuda.synchronize()
     in_bytes = sum(v.nbytes for v in host_batches[0].values())
 
+    if args.eager:
+        model.use_graph = False      # profiling aid (ncu launch lists): no graph capture anywhere, e2e included
     if args.lanes:
         model.lanes = args.lanes
     lanes = 1 if args.eager else model._lanes_for(B)
