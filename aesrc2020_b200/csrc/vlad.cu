@@ -10,17 +10,18 @@
 // so HBM traffic is the algorithmic minimum: X read once, K*D written once (ghost clusters only
 // take part in the softmax and are never accumulated).
 //
-// Register tiling keeps the shared-memory pipe from being the limit:
-//   scores   : thread = 4 descriptors x 4 clusters, marching over d in float4 steps
-//              (8 LDS.128 per 64 FMA), Wa staged in shared memory when it fits;
-//   residual : warp = 8 clusters, lane = 8 feature columns -> 64 accumulators per thread,
-//              4 LDS.128 per 64 FMA; the per-cluster L2 norm is a warp reduction, so the
-//              normalised rows go straight from registers to HBM (32 B per lane, 1 KB per warp).
+// 512 threads (16 warps: the kernel is latency bound at one CTA per SM, see profiles/r1_summary_v9.md), register tiled:
+//   scores   : thread = 4 descriptors x 4 clusters x HALF of d (warps 0-7: d < D/2 into A, warps 8-15: the rest
+//              into A2; the softmax pass adds the halves), marching over d in float4 steps (8 LDS.128 per
+//              64 FMA), Wa staged in shared memory when it fits;
+//   residual : warp = (8 clusters, half of the columns), lane = 4 feature columns -> 32 accumulators per
+//              thread, 3 LDS.128 per 32 FMA; the per-cluster L2 norm is a warp reduction + one exchange
+//              between the two column halves, and the normalised rows go straight from registers to HBM.
 #include "common.cuh"
 
 namespace sar {
 
-constexpr int VLAD_THREADS = 256;
+constexpr int VLAD_THREADS = 512;
 
 __global__ void __launch_bounds__(VLAD_THREADS) vlad_kernel(const float* __restrict__ feat, const float* __restrict__ wa,
                                                              const float* __restrict__ ba, const float* __restrict__ score,
@@ -33,12 +34,14 @@ __global__ void __launch_bounds__(VLAD_THREADS) vlad_kernel(const float* __restr
   const int SP = (S + 3) & ~3;                    // descriptors padded to the 4-row score tile
   float* X = smem;                                // [SP][XS]
   float* A = X + (size_t)SP * XS;                 // [SP][KGP]
-  float* Ws = A + (size_t)SP * KGP;               // [D][KGP] (only when wa_smem)
+  float* A2 = A + (size_t)SP * KGP;               // [SP][KGP] scores of the upper half of d
+  float* nrm = A2 + (size_t)SP * KGP;             // [8 warps pairs][8 clusters][2 halves] squared-norm partials
+  float* Ws = nrm + 128;                          // [D][KGP] (only when wa_smem)
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int b = blockIdx.x;
 
   // ---- constants first (overlaps the previous kernel's tail under programmatic dependent launch)
-  for (int i = t; i < SP * KGP; i += VLAD_THREADS) A[i] = 0.f;
+  for (int i = t; i < 2 * SP * KGP; i += VLAD_THREADS) A[i] = 0.f;       // A and A2
   if (!score && wa_smem) {
     for (int i = t; i < D * KGP; i += VLAD_THREADS) {
       const int d = i / KGP, k = i - d * KGP;
@@ -68,7 +71,9 @@ __global__ void __launch_bounds__(VLAD_THREADS) vlad_kernel(const float* __restr
     }
   } else {                                         // fused 1x1 assignment conv, 4x4 register tiles
     const int kt = KGP >> 2, tiles = (SP >> 2) * kt;
-    for (int tile = t; tile < tiles; tile += VLAD_THREADS) {
+    const int dh = t >> 8;                         // d half (warp-uniform)
+    float* Ad = dh ? A2 : A;
+    for (int tile = t & 255; tile < tiles; tile += 256) {
       const int kg4 = tile % kt, sg4 = tile / kt;
       const int k0 = 4 * kg4, s0 = 4 * sg4;
       float acc[4][4];
@@ -76,7 +81,7 @@ __global__ void __launch_bounds__(VLAD_THREADS) vlad_kernel(const float* __restr
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-      for (int d = 0; d < D; d += 4) {
+      for (int d = dh * (D >> 1); d < (dh + 1) * (D >> 1); d += 4) {
         float4 xv[4], wv[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) xv[i] = *reinterpret_cast<const float4*>(X + (size_t)(s0 + i) * XS + d);
@@ -107,7 +112,7 @@ __global__ void __launch_bounds__(VLAD_THREADS) vlad_kernel(const float* __restr
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (s0 + i < S && k0 + j < KG) A[(s0 + i) * KGP + k0 + j] = acc[i][j] + __ldg(ba + k0 + j);
+          if (s0 + i < S && k0 + j < KG) Ad[(s0 + i) * KGP + k0 + j] = acc[i][j] + (dh ? 0.f : __ldg(ba + k0 + j));
     }
   }
   __syncthreads();
@@ -115,7 +120,7 @@ __global__ void __launch_bounds__(VLAD_THREADS) vlad_kernel(const float* __restr
   // ---- softmax over clusters, one warp per descriptor row (padded columns stay 0)
   for (int s = warp; s < S; s += VLAD_THREADS / 32) {
     float m = -INFINITY;
-    for (int k = lane; k < KG; k += 32) m = fmaxf(m, A[s * KGP + k]);
+    for (int k = lane; k < KG; k += 32) { A[s * KGP + k] += A2[s * KGP + k]; m = fmaxf(m, A[s * KGP + k]); }
     m = warp_max(m);
     float sum = 0.f;
     for (int k = lane; k < KG; k += 32) {
@@ -128,81 +133,87 @@ __global__ void __launch_bounds__(VLAD_THREADS) vlad_kernel(const float* __restr
   }
   __syncthreads();
 
-  // ---- residual accumulation: warp <- 8 clusters, lane <- 8 columns (per 256-column slab)
+  // ---- residual accumulation: warp <- (8 clusters, 128 columns), lane <- 4 columns
   const int kgroups = (K + 7) >> 3;
-  for (int kgp = warp; kgp < kgroups; kgp += VLAD_THREADS / 32) {
+  const int half = warp & 1, d0 = half * 128 + 4 * lane;
+  for (int kg0 = 0; kg0 < kgroups; kg0 += VLAD_THREADS / 64) {          // uniform trip count: the loop holds a __syncthreads
+    const int kgp = kg0 + (warp >> 1);
     const int k0 = 8 * kgp;
-    {
-      const int d0 = 4 * lane, d1 = 128 + 4 * lane;  // D == 256: lane owns 2 x 4 columns (conflict-free LDS.128)
-      float acc[8][8];
-      float asum[8];
+    const bool live = kgp < kgroups;                                       // warp-uniform
+    float acc[8][4];
+    float asum[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        asum[i] = 0.f;
+    for (int i = 0; i < 8; ++i) {
+      asum[i] = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-      }
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    }
+    float ss[8];
+    if (live) {
+#pragma unroll 4
       for (int s = 0; s < S; ++s) {
         const float4 a0 = *reinterpret_cast<const float4*>(A + s * KGP + k0);
         const float4 a1 = *reinterpret_cast<const float4*>(A + s * KGP + k0 + 4);
         const float4 x0 = *reinterpret_cast<const float4*>(X + (size_t)s * XS + d0);
-        const float4 x1 = *reinterpret_cast<const float4*>(X + (size_t)s * XS + d1);
         const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+        const float xv[4] = {x0.x, x0.y, x0.z, x0.w};
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           asum[i] += av[i];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], xv[j], acc[i][j]);
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], xv[j], acc[i][j]);
         }
       }
-      // the whole row is in this warp -> per-cluster L2 norm by warp reduction
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int k = k0 + i;
+        ss[i] = 0.f;
         if (k >= K) continue;                               // warp-uniform
         const float4 c0 = __ldg(reinterpret_cast<const float4*>(centers + (size_t)k * D + d0));
-        const float4 c1 = __ldg(reinterpret_cast<const float4*>(centers + (size_t)k * D + d1));
-        const float cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-        float ss = 0.f;
+        const float cv[4] = {c0.x, c0.y, c0.z, c0.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 4; ++j) {
           acc[i][j] -= asum[i] * cv[j];
-          ss = fmaf(acc[i][j], acc[i][j], ss);
+          ss[i] = fmaf(acc[i][j], acc[i][j], ss[i]);
         }
-        ss = warp_sum(ss);
-        const float inv = 1.0f / sqrtf(fmaxf(ss, 1e-12f));
-        float o[8];
+        ss[i] = warp_sum(ss[i]);
+      }
+      if (lane < 8) {
+        float v = ss[0];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = acc[i][j] * inv;
-        if (out) {
-          float* orow = out + ((size_t)b * K + k) * D;
-          *reinterpret_cast<float4*>(orow + d0) = make_float4(o[0], o[1], o[2], o[3]);
-          *reinterpret_cast<float4*>(orow + d1) = make_float4(o[4], o[5], o[6], o[7]);
-        }
+        for (int i = 1; i < 8; ++i) v = lane == i ? ss[i] : v;
+        nrm[((warp >> 1) * 8 + lane) * 2 + half] = v;
+      }
+    }
+    __syncthreads();
+    if (live) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int k = k0 + i;
+        if (k >= K) continue;
+        const float* np = nrm + ((warp >> 1) * 8 + i) * 2;
+        const float inv = 1.0f / sqrtf(fmaxf(np[0] + np[1], 1e-12f));      // fixed order: both halves get the same bits
+        const float o[4] = {acc[i][0] * inv, acc[i][1] * inv, acc[i][2] * inv, acc[i][3] * inv};
+        if (out) *reinterpret_cast<float4*>(out + ((size_t)b * K + k) * D + d0) = make_float4(o[0], o[1], o[2], o[3]);
         if (out_planes) {                 // fp16 hi/lo planes [2][B][K*D] for the tensor-core embedding GEMM
           __half* ph = out_planes + ((size_t)b * K + k) * D;
           __half* pl = ph + (size_t)gridDim.x * K * D;
-#pragma unroll
-          for (int hlf = 0; hlf < 2; ++hlf) {
-            const float* oo = o + 4 * hlf;
-            const __half2 h01 = __floats2half2_rn(oo[0], oo[1]), h23 = __floats2half2_rn(oo[2], oo[3]);
-            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-            const __half2 l01 = __floats2half2_rn((oo[0] - f01.x) * 2048.f, (oo[1] - f01.y) * 2048.f);
-            const __half2 l23 = __floats2half2_rn((oo[2] - f23.x) * 2048.f, (oo[3] - f23.y) * 2048.f);
-            const int dd = hlf ? d1 : d0;
-            *reinterpret_cast<uint2*>(ph + dd) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
-            *reinterpret_cast<uint2*>(pl + dd) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
-          }
+          const __half2 h01 = __floats2half2_rn(o[0], o[1]), h23 = __floats2half2_rn(o[2], o[3]);
+          const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+          const __half2 l01 = __floats2half2_rn((o[0] - f01.x) * 2048.f, (o[1] - f01.y) * 2048.f);
+          const __half2 l23 = __floats2half2_rn((o[2] - f23.x) * 2048.f, (o[3] - f23.y) * 2048.f);
+          *reinterpret_cast<uint2*>(ph + d0) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+          *reinterpret_cast<uint2*>(pl + d0) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
         }
       }
     }
+    __syncthreads();                                         // nrm is reused by the next cluster groups
   }
 }
 
 static size_t vlad_smem_floats(int S, int D, int KG, bool with_w) {
   const size_t KGP = (KG + 7) & ~7, XS = D + 4, SP = (S + 3) & ~3;
-  return SP * XS + SP * KGP + (with_w ? (size_t)D * KGP : 0);
+  return SP * XS + 2 * SP * KGP + 128 + (with_w ? (size_t)D * KGP : 0);
 }
 
 }  // namespace sar

@@ -17,7 +17,7 @@ def timed(*a, **k):
 rn.forward(xd); torch.cuda.synchronize()
 tc.conv_desc = timed
 rn.forward(xd); torch.cuda.synchronize()
-for li in (16, 17, 31):
+for li in (2, 3, 5, 8, 9):
     d = dbgs[li].cpu().tolist()
     t0 = d[62]
     print("layer", li, "entry 0  prologue done %d  exit %d" % (d[61] - t0, d[63] - t0))
