@@ -31,7 +31,7 @@ __device__ __forceinline__ float lse3(float a, float b, float c) {
 __global__ void __launch_bounds__(CTC_THREADS) ctc_kernel(const float* __restrict__ logits, const float* __restrict__ labels,
                                                            const int* __restrict__ in_len, const int* __restrict__ lab_len,
                                                            float* __restrict__ loss, float* __restrict__ probs,
-                                                           int* __restrict__ status, int S, int C, int Lmax) {
+                                                           int* __restrict__ status, int S, int C, int ld, int Lmax) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ __align__(16) float sm[];
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(CTC_THREADS) ctc_kernel(const float* __restric
 
   // ---- per-frame normalisers and gathered log q
   for (int f = warp; f < S; f += CTC_THREADS / 32) {
-    const float* row = logits + ((size_t)b * S + f) * C;
+    const float* row = logits + ((size_t)b * S + f) * ld;          // rows may be padded (tensor-core ctc_pred: ld = 32-aligned C)
     float m = -INFINITY;
     for (int c = lane; c < C; c += 32) m = fmaxf(m, __ldg(row + c));
     m = warp_max(m);
@@ -116,14 +116,19 @@ __global__ void __launch_bounds__(CTC_THREADS) ctc_kernel(const float* __restric
 
 extern "C" int sar_ctc_fwd(const float* logits, const float* labels, const int* in_len, const int* lab_len,
                            float* loss, float* probs, int* status, int B, int S, int C, int Lmax, void* stream) {
+  return sar_ctc_ld_fwd(logits, C, labels, in_len, lab_len, loss, probs, status, B, S, C, Lmax, stream);
+}
+
+extern "C" int sar_ctc_ld_fwd(const float* logits, int ld, const float* labels, const int* in_len, const int* lab_len,
+                              float* loss, float* probs, int* status, int B, int S, int C, int Lmax, void* stream) {
   using namespace sar;
   SAR_REQUIRE(logits && labels && in_len && lab_len && loss, SAR_ERR_BAD_ARG, "sar_ctc_fwd: null pointer");
-  SAR_REQUIRE(B > 0 && S > 0 && C > 1 && Lmax > 0, SAR_ERR_BAD_ARG, "sar_ctc_fwd: bad dimension");
+  SAR_REQUIRE(B > 0 && S > 0 && C > 1 && Lmax > 0 && ld >= C, SAR_ERR_BAD_ARG, "sar_ctc_fwd: bad dimension");
   const int NE = 2 * Lmax + 1;
   size_t smem = sizeof(float) * ((size_t)S * NE + 2 * NE) + sizeof(int) * NE;
   SAR_REQUIRE(smem <= 227 * 1024, SAR_ERR_UNSUPPORTED, "sar_ctc_fwd: S*(2*Lmax+1) too large for shared memory (%zu B)", smem);
   cudaError_t e = cudaFuncSetAttribute(ctc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("sar_ctc_fwd: %s", cudaGetErrorString(e)); return (int)e; }
-  launch_k(ctc_kernel, dim3(B), dim3(CTC_THREADS), smem, (cudaStream_t)stream, logits, labels, in_len, lab_len, loss, probs, status, S, C, Lmax);
+  launch_k(ctc_kernel, dim3(B), dim3(CTC_THREADS), smem, (cudaStream_t)stream, logits, labels, in_len, lab_len, loss, probs, status, S, C, ld, Lmax);
   return check_launch("sar_ctc_fwd");
 }

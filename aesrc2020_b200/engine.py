@@ -286,6 +286,14 @@ class SARNetEngine:
             self._bigru(w, "CTC_BIGRU"); self._ln(w, "CTC_BIGRU_LN")
             self._dense(w, "CTC_DS"); self._ln(w, "CTC_DS_LN")
             self._dense(w, "ctc_pred", tc_ok=False)
+            if self.dense_tc and w["ctc_pred/kernel"].shape[0] % 32 == 0:
+                # ctc_pred (Dout = bpe_classes, 1000 by default) on the tensor cores: columns padded with zero
+                # weights to a multiple of 32; sar_ctc_ld_fwd reads the first bpe_classes columns of each row
+                from . import tc
+                k, b = w["ctc_pred/kernel"], w["ctc_pred/bias"]
+                padc = (-k.shape[1]) % 32
+                self.p["ctc_pred/w_tc"] = torch.from_numpy(tc.pack_dense_weights(np.pad(k, ((0, 0), (0, padc))))).to(self.device)
+                self._put("ctc_pred/bias_tc", np.pad(b, (0, padc)))
         if cfg.ar_enable:
             self._dense(w, "AR_DS"); self._ln(w, "AR_DS_LN")
             if cfg.mto == "bigru":
@@ -523,13 +531,21 @@ class SARNetEngine:
             if use_tc:
                 S_ = self.plan.seq_len
                 _, P3 = self.ln_planes(self.bigru_planes(crnn_planes, "CTC_BIGRU", (B, S_)), "CTC_BIGRU_LN", "ctc_bigru")
-                asr = ops.layernorm(self.dense_planes(P3, "CTC_DS", (B, S_), act="tanh"), p["CTC_DS_LN/gamma"], p["CTC_DS_LN/beta"])
+                y = self.dense_planes(P3, "CTC_DS", (B, S_), act="tanh")
+                if "ctc_pred/w_tc" in p:
+                    _, P5 = self.ln_planes(y, "CTC_DS_LN", "ctc_ds")
+                    asr = None
+                else:
+                    asr = ops.layernorm(y, p["CTC_DS_LN/gamma"], p["CTC_DS_LN/beta"])
             else:
                 asr = ops.layernorm(self.bigru(crnn, "CTC_BIGRU"), p["CTC_BIGRU_LN/gamma"], p["CTC_BIGRU_LN/beta"])
                 asr = self.dense_ln(asr, "CTC_DS", "CTC_DS_LN")
-            logits = ops.dense(asr, p["ctc_pred/kernel"], p["ctc_pred/bias"])
+            if asr is None:
+                logits = self.dense_planes(P5, "ctc_pred", (B, self.plan.seq_len), bias_name="ctc_pred/bias_tc")
+            else:
+                logits = ops.dense(asr, p["ctc_pred/kernel"], p["ctc_pred/bias"])
             ctc_loss, status, probs = ops.ctc(logits, inputs["x_ctc_label"], inputs["x_ctc_in_len"],
-                                              inputs["x_ctc_out_len"], want_probs=want_intermediates,
+                                              inputs["x_ctc_out_len"], want_probs=want_intermediates, classes=cfg.bpe_classes,
                                               loss=sink.get("_ctc_loss"), status=sink.get("ctc_status"))
             out["_ctc_loss"] = ctc_loss
             out["y_ctc_loss"] = ctc_loss.reshape(B, 1)

@@ -203,11 +203,13 @@ def head(emb, cls_w=None, *, emb_d=None, wd=None, onehot=None, n_classes=8, head
     return res
 
 
-def ctc(logits, labels, in_len, lab_len, *, want_probs=False, loss=None, status=None):
-    """logits (B,S,C) pre-softmax; labels (B,Lmax) float32; lens (B,) or (B,1) int32."""
+def ctc(logits, labels, in_len, lab_len, *, want_probs=False, loss=None, status=None, classes=None):
+    """logits (B,S,C) pre-softmax; labels (B,Lmax) float32; lens (B,) or (B,1) int32.  `classes` < logits.shape[-1]:
+    the rows are padded (tensor-core ctc_pred) and only the first `classes` columns count."""
     logits = _f32(logits)
     labels = _f32(labels)
-    B, S, Cc = logits.shape
+    B, S, ld = logits.shape
+    Cc = int(classes) if classes else ld
     in_len = in_len.reshape(-1).to(torch.int32).contiguous()
     lab_len = lab_len.reshape(-1).to(torch.int32).contiguous()
     if loss is None:
@@ -215,9 +217,9 @@ def ctc(logits, labels, in_len, lab_len, *, want_probs=False, loss=None, status=
     if status is None:
         status = torch.empty((B,), device=logits.device, dtype=torch.int32)
     assert loss.numel() == B and status.numel() == B and loss.is_contiguous() and status.is_contiguous()
-    probs = torch.empty_like(logits) if want_probs else None
-    check(_shim.lib().sar_ctc_fwd(ptr(logits), ptr(labels), ptr(in_len), ptr(lab_len), ptr(loss), ptr(probs),
-                                  ptr(status), B, S, Cc, labels.shape[1], stream_ptr()), "sar_ctc_fwd")
+    probs = torch.empty((B, S, Cc), device=logits.device, dtype=torch.float32) if want_probs else None
+    check(_shim.lib().sar_ctc_ld_fwd(ptr(logits), ld, ptr(labels), ptr(in_len), ptr(lab_len), ptr(loss), ptr(probs),
+                                     ptr(status), B, S, Cc, labels.shape[1], stream_ptr()), "sar_ctc_fwd")
     _count(1)
     return loss, status, probs
 

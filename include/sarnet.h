@@ -233,6 +233,10 @@ int sar_head_fwd(const float* emb, int D,
  * status (B) int32 optional: 0 ok, 1 infeasible label sequence (TF raises), 2 bad label. */
 int sar_ctc_fwd(const float* logits, const float* labels, const int* in_len, const int* lab_len,
                 float* loss, float* probs, int* status, int B, int S, int C, int Lmax, void* stream);
+/* Same, with `ld` >= C floats between consecutive (b, s) rows of `logits`: the tensor-core ctc_pred Dense pads
+ * its output columns to a multiple of 32 (1000 -> 1024); only the first C columns of a row are classes. */
+int sar_ctc_ld_fwd(const float* logits, int ld, const float* labels, const int* in_len, const int* lab_len,
+                   float* loss, float* probs, int* status, int B, int S, int C, int Lmax, void* stream);
 
 /* Deterministic batch reduction of per-sample statistics into the 8-float vector that is
  * all-reduced across GPUs (one ncclAllReduce(SUM), replaces multi_gpu_model, model.py:193-194):
