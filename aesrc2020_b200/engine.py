@@ -463,6 +463,27 @@ class SARNetEngine:
         out["loss_vector"] = ops.loss_reduce(sink.get("_sample_stats"), sink.get("_ctc_loss"), sink.get("_bn_stats"), B=B)
         return out
 
+    def forward_slot(self, inputs: Dict[str, torch.Tensor], slot: int, tag=""):
+        """Enqueue one whole step on pipeline slot `slot`: its own stream, CUDA graph and activation buffers, so
+        that consecutive (independent) batches overlap -- the tail of a step (Bi-GRU on 64 SMs, VLAD / head / Dense on
+        24-96 CTAs) leaves most SMs idle, and the next batch's stem and stage-1 convolutions fill them.  Returns
+        (outputs, stream); the caller orders the inputs before and the consumers after with events on that stream.
+        Only slot 0 uses the persistent stage-chain launches (two concurrent chains could starve each other of SMs)."""
+        st = self.slot_stream(slot)
+        with torch.cuda.stream(st):
+            self._set_lane(slot)
+            try:
+                out = self.forward_graphed(inputs, tag=(tag, "slot"))
+            finally:
+                self._set_lane(0)
+        return out, st
+
+    def slot_stream(self, slot: int) -> torch.cuda.Stream:
+        while len(self._lane_streams) <= slot:
+            self._lane_streams.append(torch.cuda.Stream(device=self.device))
+            self._lane_done.append(torch.cuda.Event())
+        return self._lane_streams[slot]
+
     def _set_lane(self, lane: int):
         self.lane = lane
         self.resnet.lane = lane

@@ -428,7 +428,7 @@ class SARModel:
         return res[0] if len(res) == 1 else res
 
     # -- pipelined prediction over a batch generator
-    PIPE_DEPTH = 2
+    PIPE_DEPTH = 3
 
     def _pipe_state(self):
         if self._pipe is None:
@@ -476,14 +476,24 @@ class SARModel:
                     dst = stage[k] = torch.empty(src.shape, dtype=want, device=self.device)
                 dst.copy_(src, non_blocking=True)
             ps["h2d"][slot].record(ps["copy"])
-        cur.wait_event(ps["h2d"][slot])
-        if self.use_graph:
-            out = self.engine().forward_lanes({k: stage[k] for k in xd}, self._lanes_for(B))
+        lanes = self._lanes_for(B)
+        if self.use_graph and lanes == 1:
+            # the whole step runs on the slot's own stream / graph / activation buffers: consecutive batches overlap
+            # on the device as well (engine.forward_slot), not only their copies
+            comp = self.engine().slot_stream(slot)
+            comp.wait_stream(cur)
+            comp.wait_event(ps["h2d"][slot])
+            out, _ = self.engine().forward_slot({k: stage[k] for k in xd}, slot)
         else:
-            out = self.engine().forward({k: stage[k] for k in xd})
+            comp = cur
+            cur.wait_event(ps["h2d"][slot])
+            if self.use_graph:
+                out = self.engine().forward_lanes({k: stage[k] for k in xd}, lanes)
+            else:
+                out = self.engine().forward({k: stage[k] for k in xd})
         if ps["free"][slot] is None:
             ps["free"][slot] = torch.cuda.Event()
-        ps["free"][slot].record(cur)
+        ps["free"][slot].record(comp)
         outs = [out[name] for name in self._outputs]
         if self.config.ctc_enable:
             outs.append(out["ctc_status"])
@@ -493,13 +503,14 @@ class SARModel:
             pin = ps["pin_out"][slot] = torch.empty((max(tot, 4096),), dtype=torch.float32, pin_memory=True)
         off = 0
         views = []
-        for o in outs:
-            dst = pin[off:off + o.numel()]
-            dst = dst.view(torch.int32) if o.dtype == torch.int32 else dst
-            dst.view(o.shape).copy_(o, non_blocking=True)
-            views.append(dst.view(o.shape))
-            off += o.numel()
-        ps["done"][slot].record(cur)
+        with torch.cuda.stream(comp):
+            for o in outs:
+                dst = pin[off:off + o.numel()]
+                dst = dst.view(torch.int32) if o.dtype == torch.int32 else dst
+                dst.view(o.shape).copy_(o, non_blocking=True)
+                views.append(dst.view(o.shape))
+                off += o.numel()
+            ps["done"][slot].record(comp)
         return slot, views
 
     def _collect(self, handle) -> List[np.ndarray]:
@@ -514,9 +525,10 @@ class SARModel:
         """Keras `Model.predict_generator` (the forward-only twin of the `fit_generator(generator, max_queue_size=20)`
         loop the reference trains with, train.py:38-44): `generator` yields one batch per step -- an input dict /
         list as utils.data_loader builds it (utils.py:102-116), or the (inputs, targets) tuple data_generator
-        yields.  Batches are pipelined PIPE_DEPTH deep: while step i runs, step i+1's inputs are DMA'd from pinned
-        host memory by the copy engine and step i-1's outputs are read back, so the host<->device copies of every
-        step stay off the kernels' critical path.  Returns the outputs concatenated over steps, as predict() does."""
+        yields.  Batches are pipelined PIPE_DEPTH deep, each in flight on a stream, CUDA graph and buffer set of its own:
+        while step i runs, step i+1's inputs are DMA'd from pinned host memory by the copy engine, its first kernels
+        fill the SMs that step i's latency-bound tail (Bi-GRU, VLAD, head) leaves idle, and step i-1's outputs are
+        read back.  Returns the outputs concatenated over steps, as predict() does."""
         from collections import deque
         it = iter(generator)
         pending = deque()

@@ -176,6 +176,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="no CUDA-graph replay (for ncu launch lists)")
     ap.add_argument("--lanes", type=int, default=0, help="concurrent micro-batch lanes per step (0 = the model's default)")
+    ap.add_argument("--pipeline", type=int, default=4, help="independent steps in flight on separate streams (1 = one stream)")
     ap.add_argument("--rotate", type=int, default=16, help="distinct input batches rotated through (L2 hygiene)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
@@ -220,13 +221,26 @@ def main():
         model.lanes = args.lanes
     lanes = 1 if args.eager else model._lanes_for(B)
 
+    depth = 1 if (args.eager or lanes > 1) else max(1, args.pipeline)
+    main_stream = torch.cuda.current_stream()
+
     def step_device(i, graphed=True):
         x = dev_batches[i % args.rotate]
+        if graphed and depth > 1:                   # consecutive batches alternate between `depth` streams / graphs
+            out, st = eng.forward_slot(x, i % depth)
+            if world > 1:
+                with torch.cuda.stream(st):
+                    tdist.all_reduce(out["loss_vector"])
+            return out
         out = eng.forward_lanes(x, lanes) if (graphed and not args.eager) else eng.forward(x)
         vec = out["loss_vector"]
         if world > 1:
             tdist.all_reduce(vec)
         return out
+
+    def join_slots():
+        for st in eng._lane_streams[:depth] if depth > 1 else []:
+            main_stream.wait_stream(st)
 
     def barrier():
         if world > 1:
@@ -247,6 +261,23 @@ def main():
         step_device(i)
     barrier()
 
+    # ---- single-stream reference: the same K steps strictly one after the other (per-step latency, reported beside
+    # the pipelined throughput)
+    single_ms = None
+    if depth > 1:
+        for i in range(3):
+            eng.forward_lanes(dev_batches[i % args.rotate], 1)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for i in range(args.steps):
+            out1 = eng.forward_lanes(dev_batches[(args.warmup + i) % args.rotate], 1)
+            if world > 1:
+                tdist.all_reduce(out1["loss_vector"])
+        s1.record()
+        barrier()
+        single_ms = s0.elapsed_time(s1) / args.steps
+
     # ---- timed region A (the `value`): K graph replays, device-resident inputs
     sampler = ClockSampler(local)
     if rank == 0:
@@ -254,11 +285,22 @@ def main():
     barrier()
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()
+    for st in (eng._lane_streams[:depth] if depth > 1 else []):
+        st.wait_stream(main_stream)                 # no slot starts before the start event
     for i in range(args.steps):
         step_device(args.warmup + i)
+    join_slots()
     t_end.record()
     barrier()
     launches = launches_per_step * args.steps       # kernels replayed from the graph
+    if depth > 1:                                   # slots >= 1 launch every layer separately (no stage chains)
+        eng._set_lane(1)
+        l0 = ops.LAUNCHES["n"]
+        eng.forward(dev_batches[0])
+        per_other = ops.LAUNCHES["n"] - l0
+        eng._set_lane(0)
+        torch.cuda.synchronize()
+        launches = sum(launches_per_step if (args.warmup + i) % depth == 0 else per_other for i in range(args.steps))
     ms = t_start.elapsed_time(t_end)
 
     # ---- timed region B (roofline): K more replays of the SAME step captured a second time with two external
@@ -383,12 +425,16 @@ def main():
                    "l2": "inputs rotate over %d distinct batches (%.0f MB > 126 MB L2); activations %.0f MB/step"
                          % (args.rotate, args.rotate * in_bytes / 1e6, 2 * Bt / 1e6 / 3),
                    "parallelism": "dp%d (batch-sharded, 1 all-reduce of 8 floats/step)" % world,
-                   "lanes": "%d concurrent micro-batch graph(s) per step on separate streams" % lanes},
+                   "lanes": "%d concurrent micro-batch graph(s) per step on separate streams" % lanes,
+                   "pipeline": "%d independent step(s) in flight (one stream + CUDA graph + buffer set each)" % depth},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
-                "api": "model.predict_generator(batches in pinned host memory, steps=K): 2-deep pipeline, wall clock over K steps",
+                "api": "model.predict_generator(batches in pinned host memory, steps=K): %d batches in flight (copy stream + one compute stream/graph per slot), wall clock over K steps" % model.PIPE_DEPTH,
                 "blocking_predict": e2e_sync_value},
         "gpu_launches": launches, "roofline": roof, "clocks": clocks,
     }
+    if single_ms is not None:
+        line["single_stream"] = {"ms_per_step": single_ms, "value": world * B / (single_ms * 1e-3), "unit": UNIT,
+                                 "note": "the same steps on ONE stream, one after the other (per-batch latency)"}
     if cpu:
         line["cpu_baseline"] = cpu
     print(json.dumps(line))

@@ -249,3 +249,30 @@ def test_predict_generator_raises_on_infeasible_ctc(cuda_device):
     with pytest.raises(_shim.SarnetError):
         model.predict_generator(iter([x, bad, x]))
     assert np.array_equal(model.predict_generator(iter([x]))[0], model.predict(x)[0])     # the pipeline survives the error
+
+
+def test_pipelined_slots_are_bitwise_the_single_stream_step(cuda_device):
+    """engine.forward_slot: consecutive batches in flight on 3 streams / graphs / buffer sets (what bench.py's value
+    loop and predict_generator do) give bitwise the single-stream outputs, batch after batch."""
+    from aesrc2020_b200 import model as mdl, utils as us
+    kw = dict(ctc_enable=True, disc_enable=True, res_type="res34", res_filters=32, mto="gvlad", vlad_clusters=64,
+              ghost_clusters=8, metric_loss="arcface")
+    model, _ = mdl.SAR_Net((500, 80, 1), **kw)
+    eng = model.engine()
+    names = ["y_accent", "y_disc", "y_ctc_loss", "loss_vector"]
+    dev = [{k: model._to_device(k, v).clone() for k, v in us.synthetic_batch(model.config, 24, seed=90 + i)[0].items()}
+           for i in range(7)]
+    ref = []
+    for d in dev:
+        out = eng.forward_graphed(d)
+        ref.append({k: out[k].clone() for k in names})
+    torch.cuda.synchronize()
+    for rep in range(2):
+        got = []
+        for i, d in enumerate(dev):
+            out, st = eng.forward_slot(d, i % 3)
+            with torch.cuda.stream(st):
+                got.append({k: out[k].clone() for k in names})      # before the slot's next replay overwrites them
+        torch.cuda.synchronize()
+        for g, r in zip(got, ref):
+            assert all(torch.equal(g[k], r[k]) for k in names), rep
