@@ -43,6 +43,7 @@ SIGNATURES = {
     "sar_layernorm_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_ll, c_int, c_f, C.c_void_p]),
     "sar_layernorm_planes_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_ll, c_int, c_ll, c_int, c_f, C.c_void_p]),
     "sar_bigru_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, C.c_void_p]),
+    "sar_bigru_nb_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, C.c_void_p]),
     "sar_vlad_fwd": (c_int, [c_fp] * 6 + [c_int] * 5 + [C.c_void_p]),
     "sar_vlad_planes_fwd": (c_int, [c_fp] * 7 + [c_int] * 5 + [C.c_void_p]),
     "sar_splitk_reduce_fwd": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_int, C.c_void_p]),

@@ -284,11 +284,17 @@ bigru_kernel(const float* __restrict__ xp, const float* __restrict__ rec, const 
 
 }  // namespace sar
 
-namespace sar { int bigru_tc_launch(const float*, const float*, const float*, float*, int, int, int, cudaStream_t); }
+namespace sar { int bigru_tc_launch(const float*, const float*, const float*, float*, int, int, int, int, cudaStream_t); }
 
 extern "C" int sar_bigru_fwd(const float* xp, const float* rec, const float* rbias, float* out,
                              int B, int S, int u, int seq, void* stream) {
+  return sar_bigru_nb_fwd(xp, rec, rbias, out, B, S, u, seq, 0, stream);
+}
+
+extern "C" int sar_bigru_nb_fwd(const float* xp, const float* rec, const float* rbias, float* out,
+                                int B, int S, int u, int seq, int nb, void* stream) {
   using namespace sar;
+  SAR_REQUIRE(nb == 0 || nb == 16 || nb == 32, SAR_ERR_BAD_ARG, "sar_bigru_nb_fwd: nb must be 0 (auto), 16 or 32");
   SAR_REQUIRE(xp && rec && rbias && out, SAR_ERR_BAD_ARG, "sar_bigru_fwd: null pointer");
   SAR_REQUIRE(B > 0 && S > 0, SAR_ERR_BAD_ARG, "sar_bigru_fwd: non-positive dimension");
   SAR_REQUIRE(u == GRU_U, SAR_ERR_UNSUPPORTED, "sar_bigru_fwd: hidden size %d unsupported (this build: %d)", u, GRU_U);
@@ -296,7 +302,7 @@ extern "C" int sar_bigru_fwd(const float* xp, const float* rec, const float* rbi
   static const bool use_ffma = getenv("SAR_GRU_FFMA") != nullptr;
   if (!use_ffma) {
     SAR_REQUIRE(aligned16(xp) && aligned16(rbias) && aligned16(out), SAR_ERR_BAD_ARG, "sar_bigru_fwd: pointers must be 16-byte aligned");
-    return bigru_tc_launch(xp, rec, rbias, out, B, S, seq, (cudaStream_t)stream);
+    return bigru_tc_launch(xp, rec, rbias, out, B, S, seq, nb, (cudaStream_t)stream);
   }
   // utterances per cluster: fewest waves of at most GRU_MAX_CLUSTERS resident clusters, weighted by the measured
   // step time of each variant (~3.9k cycles at 8 utterances, ~4.7k at 12)

@@ -338,9 +338,9 @@ bigru_tc_kernel(const float* __restrict__ xp, const float* __restrict__ rec, con
   }
 }
 
-int bigru_tc_launch(const float* xp, const float* rec, const float* rbias, float* out, int B, int S, int seq, cudaStream_t stream) {
+int bigru_tc_launch(const float* xp, const float* rec, const float* rbias, float* out, int B, int S, int seq, int nb_req, cudaStream_t stream) {
   static const int force_nb = getenv("SAR_GRU_NB") ? atoi(getenv("SAR_GRU_NB")) : 0;     // experiments: 16 or 32
-  const int nb = force_nb ? force_nb : (2 * ((B + 15) / 16) <= GT_MAX_CLUSTERS ? 16 : 32);
+  const int nb = force_nb ? force_nb : (nb_req ? nb_req : (2 * ((B + 15) / 16) <= GT_MAX_CLUSTERS ? 16 : 32));
   auto launch = [&](auto kern, size_t smem, int NBv) -> int {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("sar_bigru_fwd(tc): %s", cudaGetErrorString(e)); return (int)e; }

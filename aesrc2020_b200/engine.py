@@ -98,6 +98,7 @@ class ResNetTC:
         self._rot: Dict[tuple, int] = {}
         self.record_events = None
         self.lane = 0            # buffer namespace: concurrent micro-batch lanes never share activation buffers
+        self.no_chain = False    # forward_slot: per-layer launches only
         import os as _os
         # stages whose stride-1 layers run as one persistent chain launch (SAR_CHAIN_STAGES="" disables)
         self.chain_stages = {int(x) for x in _os.environ.get("SAR_CHAIN_STAGES", "2,3,4").split(",") if x.strip()}
@@ -181,7 +182,7 @@ class ResNetTC:
         def emit(desc, chainable):
             # lanes run concurrently on separate streams: a chain launch (CTAs spinning on tile counters of CTAs of
             # the SAME launch) needs its whole grid resident, which two lanes sharing the SMs cannot promise
-            if chainable and stage in self.chain_stages and self.lane == 0:
+            if chainable and stage in self.chain_stages and self.lane == 0 and not self.no_chain:
                 pending.append(desc)
             else:
                 flush()
@@ -468,14 +469,21 @@ class SARNetEngine:
         that consecutive (independent) batches overlap -- the tail of a step (Bi-GRU on 64 SMs, VLAD / head / Dense on
         24-96 CTAs) leaves most SMs idle, and the next batch's stem and stage-1 convolutions fill them.  Returns
         (outputs, stream); the caller orders the inputs before and the consumers after with events on that stream.
-        Only slot 0 uses the persistent stage-chain launches (two concurrent chains could starve each other of SMs)."""
+        Slots never use the persistent stage-chain launches (two concurrent chains could starve each other of SMs)."""
         st = self.slot_stream(slot)
         with torch.cuda.stream(st):
+            # kernels captured for a slot are chosen for SM-time, not latency: no stage chains (a chain holds its SMs
+            # for a whole stage) and 32 utterances per Bi-GRU cluster (32 SMs instead of 64 at B=64); measured
+            # 98.1 -> 100.9 k utt/s device, 88.2 -> 95.2 k e2e, while the same choices cost a single stream 11 %
             self._set_lane(slot)
+            self.resnet.no_chain = True
+            ops.GRU_NB["n"] = 32
             try:
                 out = self.forward_graphed(inputs, tag=(tag, "slot"))
             finally:
                 self._set_lane(0)
+                self.resnet.no_chain = False
+                ops.GRU_NB["n"] = 0
         return out, st
 
     def slot_stream(self, slot: int) -> torch.cuda.Stream:

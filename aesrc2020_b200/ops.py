@@ -105,14 +105,17 @@ def layernorm(x, gamma, beta, eps: float = LN_EPS, *, planes=None, want_dense: b
     return out
 
 
+GRU_NB = {"n": 0}       # utterances per cluster of the Bi-GRU kernel: 0 auto, 32 while several batches share the GPU
+
+
 def bigru(xp, rec, rbias, *, seq=True):
     """xp (B,S,2,3u) input projections; rec (2,u,3u); rbias (2,3u)."""
     xp = _f32(xp)
     B, S = xp.shape[0], xp.shape[1]
     u = rec.shape[1]
     out = torch.empty((B, S, 2 * u) if seq else (B, 2 * u), device=xp.device, dtype=torch.float32)
-    check(_shim.lib().sar_bigru_fwd(ptr(xp), ptr(rec), ptr(rbias), ptr(out), B, S, u, 1 if seq else 0,
-                                    stream_ptr()), "sar_bigru_fwd")
+    check(_shim.lib().sar_bigru_nb_fwd(ptr(xp), ptr(rec), ptr(rbias), ptr(out), B, S, u, 1 if seq else 0,
+                                       GRU_NB["n"], stream_ptr()), "sar_bigru_fwd")
     _count(1)
     return out
 

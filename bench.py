@@ -293,14 +293,14 @@ def main():
     t_end.record()
     barrier()
     launches = launches_per_step * args.steps       # kernels replayed from the graph
-    if depth > 1:                                   # slots >= 1 launch every layer separately (no stage chains)
+    if depth > 1:                                   # pipeline slots launch every layer separately (no stage chains)
         eng._set_lane(1)
         l0 = ops.LAUNCHES["n"]
         eng.forward(dev_batches[0])
         per_other = ops.LAUNCHES["n"] - l0
         eng._set_lane(0)
         torch.cuda.synchronize()
-        launches = sum(launches_per_step if (args.warmup + i) % depth == 0 else per_other for i in range(args.steps))
+        launches = per_other * args.steps
     ms = t_start.elapsed_time(t_end)
 
     # ---- timed region B (roofline): K more replays of the SAME step captured a second time with two external

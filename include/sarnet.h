@@ -174,6 +174,11 @@ int sar_layernorm_planes_fwd(const float* x, const float* gamma, const float* be
  * seq==0: out (B,2u)   = concat(fwd final state, bwd final state).  u must be 256. */
 int sar_bigru_fwd(const float* xp, const float* rec, const float* rbias, float* out,
                   int B, int S, int u, int seq, void* stream);
+/* Same, choosing the utterances per 8-CTA cluster: nb = 16 (shortest step: half the SM-to-SM bytes per CTA),
+ * 32 (half the SMs for the same batch: the better choice when other work shares the GPU), 0 = automatic
+ * (16 while both directions of the batch fit in one wave of 15 resident clusters). */
+int sar_bigru_nb_fwd(const float* xp, const float* rec, const float* rbias, float* out,
+                     int B, int S, int u, int seq, int nb, void* stream);
 
 /* ---- many-to-one integration ------------------------------------------------------- */
 
