@@ -366,6 +366,7 @@ def main():
     if rank != 0:
         if world > 1:
             tdist.barrier()
+            tdist.destroy_process_group()
         return
 
     # ---- roofline of the residual-block convolution kernel
@@ -440,6 +441,7 @@ def main():
     print(json.dumps(line))
     if world > 1:
         tdist.barrier()
+        tdist.destroy_process_group()
 
 
 if __name__ == "__main__":

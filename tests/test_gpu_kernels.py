@@ -99,6 +99,16 @@ def test_bigru_vs_oracle(cuda_device, B, S, Din, seq):
     got = layer(dev(x))
     want = O.bigru(t64(x), {"g/" + k: t64(v) for k, v in w.items()}, "g", seq=seq)
     assert norm_err(got, want) < 2e-5
+    # 16 or 32 utterances per cluster (sar_bigru_nb_fwd) is a scheduling choice: bitwise the same result
+    from aesrc2020_b200 import ops
+    outs = []
+    for nb in (16, 32):
+        ops.GRU_NB["n"] = nb
+        try:
+            outs.append(layer(dev(x)))
+        finally:
+            ops.GRU_NB["n"] = 0
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], got)
 
 
 @pytest.mark.parametrize("mode,K,G,S,D", [("gvlad", 64, 8, 48, 256), ("vlad", 64, 0, 48, 256),
@@ -233,6 +243,14 @@ def test_ctc_vs_oracle(cuda_device, S, C, Lmax):
     assert int(status.abs().sum()) == 0
     assert rel_err(loss.reshape(-1, 1), want) < 1e-4
     assert norm_err(p, probs) < 1e-5
+    # padded rows (sar_ctc_ld_fwd: the tensor-core ctc_pred Dense pads its columns to a multiple of 32): garbage in
+    # the pad columns must not matter, and the result is bitwise the dense-row one
+    ld = (C + 31) // 32 * 32 + 32
+    padded = torch.full((B, S, ld), 1e30, device="cuda", dtype=torch.float32)
+    padded[..., :C] = dev(logits)
+    loss2, status2, p2 = ops.ctc(padded, dev(labels), torch.from_numpy(in_len).cuda(), torch.from_numpy(lab_len).cuda(),
+                                 want_probs=True, classes=C)
+    assert torch.equal(loss2, loss) and torch.equal(status2, status) and torch.equal(p2, p)
 
 
 def test_ctc_infeasible_and_bad_labels(cuda_device):
