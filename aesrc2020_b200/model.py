@@ -401,6 +401,9 @@ class SARModel:
         xd = self._as_dict(x)
         n = len(xd["x_data"])
         on_device = isinstance(xd["x_data"], torch.Tensor) and xd["x_data"].is_cuda
+        if not on_device and n > batch_size and self.use_graph:
+            # several chunks: the pipelined path (copies and consecutive chunks overlap), same outputs
+            return self.predict_generator({k: v[b0:b0 + batch_size] for k, v in xd.items()} for b0 in range(0, n, batch_size))
         chunks: List[List] = [[] for _ in self._outputs]
         for b0 in range(0, n, batch_size):
             sl = {k: v[b0:b0 + batch_size] for k, v in xd.items()}

@@ -257,6 +257,8 @@ def main():
         eng.forward({k: v[:B // lanes] for k, v in dev_batches[0].items()})
         launches_per_step = (ops.LAUNCHES["n"] - l0 - 1) * lanes + 1
         eng._set_lane(0)
+    for i in range(depth if depth > 1 else 0):      # capture every slot's CUDA graph before the W warm-up steps
+        step_device(i)
     for i in range(args.warmup):
         step_device(i)
     barrier()
