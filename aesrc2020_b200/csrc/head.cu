@@ -24,7 +24,6 @@ struct HeadP {
   const float* w3; const float* b3;
   const float* emb_d; int Dd; const float* wd;
   const float* onehot; int n; int head; float margin, s, gamma;
-  int w_smem;                            // weights + biases are staged in shared memory before griddepcontrol.wait
   float* y_accent; float* y_accent_logits; float* y_disc; float* y_disc_logits; float* stats;
 };
 
@@ -44,13 +43,13 @@ __device__ __forceinline__ void matvec_parts(const float* x, int D, const float*
       int d = dlo;
 #pragma unroll 8
       for (; d + 1 < dhi; d += 2) {
-        const float w0 = w[(size_t)d * nout + j], w1 = w[(size_t)(d + 1) * nout + j];
+        const float w0 = __ldg(w + (size_t)d * nout + j), w1 = __ldg(w + (size_t)(d + 1) * nout + j);
         a0 = fmaf(x[d] * xscale, w0, a0);
         a1 = fmaf(x[d + 1] * xscale, w1, a1);
         if (SQ) { q0 = fmaf(w0, w0, q0); q1 = fmaf(w1, w1, q1); }
       }
       if (d < dhi) {
-        const float w0 = w[(size_t)d * nout + j];
+        const float w0 = __ldg(w + (size_t)d * nout + j);
         a0 = fmaf(x[d] * xscale, w0, a0);
         if (SQ) q0 = fmaf(w0, w0, q0);
       }
@@ -68,7 +67,7 @@ __device__ __forceinline__ void matvec_parts(const float* x, int D, const float*
     for (int j = t; j < nout; j += HEAD_THREADS) {
       float a = 0.f, q = 0.f;
       for (int d = 0; d < D; ++d) {
-        const float w0 = w[(size_t)d * nout + j];
+        const float w0 = __ldg(w + (size_t)d * nout + j);
         a = fmaf(x[d] * xscale, w0, a);
         if (SQ) q = fmaf(w0, w0, q);
       }
@@ -115,25 +114,6 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(HeadP p) {
   float* pacc = scratch + 32;            // [HEAD_THREADS]
   float* psq = pacc + HEAD_THREADS;      // [HEAD_THREADS]
   const int t = threadIdx.x, lane = t & 31, b = blockIdx.x, n = p.n;
-  // The weights are constants: stage them in shared memory BEFORE waiting for the previous kernel (programmatic
-  // dependent launch), so the four dependent mat-vec phases below read shared memory instead of paying an L2
-  // round trip each.
-  const float* w1 = p.w1; const float* b1 = p.b1; const float* w2 = p.w2; const float* b2 = p.b2;
-  const float* w3 = p.w3; const float* b3 = p.b3; const float* wd = p.wd;
-  if (p.w_smem) {
-    float* dst = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(psq + HEAD_THREADS) + 15) & ~uintptr_t(15));
-    auto stage = [&](const float*& src, int count) {
-      if (!src || count <= 0) return;
-      const int c4 = count >> 2;
-      for (int i = t; i < c4; i += HEAD_THREADS) reinterpret_cast<float4*>(dst)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
-      for (int i = 4 * c4 + t; i < count; i += HEAD_THREADS) dst[i] = __ldg(src + i);
-      src = dst;
-      dst += (count + 3) & ~3;
-    };
-    stage(w1, p.D * p.H1); stage(b1, p.H1); stage(w2, p.H1 * p.H2); stage(b2, p.H2);
-    stage(w3, p.H2 * n); stage(b3, p.w1 ? n : 0);
-    stage(wd, p.head != SAR_HEAD_NONE ? p.Dd * n : 0);
-  }
   pdl_wait();
   pdl_trigger();
   const float* yrow = p.onehot ? p.onehot + (size_t)b * n : nullptr;
@@ -143,15 +123,15 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(HeadP p) {
   if (p.w1) {
     for (int d = t; d < p.D; d += HEAD_THREADS) x[d] = __ldg(p.emb + (size_t)b * p.D + d);
     __syncthreads();
-    matvec_parts<false>(x, p.D, w1, p.H1, 1.f, pacc, psq, h1, nullptr, t);
-    for (int j = t; j < p.H1; j += HEAD_THREADS) h1[j] = fmaxf(h1[j] + b1[j], 0.f);
+    matvec_parts<false>(x, p.D, p.w1, p.H1, 1.f, pacc, psq, h1, nullptr, t);
+    for (int j = t; j < p.H1; j += HEAD_THREADS) h1[j] = fmaxf(h1[j] + __ldg(p.b1 + j), 0.f);
     __syncthreads();
-    matvec_parts<false>(h1, p.H1, w2, p.H2, 1.f, pacc, psq, h2, nullptr, t);
-    for (int j = t; j < p.H2; j += HEAD_THREADS) h2[j] = fmaxf(h2[j] + b2[j], 0.f);
+    matvec_parts<false>(h1, p.H1, p.w2, p.H2, 1.f, pacc, psq, h2, nullptr, t);
+    for (int j = t; j < p.H2; j += HEAD_THREADS) h2[j] = fmaxf(h2[j] + __ldg(p.b2 + j), 0.f);
     __syncthreads();
-    matvec_parts<false>(h2, p.H2, w3, n, 1.f, pacc, psq, h1, nullptr, t);      // h1[0..n) = logits - bias
+    matvec_parts<false>(h2, p.H2, p.w3, n, 1.f, pacc, psq, h1, nullptr, t);      // h1[0..n) = logits - bias
     if (t < 32) {
-      const float la = lane < n ? h1[lane] + b3[lane] : 0.f;
+      const float la = lane < n ? h1[lane] + __ldg(p.b3 + lane) : 0.f;
       const float pr = warp_softmax(la, lane, n);
       if (lane < n) {
         if (p.y_accent) p.y_accent[(size_t)b * n + lane] = pr;
@@ -177,7 +157,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(HeadP p) {
     ssq = block_sum(ssq, scratch);      // contains the barriers that publish x[]
     const bool normalise_x = p.head != SAR_HEAD_SOFTMAX && p.head != SAR_HEAD_CIRCLE_RAW;
     const float xinv = normalise_x ? 1.0f / sqrtf(fmaxf(ssq, 1e-12f)) : 1.f;
-    matvec_parts<true>(x, Dd, wd, n, xinv, pacc, psq, h2, wn, t);               // h2[c] = x^ . W[:, c]
+    matvec_parts<true>(x, Dd, p.wd, n, xinv, pacc, psq, h2, wn, t);               // h2[c] = x^ . W[:, c]
     if (t < 32) {
       const bool face = p.head == SAR_HEAD_SPHEREFACE || p.head == SAR_HEAD_COSFACE || p.head == SAR_HEAD_ARCFACE;
       float v = lane < n ? h2[lane] : 0.f;
@@ -262,16 +242,8 @@ extern "C" int sar_head_fwd(const float* emb, int D,
   if (hmax < HEAD_MAXC) hmax = HEAD_MAXC;
   size_t smem = sizeof(float) * ((size_t)dmax + 2 * (size_t)hmax + HEAD_MAXC + 32 + 2 * HEAD_THREADS);
   SAR_REQUIRE(smem <= 200 * 1024, SAR_ERR_UNSUPPORTED, "sar_head_fwd: embedding too wide");
-  auto pad4 = [](size_t c) { return (c + 3) & ~(size_t)3; };
-  const int Dd_eff = emb_d ? Dd : D;
-  size_t wfloats = 0;
-  if (has_cls) wfloats += pad4((size_t)D * H1) + pad4(H1) + pad4((size_t)H1 * H2) + pad4(H2) + pad4((size_t)H2 * n_classes) + pad4(n_classes);
-  if (head != SAR_HEAD_NONE) wfloats += pad4((size_t)Dd_eff * n_classes);
-  const bool wal = aligned16(w1) && aligned16(b1) && aligned16(w2) && aligned16(b2) && aligned16(w3) && aligned16(b3) && aligned16(wd);
-  const int w_smem = (wal && smem + (wfloats + 4) * sizeof(float) <= 160 * 1024) ? 1 : 0;
-  if (w_smem) smem += (wfloats + 4) * sizeof(float);
-  HeadP p{emb, D, w1, b1, H1, w2, b2, H2, w3, b3, emb_d, Dd_eff, wd, onehot, n_classes, head,
-          margin, s, gamma, w_smem, y_accent, y_accent_logits, y_disc, y_disc_logits, sample_stats};
+  HeadP p{emb, D, w1, b1, H1, w2, b2, H2, w3, b3, emb_d, emb_d ? Dd : D, wd, onehot, n_classes, head,
+          margin, s, gamma, y_accent, y_accent_logits, y_disc, y_disc_logits, sample_stats};
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("sar_head_fwd: %s", cudaGetErrorString(e)); return (int)e; }

@@ -225,6 +225,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const StemTcP p)
     const int m = quad * 32 + lane;                  // TMEM lane = A row
     const int P = ST_WP + 1;
     const int pj = et & 15;                 // pool role: 4-channel chunk (constant per thread)
+    const float4 sc4 = *reinterpret_cast<const float4*>(s_sc + 4 * pj);
+    const float4 sh4 = *reinterpret_cast<const float4*>(s_sh + 4 * pj);
     int g = 0;
     ST_PROF_DECL
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
@@ -237,7 +239,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const StemTcP p)
         mbar_wait(&tfull_bar[s], (uint32_t)(g >> 1) & 1u);
         ST_PROF(pr_wait)
         tc_fence_after();
-        // relu(bn(acc0 + acc1/2048)) of my 32 channels -> swizzled conv-row buffer
+        // raw conv sums acc0 + acc1/2048 of my 32 channels -> swizzled conv-row buffer (BN/ReLU happen in the pool)
         const int pos = tile * ST_MROWS + m;
         uint8_t* crow = c_base + pos * ST_CPITCH;
         const uint32_t tb = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * 128 + 32 * chalf);
@@ -248,14 +250,11 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const StemTcP p)
         if (m < ST_MROWS) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const int j = 8 * chalf + q;                     // 4-channel chunk
-            const float4 sc4 = *reinterpret_cast<const float4*>(s_sc + 4 * j);
-            const float4 sh4 = *reinterpret_cast<const float4*>(s_sh + 4 * j);
-            const float sc[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, sh[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
             float o[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e)                      // conv sum -> folded bias/BN -> ReLU (the pool is then a pure max)
-              o[e] = fmaxf(fmaf(fmaf(__uint_as_float(r1[4 * q + e]), 1.f / 2048.f, __uint_as_float(r0[4 * q + e])), sc[e], sh[e]), 0.f);
+            for (int e = 0; e < 4; ++e)
+              o[e] = fmaf(__uint_as_float(r1[4 * q + e]), 1.f / 2048.f, __uint_as_float(r0[4 * q + e]));
+            const int j = 8 * chalf + q;
             *reinterpret_cast<float4*>(crow + (j << 4)) = make_float4(o[0], o[1], o[2], o[3]);
           }
         }
@@ -265,48 +264,39 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const StemTcP p)
         ST_PROF(pr_work)
       }
       named_bar_sync(2, 256);
-      // ---- 3x3/s2 max-pool of the 9 (already BN'd and ReLU'd) conv rows: (pooled position, 4-channel chunk) per
-      // thread-item, 5 items per thread.  Taps outside the conv map are CLAMPED onto a valid tap of the same window
-      // (a duplicate never changes a max), so there is no masking.  The tap loops are OUTSIDE the item loop: every
-      // step has 5 independent LDS.128 in flight (the rolled item loop was latency bound: ~780 cycles per item).
-      constexpr int NIT = (ST_PH * ST_WP * 16) / 256;        // 5
-      const uint8_t* cb = c_base + (pj << 4);
-      int ro[NIT][3], co[NIT][3];
-      float4 mx[NIT];
-#pragma unroll
-      for (int i = 0; i < NIT; ++i) {
-        const int pp = (et >> 4) + 16 * i;
-        const int dh = pp / ST_WP, wp = pp - dh * ST_WP;
-#pragma unroll
-        for (int a = 0; a < 3; ++a) ro[i][a] = min(max(2 * dh + a, rlo), rhi) * (ST_WC * ST_CPITCH);
-#pragma unroll
-        for (int bb = 0; bb < 3; ++bb) co[i][bb] = min(max(2 * wp - p.ppl + bb, 0), ST_WC - 1) * ST_CPITCH;
-        mx[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-#pragma unroll
-      for (int a = 0; a < 3; ++a)
-#pragma unroll
-        for (int bb = 0; bb < 3; ++bb) {
-          float4 v[NIT];
-#pragma unroll
-          for (int i = 0; i < NIT; ++i) v[i] = *reinterpret_cast<const float4*>(cb + ro[i][a] + co[i][bb]);
-#pragma unroll
-          for (int i = 0; i < NIT; ++i) {
-            mx[i].x = fmaxf(mx[i].x, v[i].x); mx[i].y = fmaxf(mx[i].y, v[i].y);
-            mx[i].z = fmaxf(mx[i].z, v[i].z); mx[i].w = fmaxf(mx[i].w, v[i].w);
-          }
-        }
-#pragma unroll
-      for (int i = 0; i < NIT; ++i) {
+      // ---- BN + ReLU + 3x3/s2 max-pool of the 9 conv rows: (pooled position, 4-channel chunk) per thread-item.
+      // relu(max(.)) = max(0, .): start from 0 and skip rows / columns outside the conv map.
+#pragma unroll 1
+      for (int i = 0; i < (ST_PH * ST_WP * 16) / 256; ++i) {
         const int pp = (et >> 4) + 16 * i;
         const int dh = pp / ST_WP, wp = pp - dh * ST_WP;
         const int hp = hp0 + dh;
         if (hp >= p.Hp) continue;
-        const float4 m4 = mx[i];
-        const __half2 h01 = __floats2half2_rn(m4.x, m4.y), h23 = __floats2half2_rn(m4.z, m4.w);
+        // taps outside the conv map are CLAMPED onto a valid tap of the same window (a duplicate never changes
+        // a max), so there is no masking: 9 loads at row/column offsets, BN, max with 0 (= ReLU)
+        const uint8_t* cb = c_base + (pj << 4);
+        int ro[3], co[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) ro[a] = min(max(2 * dh + a, rlo), rhi) * (ST_WC * ST_CPITCH);
+#pragma unroll
+        for (int bb = 0; bb < 3; ++bb) co[bb] = min(max(2 * wp - p.ppl + bb, 0), ST_WC - 1) * ST_CPITCH;
+        float4 v[9];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int bb = 0; bb < 3; ++bb) v[3 * a + bb] = *reinterpret_cast<const float4*>(cb + ro[a] + co[bb]);
+        float4 mx = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          mx.x = fmaxf(mx.x, fmaf(v[k].x, sc4.x, sh4.x));
+          mx.y = fmaxf(mx.y, fmaf(v[k].y, sc4.y, sh4.y));
+          mx.z = fmaxf(mx.z, fmaf(v[k].z, sc4.z, sh4.z));
+          mx.w = fmaxf(mx.w, fmaf(v[k].w, sc4.w, sh4.w));
+        }
+        const __half2 h01 = __floats2half2_rn(mx.x, mx.y), h23 = __floats2half2_rn(mx.z, mx.w);
         const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-        const __half2 l01 = __floats2half2_rn((m4.x - f01.x) * 2048.f, (m4.y - f01.y) * 2048.f);
-        const __half2 l23 = __floats2half2_rn((m4.z - f23.x) * 2048.f, (m4.w - f23.y) * 2048.f);
+        const __half2 l01 = __floats2half2_rn((mx.x - f01.x) * 2048.f, (mx.y - f01.y) * 2048.f);
+        const __half2 l23 = __floats2half2_rn((mx.z - f23.x) * 2048.f, (mx.w - f23.y) * 2048.f);
         const long long row = (long long)n * Rimg + (long long)hp * P + wp;
         *reinterpret_cast<uint2*>(p.planes + (size_t)row * ST_F0 + 4 * pj) =
             make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
