@@ -112,7 +112,62 @@ __global__ void __launch_bounds__(CTC_THREADS) ctc_kernel(const float* __restric
   }
 }
 
+// Greedy CTC decode (K.ctc_decode(..., greedy=True), model.py:385-389 -> tf.nn.ctc_greedy_decoder with
+// merge_repeated=True): per frame the FIRST maximum over the C classes (softmax is monotone, so the pre-softmax
+// logits give the same path), then collapse repeats and drop blanks (blank = C-1).  One CTA per utterance: a warp
+// per frame for the argmax, one thread for the (<= S step) collapse.  dec (B, S) int32 padded with -1, len (B).
+__global__ void __launch_bounds__(CTC_THREADS) ctc_greedy_kernel(const float* __restrict__ logits, const int* __restrict__ in_len,
+                                                                  int fixed_len, int* __restrict__ dec, int* __restrict__ dec_len,
+                                                                  int S, int C, int ld) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ int best[];                 // [S]
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, b = blockIdx.x;
+  int T = in_len ? in_len[b] : fixed_len;
+  T = T < 0 ? 0 : (T > S ? S : T);
+  for (int f = warp; f < T; f += CTC_THREADS / 32) {
+    const float* row = logits + ((size_t)b * S + f) * ld;
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int c = lane; c < C; c += 32) {
+      const float v = __ldg(row + c);
+      if (v > bv) { bv = v; bi = c; }            // ascending c per lane: strict > keeps the first maximum
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) best[f] = bi;
+  }
+  __syncthreads();
+  for (int f = t; f < S; f += CTC_THREADS) dec[(size_t)b * S + f] = -1;
+  __syncthreads();
+  if (t == 0) {
+    const int blank = C - 1;
+    int prev = -1, n = 0;
+    for (int f = 0; f < T; ++f) {
+      const int v = best[f];
+      if (v != prev && v != blank) dec[(size_t)b * S + n++] = v;
+      prev = v;
+    }
+    dec_len[b] = n;
+  }
+}
+
 }  // namespace sar
+
+extern "C" int sar_ctc_greedy_fwd(const float* logits, int ld, const int* in_len, int fixed_len, int* dec, int* dec_len,
+                                  int B, int S, int C, void* stream) {
+  using namespace sar;
+  SAR_REQUIRE(logits && dec && dec_len, SAR_ERR_BAD_ARG, "sar_ctc_greedy_fwd: null pointer");
+  SAR_REQUIRE(B > 0 && S > 0 && C > 1 && ld >= C, SAR_ERR_BAD_ARG, "sar_ctc_greedy_fwd: bad dimension");
+  SAR_REQUIRE((size_t)S * sizeof(int) <= 48 * 1024, SAR_ERR_UNSUPPORTED, "sar_ctc_greedy_fwd: S too large");
+  launch_k(ctc_greedy_kernel, dim3(B), dim3(CTC_THREADS), (size_t)S * sizeof(int), (cudaStream_t)stream, logits, in_len, fixed_len,
+           dec, dec_len, S, C, ld);
+  return check_launch("sar_ctc_greedy_fwd");
+}
 
 extern "C" int sar_ctc_fwd(const float* logits, const float* labels, const int* in_len, const int* lab_len,
                            float* loss, float* probs, int* status, int B, int S, int C, int Lmax, void* stream) {

@@ -450,7 +450,7 @@ class SARNetEngine:
                         probe = self.forward({k: v.to(self.device) for k, v in sl.items()})
                         st.synchronize()
                         sink = {k: torch.zeros((B,) + tuple(v.shape[1:]), device=self.device, dtype=v.dtype)
-                                for k, v in probe.items() if k != "loss_vector"}
+                                for k, v in probe.items() if k != "loss_vector" and not k.startswith("__")}
                         if "_ctc_loss" in sink:                  # (B,1) model output = the kernel's (B,) vector
                             sink["y_ctc_loss"] = sink["_ctc_loss"].view(B, 1)
                         self._lane_sinks[(B, lanes)] = sink
@@ -577,6 +577,7 @@ class SARNetEngine:
                                               inputs["x_ctc_out_len"], want_probs=want_intermediates, classes=cfg.bpe_classes,
                                               loss=sink.get("_ctc_loss"), status=sink.get("ctc_status"))
             out["_ctc_loss"] = ctc_loss
+            out["__ctc_logits"] = logits             # (B, S, ld) pre-softmax, for the greedy decode (model.ctc_pred)
             out["y_ctc_loss"] = ctc_loss.reshape(B, 1)
             out["ctc_status"] = status
             if want_intermediates:

@@ -650,25 +650,29 @@ def sub_model(model: SARModel, input_name, output_name):
 
 
 def ctc_pred(model: SARModel, x, batch_size, input_len):
-    """model.py:385-389: greedy CTC decode of the ctc_pred posteriors (blank = C-1, merge
-    repeats).  Inference post-processing ('next' row): argmax on device, collapse on host."""
-    outs = []
+    """model.py:385-389: `K.ctc_decode(model.predict(x), [input_len]*n, greedy=True)[0][0]` -- the greedy CTC decode of
+    the ctc_pred posteriors (first maximum per frame, repeats merged, blank = C-1 dropped), dense (n, Lmax) int64 padded
+    with -1.  On device: the graphed step leaves the pre-softmax ctc_pred logits in HBM and sar_ctc_greedy_fwd decodes
+    them (argmax of the softmax = argmax of the logits); only the decoded ids travel to the host."""
+    if not model.config.ctc_enable:
+        raise SarnetError("ctc_pred needs a model built with ctc_enable=True")
     xd = model._as_dict(x)
     n = len(xd["x_data"])
-    for b0 in range(0, n, batch_size):
-        sl = {k: v[b0:b0 + batch_size] for k, v in xd.items()}
-        o = model.forward_device(sl, want_intermediates=True)
-        best = o["ctc_pred"][:, :input_len].argmax(-1).cpu().numpy()
-        blank = model.config.bpe_classes - 1
-        for row in best:
-            prev, seq = -1, []
-            for v in row:
-                if v != prev and v != blank:
-                    seq.append(int(v))
-                prev = v
-            outs.append(seq)
-    L = max([len(s) for s in outs] + [1])
-    dec = -np.ones((len(outs), L), dtype=np.int64)       # K.ctc_decode pads with -1
-    for i, s in enumerate(outs):
-        dec[i, :len(s)] = s
-    return dec
+    S = model.config.plan().seq_len
+    T = max(0, min(int(input_len), S))
+    rows = []
+    lanes, model.lanes = model.lanes, 1                  # the single-graph step keeps the ctc_pred logits
+    try:
+        for b0 in range(0, n, batch_size):
+            sl = {k: v[b0:b0 + batch_size] for k, v in xd.items()}
+            o = model.forward_device(sl)
+            dec, dec_len = ops.ctc_greedy(o["__ctc_logits"], fixed_len=T, classes=model.config.bpe_classes)
+            dec, dec_len = dec.cpu().numpy(), dec_len.cpu().numpy()
+            rows += [dec[i, :dec_len[i]] for i in range(len(dec))]
+    finally:
+        model.lanes = lanes
+    L = max([len(r) for r in rows] + [1])
+    out = -np.ones((len(rows), L), dtype=np.int64)       # K.ctc_decode pads with -1
+    for i, r in enumerate(rows):
+        out[i, :len(r)] = r
+    return out

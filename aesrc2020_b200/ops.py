@@ -227,6 +227,21 @@ def ctc(logits, labels, in_len, lab_len, *, want_probs=False, loss=None, status=
     return loss, status, probs
 
 
+def ctc_greedy(logits, in_len=None, *, fixed_len: int = 0, classes=None):
+    """sar_ctc_greedy_fwd: logits (B,S,ld) pre-softmax -> (dec (B,S) int32 padded with -1, dec_len (B,) int32)."""
+    logits = _f32(logits)
+    B, S, ld = logits.shape
+    Cc = int(classes) if classes else ld
+    if in_len is not None:
+        in_len = in_len.reshape(-1).to(torch.int32).contiguous()
+    dec = torch.empty((B, S), device=logits.device, dtype=torch.int32)
+    dec_len = torch.empty((B,), device=logits.device, dtype=torch.int32)
+    check(_shim.lib().sar_ctc_greedy_fwd(ptr(logits), ld, ptr(in_len), int(fixed_len), ptr(dec), ptr(dec_len), B, S, Cc,
+                                         stream_ptr()), "sar_ctc_greedy_fwd")
+    _count(1)
+    return dec, dec_len
+
+
 def loss_reduce(sample_stats=None, ctc_loss=None, bn_stats=None, B: Optional[int] = None):
     ref = sample_stats if sample_stats is not None else (ctc_loss if ctc_loss is not None else bn_stats)
     B = B or ref.shape[0]

@@ -243,6 +243,14 @@ int sar_ctc_fwd(const float* logits, const float* labels, const int* in_len, con
 int sar_ctc_ld_fwd(const float* logits, int ld, const float* labels, const int* in_len, const int* lab_len,
                    float* loss, float* probs, int* status, int B, int S, int C, int Lmax, void* stream);
 
+/* Greedy CTC decode of the ctc_pred posteriors from PRE-softmax logits (rows `ld` >= C floats apart).
+ * Replaces: ctc_pred() = K.ctc_decode(pred, input_len, greedy=True) (model.py:385-389; tf.nn.ctc_greedy_decoder with
+ * merge_repeated=True): per frame the first maximum over the C classes, repeats merged, blank = C-1 dropped.
+ * in_len (B) int32 or null (then every utterance uses fixed_len, as the reference's constant input_len does).
+ * dec (B,S) int32, padded with -1 like the dense tensor K.ctc_decode returns; dec_len (B) int32. */
+int sar_ctc_greedy_fwd(const float* logits, int ld, const int* in_len, int fixed_len, int* dec, int* dec_len,
+                       int B, int S, int C, void* stream);
+
 /* Deterministic batch reduction of per-sample statistics into the 8-float vector that is
  * all-reduced across GPUs (one ncclAllReduce(SUM), replaces multi_gpu_model, model.py:193-194):
  * out8 = [sum loss_accent, sum loss_disc, sum loss_ctc, sum loss_disc_bn,

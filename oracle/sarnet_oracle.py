@@ -346,6 +346,29 @@ def ctc_batch_cost(labels, probs, in_len, lab_len):
 # --------------------------------------------------------------------------
 # the whole forward (model.py:204-371)
 # --------------------------------------------------------------------------
+def ctc_greedy_decode(probs, input_len: int):
+    """ctc_pred(), model.py:385-389: K.ctc_decode(pred, [input_len]*n, greedy=True)[0][0] -- tf.nn.ctc_greedy_decoder
+    with merge_repeated=True on log(pred): per frame the first maximum over the classes, consecutive repeats merged,
+    then blanks (C-1) dropped; returned dense (n, Lmax) int64 padded with -1 (sparse_to_dense default_value=-1)."""
+    pr = probs.detach().cpu().numpy() if hasattr(probs, "detach") else np.asarray(probs)
+    n, S, C = pr.shape
+    T = max(0, min(int(input_len), S))
+    rows = []
+    for b in range(n):
+        best = pr[b, :T].argmax(-1)                      # np.argmax: first maximum
+        prev, seq = -1, []
+        for v in best:
+            if v != prev and v != C - 1:
+                seq.append(int(v))
+            prev = v
+        rows.append(seq)
+    L = max([len(r) for r in rows] + [1])
+    out = -np.ones((n, L), dtype=np.int64)
+    for i, r in enumerate(rows):
+        out[i, :len(r)] = r
+    return out
+
+
 def sar_net_forward(params: Dict[str, np.ndarray], inputs: Dict[str, np.ndarray], *,
                     ctc_enable=False, ar_enable=True, disc_enable=False, res_type="res18",
                     res_filters=64, hidden_dim=256, bn_dim=0, bpe_classes=1000, accent_classes=8,

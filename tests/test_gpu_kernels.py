@@ -304,3 +304,33 @@ def test_bad_arguments_are_rejected(cuda_device):
                   torch.zeros(2, 384, device="cuda"))
     with pytest.raises(_shim.SarnetError):
         ops.layernorm(torch.zeros(4, 8), torch.ones(8), torch.zeros(8))        # host tensors at the boundary
+
+
+def test_ctc_greedy_decode_vs_oracle(cuda_device):
+    """sar_ctc_greedy_fwd on padded logit rows vs the oracle's restatement of K.ctc_decode(greedy=True): exact ids."""
+    from aesrc2020_b200 import ops
+    rng = np.random.RandomState(11)
+    B, S, C, ld = 9, 37, 50, 64
+    logits = rng.randn(B, S, C).astype(np.float32)
+    peak = rng.randint(0, C, size=(B, S))
+    peak[:, 5:9] = peak[:, 5:6]                          # repeats to merge
+    peak[0] = C - 1                                      # all blank -> empty row
+    for b in range(B):
+        for t in range(S):
+            logits[b, t, peak[b, t]] += 6.0
+    logits[3, 2, :] = 1.0                                # exact tie -> class 0
+    padded = torch.full((B, S, ld), 1e30, device="cuda", dtype=torch.float32)
+    padded[..., :C] = dev(logits)
+    for T in (S, 20, 1):
+        dec, n = ops.ctc_greedy(padded, fixed_len=T, classes=C)
+        dec, n = dec.cpu().numpy(), n.cpu().numpy()
+        want = O.ctc_greedy_decode(torch.softmax(t64(logits), -1), T)
+        L = want.shape[1]
+        assert int(n.max()) == (want >= 0).sum(1).max()
+        assert np.array_equal(dec[:, :L], want) and (dec[:, L:] == -1).all()
+    lens = torch.from_numpy(rng.randint(0, S + 1, size=B).astype(np.int32)).cuda()
+    dec, n = ops.ctc_greedy(padded, lens, classes=C)
+    for b in range(B):
+        want = O.ctc_greedy_decode(torch.softmax(t64(logits[b:b + 1]), -1), int(lens[b]))[0]
+        want = want[want >= 0]
+        assert dec[b, :int(n[b])].cpu().numpy().tolist() == want.tolist()

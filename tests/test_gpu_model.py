@@ -276,3 +276,15 @@ def test_pipelined_slots_are_bitwise_the_single_stream_step(cuda_device):
         torch.cuda.synchronize()
         for g, r in zip(got, ref):
             assert all(torch.equal(g[k], r[k]) for k in names), rep
+
+
+def test_ctc_pred_greedy_decode_matches_posteriors(cuda_device):
+    """mdl.ctc_pred (model.py:385-389) through the graphed step + sar_ctc_greedy_fwd = the oracle's greedy decode of the
+    SAME device posteriors (the `ctc_pred` intermediate), for full and truncated input_len."""
+    from aesrc2020_b200 import model as mdl
+    model, x, _ = build("cfg5_gvlad_circle_ctc")
+    probs = model.forward_device(x, want_intermediates=True)["ctc_pred"].cpu().numpy()
+    S = probs.shape[1]
+    for T in (S, S // 2):
+        got = mdl.ctc_pred(model, x, batch_size=2, input_len=T)
+        assert np.array_equal(got, O.ctc_greedy_decode(probs, T))

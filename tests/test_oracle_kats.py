@@ -330,3 +330,18 @@ def test_forward_output_contract_and_order():
     assert torch.allclose(out["y_accent"].sum(-1), torch.ones(2, dtype=D))
     with pytest.raises(SystemExit):
         O.sar_net_forward(w, x, **{**cfg.model_kwargs(), "mto": None})       # model.py:136-138
+
+
+def test_ctc_greedy_decode_known_answers():
+    """ctc_pred (model.py:385-389): merge repeats THEN drop blanks (blank = C-1), first maximum on ties, frames beyond
+    input_len ignored, -1 padding."""
+    C = 5                                    # blank = 4
+    path = [[1, 1, 4, 1, 2, 2, 4, 4, 3], [4, 4, 4, 4, 4, 4, 4, 4, 4], [0, 4, 0, 0, 3, 3, 3, 1, 4]]
+    pr = np.full((3, 9, C), 0.1)
+    for b, row in enumerate(path):
+        for t, c in enumerate(row):
+            pr[b, t, c] = 0.6
+    pr[2, 1, :] = 0.2                        # a tie over all classes -> class 0 (first maximum), merges with the 0 before
+    got = O.ctc_greedy_decode(pr, 9)
+    assert got.tolist() == [[1, 1, 2, 3], [-1, -1, -1, -1], [0, 3, 1, -1]]
+    assert O.ctc_greedy_decode(pr, 4).tolist() == [[1, 1], [-1, -1], [0, -1]]
