@@ -54,6 +54,8 @@ SIGNATURES = {
                              c_fp, c_int, c_fp, c_fp, c_int, c_int, c_f, c_f, c_f,
                              c_fp, c_fp, c_fp, c_fp, c_fp, c_int, C.c_void_p]),
     "sar_ctc_fwd": (c_int, [c_fp, c_fp, c_ip, c_ip, c_fp, c_fp, c_ip, c_int, c_int, c_int, c_int, C.c_void_p]),
+    "sar_feat_batch_fwd": (c_int, [c_fp, c_ip, c_fp, c_int, c_int, c_int, C.c_void_p]),
+    "sar_labels_pack_fwd": (c_int, [c_ip, c_int, c_fp, c_ip, c_ip, c_int, c_int, c_fp, c_ip, c_ip, c_ip, c_int, C.c_void_p]),
     "sar_ctc_greedy_fwd": (c_int, [c_fp, c_int, c_ip, c_int, c_ip, c_ip, c_int, c_int, c_int, C.c_void_p]),
     "sar_ctc_ld_fwd": (c_int, [c_fp, c_int, c_fp, c_ip, c_ip, c_fp, c_fp, c_ip, c_int, c_int, c_int, c_int, C.c_void_p]),
     "sar_loss_reduce_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, C.c_void_p]),

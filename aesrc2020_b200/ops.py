@@ -252,6 +252,38 @@ def loss_reduce(sample_stats=None, ctc_loss=None, bn_stats=None, B: Optional[int
     return out8
 
 
+def feat_batch(feats, frame_offsets, T: int):
+    """sar_feat_batch_fwd: feats (total frames, D) fp32 + frame_offsets (B+1) int64 -> x_data (B,T,D)."""
+    feats = _f32(feats)
+    B = frame_offsets.numel() - 1
+    D = int(feats.shape[1])
+    x = torch.empty((B, T, D), device=feats.device, dtype=torch.float32)
+    check(_shim.lib().sar_feat_batch_fwd(ptr(feats), ptr(frame_offsets), ptr(x), B, T, D, stream_ptr()), "sar_feat_batch_fwd")
+    _count(1)
+    return x
+
+
+def labels_pack(accent=None, n_classes=0, trans=None, trans_offsets=None, Lmax=0, encoder_len=0):
+    """sar_labels_pack_fwd -> dict with x_accent (B,n) and/or x_ctc_label (B,Lmax) f32, x_ctc_out_len / x_ctc_in_len
+    (B,1) int32, and `status` (1,) int32."""
+    ref = accent if accent is not None else trans_offsets
+    dev = ref.device
+    B = accent.numel() if accent is not None else trans_offsets.numel() - 1
+    out = {"status": torch.zeros((1,), device=dev, dtype=torch.int32)}
+    onehot = lab = olen = ilen = None
+    if accent is not None:
+        onehot = out["x_accent"] = torch.empty((B, n_classes), device=dev, dtype=torch.float32)
+    if trans_offsets is not None:
+        lab = out["x_ctc_label"] = torch.empty((B, Lmax), device=dev, dtype=torch.float32)
+        olen = out["x_ctc_out_len"] = torch.empty((B, 1), device=dev, dtype=torch.int32)
+        ilen = out["x_ctc_in_len"] = torch.empty((B, 1), device=dev, dtype=torch.int32)
+    check(_shim.lib().sar_labels_pack_fwd(ptr(accent), int(n_classes), ptr(onehot), ptr(trans), ptr(trans_offsets), int(Lmax),
+                                          int(encoder_len), ptr(lab), ptr(olen), ptr(ilen), ptr(out["status"]), B,
+                                          stream_ptr()), "sar_labels_pack_fwd")
+    _count(1)
+    return out
+
+
 def fbank(wav, offsets, melfb_t, Fmax: int, T: int):
     """wav (N,) float32 concatenated utterances, offsets (B+1,) int64 -> x_data (B,T,80)."""
     wav = _f32(wav)

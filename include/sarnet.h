@@ -273,6 +273,23 @@ int sar_loss_reduce_fwd(const float* sample_stats, const float* ctc_loss, const 
 int sar_fbank_fwd(const float* wav, const long long* offsets, const float* melfb_t,
                   float* feat_ws, float* x_data, int B, int Fmax, int T, void* stream);
 
+/* ---- on-device batch assembly (the callers' side of the path: utils.data_loader, utils.py:71-117) ---------- */
+
+/* x_data[b] = feat_reshape(feat_norm(feat_b), T) (utils.py:35-46,91): per-utterance, per-bin sklearn MinMaxScaler
+ * over ALL frames of the utterance (zero range -> scale 1), then truncate / zero-pad to T frames.
+ * feats (total frames, D) fp32: the un-padded feature matrices of the batch, concatenated (ONE upload);
+ * frame_offsets (B+1) int64; x_data (B,T,D) output.  D <= 512. */
+int sar_feat_batch_fwd(const float* feats, const long long* frame_offsets, float* x_data, int B, int T, int D, void* stream);
+
+/* Label packing of data_loader: onehot (B,n_classes) = to_categorical(accent) (utils.py:100; null to skip);
+ * ctc_label (B,Lmax) fp32 = text_ids_norm(trans_b, Lmax) -- truncate, pad with EOS_ID = 2 (utils.py:57-63,95; null to
+ * skip), ctc_out_len (B) = min(len, Lmax), ctc_in_len (B) = encoder_len (utils.py:96-97).  trans: concatenated int32
+ * token ids, trans_offsets (B+1) int64.  status (1) int32 optional: bit 0 set when an accent id is outside
+ * [0, n_classes) (to_categorical raises). */
+int sar_labels_pack_fwd(const int* accent, int n_classes, float* onehot,
+                        const int* trans, const long long* trans_offsets, int Lmax, int encoder_len,
+                        float* ctc_label, int* ctc_out_len, int* ctc_in_len, int* status, int B, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

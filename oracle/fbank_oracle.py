@@ -92,3 +92,36 @@ def feat_reshape(feat: np.ndarray, max_len: int = 1200) -> np.ndarray:
 def wav_to_x_data(signal: np.ndarray, max_len: int) -> np.ndarray:
     """make_fbank.py:27 -> utils.py:91,102: (max_len, 80, 1) float32 model input."""
     return np.float32(feat_reshape(feat_norm(fbank(signal)), max_len)[:, :, None])
+
+
+def data_loader(lst, ctc_enable=False, ar_enable=False, disc_enable=False, data_dct=None, accent_dct=None, trans_dct=None,
+                max_input_len=1200, max_ctc_len=72, encoder_len=100, accent_classes=8, bn=0):
+    """utils.py:71-117 restated with numpy (feat_norm / feat_reshape above; text_ids_norm utils.py:57-63 with EOS_ID = 2;
+    to_categorical): `data_dct[utt]` is the (frames, dims) feature matrix itself (the reference unpickles it, utils.py:91)."""
+    inputs, in_len, lab_len, labels, accents = [], [], [], [], []
+    for utt in lst:
+        inputs.append(feat_reshape(feat_norm(np.asarray(data_dct[utt], dtype=np.float64)), max_input_len))
+        if ctc_enable and trans_dct:
+            ids = list(trans_dct[utt])[:max_ctc_len]
+            in_len.append(encoder_len)
+            lab_len.append(min(len(trans_dct[utt]), max_ctc_len))
+            labels.append(ids + [2] * (max_ctc_len - len(ids)))
+        if ar_enable and accent_dct:
+            oh = np.zeros(accent_classes, dtype=np.float32)      # keras to_categorical: dtype="float32"
+            oh[int(accent_dct[utt])] = 1.0
+            accents.append(oh)
+    input_data = {"x_data": np.float32(np.expand_dims(np.asarray(inputs), axis=3))}
+    output_data = {}
+    if ctc_enable:
+        input_data["x_ctc_in_len"] = np.int32(np.expand_dims(np.asarray(in_len), axis=1))
+        input_data["x_ctc_out_len"] = np.int32(np.expand_dims(np.asarray(lab_len), axis=1))
+        input_data["x_ctc_label"] = np.float32(np.asarray(labels))
+        output_data["y_ctc_loss"] = np.zeros([len(lst)])
+    if ar_enable:
+        output_data["y_accent"] = np.asarray(accents)
+    if disc_enable:
+        input_data["x_accent"] = np.asarray(accents)
+        output_data["y_disc"] = np.asarray(accents)
+        if bn:
+            output_data["y_disc_bn"] = np.asarray(accents)
+    return input_data, output_data

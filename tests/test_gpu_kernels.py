@@ -334,3 +334,40 @@ def test_ctc_greedy_decode_vs_oracle(cuda_device):
         want = O.ctc_greedy_decode(torch.softmax(t64(logits[b:b + 1]), -1), int(lens[b]))[0]
         want = want[want >= 0]
         assert dec[b, :int(n[b])].cpu().numpy().tolist() == want.tolist()
+
+
+def test_data_loader_on_device_vs_oracle(cuda_device, tmp_path):
+    """utils.data_loader: sar_feat_batch_fwd + sar_labels_pack_fwd against the oracle's restatement of
+    utils.py:71-117 -- ragged utterances (1 frame ... longer than max_input_len), a constant column, pickle paths and
+    in-memory arrays, truncated transcripts; the result feeds model inputs unchanged."""
+    from aesrc2020_b200 import utils as us, _shim
+    from oracle import fbank_oracle as FO
+    import pickle
+    rng = np.random.RandomState(5)
+    lst = ["u%d" % i for i in range(7)]
+    frames = [37, 120, 64, 333, 1, 100, 99]
+    data = {u: (rng.rand(n, 80) * 40 - 5).astype(np.float32) for u, n in zip(lst, frames)}
+    data["u2"][:, 7] = 3.25
+    acc = {u: str((3 * i) % 8) for i, u in enumerate(lst)}
+    trans = {u: [int(v) for v in rng.randint(3, 999, size=n)] for u, n in zip(lst, [4, 90, 1, 72, 10, 73, 30])}
+    paths = dict(data)
+    for u in lst[:3]:                                        # the reference stores pickles (utils.py:14-22,91)
+        p = tmp_path / (u + ".pkl")
+        with open(p, "wb") as f:
+            pickle.dump(data[u], f)
+        paths[u] = str(p)
+    kw = dict(max_input_len=100, max_ctc_len=72, encoder_len=13, accent_classes=8, bn=1)
+    got_x, got_y = us.data_loader(lst, True, True, True, paths, acc, trans, **kw)
+    want_x, want_y = FO.data_loader(lst, True, True, True, data, acc, trans, **kw)
+    assert set(got_x) == set(want_x) and set(got_y) == set(want_y)
+    for k, w in want_x.items():
+        g = got_x[k].cpu().numpy()
+        assert g.shape == w.shape and g.dtype == w.dtype, k
+        if k == "x_data":
+            assert np.abs(g - w).max() < 2e-6
+            assert not g[4, 1:].any() and not g[0, 37:].any()      # zero padding
+        else:
+            assert np.array_equal(g, w), k
+    assert np.array_equal(got_y["y_disc_bn"].cpu().numpy(), want_y["y_disc_bn"])
+    with pytest.raises(_shim.SarnetError):
+        us.data_loader(lst, False, True, True, data, dict(acc, u3="8"), None, **kw)

@@ -288,3 +288,24 @@ def test_ctc_pred_greedy_decode_matches_posteriors(cuda_device):
     for T in (S, S // 2):
         got = mdl.ctc_pred(model, x, batch_size=2, input_len=T)
         assert np.array_equal(got, O.ctc_greedy_decode(probs, T))
+
+
+def test_data_loader_feeds_predict_without_host_round_trip(cuda_device):
+    """utils.data_loader's device tensors go straight into model.predict (zero-copy path) and give what the host-assembled
+    batch (oracle data_loader -> numpy -> predict) gives."""
+    from aesrc2020_b200 import utils as us
+    from oracle import fbank_oracle as FO
+    model, _, _ = build("cfg5_gvlad_circle_ctc")
+    rng = np.random.RandomState(8)
+    lst = ["a", "b", "c"]
+    data = {u: rng.rand(n, 80).astype(np.float32) * 9 for u, n in zip(lst, [480, 500, 650])}
+    acc = {"a": 1, "b": 7, "c": 0}
+    trans = {u: [int(v) for v in rng.randint(3, 998, size=n)] for u, n in zip(lst, [5, 9, 3])}
+    kw = dict(max_input_len=500, max_ctc_len=72, encoder_len=model.config.plan().seq_len, accent_classes=8)
+    xd, _ = us.data_loader(lst, True, True, True, data, acc, trans, **kw)
+    xh, _ = FO.data_loader(lst, True, True, True, data, acc, trans, **kw)
+    got = model.predict(xd, batch_size=3)
+    want = model.predict(xh, batch_size=3)
+    assert all(isinstance(g, torch.Tensor) and g.is_cuda for g in got)
+    for g, w in zip(got, want):
+        assert np.allclose(g.cpu().numpy(), w, rtol=2e-4, atol=1e-6)

@@ -50,3 +50,31 @@ def test_feat_reshape_pad_and_truncate():
     assert p.shape == (9, 2) and np.array_equal(p[:6], f) and (p[6:] == 0).all()
     x = FO.wav_to_x_data(np.random.RandomState(2).randn(8000), 60)
     assert x.shape == (60, 80, 1) and x.dtype == np.float32 and (x[49:] == 0).all()
+
+
+def test_data_loader_oracle_matches_sklearn_and_reference_contract():
+    """oracle data_loader (utils.py:71-117): x_data against sklearn's MinMaxScaler itself (the reference's MMS), label
+    packing against the reference's text_ids_norm / to_categorical semantics, shapes and dtypes of utils.py:102-116."""
+    from sklearn.preprocessing import MinMaxScaler
+    from oracle import fbank_oracle as FO
+    rng = np.random.RandomState(3)
+    lst = ["u%d" % i for i in range(5)]
+    frames = [37, 120, 64, 200, 1]
+    data = {u: rng.rand(n, 80) * 50 for u, n in zip(lst, frames)}
+    data["u2"][:, 7] = 3.25                                 # constant column -> zeros
+    acc = {u: str(i % 8) for i, u in enumerate(lst)}
+    trans = {u: list(rng.randint(3, 999, size=n)) for u, n in zip(lst, [4, 90, 1, 72, 10])}
+    x, y = FO.data_loader(lst, True, True, True, data, acc, trans, max_input_len=100, max_ctc_len=72, encoder_len=13, bn=1)
+    assert x["x_data"].shape == (5, 100, 80, 1) and x["x_data"].dtype == np.float32
+    for i, u in enumerate(lst):
+        want = MinMaxScaler().fit_transform(data[u])
+        n = min(frames[i], 100)
+        assert np.allclose(x["x_data"][i, :n, :, 0], want[:n], atol=1e-6)
+        assert not x["x_data"][i, n:].any()
+    assert x["x_ctc_label"].dtype == np.float32 and x["x_ctc_label"].shape == (5, 72)
+    assert x["x_ctc_label"][0].tolist() == [float(v) for v in trans["u0"]] + [2.0] * 68
+    assert x["x_ctc_label"][1].tolist() == [float(v) for v in trans["u1"][:72]]
+    assert x["x_ctc_out_len"].reshape(-1).tolist() == [4, 72, 1, 72, 10] and x["x_ctc_out_len"].dtype == np.int32
+    assert x["x_ctc_in_len"].reshape(-1).tolist() == [13] * 5 and x["x_ctc_in_len"].shape == (5, 1)
+    assert x["x_accent"].argmax(1).tolist() == [0, 1, 2, 3, 4] and x["x_accent"].sum() == 5
+    assert set(y) == {"y_ctc_loss", "y_accent", "y_disc", "y_disc_bn"}
