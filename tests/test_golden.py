@@ -150,3 +150,57 @@ def test_cuda_layers_match_reference_source(cuda_device):
     for gm, m in ((256, 0.25), (256, 0.2), (64, 0.4)):
         got = ls.circle_loss(c(g["circle/y"]), c(g["circle/cos"]), gamma=gm, margin=m)
         assert rel_err(got, g["circle/g%d_m%g" % (gm, m)], floor=1e-3) < REL_TOL
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# utils.data_loader: fixture made by the reference's own utils.py (tests/golden/make_golden_utils.py)
+def _utils_fixture():
+    z = np.load(os.path.join(GOLD, "utils_data_loader.npz"))
+    lst = [str(u) for u in z["in/lst"]]
+    fo = np.concatenate([[0], np.cumsum(z["in/frames"])])
+    to = np.concatenate([[0], np.cumsum(z["in/trans_len"])])
+    data = {u: z["in/feats"][fo[i]:fo[i + 1]] for i, u in enumerate(lst)}
+    acc = {u: int(z["in/accent"][i]) for i, u in enumerate(lst)}
+    trans = {u: [int(v) for v in z["in/trans"][to[i]:to[i + 1]]] for i, u in enumerate(lst)}
+    kw = {k[3:]: int(z[k]) for k in z.files if k.startswith("kw/")}
+    return z, lst, data, acc, trans, kw
+
+
+def test_oracle_data_loader_reproduces_the_reference_utils_fixture():
+    """oracle/fbank_oracle.data_loader == the reference's utils.data_loader (utils.py:71-117, real sklearn MinMaxScaler)
+    on ragged pickled features: x_data to float32 rounding, every label tensor exactly, dtypes and shapes."""
+    from oracle import fbank_oracle as FO
+    z, lst, data, acc, trans, kw = _utils_fixture()
+    x, y = FO.data_loader(lst, True, True, True, data, acc, trans, **kw)
+    assert {"x/" + k for k in x} | {"y/" + k for k in y} == {k for k in z.files if k[:2] in ("x/", "y/")}
+    for k, v in list(x.items()) + list(y.items()):
+        ref = z[("x/" if k in x else "y/") + k]
+        assert v.shape == ref.shape and v.dtype == ref.dtype, k
+        if k == "x_data":
+            assert np.abs(v - ref).max() < 3e-7
+        else:
+            assert np.array_equal(v, ref), k
+    # the helper known answers of the same fixture
+    from aesrc2020_b200 import utils as us
+    assert us.text_ids_norm(list(range(10, 30)), 8) == z["text_ids_norm/long"].tolist()
+    assert us.text_ids_norm([5, 6], 8) == z["text_ids_norm/short"].tolist()
+    assert np.array_equal(us.feat_reshape(np.arange(12.0).reshape(3, 4), 5), z["feat_reshape/pad"])
+    assert np.array_equal(us.feat_reshape(np.arange(12.0).reshape(3, 4), 2), z["feat_reshape/cut"])
+    assert us.cal_descriptors(1200, 80) == int(z["cal_descriptors_1200_80"]) == 114
+
+
+@pytest.mark.gpu
+def test_device_data_loader_reproduces_the_reference_utils_fixture(cuda_device):
+    """aesrc2020_b200.utils.data_loader (sar_feat_batch_fwd + sar_labels_pack_fwd) == the reference's utils.data_loader
+    fixture: x_data within fp32 arithmetic of the float64 MinMaxScaler, labels exactly."""
+    from aesrc2020_b200 import utils as us
+    z, lst, data, acc, trans, kw = _utils_fixture()
+    x, y = us.data_loader(lst, True, True, True, data, acc, trans, **kw)
+    for k, v in list(x.items()) + list(y.items()):
+        ref = z[("x/" if k in x else "y/") + k]
+        got = v.cpu().numpy() if hasattr(v, "cpu") else np.asarray(v)
+        assert got.shape == ref.shape and got.dtype == ref.dtype, k
+        if k == "x_data":
+            assert np.abs(got - ref).max() < 2e-6
+        else:
+            assert np.array_equal(got, ref), k
