@@ -304,8 +304,12 @@ class SARModel:
         _weights.save_weights(path, self.weights)
 
     def load_weights(self, path, by_name=True, skip_mismatch=True):
-        """model.py:181-183 semantics: load by name, silently skip shape mismatches."""
+        """model.py:181-183 semantics: load by name, silently skip shape mismatches.  An `.npz` keyed by KERAS weight
+        names (`conv2d_1/kernel:0`, ...: `np.savez(path, **{w.name: v ...})` on the TF side) is mapped
+        to the canonical names first (weights.keras_weight_names)."""
         loaded = _weights.load_weights(path)
+        if any(k.endswith(":0") for k in loaded):
+            loaded = _weights.from_keras_named(self.config, loaded)
         for k, v in loaded.items():
             if k in self.weights and tuple(self.weights[k].shape) == tuple(v.shape):
                 self.weights[k] = np.ascontiguousarray(v, dtype=np.float32)

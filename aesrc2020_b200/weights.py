@@ -10,8 +10,11 @@ Model-level layer names are the reference's explicit Keras names (model.py:252-3
 95-106).  ResNet layers have no stable Keras names (resnet.py passes no `name=`), so
 they get canonical names resnet/s{stage}b{block}/{bn1,conv1,bn2,conv2,short}.
 
-Files are `.npz` (h5py is not available in this image; the .h5 importer is a
-"next" row).
+Files are `.npz`.  h5py is not available in this image, so the HDF5 container of a Keras `.h5`
+checkpoint is not parsed here; its NAMING half is: `keras_weight_names(cfg)` gives the
+Keras weight name (`conv2d_7/kernel:0`, `CRNN/forward_cu_dnngru_1/bias:0`, ...) of every canonical weight,
+and `from_keras_named` / `SARModel.load_weights` accept an `.npz` keyed by those names, which one line
+on the TF side produces.  The tensor layouts need no conversion (see above).
 """
 from __future__ import annotations
 
@@ -167,3 +170,58 @@ def save_weights(path: str, weights: Dict[str, np.ndarray]) -> None:
 def load_weights(path: str) -> Dict[str, np.ndarray]:
     with np.load(path) as z:
         return {k.replace("|", "/"): z[k] for k in z.files}
+
+
+def keras_weight_names(cfg: SARConfig) -> "OrderedDict[str, str]":
+    """canonical weight name -> the name Keras gives that weight in a FRESH session (`layer.weights[i].name`, the
+    `weight_names` attribute of a `.h5` checkpoint), for the graph model.SAR_Net(cfg) builds.
+
+    Layers the reference names keep their names (model.py:252-322).  The unnamed ones are called
+    `<snake_case(class)>_<uid>` with the uid counted per class from 1 in CREATION order (keras Layer.__init__): the ResNet's
+    Conv2D / BatchNormalization (resnet.py passes no `name=`; per block: bn_a, conv_a, bn_b, conv_b, then the shortcut
+    conv -- resnet.py:111-123,82) and the CuDNNGRU inside every Bidirectional, whose two copies Bidirectional renames
+    `forward_<name>` / `backward_<name>`.  weight_shapes(cfg) is in creation order, so walking it reproduces the uids;
+    pinned by tests/golden/keras_names.json (the reference's own model.py executed on minikeras)."""
+    out: "OrderedDict[str, str]" = OrderedDict()
+    uid = {"conv2d": 0, "batch_normalization": 0, "cu_dnngru": 0}
+    layer_of: Dict[str, str] = {}
+    for name in weight_shapes(cfg):
+        parts = name.split("/")
+        weight = parts[-1]
+        if len(parts) >= 3 and parts[-2] in ("forward", "backward"):
+            owner = "/".join(parts[:-2])                                  # the Bidirectional layer (named)
+            if owner not in layer_of:
+                uid["cu_dnngru"] += 1
+                layer_of[owner] = "cu_dnngru_%d" % uid["cu_dnngru"]
+            out[name] = "%s/%s_%s/%s:0" % (owner, parts[-2], layer_of[owner], weight)
+            continue
+        layer = "/".join(parts[:-1])
+        if layer.startswith("resnet/"):
+            if layer not in layer_of:
+                kind = "batch_normalization" if weight in ("gamma", "beta", "moving_mean", "moving_variance") else "conv2d"
+                uid[kind] += 1
+                layer_of[layer] = "%s_%d" % (kind, uid[kind])
+            out[name] = "%s/%s:0" % (layer_of[layer], weight)
+        else:
+            out[name] = "%s/%s:0" % (layer, weight)
+    return out
+
+
+def from_keras_named(cfg: SARConfig, named) -> Dict[str, np.ndarray]:
+    """Canonical weights from a mapping keyed by Keras weight names (`conv2d_1/kernel:0`; the HDF5 spelling
+    `conv2d_1/conv2d_1/kernel:0` and names without the `:0` suffix are accepted too).  Missing or mis-shaped entries are
+    skipped like load_weights(by_name=True, skip_mismatch=True) does (model.py:181-183); layouts are Keras' own."""
+    def norm(k):
+        k = k[:-2] if k.endswith(":0") else k
+        p = k.split("/")
+        if len(p) >= 3 and p[0] == p[1]:
+            p = p[1:]
+        return "/".join(p)
+    src = {norm(k): v for k, v in named.items()}
+    shapes = weight_shapes(cfg)
+    out = {}
+    for canon, kname in keras_weight_names(cfg).items():
+        v = src.get(norm(kname))
+        if v is not None and tuple(np.shape(v)) == tuple(shapes[canon]):
+            out[canon] = np.ascontiguousarray(v, dtype=np.float32)
+    return out

@@ -24,7 +24,16 @@ LAYERS = []
 RNG = np.random.RandomState(0)
 QUEUE = None            # optional list of (canonical_name, array): weights handed out in creation order
 USED = []               # (canonical_name, owning layer) for every weight taken from QUEUE
+UIDS = {}               # Keras-style per-prefix layer counters (K.get_uid), reset with the graph
 K_EPS = 1e-7
+
+
+def _snake(name):
+    """keras.engine.base_layer._to_snake_case: Conv2D -> conv2d, BatchNormalization -> batch_normalization,
+    CuDNNGRU -> cu_dnngru."""
+    import re
+    inter = re.sub("(.)([A-Z][a-z0-9]+)", r"\1_\2", name)
+    return re.sub("([a-z])([A-Z])", r"\1_\2", inter).lower()
 
 
 def reset(seed=0, queue=None):
@@ -36,6 +45,7 @@ def reset(seed=0, queue=None):
     FEED.clear()
     del LAYERS[:]
     del USED[:]
+    UIDS.clear()
     RNG.seed(seed)
     QUEUE = list(queue) if queue is not None else None
 
@@ -108,6 +118,15 @@ def _init(shape, kind):
 class Layer:
     def __init__(self, name=None, **kwargs):
         self.name = name
+        # [KERAS-SEMANTICS] Layer.__init__: an unnamed layer is called <snake_case(class)>_<uid>, the uid counted per
+        # prefix from 1 in a fresh session; a named layer consumes no uid.  `name` stays None for unnamed layers
+        # (the creation-order checks of _take rely on it); `keras_name` is what Keras would have called the layer.
+        if name is None:
+            prefix = _snake(type(self).__name__)
+            UIDS[prefix] = UIDS.get(prefix, 0) + 1
+            self.keras_name = "%s_%d" % (prefix, UIDS[prefix])
+        else:
+            self.keras_name = name
         self.weights = {}
         self.built = False
         LAYERS.append(self)
@@ -335,8 +354,13 @@ class Bidirectional(Layer):
         super().__init__(name)
         LAYERS.remove(layer)                    # the wrapped layer is owned by this one
         self.fwd = layer
-        self.bwd = CuDNNGRU(layer.units, return_sequences=layer.return_sequences)
+        # [KERAS-SEMANTICS] Bidirectional: backward_layer = layer.__class__.from_config(layer.get_config()) -- same name,
+        # no new uid -- then forward_layer.name = 'forward_' + name, backward_layer.name = 'backward_' + name
+        base = layer.keras_name
+        self.bwd = CuDNNGRU(layer.units, return_sequences=layer.return_sequences, name=base)
+        self.bwd.name = None
         LAYERS.remove(self.bwd)
+        self.fwd.keras_name, self.bwd.keras_name = "forward_" + base, "backward_" + base
         self.merge_mode = merge_mode
 
     def build(self, shp):

@@ -204,3 +204,49 @@ def test_device_data_loader_reproduces_the_reference_utils_fixture(cuda_device):
             assert np.abs(got - ref).max() < 2e-6
         else:
             assert np.array_equal(got, ref), k
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Keras weight names (the naming half of the .h5 importer)
+def test_keras_weight_names_match_the_reference_creation_order():
+    """weights.keras_weight_names == the names obtained by executing the reference's model.py / resnet.py on minikeras
+    with Keras' layer auto-naming rule (tests/golden/make_golden_names.py), for all 8 fixture graphs; and SURVEY
+    Appendix A's spot values (shortcut convs are created last in a block: conv2d_4, conv2d_11)."""
+    with open(os.path.join(GOLD, "keras_names.json")) as f:
+        fx = json.load(f)
+    assert len(fx) == 8
+    for case, rec in fx.items():
+        cfg = SARConfig(input_shape=(rec["T"], 80, 1), **rec["kwargs"])
+        got = W.keras_weight_names(cfg)
+        assert list(got) == list(W.weight_shapes(cfg))
+        assert dict(got) == rec["names"], case
+    n = fx["cfg2_gvlad_arcface"]["names"]
+    assert n["resnet/s1b1/short/kernel"] == "conv2d_4/kernel:0" and n["resnet/s2b1/short/kernel"] == "conv2d_11/kernel:0"
+    assert n["CRNN/backward/recurrent_kernel"] == "CRNN/backward_cu_dnngru_1/recurrent_kernel:0"
+
+
+def test_keras_named_npz_loads_into_canonical_weights(tmp_path):
+    """An .npz keyed by Keras weight names (what `np.savez(path, **{w.name: v})` writes on the TF side), in either the
+    `layer/weight:0` or the HDF5 `layer/layer/weight:0` spelling, maps back to the canonical container; entries with a
+    wrong shape or unknown name are skipped (load_weights(by_name=True, skip_mismatch=True), model.py:181-183)."""
+    cfg = SARConfig(input_shape=(200, 80, 1), ctc_enable=True, disc_enable=True, res_type="res18", res_filters=16, mto="bigru",
+                    metric_loss="cosface")
+    w = W.init_weights(cfg, seed=5)
+    names = W.keras_weight_names(cfg)
+    assert sum(1 for v in names.values() if "cu_dnngru_3" in v) == 6          # CRNN, CTC_BIGRU, AR_MERGE in creation order
+    keras = {names[k]: v for k, v in w.items()}
+    back = W.from_keras_named(cfg, keras)
+    assert set(back) == set(w) and all(np.array_equal(back[k], w[k]) for k in w)
+    h5 = {("%s/%s" % (k.split("/")[0], k)): v for k, v in keras.items()}
+    back = W.from_keras_named(cfg, h5)
+    assert set(back) == set(w)
+    keras["conv2d_1/kernel:0"] = np.zeros((3, 3, 1, 16), np.float32)             # wrong shape -> skipped
+    keras["not_a_layer/kernel:0"] = np.zeros(3, np.float32)
+    back = W.from_keras_named(cfg, keras)
+    assert "resnet/stem/kernel" not in back and len(back) == len(w) - 1
+    p = str(tmp_path / "keras_named.npz")
+    np.savez(p, **{names[k]: v for k, v in w.items()})
+    loaded = W.load_weights(p)
+    assert any(k.endswith(":0") for k in loaded)
+    back = W.from_keras_named(cfg, loaded)
+    assert all(np.array_equal(back[k], w[k]) for k in w)

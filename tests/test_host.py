@@ -147,3 +147,18 @@ def test_synthetic_batch_contract_and_utils():
     assert us.text_ids_norm([5, 6, 7], 5) == [5, 6, 7, 2, 2] and us.text_ids_norm(list(range(9)), 4) == [0, 1, 2, 3]
     assert us.cal_descriptors(1200, 80) == 114                                              # utils.py:193
     assert fb.num_frames(16000 * 5) == 499 and fb.mel_filterbank().shape == (80, 257)
+
+
+def test_model_load_weights_accepts_a_keras_named_npz(tmp_path, capsys):
+    """SARModel.load_weights maps an .npz keyed by Keras weight names (`conv2d_1/kernel:0`, ...) to the canonical names."""
+    from aesrc2020_b200 import model as mdl, weights as W
+    kw = dict(disc_enable=True, res_type="res18", res_filters=16, mto="avg", metric_loss="softmax")
+    m, _ = mdl.SAR_Net((200, 80, 1), seed=3, **kw)
+    o, _ = mdl.SAR_Net((200, 80, 1), seed=4, **kw)
+    capsys.readouterr()
+    names = W.keras_weight_names(m.config)
+    p = str(tmp_path / "keras_named.npz")
+    np.savez(p, **{names[k]: v for k, v in m.weights.items()})
+    assert not np.array_equal(o.weights["resnet/stem/kernel"], m.weights["resnet/stem/kernel"])
+    o.load_weights(p)
+    assert all(np.array_equal(o.weights[k], m.weights[k]) for k in m.weights)
