@@ -47,6 +47,7 @@ SIGNATURES = {
     "sar_vlad_fwd": (c_int, [c_fp] * 6 + [c_int] * 5 + [C.c_void_p]),
     "sar_vlad_planes_fwd": (c_int, [c_fp] * 7 + [c_int] * 5 + [C.c_void_p]),
     "sar_splitk_reduce_fwd": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_int, C.c_void_p]),
+    "sar_softmax_rows_fwd": (c_int, [c_fp, c_int, c_fp, c_ll, c_int, C.c_void_p]),
     "sar_avgpool_fwd": (c_int, [c_fp, c_fp, c_int, c_int, c_int, C.c_void_p]),
     "sar_gemm_splitk_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
     "sar_gemm_splitk_fwd": (c_int, [c_fp] * 4 + [c_int] * 3 + [C.c_void_p, c_sz, C.c_void_p]),

@@ -1,5 +1,8 @@
 // api.cu -- error channel and library identification for libsarnet_sm100.so
 #include <stdlib.h>
+#include <mutex>
+#include <utility>
+#include <vector>
 #include "common.cuh"
 
 namespace sar {
@@ -9,6 +12,28 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+int allow_max_smem_impl(const void* fn, const char* what) {
+  static std::mutex mu;
+  static std::vector<std::pair<int, const void*>> done;      // (device, function) pairs already raised
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(mu);
+  for (const auto& d : done)
+    if (d.first == dev && d.second == fn) return SAR_OK;
+  // the opt-in limit covers static + dynamic shared memory: leave room for the kernel's static allocations
+  cudaFuncAttributes fa{};
+  cudaError_t e = cudaFuncGetAttributes(&fa, fn);
+  int optin = 0;
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (e == cudaSuccess) {
+    long long lim = (long long)optin - (long long)fa.sharedSizeBytes;
+    if (lim > (long long)SAR_MAX_DYN_SMEM) lim = (long long)SAR_MAX_DYN_SMEM;
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim);
+  }
+  if (e != cudaSuccess) { set_error("%s: cudaFuncSetAttribute(max dynamic shared memory): %s", what, cudaGetErrorString(e)); return (int)e; }
+  done.emplace_back(dev, fn);
+  return SAR_OK;
 }
 bool pdl_enabled() {
   static int on = -1;

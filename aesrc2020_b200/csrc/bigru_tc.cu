@@ -253,8 +253,11 @@ bigru_tc_kernel(const float* __restrict__ xp, const float* __restrict__ rec, con
     const int ub = UPT * o * 2;                                  // byte offset of my units in the 64-byte row
     const uint32_t my_off = (uint32_t)(n * GT_ROWB + (((ub >> 4) ^ ((n >> 1) & 3)) << 4) + (ub & 15));
     // threads 0..7 push the block to CTA rank + t of the cluster (atom `rank` there, and that atom's barrier)
-    const uint32_t rdst = gt_mapa(b_u + (uint32_t)(rank * B_ATOM), (uint32_t)((rank + t) & 7));
-    const uint32_t rbar = gt_mapa(hbar_u + (uint32_t)(rank * 8), (uint32_t)((rank + t) & 7));
+    // (both buffers' addresses are mapped one by one: compute-sanitizer's memcheck rejects an offset added to a
+    // mapa result -- "not located in remote CTA" -- although the hardware accepts it)
+    const uint32_t peer = (uint32_t)((rank + t) & 7);
+    const uint32_t rdst_a = gt_mapa(b_u + (uint32_t)(rank * B_ATOM), peer), rdst_b = gt_mapa(b_u + (uint32_t)(rank * B_ATOM + B_BUF), peer);
+    const uint32_t rbar_a = gt_mapa(hbar_u + (uint32_t)(rank * 8), peer), rbar_b = gt_mapa(hbar_u + (uint32_t)(rank * 8 + GT_CL * 8), peer);
 #ifdef SAR_GRU_PROFILE
     long long stamps[32];
 #endif
@@ -309,7 +312,7 @@ bigru_tc_kernel(const float* __restrict__ xp, const float* __restrict__ rec, con
         fence_proxy_async();                        // the bulk copy reads shared memory through the async proxy
         named_bar_sync(2, GT_GATE_THREADS);
         if (t < GT_CL)
-          bulk_push(rdst + (uint32_t)((cur ^ 1) * B_BUF), sb, (uint32_t)B_ATOM, rbar + (uint32_t)((cur ^ 1) * GT_CL * 8));
+          bulk_push(cur ? rdst_a : rdst_b, sb, (uint32_t)B_ATOM, cur ? rbar_a : rbar_b);
       }
       if (bvalid) {
         const int tt = dir ? (S - 1 - step) : step;
@@ -338,19 +341,34 @@ bigru_tc_kernel(const float* __restrict__ xp, const float* __restrict__ rec, con
   }
 }
 
-int bigru_tc_launch(const float* xp, const float* rec, const float* rbias, float* out, int B, int S, int seq, int nb_req, cudaStream_t stream) {
+static int bigru_tc_launch(const float* xp, const float* rec, const float* rbias, float* out, int B, int S, int seq, int nb_req, cudaStream_t stream) {
   static const int force_nb = getenv("SAR_GRU_NB") ? atoi(getenv("SAR_GRU_NB")) : 0;     // experiments: 16 or 32
   const int nb = force_nb ? force_nb : (nb_req ? nb_req : (2 * ((B + 15) / 16) <= GT_MAX_CLUSTERS ? 16 : 32));
   auto launch = [&](auto kern, size_t smem, int NBv) -> int {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("sar_bigru_fwd(tc): %s", cudaGetErrorString(e)); return (int)e; }
+    { const int arc = allow_max_smem(kern, "sar_bigru_fwd"); if (arc) return arc; }
     const int groups = (B + NBv - 1) / NBv;
     launch_k(kern, dim3(GT_CL * groups * 2), dim3(GT_THREADS), smem, stream, xp, rec, rbias, out, B, S, seq);
     return 0;
   };
   const int rc = nb == 16 ? launch(bigru_tc_kernel<16>, GtCfg<16>::SMEM, 16) : launch(bigru_tc_kernel<32>, GtCfg<32>::SMEM, 32);
   if (rc) return rc;
-  return check_launch("sar_bigru_fwd(tc)");
+  return check_launch("sar_bigru_fwd");
 }
 
 }  // namespace sar
+
+extern "C" int sar_bigru_fwd(const float* xp, const float* rec, const float* rbias, float* out,
+                             int B, int S, int u, int seq, void* stream) {
+  return sar_bigru_nb_fwd(xp, rec, rbias, out, B, S, u, seq, 0, stream);
+}
+
+extern "C" int sar_bigru_nb_fwd(const float* xp, const float* rec, const float* rbias, float* out,
+                                int B, int S, int u, int seq, int nb, void* stream) {
+  using namespace sar;
+  SAR_REQUIRE(nb == 0 || nb == 16 || nb == 32, SAR_ERR_BAD_ARG, "sar_bigru_nb_fwd: nb must be 0 (auto), 16 or 32");
+  SAR_REQUIRE(xp && rec && rbias && out, SAR_ERR_BAD_ARG, "sar_bigru_fwd: null pointer");
+  SAR_REQUIRE(B > 0 && S > 0, SAR_ERR_BAD_ARG, "sar_bigru_fwd: non-positive dimension");
+  SAR_REQUIRE(u == GT_U, SAR_ERR_UNSUPPORTED, "sar_bigru_fwd: hidden size %d unsupported (this build: %d)", u, GT_U);
+  SAR_REQUIRE(aligned16(xp) && aligned16(rbias) && aligned16(out), SAR_ERR_BAD_ARG, "sar_bigru_fwd: pointers must be 16-byte aligned");
+  return bigru_tc_launch(xp, rec, rbias, out, B, S, seq, nb, (cudaStream_t)stream);
+}

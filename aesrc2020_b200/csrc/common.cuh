@@ -48,10 +48,37 @@ inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
   return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
+// Cooperative launch: the driver guarantees that EVERY CTA of the grid is resident at once (or refuses the launch)
+// -- required by kernels whose CTAs wait on each other (conv_tc_chain_kernel spins on tile counters that other CTAs
+// of the same launch publish).  A cooperative launch is a full dependency on the previous kernel (no programmatic
+// overlap), which the chain's griddepcontrol instructions tolerate (they are no-ops then).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k_coop(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #endif
+
+// Dynamic shared memory above 48 KB is an opt-in per (device, function).  It is raised ONCE to the device maximum and
+// never lowered: a per-launch cudaFuncSetAttribute(exact size) left the function's attribute at whatever the LAST
+// launch of that instantiation needed, and tools that re-launch a captured graph's kernel nodes one by one (ncu's
+// graph-node profiling) then saw LaunchFailed for nodes captured with a larger size (ncu_rc = 9).
+int allow_max_smem_impl(const void* fn, const char* what);
+template <typename... KArgs>
+inline int allow_max_smem(void (*kern)(KArgs...), const char* what) {
+  return allow_max_smem_impl(reinterpret_cast<const void*>(kern), what);
+}
+constexpr size_t SAR_MAX_DYN_SMEM = 227 * 1024;
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

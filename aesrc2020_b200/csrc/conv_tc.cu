@@ -1203,8 +1203,7 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
     size_t smem = fixed + (size_t)sp.nslab * 2 * sp.slab_bytes + (size_t)nb * 2 * sp.bplane_bytes;
     if (p.epi_alias && smem - fixed < (size_t)EPI_BYTES) smem = fixed + EPI_BYTES;    // aliased staging needs 64 KB of operand region
     auto launch = [&](auto kern) -> int {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) { set_error("sar_conv_tc_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+      { const int arc = allow_max_smem(kern, "sar_conv_tc_fwd"); if (arc) return arc; }
       launch_k(kern, dim3(grid), dim3(SL_THREADS), smem, (cudaStream_t)stream, mapA, mapS, mapWm, mapWs, p, sp);
       return 0;
     };
@@ -1228,8 +1227,7 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
   } else {
     p.stages = p.epi_alias ? 3 : 2;
     const size_t smem = 1024 + (size_t)p.stages * TC_STAGE_BYTES + (p.epi_alias ? 0 : EPI_BYTES) + 256 + 3 * (size_t)d->cout * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("sar_conv_tc_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    { const int arc = allow_max_smem(conv_tc_kernel, "sar_conv_tc_fwd"); if (arc) return arc; }
     launch_k(conv_tc_kernel, dim3(grid), dim3(TC_THREADS), smem, (cudaStream_t)stream, mapA, mapS, mapWm, mapWs, p);
   }
   return check_launch("sar_conv_tc_fwd");
@@ -1329,9 +1327,17 @@ extern "C" int sar_conv_tc_chain_fwd(const sar_tc_conv* descs, int n, void* work
   const int grid = tiles < sms ? tiles : sms;
   const size_t smem = fixed + (size_t)sp.nslab * slab1 + (size_t)sp.nring * 2 * sp.bplane_bytes;
   auto launch = [&](auto kern) -> int {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("sar_conv_tc_chain_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-    launch_k(kern, dim3(grid), dim3(SL_THREADS), smem, (cudaStream_t)stream, cp);
+    { const int arc = allow_max_smem(kern, "sar_conv_tc_chain_fwd"); if (arc) return arc; }
+    // every CTA spin-waits on counters other CTAs of this launch publish: the whole grid must be co-resident.
+    // cooperative launch makes the driver guarantee it (MPS / green contexts / a concurrent kernel could otherwise
+    // leave waiting CTAs resident and their producers unscheduled).  SAR_CHAIN_COOP=0: plain PDL launch (A/B aid).
+    static const bool coop = !(getenv("SAR_CHAIN_COOP") && getenv("SAR_CHAIN_COOP")[0] == '0');
+    int nblk = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, kern, SL_THREADS, smem);
+    if (nblk * sms < grid) { set_error("sar_conv_tc_chain_fwd: grid of %d CTAs cannot be co-resident (%d per SM x %d SMs)", grid, nblk, sms); return SAR_ERR_UNSUPPORTED; }
+    cudaError_t le = coop ? launch_k_coop(kern, dim3(grid), dim3(SL_THREADS), smem, (cudaStream_t)stream, cp)
+                          : launch_k(kern, dim3(grid), dim3(SL_THREADS), smem, (cudaStream_t)stream, cp);
+    if (le != cudaSuccess) { set_error("sar_conv_tc_chain_fwd: launch: %s", cudaGetErrorString(le)); return (int)le; }
     return 0;
   };
   const int lrc = g0.kc_main == 64 ? launch(conv_tc_chain_kernel<64>) : launch(conv_tc_chain_kernel<32>);

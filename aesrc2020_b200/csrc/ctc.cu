@@ -182,8 +182,7 @@ extern "C" int sar_ctc_ld_fwd(const float* logits, int ld, const float* labels, 
   const int NE = 2 * Lmax + 1;
   size_t smem = sizeof(float) * ((size_t)S * NE + 2 * NE) + sizeof(int) * NE;
   SAR_REQUIRE(smem <= 227 * 1024, SAR_ERR_UNSUPPORTED, "sar_ctc_fwd: S*(2*Lmax+1) too large for shared memory (%zu B)", smem);
-  cudaError_t e = cudaFuncSetAttribute(ctc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) { set_error("sar_ctc_fwd: %s", cudaGetErrorString(e)); return (int)e; }
+  { const int arc = allow_max_smem(ctc_kernel, "sar_ctc_fwd"); if (arc) return arc; }
   launch_k(ctc_kernel, dim3(B), dim3(CTC_THREADS), smem, (cudaStream_t)stream, logits, labels, in_len, lab_len, loss, probs, status, S, C, ld, Lmax);
   return check_launch("sar_ctc_fwd");
 }

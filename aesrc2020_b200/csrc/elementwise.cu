@@ -155,9 +155,57 @@ static inline unsigned grid_for(long long total, int threads) {
   return (unsigned)(g < cap ? (g > 0 ? g : 1) : cap);
 }
 
+// Row softmax (Dense(..., activation='softmax'), model.py:35-42,268; the ctc_pred posteriors K.ctc_decode reads,
+// model.py:385-389): one warp per row, the row is read twice (max, then exp/sum with the values kept in registers for
+// C <= 1024, re-read beyond), written once.  `ld` >= C is the row pitch of the input (tensor-core ctc_pred pads 1000
+// classes to 1024 columns); the output is dense (rows, C).
+__global__ void softmax_rows_kernel(const float* __restrict__ x, int ld, float* __restrict__ out, long long rows, int C) {
+  pdl_wait();
+  pdl_trigger();
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + (size_t)row * ld;
+  float* orow = out + (size_t)row * C;
+  constexpr int KEEP = 32;                           // values per lane kept in registers (C <= 1024)
+  float v[KEEP];
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < KEEP; ++i) {
+    const int c = lane + 32 * i;
+    v[i] = c < C ? __ldg(xr + c) : -INFINITY;
+    m = fmaxf(m, v[i]);
+  }
+  for (int c = lane + 32 * KEEP; c < C; c += 32) m = fmaxf(m, __ldg(xr + c));
+  m = warp_max(m);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < KEEP; ++i) {
+    v[i] = (lane + 32 * i < C) ? expf(v[i] - m) : 0.f;
+    sum += v[i];
+  }
+  for (int c = lane + 32 * KEEP; c < C; c += 32) sum += expf(__ldg(xr + c) - m);
+  sum = warp_sum(sum);
+#pragma unroll
+  for (int i = 0; i < KEEP; ++i) {
+    const int c = lane + 32 * i;
+    if (c < C) orow[c] = v[i] / sum;
+  }
+  for (int c = lane + 32 * KEEP; c < C; c += 32) orow[c] = expf(__ldg(xr + c) - m) / sum;
+}
+
 }  // namespace sar
 
 extern "C" {
+
+int sar_softmax_rows_fwd(const float* x, int ld, float* out, long long rows, int C, void* stream) {
+  using namespace sar;
+  SAR_REQUIRE(x && out, SAR_ERR_BAD_ARG, "sar_softmax_rows_fwd: null pointer");
+  SAR_REQUIRE(rows > 0 && C > 0 && ld >= C, SAR_ERR_BAD_ARG, "sar_softmax_rows_fwd: need rows > 0, 0 < C <= ld");
+  const int warps = 8;
+  launch_k(softmax_rows_kernel, dim3((unsigned)((rows + warps - 1) / warps)), dim3(warps * 32), 0, (cudaStream_t)stream, x, ld, out, rows, C);
+  return check_launch("sar_softmax_rows_fwd");
+}
 
 int sar_maxpool2d_fwd(const float* x, float* out, int B, int H, int W, int C, int Ho, int Wo,
                       int k, int stride, int pad_t, int pad_l, void* stream) {

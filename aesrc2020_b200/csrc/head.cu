@@ -244,10 +244,7 @@ extern "C" int sar_head_fwd(const float* emb, int D,
   SAR_REQUIRE(smem <= 200 * 1024, SAR_ERR_UNSUPPORTED, "sar_head_fwd: embedding too wide");
   HeadP p{emb, D, w1, b1, H1, w2, b2, H2, w3, b3, emb_d, emb_d ? Dd : D, wd, onehot, n_classes, head,
           margin, s, gamma, y_accent, y_accent_logits, y_disc, y_disc_logits, sample_stats};
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("sar_head_fwd: %s", cudaGetErrorString(e)); return (int)e; }
-  }
+  { const int arc = allow_max_smem(head_kernel, "sar_head_fwd"); if (arc) return arc; }
   launch_k(head_kernel, dim3(B), dim3(HEAD_THREADS), smem, (cudaStream_t)stream, p);
   return check_launch("sar_head_fwd");
 }

@@ -189,8 +189,7 @@ extern "C" int sar_stem_pool_fwd(const float* x, const float* w, const float* bi
   if (p.XW < D + p.pl + 4) p.XW = (D + p.pl + 7) & ~3;
   const size_t smem = sizeof(float) * ((size_t)49 * F0 + (size_t)SP_IR * p.XW + (size_t)SP_CR * p.Wc * F0);
   SAR_REQUIRE(smem <= 113 * 1024, SAR_ERR_UNSUPPORTED, "sar_stem_pool_fwd: feature dim too wide for shared memory (%zu B)", smem);
-  cudaError_t e = cudaFuncSetAttribute(stem_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) { set_error("sar_stem_pool_fwd: %s", cudaGetErrorString(e)); return (int)e; }
+  { const int arc = allow_max_smem(stem_pool_kernel, "sar_stem_pool_fwd"); if (arc) return arc; }
   dim3 grid((p.Hp + SP_PH - 1) / SP_PH, B);
   launch_k(stem_pool_kernel, dim3(grid), dim3(SP_THREADS), smem, (cudaStream_t)stream, p);
   return check_launch("sar_stem_pool_fwd");

@@ -331,8 +331,7 @@ int stem_tc_launch(const float* x, const float* w, const float* bias, const floa
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const size_t smem = 1024 + 5 * (size_t)ST_APLANE + ST_CS_BYTES + 2 * ST_XBUF + 128 + 2 * ST_F0 * sizeof(float);
-  cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) { set_error("sar_stem_pool_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+  { const int arc = allow_max_smem(stem_tc_kernel, "sar_stem_pool_fwd"); if (arc) return arc; }
   const int grid = p.n_items < sms ? p.n_items : sms;
   launch_k(stem_tc_kernel, dim3(grid), dim3(ST_THREADS), smem, stream, p);
   return check_launch("sar_stem_pool_fwd(tc)");

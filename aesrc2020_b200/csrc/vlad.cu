@@ -240,8 +240,7 @@ extern "C" int sar_vlad_planes_fwd(const float* feat, const float* w_assign, con
   int wa_smem = (!score && vlad_smem_floats(S, D, K + G, true) * sizeof(float) <= limit) ? 1 : 0;
   size_t smem = vlad_smem_floats(S, D, K + G, wa_smem != 0) * sizeof(float);
   SAR_REQUIRE(smem <= limit, SAR_ERR_UNSUPPORTED, "sar_vlad_fwd: S*D too large for shared memory (%zu B)", smem);
-  cudaError_t e = cudaFuncSetAttribute(vlad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) { set_error("sar_vlad_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+  { const int arc = allow_max_smem(vlad_kernel, "sar_vlad_fwd"); if (arc) return arc; }
   launch_k(vlad_kernel, dim3(B), dim3(VLAD_THREADS), smem, (cudaStream_t)stream, feat, w_assign, b_assign, score, centers, out, reinterpret_cast<__half*>(out_planes), S, D, K, G, wa_smem);
   return check_launch("sar_vlad_fwd");
 }

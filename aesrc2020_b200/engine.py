@@ -7,6 +7,7 @@ No PyTorch math is on the path: torch only allocates buffers.
 """
 from __future__ import annotations
 
+from dataclasses import dataclass
 from typing import Dict, List, Optional
 
 import numpy as np
@@ -16,6 +17,24 @@ from . import ops
 from .config import SARConfig, ResNetPlan
 
 BN_EPS = 1e-3      # Keras BatchNormalization default epsilon (resnet.py:25, model.py:29-30)
+
+
+@dataclass(frozen=True)
+class StepOpts:
+    """How ONE step is launched.  Passed explicitly down the call chain (never stored on the engine or in a module
+    global), so that several steps -- pipeline slots, micro-batch lanes, threads -- can be captured concurrently.
+
+    lane      buffer namespace: steps that may be in flight at the same time never share activation buffers
+    no_chain  per-layer conv launches only (no persistent stage-chain launch: a chain needs its whole grid resident)
+    gru_nb    utterances per Bi-GRU cluster (0 = the kernel's choice, 32 = fewer SMs per step)
+    """
+    lane: int = 0
+    no_chain: bool = False
+    gru_nb: int = 0
+
+
+DEFAULT_OPTS = StepOpts()
+SLOT_OPTS = lambda slot: StepOpts(lane=slot, no_chain=True, gru_nb=32)
 
 
 def fold_bn(w: Dict[str, np.ndarray], name: str):
@@ -97,8 +116,6 @@ class ResNetTC:
         self._bufs: Dict[tuple, list] = {}
         self._rot: Dict[tuple, int] = {}
         self.record_events = None
-        self.lane = 0            # buffer namespace: concurrent micro-batch lanes never share activation buffers
-        self.no_chain = False    # forward_slot: per-layer launches only
         import os as _os
         # stages whose stride-1 layers run as one persistent chain launch (SAR_CHAIN_STAGES="" disables)
         self.chain_stages = {int(x) for x in _os.environ.get("SAR_CHAIN_STAGES", "2,3,4").split(",") if x.strip()}
@@ -129,22 +146,23 @@ class ResNetTC:
     def bn(self, name):
         return (self.p[name + "/scale"], self.p[name + "/shift"]) if name else None
 
-    def _buf(self, B, H, W, C, split, role):
-        """2-slot rotation of zero-initialised plane buffers per (geometry, role)."""
-        key = (self.lane, B, H, W, C, bool(split), role)
+    def _buf(self, lane, B, H, W, C, split, role):
+        """2-slot rotation of zero-initialised plane buffers per (lane, geometry, role)."""
+        key = (lane, B, H, W, C, bool(split), role)
         if key not in self._bufs:
             self._bufs[key] = [self.tc.alloc_planes(B, H, W, C, split, self.device) for _ in range(2)]
             self._rot[key] = 0
         self._rot[key] ^= 1
         return self._bufs[key][self._rot[key]]
 
-    def forward(self, x: torch.Tensor, as_planes: bool = False):
+    def forward(self, x: torch.Tensor, as_planes: bool = False, opts: StepOpts = DEFAULT_OPTS):
         """x (B,T,80,1) fp32 -> (B,H',W',C) after the final BN->ReLU: fp32 NHWC, or (as_planes) the hi/lo
         planes a tensor-core Dense consumes directly."""
         tc, pl, p = self.tc, self.plan, self.p
         B = x.shape[0]
         st = pl.stem
-        cur = self._buf(B, pl.pool_hout, pl.pool_wout, st.cout, False, "raw")   # the first block is never strided
+        lane = opts.lane
+        cur = self._buf(lane, B, pl.pool_hout, pl.pool_wout, st.cout, False, "raw")   # the first block is never strided
         if st.cout % 16 == 0 and st.cout <= 64 and st.wout % 4 == 0:
             s_, t_ = self.bn(st.post_bn)                                        # fused stem: conv+BN+ReLU+pool
             tc.stem_pool(x, p["stem/kernel"], p["stem/bias"], s_, t_, cur)
@@ -173,7 +191,7 @@ class ResNetTC:
             if len(pending) == 1:
                 tc.conv_launch(pending[0])
             else:
-                key = ("chain", self.lane, B, stage, len(pending))
+                key = ("chain", lane, B, stage, len(pending))
                 if key not in self._bufs:
                     self._bufs[key] = tc.chain_workspace(pending, self.device)
                 tc.conv_tc_chain(pending, self._bufs[key])
@@ -182,7 +200,7 @@ class ResNetTC:
         def emit(desc, chainable):
             # lanes run concurrently on separate streams: a chain launch (CTAs spinning on tile counters of CTAs of
             # the SAME launch) needs its whole grid resident, which two lanes sharing the SMs cannot promise
-            if chainable and stage in self.chain_stages and self.lane == 0 and not self.no_chain:
+            if chainable and stage in self.chain_stages and not opts.no_chain:
                 pending.append(desc)
             else:
                 flush()
@@ -195,7 +213,7 @@ class ResNetTC:
             if first:
                 flush()
                 stage += 1
-            c1_act = self._buf(B, c1.hout, c1.wout, c1.cout, False, "c1")
+            c1_act = self._buf(lane, B, c1.hout, c1.wout, c1.cout, False, "c1")
             emit(tc.conv_desc(cur_act, p[b.name + "/w1"], p[b.name + "/b1"], out_hw=(c1.hout, c1.wout),
                               taps=tc.tap_table(3, 3, c1.stride, c1.pad_t, c1.pad_l, c1.wout), cout=c1.cout,
                               out_act=c1_act, act=self.bn(c2.pre_bn)), chainable=not first)
@@ -204,13 +222,13 @@ class ResNetTC:
                           res=None if b.short else cur_raw)
             if nxt is not None:
                 ns = nxt.conv1.stride == 2
-                nraw = self._buf(B, c2.hout, c2.wout, c2.cout, ns, "raw")
-                nact = self._buf(B, c2.hout, c2.wout, c2.cout, ns, "act")
+                nraw = self._buf(lane, B, c2.hout, c2.wout, c2.cout, ns, "raw")
+                nact = self._buf(lane, B, c2.hout, c2.wout, c2.cout, ns, "act")
                 emit(tc.conv_desc(c1_act, p[b.name + "/w2"], p[b.name + "/b2"], out_raw=nraw, out_act=nact,
                                   act=self.bn(nxt.conv1.pre_bn), **common), chainable=True)
                 cur_raw, cur_act = nraw, nact
             elif as_planes:
-                out_dense = self._buf(B, c2.hout, c2.wout, c2.cout, False, "final")
+                out_dense = self._buf(lane, B, c2.hout, c2.wout, c2.cout, False, "final")
                 emit(tc.conv_desc(c1_act, p[b.name + "/w2"], p[b.name + "/b2"], act=self.bn(pl.final_bn),
                                   out_act=out_dense, **common), chainable=True)
             else:
@@ -234,19 +252,28 @@ class SARNetEngine:
         self.conv_path = conv_path
         tc_ok = all(c.cin % 32 == 0 and c.cout % 32 == 0 for c in self.plan.convs()[1:])
         if conv_path == "tc" and not tc_ok:
-            conv_path = self.conv_path = "ffma"   # channel counts not multiples of 32: CUDA-core kernel
+            # The tcgen05 kernels tile channels in chunks of 32.  Other widths (e.g. res_filters=16) run the
+            # hand-written CUDA-core kernels (csrc/conv_ffma.cu) -- still this library on the GPU, but a different,
+            # much slower code path: say so instead of selecting it silently ("Supported shapes").
+            import warnings
+            warnings.warn("aesrc2020_b200: res_filters=%d gives channel counts that are not multiples of 32; the residual "
+                          "blocks run on the CUDA-core conv_ffma kernels instead of the tcgen05 tensor-core path"
+                          % cfg.res_filters, RuntimeWarning, stacklevel=3)
+            conv_path = self.conv_path = "ffma"
         self.resnet = (ResNetTC if conv_path == "tc" else ResNetDevice)(self.plan, weights, self.device)
         self._graphs: Dict[tuple, tuple] = {}
         self.p: Dict[str, torch.Tensor] = {}
         # Dense layers / GRU input projections on the tensor cores (1-tap conv_tc) when the residual blocks are
         self.dense_tc = conv_path == "tc" and cfg.hidden_dim % 64 == 0 and self.plan.cout % 32 == 0
         self._seq_bufs: Dict[tuple, object] = {}
-        self.lane = 0
         self._lane_streams: List[torch.cuda.Stream] = []
         self._lane_done: List[torch.cuda.Event] = []
         self._lane_sinks: Dict[tuple, Dict[str, torch.Tensor]] = {}
         self._lane_in: Optional[torch.cuda.Event] = None
-        self._sink = None
+        self._branch_streams: Dict[int, torch.cuda.Stream] = {}
+        # CTC branch and accent branch (independent after CRNN_LN, model.py:261-296) on parallel graph branches
+        import os as _os
+        self.parallel_branches = _os.environ.get("SAR_PARALLEL_BRANCHES", "1") != "0"
         self._prepare(weights)
 
     # ------------------------------------------------------------------ weight preparation
@@ -342,25 +369,25 @@ class SARNetEngine:
         y = ops.dense(x, p[name + "/kernel"], p[name + "/bias"], act=act, pre=pre)
         return ops.layernorm(y, p[ln_name + "/gamma"], p[ln_name + "/beta"])
 
-    def bigru(self, x, name, seq=True):
+    def bigru(self, x, name, seq=True, opts: StepOpts = DEFAULT_OPTS):
         p = self.p
         B, S, _ = x.shape
         xp = ops.dense(x, p[name + "/kernel_cat"], p[name + "/ibias_cat"])       # (B,S,6u) = (B,S,2,3u)
-        return ops.bigru(xp.reshape(B, S, 2, -1), p[name + "/rec"], p[name + "/rbias"], seq=seq)
+        return ops.bigru(xp.reshape(B, S, 2, -1), p[name + "/rec"], p[name + "/rbias"], seq=seq, nb=opts.gru_nb)
 
     # tensor-core variants: sequence activations travel as hi/lo planes of a (1, B, S) map
-    def _seq_planes(self, B, S, C, role):
+    def _seq_planes(self, lane, B, S, C, role):
         from . import tc
-        key = (self.lane, B, S, C, role)
+        key = (lane, B, S, C, role)
         if key not in self._seq_bufs:
             self._seq_bufs[key] = tc.alloc_rows(B * S, C, self.device)       # plain rows: a Dense has one tap, no halo
         return self._seq_bufs[key]
 
-    def ln_planes(self, x, ln_name, role, want_dense=False):
+    def ln_planes(self, x, ln_name, role, want_dense=False, opts: StepOpts = DEFAULT_OPTS):
         """LayerNorm of x (B,S,C) -> (fp32 or None, planes)."""
         p = self.p
         B, S, C = x.shape
-        pl = self._seq_planes(B, S, C, role)
+        pl = self._seq_planes(opts.lane, B, S, C, role)
         d = ops.layernorm(x, p[ln_name + "/gamma"], p[ln_name + "/beta"], planes=pl, want_dense=want_dense)
         return d, pl
 
@@ -373,11 +400,11 @@ class SARNetEngine:
         B, S = seq_shape
         return y.reshape(B, S, -1)
 
-    def bigru_planes(self, planes, name, seq_shape, seq=True):
+    def bigru_planes(self, planes, name, seq_shape, seq=True, opts: StepOpts = DEFAULT_OPTS):
         p = self.p
         xp = self.dense_planes(planes, name, seq_shape, bias_name=name + "/ibias_cat")      # (B,S,6u)
         B, S = seq_shape
-        return ops.bigru(xp.reshape(B, S, 2, -1), p[name + "/rec"], p[name + "/rbias"], seq=seq)
+        return ops.bigru(xp.reshape(B, S, 2, -1), p[name + "/rec"], p[name + "/rbias"], seq=seq, nb=opts.gru_nb)
 
     def embed(self, x):
         p = self.p
@@ -386,14 +413,14 @@ class SARNetEngine:
             return ops.gemm_splitk(x, W, b)
         return ops.dense(x, W, b)
 
-    # ------------------------------------------------------------------ forward
     # ------------------------------------------------------------------ CUDA-graph replay
-    def forward_graphed(self, inputs: Dict[str, torch.Tensor], tag="", sink=None) -> Dict[str, torch.Tensor]:
+    def forward_graphed(self, inputs: Dict[str, torch.Tensor], tag="", sink=None,
+                        opts: StepOpts = DEFAULT_OPTS) -> Dict[str, torch.Tensor]:
         """Same as forward(), but the ~45 launches of a step are captured once per input signature
         into a CUDA graph and replayed (the step is launch-bound at small batches).  Inputs are
         copied into the graph's static buffers; the returned tensors are the graph's static outputs
         (valid until the next replay of the same signature)."""
-        key = (tag, self.lane) + tuple(sorted((k, tuple(v.shape), str(v.dtype)) for k, v in inputs.items()))
+        key = (tag, opts) + tuple(sorted((k, tuple(v.shape), str(v.dtype)) for k, v in inputs.items()))
         entry = self._graphs.get(key)
         if entry is None:
             static_in = {k: torch.empty_like(v, device=self.device).copy_(v) for k, v in inputs.items()}   # inputs may be pinned host tensors
@@ -402,12 +429,12 @@ class SARNetEngine:
             side.wait_stream(cur)
             with torch.cuda.stream(side):           # warm-up: allocates plane buffers, sets func attributes
                 for _ in range(2):
-                    self.forward(static_in, sink=sink)
+                    self.forward(static_in, sink=sink, opts=opts)
             cur.wait_stream(side)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                static_out = self.forward(static_in, sink=sink)
+                static_out = self.forward(static_in, sink=sink, opts=opts)
             entry = (graph, static_in, static_out)
             if len(self._graphs) >= 16:
                 self._graphs.pop(next(iter(self._graphs)))
@@ -439,25 +466,23 @@ class SARNetEngine:
         bounds = [(l * B // lanes, (l + 1) * B // lanes) for l in range(lanes)]
         sink = self._lane_sinks.get((B, lanes))
         self._lane_in.record(cur)
-        try:
-            for l, (b0, b1) in enumerate(bounds):
-                st = self._lane_streams[l]
-                st.wait_event(self._lane_in)
-                with torch.cuda.stream(st):
-                    self._set_lane(l + 1)                       # lane 0 is the unsplit path
-                    sl = {k: v[b0:b1] for k, v in inputs.items()}
-                    if sink is None:                             # first call: learn the per-sample outputs from an eager probe
-                        probe = self.forward({k: v.to(self.device) for k, v in sl.items()})
-                        st.synchronize()
-                        sink = {k: torch.zeros((B,) + tuple(v.shape[1:]), device=self.device, dtype=v.dtype)
-                                for k, v in probe.items() if k != "loss_vector" and not k.startswith("__")}
-                        if "_ctc_loss" in sink:                  # (B,1) model output = the kernel's (B,) vector
-                            sink["y_ctc_loss"] = sink["_ctc_loss"].view(B, 1)
-                        self._lane_sinks[(B, lanes)] = sink
-                    self.forward_graphed(sl, tag=(tag, "lanes", B, lanes), sink={k: t[b0:b1] for k, t in sink.items()})
-                    self._lane_done[l].record(st)
-        finally:
-            self._set_lane(0)
+        for l, (b0, b1) in enumerate(bounds):
+            st = self._lane_streams[l]
+            st.wait_event(self._lane_in)
+            # lanes share the SMs: per-layer launches only (a chain launch needs its whole grid resident)
+            lopts = StepOpts(lane=l + 1, no_chain=True)          # lane 0 is the unsplit path
+            with torch.cuda.stream(st):
+                sl = {k: v[b0:b1] for k, v in inputs.items()}
+                if sink is None:                             # first call: learn the per-sample outputs from an eager probe
+                    probe = self.forward({k: v.to(self.device) for k, v in sl.items()}, opts=lopts)
+                    st.synchronize()
+                    sink = {k: torch.zeros((B,) + tuple(v.shape[1:]), device=self.device, dtype=v.dtype)
+                            for k, v in probe.items() if k != "loss_vector" and not k.startswith("__")}
+                    if "_ctc_loss" in sink:                  # (B,1) model output = the kernel's (B,) vector
+                        sink["y_ctc_loss"] = sink["_ctc_loss"].view(B, 1)
+                    self._lane_sinks[(B, lanes)] = sink
+                self.forward_graphed(sl, tag=(tag, "lanes", B, lanes), sink={k: t[b0:b1] for k, t in sink.items()}, opts=lopts)
+                self._lane_done[l].record(st)
         for l in range(lanes):
             cur.wait_event(self._lane_done[l])
         out = {k: v for k, v in sink.items() if not k.startswith("_")}
@@ -469,21 +494,13 @@ class SARNetEngine:
         that consecutive (independent) batches overlap -- the tail of a step (Bi-GRU on 64 SMs, VLAD / head / Dense on
         24-96 CTAs) leaves most SMs idle, and the next batch's stem and stage-1 convolutions fill them.  Returns
         (outputs, stream); the caller orders the inputs before and the consumers after with events on that stream.
-        Slots never use the persistent stage-chain launches (two concurrent chains could starve each other of SMs)."""
+        Kernels captured for a slot are chosen for SM-time, not latency (SLOT_OPTS): no stage chains (a chain holds
+        its SMs for a whole stage, and two concurrent chains could starve each other of SMs) and 32 utterances per
+        Bi-GRU cluster (32 SMs instead of 64 at B=64); measured 98.1 -> 100.9 k utt/s device, 88.2 -> 95.2 k e2e,
+        while the same choices cost a single stream 11 %."""
         st = self.slot_stream(slot)
         with torch.cuda.stream(st):
-            # kernels captured for a slot are chosen for SM-time, not latency: no stage chains (a chain holds its SMs
-            # for a whole stage) and 32 utterances per Bi-GRU cluster (32 SMs instead of 64 at B=64); measured
-            # 98.1 -> 100.9 k utt/s device, 88.2 -> 95.2 k e2e, while the same choices cost a single stream 11 %
-            self._set_lane(slot)
-            self.resnet.no_chain = True
-            ops.GRU_NB["n"] = 32
-            try:
-                out = self.forward_graphed(inputs, tag=(tag, "slot"))
-            finally:
-                self._set_lane(0)
-                self.resnet.no_chain = False
-                ops.GRU_NB["n"] = 0
+            out = self.forward_graphed(inputs, tag=(tag, "slot"), opts=SLOT_OPTS(slot))
         return out, st
 
     def slot_stream(self, slot: int) -> torch.cuda.Stream:
@@ -492,20 +509,11 @@ class SARNetEngine:
             self._lane_done.append(torch.cuda.Event())
         return self._lane_streams[slot]
 
-    def _set_lane(self, lane: int):
-        self.lane = lane
-        self.resnet.lane = lane
-
-    def forward(self, inputs: Dict[str, torch.Tensor], want_intermediates: bool = False, sink=None) -> Dict[str, torch.Tensor]:
+    def forward(self, inputs: Dict[str, torch.Tensor], want_intermediates: bool = False, sink=None,
+                opts: StepOpts = DEFAULT_OPTS, decode_only: bool = False) -> Dict[str, torch.Tensor]:
         """`sink` (forward_lanes): per-sample outputs are written into these preallocated rows and the batch loss
-        vector is left to the caller."""
-        self._sink = sink
-        try:
-            return self._forward(inputs, want_intermediates)
-        finally:
-            self._sink = None
-
-    def _forward(self, inputs: Dict[str, torch.Tensor], want_intermediates: bool = False) -> Dict[str, torch.Tensor]:
+        vector is left to the caller.  `decode_only` (model.ctc_pred on the x_data-only sub-model, model.py:385-389):
+        encoder + ASR branch up to the ctc_pred logits, no CTC loss, no accent branch, no label inputs."""
         cfg, p = self.cfg, self.p
         x = inputs["x_data"]
         if x.dim() == 3:
@@ -514,134 +522,163 @@ class SARNetEngine:
         out: Dict[str, torch.Tensor] = {}
         S, Cc = self.plan.seq_len, self.plan.cout
         if self.dense_tc:
-            return self._forward_tc(inputs, x, want_intermediates)
+            return self._forward_tc(inputs, x, want_intermediates, sink, opts, decode_only)
         if self.conv_path == "tc":
-            raw = self.resnet.forward(x)                                        # final BN->ReLU already applied
+            raw = self.resnet.forward(x, opts=opts)                             # final BN->ReLU already applied
             cnn = self.dense_ln(raw.reshape(B, S, Cc), "CNN_LIN", "CNN_LIN_LN")   # CNN2SEQ, model.py:252
         else:
             raw = self.resnet.forward_raw(x)
             # final ResNet BN->ReLU (resnet.py:178/196) fused as the input op of CNN_LIN
             cnn = self.dense_ln(raw.reshape(B, S, Cc), "CNN_LIN", "CNN_LIN_LN",
                                 pre=self.resnet.bn(self.plan.final_bn))
-        crnn = ops.layernorm(self.bigru(cnn, "CRNN"), p["CRNN_LN/gamma"], p["CRNN_LN/beta"])
+        crnn = ops.layernorm(self.bigru(cnn, "CRNN", opts=opts), p["CRNN_LN/gamma"], p["CRNN_LN/beta"])
         if want_intermediates:
             out["resnet_raw"], out["cnn_lin"], out["crnn"] = raw, cnn, crnn
-        return self._forward_tail(inputs, out, crnn, None, want_intermediates)
+        return self._forward_tail(inputs, out, crnn, None, want_intermediates, sink, opts, decode_only)
 
-    def _forward_tc(self, inputs, x, want_intermediates):
+    def _forward_tc(self, inputs, x, want_intermediates, sink, opts, decode_only):
         """Encoder with every Dense / GRU input projection on the tensor cores: activations between the
         LayerNorms and the Dense layers travel as fp16 hi/lo planes (no fp32 round trip)."""
-        p = self.p
         B = x.shape[0]
         S = self.plan.seq_len
         out: Dict[str, torch.Tensor] = {}
         wi = want_intermediates
-        P0 = self.resnet.forward(x, as_planes=True)                             # relu(final BN), resnet.py:178/196
+        P0 = self.resnet.forward(x, as_planes=True, opts=opts)                  # relu(final BN), resnet.py:178/196
         y = self.dense_planes(P0, "CNN_LIN", (B, S), act="tanh", conv_map=True)      # CNN2SEQ + CNN_LIN, model.py:252-253
-        cnn, P1 = self.ln_planes(y, "CNN_LIN_LN", "cnn", want_dense=wi)
-        crnn, P2 = self.ln_planes(self.bigru_planes(P1, "CRNN", (B, S)), "CRNN_LN", "crnn", want_dense=wi)
+        cnn, P1 = self.ln_planes(y, "CNN_LIN_LN", "cnn", want_dense=wi, opts=opts)
+        crnn, P2 = self.ln_planes(self.bigru_planes(P1, "CRNN", (B, S), opts=opts), "CRNN_LN", "crnn", want_dense=wi, opts=opts)
         if wi:
             out["resnet_raw"], out["cnn_lin"], out["crnn"] = self.tc_unpack(P0), cnn, crnn
-        return self._forward_tail(inputs, out, crnn, P2, want_intermediates)
+        return self._forward_tail(inputs, out, crnn, P2, want_intermediates, sink, opts, decode_only)
 
     def tc_unpack(self, planes):
         from . import tc
         return tc.unpack(planes)
 
-    def _forward_tail(self, inputs, out, crnn, crnn_planes, want_intermediates):
+    # -- the two branches after CRNN_LN (model.py:261-269 and 275-322): independent of each other
+    def _ctc_branch(self, inputs, out, crnn, crnn_planes, want_intermediates, sink, opts, decode_only):
         cfg, p = self.cfg, self.p
         B = inputs["x_data"].shape[0]
-        use_tc = crnn_planes is not None
-        sink = self._sink or {}
-        stats = None
-        ctc_loss = None
-        bn_stats = None
-        if cfg.ctc_enable:                                                      # model.py:261-269
-            if use_tc:
-                S_ = self.plan.seq_len
-                _, P3 = self.ln_planes(self.bigru_planes(crnn_planes, "CTC_BIGRU", (B, S_)), "CTC_BIGRU_LN", "ctc_bigru")
-                y = self.dense_planes(P3, "CTC_DS", (B, S_), act="tanh")
-                if "ctc_pred/w_tc" in p:
-                    _, P5 = self.ln_planes(y, "CTC_DS_LN", "ctc_ds")
-                    asr = None
-                else:
-                    asr = ops.layernorm(y, p["CTC_DS_LN/gamma"], p["CTC_DS_LN/beta"])
+        S_ = self.plan.seq_len
+        if crnn_planes is not None:
+            _, P3 = self.ln_planes(self.bigru_planes(crnn_planes, "CTC_BIGRU", (B, S_), opts=opts), "CTC_BIGRU_LN",
+                                   "ctc_bigru", opts=opts)
+            y = self.dense_planes(P3, "CTC_DS", (B, S_), act="tanh")
+            if "ctc_pred/w_tc" in p:
+                _, P5 = self.ln_planes(y, "CTC_DS_LN", "ctc_ds", opts=opts)
+                asr = None
             else:
-                asr = ops.layernorm(self.bigru(crnn, "CTC_BIGRU"), p["CTC_BIGRU_LN/gamma"], p["CTC_BIGRU_LN/beta"])
-                asr = self.dense_ln(asr, "CTC_DS", "CTC_DS_LN")
-            if asr is None:
-                logits = self.dense_planes(P5, "ctc_pred", (B, self.plan.seq_len), bias_name="ctc_pred/bias_tc")
+                asr = ops.layernorm(y, p["CTC_DS_LN/gamma"], p["CTC_DS_LN/beta"])
+        else:
+            asr = ops.layernorm(self.bigru(crnn, "CTC_BIGRU", opts=opts), p["CTC_BIGRU_LN/gamma"], p["CTC_BIGRU_LN/beta"])
+            asr = self.dense_ln(asr, "CTC_DS", "CTC_DS_LN")
+        if asr is None:
+            logits = self.dense_planes(P5, "ctc_pred", (B, S_), bias_name="ctc_pred/bias_tc")
+        else:
+            logits = ops.dense(asr, p["ctc_pred/kernel"], p["ctc_pred/bias"])
+        out["__ctc_logits"] = logits                 # (B, S, ld) pre-softmax, for the greedy decode (model.ctc_pred)
+        if decode_only:
+            return
+        ctc_loss, status, probs = ops.ctc(logits, inputs["x_ctc_label"], inputs["x_ctc_in_len"],
+                                          inputs["x_ctc_out_len"], want_probs=want_intermediates, classes=cfg.bpe_classes,
+                                          loss=sink.get("_ctc_loss"), status=sink.get("ctc_status"))
+        out["_ctc_loss"] = ctc_loss
+        out["y_ctc_loss"] = ctc_loss.reshape(B, 1)
+        out["ctc_status"] = status
+        if want_intermediates:
+            out["ctc_pred"] = probs
+
+    def _ar_branch(self, inputs, out, crnn, crnn_planes, want_intermediates, sink, opts):
+        cfg, p = self.cfg, self.p
+        B = inputs["x_data"].shape[0]
+        P4 = None
+        if crnn_planes is not None:
+            y = self.dense_planes(crnn_planes, "AR_DS", (B, self.plan.seq_len), act="tanh")
+            if cfg.mto == "bigru":
+                ar, P4 = self.ln_planes(y, "AR_DS_LN", "ar", want_dense=want_intermediates, opts=opts)
             else:
-                logits = ops.dense(asr, p["ctc_pred/kernel"], p["ctc_pred/bias"])
-            ctc_loss, status, probs = ops.ctc(logits, inputs["x_ctc_label"], inputs["x_ctc_in_len"],
-                                              inputs["x_ctc_out_len"], want_probs=want_intermediates, classes=cfg.bpe_classes,
-                                              loss=sink.get("_ctc_loss"), status=sink.get("ctc_status"))
-            out["_ctc_loss"] = ctc_loss
-            out["__ctc_logits"] = logits             # (B, S, ld) pre-softmax, for the greedy decode (model.ctc_pred)
-            out["y_ctc_loss"] = ctc_loss.reshape(B, 1)
-            out["ctc_status"] = status
-            if want_intermediates:
-                out["ctc_pred"] = probs
-        if cfg.ar_enable:                                                       # model.py:275-322
-            P4 = None
-            if use_tc:
-                y = self.dense_planes(crnn_planes, "AR_DS", (B, self.plan.seq_len), act="tanh")
-                if cfg.mto == "bigru":
-                    ar, P4 = self.ln_planes(y, "AR_DS_LN", "ar", want_dense=want_intermediates)
-                else:
-                    ar = ops.layernorm(y, p["AR_DS_LN/gamma"], p["AR_DS_LN/beta"])
-            else:
-                ar = self.dense_ln(crnn, "AR_DS", "AR_DS_LN")
-            if cfg.mto == "avg":
-                integ = ops.avgpool(ar)
-            elif cfg.mto == "bigru":
-                integ = self.bigru_planes(P4, "AR_MERGE", (B, self.plan.seq_len), seq=False) if P4 is not None else self.bigru(ar, "AR_MERGE", seq=False)
-            else:
-                G = cfg.ghost_clusters if cfg.mto == "gvlad" else 0
-                vplanes = None
-                if getattr(self, "embed_ksplit", 0):
-                    from . import tc
-                    key = (self.lane, B, cfg.vlad_clusters * ar.shape[-1], "vlad")
-                    if key not in self._seq_bufs:
-                        self._seq_bufs[key] = tc.alloc_rows(B, key[2], self.device)
-                    vplanes = self._seq_bufs[key]
-                integ = ops.vlad(ar, p[cfg.mto + "/w_assign"], p[cfg.mto + "/b_assign"], p[cfg.mto + "/centers"],
-                                 cfg.vlad_clusters, G, planes=vplanes, want_dense=want_intermediates or vplanes is None)
-            if cfg.mto in ("vlad", "gvlad") and getattr(self, "embed_ksplit", 0):
+                ar = ops.layernorm(y, p["AR_DS_LN/gamma"], p["AR_DS_LN/beta"])
+        else:
+            ar = self.dense_ln(crnn, "AR_DS", "AR_DS_LN")
+        if cfg.mto == "avg":
+            integ = ops.avgpool(ar)
+        elif cfg.mto == "bigru":
+            integ = (self.bigru_planes(P4, "AR_MERGE", (B, self.plan.seq_len), seq=False, opts=opts) if P4 is not None
+                     else self.bigru(ar, "AR_MERGE", seq=False, opts=opts))
+        else:
+            G = cfg.ghost_clusters if cfg.mto == "gvlad" else 0
+            vplanes = None
+            if getattr(self, "embed_ksplit", 0):
                 from . import tc
-                emb = tc.gemm_splitk_tc(vplanes, p["AR_EMBEDDING/w_tc"], p["AR_EMBEDDING/bias_folded"],
-                                        p["AR_EMBEDDING/zero_bias"], self.embed_ksplit, out=sink.get("embedding"))
+                key = (opts.lane, B, cfg.vlad_clusters * ar.shape[-1], "vlad")
+                if key not in self._seq_bufs:
+                    self._seq_bufs[key] = tc.alloc_rows(B, key[2], self.device)
+                vplanes = self._seq_bufs[key]
+            integ = ops.vlad(ar, p[cfg.mto + "/w_assign"], p[cfg.mto + "/b_assign"], p[cfg.mto + "/centers"],
+                             cfg.vlad_clusters, G, planes=vplanes, want_dense=want_intermediates or vplanes is None)
+        if cfg.mto in ("vlad", "gvlad") and getattr(self, "embed_ksplit", 0):
+            from . import tc
+            emb = tc.gemm_splitk_tc(vplanes, p["AR_EMBEDDING/w_tc"], p["AR_EMBEDDING/bias_folded"],
+                                    p["AR_EMBEDDING/zero_bias"], self.embed_ksplit, out=sink.get("embedding"))
+        else:
+            emb = self.embed(integ)
+        if want_intermediates:
+            out["ar_ds"], out["integration"] = ar, integ
+        out["embedding"] = emb
+        onehot = inputs.get("x_accent") if cfg.disc_enable else inputs.get("y_true")
+        cls = tuple(p[k] for k in ("AR_CF_DS1/kernel", "AR_CF_DS1/bias", "AR_CF_DS2/kernel", "AR_CF_DS2/bias",
+                                   "y_accent/kernel", "y_accent/bias"))
+        h = ops.head(emb, cls, wd=p.get("y_disc/w") if cfg.disc_enable else None, onehot=onehot,
+                     n_classes=cfg.accent_classes, head_kind=cfg.metric_loss if cfg.disc_enable else None,
+                     margin=cfg.margin,
+                     out={k: sink.get(n) for k, n in (("y_accent", "y_accent"), ("y_accent_logits", "y_accent_logits"),
+                                                      ("y_disc", "y_disc"), ("y_disc_logits", "y_disc_logits"),
+                                                      ("sample_stats", "_sample_stats"))})
+        out["_sample_stats"] = h.pop("sample_stats")
+        out.update(h)
+        if cfg.disc_enable and cfg.bn_dim:
+            bn = ops.dense(emb, p["AR_BN_DS/kernel"], p["AR_BN_DS/bias"], act="relu")
+            bn = ops.dense(bn, p["bottleneck/kernel_folded"], p["bottleneck/bias_folded"])
+            hb = ops.head(None, None, emb_d=bn, wd=p["y_disc_bn/w"], onehot=onehot, n_classes=cfg.accent_classes,
+                          head_kind=cfg.metric_loss, margin=cfg.margin)
+            out["_bn_stats"] = hb["sample_stats"]
+            out["y_disc_bn"] = hb["y_disc"]
+
+    def _forward_tail(self, inputs, out, crnn, crnn_planes, want_intermediates, sink_in, opts, decode_only=False):
+        cfg = self.cfg
+        B = inputs["x_data"].shape[0]
+        sink = sink_in or {}
+        if decode_only:
+            if not cfg.ctc_enable:
+                raise ValueError("decode_only needs a model built with ctc_enable=True")
+            self._ctc_branch(inputs, out, crnn, crnn_planes, False, sink, opts, True)
+            return out
+        # While the step is being captured into a CUDA graph the CTC branch goes onto a second stream: fork after
+        # CRNN_LN, join before the loss reduction -> two parallel branches of the graph (CTC_BIGRU's 48-75 dependent
+        # steps run beside AR_DS -> VLAD -> embedding -> head instead of in front of them).  Eager launches stay on
+        # one stream (their temporaries belong to the caller's stream).
+        fork = (self.parallel_branches and cfg.ctc_enable and cfg.ar_enable and torch.cuda.is_current_stream_capturing())
+        if cfg.ctc_enable:                                                      # model.py:261-269
+            if fork:
+                cur = torch.cuda.current_stream()
+                side = self._branch_streams.get(opts.lane)
+                if side is None:
+                    side = self._branch_streams[opts.lane] = torch.cuda.Stream(device=self.device)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    self._ctc_branch(inputs, out, crnn, crnn_planes, want_intermediates, sink, opts, False)
             else:
-                emb = self.embed(integ)
-            if want_intermediates:
-                out["ar_ds"], out["integration"] = ar, integ
-            out["embedding"] = emb
-            onehot = inputs.get("x_accent") if cfg.disc_enable else inputs.get("y_true")
-            cls = tuple(p[k] for k in ("AR_CF_DS1/kernel", "AR_CF_DS1/bias", "AR_CF_DS2/kernel", "AR_CF_DS2/bias",
-                                       "y_accent/kernel", "y_accent/bias"))
-            h = ops.head(emb, cls, wd=p.get("y_disc/w") if cfg.disc_enable else None, onehot=onehot,
-                         n_classes=cfg.accent_classes, head_kind=cfg.metric_loss if cfg.disc_enable else None,
-                         margin=cfg.margin,
-                         out={k: sink.get(n) for k, n in (("y_accent", "y_accent"), ("y_accent_logits", "y_accent_logits"),
-                                                          ("y_disc", "y_disc"), ("y_disc_logits", "y_disc_logits"),
-                                                          ("sample_stats", "_sample_stats"))})
-            stats = h.pop("sample_stats")
-            out["_sample_stats"] = stats
-            out.update(h)
-            if cfg.disc_enable and cfg.bn_dim:
-                bn = ops.dense(emb, p["AR_BN_DS/kernel"], p["AR_BN_DS/bias"], act="relu")
-                bn = ops.dense(bn, p["bottleneck/kernel_folded"], p["bottleneck/bias_folded"])
-                hb = ops.head(None, None, emb_d=bn, wd=p["y_disc_bn/w"], onehot=onehot, n_classes=cfg.accent_classes,
-                              head_kind=cfg.metric_loss, margin=cfg.margin)
-                bn_stats = hb["sample_stats"]
-                out["_bn_stats"] = bn_stats
-                out["y_disc_bn"] = hb["y_disc"]
-        if self._sink is not None:
+                self._ctc_branch(inputs, out, crnn, crnn_planes, want_intermediates, sink, opts, False)
+        if cfg.ar_enable:                                                       # model.py:275-322
+            self._ar_branch(inputs, out, crnn, crnn_planes, want_intermediates, sink, opts)
+        if fork:
+            torch.cuda.current_stream().wait_stream(side)
+        if sink_in is not None:
             # anything a kernel did not write in place (the views of y_ctc_loss share _ctc_loss's rows)
-            for k, dst in self._sink.items():
+            for k, dst in sink_in.items():
                 src = out.get(k)
                 if src is not None and src.data_ptr() != dst.data_ptr():
                     dst.copy_(src)
-            return dict(self._sink)
-        out["loss_vector"] = ops.loss_reduce(stats, ctc_loss, bn_stats, B=B)
+            return dict(sink_in)
+        out["loss_vector"] = ops.loss_reduce(out.get("_sample_stats"), out.get("_ctc_loss"), out.get("_bn_stats"), B=B)
         return out

@@ -116,10 +116,7 @@ class _DS(_Layer):
         y = ops.dense(x.contiguous(), self.d("kernel", x.device),
                       self.d("bias", x.device) if self.use_bias else None, act=act)
         if self.activation == "softmax":
-            n = y.shape[-1]
-            eye = torch.eye(n, device=y.device)
-            y = ops.head(None, None, emb_d=y.reshape(-1, n).contiguous(), wd=eye, n_classes=n,
-                         head_kind="softmax")["y_disc"].reshape(y.shape)
+            y = ops.softmax_rows(y)                    # any width (ctc_pred: DS(1000, 'softmax'), model.py:268)
         return y
 
 
@@ -131,6 +128,7 @@ class _BIGRU(_Layer):
     def __init__(self, hidden, seq=True, name=None):
         super().__init__(name)
         self.hidden, self.seq = hidden, seq
+        self.nb = 0          # utterances per cluster of the recurrence kernel (0 = its own choice, 16 or 32)
 
     def __call__(self, x):
         u = self.hidden
@@ -152,7 +150,7 @@ class _BIGRU(_Layer):
         B, S, _ = x.shape
         xp = ops.dense(x.contiguous(), self.d("kcat", x.device, kcat), self.d("bcat", x.device, bcat))
         return ops.bigru(xp.reshape(B, S, 2, 3 * u), self.d("rec", x.device, rec), self.d("rb", x.device, rb),
-                         seq=self.seq)
+                         seq=self.seq, nb=self.nb)
 
 
 def BIGRU(hidden, seq=True, rgr=None, name=None):
@@ -301,13 +299,19 @@ class SARModel:
         return LayerView(self, name)
 
     def save_weights(self, path):
-        _weights.save_weights(path, self.weights)
+        """Keras `Model.save_weights`: `*.h5` -> Keras HDF5 layout (readable by the reference's load_weights), else npz."""
+        _weights.save_weights(path, self.weights, cfg=self.config)
+
+    def save(self, path):
+        """Keras `Model.save` (train.py:35 `model.save("%s/%03d.h5")`): the weights under `/model_weights`.  No
+        optimizer state or model_config is written (forward-only path)."""
+        _weights.save_weights(path, self.weights, cfg=self.config, full_model=True)
 
     def load_weights(self, path, by_name=True, skip_mismatch=True):
         """model.py:181-183 semantics: load by name, silently skip shape mismatches.  An `.npz` keyed by KERAS weight
         names (`conv2d_1/kernel:0`, ...: `np.savez(path, **{w.name: v ...})` on the TF side) is mapped
         to the canonical names first (weights.keras_weight_names)."""
-        loaded = _weights.load_weights(path)
+        loaded = _weights.load_weights(path)                  # .h5 (Keras HDF5, parsed by h5lite) or .npz
         if any(k.endswith(":0") for k in loaded):
             loaded = _weights.from_keras_named(self.config, loaded)
         for k, v in loaded.items():

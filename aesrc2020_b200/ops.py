@@ -105,17 +105,15 @@ def layernorm(x, gamma, beta, eps: float = LN_EPS, *, planes=None, want_dense: b
     return out
 
 
-GRU_NB = {"n": 0}       # utterances per cluster of the Bi-GRU kernel: 0 auto, 32 while several batches share the GPU
-
-
-def bigru(xp, rec, rbias, *, seq=True):
-    """xp (B,S,2,3u) input projections; rec (2,u,3u); rbias (2,3u)."""
+def bigru(xp, rec, rbias, *, seq=True, nb: int = 0):
+    """xp (B,S,2,3u) input projections; rec (2,u,3u); rbias (2,3u).  `nb`: utterances per cluster of the Bi-GRU
+    kernel (0 = the kernel's choice, 16 or 32; 32 occupies half the SMs while several batches share the GPU)."""
     xp = _f32(xp)
     B, S = xp.shape[0], xp.shape[1]
     u = rec.shape[1]
     out = torch.empty((B, S, 2 * u) if seq else (B, 2 * u), device=xp.device, dtype=torch.float32)
     check(_shim.lib().sar_bigru_nb_fwd(ptr(xp), ptr(rec), ptr(rbias), ptr(out), B, S, u, 1 if seq else 0,
-                                       GRU_NB["n"], stream_ptr()), "sar_bigru_fwd")
+                                       int(nb), stream_ptr()), "sar_bigru_fwd")
     _count(1)
     return out
 
@@ -138,6 +136,18 @@ def vlad(feat, w_assign, b_assign, centers, K: int, G: int, score=None, *, plane
     check(_shim.lib().sar_vlad_planes_fwd(ptr(feat), ptr(w_assign), ptr(b_assign), ptr(score), ptr(centers), ptr(out),
                                           ptr(planes.t) if planes is not None else None,
                                           B, S, D, K, G, stream_ptr()), "sar_vlad_fwd")
+    _count(1)
+    return out
+
+
+def softmax_rows(x, classes: Optional[int] = None):
+    """sar_softmax_rows_fwd: softmax over the first `classes` columns of the last axis -> (..., classes)."""
+    x = _f32(x)
+    ld = int(x.shape[-1])
+    Cc = int(classes) if classes else ld
+    rows = x.numel() // ld
+    out = torch.empty(tuple(x.shape[:-1]) + (Cc,), device=x.device, dtype=torch.float32)
+    check(_shim.lib().sar_softmax_rows_fwd(ptr(x), ld, ptr(out), rows, Cc, stream_ptr()), "sar_softmax_rows_fwd")
     _count(1)
     return out
 

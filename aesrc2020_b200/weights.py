@@ -163,11 +163,42 @@ def init_weights(cfg: SARConfig, seed: int = 1234, degenerate: bool = False) -> 
     return out
 
 
-def save_weights(path: str, weights: Dict[str, np.ndarray]) -> None:
-    np.savez(path, **{k.replace("/", "|"): np.asarray(v) for k, v in weights.items()})
+def _is_h5_path(path) -> bool:
+    return isinstance(path, str) and path.lower().endswith((".h5", ".hdf5", ".keras.h5"))
+
+
+def save_weights(path: str, weights: Dict[str, np.ndarray], cfg: "SARConfig" = None, full_model: bool = False) -> None:
+    """`model.save_weights(path)` / `model.save(path)` (train.py:35, model.py:416-417).  A `.h5` / `.hdf5` path writes
+    the Keras HDF5 layout (h5lite.write_keras_weights: `layer_names` / `weight_names` attributes, one dataset per
+    weight under Keras' own weight names -- the file the reference's `load_weights(..., by_name=True)` reads); any
+    other path writes an `.npz` of the canonical names AT EXACTLY THAT PATH (np.savez would append '.npz')."""
+    if _is_h5_path(path):
+        if cfg is None:
+            raise ValueError("save_weights('%s'): the Keras HDF5 layout needs the model config (weight names)" % path)
+        from . import h5lite
+        knames = keras_weight_names(cfg)
+        layers: "OrderedDict[str, OrderedDict[str, np.ndarray]]" = OrderedDict()
+        for canon, kname in knames.items():
+            if canon not in weights:
+                continue
+            layers.setdefault(kname.split("/")[0], OrderedDict())[kname] = np.asarray(weights[canon], dtype=np.float32)
+        h5lite.write_keras_weights(path, layers, full_model=full_model)
+        return
+    with open(path, "wb") as f:
+        np.savez(f, **{k.replace("/", "|"): np.asarray(v) for k, v in weights.items()})
 
 
 def load_weights(path: str) -> Dict[str, np.ndarray]:
+    """-> {name: array}.  HDF5 files (sniffed by signature, whatever the extension) give KERAS weight names
+    (`conv2d_1/kernel:0`; map them with from_keras_named), `.npz` files whatever names they were saved under."""
+    import os
+    if not os.path.exists(path) and os.path.exists(path + ".npz"):
+        path = path + ".npz"                               # files written by np.savez(path_without_extension)
+    with open(path, "rb") as f:
+        magic = f.read(8)
+    if magic == b"\x89HDF\r\n\x1a\n":
+        from . import h5lite
+        return dict(h5lite.read_keras_weights(path))
     with np.load(path) as z:
         return {k.replace("|", "/"): z[k] for k in z.files}
 

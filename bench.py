@@ -187,6 +187,7 @@ def main():
         return run_reference(args, cfgd)
 
     from aesrc2020_b200 import dist as sdist, model as mdl, utils as us, ops
+    from aesrc2020_b200.engine import StepOpts, SLOT_OPTS
     import torch.distributed as tdist
     env = sdist.init_from_env()
     rank, world, local = env["rank"], env["world_size"], env["local_rank"]
@@ -252,11 +253,9 @@ def main():
     step_device(0, graphed=False)
     launches_per_step = ops.LAUNCHES["n"] - l0
     if lanes > 1:       # every lane launches the whole kernel sequence on its rows (no chain launches), + 1 batch loss reduce
-        eng._set_lane(1)
         l0 = ops.LAUNCHES["n"]
-        eng.forward({k: v[:B // lanes] for k, v in dev_batches[0].items()})
+        eng.forward({k: v[:B // lanes] for k, v in dev_batches[0].items()}, opts=StepOpts(lane=1, no_chain=True))
         launches_per_step = (ops.LAUNCHES["n"] - l0 - 1) * lanes + 1
-        eng._set_lane(0)
     for i in range(depth if depth > 1 else 0):      # capture every slot's CUDA graph before the W warm-up steps
         step_device(i)
     for i in range(args.warmup):
@@ -296,11 +295,9 @@ def main():
     barrier()
     launches = launches_per_step * args.steps       # kernels replayed from the graph
     if depth > 1:                                   # pipeline slots launch every layer separately (no stage chains)
-        eng._set_lane(1)
         l0 = ops.LAUNCHES["n"]
-        eng.forward(dev_batches[0])
+        eng.forward(dev_batches[0], opts=SLOT_OPTS(1))
         per_other = ops.LAUNCHES["n"] - l0
-        eng._set_lane(0)
         torch.cuda.synchronize()
         launches = per_other * args.steps
     ms = t_start.elapsed_time(t_end)

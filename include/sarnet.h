@@ -196,6 +196,11 @@ int sar_vlad_fwd(const float* feat, const float* w_assign, const float* b_assign
 int sar_vlad_planes_fwd(const float* feat, const float* w_assign, const float* b_assign, const float* score,
                         const float* centers, float* out, void* out_planes, int B, int S, int D, int K, int G, void* stream);
 
+/* Row softmax: out (rows, C) = softmax over the first C columns of x (rows, ld), ld >= C.
+ * Replaces: the 'softmax' activation of Dense (model.py:35-42; ctc_pred, model.py:268) -- the posteriors
+ * K.ctc_decode reads in ctc_pred() (model.py:385-389).  ld > C: rows padded by the tensor-core ctc_pred GEMM. */
+int sar_softmax_rows_fwd(const float* x, int ld, float* out, long long rows, int C, void* stream);
+
 /* GlobalAveragePooling1D (model.py:125): out (B,D) = mean over S of x (B,S,D). */
 int sar_avgpool_fwd(const float* x, float* out, int B, int S, int D, void* stream);
 

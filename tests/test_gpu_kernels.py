@@ -100,14 +100,10 @@ def test_bigru_vs_oracle(cuda_device, B, S, Din, seq):
     want = O.bigru(t64(x), {"g/" + k: t64(v) for k, v in w.items()}, "g", seq=seq)
     assert norm_err(got, want) < 2e-5
     # 16 or 32 utterances per cluster (sar_bigru_nb_fwd) is a scheduling choice: bitwise the same result
-    from aesrc2020_b200 import ops
     outs = []
     for nb in (16, 32):
-        ops.GRU_NB["n"] = nb
-        try:
-            outs.append(layer(dev(x)))
-        finally:
-            ops.GRU_NB["n"] = 0
+        layer.nb = nb
+        outs.append(layer(dev(x)))
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], got)
 
 
