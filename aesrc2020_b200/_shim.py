@@ -46,6 +46,8 @@ SIGNATURES = {
     "sar_bigru_nb_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, C.c_void_p]),
     "sar_vlad_fwd": (c_int, [c_fp] * 6 + [c_int] * 5 + [C.c_void_p]),
     "sar_vlad_planes_fwd": (c_int, [c_fp] * 7 + [c_int] * 5 + [C.c_void_p]),
+    "sar_vlad_tc_supported": (c_int, [c_int] * 5),
+    "sar_vlad_tc_fwd": (c_int, [c_fp, c_ll, c_fp, c_fp, c_fp, c_fp, c_fp] + [c_int] * 5 + [C.c_void_p]),
     "sar_splitk_reduce_fwd": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_int, C.c_void_p]),
     "sar_softmax_rows_fwd": (c_int, [c_fp, c_int, c_fp, c_ll, c_int, C.c_void_p]),
     "sar_avgpool_fwd": (c_int, [c_fp, c_fp, c_int, c_int, c_int, C.c_void_p]),

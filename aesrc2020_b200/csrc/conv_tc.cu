@@ -1031,7 +1031,11 @@ static EncodeTiledFn get_encode() {
 }
 
 // planes tensor [planes][rows][ch] fp16, box = (kc, box_rows, 1)
+int tc_make_map(CUtensorMap* map, const void* base, long long rows, int ch, int planes, int kc, int box_rows);
 static int make_map(CUtensorMap* map, const void* base, long long rows, int ch, int planes, int kc, int box_rows) {
+  return tc_make_map(map, base, rows, ch, planes, kc, box_rows);
+}
+int tc_make_map(CUtensorMap* map, const void* base, long long rows, int ch, int planes, int kc, int box_rows) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return SAR_ERR_UNSUPPORTED; }
   cuuint64_t dims[3] = {(cuuint64_t)ch, (cuuint64_t)rows, (cuuint64_t)planes};

@@ -332,6 +332,9 @@ class SARNetEngine:
                 self._put(pre + "/w_assign", k.reshape(k.shape[2], k.shape[3]))
                 self._put(pre + "/b_assign", w[pre + "_center_assignment/bias"])
                 self._put(pre + "/centers", w[pre + "_pool/centers"])
+                if self.dense_tc:
+                    from . import tc
+                    self.p[pre + "/w_assign_tc"] = torch.from_numpy(tc.pack_vlad_assign(k.reshape(k.shape[2], k.shape[3]))).to(self.device)
             # AR_BN1 -> AR_EMBEDDING -> AR_BN2 folded into one affine map (float64 on the host)
             s1, t1 = fold_bn(w, "AR_BN1")
             s2, t2 = fold_bn(w, "AR_BN2")
@@ -415,12 +418,12 @@ class SARNetEngine:
 
     # ------------------------------------------------------------------ CUDA-graph replay
     def forward_graphed(self, inputs: Dict[str, torch.Tensor], tag="", sink=None,
-                        opts: StepOpts = DEFAULT_OPTS) -> Dict[str, torch.Tensor]:
+                        opts: StepOpts = DEFAULT_OPTS, decode_only: bool = False) -> Dict[str, torch.Tensor]:
         """Same as forward(), but the ~45 launches of a step are captured once per input signature
         into a CUDA graph and replayed (the step is launch-bound at small batches).  Inputs are
         copied into the graph's static buffers; the returned tensors are the graph's static outputs
         (valid until the next replay of the same signature)."""
-        key = (tag, opts) + tuple(sorted((k, tuple(v.shape), str(v.dtype)) for k, v in inputs.items()))
+        key = (tag, opts, decode_only) + tuple(sorted((k, tuple(v.shape), str(v.dtype)) for k, v in inputs.items()))
         entry = self._graphs.get(key)
         if entry is None:
             static_in = {k: torch.empty_like(v, device=self.device).copy_(v) for k, v in inputs.items()}   # inputs may be pinned host tensors
@@ -429,12 +432,12 @@ class SARNetEngine:
             side.wait_stream(cur)
             with torch.cuda.stream(side):           # warm-up: allocates plane buffers, sets func attributes
                 for _ in range(2):
-                    self.forward(static_in, sink=sink, opts=opts)
+                    self.forward(static_in, sink=sink, opts=opts, decode_only=decode_only)
             cur.wait_stream(side)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                static_out = self.forward(static_in, sink=sink, opts=opts)
+                static_out = self.forward(static_in, sink=sink, opts=opts, decode_only=decode_only)
             entry = (graph, static_in, static_out)
             if len(self._graphs) >= 16:
                 self._graphs.pop(next(iter(self._graphs)))
@@ -592,9 +595,15 @@ class SARNetEngine:
         cfg, p = self.cfg, self.p
         B = inputs["x_data"].shape[0]
         P4 = None
+        S_ = self.plan.seq_len
+        G = cfg.ghost_clusters if cfg.mto == "gvlad" else 0
+        vlad_on_tc = False
         if crnn_planes is not None:
-            y = self.dense_planes(crnn_planes, "AR_DS", (B, self.plan.seq_len), act="tanh")
-            if cfg.mto == "bigru":
+            y = self.dense_planes(crnn_planes, "AR_DS", (B, S_), act="tanh")
+            if cfg.mto in ("vlad", "gvlad") and (cfg.mto + "/w_assign_tc") in p:
+                from . import tc
+                vlad_on_tc = tc.vlad_tc_supported(B, S_, y.shape[-1], cfg.vlad_clusters, G)
+            if cfg.mto == "bigru" or vlad_on_tc:
                 ar, P4 = self.ln_planes(y, "AR_DS_LN", "ar", want_dense=want_intermediates, opts=opts)
             else:
                 ar = ops.layernorm(y, p["AR_DS_LN/gamma"], p["AR_DS_LN/beta"])
@@ -603,19 +612,23 @@ class SARNetEngine:
         if cfg.mto == "avg":
             integ = ops.avgpool(ar)
         elif cfg.mto == "bigru":
-            integ = (self.bigru_planes(P4, "AR_MERGE", (B, self.plan.seq_len), seq=False, opts=opts) if P4 is not None
+            integ = (self.bigru_planes(P4, "AR_MERGE", (B, S_), seq=False, opts=opts) if P4 is not None
                      else self.bigru(ar, "AR_MERGE", seq=False, opts=opts))
         else:
-            G = cfg.ghost_clusters if cfg.mto == "gvlad" else 0
             vplanes = None
             if getattr(self, "embed_ksplit", 0):
                 from . import tc
-                key = (opts.lane, B, cfg.vlad_clusters * ar.shape[-1], "vlad")
+                key = (opts.lane, B, cfg.vlad_clusters * cfg.hidden_dim, "vlad")
                 if key not in self._seq_bufs:
                     self._seq_bufs[key] = tc.alloc_rows(B, key[2], self.device)
                 vplanes = self._seq_bufs[key]
-            integ = ops.vlad(ar, p[cfg.mto + "/w_assign"], p[cfg.mto + "/b_assign"], p[cfg.mto + "/centers"],
-                             cfg.vlad_clusters, G, planes=vplanes, want_dense=want_intermediates or vplanes is None)
+            if vlad_on_tc:                       # both contractions on the tensor cores (csrc/vlad_tc.cu)
+                integ = tc.vlad_tc(P4, p[cfg.mto + "/w_assign_tc"], p[cfg.mto + "/b_assign"], p[cfg.mto + "/centers"],
+                                   B, S_, cfg.vlad_clusters, G, planes=vplanes,
+                                   want_dense=want_intermediates or vplanes is None)
+            else:                                # shapes outside the tensor-core kernel's tiles: CUDA-core kernel (vlad.cu)
+                integ = ops.vlad(ar, p[cfg.mto + "/w_assign"], p[cfg.mto + "/b_assign"], p[cfg.mto + "/centers"],
+                                 cfg.vlad_clusters, G, planes=vplanes, want_dense=want_intermediates or vplanes is None)
         if cfg.mto in ("vlad", "gvlad") and getattr(self, "embed_ksplit", 0):
             from . import tc
             emb = tc.gemm_splitk_tc(vplanes, p["AR_EMBEDDING/w_tc"], p["AR_EMBEDDING/bias_folded"],

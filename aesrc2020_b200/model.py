@@ -368,6 +368,15 @@ class SARModel:
             return dict(zip(self.config.input_names(), x))
         return {"x_data": x}
 
+    @property
+    def decode_only(self) -> bool:
+        """A sub-model whose only output is `ctc_pred` (sub_model(model, 'x_data', 'ctc_pred'), model.py:380-383):
+        encoder + ASR branch, x_data is its only input."""
+        return list(self._outputs) == ["ctc_pred"]
+
+    def required_inputs(self) -> List[str]:
+        return ["x_data"] if self.decode_only else self.config.input_names()
+
     def _lanes_for(self, B: int) -> int:
         """Micro-batch lanes of a graphed step: batches too small to fill the GPU with one kernel at a time are
         split so that independent kernels of the lanes overlap (measured: profiles/r1_lanes.md)."""
@@ -379,10 +388,20 @@ class SARModel:
         """One forward on the device.  `graph` (default: self.use_graph) replays a captured CUDA graph
         of the step; the returned tensors are then the graph's static outputs."""
         xd = self._as_dict(x)
-        missing = [k for k in self.config.input_names() if k not in xd]
+        missing = [k for k in self.required_inputs() if k not in xd]
         if missing:
             raise ValueError("missing model inputs: %s" % missing)
         use_graph = self.use_graph if graph is None else graph
+        if self.decode_only:
+            # decode-only inference: no labels, no CTC loss, no accent branch (the reference predicts ctc_pred on
+            # the x_data -> ctc_pred sub-model, model.py:380-389)
+            xin = {"x_data": self._to_device("x_data", xd["x_data"])}
+            eng = self.engine()
+            out = (eng.forward_graphed(xin, tag="decode", decode_only=True) if use_graph
+                   else eng.forward(xin, decode_only=True))
+            out = dict(out)
+            out["ctc_pred"] = ops.softmax_rows(out["__ctc_logits"], classes=self.config.bpe_classes)
+            return out
         if use_graph and not want_intermediates:
             # host inputs go from page-locked memory STRAIGHT into the captured graph's static input buffers
             # (one asynchronous H2D per input, no intermediate device tensor)
@@ -409,7 +428,7 @@ class SARModel:
         xd = self._as_dict(x)
         n = len(xd["x_data"])
         on_device = isinstance(xd["x_data"], torch.Tensor) and xd["x_data"].is_cuda
-        if not on_device and n > batch_size and self.use_graph:
+        if not on_device and n > batch_size and self.use_graph and not self.decode_only:
             # several chunks: the pipelined path (copies and consecutive chunks overlap), same outputs
             return self.predict_generator({k: v[b0:b0 + batch_size] for k, v in xd.items()} for b0 in range(0, n, batch_size))
         chunks: List[List] = [[] for _ in self._outputs]
@@ -458,7 +477,7 @@ class SARModel:
         step and the D2H of its outputs on the compute stream.  Returns the handle _collect() waits on."""
         ps = self._pipe_state()
         xd = self._as_dict(x)
-        missing = [k for k in self.config.input_names() if k not in xd]
+        missing = [k for k in self.required_inputs() if k not in xd]
         if missing:
             raise ValueError("missing model inputs: %s" % missing)
         B = len(xd["x_data"])
@@ -471,6 +490,12 @@ class SARModel:
                 want = torch.int32 if k in ("x_ctc_in_len", "x_ctc_out_len") else torch.float32
                 if isinstance(v, torch.Tensor):
                     src = v
+                    if v.is_cuda:
+                        # produced by kernels on the CALLER's stream (utils.data_loader / fbank_batch hand their
+                        # outputs over without a host round trip): the staging copy must run after them, and the
+                        # caching allocator must not recycle the tensor while the copy stream still reads it
+                        ps["copy"].wait_stream(cur)
+                        v.record_stream(ps["copy"])
                 else:
                     a = np.ascontiguousarray(v).astype(np.int32 if want == torch.int32 else np.float32, copy=False)
                     src = torch.from_numpy(a)
@@ -541,6 +566,10 @@ class SARModel:
         fill the SMs that step i's latency-bound tail (Bi-GRU, VLAD, head) leaves idle, and step i-1's outputs are
         read back.  Returns the outputs concatenated over steps, as predict() does."""
         from collections import deque
+        if self.decode_only:                      # x_data -> ctc_pred sub-model: plain per-batch predict
+            outs = [self.predict(x[0] if isinstance(x, tuple) else x, batch_size=1 << 30)
+                    for i, x in enumerate(generator) if steps is None or i < steps]
+            return np.concatenate(outs, 0) if outs else np.zeros((0,), np.float32)
         it = iter(generator)
         pending = deque()
         chunks: List[List] = [[] for _ in self._outputs]
@@ -648,6 +677,8 @@ def SAR_Net(input_shape, ctc_enable=False, ar_enable=True, disc_enable=False, re
 def sub_model(model: SARModel, input_name, output_name):
     """Model(inputs=get_layer(input_name).input, outputs=get_layer(output_name).output)."""
     valid = model.config.output_names() + ["embedding", "y_accent_logits", "y_disc_logits"]
+    if model.config.ctc_enable:
+        valid.append("ctc_pred")           # x_data -> posteriors (B, S, bpe_classes): decode-only, needs no labels
     if output_name == "AR_BN2":
         output_name = "embedding"
     if output_name not in valid:
@@ -669,16 +700,14 @@ def ctc_pred(model: SARModel, x, batch_size, input_len):
     S = model.config.plan().seq_len
     T = max(0, min(int(input_len), S))
     rows = []
-    lanes, model.lanes = model.lanes, 1                  # the single-graph step keeps the ctc_pred logits
-    try:
-        for b0 in range(0, n, batch_size):
-            sl = {k: v[b0:b0 + batch_size] for k, v in xd.items()}
-            o = model.forward_device(sl)
-            dec, dec_len = ops.ctc_greedy(o["__ctc_logits"], fixed_len=T, classes=model.config.bpe_classes)
-            dec, dec_len = dec.cpu().numpy(), dec_len.cpu().numpy()
-            rows += [dec[i, :dec_len[i]] for i in range(len(dec))]
-    finally:
-        model.lanes = lanes
+    # x_data is the only input the decode needs: the step runs as the x_data -> ctc_pred sub-model whatever model
+    # object was passed (label inputs, if present, are ignored -- dummy labels must not trip the infeasible-CTC check)
+    dm = model if model.decode_only else sub_model(model, "x_data", "ctc_pred")
+    for b0 in range(0, n, batch_size):
+        o = dm.forward_device({"x_data": xd["x_data"][b0:b0 + batch_size]})
+        dec, dec_len = ops.ctc_greedy(o["__ctc_logits"], fixed_len=T, classes=model.config.bpe_classes)
+        dec, dec_len = dec.cpu().numpy(), dec_len.cpu().numpy()
+        rows += [dec[i, :dec_len[i]] for i in range(len(dec))]
     L = max([len(r) for r in rows] + [1])
     out = -np.ones((len(rows), L), dtype=np.int64)       # K.ctc_decode pads with -1
     for i, r in enumerate(rows):

@@ -246,3 +246,30 @@ def gemm_splitk_tc(a: Planes, w_packed: torch.Tensor, bias: torch.Tensor, zero_b
     check(_shim.lib().sar_splitk_reduce_fwd(ptr(ws), ptr(bias), ptr(out), M, N, ksplit, stream_ptr()), "sar_splitk_reduce_fwd")
     ops._count(1)
     return out
+
+
+def pack_vlad_assign(w_assign: np.ndarray) -> np.ndarray:
+    """Assignment kernel (D, K+G) -> the packed form sar_vlad_tc_fwd takes: [2][KGP][D] fp16 hi/lo, KGP = K+G rounded up
+    to 16 with zero rows."""
+    d, kg = w_assign.shape
+    pad = (-kg) % 16
+    return pack_dense_weights(np.pad(np.asarray(w_assign, dtype=np.float32), ((0, 0), (0, pad))))
+
+
+def vlad_tc_supported(B: int, S: int, D: int, K: int, G: int) -> bool:
+    return bool(_shim.load_library().sar_vlad_tc_supported(int(B), int(S), int(D), int(K), int(G)))
+
+
+def vlad_tc(x: Planes, wa_packed: torch.Tensor, b_assign: torch.Tensor, centers: torch.Tensor, B: int, S: int, K: int,
+            G: int, *, planes: Optional[Planes] = None, want_dense: bool = True) -> Optional[torch.Tensor]:
+    """sar_vlad_tc_fwd: x = hi/lo planes of the (B*S, 256) descriptors -> (B, K*256) fp32 and/or `planes` (alloc_rows(B, K*256))."""
+    D = x.C
+    assert x.rows >= B * S and tuple(centers.shape) == (K + G, D)
+    out = torch.empty((B, K * D), device=x.t.device, dtype=torch.float32) if (want_dense or planes is None) else None
+    if planes is not None:
+        assert tuple(planes.t.shape) == (2, B, K * D), (tuple(planes.t.shape), (2, B, K * D))
+    check(_shim.lib().sar_vlad_tc_fwd(ptr(x.t), x.rows, ptr(wa_packed), ptr(b_assign), ptr(centers), ptr(out),
+                                      ptr(planes.t) if planes is not None else None, B, S, D, K, G, stream_ptr()),
+          "sar_vlad_tc_fwd")
+    ops._count(1)
+    return out

@@ -196,6 +196,18 @@ int sar_vlad_fwd(const float* feat, const float* w_assign, const float* b_assign
 int sar_vlad_planes_fwd(const float* feat, const float* w_assign, const float* b_assign, const float* score,
                         const float* centers, float* out, void* out_planes, int B, int S, int D, int K, int G, void* stream);
 
+/* Tensor-core NetVLAD / GhostVLAD (csrc/vlad_tc.cu): the same result as sar_vlad_planes_fwd with the fused assignment
+ * conv, but both contractions (scores = X @ Wa, V = A^T @ X) run as tcgen05.mma (fp16 hi/lo operands, fp32 accumulate).
+ *   x_planes   fp16 hi/lo planes [2][x_rows][256] of the (B*S, 256) descriptors (sar_layernorm_planes_fwd, seg = 0)
+ *   wa_packed  fp16 hi/lo [2][KGP][256], KGP = K+G rounded up to 16: row kg = column kg of the assignment kernel
+ *              (w_assign[:, kg]), zero rows for the padding
+ * `out` (B, K*256) fp32 and/or `out_planes` [2][B][K*256] fp16 hi/lo.  Shapes: D == 256, S <= 128, K+G <= 128 and the
+ * tiles must fit shared memory: sar_vlad_tc_supported() returns 1 when they do (0: call sar_vlad_fwd instead).
+ * Replaces: model.py:82-109 (vlad()), VLAD.py:26-49 (VladPooling.call). */
+int sar_vlad_tc_supported(int B, int S, int D, int K, int G);
+int sar_vlad_tc_fwd(const void* x_planes, long long x_rows, const void* wa_packed, const float* b_assign,
+                    const float* centers, float* out, void* out_planes, int B, int S, int D, int K, int G, void* stream);
+
 /* Row softmax: out (rows, C) = softmax over the first C columns of x (rows, ld), ld >= C.
  * Replaces: the 'softmax' activation of Dense (model.py:35-42; ctc_pred, model.py:268) -- the posteriors
  * K.ctc_decode reads in ctc_pred() (model.py:385-389).  ld > C: rows padded by the tensor-core ctc_pred GEMM. */

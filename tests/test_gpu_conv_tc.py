@@ -217,3 +217,57 @@ def test_vlad_planes_output_matches_dense(cuda_device):
     rebuilt = planes.t[0].float() + planes.t[1].float() / 2048.0
     assert float((rebuilt - dense).abs().max()) < 2.0 ** -21
     assert ops.vlad(feat, wa, ba, cen, K, G, planes=planes, want_dense=False) is None
+
+
+def _planes_of_rows(x2d):
+    """(M, C) float array -> hi/lo planes [2][M][C] like sar_layernorm_planes_fwd writes them."""
+    from aesrc2020_b200 import tc
+    x = torch.as_tensor(np.ascontiguousarray(x2d, dtype=np.float32), device="cuda")
+    hi = x.half()
+    lo = ((x - hi.float()) * 2048.0).half()
+    return tc.Planes(torch.stack([hi, lo]).contiguous(), 1, x.shape[0], 1, x.shape[1], False)
+
+
+@pytest.mark.parametrize("mode,K,G,S,B", [("gvlad", 64, 8, 48, 3), ("vlad", 64, 0, 48, 64), ("gvlad", 8, 2, 21, 5),
+                                          ("gvlad", 10, 3, 114, 2), ("vlad", 4, 0, 5, 1), ("gvlad", 64, 8, 75, 4),
+                                          ("gvlad", 64, 8, 48, 200), ("gvlad", 64, 8, 48, 90), ("gvlad", 32, 8, 128, 7),
+                                          ("vlad", 100, 0, 16, 3)])
+def test_vlad_tc_vs_literal_5d_formula(cuda_device, mode, K, G, S, B):
+    """Tensor-core NetVLAD/GhostVLAD (csrc/vlad_tc.cu: tcgen05 scores + residual GEMMs, MN-major operands) vs the literal
+    (B,1,S,K+G,D) broadcast of VLAD.py:33-48 in float64, the CUDA-core kernel, and its own planes output.  Shapes cover
+    one and several cluster slices per utterance, several items per persistent CTA (B = 200: one slice, B = 90: two),
+    single- and double-buffered X tiles, S = 128 and K > 64."""
+    from aesrc2020_b200 import ops, tc
+    D = 256
+    assert tc.vlad_tc_supported(B, S, D, K, G)
+    rng = np.random.RandomState(K + S + B)
+    feat = rng.randn(B, S, D)
+    wa = rng.randn(D, K + G) / np.sqrt(D) * 3
+    ba = rng.randn(K + G) * 0.1
+    cen = rng.randn(K + G, D) / np.sqrt(D)
+    xp = _planes_of_rows(feat.reshape(B * S, D))
+    x32 = (xp.t[0].double() + xp.t[1].double() / 2048.0).cpu().numpy().reshape(B, 1, S, D)    # what the kernel is given
+    score = t64(x32) @ t64(wa) + t64(ba)
+    want = O.vlad_pooling(t64(x32), score, t64(cen), mode, K)
+    wap = torch.from_numpy(tc.pack_vlad_assign(wa.astype(np.float32))).cuda()
+    planes = tc.alloc_rows(B, K * D, "cuda")
+    got = tc.vlad_tc(xp, wap, dev(ba), dev(cen), B, S, K, G, planes=planes)
+    assert norm_err(got, want) < 2e-5
+    ref = ops.vlad(dev(x32.reshape(B, S, D)), dev(wa), dev(ba), dev(cen), K, G)
+    assert norm_err(got, ref) < 2e-5
+    rebuilt = planes.t[0].float() + planes.t[1].float() / 2048.0
+    assert float((rebuilt - got).abs().max()) < 2.0 ** -21
+    assert tc.vlad_tc(xp, wap, dev(ba), dev(cen), B, S, K, G, planes=planes, want_dense=False) is None
+    again = tc.vlad_tc(xp, wap, dev(ba), dev(cen), B, S, K, G)
+    assert torch.equal(again, got)                       # deterministic (fixed reduction orders)
+
+
+def test_vlad_tc_unsupported_shapes_are_refused(cuda_device):
+    from aesrc2020_b200 import tc, _shim
+    assert not tc.vlad_tc_supported(4, 200, 256, 64, 8)          # S > 128
+    assert not tc.vlad_tc_supported(4, 48, 128, 64, 8)           # D != 256
+    assert not tc.vlad_tc_supported(4, 128, 256, 120, 8)         # tiles do not fit shared memory
+    xp = _planes_of_rows(np.zeros((4 * 200, 256)))
+    with pytest.raises(_shim.SarnetError):
+        tc.vlad_tc(xp, torch.zeros(2, 80, 256, dtype=torch.float16, device="cuda"), torch.zeros(72, device="cuda"),
+                   torch.zeros(72, 256, device="cuda"), 4, 200, 64, 8)

@@ -1,11 +1,13 @@
 """GPU parity of the whole forward (SAR_Net(...).predict through the C ABI) against the float64
 CPU oracle, for the BASELINE.json configurations at oracle-sized batches, plus the
 size-independent properties used at full size (batch-split invariance, padding semantics)."""
+import os
+
 import numpy as np
 import pytest
 import torch
 
-from helpers import rel_err, norm_err, REL_TOL
+from helpers import rel_err, norm_err, REL_TOL, dev
 from oracle import sarnet_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -309,3 +311,87 @@ def test_data_loader_feeds_predict_without_host_round_trip(cuda_device):
     assert all(isinstance(g, torch.Tensor) and g.is_cuda for g in got)
     for g, w in zip(got, want):
         assert np.allclose(g.cpu().numpy(), w, rtol=2e-4, atol=1e-6)
+
+
+def test_ctc_pred_is_decode_only_and_sub_model_exposes_the_posteriors(cuda_device):
+    """the reference decodes on sub_model(model, 'x_data', 'ctc_pred') with x as the only input
+    (model.py:380-389).  ctc_pred() must not need label inputs, dummy labels must not trip the infeasible-CTC check, and
+    the sub-model's predict() returns the (B, S, bpe_classes) posteriors."""
+    from aesrc2020_b200 import model as mdl
+    model, x, _ = build("cfg5_gvlad_circle_ctc")
+    S = model.config.plan().seq_len
+    full = model.forward_device(x, want_intermediates=True)["ctc_pred"].cpu().numpy()
+    only_x = {"x_data": x["x_data"]}
+    got = mdl.ctc_pred(model, only_x, batch_size=2, input_len=S)
+    assert np.array_equal(got, O.ctc_greedy_decode(full, S))
+    bad = dict(x)
+    bad["x_ctc_out_len"] = np.full_like(np.asarray(x["x_ctc_out_len"]), 71)      # infeasible for the loss: ignored here
+    assert np.array_equal(mdl.ctc_pred(model, bad, batch_size=2, input_len=S), got)
+    sm = mdl.sub_model(model, "x_data", "ctc_pred")
+    assert sm.required_inputs() == ["x_data"]
+    probs = sm.predict(only_x, batch_size=2)
+    assert probs.shape == full.shape
+    assert rel_err(probs, full) < 1e-5 and np.allclose(probs.sum(-1), 1.0, atol=1e-5)
+    assert np.array_equal(mdl.ctc_pred(sm, x["x_data"], batch_size=1, input_len=S), got)
+    with pytest.raises(ValueError):
+        mdl.sub_model(mdl.SAR_Net((200, 80, 1), res_type="res18", res_filters=32, mto="avg")[0], "x_data", "ctc_pred")
+
+
+def test_predict_generator_accepts_device_batches_from_data_loader(cuda_device):
+    """predict_generator's staging copy runs on a private copy stream; device tensors produced on the caller's
+    stream (utils.data_loader kernels) must be ordered before it.  Many rounds with fresh tensors every step (so the
+    caching allocator recycles them) against per-batch predict."""
+    from aesrc2020_b200 import utils as us
+    model, _, _ = build("cfg5_gvlad_circle_ctc")
+    rng = np.random.RandomState(11)
+    lst = ["a", "b", "c", "d"]
+    kw = dict(max_input_len=500, max_ctc_len=72, encoder_len=model.config.plan().seq_len, accent_classes=8)
+    datas = []
+    for r in range(6):
+        data = {u: rng.rand(n, 80).astype(np.float32) * 9 for u, n in zip(lst, rng.randint(300, 700, size=4))}
+        acc = {u: int(rng.randint(0, 8)) for u in lst}
+        trans = {u: [int(v) for v in rng.randint(3, 998, size=rng.randint(3, 9))] for u in lst}
+        datas.append((data, acc, trans))
+
+    def gen():
+        for data, acc, trans in datas:
+            yield us.data_loader(lst, True, True, True, data, acc, trans, **kw)      # (inputs, targets), device tensors
+    want = [model.predict(us.data_loader(lst, True, True, True, d, a, t, **kw)[0], batch_size=4) for d, a, t in datas]
+    got = model.predict_generator(gen())
+    for i in range(len(got)):
+        w = np.concatenate([(o[i].cpu().numpy() if isinstance(o[i], torch.Tensor) else o[i]) for o in want], 0)
+        assert np.allclose(got[i], w, rtol=2e-4, atol=1e-6), i
+
+
+def test_ds_softmax_wider_than_the_head_kernel(cuda_device):
+    """DS(1000, 'softmax') (the reference's ctc_pred layer, model.py:268) through the layer surface."""
+    from aesrc2020_b200 import model as mdl
+    rng = np.random.RandomState(3)
+    x = rng.randn(7, 5, 64).astype(np.float32)
+    for n in (8, 33, 1000, 1500):
+        layer = mdl.DS(n, "softmax", name="d")
+        w = {"kernel": rng.randn(64, n).astype(np.float32) * 0.3, "bias": rng.randn(n).astype(np.float32)}
+        layer.set_weights_dict(w)
+        got = layer(dev(x)).cpu().numpy()
+        z = x.astype(np.float64) @ w["kernel"].astype(np.float64) + w["bias"]
+        e = np.exp(z - z.max(-1, keepdims=True))
+        assert got.shape == (7, 5, n) and rel_err(got, e / e.sum(-1, keepdims=True)) < 2e-4
+
+
+def test_model_saves_and_loads_keras_h5(cuda_device, tmp_path):
+    """model.save_weights('x.h5') / model.save('x.h5') (train.py:35) write the Keras HDF5 layout at exactly that path and
+    load_weights / raw_model read it back by name (model.py:181-183)."""
+    from aesrc2020_b200 import model as mdl, h5lite
+    model, x, _ = build("cfg2_gvlad_arcface")
+    kw = CONFIGS["cfg2_gvlad_arcface"]["kw"]
+    want = model.predict(x, batch_size=8)
+    for fn, name in ((model.save_weights, "w.h5"), (model.save, "m.h5")):
+        p = str(tmp_path / name)
+        fn(p)
+        assert os.path.exists(p) and not os.path.exists(p + ".npz")
+        names = list(h5lite.read_keras_weights(p))
+        assert "conv2d_1/kernel:0" in names and "gvlad_pool/centers:0" in names
+        m2, _ = mdl.SAR_Net((model.config.input_shape[0], 80, 1), seed=999, raw_model=p, **kw)
+        got = m2.predict(x, batch_size=8)
+        for g, w in zip(got, want):
+            assert np.array_equal(g, w)
