@@ -63,6 +63,7 @@ SIGNATURES = {
     "sar_ctc_ld_fwd": (c_int, [c_fp, c_int, c_fp, c_ip, c_ip, c_fp, c_fp, c_ip, c_int, c_int, c_int, c_int, C.c_void_p]),
     "sar_loss_reduce_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, C.c_void_p]),
     "sar_fbank_fwd": (c_int, [c_fp, c_ip, c_fp, c_fp, c_fp, c_int, c_int, c_int, C.c_void_p]),
+    "sar_fbank_pcm16_fwd": (c_int, [c_ip, c_ip, c_fp, c_fp, c_fp, c_int, c_int, c_int, C.c_void_p]),
 }
 
 

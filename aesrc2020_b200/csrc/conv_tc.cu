@@ -37,7 +37,8 @@ constexpr int TC_BM = 128;            // output rows per tile (TMEM lanes)
 constexpr int TC_STAGES = 3;
 constexpr int TC_PLANE_BYTES = 16384; // 128 rows x 128 B (kc = 64) per operand plane
 constexpr int TC_STAGE_BYTES = 4 * TC_PLANE_BYTES;
-constexpr int TC_THREADS = 320;
+constexpr int TC_THREADS = 320;            // 8 epilogue warps + TMA producer + MMA issuer
+constexpr int TC_THREADS_MAX = 576;        // 16 epilogue warps: one warp per (quadrant, 32-column chunk) of a single 128-wide tile
 // Warp roles.  The SM's schedulers favour the HIGHEST warp id of a sub-partition (wid % 4), so the two
 // single-lane issuing warps get ids 4 and 5: they share sub-partitions 0 and 1 with epilogue warps 0 and 1
 // and win arbitration while those spin on an mbarrier (with ids 0/1 the MMA warp crawled at ~600 cycles/tap).
@@ -77,7 +78,10 @@ struct TcParams {
   const int* flag_dep;                   // [m_tiles] the same counters of the layer this one reads (or null)
   int flag_need;                         // items per M tile = 4 * Cout / 32
   int epi_mode;                          // epilogue mode of this layer (-1, 0, 2, 3)
+  int tma_out;                           // plane outputs of an unsplit map leave through TMA stores (see epilogue_item)
 };
+// tensor maps of the plane outputs, box = (32 channels, 32 rows, 1 plane), 64B swizzle
+struct OutMaps { CUtensorMap raw, act; };
 
 // ------------------------------------------------------------------ epilogue (shared by both kernels)
 // Work item = (tile, 32-column chunk) handled by ONE warp.  The eight epilogue warps are two groups of four (one
@@ -128,12 +132,13 @@ __device__ __noinline__ float tanh_precise(float x) { return tanhf(x); }
 // per-warp area (s_bias_u, 32 floats apart), shortcut rows are read with ld.global.cg (another CTA wrote them
 // during this very kernel), and the finished item is published in the layer's per-M-tile counter.
 template <int MODE, bool CHAIN = false>
-__device__ __forceinline__ void epilogue_item(const TcParams& p, int tile, int c, int it, int quad, int lane,
+__device__ __forceinline__ void epilogue_item(const TcParams& p, const OutMaps& om, int tile, int c, int it, int quad, int lane,
                                            uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar,
                                            uint32_t s_bias_u, uint32_t stage_u) {
   const int BN = p.BN;
   const int as = it & 1;
   const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+  if (p.dbg && blockIdx.x == 0 && lane == 0 && it < 2 && c < 4) p.dbg[64 + ((it * 4 + c) * 4 + quad) * 4] = clock64();
   const int z = tile / p.mn_tiles, tmn = tile - z * p.mn_tiles;         // K slice (split-K), tile within the M x N grid
   const int mt = tmn / p.n_tiles, nt = tmn - mt * p.n_tiles;
   const int n0 = nt * BN, c0 = c * 32;
@@ -193,10 +198,21 @@ __device__ __forceinline__ void epilogue_item(const TcParams& p, int tile, int c
   const size_t lo_off = (size_t)(p.split ? p.R2 : p.R) * p.Cout;       // hi plane -> lo plane, in elements
   const uint32_t sw = (uint32_t)((lane >> 1) & 3);
   const uint32_t rowoff = (uint32_t)lane * 64u;
+  // TMA-store path (plane outputs of an unsplit map): the staging tiles ARE the 64B-swizzled boxes of the output
+  // tensor maps (slot = piece ^ ((row >> 1) & 3) is CU_TENSOR_MAP_SWIZZLE_64B for 64-byte rows), so the write-out
+  // is one cp.async.bulk.tensor store per plane instead of an LDS -> STG loop; pad rows are staged as zeros.
+  const bool tma_out = p.tma_out != 0;
+  const bool zrow = tma_out && drow_p < 0;
   mbar_wait(&tfull_bar[as], aphase);
   tc_fence_after();
-#define EPI_STAMP(j) if (p.dbg && blockIdx.x == 0 && quad == 0 && lane == 0 && it < 4 && c == 0) p.dbg[32 + it * 6 + (j)] = clock64();
-  EPI_STAMP(0)
+  if (tma_out) {                                     // the previous item's stores have finished reading the staging
+    if (lane == 0) bulk_wait_read0();
+    __syncwarp();
+  }
+  // profiling aid (sar_tc_conv.dbg, >= 256 int64): CTA 0, per (quadrant, chunk) item of the first two tiles:
+  // [item entered | accumulator ready | math + staging done | item finished]
+#define EPI_STAMP(j) if (p.dbg && blockIdx.x == 0 && lane == 0 && it < 2 && c < 4) p.dbg[64 + ((it * 4 + c) * 4 + quad) * 4 + (j)] = clock64();
+  EPI_STAMP(1)
   if (has_res) {                                     // shortcut pieces -> staging
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -242,6 +258,7 @@ __device__ __forceinline__ void epilogue_item(const TcParams& p, int tile, int c
     if (out_raw) {                                   // in place: a lane only reads and writes its own row here
       uint4 hi, lo;
       split8(v, hi, lo);
+      if (zrow) { hi = make_uint4(0, 0, 0, 0); lo = hi; }
       sts128(rb + off, hi);
       sts128(rb + EPI_PLANE_BYTES + off, lo);
     }
@@ -262,6 +279,7 @@ __device__ __forceinline__ void epilogue_item(const TcParams& p, int tile, int c
       if (out_act) {
         uint4 hi, lo;
         split8(v, hi, lo);
+        if (zrow) { hi = make_uint4(0, 0, 0, 0); lo = hi; }
         sts128(ab + off, hi);
         sts128(ab + EPI_PLANE_BYTES + off, lo);
       } else {                                       // fp32 tile: 32 rows x 128 B, 16-byte piece j in slot j ^ (row & 7)
@@ -272,8 +290,17 @@ __device__ __forceinline__ void epilogue_item(const TcParams& p, int tile, int c
       }
     }
   }
-  EPI_STAMP(3)
+  EPI_STAMP(2)
+  if (tma_out) fence_proxy_async();                  // my generic-proxy staging writes -> visible to the TMA engine
   __syncwarp();
+  if (tma_out) {
+    if (lane == 0) {
+      const int cc = n0 + c0, cr = (int)row0;
+      if (out_raw) { tma_store_3d(&om.raw, rb, cc, cr, 0); tma_store_3d(&om.raw, rb + EPI_PLANE_BYTES, cc, cr, 1); }
+      if (out_act) { tma_store_3d(&om.act, ab, cc, cr, 0); tma_store_3d(&om.act, ab + EPI_PLANE_BYTES, cc, cr, 1); }
+      bulk_commit();
+    }
+  } else
   // write-out of the plane tiles: every store instruction covers 8 rows x 64 B
   if (out_raw || out_act) {
 #pragma unroll 1
@@ -310,37 +337,42 @@ __device__ __forceinline__ void epilogue_item(const TcParams& p, int tile, int c
   __syncwarp();                                      // staging is reused by this warp's next item
   if (CHAIN && p.flag_done) {                        // publish: the rows this item wrote are visible GPU-wide
     if (lane == 0) {
+      if (tma_out) { bulk_wait0(); asm volatile("fence.proxy.async;" ::: "memory"); }   // the bulk stores have landed
       __threadfence();
       atomicAdd(p.flag_done + mt, 1);
     }
   }
-  EPI_STAMP(5)
+  EPI_STAMP(3)
 #undef EPI_STAMP
 }
 
 // all items of this CTA for one epilogue warp
 template <int MODE>
-__device__ __forceinline__ void epilogue_warp(const TcParams& p, int total_tiles, int warp, int lane, uint32_t tmem_base,
-                                              uint64_t* tfull_bar, uint64_t* tempty_bar, const float* s_bias, uint8_t* epi_base) {
+__device__ __forceinline__ void epilogue_warp(const TcParams& p, const OutMaps& om, int total_tiles, int warp, int lane, int ngroups,
+                                              uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar, const float* s_bias,
+                                              uint8_t* epi_base) {
   const int quad = warp & 3, group = warp >> 2;
   const uint32_t stage_u = smem_u32(epi_base + (size_t)warp * EPI_WARP_BYTES);
   const uint32_t s_bias_u = smem_u32(s_bias);
   const int nchunks = p.BN >> 5;
-  int it = 0;
+  int it = 0, item = 0;
   for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it)
-    for (int c = 0; c < nchunks; ++c)
-      if (((it * nchunks + c) & 1) == group)
-        epilogue_item<MODE>(p, tile, c, it, quad, lane, tmem_base, tfull_bar, tempty_bar, s_bias_u, stage_u);
+    for (int c = 0; c < nchunks; ++c, ++item)
+      if (item % ngroups == group)
+        epilogue_item<MODE>(p, om, tile, c, it, quad, lane, tmem_base, tfull_bar, tempty_bar, s_bias_u, stage_u);
+  if (p.tma_out && lane == 0) bulk_wait0();          // my bulk stores are complete before the CTA may exit
 }
 
 // ------------------------------------------------------------------ the kernel
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS_MAX, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapS,
                const __grid_constant__ CUtensorMap mapWm, const __grid_constant__ CUtensorMap mapWs,
-               const TcParams p) {
+               const __grid_constant__ OutMaps om, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   // [stages x 64 KB ring][epilogue staging 64 KB unless aliased onto the ring][barriers][bias | scale | shift]
+  const int nepi = (int)(blockDim.x >> 5) - 2;          // epilogue warps (8, or 16 for a single wide tile per CTA)
+  const int WARP_TMA = nepi, WARP_MMA = nepi + 1;
   uint8_t* epi_own = smem + (size_t)p.stages * TC_STAGE_BYTES;
   uint8_t* epi_base = p.epi_alias ? smem : epi_own;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_own + (p.epi_alias ? 0 : EPI_BYTES));
@@ -357,7 +389,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const uint32_t tmem_cols = (4 * BN <= 128) ? 128u : (4 * BN <= 256 ? 256u : 512u);   // 2 stages x (acc0, acc1)
 
   // short prologue: see conv_tc_slab_kernel
-  if (warp == TC_WARP_TMA) {
+  if (warp == WARP_TMA) {
     if (lane < 2 * TC_STAGES + 4) {
       const bool is_tempty = lane >= 2 * TC_STAGES + 2;
       mbar_init(&full_bar[lane], is_tempty ? 4u * (uint32_t)(BN >> 5) : 1u);
@@ -368,7 +400,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       if (p.chunks_sc) { prefetch_tmap(&mapS); prefetch_tmap(&mapWs); }
     }
   }
-  if (warp == TC_WARP_MMA) {
+  if (warp == WARP_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -376,13 +408,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
-  if (warp < 8) {
-    for (int i = threadIdx.x; i < p.Cout; i += 256) {
+  if (warp < nepi) {
+    for (int i = threadIdx.x; i < p.Cout; i += nepi * 32) {
       s_bias[i] = p.bias ? p.bias[i] : 0.f;
       s_scale[i] = p.act_scale ? p.act_scale[i] : 1.f;
       s_shift[i] = p.act_shift ? p.act_shift[i] : 0.f;
     }
-    named_bar_sync(1, 256);
+    named_bar_sync(1, nepi * 32);
   }
 
   const int n_main = p.ksplit > 1 ? p.ksteps_split : p.ntaps * p.chunks_main;      // split-K: one tap, a slice of the chunks
@@ -391,7 +423,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   pdl_wait();          // everything above touched only constants (bias / BN affines) and on-chip state
   pdl_trigger();
 
-  if (warp == TC_WARP_TMA) {
+  if (warp == WARP_TMA) {
     // ===================== TMA producer (whole warp converged, one elected lane issues) =====================
     int stage = 0; uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -430,7 +462,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == TC_WARP_MMA) {
+  } else if (warp == WARP_MMA) {
     // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
     // instruction descriptor: D=f32, A=B=f16, K-major both, N=BN, M=128
     const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
@@ -469,12 +501,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
   } else {
     // ===================== epilogue warps (TMEM lane quadrant = warp % 4) =====================
-    epilogue_warp<-1>(p, total_tiles, warp, lane, tmem_base, tfull_bar, tempty_bar, s_bias, epi_base);
+    epilogue_warp<-1>(p, om, total_tiles, warp, lane, nepi >> 2, tmem_base, tfull_bar, tempty_bar, s_bias, epi_base);
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == TC_WARP_MMA) {
+  if (warp == WARP_MMA) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
   }
@@ -510,13 +542,15 @@ struct SlabParams {
 __device__ __forceinline__ uint64_t make_desc_shifted(uint32_t saddr, int row_bytes) { return make_desc(saddr, row_bytes); }
 
 template <int KC, bool RESIDENT, int EPI_MODE>
-__global__ void __launch_bounds__(SL_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS_MAX, 1)
 conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapS,
                     const __grid_constant__ CUtensorMap mapWm, const __grid_constant__ CUtensorMap mapWs,
-                    const TcParams p, const SlabParams sp) {
+                    const __grid_constant__ OutMaps om, const TcParams p, const SlabParams sp) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const long long t_entry = p.dbg ? clock64() : 0;
+  const int nepi = (int)(blockDim.x >> 5) - 2;          // epilogue warps (8, or 16 for a single wide tile per CTA)
+  const int WARP_TMA = nepi, WARP_MMA = nepi + 1;
   const int n_main = p.ntaps * p.chunks_main;
   const int n_ksteps = n_main + p.chunks_sc;
   const int nb = sp.resident ? n_ksteps : sp.nring;                    // weight slots in smem
@@ -545,7 +579,7 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   // Short prologue (it is on the critical path of every layer: the previous kernel's CTA must leave the SM before
   // this one starts): the 52 mbarriers are initialised one per lane, TMEM is allocated by the MMA warp, and only
   // the epilogue warps wait for the bias / BN vectors (they are idle until the first accumulator is ready).
-  if (warp == SL_WARP_TMA) {
+  if (warp == WARP_TMA) {
     constexpr int NBAR = 2 * SL_MAX_SLABS + 2 * SL_MAX_RING + 2 + 2 + 8;       // contiguous from sfull_bar
     for (int i = lane; i < NBAR; i += 32) {
       const bool is_tempty = (i == 2 * SL_MAX_SLABS + 2 * SL_MAX_RING + 2) || (i == 2 * SL_MAX_SLABS + 2 * SL_MAX_RING + 3);
@@ -557,7 +591,7 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       if (p.chunks_sc) { prefetch_tmap(&mapS); prefetch_tmap(&mapWs); }
     }
   }
-  if (warp == SL_WARP_MMA) {
+  if (warp == WARP_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -565,13 +599,13 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
-  if (warp < 8) {
-    for (int i = threadIdx.x; i < p.Cout; i += 256) {
+  if (warp < nepi) {
+    for (int i = threadIdx.x; i < p.Cout; i += nepi * 32) {
       s_bias[i] = p.bias ? p.bias[i] : 0.f;
       s_scale[i] = p.act_scale ? p.act_scale[i] : 1.f;
       s_shift[i] = p.act_shift ? p.act_shift[i] : 0.f;
     }
-    named_bar_sync(1, 256);
+    named_bar_sync(1, nepi * 32);
   }
   if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[61] = clock64();     // prologue done
 
@@ -583,7 +617,7 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     return c < p.chunks_main ? (tap * p.chunks_main + c) * p.kc_main : n_main * p.kc_main + (c - p.chunks_main) * p.kc_sc;
   };
 
-  if (warp == SL_WARP_TMA) {
+  if (warp == WARP_TMA) {
     // ===================== TMA producer (whole warp converged, one elected lane issues) =====================
     {
       if (sp.resident) {
@@ -650,7 +684,7 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         }
       }
     }
-  } else if (warp == SL_WARP_MMA) {
+  } else if (warp == WARP_MMA) {
     // ===================== MMA issuer: ONE elected lane runs the whole loop =====================
     // The loop is issue-bound (one thread, dependent uniform-datapath ops at ~8 cycles each), so the
     // instruction count per tcgen05.mma is what sets the speed of the thin layers:
@@ -752,12 +786,12 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     __syncwarp();
   } else {
     pdl_wait();                               // identity-shortcut rows and the output planes
-    epilogue_warp<EPI_MODE>(p, total_tiles, warp, lane, tmem_base, tfull_bar, tempty_bar, s_bias, epi_base);
+    epilogue_warp<EPI_MODE>(p, om, total_tiles, warp, lane, nepi >> 2, tmem_base, tfull_bar, tempty_bar, s_bias, epi_base);
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == SL_WARP_MMA) {
+  if (warp == WARP_MMA) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
   }
@@ -778,7 +812,7 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 // Weights stream through the TMA ring (non-resident form of conv_tc_slab_kernel), epilogue staging has its own
 // 64 KB, the per-item bias / BN vectors a 3 KB per-warp area.
 constexpr int CH_MAX = 12;
-struct ChainPhase { CUtensorMap mapA, mapS, mapWm, mapWs; TcParams p; };
+struct ChainPhase { CUtensorMap mapA, mapS, mapWm, mapWs; OutMaps om; TcParams p; };
 struct ChainParams {
   int n_phases;
   int* flags;                    // [n_phases][m_tiles] counters + [1] CTA exit counter (self-cleaning)
@@ -983,16 +1017,18 @@ __global__ void __launch_bounds__(SL_THREADS, 1) conv_tc_chain_kernel(const __gr
     int it = 0;
     for (int ph = 0; ph < cp.n_phases; ++ph) {
       const TcParams& p = cp.ph[ph].p;
+      const OutMaps& om = cp.ph[ph].om;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it)
         for (int c = 0; c < nchunks; ++c)
           if (((it * nchunks + c) & 1) == group) {
             switch (p.epi_mode) {
-              case 0: epilogue_item<0, true>(p, tile, c, it, quad, lane, tmem_base, tfull_bar, tempty_bar, vec_u, stage_u); break;
-              case 3: epilogue_item<3, true>(p, tile, c, it, quad, lane, tmem_base, tfull_bar, tempty_bar, vec_u, stage_u); break;
-              default: epilogue_item<-1, true>(p, tile, c, it, quad, lane, tmem_base, tfull_bar, tempty_bar, vec_u, stage_u); break;
+              case 0: epilogue_item<0, true>(p, om, tile, c, it, quad, lane, tmem_base, tfull_bar, tempty_bar, vec_u, stage_u); break;
+              case 3: epilogue_item<3, true>(p, om, tile, c, it, quad, lane, tmem_base, tfull_bar, tempty_bar, vec_u, stage_u); break;
+              default: epilogue_item<-1, true>(p, om, tile, c, it, quad, lane, tmem_base, tfull_bar, tempty_bar, vec_u, stage_u); break;
             }
           }
     }
+    if (lane == 0) bulk_wait0();                     // (items of TMA-store layers already waited before publishing)
   }
 
   tc_fence_before();
@@ -1125,6 +1161,19 @@ static int fill_params(const sar_tc_conv* d, TcParams& p) {
     SAR_REQUIRE(p.chunks_main % p.ksplit == 0, SAR_ERR_BAD_ARG, "sar_conv_tc_fwd: ksplit must divide a_ch / %d", p.kc_main);
   }
   p.ksteps_split = p.ksplit > 1 ? p.chunks_main / p.ksplit : 0;
+  // plane outputs of an unsplit map leave through TMA stores (SAR_TC_TMA_OUT=0: the LDS -> STG write-out, an A/B aid)
+  static const bool tma_ok = !(getenv("SAR_TC_TMA_OUT") && getenv("SAR_TC_TMA_OUT")[0] == '0');
+  p.tma_out = (tma_ok && !p.split && !d->out_dense && (d->out_raw || d->out_act)) ? 1 : 0;
+  return SAR_OK;
+}
+
+// tensor maps of the plane outputs for the TMA-store epilogue (dummies when the layer does not use it)
+static int fill_out_maps(const sar_tc_conv* d, const TcParams& p, const CUtensorMap& dummy, OutMaps& om) {
+  om.raw = dummy; om.act = dummy;
+  if (!p.tma_out) return SAR_OK;
+  int rc;
+  if (d->out_raw && (rc = tc_make_map(&om.raw, d->out_raw, p.R, d->cout, 2, 32, 32))) return rc;
+  if (d->out_act && (rc = tc_make_map(&om.act, d->out_act, p.R, d->cout, 2, 32, 32))) return rc;
   return SAR_OK;
 }
 }  // namespace sar
@@ -1200,15 +1249,23 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
   } else {
     mapS = mapA; mapWs = mapWm;
   }
+  OutMaps om;
+  if ((rc = fill_out_maps(d, p, mapA, om))) return rc;
   const int tiles = p.mn_tiles * p.ksplit;
   const int grid = tiles < sms ? tiles : sms;
+  // 16 epilogue warps when every CTA owns ONE 128-wide tile: its 16 (quadrant, 32-column) items then drain in one
+  // round instead of two -- the epilogue of such a launch is a tail nothing overlaps (SAR_TC_EPI16=0 disables)
+  static const bool epi16_ok = !(getenv("SAR_TC_EPI16") && getenv("SAR_TC_EPI16")[0] == '0');
+  auto threads_for = [&](size_t operand_bytes) {
+    return (epi16_ok && p.epi_alias && p.BN >= 128 && operand_bytes >= 2 * (size_t)EPI_BYTES) ? TC_THREADS_MAX : TC_THREADS;
+  };
   if (slab) {
     const int nb = sp.resident ? (p.ntaps * p.chunks_main + p.chunks_sc) : sp.nring;
     size_t smem = fixed + (size_t)sp.nslab * 2 * sp.slab_bytes + (size_t)nb * 2 * sp.bplane_bytes;
     if (p.epi_alias && smem - fixed < (size_t)EPI_BYTES) smem = fixed + EPI_BYTES;    // aliased staging needs 64 KB of operand region
     auto launch = [&](auto kern) -> int {
       { const int arc = allow_max_smem(kern, "sar_conv_tc_fwd"); if (arc) return arc; }
-      launch_k(kern, dim3(grid), dim3(SL_THREADS), smem, (cudaStream_t)stream, mapA, mapS, mapWm, mapWs, p, sp);
+      launch_k(kern, dim3(grid), dim3(threads_for(smem - fixed)), smem, (cudaStream_t)stream, mapA, mapS, mapWm, mapWs, om, p, sp);
       return 0;
     };
     // epilogue mode: the residual-block combinations get compile-time flags (bit 0 identity shortcut, bit 1 raw out)
@@ -1232,7 +1289,7 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
     p.stages = p.epi_alias ? 3 : 2;
     const size_t smem = 1024 + (size_t)p.stages * TC_STAGE_BYTES + (p.epi_alias ? 0 : EPI_BYTES) + 256 + 3 * (size_t)d->cout * sizeof(float);
     { const int arc = allow_max_smem(conv_tc_kernel, "sar_conv_tc_fwd"); if (arc) return arc; }
-    launch_k(conv_tc_kernel, dim3(grid), dim3(TC_THREADS), smem, (cudaStream_t)stream, mapA, mapS, mapWm, mapWs, p);
+    launch_k(conv_tc_kernel, dim3(grid), dim3(threads_for((size_t)p.stages * TC_STAGE_BYTES)), smem, (cudaStream_t)stream, mapA, mapS, mapWm, mapWs, om, p);
   }
   return check_launch("sar_conv_tc_fwd");
 }
@@ -1326,6 +1383,7 @@ extern "C" int sar_conv_tc_chain_fwd(const sar_tc_conv* descs, int n, void* work
     } else {
       P.mapS = P.mapA; P.mapWs = P.mapWm;
     }
+    if ((rc = fill_out_maps(d, p, P.mapA, P.om))) return rc;
   }
   const int tiles = g0.m_tiles * (cout / BN);
   const int grid = tiles < sms ? tiles : sms;

@@ -189,11 +189,19 @@ vlad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
     const bool row_valid = tid < p.S;
     const uint32_t a_u = smem_u32(as_);
     int it = 0;
+#ifdef SAR_VLAD_PROFILE
+    long long st[8];
+#define VT_STAMP(j) if (blockIdx.x == 0 && tid == 0 && it == 1) st[j] = clock64();
+#else
+#define VT_STAMP(j)
+#endif
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
       const int b = item / p.nsplit, h = item - b * p.nsplit;
+      VT_STAMP(0)
       const int k_lo = h * KL;                                  // this item's clusters: [k_lo, min(K, k_lo + KL))
       mbar_wait(sfull, (uint32_t)it & 1u);
       tc_fence_after();
+      VT_STAMP(1)
       // ---- online softmax over the K+G scores of my descriptor row (VLAD.py:34-35)
       float mx = -INFINITY, sum = 0.f;
       for (int g = 0; g < KGP; g += 16) {
@@ -217,6 +225,7 @@ vlad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
         mx = nm;
       }
       const float inv_sum = 1.0f / sum;
+      VT_STAMP(2)
       // ---- probabilities of my cluster slice -> [P_hi | P_lo] rows (MN-major B operand), column sums by shuffles
       for (int jb = 0; jb < KL; jb += 32) {
         float pr[32];
@@ -263,6 +272,7 @@ vlad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
         const float cs = warp_transpose_sum(pr, lane);          // sum over this warp's 32 rows of column jb + lane
         s_part[warp * 64 + jb + lane] = cs;
       }
+      VT_STAMP(3)
       fence_proxy_async();                                      // generic-proxy writes -> visible to tcgen05.mma
       tc_fence_before();
       mbar_arrive(afull);
@@ -270,16 +280,29 @@ vlad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
       if (tid < KL) s_asum[tid] = (s_part[tid] + s_part[64 + tid]) + (s_part[128 + tid] + s_part[192 + tid]);
       named_bar_sync(1, 128);
       // ---- residual epilogue: thread = feature column d of both M tiles
-      mbar_wait(vfull, (uint32_t)it & 1u);
-      tc_fence_after();
       for (int kb = 0; kb < KL; kb += 32) {
         float v[2][32];
         float ssq[32];
+        // the cluster centres of this block: 64 independent loads per thread, in flight BEFORE the accumulators are
+        // waited for (they are L2 hits: 72 KB shared by every CTA, more than the L1 left beside 190 KB of shared
+        // memory; loaded one by one behind the TMEM reads they cost ~100 dependent L2 round trips per item)
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const int k = k_lo + kb + e;
+            v[t][e] = __ldg(p.centers + (size_t)(k < p.K ? k : p.K - 1) * VT_D + t * 128 + tid);
+          }
+        if (kb == 0) {
+          VT_STAMP(4)
+          mbar_wait(vfull, (uint32_t)it & 1u);
+          tc_fence_after();
+          VT_STAMP(5)
+        }
 #pragma unroll
         for (int e = 0; e < 32; ++e) ssq[e] = 0.f;
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
-          const int d = t * 128 + tid;
 #pragma unroll
           for (int g = 0; g < 32; g += 16) {
             if (kb + g < KL) {
@@ -290,11 +313,8 @@ vlad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
 #pragma unroll
               for (int e = 0; e < 16; ++e) {
                 const int k = k_lo + kb + g + e;
-                float x = 0.f;
-                if (k < p.K) {
-                  const float acc = fmaf(__uint_as_float(r1[e]), VT_LO_INV, __uint_as_float(r0[e]));
-                  x = fmaf(-s_asum[kb + g + e], __ldg(p.centers + (size_t)k * VT_D + d), acc);     // VLAD.py:38-45
-                }
+                const float acc = fmaf(__uint_as_float(r1[e]), VT_LO_INV, __uint_as_float(r0[e]));
+                const float x = (k < p.K) ? fmaf(-s_asum[kb + g + e], v[t][g + e], acc) : 0.f;     // VLAD.py:38-45
                 v[t][g + e] = x;
                 ssq[g + e] = fmaf(x, x, ssq[g + e]);
               }
@@ -330,6 +350,12 @@ vlad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
         named_bar_sync(1, 128);                                 // s_ss / s_inv are reused by the next cluster block
       }
       tc_fence_before();                                        // my TMEM reads are ordered before the next item's MMAs
+      VT_STAMP(6)
+#ifdef SAR_VLAD_PROFILE
+      if (blockIdx.x == 0 && tid == 0 && it == 1)
+        printf("vlad_tc item 1: wait scores %lld | softmax %lld | probs+tile %lld | asum+centers issue %lld | wait GEMM2 %lld | epilogue %lld | total %lld\n",
+               st[1] - st[0], st[2] - st[1], st[3] - st[2], st[4] - st[3], st[5] - st[4], st[6] - st[5], st[6] - st[0]);
+#endif
     }
   }
 

@@ -366,6 +366,25 @@ class SARNetEngine:
                 key = "y_disc_bn/W" if cfg.metric_loss in ("sphereface", "cosface", "arcface") else "y_disc_bn/kernel"
                 self._put("y_disc_bn/w", w[key])
 
+    # ------------------------------------------------------------------ timed segments (bench.py)
+    # segment_events = {"vlad": []}: the named segment is bracketed by a CUDA event pair; while the step is being
+    # captured the events are EXTERNAL ones, i.e. event-record nodes of the graph, re-recorded by every replay.
+    segment_events: Optional[Dict[str, list]] = None
+
+    def _seg_begin(self, name):
+        if self.segment_events is None or name not in self.segment_events:
+            return None
+        ext = torch.cuda.is_current_stream_capturing()
+        e0 = torch.cuda.Event(enable_timing=True, external=ext)
+        e1 = torch.cuda.Event(enable_timing=True, external=ext)
+        e0.record()
+        return name, e0, e1
+
+    def _seg_end(self, h):
+        if h is not None:
+            h[2].record()
+            self.segment_events[h[0]].append((h[1], h[2]))
+
     # ------------------------------------------------------------------ building blocks
     def dense_ln(self, x, name, ln_name, act="tanh", pre=None):
         p = self.p
@@ -622,6 +641,7 @@ class SARNetEngine:
                 if key not in self._seq_bufs:
                     self._seq_bufs[key] = tc.alloc_rows(B, key[2], self.device)
                 vplanes = self._seq_bufs[key]
+            seg = self._seg_begin("vlad")
             if vlad_on_tc:                       # both contractions on the tensor cores (csrc/vlad_tc.cu)
                 integ = tc.vlad_tc(P4, p[cfg.mto + "/w_assign_tc"], p[cfg.mto + "/b_assign"], p[cfg.mto + "/centers"],
                                    B, S_, cfg.vlad_clusters, G, planes=vplanes,
@@ -629,6 +649,7 @@ class SARNetEngine:
             else:                                # shapes outside the tensor-core kernel's tiles: CUDA-core kernel (vlad.cu)
                 integ = ops.vlad(ar, p[cfg.mto + "/w_assign"], p[cfg.mto + "/b_assign"], p[cfg.mto + "/centers"],
                                  cfg.vlad_clusters, G, planes=vplanes, want_dense=want_intermediates or vplanes is None)
+            self._seg_end(seg)
         if cfg.mto in ("vlad", "gvlad") and getattr(self, "embed_ksplit", 0):
             from . import tc
             emb = tc.gemm_splitk_tc(vplanes, p["AR_EMBEDDING/w_tc"], p["AR_EMBEDDING/bias_folded"],

@@ -294,13 +294,17 @@ def labels_pack(accent=None, n_classes=0, trans=None, trans_offsets=None, Lmax=0
     return out
 
 
-def fbank(wav, offsets, melfb_t, Fmax: int, T: int):
-    """wav (N,) float32 concatenated utterances, offsets (B+1,) int64 -> x_data (B,T,80)."""
-    wav = _f32(wav)
+def fbank(wav, offsets, melfb_t, Fmax: int, T: int, out=None, feat_ws=None):
+    """wav (N,) concatenated utterances -- float32 in [-1, 1) or int16 PCM -- offsets (B+1,) int64 -> x_data (B,T,80).
+    `out` / `feat_ws`: preallocated (B,T,80) / (B,Fmax,80) fp32 (a graph's static buffers)."""
+    if wav.dtype not in (torch.float32, torch.int16):
+        raise _shim.SarnetError("fbank: wav must be float32 or int16, got %s" % wav.dtype)
+    wav = wav.contiguous()
     B = offsets.numel() - 1
-    feat = torch.empty((B, Fmax, 80), device=wav.device, dtype=torch.float32)
-    x = torch.empty((B, T, 80), device=wav.device, dtype=torch.float32)
-    check(_shim.lib().sar_fbank_fwd(ptr(wav), ptr(offsets), ptr(melfb_t), ptr(feat), ptr(x), B, Fmax, T,
-                                    stream_ptr()), "sar_fbank_fwd")
+    feat = feat_ws if feat_ws is not None else torch.empty((B, Fmax, 80), device=wav.device, dtype=torch.float32)
+    x = out if out is not None else torch.empty((B, T, 80), device=wav.device, dtype=torch.float32)
+    assert tuple(feat.shape) == (B, Fmax, 80) and x.numel() == B * T * 80 and x.is_contiguous()
+    fn = _shim.lib().sar_fbank_pcm16_fwd if wav.dtype == torch.int16 else _shim.lib().sar_fbank_fwd
+    check(fn(ptr(wav), ptr(offsets), ptr(melfb_t), ptr(feat), ptr(x), B, Fmax, T, stream_ptr()), "sar_fbank_fwd")
     _count(2)
     return x, feat

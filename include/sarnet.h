@@ -289,6 +289,10 @@ int sar_loss_reduce_fwd(const float* sample_stats, const float* ctc_loss, const 
  * x_data (B,T,80) output. */
 int sar_fbank_fwd(const float* wav, const long long* offsets, const float* melfb_t,
                   float* feat_ws, float* x_data, int B, int Fmax, int T, void* stream);
+/* Same from 16-bit PCM (sample / 32768, what soundfile.read hands psf.fbank, make_fbank.py:26-27): the host ships
+ * raw audio (2 B/sample) and the whole front-end runs on the device. */
+int sar_fbank_pcm16_fwd(const int16_t* pcm, const long long* offsets, const float* melfb_t,
+                        float* feat_ws, float* x_data, int B, int Fmax, int T, void* stream);
 
 /* ---- on-device batch assembly (the callers' side of the path: utils.data_loader, utils.py:71-117) ---------- */
 

@@ -35,7 +35,7 @@ S = eng.plan.seq_len
 rn = eng.resnet
 res["forward_total"] = timeit(lambda: eng.forward(xd))
 res["resnet_total"] = timeit(lambda: rn.forward(xd["x_data"]))
-cur = rn._buf(B, eng.plan.pool_hout, eng.plan.pool_wout, 64, False, "raw")
+cur = rn._buf(0, B, eng.plan.pool_hout, eng.plan.pool_wout, 64, False, "raw")
 s_, t_ = rn.bn(eng.plan.stem.post_bn)
 res["stem_pool"] = timeit(lambda: tc.stem_pool(xd["x_data"], rn.p["stem/kernel"], rn.p["stem/bias"], s_, t_, cur))
 seq = torch.randn(B, S, 256, device=dev)
@@ -48,6 +48,9 @@ res["gru_proj_512_1536"] = timeit(lambda: ops.dense(seq512, p["CTC_BIGRU/kernel_
 xp = torch.randn(B, S, 2, 768, device=dev) * 0.1
 res["bigru_recurrence"] = timeit(lambda: ops.bigru(xp, p["CRNN/rec"], p["CRNN/rbias"], seq=True))
 res["vlad"] = timeit(lambda: ops.vlad(seq, p["gvlad/w_assign"], p["gvlad/b_assign"], p["gvlad/centers"], 64, 8))
+xpl = tc.Planes((torch.randn(2, B * S, 256, device=dev) * 0.5).half(), 1, B * S, 1, 256, False)
+vpl = tc.alloc_rows(B, 64 * 256, dev)
+res["vlad_tc"] = timeit(lambda: tc.vlad_tc(xpl, p["gvlad/w_assign_tc"], p["gvlad/b_assign"], p["gvlad/centers"], B, S, 64, 8, planes=vpl, want_dense=False))
 integ = torch.randn(B, 16384, device=dev)
 res["embed_splitk"] = timeit(lambda: eng.embed(integ))
 emb = torch.randn(B, 256, device=dev)

@@ -17,8 +17,9 @@ seed)` -- a pure numpy RandomState function -- handed to the reference graph in 
 order with shape and name checks (minikeras.reset(queue=...)).  A test regenerates the same
 weights from (cfg, seed); `weights_l1` in each fixture guards against RNG drift.
 
-What these fixtures pin: graph wiring and the reference-authored arithmetic.  What they do not pin:
-the third-party primitives (see minikeras docstring).
+What these fixtures pin: graph wiring and the reference-authored arithmetic.  The third-party primitives underneath
+(minikeras) are asserted against PyTorch's own conv / batch-norm / pool / GRU / layer-norm / CTC kernels by
+check_minikeras.assert_primitives_match_torch() before anything is written (and again by tests/test_golden.py).
 """
 import json
 import os
@@ -167,6 +168,10 @@ def layer_cases():
 
 def main():
     only = sys.argv[1:]
+    # the stand-in primitives are checked against PyTorch's own kernels BEFORE any fixture is written, so the fixtures
+    # are tied to an implementation that is independent of minikeras and of the oracle (check_minikeras.py)
+    from check_minikeras import assert_primitives_match_torch
+    assert_primitives_match_torch(verbose=True)
     for name in CASES:
         if only and name not in only:
             continue

@@ -250,3 +250,21 @@ def test_keras_named_npz_loads_into_canonical_weights(tmp_path):
     assert any(k.endswith(":0") for k in loaded)
     back = W.from_keras_named(cfg, loaded)
     assert all(np.array_equal(back[k], w[k]) for k in w)
+
+
+def test_minikeras_primitives_match_torch():
+    """The eager Keras/TF stand-in the fixtures were generated on agrees with PyTorch's own kernels (F.conv2d with explicit
+    TF-SAME pads, F.batch_norm, F.max_pool2d, nn.GRU with permuted gates, F.layer_norm(eps=1e-14), F.ctc_loss, F.normalize)
+    to 1e-10: the golden files are tied to an implementation independent of minikeras and of the oracle."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    mods = {k: sys.modules.get(k) for k in ("keras", "tensorflow", "keras_layer_normalization")}
+    try:
+        from check_minikeras import assert_primitives_match_torch
+        res = assert_primitives_match_torch()
+        assert set(res) == {"conv2d", "bn/pool/dense", "gru/ln", "ctc/l2n"} and max(res.values()) < 1e-10
+    finally:                                   # minikeras installs stand-in `keras` / `tensorflow` modules: remove them
+        for k in list(sys.modules):
+            if k.split(".")[0] in ("keras", "tensorflow", "keras_layer_normalization", "minikeras", "check_minikeras"):
+                if mods.get(k) is None:
+                    sys.modules.pop(k, None)
