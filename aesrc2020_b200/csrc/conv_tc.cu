@@ -79,6 +79,11 @@ struct TcParams {
   int flag_need;                         // items per M tile = 4 * Cout / 32
   int epi_mode;                          // epilogue mode of this layer (-1, 0, 2, 3)
   int tma_out;                           // plane outputs of an unsplit map leave through TMA stores (see epilogue_item)
+  // The residual stream between the blocks of a stage as ONE fp32 plane [R][Cout] (flat-pad rows) instead of hi/lo
+  // planes: it is only ever added in an epilogue (never an MMA operand), so the hi/lo split on write and the re-join
+  // on read -- 16 of the ~18 instructions per element a conv2 epilogue spends on it -- are dropped.
+  const float* res32;                    // identity shortcut, fp32 (instead of `res`)
+  float* out_raw32;                      // raw sum, fp32 (instead of `out_raw`); needs tma_out
 };
 // tensor maps of the plane outputs, box = (32 channels, 32 rows, 1 plane), 64B swizzle
 struct OutMaps { CUtensorMap raw, act; };
@@ -143,8 +148,9 @@ __device__ __forceinline__ void epilogue_item(const TcParams& p, const OutMaps& 
   const int mt = tmn / p.n_tiles, nt = tmn - mt * p.n_tiles;
   const int n0 = nt * BN, c0 = c * 32;
   const long long row0 = (long long)mt * TC_BM + quad * 32;
-  const bool has_res = MODE < 0 ? (p.res != nullptr) : ((MODE & 1) != 0);
-  const bool out_raw = MODE < 0 ? (p.out_raw != nullptr) : ((MODE & 2) != 0);
+  const bool res32 = p.res32 != nullptr, raw32 = p.out_raw32 != nullptr;
+  const bool has_res = MODE < 0 ? (p.res != nullptr || res32) : ((MODE & 1) != 0);
+  const bool out_raw = MODE < 0 ? (p.out_raw != nullptr || raw32) : ((MODE & 2) != 0);
   const bool out_act = MODE < 0 ? (p.out_act != nullptr) : true;
   const bool out_dense = MODE < 0 ? (p.out_dense != nullptr) : false;
   const int act_kind = MODE < 0 ? p.act_kind : 0;
@@ -152,19 +158,32 @@ __device__ __forceinline__ void epilogue_item(const TcParams& p, const OutMaps& 
   // global side of the plane tiles: lane -> (row 8i + lane/4, 16-byte piece lane%4); slot = piece ^ ((row >> 1) & 3)
   const int g_row = lane >> 2, g_piece = lane & 3;
   const size_t g_col = (size_t)(n0 + c0 + 8 * g_piece);
-  uint4 res_h[4], res_l[4];
+  uint4 res_h[4], res_l[4];                          // planes: 4 hi + 4 lo pieces; fp32: pieces of rows 4i + lane/8
   if (has_res) {
+    if (res32) {                                     // lane -> (row 4i + lane/8, 16-byte piece lane%8), 128-byte rows
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const long long q = row0 + 8 * i + g_row;
-      res_h[i] = make_uint4(0, 0, 0, 0); res_l[i] = make_uint4(0, 0, 0, 0);
-      if (q < p.R) {
-        if (CHAIN) {
-          res_h[i] = __ldcg(reinterpret_cast<const uint4*>(p.res + (size_t)q * p.Cout + g_col));
-          res_l[i] = __ldcg(reinterpret_cast<const uint4*>(p.res + ((size_t)p.R + q) * p.Cout + g_col));
-        } else {
-          res_h[i] = __ldg(reinterpret_cast<const uint4*>(p.res + (size_t)q * p.Cout + g_col));
-          res_l[i] = __ldg(reinterpret_cast<const uint4*>(p.res + ((size_t)p.R + q) * p.Cout + g_col));
+      for (int i = 0; i < 8; ++i) {
+        const long long q = row0 + 4 * i + (lane >> 3);
+        uint4 r = make_uint4(0, 0, 0, 0);
+        if (q < p.R) {
+          const uint4* src = reinterpret_cast<const uint4*>(p.res32 + (size_t)q * p.Cout + n0 + c0 + 4 * (lane & 7));
+          r = CHAIN ? __ldcg(src) : __ldg(src);
+        }
+        if (i < 4) res_h[i] = r; else res_l[i - 4] = r;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const long long q = row0 + 8 * i + g_row;
+        res_h[i] = make_uint4(0, 0, 0, 0); res_l[i] = make_uint4(0, 0, 0, 0);
+        if (q < p.R) {
+          if (CHAIN) {
+            res_h[i] = __ldcg(reinterpret_cast<const uint4*>(p.res + (size_t)q * p.Cout + g_col));
+            res_l[i] = __ldcg(reinterpret_cast<const uint4*>(p.res + ((size_t)p.R + q) * p.Cout + g_col));
+          } else {
+            res_h[i] = __ldg(reinterpret_cast<const uint4*>(p.res + (size_t)q * p.Cout + g_col));
+            res_l[i] = __ldg(reinterpret_cast<const uint4*>(p.res + ((size_t)p.R + q) * p.Cout + g_col));
+          }
         }
       }
     }
@@ -214,11 +233,42 @@ __device__ __forceinline__ void epilogue_item(const TcParams& p, const OutMaps& 
 #define EPI_STAMP(j) if (p.dbg && blockIdx.x == 0 && lane == 0 && it < 2 && c < 4) p.dbg[64 + ((it * 4 + c) * 4 + quad) * 4 + (j)] = clock64();
   EPI_STAMP(1)
   if (has_res) {                                     // shortcut pieces -> staging
+    if (res32) {                                     // 32 rows x 128 B, piece j of a row in slot j ^ (row & 7)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint32_t off = (uint32_t)(8 * i + g_row) * 64u + (((uint32_t)g_piece ^ (uint32_t)(((8 * i + g_row) >> 1) & 3)) << 4);
-      sts128(rb + off, res_h[i]);
-      sts128(rb + EPI_PLANE_BYTES + off, res_l[i]);
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t r_ = (uint32_t)(4 * i + (lane >> 3));
+        sts128(rb + r_ * 128u + ((((uint32_t)lane & 7u) ^ (r_ & 7u)) << 4), i < 4 ? res_h[i] : res_l[i - 4]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t off = (uint32_t)(8 * i + g_row) * 64u + (((uint32_t)g_piece ^ (uint32_t)(((8 * i + g_row) >> 1) & 3)) << 4);
+        sts128(rb + off, res_h[i]);
+        sts128(rb + EPI_PLANE_BYTES + off, res_l[i]);
+      }
+    }
+    __syncwarp();
+  }
+  // fp32 tile of the residual stream (res32 in, raw32 out, in place): my row, 16-byte pieces 2g and 2g + 1
+  const uint32_t frow = rb + (uint32_t)lane * 128u;
+  const uint32_t fx7 = (uint32_t)(lane & 7);
+  // fp32 shortcut in, hi/lo PLANES out (a stage-ending conv2: its raw sum is the next stage's projection operand): the
+  // plane tiles are staged on top of the fp32 tile, whose rows do not coincide with plane rows -- every lane first
+  // takes its whole shortcut row into registers
+  // ... and the mirror case, hi/lo plane shortcut in, fp32 raw sum out (the first block of a stage with an identity
+  // shortcut on the stem's planes: res18 with 64 filters).  (The host routes both combinations to MODE -1.)
+  const bool res_to_regs = MODE < 0 && has_res && out_raw && (res32 != raw32);
+  uint4 rrow[8];
+  if (res_to_regs) {
+    if (res32) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) rrow[j] = lds128(frow + ((((uint32_t)j) ^ fx7) << 4));
+    } else {                                         // planes: pieces 0..3 of my hi row, then of my lo row
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        rrow[j] = lds128(rb + rowoff + ((((uint32_t)j) ^ sw) << 4));
+        rrow[4 + j] = lds128(rb + EPI_PLANE_BYTES + rowoff + ((((uint32_t)j) ^ sw) << 4));
+      }
     }
     __syncwarp();
   }
@@ -244,8 +294,25 @@ __device__ __forceinline__ void epilogue_item(const TcParams& p, const OutMaps& 
       for (int e = 0; e < 8; ++e) v[e] = fmaf(__uint_as_float(r1[e]), TC_LO_INV, __uint_as_float(r0[e])) + bb[e];
     }
     const uint32_t off = rowoff + (((uint32_t)g ^ sw) << 4);
-    if (has_res) {
-      const uint4 rh = lds128(rb + off), rl = lds128(rb + EPI_PLANE_BYTES + off);
+    const uint32_t f0 = frow + ((((uint32_t)(2 * g)) ^ fx7) << 4), f1 = frow + ((((uint32_t)(2 * g + 1)) ^ fx7) << 4);
+    if (has_res && res32) {
+      uint4 a, b;
+      if (res_to_regs) {                             // (g is a compile-time index only when the loop is unrolled)
+        a = g == 0 ? rrow[0] : g == 1 ? rrow[2] : g == 2 ? rrow[4] : rrow[6];
+        b = g == 0 ? rrow[1] : g == 1 ? rrow[3] : g == 2 ? rrow[5] : rrow[7];
+      } else {
+        a = lds128(f0); b = lds128(f1);
+      }
+      v[0] += __uint_as_float(a.x); v[1] += __uint_as_float(a.y); v[2] += __uint_as_float(a.z); v[3] += __uint_as_float(a.w);
+      v[4] += __uint_as_float(b.x); v[5] += __uint_as_float(b.y); v[6] += __uint_as_float(b.z); v[7] += __uint_as_float(b.w);
+    } else if (has_res) {
+      uint4 rh, rl;
+      if (res_to_regs) {
+        rh = g == 0 ? rrow[0] : g == 1 ? rrow[1] : g == 2 ? rrow[2] : rrow[3];
+        rl = g == 0 ? rrow[4] : g == 1 ? rrow[5] : g == 2 ? rrow[6] : rrow[7];
+      } else {
+        rh = lds128(rb + off); rl = lds128(rb + EPI_PLANE_BYTES + off);
+      }
       const __half2* ah = reinterpret_cast<const __half2*>(&rh);
       const __half2* bl = reinterpret_cast<const __half2*>(&rl);
 #pragma unroll
@@ -255,7 +322,10 @@ __device__ __forceinline__ void epilogue_item(const TcParams& p, const OutMaps& 
         v[e * 2 + 1] += fmaf(fl.y, TC_LO_INV, fh.y);
       }
     }
-    if (out_raw) {                                   // in place: a lane only reads and writes its own row here
+    if (out_raw && raw32) {                          // in place (a lane only touches its own row); pads need no zeros:
+      sts128(f0, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])));   // the
+      sts128(f1, make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7])));   // stream is never an MMA operand
+    } else if (out_raw) {                            // in place: a lane only reads and writes its own row here
       uint4 hi, lo;
       split8(v, hi, lo);
       if (zrow) { hi = make_uint4(0, 0, 0, 0); lo = hi; }
@@ -296,7 +366,8 @@ __device__ __forceinline__ void epilogue_item(const TcParams& p, const OutMaps& 
   if (tma_out) {
     if (lane == 0) {
       const int cc = n0 + c0, cr = (int)row0;
-      if (out_raw) { tma_store_3d(&om.raw, rb, cc, cr, 0); tma_store_3d(&om.raw, rb + EPI_PLANE_BYTES, cc, cr, 1); }
+      if (out_raw && raw32) tma_store_3d(&om.raw, rb, cc, cr, 0);          // one fp32 box, 128B swizzle
+      else if (out_raw) { tma_store_3d(&om.raw, rb, cc, cr, 0); tma_store_3d(&om.raw, rb + EPI_PLANE_BYTES, cc, cr, 1); }
       if (out_act) { tma_store_3d(&om.act, ab, cc, cr, 0); tma_store_3d(&om.act, ab + EPI_PLANE_BYTES, cc, cr, 1); }
       bulk_commit();
     }
@@ -364,7 +435,7 @@ __device__ __forceinline__ void epilogue_warp(const TcParams& p, const OutMaps& 
 }
 
 // ------------------------------------------------------------------ the kernel
-__global__ void __launch_bounds__(TC_THREADS_MAX, 1)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapS,
                const __grid_constant__ CUtensorMap mapWm, const __grid_constant__ CUtensorMap mapWs,
                const __grid_constant__ OutMaps om, const TcParams p) {
@@ -541,8 +612,9 @@ struct SlabParams {
 // row-shifted start needs no base-offset field (setting (addr>>7)&7 there gives wrong results).
 __device__ __forceinline__ uint64_t make_desc_shifted(uint32_t saddr, int row_bytes) { return make_desc(saddr, row_bytes); }
 
+// (the generic epilogue, EPI_MODE -1, needs more registers than 576 threads leave: it keeps the 320-thread bound)
 template <int KC, bool RESIDENT, int EPI_MODE>
-__global__ void __launch_bounds__(TC_THREADS_MAX, 1)
+__global__ void __launch_bounds__(EPI_MODE >= 0 ? TC_THREADS_MAX : TC_THREADS, 1)
 conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapS,
                     const __grid_constant__ CUtensorMap mapWm, const __grid_constant__ CUtensorMap mapWs,
                     const __grid_constant__ OutMaps om, const TcParams p, const SlabParams sp) {
@@ -1071,15 +1143,20 @@ int tc_make_map(CUtensorMap* map, const void* base, long long rows, int ch, int 
 static int make_map(CUtensorMap* map, const void* base, long long rows, int ch, int planes, int kc, int box_rows) {
   return tc_make_map(map, base, rows, ch, planes, kc, box_rows);
 }
+static int make_map_t(CUtensorMap* map, const void* base, long long rows, int ch, int planes, int kc, int box_rows, int esize);
 int tc_make_map(CUtensorMap* map, const void* base, long long rows, int ch, int planes, int kc, int box_rows) {
+  return make_map_t(map, base, rows, ch, planes, kc, box_rows, 2);
+}
+// esize 2: fp16 planes; esize 4: one fp32 plane (the residual stream)
+static int make_map_t(CUtensorMap* map, const void* base, long long rows, int ch, int planes, int kc, int box_rows, int esize) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return SAR_ERR_UNSUPPORTED; }
   cuuint64_t dims[3] = {(cuuint64_t)ch, (cuuint64_t)rows, (cuuint64_t)planes};
-  cuuint64_t strides[2] = {(cuuint64_t)ch * 2, (cuuint64_t)rows * ch * 2};
+  cuuint64_t strides[2] = {(cuuint64_t)ch * esize, (cuuint64_t)rows * ch * esize};
   cuuint32_t box[3] = {(cuuint32_t)kc, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUtensorMapSwizzle sw = (kc * 2 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+  CUtensorMapSwizzle sw = (kc * esize == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = enc(map, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d): rows=%lld ch=%d planes=%d kc=%d box_rows=%d", (int)r, rows, ch, planes, kc, box_rows); return SAR_ERR_BAD_ARG; }
@@ -1109,7 +1186,7 @@ static int fill_params(const sar_tc_conv* d, TcParams& p) {
               "sar_conv_tc_fwd: non-positive dimension");
   SAR_REQUIRE(d->a_ch % 32 == 0 && d->cout % 32 == 0 && (!d->s || d->s_ch % 32 == 0), SAR_ERR_UNSUPPORTED,
               "sar_conv_tc_fwd: channel counts must be multiples of 32 (a_ch=%d s_ch=%d cout=%d)", d->a_ch, d->s_ch, d->cout);
-  SAR_REQUIRE(d->out_raw || d->out_act || d->out_dense, SAR_ERR_BAD_ARG, "sar_conv_tc_fwd: no output requested");
+  SAR_REQUIRE(d->out_raw || d->out_raw_f32 || d->out_act || d->out_dense, SAR_ERR_BAD_ARG, "sar_conv_tc_fwd: no output requested");
   SAR_REQUIRE(d->act_kind >= 0 && d->act_kind <= 2, SAR_ERR_BAD_ARG, "sar_conv_tc_fwd: act_kind must be 0, 1 or 2");
   SAR_REQUIRE(!(d->out_act || d->out_dense) || d->act_kind != 0 || (d->act_scale && d->act_shift), SAR_ERR_BAD_ARG,
               "sar_conv_tc_fwd: act_kind 0 (BN->ReLU) outputs need act_scale/act_shift");
@@ -1144,6 +1221,12 @@ static int fill_params(const sar_tc_conv* d, TcParams& p) {
   p.n_tiles = d->cout / p.BN;
   p.bias = d->bias; p.act_scale = d->act_scale; p.act_shift = d->act_shift;
   p.res = reinterpret_cast<const __half*>(d->res);
+  p.res32 = d->res_f32;
+  p.out_raw32 = d->out_raw_f32;
+  SAR_REQUIRE(!(d->res && d->res_f32) && !(d->out_raw && d->out_raw_f32), SAR_ERR_BAD_ARG,
+              "sar_conv_tc_fwd: the residual stream is either hi/lo planes or one fp32 plane, not both");
+  SAR_REQUIRE((!d->res_f32 || aligned16(d->res_f32)) && (!d->out_raw_f32 || aligned16(d->out_raw_f32)), SAR_ERR_ALIGN,
+              "sar_conv_tc_fwd: fp32 residual pointers must be 16-byte aligned");
   p.out_raw = reinterpret_cast<__half*>(d->out_raw);
   p.out_act = reinterpret_cast<__half*>(d->out_act);
   p.out_dense = d->out_dense;
@@ -1163,7 +1246,10 @@ static int fill_params(const sar_tc_conv* d, TcParams& p) {
   p.ksteps_split = p.ksplit > 1 ? p.chunks_main / p.ksplit : 0;
   // plane outputs of an unsplit map leave through TMA stores (SAR_TC_TMA_OUT=0: the LDS -> STG write-out, an A/B aid)
   static const bool tma_ok = !(getenv("SAR_TC_TMA_OUT") && getenv("SAR_TC_TMA_OUT")[0] == '0');
-  p.tma_out = (tma_ok && !p.split && !d->out_dense && (d->out_raw || d->out_act)) ? 1 : 0;
+  p.tma_out = (tma_ok && !p.split && !d->out_dense && (d->out_raw || d->out_raw_f32 || d->out_act)) ? 1 : 0;
+  SAR_REQUIRE(!d->out_raw_f32 || p.tma_out, SAR_ERR_UNSUPPORTED,
+              "sar_conv_tc_fwd: out_raw_f32 needs the TMA-store epilogue (unsplit plane outputs, SAR_TC_TMA_OUT unset)");
+  SAR_REQUIRE(!(p.ksplit > 1) || (!d->res_f32 && !d->out_raw_f32), SAR_ERR_BAD_ARG, "sar_conv_tc_fwd: split-K has no residual stream");
   return SAR_OK;
 }
 
@@ -1173,6 +1259,7 @@ static int fill_out_maps(const sar_tc_conv* d, const TcParams& p, const CUtensor
   if (!p.tma_out) return SAR_OK;
   int rc;
   if (d->out_raw && (rc = tc_make_map(&om.raw, d->out_raw, p.R, d->cout, 2, 32, 32))) return rc;
+  if (d->out_raw_f32 && (rc = make_map_t(&om.raw, d->out_raw_f32, p.R, d->cout, 1, 32, 32, 4))) return rc;
   if (d->out_act && (rc = tc_make_map(&om.act, d->out_act, p.R, d->cout, 2, 32, 32))) return rc;
   return SAR_OK;
 }
@@ -1256,21 +1343,23 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
   // 16 epilogue warps when every CTA owns ONE 128-wide tile: its 16 (quadrant, 32-column) items then drain in one
   // round instead of two -- the epilogue of such a launch is a tail nothing overlaps (SAR_TC_EPI16=0 disables)
   static const bool epi16_ok = !(getenv("SAR_TC_EPI16") && getenv("SAR_TC_EPI16")[0] == '0');
-  auto threads_for = [&](size_t operand_bytes) {
-    return (epi16_ok && p.epi_alias && p.BN >= 128 && operand_bytes >= 2 * (size_t)EPI_BYTES) ? TC_THREADS_MAX : TC_THREADS;
+  auto threads_for = [&](size_t operand_bytes, int mode) {
+    return (epi16_ok && mode >= 0 && p.epi_alias && p.BN >= 128 && operand_bytes >= 2 * (size_t)EPI_BYTES) ? TC_THREADS_MAX : TC_THREADS;
   };
   if (slab) {
     const int nb = sp.resident ? (p.ntaps * p.chunks_main + p.chunks_sc) : sp.nring;
     size_t smem = fixed + (size_t)sp.nslab * 2 * sp.slab_bytes + (size_t)nb * 2 * sp.bplane_bytes;
     if (p.epi_alias && smem - fixed < (size_t)EPI_BYTES) smem = fixed + EPI_BYTES;    // aliased staging needs 64 KB of operand region
-    auto launch = [&](auto kern) -> int {
-      { const int arc = allow_max_smem(kern, "sar_conv_tc_fwd"); if (arc) return arc; }
-      launch_k(kern, dim3(grid), dim3(threads_for(smem - fixed)), smem, (cudaStream_t)stream, mapA, mapS, mapWm, mapWs, om, p, sp);
-      return 0;
-    };
     // epilogue mode: the residual-block combinations get compile-time flags (bit 0 identity shortcut, bit 1 raw out)
     int mode = -1;
-    if (d->out_act && !d->out_dense && d->act_kind == 0 && !p.split) mode = (d->res ? 1 : 0) | (d->out_raw ? 2 : 0);
+    auto launch = [&](auto kern) -> int {
+      { const int arc = allow_max_smem(kern, "sar_conv_tc_fwd"); if (arc) return arc; }
+      const int m_eff = (mode == 0 || mode == 2 || mode == 3) ? mode : -1;
+      launch_k(kern, dim3(grid), dim3(threads_for(smem - fixed, m_eff)), smem, (cudaStream_t)stream, mapA, mapS, mapWm, mapWs, om, p, sp);
+      return 0;
+    };
+    if (d->out_act && !d->out_dense && d->act_kind == 0 && !p.split && !(d->res_f32 && d->out_raw) && !(d->res && d->out_raw_f32))
+      mode = ((d->res || d->res_f32) ? 1 : 0) | ((d->out_raw || d->out_raw_f32) ? 2 : 0);
     auto pick = [&](auto kc_tag, auto res_tag) -> int {
       constexpr int KCv = decltype(kc_tag)::value;
       constexpr bool RSv = decltype(res_tag)::value;
@@ -1289,7 +1378,7 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
     p.stages = p.epi_alias ? 3 : 2;
     const size_t smem = 1024 + (size_t)p.stages * TC_STAGE_BYTES + (p.epi_alias ? 0 : EPI_BYTES) + 256 + 3 * (size_t)d->cout * sizeof(float);
     { const int arc = allow_max_smem(conv_tc_kernel, "sar_conv_tc_fwd"); if (arc) return arc; }
-    launch_k(conv_tc_kernel, dim3(grid), dim3(threads_for((size_t)p.stages * TC_STAGE_BYTES)), smem, (cudaStream_t)stream, mapA, mapS, mapWm, mapWs, om, p);
+    launch_k(conv_tc_kernel, dim3(grid), dim3(TC_THREADS), smem, (cudaStream_t)stream, mapA, mapS, mapWm, mapWs, om, p);
   }
   return check_launch("sar_conv_tc_fwd");
 }
@@ -1368,8 +1457,8 @@ extern "C" int sar_conv_tc_chain_fwd(const sar_tc_conv* descs, int n, void* work
     p.flag_need = 4 * (cout / 32);
     p.epi_mode = -1;
     if (d->out_act && d->act_kind == 0 && !p.split) {
-      const int m = (d->res ? 1 : 0) | (d->out_raw ? 2 : 0);
-      if (m == 0 || m == 3) p.epi_mode = m;
+      const int m = ((d->res || d->res_f32) ? 1 : 0) | ((d->out_raw || d->out_raw_f32) ? 2 : 0);
+      if ((m == 0 || m == 3) && !(d->res_f32 && d->out_raw) && !(d->res && d->out_raw_f32)) p.epi_mode = m;
     }
     const int ktot = 9 * d->a_ch + (d->s ? d->s_ch : 0);
     int rc;

@@ -13,7 +13,7 @@
 //     K-major A operand of the score GEMM (M = s, K = d) and the MN-major A operand of the residual GEMM (M = d, K = s):
 //     no transpose anywhere.
 //   * Wa^T hi/lo ([2][KGP][256], packed on the host) is loaded once per CTA and stays resident (persistent CTAs).
-//   * scores: thread = descriptor row; online softmax straight out of tensor memory; the probabilities of this item's
+//   * scores: two threads per descriptor row (column halves); online softmax straight out of tensor memory; the probabilities of this item's
 //     cluster slice go to shared memory as fp16 hi/lo rows [s][P_hi | P_lo] -- the MN-major B operand of the second
 //     GEMM (N = cluster) -- and their column sums (sum_s A[s,k]) are reduced with warp shuffles.
 //   * residual: thread = feature column d (two 128-column M tiles); V[k][d] = acc - asum[k] * c[k][d], squared norms
@@ -21,7 +21,7 @@
 //     64 B (fp16 planes for the tensor-core AR_EMBEDDING GEMM) of one output row.
 // HBM traffic is the algorithmic minimum (X read once per slice from L2/HBM, K*D written once).
 //
-// Roles: warps 0-3 compute (TMEM lane quadrant = warp), warp 4 = TMA producer + MMA issuer (one elected lane).
+// Roles: warps 0-7 compute (TMEM lane quadrant = warp & 3), warp 8 = TMA producer + MMA issuer (one elected lane).
 // Limits: D == 256, S <= 128, K + G <= 128 and the tiles must fit shared memory; sar_vlad_tc_supported() tells, the
 // CUDA-core kernel (vlad.cu) covers everything else (and the VladPooling([feat, score]) surface with given scores).
 #include <cuda.h>
@@ -31,10 +31,10 @@
 
 namespace sar {
 
-constexpr int VT_THREADS = 160;
-constexpr int VT_WARP_MMA = 4;
+constexpr int VT_THREADS = 288;              // 8 compute warps + the TMA / MMA warp
+constexpr int VT_WARP_MMA = 8;
 constexpr int VT_D = 256;
-constexpr int VT_MISC_BYTES = 4096;
+constexpr int VT_MISC_BYTES = 6144;
 constexpr float VT_LO_INV = 1.f / 2048.f;
 constexpr uint32_t VT_ACC2 = 256;                 // TMEM column of the residual accumulators (scores use [0, 2*KGP))
 
@@ -79,14 +79,16 @@ vlad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
   uint64_t* xfull = wfull + 1;                                  // [2]
   uint64_t* xempty = xfull + 2;                                 // [2]
   uint64_t* sfull = xempty + 2;                                 // scores complete
-  uint64_t* afull = sfull + 1;                                  // probability tile written (128 arrivals)
+  uint64_t* afull = sfull + 1;                                  // probability tile written (256 arrivals)
   uint64_t* vfull = afull + 1;                                  // residual accumulators complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 64);
   float* s_ba = reinterpret_cast<float*>(misc + 128);           // [128]
   float* s_part = s_ba + 128;                                   // [4 warps][64] column sums of the probabilities
   float* s_asum = s_part + 256;                                 // [64]
-  float* s_ss = s_asum + 64;                                    // [4 warps][32] squared-norm partials
-  float* s_inv = s_ss + 128;                                    // [32]
+  float* s_ss = s_asum + 64;                                    // [8 warps][32] squared-norm partials
+  float* s_inv = s_ss + 256;                                    // [32]
+  float* s_mx = s_inv + 32;                                     // [2 halves][128 rows] softmax partial max
+  float* s_sm = s_mx + 256;                                     // [2 halves][128 rows] softmax partial sum
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
   const int KGP = p.KGP, KL = p.KL;
@@ -96,7 +98,7 @@ vlad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
       mbar_init(wfull, 1);
       mbar_init(&xfull[0], 1); mbar_init(&xfull[1], 1);
       mbar_init(&xempty[0], 1); mbar_init(&xempty[1], 1);
-      mbar_init(sfull, 1); mbar_init(afull, 128); mbar_init(vfull, 1);
+      mbar_init(sfull, 1); mbar_init(afull, 256); mbar_init(vfull, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       prefetch_tmap(&mapX); prefetch_tmap(&mapW);
     }
@@ -184,10 +186,17 @@ vlad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
     }
   } else {
     // ===================== compute warps =====================
+    // 8 warps: quad = warp & 3 is the TMEM lane quadrant (rows quad*32 .. +31), hf = warp >> 2 splits the work of a
+    // quadrant in two: the score columns (softmax partials are merged through shared memory), the 32-cluster blocks
+    // of the probability tile, and the two 128-column M tiles of the residual epilogue.  Two warps per scheduler, and
+    // half the per-thread work of a 4-warp layout: the phases are chains of dependent ALU ops, i.e. latency bound.
     pdl_wait();                                                 // centers are constants, the outputs are not
-    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-    const bool row_valid = tid < p.S;
+    const int quad = warp & 3, hf = warp >> 2;
+    const int row = quad * 32 + lane;                           // descriptor row s (scores) / feature column d (residual)
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const bool row_valid = row < p.S;
     const uint32_t a_u = smem_u32(as_);
+    constexpr float LOG2E = 1.4426950408889634f;
     int it = 0;
 #ifdef SAR_VLAD_PROFILE
     long long st[8];
@@ -202,32 +211,42 @@ vlad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
       mbar_wait(sfull, (uint32_t)it & 1u);
       tc_fence_after();
       VT_STAMP(1)
-      // ---- online softmax over the K+G scores of my descriptor row (VLAD.py:34-35)
+      // ---- softmax over the K+G scores of my row (VLAD.py:34-35): my half of the 16-column groups, online
       float mx = -INFINITY, sum = 0.f;
-      for (int g = 0; g < KGP; g += 16) {
+      for (int g = 16 * hf; g < KGP; g += 32) {
         uint32_t r0[16], r1[16];
         tmem_ld16(lane_base + (uint32_t)g, r0);
         tmem_ld16(lane_base + (uint32_t)(KGP + g), r1);
         tmem_ld_wait();
         float v[16];
         float gm = -INFINITY;
+        const int nv = p.KG - g;                                // valid columns of this group (>= 16: all)
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
-          v[e] = fmaf(__uint_as_float(r1[e]), VT_LO_INV, __uint_as_float(r0[e])) + s_ba[g + e];
-          if (g + e < p.KG) gm = fmaxf(gm, v[e]);
+          v[e] = (fmaf(__uint_as_float(r1[e]), VT_LO_INV, __uint_as_float(r0[e])) + s_ba[g + e]) * LOG2E;
+          if (e >= nv) v[e] = -INFINITY;
+          gm = fmaxf(gm, v[e]);
         }
         const float nm = fmaxf(mx, gm);
         float part = 0.f;
 #pragma unroll
-        for (int e = 0; e < 16; ++e)
-          if (g + e < p.KG) part += expf(v[e] - nm);
-        sum = sum * expf(mx - nm) + part;                       // first group: sum = 0, expf(-inf) = 0
+        for (int e = 0; e < 16; ++e) part += exp2f(v[e] - nm);  // exp2f(-inf) = 0 for the padded columns
+        sum = (mx == -INFINITY ? 0.f : sum * exp2f(mx - nm)) + part;
         mx = nm;
+      }
+      s_mx[hf * 128 + row] = mx;
+      s_sm[hf * 128 + row] = sum;
+      named_bar_sync(1, 256);
+      {
+        const float m0 = s_mx[row], m1 = s_mx[128 + row], q0 = s_sm[row], q1 = s_sm[128 + row];
+        mx = fmaxf(m0, m1);
+        sum = (m0 == -INFINITY ? 0.f : q0 * exp2f(m0 - mx)) + (m1 == -INFINITY ? 0.f : q1 * exp2f(m1 - mx));
       }
       const float inv_sum = 1.0f / sum;
       VT_STAMP(2)
-      // ---- probabilities of my cluster slice -> [P_hi | P_lo] rows (MN-major B operand), column sums by shuffles
-      for (int jb = 0; jb < KL; jb += 32) {
+      // ---- probabilities of my cluster slice -> [P_hi | P_lo] rows (MN-major B operand), column sums by shuffles:
+      //      32-cluster block jb = 32 * hf (+ 64 ...) is mine
+      for (int jb = 32 * hf; jb < KL; jb += 64) {
         float pr[32];
 #pragma unroll
         for (int g = 0; g < 32; g += 16) {
@@ -236,18 +255,19 @@ vlad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
             tmem_ld16(lane_base + (uint32_t)(k_lo + jb + g), r0);
             tmem_ld16(lane_base + (uint32_t)(KGP + k_lo + jb + g), r1);
             tmem_ld_wait();
+            const int nv = row_valid ? p.K - (k_lo + jb + g) : 0;          // clusters of this group that exist
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
               const int k = k_lo + jb + g + e;
-              const float v = fmaf(__uint_as_float(r1[e]), VT_LO_INV, __uint_as_float(r0[e])) + s_ba[k < 128 ? k : 0];
-              pr[g + e] = (row_valid && k < p.K) ? expf(v - mx) * inv_sum : 0.f;
+              const float v = (fmaf(__uint_as_float(r1[e]), VT_LO_INV, __uint_as_float(r0[e])) + s_ba[k & 127]) * LOG2E;
+              pr[g + e] = (e < nv) ? exp2f(v - mx) * inv_sum : 0.f;
             }
           } else {
 #pragma unroll
             for (int e = 0; e < 16; ++e) pr[g + e] = 0.f;
           }
         }
-        if (tid < p.S_pad) {
+        if (row < p.S_pad) {
 #pragma unroll
           for (int u = 0; u < 4; ++u) {                         // 8 probabilities = one 16-byte unit of hi and of lo
             if (jb + 8 * u < KL) {
@@ -256,43 +276,43 @@ vlad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
               for (int e = 0; e < 4; ++e) {
                 const float a0 = pr[8 * u + 2 * e], a1 = pr[8 * u + 2 * e + 1];
                 const __half2 h2 = __floats2half2_rn(a0, a1);
-                const float2 hf = __half22float2(h2);
-                const __half2 l2 = __floats2half2_rn((a0 - hf.x) * 2048.f, (a1 - hf.y) * 2048.f);
+                const float2 hf2 = __half22float2(h2);
+                const __half2 l2 = __floats2half2_rn((a0 - hf2.x) * 2048.f, (a1 - hf2.y) * 2048.f);
                 hh[e] = *reinterpret_cast<const uint32_t*>(&h2);
                 ll[e] = *reinterpret_cast<const uint32_t*>(&l2);
               }
               const int jh = jb + 8 * u, jl = KL + jb + 8 * u;  // column of the unit in [P_hi | P_lo]
-              const uint32_t ah = a_u + (uint32_t)((jh >> 6) * p.acb + tid * 128 + ((((jh & 63) >> 3) ^ (tid & 7)) << 4));
-              const uint32_t al = a_u + (uint32_t)((jl >> 6) * p.acb + tid * 128 + ((((jl & 63) >> 3) ^ (tid & 7)) << 4));
+              const uint32_t ah = a_u + (uint32_t)((jh >> 6) * p.acb + row * 128 + ((((jh & 63) >> 3) ^ (row & 7)) << 4));
+              const uint32_t al = a_u + (uint32_t)((jl >> 6) * p.acb + row * 128 + ((((jl & 63) >> 3) ^ (row & 7)) << 4));
               asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ah), "r"(hh[0]), "r"(hh[1]), "r"(hh[2]), "r"(hh[3]) : "memory");
               asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(al), "r"(ll[0]), "r"(ll[1]), "r"(ll[2]), "r"(ll[3]) : "memory");
             }
           }
         }
         const float cs = warp_transpose_sum(pr, lane);          // sum over this warp's 32 rows of column jb + lane
-        s_part[warp * 64 + jb + lane] = cs;
+        s_part[quad * 64 + jb + lane] = cs;
       }
       VT_STAMP(3)
       fence_proxy_async();                                      // generic-proxy writes -> visible to tcgen05.mma
       tc_fence_before();
       mbar_arrive(afull);
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 256);
       if (tid < KL) s_asum[tid] = (s_part[tid] + s_part[64 + tid]) + (s_part[128 + tid] + s_part[192 + tid]);
-      named_bar_sync(1, 128);
-      // ---- residual epilogue: thread = feature column d of both M tiles
+      named_bar_sync(1, 256);
+      // ---- residual epilogue: thread = feature column d = hf * 128 + row of M tile hf
+      const int d = hf * 128 + row;
       for (int kb = 0; kb < KL; kb += 32) {
-        float v[2][32];
+        float v[32];
         float ssq[32];
-        // the cluster centres of this block: 64 independent loads per thread, in flight BEFORE the accumulators are
-        // waited for (they are L2 hits: 72 KB shared by every CTA, more than the L1 left beside 190 KB of shared
-        // memory; loaded one by one behind the TMEM reads they cost ~100 dependent L2 round trips per item)
+        const int kbase = k_lo + kb;
+        int nk = KL - kb;                                       // clusters of this block that exist (uniform)
+        if (p.K - kbase < nk) nk = p.K - kbase;
+        if (nk > 32) nk = 32;
+        // the cluster centres of this block: 32 independent loads per thread, in flight BEFORE the accumulators are
+        // waited for (L2 hits: 72 KB shared by every CTA, more than the L1 left beside 190 KB of shared memory)
+        const float* cptr = p.centers + (size_t)kbase * VT_D + d;
 #pragma unroll
-        for (int t = 0; t < 2; ++t)
-#pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const int k = k_lo + kb + e;
-            v[t][e] = __ldg(p.centers + (size_t)(k < p.K ? k : p.K - 1) * VT_D + t * 128 + tid);
-          }
+        for (int e = 0; e < 32; ++e) v[e] = (e < nk) ? __ldg(cptr + e * VT_D) : 0.f;
         if (kb == 0) {
           VT_STAMP(4)
           mbar_wait(vfull, (uint32_t)it & 1u);
@@ -300,54 +320,55 @@ vlad_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
           VT_STAMP(5)
         }
 #pragma unroll
-        for (int e = 0; e < 32; ++e) ssq[e] = 0.f;
+        for (int g = 0; g < 32; g += 16) {
+          if (kb + g < KL) {
+            uint32_t r0[16], r1[16];
+            tmem_ld16(lane_base + VT_ACC2 + (uint32_t)(hf * 2 * KL + kb + g), r0);
+            tmem_ld16(lane_base + VT_ACC2 + (uint32_t)(hf * 2 * KL + KL + kb + g), r1);
+            tmem_ld_wait();
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-#pragma unroll
-          for (int g = 0; g < 32; g += 16) {
-            if (kb + g < KL) {
-              uint32_t r0[16], r1[16];
-              tmem_ld16(lane_base + VT_ACC2 + (uint32_t)(t * 2 * KL + kb + g), r0);
-              tmem_ld16(lane_base + VT_ACC2 + (uint32_t)(t * 2 * KL + KL + kb + g), r1);
-              tmem_ld_wait();
-#pragma unroll
-              for (int e = 0; e < 16; ++e) {
-                const int k = k_lo + kb + g + e;
-                const float acc = fmaf(__uint_as_float(r1[e]), VT_LO_INV, __uint_as_float(r0[e]));
-                const float x = (k < p.K) ? fmaf(-s_asum[kb + g + e], v[t][g + e], acc) : 0.f;     // VLAD.py:38-45
-                v[t][g + e] = x;
-                ssq[g + e] = fmaf(x, x, ssq[g + e]);
-              }
-            } else {
-#pragma unroll
-              for (int e = 0; e < 16; ++e) v[t][g + e] = 0.f;
+            for (int e = 0; e < 16; ++e) {
+              const float acc = fmaf(__uint_as_float(r1[e]), VT_LO_INV, __uint_as_float(r0[e]));
+              const float x = (g + e < nk) ? fmaf(-s_asum[kb + g + e], v[g + e], acc) : 0.f;       // VLAD.py:38-45
+              v[g + e] = x;
+              ssq[g + e] = x * x;
             }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) { v[g + e] = 0.f; ssq[g + e] = 0.f; }
           }
         }
         const float ws_ = warp_transpose_sum(ssq, lane);
         s_ss[warp * 32 + lane] = ws_;
-        named_bar_sync(1, 128);
-        if (tid < 32) s_inv[tid] = 1.0f / sqrtf(fmaxf((s_ss[tid] + s_ss[32 + tid]) + (s_ss[64 + tid] + s_ss[96 + tid]), 1e-12f));   // VLAD.py:47-48
-        named_bar_sync(1, 128);
+        named_bar_sync(1, 256);
+        if (tid < 32) {
+          float tot = 0.f;
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          const int d = t * 128 + tid;
+          for (int w8 = 0; w8 < 8; ++w8) tot += s_ss[w8 * 32 + tid];
+          s_inv[tid] = 1.0f / sqrtf(fmaxf(tot, 1e-12f));                                           // VLAD.py:47-48
+        }
+        named_bar_sync(1, 256);
+        const size_t o0 = ((size_t)b * p.K + kbase) * VT_D + d;
+        if (p.out) {
+          float* po = p.out + o0;
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (e < nk) po[e * VT_D] = v[e] * s_inv[e];
+        }
+        if (p.out_planes) {
+          __half* ph = p.out_planes + o0;
+          __half* pl = ph + (size_t)p.B * p.K * VT_D;
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
-            const int k = k_lo + kb + e;
-            if (kb + e < KL && k < p.K) {
-              const float o = v[t][e] * s_inv[e];
-              const size_t idx = ((size_t)b * p.K + k) * VT_D + d;
-              if (p.out) p.out[idx] = o;
-              if (p.out_planes) {
-                const __half hi = __float2half_rn(o);
-                p.out_planes[idx] = hi;
-                p.out_planes[(size_t)p.B * p.K * VT_D + idx] = __float2half_rn((o - __half2float(hi)) * 2048.f);
-              }
+            if (e < nk) {
+              const float o = v[e] * s_inv[e];
+              const __half hi = __float2half_rn(o);
+              ph[e * VT_D] = hi;
+              pl[e * VT_D] = __float2half_rn((o - __half2float(hi)) * 2048.f);
             }
           }
         }
-        named_bar_sync(1, 128);                                 // s_ss / s_inv are reused by the next cluster block
+        named_bar_sync(1, 256);                                 // s_ss / s_inv are reused by the next cluster block
       }
       tc_fence_before();                                        // my TMEM reads are ordered before the next item's MMAs
       VT_STAMP(6)

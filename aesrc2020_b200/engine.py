@@ -119,6 +119,8 @@ class ResNetTC:
         import os as _os
         # stages whose stride-1 layers run as one persistent chain launch (SAR_CHAIN_STAGES="" disables)
         self.chain_stages = {int(x) for x in _os.environ.get("SAR_CHAIN_STAGES", "2,3,4").split(",") if x.strip()}
+        # residual stream between identity-shortcut blocks as one fp32 plane (SAR_RAW32=0: hi/lo planes, an A/B aid)
+        self.raw32 = _os.environ.get("SAR_RAW32", "1") != "0" and _os.environ.get("SAR_TC_TMA_OUT", "1") != "0"
 
         def put(name, arr, dtype=np.float32):
             self.p[name] = torch.from_numpy(np.ascontiguousarray(arr, dtype=dtype)).to(device)
@@ -206,6 +208,7 @@ class ResNetTC:
                 flush()
                 tc.conv_launch(desc)
 
+        raw32_in = None          # the previous block's raw sum as one fp32 plane (None: cur_raw planes)
         for i, b in enumerate(pl.blocks):
             nxt = pl.blocks[i + 1] if i + 1 < len(pl.blocks) else None
             c1, c2 = b.conv1, b.conv2
@@ -218,15 +221,32 @@ class ResNetTC:
                               taps=tc.tap_table(3, 3, c1.stride, c1.pad_t, c1.pad_l, c1.wout), cout=c1.cout,
                               out_act=c1_act, act=self.bn(c2.pre_bn)), chainable=not first)
             taps2 = tc.tap_table(3, 3, 1, 1, 1, c2.wout)
+            # identity shortcut: the previous block's raw sum, as hi/lo planes or (raw32_in) one fp32 plane
             common = dict(out_hw=(c2.hout, c2.wout), taps=taps2, cout=c2.cout, short=cur_raw if b.short else None,
-                          res=None if b.short else cur_raw)
+                          res=None if (b.short or raw32_in is not None) else cur_raw,
+                          res_f32=None if b.short else raw32_in)
             if nxt is not None:
                 ns = nxt.conv1.stride == 2
-                nraw = self._buf(lane, B, c2.hout, c2.wout, c2.cout, ns, "raw")
                 nact = self._buf(lane, B, c2.hout, c2.wout, c2.cout, ns, "act")
-                emit(tc.conv_desc(c1_act, p[b.name + "/w2"], p[b.name + "/b2"], out_raw=nraw, out_act=nact,
-                                  act=self.bn(nxt.conv1.pre_bn), **common), chainable=True)
-                cur_raw, cur_act = nraw, nact
+                # The raw sum feeds the NEXT block's shortcut.  If that is an identity shortcut it is only added in
+                # conv2's epilogue: one fp32 plane, no hi/lo split.  If it is a projection (first block of the next
+                # stage) it is an MMA operand: hi/lo planes.
+                if self.raw32 and nxt.short is None and not ns:
+                    key = (lane, B, c2.hout, c2.wout, c2.cout, "raw32")
+                    if key not in self._bufs:
+                        self._bufs[key] = [tc.alloc_raw32(B, c2.hout, c2.wout, c2.cout, self.device) for _ in range(2)]
+                        self._rot[key] = 0
+                    self._rot[key] ^= 1
+                    nraw32 = self._bufs[key][self._rot[key]]
+                    emit(tc.conv_desc(c1_act, p[b.name + "/w2"], p[b.name + "/b2"], out_raw_f32=nraw32, out_act=nact,
+                                      act=self.bn(nxt.conv1.pre_bn), **common), chainable=True)
+                    cur_raw, raw32_in = None, nraw32
+                else:
+                    nraw = self._buf(lane, B, c2.hout, c2.wout, c2.cout, ns, "raw")
+                    emit(tc.conv_desc(c1_act, p[b.name + "/w2"], p[b.name + "/b2"], out_raw=nraw, out_act=nact,
+                                      act=self.bn(nxt.conv1.pre_bn), **common), chainable=True)
+                    cur_raw, raw32_in = nraw, None
+                cur_act = nact
             elif as_planes:
                 out_dense = self._buf(lane, B, c2.hout, c2.wout, c2.cout, False, "final")
                 emit(tc.conv_desc(c1_act, p[b.name + "/w2"], p[b.name + "/b2"], act=self.bn(pl.final_bn),

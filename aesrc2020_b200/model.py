@@ -19,7 +19,7 @@ from typing import Dict, List, Optional, Sequence, Union
 import numpy as np
 import torch
 
-from . import ops, weights as _weights
+from . import ops, weights as _weights, utils as _utils
 from . import losses as ls
 from . import VLAD as vd
 from .config import SARConfig
@@ -490,7 +490,10 @@ class SARModel:
                 want = torch.int32 if k in ("x_ctc_in_len", "x_ctc_out_len") else torch.float32
                 if isinstance(v, torch.Tensor):
                     src = v
-                    if v.is_cuda:
+                    if v.is_cuda and getattr(xd, "ready", None) is not None:
+                        ps["copy"].wait_event(xd.ready)      # produced on a PinnedRing worker's stream
+                        v.record_stream(ps["copy"])
+                    elif v.is_cuda:
                         # produced by kernels on the CALLER's stream (utils.data_loader / fbank_batch hand their
                         # outputs over without a host round trip): the staging copy must run after them, and the
                         # caching allocator must not recycle the tensor while the copy stream still reads it
@@ -557,19 +560,28 @@ class SARModel:
                               "(Not enough time for target transition sequence)")
         return [v.numpy().copy() for v in views[:len(self._outputs)]]
 
-    def predict_generator(self, generator, steps=None, max_queue_size=10, workers=1, use_multiprocessing=False, verbose=0):
+    def predict_generator(self, generator, steps=None, max_queue_size=10, workers=1, use_multiprocessing=False, verbose=0,
+                          prefetch: bool = False):
         """Keras `Model.predict_generator` (the forward-only twin of the `fit_generator(generator, max_queue_size=20)`
         loop the reference trains with, train.py:38-44): `generator` yields one batch per step -- an input dict /
         list as utils.data_loader builds it (utils.py:102-116), or the (inputs, targets) tuple data_generator
         yields.  Batches are pipelined PIPE_DEPTH deep, each in flight on a stream, CUDA graph and buffer set of its own:
         while step i runs, step i+1's inputs are DMA'd from pinned host memory by the copy engine, its first kernels
         fill the SMs that step i's latency-bound tail (Bi-GRU, VLAD, head) leaves idle, and step i-1's outputs are
-        read back.  Returns the outputs concatenated over steps, as predict() does."""
+        read back.  Returns the outputs concatenated over steps, as predict() does.
+        `prefetch=True` runs the generator on a worker thread like Keras does (`workers`, `max_queue_size`): a
+        utils.PinnedRing keeps max_queue_size batches staged in page-locked memory ahead of the device."""
         from collections import deque
         if self.decode_only:                      # x_data -> ctc_pred sub-model: plain per-batch predict
             outs = [self.predict(x[0] if isinstance(x, tuple) else x, batch_size=1 << 30)
                     for i, x in enumerate(generator) if steps is None or i < steps]
             return np.concatenate(outs, 0) if outs else np.zeros((0,), np.float32)
+        ring = None
+        if workers and workers >= 1 and prefetch and not isinstance(generator, _utils.PinnedRing):
+            # Keras runs the generator on a worker thread and queues max_queue_size batches; here that thread also
+            # stages host arrays into a ring of pinned buffers, so this thread only launches
+            ring = generator = _utils.PinnedRing(generator, max_queue_size=max_queue_size, keep=self.PIPE_DEPTH + 2,
+                                                 device=torch.device(self.device))
         it = iter(generator)
         pending = deque()
         chunks: List[List] = [[] for _ in self._outputs]
@@ -578,19 +590,23 @@ class SARModel:
             for i, a in enumerate(self._collect(pending.popleft())):
                 chunks[i].append(a)
         n = 0
-        while steps is None or n < steps:
-            try:
-                x = next(it)
-            except StopIteration:
-                break
-            if isinstance(x, tuple):
-                x = x[0]
-            if len(pending) >= self.PIPE_DEPTH:
+        try:
+            while steps is None or n < steps:
+                try:
+                    x = next(it)
+                except StopIteration:
+                    break
+                if isinstance(x, tuple):
+                    x = x[0]
+                if len(pending) >= self.PIPE_DEPTH:
+                    drain()
+                pending.append(self._submit(x, n % self.PIPE_DEPTH))
+                n += 1
+            while pending:
                 drain()
-            pending.append(self._submit(x, n % self.PIPE_DEPTH))
-            n += 1
-        while pending:
-            drain()
+        finally:
+            if ring is not None:
+                ring.close()
         res = [np.concatenate(c, 0) for c in chunks] if n else [np.zeros((0,), np.float32) for _ in chunks]
         return res[0] if len(res) == 1 else res
 

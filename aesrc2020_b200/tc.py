@@ -33,6 +33,7 @@ class sar_tc_conv(C.Structure):
         ("dbg", C.c_void_p),
         ("act_kind", C.c_int),
         ("nopad", C.c_int), ("ksplit", C.c_int),
+        ("res_f32", C.c_void_p), ("out_raw_f32", C.c_void_p),
     ]
 
 ACT_KIND = {"bn_relu": 0, None: 1, "none": 1, "linear": 1, "tanh": 2}
@@ -68,6 +69,12 @@ def alloc_planes(B, H, W, Cc, split, device) -> Planes:
     n = 8 if split else 2
     t = torch.zeros((n, plane_rows(B, H, W, split), Cc), device=device, dtype=torch.float16)
     return Planes(t, B, H, W, Cc, bool(split))
+
+
+def alloc_raw32(B, H, W, Cc, device) -> torch.Tensor:
+    """The residual stream of a stage as ONE fp32 plane: (B*(H+1)*(W+1), C) flat-pad rows (pad rows are never read
+    for anything that is kept)."""
+    return torch.zeros((plane_rows(B, H, W, False), Cc), device=device, dtype=torch.float32)
 
 
 def pack(x: torch.Tensor, split=False, affine=None, relu=False, out: Optional[Planes] = None) -> Planes:
@@ -148,8 +155,10 @@ def tap_table(kh: int, kw: int, stride: int, pad_t: int, pad_l: int, W_out: int)
 def conv_desc(a: Planes, w_packed: torch.Tensor, bias: torch.Tensor, *, out_hw: Tuple[int, int], taps, cout: int,
             short: Optional[Planes] = None, res: Optional[Planes] = None, out_raw: Optional[Planes] = None,
             out_act: Optional[Planes] = None, act=None, out_dense: Optional[torch.Tensor] = None, dbg=None,
-            act_kind: int = 0, nopad: bool = False, ksplit: int = 1) -> sar_tc_conv:
-    """The `sar_tc_conv` descriptor of one layer.  taps = (row_offsets, plane_bases)."""
+            act_kind: int = 0, nopad: bool = False, ksplit: int = 1, res_f32: Optional[torch.Tensor] = None,
+            out_raw_f32: Optional[torch.Tensor] = None) -> sar_tc_conv:
+    """The `sar_tc_conv` descriptor of one layer.  taps = (row_offsets, plane_bases).  res_f32 / out_raw_f32: the
+    residual stream as one fp32 (R, cout) plane (alloc_raw32) instead of hi/lo planes."""
     d = sar_tc_conv()
     d.a, d.a_rows, d.a_ch, d.a_planes = ptr(a.t), a.rows, a.C, a.nplanes
     offs, planes = taps
@@ -181,6 +190,12 @@ def conv_desc(a: Planes, w_packed: torch.Tensor, bias: torch.Tensor, *, out_hw: 
     d.dbg = ptr(dbg) if dbg is not None else None
     d.act_kind = int(act_kind)
     d.nopad, d.ksplit = (1 if nopad else 0), int(ksplit)
+    R = plane_rows(a.B, H, W, False)
+    for t_ in (res_f32, out_raw_f32):
+        if t_ is not None:
+            assert t_.dtype == torch.float32 and tuple(t_.shape) == (R, cout) and t_.is_contiguous(), (tuple(t_.shape), (R, cout))
+    d.res_f32 = ptr(res_f32) if res_f32 is not None else None
+    d.out_raw_f32 = ptr(out_raw_f32) if out_raw_f32 is not None else None
     return d
 
 

@@ -1,8 +1,9 @@
 """Mirror of the parts of the reference's utils.py that sit on the hot path's boundary:
 the input dict contract (utils.py:102-116), label padding (utils.py:57-63) and the shape
-known-answer `cal_descriptors` (utils.py:156-159).  Pickle/scp file handling and the
-shuffling generator are data preparation and stay out of scope; `synthetic_batch` provides
-the seeded synthetic inputs the benchmarks and tests use instead.
+known-answer `cal_descriptors` (utils.py:156-159), `data_loader` / `data_generator`
+(utils.py:71-154) with the per-batch work on the device, and `PinnedRing`, the background
+producer that stands in for Keras' generator queue (train.py:44 `max_queue_size=20`).
+`synthetic_batch` provides the seeded synthetic inputs the benchmarks and tests use.
 """
 from __future__ import annotations
 
@@ -164,3 +165,167 @@ def pinned_like(arrays: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
         t.copy_(torch.from_numpy(a))
         out[k] = t.numpy()          # the array keeps the tensor alive through its .base
     return out
+
+
+def data_generator(lst, ctc_enable=False, ar_enable=False, disc_enable=False, batch_size=32, data_dct=None, accent_dct=None,
+                   trans_dct=None, max_input_len=1200, max_ctc_len=72, encoder_len=100, accent_classes=8, bn=0,
+                   device="cuda", seed=None):
+    """utils.py:120-154: endless generator of (inputs, targets) batches -- shuffle `lst`, cut it into len(lst) // batch_size
+    batches, data_loader() each, start over.  Batches are assembled on the device (data_loader above); `seed` makes the
+    shuffles reproducible (the reference uses the global `random.shuffle`)."""
+    import random
+    rnd = random.Random(seed) if seed is not None else random
+    lst = list(lst)
+    n_batchs = len(lst) // batch_size
+    if n_batchs < 1:
+        raise ValueError("data_generator: %d utterances do not fill one batch of %d" % (len(lst), batch_size))
+    while True:
+        rnd.shuffle(lst)
+        for i in range(n_batchs):
+            sub = lst[i * batch_size:(i + 1) * batch_size]
+            yield data_loader(sub, ctc_enable=ctc_enable, ar_enable=ar_enable, disc_enable=disc_enable, data_dct=data_dct,
+                              accent_dct=accent_dct, trans_dct=trans_dct, max_input_len=max_input_len,
+                              max_ctc_len=max_ctc_len, encoder_len=encoder_len, accent_classes=accent_classes, bn=bn,
+                              device=device)
+
+
+class RingBatch(dict):
+    """An input dict handed out by PinnedRing: `ready` is a CUDA event recorded after the producer thread's device work
+    for this batch (None for host batches); consumers order their stream behind it."""
+    ready = None
+
+
+class PinnedRing:
+    """Background batch producer: the twin of Keras' GeneratorEnqueuer behind `fit_generator(generator,
+    max_queue_size=20)` (train.py:38-44), which the reference relies on to keep the GPU fed.
+
+    A worker thread drains `generator` (anything yielding an input dict or an (inputs, targets) tuple) and keeps up to
+    `max_queue_size` batches ready:
+      * host (numpy) arrays are staged into a RING of page-locked buffers -- allocated once per slot, key and shape, then
+        reused -- so that model.predict / predict_generator DMA them to the device in place (no per-batch pinning, no
+        staging memcpy on the consumer's thread); arrays that already live in pinned memory pass through untouched;
+      * CUDA tensors (utils.data_loader assembles batches on the device) pass through; the worker runs the generator
+        under a stream of its own and records an event per batch (RingBatch.ready) that the consumer waits on.
+    Slot lifetime: a handed-out batch stays valid until `keep` further batches have been taken (predict_generator has
+    finished the H2D of batch i before it asks for batch i + PIPE_DEPTH + 1)."""
+
+    _END = object()
+
+    def __init__(self, generator, max_queue_size: int = 20, keep: int = 8, device=None):
+        import queue
+        import threading
+        self.gen = iter(generator)
+        self.mq = max(1, int(max_queue_size))
+        self.keep = max(1, int(keep))
+        self.nslots = self.mq + self.keep
+        self.slots = [dict() for _ in range(self.nslots)]
+        self.q = queue.Queue(maxsize=self.mq)
+        self.cv = threading.Condition()
+        self.handed = 0
+        self.stop = False
+        self.error = None
+        self.device = device
+        self.staged_bytes = 0
+        self.thread = threading.Thread(target=self._run, name="sarnet-pinned-ring", daemon=True)
+        self.thread.start()
+
+    # ---- producer thread
+    def _stage(self, slot, k, v):
+        import torch
+        if isinstance(v, torch.Tensor):
+            return v
+        a = np.ascontiguousarray(v)
+        if a.dtype == np.float64:
+            a = a.astype(np.float32)
+        t = torch.from_numpy(a)
+        if t.is_pinned():
+            return a
+        pin = slot.get(k)
+        if pin is None or pin.shape != t.shape or pin.dtype != t.dtype:
+            pin = slot[k] = torch.empty(t.shape, dtype=t.dtype, pin_memory=torch.cuda.is_available())
+        pin.copy_(t)
+        self.staged_bytes += a.nbytes
+        return pin.numpy()
+
+    def _run(self):
+        import contextlib
+        import torch
+        i = 0
+        try:
+            ctx = contextlib.nullcontext()
+            stream = None
+            if torch.cuda.is_available():
+                dev = torch.device(self.device) if self.device is not None else None
+                if dev is not None and dev.type == "cuda" and dev.index is not None:
+                    torch.cuda.set_device(dev)
+                stream = torch.cuda.Stream()
+                ctx = torch.cuda.stream(stream)
+            with ctx:
+                for item in self.gen:
+                    with self.cv:                 # slot i % nslots: its previous batch must be `keep` hand-outs old
+                        while not self.stop and self.handed < i - self.mq + 1:
+                            self.cv.wait(0.05)
+                        if self.stop:
+                            return
+                    inputs, targets = (item if isinstance(item, tuple) else (item, None))
+                    slot = self.slots[i % self.nslots]
+                    out = RingBatch((k, self._stage(slot, k, v)) for k, v in inputs.items())
+                    if stream is not None and any(isinstance(v, torch.Tensor) and v.is_cuda for v in out.values()):
+                        out.ready = torch.cuda.Event()
+                        out.ready.record(stream)
+                    while not self.stop:
+                        try:
+                            self.q.put((out, targets), timeout=0.05)
+                            break
+                        except Exception:
+                            continue
+                    if self.stop:
+                        return
+                    i += 1
+        except BaseException as e:                # surfaced on the consumer's thread by __next__
+            self.error = e
+        finally:
+            while not self.stop:
+                try:
+                    self.q.put(self._END, timeout=0.05)
+                    break
+                except Exception:
+                    continue
+
+    # ---- consumer
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        import queue
+        while True:                               # never block forever on a producer that died
+            try:
+                item = self.q.get(timeout=0.2)
+                break
+            except queue.Empty:
+                if not self.thread.is_alive() and self.q.empty():
+                    if self.error is not None:
+                        raise self.error
+                    raise StopIteration
+        if item is self._END:
+            self.q.put(self._END)
+            if self.error is not None:
+                raise self.error
+            raise StopIteration
+        with self.cv:
+            self.handed += 1
+            self.cv.notify_all()
+        out, targets = item
+        return out if targets is None else (out, targets)
+
+    def close(self):
+        self.stop = True
+        with self.cv:
+            self.cv.notify_all()
+        self.thread.join(timeout=2.0)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()

@@ -127,12 +127,17 @@ typedef struct sar_tc_conv {
   float* out_dense;
   int out_split;
   int B, H, W;          /* output map geometry */
-  void* dbg;            /* optional device buffer of >= 64 int64 clock64() stamps of CTA 0 (profiling aid); NULL */
+  void* dbg;            /* optional device buffer of >= 256 int64 clock64() stamps of CTA 0 (profiling aid); NULL */
   int act_kind;         /* out_act / out_dense activation: 0 relu(act_scale*v+act_shift) (the next layer's BN->ReLU),
                            1 identity, 2 tanh(v) -- the Dense layers of model.py:35-42 run as 1-tap "convolutions" */
   int nopad;            /* 1: the operand / output rows are plain row-major (B*H*W rows, no pad row or column): GEMM use */
   int ksplit;           /* > 1: split-K for a 1-tap GEMM with a long K (a_ch): K slice z writes its fp32 partial products to
                            out_dense + z*B*H*W*cout (identity activation, zero bias); sum them with sar_splitk_reduce_fwd */
+  const float* res_f32; /* the identity shortcut as ONE fp32 plane [R][cout] (flat-pad rows) instead of `res` hi/lo planes */
+  float* out_raw_f32;   /* the raw sum as one fp32 plane [R][cout] instead of `out_raw`: the residual stream between the
+                           blocks of a stage is only ever ADDED in an epilogue (resnet.py:123,89), never an MMA operand, so
+                           it needs no hi/lo split; pad rows are left unwritten (their sums are discarded downstream).
+                           Needs unsplit outputs (the TMA-store epilogue). */
 } sar_tc_conv;
 int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream);
 

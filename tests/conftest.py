@@ -20,3 +20,11 @@ def cuda_device():
     from aesrc2020_b200 import _shim
     _shim.lib()
     return torch.device("cuda:0")
+
+
+def pytest_collection_modifyitems(config, items):
+    """A protocol bug in a kernel can hang a GPU test: every GPU test gets a wall-clock limit (pytest-timeout, thread
+    method: the process is killed, which also ends a hung CUDA call)."""
+    for it in items:
+        if "gpu" in it.keywords and not any(m.name == "timeout" for m in it.iter_markers()):
+            it.add_marker(pytest.mark.timeout(240, method="thread"))

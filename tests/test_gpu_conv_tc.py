@@ -271,3 +271,52 @@ def test_vlad_tc_unsupported_shapes_are_refused(cuda_device):
     with pytest.raises(_shim.SarnetError):
         tc.vlad_tc(xp, torch.zeros(2, 80, 256, dtype=torch.float16, device="cuda"), torch.zeros(72, device="cuda"),
                    torch.zeros(72, 256, device="cuda"), 4, 200, 64, 8)
+
+
+@pytest.mark.parametrize("B,H,W,C,res_in,split_out", [(2, 11, 10, 64, True, False), (3, 25, 20, 32, True, False),
+                                                       (2, 6, 3, 256, True, False), (2, 7, 5, 128, False, False),
+                                                       (48, 125, 20, 32, True, False), (2, 13, 10, 64, True, True)])
+def test_residual_stream_as_one_fp32_plane(cuda_device, B, H, W, C, res_in, split_out):
+    """res_f32 / out_raw_f32 (sar_tc_conv): the identity shortcut read from, and the raw sum written to, ONE fp32 plane of
+    flat-pad rows instead of hi/lo planes -- same values as the planes form (the stream is only added, never an MMA
+    operand).  Covers the compile-time epilogue modes (res + raw + act), the generic one (raw32 in, split planes out: a
+    stage-ending conv2) and a many-tile persistent launch."""
+    from aesrc2020_b200 import tc
+    rng = np.random.RandomState(H * 31 + C)
+    x = _f32(rng.randn(B, H, W, C))
+    w = _f32(rng.randn(3, 3, C, C) * np.sqrt(2.0 / (9 * C)))
+    b = _f32(rng.randn(C) * 0.1)
+    r = _f32(rng.randn(B, H, W, C))
+    qs, qt = _f32(rng.rand(C) + 0.5), _f32(rng.randn(C) * 0.3)
+    want = O.conv2d(t64(x), t64(w), t64(b), 1, "same") + (t64(r) if res_in else 0)
+    want_act = torch.relu(want * t64(qs) + t64(qt))
+    a = tc.pack(dev(x))
+    wp = torch.from_numpy(tc.pack_weights(w)).cuda()
+    P, Rimg = W + 1, (H + 1) * (W + 1)
+    res32 = None
+    if res_in:                                           # flat-pad fp32 plane of the shortcut (pads: arbitrary values)
+        res32 = torch.full((B * Rimg, C), 7.5, device="cuda")
+        res32.view(B, H + 1, W + 1, C)[:, :H, :W] = dev(r)
+    out_act = tc.alloc_planes(B, H, W, C, split_out, "cuda")
+    kw = dict(out_hw=(H, W), taps=tc.tap_table(3, 3, 1, 1, 1, W), cout=C, out_act=out_act, act=(dev(qs), dev(qt)), res_f32=res32)
+    if res_in and not split_out and B == 2:              # the mirror mix: hi/lo PLANES shortcut in, fp32 raw sum out
+        raw32b = torch.full((B * Rimg, C), -3.0, device="cuda")
+        kwb = dict(kw, res_f32=None, res=tc.pack(dev(r)), out_act=tc.alloc_planes(B, H, W, C, False, "cuda"))
+        tc.conv_tc(a, wp, dev(b), out_raw_f32=raw32b, **kwb)
+        assert norm_err(raw32b.view(B, H + 1, W + 1, C)[:, :H, :W], want) < 1e-5
+        assert norm_err(tc.unpack(kwb["out_act"]), want_act) < 1e-5
+    if split_out:                                        # stage-ending conv2: fp32 shortcut in, phase-split planes out
+        out_raw = tc.alloc_planes(B, H, W, C, True, "cuda")
+        tc.conv_tc(a, wp, dev(b), out_raw=out_raw, **kw)
+        got_raw = tc.unpack(out_raw)
+    else:
+        raw32 = torch.full((B * Rimg, C), -3.0, device="cuda")
+        tc.conv_tc(a, wp, dev(b), out_raw_f32=raw32, **kw)
+        got_raw = raw32.view(B, H + 1, W + 1, C)[:, :H, :W]
+    torch.cuda.synchronize()
+    assert norm_err(got_raw, want) < 1e-5
+    assert norm_err(tc.unpack(out_act), want_act) < 1e-5
+    if not split_out:
+        q = torch.arange(out_act.rows, device="cuda")
+        pad = ((q % Rimg) // P == H) | (q % P == W)
+        assert float(out_act.t[:, pad].float().abs().max()) == 0.0          # activated planes: pads stay zero
