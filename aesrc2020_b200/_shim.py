@@ -37,6 +37,7 @@ SIGNATURES = {
     "sar_conv_tc_fwd": (c_int, [C.c_void_p, C.c_void_p]),
     "sar_conv_tc_chain_workspace_bytes": (c_sz, [C.c_void_p, c_int]),
     "sar_conv_tc_chain_fwd": (c_int, [C.c_void_p, c_int, C.c_void_p, c_sz, C.c_void_p]),
+    "sar_conv_tc_chain_grid_fwd": (c_int, [C.c_void_p, c_int, C.c_void_p, c_sz, c_int, C.c_void_p]),
     "sar_stem_pool_fwd": (c_int, [c_fp] * 6 + [c_int] * 4 + [C.c_void_p]),
     "sar_maxpool2d_fwd": (c_int, [c_fp, c_fp] + [c_int] * 10 + [C.c_void_p]),
     "sar_affine_relu_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_ll, c_int, c_int, C.c_void_p]),
@@ -62,6 +63,17 @@ SIGNATURES = {
     "sar_ctc_greedy_fwd": (c_int, [c_fp, c_int, c_ip, c_int, c_ip, c_ip, c_int, c_int, c_int, C.c_void_p]),
     "sar_ctc_ld_fwd": (c_int, [c_fp, c_int, c_fp, c_ip, c_ip, c_fp, c_fp, c_ip, c_int, c_int, c_int, c_int, C.c_void_p]),
     "sar_loss_reduce_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, C.c_void_p]),
+    "sar_gemm_fwd": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_f, c_f, C.c_void_p]),
+    "sar_bn_train_fwd": (c_int, [c_fp] * 8 + [c_int, c_int, c_f, c_f, C.c_void_p]),
+    "sar_bn_train_bwd": (c_int, [c_fp] * 8 + [c_int, c_int, C.c_void_p]),
+    "sar_bias_act_fwd": (c_int, [c_fp, c_fp, c_fp, c_ll, c_int, c_int, C.c_void_p]),
+    "sar_relu_bwd": (c_int, [c_fp, c_fp, c_fp, c_ll, C.c_void_p]),
+    "sar_colsum_fwd": (c_int, [c_fp, c_fp, c_int, c_int, C.c_void_p]),
+    "sar_l2norm_fwd": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_int, C.c_void_p]),
+    "sar_l2norm_bwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_f, C.c_void_p]),
+    "sar_head_grad_fwd": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_f, c_f, c_f, c_f, c_f, c_fp, c_fp, c_fp, c_int, C.c_void_p]),
+    "sar_adam_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_ll, c_f, c_f, c_f, c_f, c_f, C.c_void_p]),
+    "sar_unit_norm_fwd": (c_int, [c_fp, c_int, c_int, C.c_void_p]),
     "sar_fbank_fwd": (c_int, [c_fp, c_ip, c_fp, c_fp, c_fp, c_int, c_int, c_int, C.c_void_p]),
     "sar_fbank_pcm16_fwd": (c_int, [c_ip, c_ip, c_fp, c_fp, c_fp, c_int, c_int, c_int, C.c_void_p]),
 }

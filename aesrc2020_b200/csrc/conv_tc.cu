@@ -1391,6 +1391,11 @@ extern "C" size_t sar_conv_tc_chain_workspace_bytes(const sar_tc_conv* first, in
 }
 
 extern "C" int sar_conv_tc_chain_fwd(const sar_tc_conv* descs, int n, void* workspace, size_t workspace_bytes, void* stream) {
+  return sar_conv_tc_chain_grid_fwd(descs, n, workspace, workspace_bytes, 0, stream);
+}
+
+extern "C" int sar_conv_tc_chain_grid_fwd(const sar_tc_conv* descs, int n, void* workspace, size_t workspace_bytes, int max_ctas,
+                                          void* stream) {
   using namespace sar;
   SAR_REQUIRE(descs && n >= 1 && n <= CH_MAX, SAR_ERR_BAD_ARG, "sar_conv_tc_chain_fwd: need 1..%d layers", CH_MAX);
   SAR_REQUIRE(workspace && workspace_bytes >= sar_conv_tc_chain_workspace_bytes(descs, n), SAR_ERR_WORKSPACE,
@@ -1475,7 +1480,8 @@ extern "C" int sar_conv_tc_chain_fwd(const sar_tc_conv* descs, int n, void* work
     if ((rc = fill_out_maps(d, p, P.mapA, P.om))) return rc;
   }
   const int tiles = g0.m_tiles * (cout / BN);
-  const int grid = tiles < sms ? tiles : sms;
+  int grid = tiles < sms ? tiles : sms;
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;          // leave SMs to a chain of another stream (cooperative launches)
   const size_t smem = fixed + (size_t)sp.nslab * slab1 + (size_t)sp.nring * 2 * sp.bplane_bytes;
   auto launch = [&](auto kern) -> int {
     { const int arc = allow_max_smem(kern, "sar_conv_tc_chain_fwd"); if (arc) return arc; }

@@ -34,7 +34,7 @@ __device__ __forceinline__ float fb_sample(const short* y, long long j) { return
 // built once: the 128 + 257 twiddles (sincospif, once per CTA instead of once per butterfly) and a COMPACT copy of the
 // mel filterbank -- the triangles overlap only their neighbours, so a filter touches ~6 of the 257 bins (at most
 // FB_MAXW); the dense (257 x 80) projection the first version read from L2 for every frame was 40x the work.
-constexpr int FB_FPC = 16;           // frames per CTA
+constexpr int FB_FPC = 32;           // frames per CTA
 constexpr int FB_MAXNZ = 1024;       // non-zero filterbank weights (2 * 257 for triangular filters; 1024 = any sane bank)
 
 template <typename SampleT>
@@ -60,12 +60,20 @@ __global__ void __launch_bounds__(256) fbank_frame_kernel(const SampleT* __restr
     sincospif(-(float)k / 256.0f, &sn, &cs);
     pt[k] = make_float2(cs, sn);
   }
-  if (t < FB_NFILT) {                           // support of filter t: first / last non-zero bin
-    int lo = FB_NBIN, hi = -1;
-    for (int k = 0; k < FB_NBIN; ++k)
-      if (__ldg(melfb_t + k * FB_NFILT + t) != 0.f) { if (k < lo) lo = k; hi = k; }
-    m_lo[t] = hi >= 0 ? lo : 0;
-    m_len[t] = hi >= 0 ? hi - lo + 1 : 0;
+  // support of every filter (first / last non-zero bin): the whole CTA scans the (257 x 80) matrix once, coalesced
+  __shared__ int s_lo[FB_NFILT], s_hi[FB_NFILT];
+  if (t < FB_NFILT) { s_lo[t] = FB_NBIN; s_hi[t] = -1; }
+  __syncthreads();
+  for (int i = t; i < FB_NBIN * FB_NFILT; i += 256)
+    if (__ldg(melfb_t + i) != 0.f) {
+      const int k = i / FB_NFILT, j = i - k * FB_NFILT;
+      atomicMin(&s_lo[j], k);
+      atomicMax(&s_hi[j], k);
+    }
+  __syncthreads();
+  if (t < FB_NFILT) {
+    m_lo[t] = s_hi[t] >= 0 ? s_lo[t] : 0;
+    m_len[t] = s_hi[t] >= 0 ? s_hi[t] - s_lo[t] + 1 : 0;
   }
   __syncthreads();
   if (t == 0) {
@@ -138,33 +146,43 @@ __global__ void __launch_bounds__(256) fbank_frame_kernel(const SampleT* __restr
   }
 }
 
-__global__ void __launch_bounds__(320) fbank_norm_kernel(const float* __restrict__ feat, const long long* __restrict__ offsets,
-                                                          float* __restrict__ x_data, int Fmax, int T) {
+// One CTA per utterance, 1000 threads = 50 frame phases x 20 float4 column groups: per-bin min / max over ALL frames of
+// the utterance (before truncation, as the reference does), then scale to [0,1] and write (T,80) zero padded.
+constexpr int FBN_PH = 50, FBN_C4 = FB_NFILT / 4, FBN_THREADS = FBN_PH * FBN_C4;
+__global__ void __launch_bounds__(FBN_THREADS) fbank_norm_kernel(const float* __restrict__ feat, const long long* __restrict__ offsets,
+                                                                  float* __restrict__ x_data, int Fmax, int T) {
   pdl_wait();
   pdl_trigger();
-  __shared__ float smin[4][FB_NFILT], smax[4][FB_NFILT];
-  const int b = blockIdx.x, m = threadIdx.x % FB_NFILT, q = threadIdx.x / FB_NFILT;   // 4 frame-phases
+  __shared__ float4 smin[FBN_PH][FBN_C4], smax[FBN_PH][FBN_C4];
+  const int b = blockIdx.x, c4 = threadIdx.x % FBN_C4, q = threadIdx.x / FBN_C4;
   const long long n = offsets[b + 1] - offsets[b];
   const int nf = n > 0 ? min(fb_num_frames(n), Fmax) : 0;
-  const float* fr = feat + (size_t)b * Fmax * FB_NFILT;
-  float mn = INFINITY, mx = -INFINITY;
-  for (int f = q; f < nf; f += 4) {
-    float v = fr[(size_t)f * FB_NFILT + m];
-    mn = fminf(mn, v); mx = fmaxf(mx, v);
+  const float4* fr = reinterpret_cast<const float4*>(feat + (size_t)b * Fmax * FB_NFILT);
+  float4 mn = make_float4(INFINITY, INFINITY, INFINITY, INFINITY), mx = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  for (int f = q; f < nf; f += FBN_PH) {
+    const float4 v = fr[(size_t)f * FBN_C4 + c4];
+    mn.x = fminf(mn.x, v.x); mn.y = fminf(mn.y, v.y); mn.z = fminf(mn.z, v.z); mn.w = fminf(mn.w, v.w);
+    mx.x = fmaxf(mx.x, v.x); mx.y = fmaxf(mx.y, v.y); mx.z = fmaxf(mx.z, v.z); mx.w = fmaxf(mx.w, v.w);
   }
-  smin[q][m] = mn; smax[q][m] = mx;
+  smin[q][c4] = mn; smax[q][c4] = mx;
   __syncthreads();
-  mn = fminf(fminf(smin[0][m], smin[1][m]), fminf(smin[2][m], smin[3][m]));
-  mx = fmaxf(fmaxf(smax[0][m], smax[1][m]), fmaxf(smax[2][m], smax[3][m]));
-  float rng = mx - mn;
-  if (!(rng > 0.f)) rng = 1.f;                 // sklearn: zero range -> scale 1 -> column of zeros
-  const float scale = 1.f / rng;
-  const float off = -mn * scale;
-  float* xo = x_data + (size_t)b * T * FB_NFILT;
-  for (int f = q; f < T; f += 4) {
-    float v = 0.f;
-    if (f < nf) v = fmaf(fr[(size_t)f * FB_NFILT + m], scale, off);
-    xo[(size_t)f * FB_NFILT + m] = v;
+  for (int i = 0; i < FBN_PH; ++i) {
+    const float4 a = smin[i][c4], c = smax[i][c4];
+    mn.x = fminf(mn.x, a.x); mn.y = fminf(mn.y, a.y); mn.z = fminf(mn.z, a.z); mn.w = fminf(mn.w, a.w);
+    mx.x = fmaxf(mx.x, c.x); mx.y = fmaxf(mx.y, c.y); mx.z = fmaxf(mx.z, c.z); mx.w = fmaxf(mx.w, c.w);
+  }
+  // sklearn MinMaxScaler: zero range -> scale 1 -> column of zeros
+  auto sc = [](float lo, float hi) { const float r = hi - lo; return 1.f / ((r > 0.f) ? r : 1.f); };
+  const float4 scale = make_float4(sc(mn.x, mx.x), sc(mn.y, mx.y), sc(mn.z, mx.z), sc(mn.w, mx.w));
+  const float4 off = make_float4(-mn.x * scale.x, -mn.y * scale.y, -mn.z * scale.z, -mn.w * scale.w);
+  float4* xo = reinterpret_cast<float4*>(x_data + (size_t)b * T * FB_NFILT);
+  for (int f = q; f < T; f += FBN_PH) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (f < nf) {
+      const float4 w = fr[(size_t)f * FBN_C4 + c4];
+      v = make_float4(fmaf(w.x, scale.x, off.x), fmaf(w.y, scale.y, off.y), fmaf(w.z, scale.z, off.z), fmaf(w.w, scale.w, off.w));
+    }
+    xo[(size_t)f * FBN_C4 + c4] = v;
   }
 }
 
@@ -177,11 +195,12 @@ static int fbank_launch(const SampleT* wav, const long long* offsets, const floa
   SAR_REQUIRE(wav && offsets && melfb_t && feat_ws && x_data, SAR_ERR_BAD_ARG, "sar_fbank_fwd: null pointer");
   SAR_REQUIRE(B > 0 && Fmax > 0 && T > 0, SAR_ERR_BAD_ARG, "sar_fbank_fwd: non-positive dimension");
   SAR_REQUIRE(B <= 65535, SAR_ERR_UNSUPPORTED, "sar_fbank_fwd: B > 65535");
+  SAR_REQUIRE(aligned16(feat_ws) && aligned16(x_data), SAR_ERR_ALIGN, "sar_fbank_fwd: feat_ws / x_data must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   launch_k(fbank_frame_kernel<SampleT>, dim3(dim3((Fmax + FB_FPC - 1) / FB_FPC, B)), dim3(256), 0, st, wav, offsets, melfb_t, feat_ws, Fmax);
   int rc = check_launch("sar_fbank_fwd(frames)");
   if (rc) return rc;
-  launch_k(fbank_norm_kernel, dim3(B), dim3(4 * FB_NFILT), 0, st, feat_ws, offsets, x_data, Fmax, T);
+  launch_k(fbank_norm_kernel, dim3(B), dim3(FBN_THREADS), 0, st, feat_ws, offsets, x_data, Fmax, T);
   return check_launch("sar_fbank_fwd(norm)");
 }
 }  // namespace sar

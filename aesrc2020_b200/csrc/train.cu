@@ -1,0 +1,376 @@
+// train.cu -- first slice of TRAINING mode: the building blocks of one optimisation step of the accent
+// head (model.py:286-296, 142-167 in training mode; compile(), model.py:187-201: Adam(lr, decay=2e-4)).
+//
+//   sar_gemm_fwd          C = alpha * op(A) op(B) + beta * C    the Dense forward / backward contractions (x W, g W^T, x^T g)
+//   sar_bn_train_fwd/bwd  BatchNormalization in training mode: batch statistics per replica (what multi_gpu_model does),
+//                         eps 1e-3, moving averages with momentum 0.99; and its backward
+//   sar_bias_act_fwd      y = act(x + b)                        Dense epilogue (relu / none)
+//   sar_relu_bwd          g * (h > 0)
+//   sar_l2norm_fwd/bwd    K.l2_normalize along rows or columns and its backward (Face heads, Circle-Loss head)
+//   sar_head_grad_fwd     softmax + categorical cross-entropy of y_accent and the margin head (SphereFace / CosFace /
+//                         ArcFace / Dense softmax / Circle-Loss): per-sample losses and d loss / d logits, d loss / d cos
+//   sar_adam_fwd          Keras Adam update (+ l2 regulariser gradient, + unit_norm constraint helper)
+//
+// All fp32, CUDA cores, deterministic reduction orders.  This slice is about CORRECT training arithmetic behind the
+// C ABI (checked against float64 autograd, tests/test_gpu_train.py), not yet about speed: the contractions of the head are
+// <= 0.3 GFLOP per step.
+#include "common.cuh"
+
+namespace sar {
+
+// ------------------------------------------------------------------ small fp32 GEMM, row-major, optional transposes
+constexpr int TG = 64, TGK = 16;
+__global__ void __launch_bounds__(256) gemm_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
+                                                    int M, int N, int K, int ta, int tb, float alpha, float beta) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ float As[TGK][TG + 4], Bs[TGK][TG + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * TG, n0 = blockIdx.x * TG;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += TGK) {
+    for (int i = threadIdx.x; i < TG * TGK; i += 256) {
+      // A tile: element (m, k) = ta ? A[k][m] : A[m][k]; index so that consecutive threads read consecutive addresses
+      int m, k;
+      if (ta) { m = i % TG; k = i / TG; } else { k = i % TGK; m = i / TGK; }
+      const int gm = m0 + m, gk = k0 + k;
+      As[k][m] = (gm < M && gk < K) ? (ta ? A[(size_t)gk * M + gm] : A[(size_t)gm * K + gk]) : 0.f;
+      int n, kb;
+      if (tb) { kb = i % TGK; n = i / TGK; } else { n = i % TG; kb = i / TG; }
+      const int gn = n0 + n, gkb = k0 + kb;
+      Bs[kb][n] = (gn < N && gkb < K) ? (tb ? B[(size_t)gn * K + gkb] : B[(size_t)gkb * N + gn]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < TGK; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[k][ty * 4 + i]; b[i] = Bs[k][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gm = m0 + ty * 4 + i, gn = n0 + tx * 4 + j;
+      if (gm < M && gn < N) {
+        float* c = C + (size_t)gm * N + gn;
+        *c = alpha * acc[i][j] + (beta != 0.f ? beta * *c : 0.f);
+      }
+    }
+}
+
+// ------------------------------------------------------------------ BatchNormalization, training mode, (rows, C)
+// one thread per channel, rows walked in a fixed order (coalesced across channels)
+__global__ void bn_train_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    float* __restrict__ mov_mean, float* __restrict__ mov_var, float* __restrict__ y,
+                                    float* __restrict__ save_mean, float* __restrict__ save_invstd, int rows, int C, float eps,
+                                    float momentum) {
+  pdl_wait();
+  pdl_trigger();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int r = 0; r < rows; ++r) s += x[(size_t)r * C + c];
+  const float mean = s / rows;
+  float q = 0.f;
+  for (int r = 0; r < rows; ++r) { const float d = x[(size_t)r * C + c] - mean; q = fmaf(d, d, q); }
+  const float var = q / rows;                                   // biased (Keras' non-fused path, also for the moving average)
+  const float inv = 1.0f / sqrtf(var + eps);
+  const float g = gamma[c], b = beta[c];
+  for (int r = 0; r < rows; ++r) y[(size_t)r * C + c] = (x[(size_t)r * C + c] - mean) * inv * g + b;
+  save_mean[c] = mean; save_invstd[c] = inv;
+  if (mov_mean) mov_mean[c] = momentum * mov_mean[c] + (1.f - momentum) * mean;
+  if (mov_var) mov_var[c] = momentum * mov_var[c] + (1.f - momentum) * var;
+}
+__global__ void bn_train_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ gamma,
+                                    const float* __restrict__ save_mean, const float* __restrict__ save_invstd,
+                                    float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int C) {
+  pdl_wait();
+  pdl_trigger();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float mean = save_mean[c], inv = save_invstd[c], g = gamma[c];
+  float sb = 0.f, sg = 0.f;
+  for (int r = 0; r < rows; ++r) {
+    const float d = dy[(size_t)r * C + c];
+    sb += d;
+    sg = fmaf(d, (x[(size_t)r * C + c] - mean) * inv, sg);
+  }
+  dbeta[c] = sb; dgamma[c] = sg;
+  if (dx) {
+    const float ib = sb / rows, ig = sg / rows;
+    for (int r = 0; r < rows; ++r) {
+      const float xh = (x[(size_t)r * C + c] - mean) * inv;
+      dx[(size_t)r * C + c] = g * inv * (dy[(size_t)r * C + c] - ib - xh * ig);
+    }
+  }
+}
+
+__global__ void bias_act_kernel(const float* __restrict__ x, const float* __restrict__ b, float* __restrict__ y, long long n, int C, int relu) {
+  pdl_wait();
+  pdl_trigger();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = x[i] + (b ? b[i % C] : 0.f);
+    y[i] = relu ? fmaxf(v, 0.f) : v;
+  }
+}
+__global__ void relu_bwd_kernel(const float* __restrict__ g, const float* __restrict__ h, float* __restrict__ out, long long n) {
+  pdl_wait();
+  pdl_trigger();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = h[i] > 0.f ? g[i] : 0.f;
+}
+// column sums of g (rows, C): the bias gradients
+__global__ void colsum_kernel(const float* __restrict__ g, float* __restrict__ out, int rows, int C) {
+  pdl_wait();
+  pdl_trigger();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int r = 0; r < rows; ++r) s += g[(size_t)r * C + c];
+  out[c] = s;
+}
+
+// ------------------------------------------------------------------ K.l2_normalize (eps 1e-12 under the root) and backward
+// axis 1: every row of v (rows, D); axis 0: every column.  One thread per vector, fixed order.
+__global__ void l2norm_fwd_kernel(const float* __restrict__ v, float* __restrict__ out, float* __restrict__ inv_out, int rows, int D, int axis) {
+  pdl_wait();
+  pdl_trigger();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nvec = axis ? rows : D, len = axis ? D : rows;
+  if (i >= nvec) return;
+  const size_t base = axis ? (size_t)i * D : (size_t)i, stride = axis ? 1 : (size_t)D;
+  float q = 0.f;
+  for (int j = 0; j < len; ++j) { const float a = v[base + j * stride]; q = fmaf(a, a, q); }
+  const float inv = 1.0f / sqrtf(fmaxf(q, 1e-12f));
+  for (int j = 0; j < len; ++j) out[base + j * stride] = v[base + j * stride] * inv;
+  inv_out[i] = inv;
+}
+// d loss / d v = (u - vhat (vhat . u)) * inv      (u = d loss / d vhat)
+__global__ void l2norm_bwd_kernel(const float* __restrict__ vhat, const float* __restrict__ inv, const float* __restrict__ u,
+                                  float* __restrict__ out, int rows, int D, int axis, float beta) {
+  pdl_wait();
+  pdl_trigger();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nvec = axis ? rows : D, len = axis ? D : rows;
+  if (i >= nvec) return;
+  const size_t base = axis ? (size_t)i * D : (size_t)i, stride = axis ? 1 : (size_t)D;
+  float dot = 0.f;
+  for (int j = 0; j < len; ++j) dot = fmaf(vhat[base + j * stride], u[base + j * stride], dot);
+  const float s = inv[i];
+  for (int j = 0; j < len; ++j) {
+    const size_t o = base + j * stride;
+    const float g = (u[o] - vhat[o] * dot) * s;
+    out[o] = beta != 0.f ? beta * out[o] + g : g;
+  }
+}
+
+// ------------------------------------------------------------------ losses and their gradients w.r.t. logits / cosines
+// One thread per utterance (n <= 32 classes).  head: sar head selector (SAR_HEAD_*).
+//   g_acc (B,n) = w_acc / B * d CE(softmax(z_acc)) / d z_acc
+//   g_disc (B,n) = w_disc / B * d loss_disc / d (cos for the Face / Circle heads, logits for the softmax head)
+//   losses (B,2) per-sample [CE_accent, loss_disc]
+// Keras' categorical_crossentropy clips p to [1e-7, 1 - 1e-7]: outside that range the gradient is zero.
+constexpr float TK_EPS = 1e-7f;
+__global__ void head_grad_kernel(const float* __restrict__ z_acc, const float* __restrict__ c_disc, const float* __restrict__ onehot,
+                                 int n, int head, float margin, float s, float gamma, float w_acc, float w_disc,
+                                 float* __restrict__ g_acc, float* __restrict__ g_disc, float* __restrict__ losses, int B) {
+  pdl_wait();
+  pdl_trigger();
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float* y = onehot + (size_t)b * n;
+  int lab = 0;
+  for (int j = 1; j < n; ++j) if (y[j] > y[lab]) lab = j;
+  float z[32], p[32];
+  auto softmax_ce = [&](float* zz, float& loss, bool& clipped) {      // p <- softmax(zz)
+    float m = -INFINITY;
+    for (int j = 0; j < n; ++j) m = fmaxf(m, zz[j]);
+    float sum = 0.f;
+    for (int j = 0; j < n; ++j) { p[j] = expf(zz[j] - m); sum += p[j]; }
+    for (int j = 0; j < n; ++j) p[j] /= sum;
+    const float pl = p[lab];
+    clipped = pl < TK_EPS || pl > 1.f - TK_EPS;
+    loss = -logf(fminf(fmaxf(pl, TK_EPS), 1.f - TK_EPS));
+  };
+  if (z_acc) {
+    for (int j = 0; j < n; ++j) z[j] = z_acc[(size_t)b * n + j];
+    float loss; bool clipped;
+    softmax_ce(z, loss, clipped);
+    for (int j = 0; j < n; ++j) g_acc[(size_t)b * n + j] = clipped ? 0.f : (p[j] - (j == lab ? 1.f : 0.f)) * (w_acc / B);
+    losses[2 * b] = loss;
+  }
+  if (c_disc && head != SAR_HEAD_NONE) {
+    float c[32], dz[32];                                        // dz[j] = d logit_j / d c_j
+    for (int j = 0; j < n; ++j) { c[j] = c_disc[(size_t)b * n + j]; z[j] = c[j]; dz[j] = 1.f; }
+    if (head == SAR_HEAD_SPHEREFACE || head == SAR_HEAD_COSFACE || head == SAR_HEAD_ARCFACE) {
+      for (int j = 0; j < n; ++j) { z[j] = s * c[j]; dz[j] = s; }
+      const float cl = c[lab];
+      if (head == SAR_HEAD_COSFACE) {
+        z[lab] = s * (cl - margin);                                                  // losses.py:84
+      } else {
+        const float cc = fminf(fmaxf(cl, -1.f + TK_EPS), 1.f - TK_EPS);
+        const bool inside = cl > -1.f + TK_EPS && cl < 1.f - TK_EPS;                 // K.clip: zero gradient outside
+        const float th = acosf(cc), sn = sqrtf(fmaxf(1.f - cc * cc, 1e-30f));
+        if (head == SAR_HEAD_ARCFACE) { z[lab] = s * cosf(th + margin); dz[lab] = inside ? s * sinf(th + margin) / sn : 0.f; }
+        else { z[lab] = s * cosf(margin * th); dz[lab] = inside ? s * margin * sinf(margin * th) / sn : 0.f; }
+      }
+    } else if (head == SAR_HEAD_CIRCLE || head == SAR_HEAD_CIRCLE_RAW) {             // losses.py:157-172
+      for (int j = 0; j < n; ++j) {
+        if (j == lab) { const float ap = fmaxf(1.f + margin - c[j], 0.f); z[j] = gamma * ap * (c[j] - (1.f - margin)); dz[j] = ap > 0.f ? gamma * (2.f - 2.f * c[j]) : 0.f; }
+        else { const float an = fmaxf(c[j] + margin, 0.f); z[j] = gamma * an * (c[j] - margin); dz[j] = an > 0.f ? gamma * 2.f * c[j] : 0.f; }
+      }
+    }
+    float loss; bool clipped;
+    softmax_ce(z, loss, clipped);
+    if (head == SAR_HEAD_CIRCLE || head == SAR_HEAD_CIRCLE_RAW) {                    // -sum y log_softmax: no clip
+      clipped = false;
+      float m = -INFINITY;
+      for (int j = 0; j < n; ++j) m = fmaxf(m, z[j]);
+      float sum = 0.f;
+      for (int j = 0; j < n; ++j) sum += expf(z[j] - m);
+      loss = -(z[lab] - m - logf(sum));
+    }
+    for (int j = 0; j < n; ++j) g_disc[(size_t)b * n + j] = clipped ? 0.f : (p[j] - (j == lab ? 1.f : 0.f)) * dz[j] * (w_disc / B);
+    losses[2 * b + 1] = loss;
+  }
+}
+
+// ------------------------------------------------------------------ Adam (Keras 2.2.4) + l2 regulariser + unit_norm
+// g_eff = g + 2 * l2 * p ; m, v updated in place ; p -= lr_t * m / (sqrt(v) + eps)   (lr_t computed by the caller)
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            long long n, float lr_t, float b1, float b2, float eps, float l2) {
+  pdl_wait();
+  pdl_trigger();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float ge = fmaf(2.f * l2, p[i], g[i]);
+    const float mi = b1 * m[i] + (1.f - b1) * ge;
+    const float vi = b2 * v[i] + (1.f - b2) * ge * ge;
+    m[i] = mi; v[i] = vi;
+    p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+// keras.constraints.unit_norm(axis=0): W[:, j] /= (1e-7 + ||W[:, j]||), W (D, n)
+__global__ void unit_norm_kernel(float* __restrict__ w, int D, int n) {
+  pdl_wait();
+  pdl_trigger();
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  float q = 0.f;
+  for (int d = 0; d < D; ++d) q = fmaf(w[(size_t)d * n + j], w[(size_t)d * n + j], q);
+  const float inv = 1.f / (1e-7f + sqrtf(q));
+  for (int d = 0; d < D; ++d) w[(size_t)d * n + j] *= inv;
+}
+
+static unsigned blocks_for(long long n, int bs, int cap = 4096) {
+  long long b = (n + bs - 1) / bs;
+  return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace sar
+
+extern "C" {
+
+int sar_gemm_fwd(const float* A, const float* B, float* C, int M, int N, int K, int trans_a, int trans_b, float alpha, float beta,
+                 void* stream) {
+  using namespace sar;
+  SAR_REQUIRE(A && B && C, SAR_ERR_BAD_ARG, "sar_gemm_fwd: null pointer");
+  SAR_REQUIRE(M > 0 && N > 0 && K > 0, SAR_ERR_BAD_ARG, "sar_gemm_fwd: non-positive dimension");
+  launch_k(gemm_kernel, dim3((N + TG - 1) / TG, (M + TG - 1) / TG), dim3(256), 0, (cudaStream_t)stream, A, B, C, M, N, K, trans_a ? 1 : 0,
+           trans_b ? 1 : 0, alpha, beta);
+  return check_launch("sar_gemm_fwd");
+}
+
+int sar_bn_train_fwd(const float* x, const float* gamma, const float* beta, float* moving_mean, float* moving_var, float* y,
+                     float* save_mean, float* save_invstd, int rows, int C, float eps, float momentum, void* stream) {
+  using namespace sar;
+  SAR_REQUIRE(x && gamma && beta && y && save_mean && save_invstd, SAR_ERR_BAD_ARG, "sar_bn_train_fwd: null pointer");
+  SAR_REQUIRE(rows > 0 && C > 0, SAR_ERR_BAD_ARG, "sar_bn_train_fwd: non-positive dimension");
+  launch_k(bn_train_fwd_kernel, dim3((C + 127) / 128), dim3(128), 0, (cudaStream_t)stream, x, gamma, beta, moving_mean, moving_var, y,
+           save_mean, save_invstd, rows, C, eps, momentum);
+  return check_launch("sar_bn_train_fwd");
+}
+
+int sar_bn_train_bwd(const float* x, const float* dy, const float* gamma, const float* save_mean, const float* save_invstd,
+                     float* dx, float* dgamma, float* dbeta, int rows, int C, void* stream) {
+  using namespace sar;
+  SAR_REQUIRE(x && dy && gamma && save_mean && save_invstd && dgamma && dbeta, SAR_ERR_BAD_ARG, "sar_bn_train_bwd: null pointer");
+  SAR_REQUIRE(rows > 0 && C > 0, SAR_ERR_BAD_ARG, "sar_bn_train_bwd: non-positive dimension");
+  launch_k(bn_train_bwd_kernel, dim3((C + 127) / 128), dim3(128), 0, (cudaStream_t)stream, x, dy, gamma, save_mean, save_invstd, dx,
+           dgamma, dbeta, rows, C);
+  return check_launch("sar_bn_train_bwd");
+}
+
+int sar_bias_act_fwd(const float* x, const float* bias, float* y, long long rows, int C, int act, void* stream) {
+  using namespace sar;
+  SAR_REQUIRE(x && y, SAR_ERR_BAD_ARG, "sar_bias_act_fwd: null pointer");
+  SAR_REQUIRE(rows > 0 && C > 0 && (act == SAR_ACT_NONE || act == SAR_ACT_RELU), SAR_ERR_BAD_ARG, "sar_bias_act_fwd: bad argument");
+  launch_k(bias_act_kernel, dim3(blocks_for(rows * C, 256)), dim3(256), 0, (cudaStream_t)stream, x, bias, y, rows * C, C, act == SAR_ACT_RELU ? 1 : 0);
+  return check_launch("sar_bias_act_fwd");
+}
+
+int sar_relu_bwd(const float* g, const float* h, float* out, long long n, void* stream) {
+  using namespace sar;
+  SAR_REQUIRE(g && h && out && n > 0, SAR_ERR_BAD_ARG, "sar_relu_bwd: bad argument");
+  launch_k(relu_bwd_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, (cudaStream_t)stream, g, h, out, n);
+  return check_launch("sar_relu_bwd");
+}
+
+int sar_colsum_fwd(const float* g, float* out, int rows, int C, void* stream) {
+  using namespace sar;
+  SAR_REQUIRE(g && out && rows > 0 && C > 0, SAR_ERR_BAD_ARG, "sar_colsum_fwd: bad argument");
+  launch_k(colsum_kernel, dim3((C + 127) / 128), dim3(128), 0, (cudaStream_t)stream, g, out, rows, C);
+  return check_launch("sar_colsum_fwd");
+}
+
+int sar_l2norm_fwd(const float* v, float* out, float* inv_norm, int rows, int D, int axis, void* stream) {
+  using namespace sar;
+  SAR_REQUIRE(v && out && inv_norm && rows > 0 && D > 0 && (axis == 0 || axis == 1), SAR_ERR_BAD_ARG, "sar_l2norm_fwd: bad argument");
+  const int nvec = axis ? rows : D;
+  launch_k(l2norm_fwd_kernel, dim3((nvec + 63) / 64), dim3(64), 0, (cudaStream_t)stream, v, out, inv_norm, rows, D, axis);
+  return check_launch("sar_l2norm_fwd");
+}
+
+int sar_l2norm_bwd(const float* vhat, const float* inv_norm, const float* u, float* out, int rows, int D, int axis, float beta,
+                   void* stream) {
+  using namespace sar;
+  SAR_REQUIRE(vhat && inv_norm && u && out && rows > 0 && D > 0 && (axis == 0 || axis == 1), SAR_ERR_BAD_ARG, "sar_l2norm_bwd: bad argument");
+  const int nvec = axis ? rows : D;
+  launch_k(l2norm_bwd_kernel, dim3((nvec + 63) / 64), dim3(64), 0, (cudaStream_t)stream, vhat, inv_norm, u, out, rows, D, axis, beta);
+  return check_launch("sar_l2norm_bwd");
+}
+
+int sar_head_grad_fwd(const float* z_accent, const float* c_disc, const float* onehot, int n_classes, int head, float margin, float s,
+                      float gamma, float w_accent, float w_disc, float* g_accent, float* g_disc, float* losses, int B, void* stream) {
+  using namespace sar;
+  SAR_REQUIRE(onehot && losses && (z_accent || c_disc), SAR_ERR_BAD_ARG, "sar_head_grad_fwd: null pointer");
+  SAR_REQUIRE((!z_accent || g_accent) && (!c_disc || g_disc), SAR_ERR_BAD_ARG, "sar_head_grad_fwd: missing gradient output");
+  SAR_REQUIRE(B > 0 && n_classes > 0 && n_classes <= 32, SAR_ERR_UNSUPPORTED, "sar_head_grad_fwd: 1 <= n_classes <= 32");
+  SAR_REQUIRE(head >= SAR_HEAD_NONE && head <= SAR_HEAD_CIRCLE_RAW, SAR_ERR_BAD_ARG, "sar_head_grad_fwd: bad head selector");
+  launch_k(head_grad_kernel, dim3((B + 63) / 64), dim3(64), 0, (cudaStream_t)stream, z_accent, c_disc, onehot, n_classes, head, margin, s,
+           gamma, w_accent, w_disc, g_accent, g_disc, losses, B);
+  return check_launch("sar_head_grad_fwd");
+}
+
+int sar_adam_fwd(float* p, const float* g, float* m, float* v, long long n, float lr_t, float beta1, float beta2, float eps, float l2,
+                 void* stream) {
+  using namespace sar;
+  SAR_REQUIRE(p && g && m && v && n > 0, SAR_ERR_BAD_ARG, "sar_adam_fwd: bad argument");
+  launch_k(adam_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, n, lr_t, beta1, beta2, eps, l2);
+  return check_launch("sar_adam_fwd");
+}
+
+int sar_unit_norm_fwd(float* w, int D, int n, void* stream) {
+  using namespace sar;
+  SAR_REQUIRE(w && D > 0 && n > 0, SAR_ERR_BAD_ARG, "sar_unit_norm_fwd: bad argument");
+  launch_k(unit_norm_kernel, dim3((n + 63) / 64), dim3(64), 0, (cudaStream_t)stream, w, D, n);
+  return check_launch("sar_unit_norm_fwd");
+}
+
+}  // extern "C"

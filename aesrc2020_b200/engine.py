@@ -31,10 +31,18 @@ class StepOpts:
     lane: int = 0
     no_chain: bool = False
     gru_nb: int = 0
+    chain_ctas: int = 0       # > 0: stage chains with at most this many CTAs (several steps in flight share the SMs)
 
 
 DEFAULT_OPTS = StepOpts()
-SLOT_OPTS = lambda slot: StepOpts(lane=slot, no_chain=True, gru_nb=32)
+import os as _os
+_SLOT_CHAIN = int(_os.environ.get("SAR_SLOT_CHAIN_CTAS", "0"))       # experiment: capped stage chains inside pipeline slots
+
+
+def SLOT_OPTS(slot):
+    if _SLOT_CHAIN > 0:
+        return StepOpts(lane=slot, no_chain=False, gru_nb=32, chain_ctas=_SLOT_CHAIN)
+    return StepOpts(lane=slot, no_chain=True, gru_nb=32)
 
 
 def fold_bn(w: Dict[str, np.ndarray], name: str):
@@ -196,7 +204,7 @@ class ResNetTC:
                 key = ("chain", lane, B, stage, len(pending))
                 if key not in self._bufs:
                     self._bufs[key] = tc.chain_workspace(pending, self.device)
-                tc.conv_tc_chain(pending, self._bufs[key])
+                tc.conv_tc_chain(pending, self._bufs[key], max_ctas=opts.chain_ctas)
             pending.clear()
 
         def emit(desc, chainable):

@@ -215,11 +215,12 @@ def chain_workspace(descs, device) -> torch.Tensor:
     return torch.zeros((n + 3) // 4, device=device, dtype=torch.int32)
 
 
-def conv_tc_chain(descs, workspace: torch.Tensor):
-    """sar_conv_tc_chain_fwd: the stride-1 3x3 layers of one stage in one persistent launch."""
+def conv_tc_chain(descs, workspace: torch.Tensor, max_ctas: int = 0):
+    """sar_conv_tc_chain_grid_fwd: the stride-1 3x3 layers of one stage in one persistent (cooperative) launch;
+    `max_ctas` caps the grid so that chains of several streams share the SMs."""
     arr = (sar_tc_conv * len(descs))(*descs)
-    check(_shim.lib().sar_conv_tc_chain_fwd(arr, len(descs), ptr(workspace), workspace.numel() * 4, stream_ptr()),
-          "sar_conv_tc_chain_fwd")
+    check(_shim.lib().sar_conv_tc_chain_grid_fwd(arr, len(descs), ptr(workspace), workspace.numel() * 4, int(max_ctas),
+                                                 stream_ptr()), "sar_conv_tc_chain_fwd")
     ops._count(1)
 
 

@@ -1,0 +1,277 @@
+"""Training mode, first slice: one optimisation step of the reference's accent head on the device.
+
+What the reference does with the path is `train_model.fit_generator(...)` (train.py:38-44) on a model compiled with
+`Adam(lr, decay=2e-4)` (model.py:187-201).  This module builds the first slice of that: the layers AFTER
+`integration(...)` -- AR_BN1 -> AR_EMBEDDING -> AR_BN2 -> AR_CF_DS1 -> AR_CF_DS2 -> y_accent and the y_disc margin head
+(model.py:286-296, 142-167) -- run in TRAINING mode (batch-statistic BatchNormalization per replica, the l2(1e-4)
+regularisers of DS, the loss weights of model.py:344-367), are differentiated by hand-written backward kernels
+(csrc/train.cu through the C ABI) and updated with Keras' Adam; with `torch.distributed` initialised the gradients are
+all-reduced (mean) over the replicas -- the path's first bandwidth-relevant collective (4.2 M parameters at K = 64).
+The encoder in front (ResNet, Bi-GRU, AR_DS, VLAD) is the frozen inference engine and supplies `integ`.
+
+`HeadTrainer(model).train_on_batch(x)` mirrors Keras' `train_on_batch`: returns the weighted total and the per-output
+losses; `fit_generator(generator, steps_per_epoch, epochs)` loops it over utils.data_generator batches.  Not built yet:
+gradients of the encoder kernels (convolutions, Bi-GRU, CTC), i.e. end-to-end training.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import _shim, ops
+from ._shim import check, ptr, stream_ptr
+
+BN_EPS, BN_MOMENTUM = 1e-3, 0.99            # Keras BatchNormalization defaults
+L2_REG = 1e-4                               # DS(..., rgr=l2(1e-4)), model.py:35-42
+ADAM_B1, ADAM_B2, ADAM_EPS, ADAM_DECAY = 0.9, 0.999, 1e-7, 2e-4      # Adam(lr, decay=2e-4), model.py:197
+
+TRAINABLE = ("AR_BN1/gamma", "AR_BN1/beta", "AR_EMBEDDING/kernel", "AR_EMBEDDING/bias", "AR_BN2/gamma", "AR_BN2/beta",
+             "AR_CF_DS1/kernel", "AR_CF_DS1/bias", "AR_CF_DS2/kernel", "AR_CF_DS2/bias", "y_accent/kernel", "y_accent/bias")
+L2_KEYS = {"AR_EMBEDDING/kernel", "AR_EMBEDDING/bias", "AR_CF_DS1/kernel", "AR_CF_DS1/bias", "AR_CF_DS2/kernel",
+           "AR_CF_DS2/bias", "y_accent/kernel", "y_accent/bias"}
+
+
+# ---------------------------------------------------------------------------------------- thin wrappers (one per entry point)
+def gemm(a, b, *, ta=False, tb=False, alpha=1.0, beta=0.0, out=None):
+    M = a.shape[1] if ta else a.shape[0]
+    K = a.shape[0] if ta else a.shape[1]
+    N = b.shape[0] if tb else b.shape[1]
+    assert (b.shape[1] if tb else b.shape[0]) == K, (a.shape, b.shape, ta, tb)
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=torch.float32)
+    check(_shim.lib().sar_gemm_fwd(ptr(a), ptr(b), ptr(out), M, N, K, int(ta), int(tb), float(alpha), float(beta), stream_ptr()),
+          "sar_gemm_fwd")
+    ops._count(1)
+    return out
+
+
+def bn_train_fwd(x, gamma, beta, mov_mean=None, mov_var=None):
+    rows, C = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty((C,), device=x.device, dtype=torch.float32)
+    inv = torch.empty((C,), device=x.device, dtype=torch.float32)
+    check(_shim.lib().sar_bn_train_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(mov_mean), ptr(mov_var), ptr(y), ptr(mean), ptr(inv),
+                                       rows, C, BN_EPS, BN_MOMENTUM, stream_ptr()), "sar_bn_train_fwd")
+    ops._count(1)
+    return y, mean, inv
+
+
+def bn_train_bwd(x, dy, gamma, mean, inv, want_dx=True):
+    rows, C = x.shape
+    dx = torch.empty_like(x) if want_dx else None
+    dg = torch.empty((C,), device=x.device, dtype=torch.float32)
+    db = torch.empty((C,), device=x.device, dtype=torch.float32)
+    check(_shim.lib().sar_bn_train_bwd(ptr(x), ptr(dy), ptr(gamma), ptr(mean), ptr(inv), ptr(dx), ptr(dg), ptr(db), rows, C,
+                                       stream_ptr()), "sar_bn_train_bwd")
+    ops._count(1)
+    return dx, dg, db
+
+
+def bias_act(x, bias, relu=False):
+    y = torch.empty_like(x)
+    check(_shim.lib().sar_bias_act_fwd(ptr(x), ptr(bias), ptr(y), x.shape[0], x.shape[1], 1 if relu else 0, stream_ptr()),
+          "sar_bias_act_fwd")
+    ops._count(1)
+    return y
+
+
+def relu_bwd(g, h):
+    out = torch.empty_like(g)
+    check(_shim.lib().sar_relu_bwd(ptr(g), ptr(h), ptr(out), g.numel(), stream_ptr()), "sar_relu_bwd")
+    ops._count(1)
+    return out
+
+
+def colsum(g):
+    out = torch.empty((g.shape[1],), device=g.device, dtype=torch.float32)
+    check(_shim.lib().sar_colsum_fwd(ptr(g), ptr(out), g.shape[0], g.shape[1], stream_ptr()), "sar_colsum_fwd")
+    ops._count(1)
+    return out
+
+
+def l2norm_fwd(v, axis):
+    out = torch.empty_like(v)
+    inv = torch.empty((v.shape[0] if axis else v.shape[1],), device=v.device, dtype=torch.float32)
+    check(_shim.lib().sar_l2norm_fwd(ptr(v), ptr(out), ptr(inv), v.shape[0], v.shape[1], int(axis), stream_ptr()), "sar_l2norm_fwd")
+    ops._count(1)
+    return out, inv
+
+
+def l2norm_bwd(vhat, inv, u, axis, out=None, beta=0.0):
+    if out is None:
+        out = torch.empty_like(vhat)
+    check(_shim.lib().sar_l2norm_bwd(ptr(vhat), ptr(inv), ptr(u), ptr(out), vhat.shape[0], vhat.shape[1], int(axis), float(beta),
+                                     stream_ptr()), "sar_l2norm_bwd")
+    ops._count(1)
+    return out
+
+
+def head_grad(z_acc, c_disc, onehot, head_kind, margin, w_acc, w_disc, s=ops.FACE_S, gamma=ops.CIRCLE_GAMMA):
+    B, n = onehot.shape
+    g_acc = torch.empty((B, n), device=onehot.device, dtype=torch.float32) if z_acc is not None else None
+    g_disc = torch.empty((B, n), device=onehot.device, dtype=torch.float32) if c_disc is not None else None
+    losses = torch.zeros((B, 2), device=onehot.device, dtype=torch.float32)
+    check(_shim.lib().sar_head_grad_fwd(ptr(z_acc), ptr(c_disc), ptr(onehot), n, ops.HEAD[head_kind], float(margin), float(s),
+                                        float(gamma), float(w_acc), float(w_disc), ptr(g_acc), ptr(g_disc), ptr(losses), B,
+                                        stream_ptr()), "sar_head_grad_fwd")
+    ops._count(1)
+    return g_acc, g_disc, losses
+
+
+def adam_step(p, g, m, v, lr_t, l2=0.0):
+    check(_shim.lib().sar_adam_fwd(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), float(lr_t), ADAM_B1, ADAM_B2, ADAM_EPS, float(l2),
+                                   stream_ptr()), "sar_adam_fwd")
+    ops._count(1)
+
+
+def unit_norm(w):
+    check(_shim.lib().sar_unit_norm_fwd(ptr(w), w.shape[0], w.shape[1], stream_ptr()), "sar_unit_norm_fwd")
+    ops._count(1)
+
+
+def adam_lr_t(lr: float, iterations: int) -> float:
+    """Keras 2.2.4 Adam.get_updates: lr / (1 + decay * iterations) * sqrt(1 - b2^t) / (1 - b1^t), t = iterations + 1."""
+    t = iterations + 1
+    return lr / (1.0 + ADAM_DECAY * iterations) * float(np.sqrt(1.0 - ADAM_B2 ** t) / (1.0 - ADAM_B1 ** t))
+
+
+# ---------------------------------------------------------------------------------------- the trainer
+class HeadTrainer:
+    """Fine-tunes the accent head of a SARModel on the device (module docstring)."""
+
+    def __init__(self, model, lr: float = 0.01, group=None):
+        cfg = model.config
+        if not cfg.ar_enable:
+            raise ValueError("HeadTrainer needs ar_enable=True")
+        self.model, self.cfg, self.lr, self.group = model, cfg, float(lr), group
+        self.iterations = 0
+        self.head_kind = cfg.metric_loss if cfg.disc_enable else None
+        self.disc_key = None
+        if cfg.disc_enable:
+            self.disc_key = "y_disc/W" if cfg.metric_loss in ("sphereface", "cosface", "arcface") else "y_disc/kernel"
+        self.keys: List[str] = list(TRAINABLE) + ([self.disc_key] if self.disc_key else [])
+        self.l2 = set(L2_KEYS) | ({"y_disc/kernel"} if (cfg.disc_enable and cfg.metric_loss == "softmax") else set())
+        lw = cfg.loss_weights()
+        self.w_acc, self.w_disc = float(lw.get("y_accent", 0.0)), float(lw.get("y_disc", 0.0))
+        dev = torch.device(model.device)
+        put = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+        bn_stats = [b + s for b in ("AR_BN1", "AR_BN2") for s in ("/moving_mean", "/moving_variance")]
+        self.p: Dict[str, torch.Tensor] = {k: put(model.weights[k]) for k in self.keys + bn_stats}
+        self.m = {k: torch.zeros_like(self.p[k]) for k in self.keys}
+        self.v = {k: torch.zeros_like(self.p[k]) for k in self.keys}
+        self.last_grads: Dict[str, torch.Tensor] = {}
+
+    # ---- frozen encoder: x_data -> integ (B, K*D | D | 2u)
+    def encode(self, x) -> torch.Tensor:
+        out = self.model.forward_device(x, want_intermediates=True, graph=False)
+        return out["integration"].contiguous()
+
+    # ---- one step on (integ, onehot) device tensors
+    def step_on_features(self, integ: torch.Tensor, onehot: torch.Tensor) -> Dict[str, float]:
+        p, cfg = self.p, self.cfg
+        B = integ.shape[0]
+        # forward, training mode
+        x1, m1, i1 = bn_train_fwd(integ, p["AR_BN1/gamma"], p["AR_BN1/beta"], p["AR_BN1/moving_mean"], p["AR_BN1/moving_variance"])
+        e0 = bias_act(gemm(x1, p["AR_EMBEDDING/kernel"]), p["AR_EMBEDDING/bias"])
+        e, m2, i2 = bn_train_fwd(e0, p["AR_BN2/gamma"], p["AR_BN2/beta"], p["AR_BN2/moving_mean"], p["AR_BN2/moving_variance"])
+        h1 = bias_act(gemm(e, p["AR_CF_DS1/kernel"]), p["AR_CF_DS1/bias"], relu=True)
+        h2 = bias_act(gemm(h1, p["AR_CF_DS2/kernel"]), p["AR_CF_DS2/bias"], relu=True)
+        z = bias_act(gemm(h2, p["y_accent/kernel"]), p["y_accent/bias"])
+        c = xh = xinv = wh = winv = None
+        kind = self.head_kind
+        if kind in ("sphereface", "cosface", "arcface"):
+            xh, xinv = l2norm_fwd(e, 1)
+            wh, winv = l2norm_fwd(p[self.disc_key], 0)
+            c = gemm(xh, wh)
+        elif kind == "circleloss":
+            xh, xinv = l2norm_fwd(e, 1)
+            c = gemm(xh, p[self.disc_key])
+        elif kind == "softmax":
+            c = gemm(e, p[self.disc_key])
+        g_z, g_c, losses = head_grad(z, c, onehot, kind, cfg.margin, self.w_acc, self.w_disc)
+        # backward
+        g: Dict[str, torch.Tensor] = {}
+        g["y_accent/kernel"], g["y_accent/bias"] = gemm(h2, g_z, ta=True), colsum(g_z)
+        g_h2 = relu_bwd(gemm(g_z, p["y_accent/kernel"], tb=True), h2)
+        g["AR_CF_DS2/kernel"], g["AR_CF_DS2/bias"] = gemm(h1, g_h2, ta=True), colsum(g_h2)
+        g_h1 = relu_bwd(gemm(g_h2, p["AR_CF_DS2/kernel"], tb=True), h1)
+        g["AR_CF_DS1/kernel"], g["AR_CF_DS1/bias"] = gemm(e, g_h1, ta=True), colsum(g_h1)
+        g_e = gemm(g_h1, p["AR_CF_DS1/kernel"], tb=True)
+        if kind in ("sphereface", "cosface", "arcface"):
+            g[self.disc_key] = l2norm_bwd(wh, winv, gemm(xh, g_c, ta=True), 0)
+            l2norm_bwd(xh, xinv, gemm(g_c, wh, tb=True), 1, out=g_e, beta=1.0)
+        elif kind == "circleloss":
+            g[self.disc_key] = gemm(xh, g_c, ta=True)
+            l2norm_bwd(xh, xinv, gemm(g_c, p[self.disc_key], tb=True), 1, out=g_e, beta=1.0)
+        elif kind == "softmax":
+            g[self.disc_key] = gemm(e, g_c, ta=True)
+            gemm(g_c, p[self.disc_key], tb=True, out=g_e, beta=1.0)
+        g_e0, g["AR_BN2/gamma"], g["AR_BN2/beta"] = bn_train_bwd(e0, g_e, p["AR_BN2/gamma"], m2, i2)
+        g["AR_EMBEDDING/kernel"], g["AR_EMBEDDING/bias"] = gemm(x1, g_e0, ta=True), colsum(g_e0)
+        g_x1 = gemm(g_e0, p["AR_EMBEDDING/kernel"], tb=True)
+        _, g["AR_BN1/gamma"], g["AR_BN1/beta"] = bn_train_bwd(integ, g_x1, p["AR_BN1/gamma"], m1, i1, want_dx=False)
+        self._all_reduce(g)
+        self.last_grads = g
+        # Adam (the l2 regulariser's gradient 2 * 1e-4 * w is added inside the kernel), then the kernel constraint
+        lr_t = adam_lr_t(self.lr, self.iterations)
+        for k in self.keys:
+            adam_step(p[k], g[k], self.m[k], self.v[k], lr_t, l2=L2_REG if k in self.l2 else 0.0)
+        if kind == "circleloss":
+            unit_norm(p[self.disc_key])
+        self.iterations += 1
+        lm = losses.mean(0).tolist()
+        out = {"loss_accent": lm[0]}
+        total = self.w_acc * lm[0]
+        if kind:
+            out["loss_disc"] = lm[1]
+            total += self.w_disc * lm[1]
+        out["loss"] = total                        # data terms (Keras adds the regulariser terms to the reported total)
+        return out
+
+    def _all_reduce(self, grads: Dict[str, torch.Tensor]):
+        """Mean of the replicas' gradients: ONE flat all-reduce (NCCL over NVLink when initialised)."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+            return
+        flat = torch.cat([grads[k].reshape(-1) for k in self.keys])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+        flat /= dist.get_world_size(self.group)
+        off = 0
+        for k in self.keys:
+            n = grads[k].numel()
+            grads[k].copy_(flat[off:off + n].view_as(grads[k]))
+            off += n
+
+    # ---- Keras-like surface
+    def train_on_batch(self, x, y=None) -> Dict[str, float]:
+        xd = self.model._as_dict(x)
+        onehot = xd.get("x_accent") if self.cfg.disc_enable else (y or {}).get("y_accent")
+        if onehot is None:
+            raise ValueError("train_on_batch needs the accent labels (x_accent, or y['y_accent'])")
+        onehot = self.model._to_device("x_accent", onehot).contiguous()
+        return self.step_on_features(self.encode(xd), onehot)
+
+    def fit_generator(self, generator, steps_per_epoch: int, epochs: int = 1, verbose: int = 0):
+        """train.py:38-44 shape: `epochs` x `steps_per_epoch` batches of (inputs, targets) from the generator."""
+        history = []
+        it = iter(generator)
+        for ep in range(epochs):
+            acc = []
+            for _ in range(steps_per_epoch):
+                item = next(it)
+                x, y = item if isinstance(item, tuple) else (item, None)
+                acc.append(self.train_on_batch(x, y))
+            history.append({k: float(np.mean([a[k] for a in acc])) for k in acc[0]})
+            if verbose:
+                print("epoch %d: %s" % (ep, history[-1]))
+        self.sync_to_model()
+        return history
+
+    def sync_to_model(self):
+        """Write the trained parameters (and the BN moving statistics) back into model.weights; the inference engine
+        is rebuilt on next use."""
+        for k, t in self.p.items():
+            self.model.weights[k] = t.detach().cpu().numpy().astype(np.float32)
+        self.model._engine = None

@@ -148,6 +148,11 @@ int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream);
  * Results are bitwise those of n sar_conv_tc_fwd calls. */
 size_t sar_conv_tc_chain_workspace_bytes(const sar_tc_conv* first, int n);
 int sar_conv_tc_chain_fwd(const sar_tc_conv* descs, int n, void* workspace, size_t workspace_bytes, void* stream);
+/* Same with the grid capped at `max_ctas` CTAs (0: one per SM): the launch is cooperative (all CTAs co-resident), so two
+ * capped chains of different streams share the GPU -- every CTA then walks several tiles per layer back to back, with the
+ * epilogue of one under the mainloop of the next (less SM-time per layer than one launch per layer). */
+int sar_conv_tc_chain_grid_fwd(const sar_tc_conv* descs, int n, void* workspace, size_t workspace_bytes, int max_ctas,
+                               void* stream);
 
 /* MaxPooling2D(3x3, strides 2, 'same') -- resnet.py:174,192.  Padded cells never win. */
 int sar_maxpool2d_fwd(const float* x, float* out, int B, int H, int W, int C, int Ho, int Wo,
@@ -280,6 +285,44 @@ int sar_ctc_greedy_fwd(const float* logits, int ld, const int* in_len, int fixed
  * sample_stats (B,4) or NULL, ctc_loss (B) or NULL, bn_stats (B,4) or NULL. */
 int sar_loss_reduce_fwd(const float* sample_stats, const float* ctc_loss, const float* bn_stats,
                         float* out8, int B, void* stream);
+
+/* ---- training mode, first slice ------------------------------------------
+ * Building blocks of one optimisation step of the accent head -- the layers after integration() of model.py:286-296 and
+ * disc_loss (model.py:142-167) in TRAINING mode, the loss wiring of model.py:344-367 and compile()'s Adam(lr, decay=2e-4)
+ * (model.py:187-201).  fp32, deterministic; aesrc2020_b200/training.py composes them (HeadTrainer). */
+
+/* C (M,N) = alpha * op(A) op(B) + beta * C, row-major; trans_a: A is stored (K,M); trans_b: B is stored (N,K).
+ * Replaces: the Dense forward / backward contractions (x W, g W^T, x^T g). */
+int sar_gemm_fwd(const float* A, const float* B, float* C, int M, int N, int K, int trans_a, int trans_b, float alpha, float beta,
+                 void* stream);
+/* BatchNormalization in training mode on (rows, C): batch mean / BIASED variance per replica (what multi_gpu_model's towers
+ * do), y = gamma (x - mean) / sqrt(var + eps) + beta, moving statistics updated in place with `momentum` (NULL: not
+ * updated).  save_mean / save_invstd (C) feed the backward.  Replaces: BN(name=...) of model.py:29-30 with learning phase 1. */
+int sar_bn_train_fwd(const float* x, const float* gamma, const float* beta, float* moving_mean, float* moving_var, float* y,
+                     float* save_mean, float* save_invstd, int rows, int C, float eps, float momentum, void* stream);
+int sar_bn_train_bwd(const float* x, const float* dy, const float* gamma, const float* save_mean, const float* save_invstd,
+                     float* dx /* may be NULL */, float* dgamma, float* dbeta, int rows, int C, void* stream);
+/* y = act(x + bias) on (rows, C), act in {SAR_ACT_NONE, SAR_ACT_RELU}; out = g * (h > 0); out (C) = column sums of g (rows, C). */
+int sar_bias_act_fwd(const float* x, const float* bias, float* y, long long rows, int C, int act, void* stream);
+int sar_relu_bwd(const float* g, const float* h, float* out, long long n, void* stream);
+int sar_colsum_fwd(const float* g, float* out, int rows, int C, void* stream);
+/* K.l2_normalize of every row (axis 1) or column (axis 0) of v (rows, D): out = v / sqrt(max(|v|^2, 1e-12)), inv_norm per
+ * vector; backward: out = beta * out + (u - vhat (vhat . u)) * inv_norm, u = d loss / d vhat.  (losses.py:30-33, model.py:162) */
+int sar_l2norm_fwd(const float* v, float* out, float* inv_norm, int rows, int D, int axis, void* stream);
+int sar_l2norm_bwd(const float* vhat, const float* inv_norm, const float* u, float* out, int rows, int D, int axis, float beta,
+                   void* stream);
+/* Losses of the two accent outputs and their gradients (model.py:344-357, losses.py): z_accent (B,n) pre-softmax logits of
+ * y_accent; c_disc (B,n) the margin head's cosines (SAR_HEAD_SPHEREFACE / COSFACE / ARCFACE / CIRCLE) or logits
+ * (SAR_HEAD_SOFTMAX).  g_accent = w_accent / B * dCE/dz, g_disc = w_disc / B * d loss_disc / d c_disc (margin, scale s and
+ * Circle-Loss weighting chained in), losses (B,2) = per-sample [CE_accent, loss_disc]. */
+int sar_head_grad_fwd(const float* z_accent, const float* c_disc, const float* onehot, int n_classes, int head, float margin, float s,
+                      float gamma, float w_accent, float w_disc, float* g_accent, float* g_disc, float* losses, int B, void* stream);
+/* Keras 2.2.4 Adam: g' = g + 2 l2 p (the l2 regulariser of DS, model.py:35-42); m, v, p updated in place;
+ * p -= lr_t m / (sqrt(v) + eps).  lr_t = lr / (1 + decay * iterations) * sqrt(1 - beta2^t) / (1 - beta1^t) is the caller's. */
+int sar_adam_fwd(float* p, const float* g, float* m, float* v, long long n, float lr_t, float beta1, float beta2, float eps, float l2,
+                 void* stream);
+/* keras.constraints.unit_norm(axis=0) on W (D, n): the Circle-Loss head's kernel constraint (model.py:163). */
+int sar_unit_norm_fwd(float* w, int D, int n, void* stream);
 
 /* ---- feature front-end ------------------------------------------------------------- */
 

@@ -1,0 +1,121 @@
+"""TEST INFRASTRUCTURE -- float64 torch restatement of ONE TRAINING STEP of the reference's accent head
+(first slice): the layers after `integration(...)` of model.py:286-296 / 142-167 in TRAINING mode
+
+    integ -> AR_BN1 (batch statistics) -> AR_EMBEDDING Dense(+l2) -> AR_BN2 (batch statistics)
+          -> AR_CF_DS1 relu -> AR_CF_DS2 relu -> y_accent softmax            (categorical cross-entropy)
+          -> y_disc: SphereFace / CosFace / ArcFace / softmax Dense / l2norm + Dense (Circle-Loss)
+
+with the loss wiring of model.py:344-367 (loss_weights), the l2(1e-4) kernel / bias regularisers of DS (model.py:35-42),
+and `Adam(lr, decay=2e-4)` (model.py:197).  Gradients come from torch autograd on this float64 graph; the graph itself is
+the oracle's own forward functions (sarnet_oracle.face_logits / circle_loss / categorical_crossentropy), and the tests
+pin the gradients with central finite differences and Adam / BatchNorm against torch.optim.Adam / F.batch_norm.
+
+Only tests/ may import this module.  [KERAS-SEMANTICS] constants (Keras 2.2.4 on TF 1.13, third-party, restated):
+  * BatchNormalization(training): biased batch variance, eps 1e-3, moving = 0.99 * moving + 0.01 * batch (2-D inputs take
+    the non-fused path: the moving variance is updated with the BIASED batch variance);
+  * Adam: lr_t = lr / (1 + decay * iterations) * sqrt(1 - b2^t) / (1 - b1^t), t = iterations + 1, update
+    p -= lr_t * m / (sqrt(v) + 1e-7) (epsilon OUTSIDE the square root, K.epsilon());
+  * regulariser l2(c): c * sum(w^2) added to the loss (kernel AND bias of every DS layer);
+  * unit_norm constraint (Circle-Loss head, model.py:163): W <- W / (1e-7 + ||W[:, j]||) after every update.
+"""
+from __future__ import annotations
+
+from typing import Dict, Tuple
+
+import numpy as np
+import torch
+
+from . import sarnet_oracle as O
+
+BN_EPS, BN_MOMENTUM = 1e-3, 0.99
+L2_REG = 1e-4
+ADAM_B1, ADAM_B2, ADAM_EPS, ADAM_DECAY = 0.9, 0.999, 1e-7, 2e-4
+
+TRAINABLE = ("AR_BN1/gamma", "AR_BN1/beta", "AR_EMBEDDING/kernel", "AR_EMBEDDING/bias", "AR_BN2/gamma", "AR_BN2/beta",
+             "AR_CF_DS1/kernel", "AR_CF_DS1/bias", "AR_CF_DS2/kernel", "AR_CF_DS2/bias", "y_accent/kernel", "y_accent/bias")
+L2_KEYS = ("AR_EMBEDDING/kernel", "AR_EMBEDDING/bias", "AR_CF_DS1/kernel", "AR_CF_DS1/bias", "AR_CF_DS2/kernel",
+           "AR_CF_DS2/bias", "y_accent/kernel", "y_accent/bias")
+
+
+def disc_key(metric_loss: str) -> str:
+    return "y_disc/W" if metric_loss in ("sphereface", "cosface", "arcface") else "y_disc/kernel"
+
+
+def trainable_keys(disc_enable: bool, metric_loss: str):
+    return list(TRAINABLE) + ([disc_key(metric_loss)] if disc_enable else [])
+
+
+def l2_keys(disc_enable: bool, metric_loss: str):
+    # DS(accent_classes, 'softmax', use_bias=False) carries the l2 kernel regulariser; the Face layers and the
+    # Circle-Loss Dense do not (losses.py:13 regularizer=None; model.py:163 plain Dense)
+    return list(L2_KEYS) + (["y_disc/kernel"] if (disc_enable and metric_loss == "softmax") else [])
+
+
+def bn_train(x, gamma, beta):
+    mean = x.mean(0)
+    var = ((x - mean) ** 2).mean(0)
+    return (x - mean) / torch.sqrt(var + BN_EPS) * gamma + beta, mean, var
+
+
+def head_loss(p: Dict[str, torch.Tensor], integ: torch.Tensor, onehot: torch.Tensor, *, disc_enable: bool, metric_loss: str,
+              margin: float, w_accent: float, w_disc: float):
+    """-> (total loss incl. regularisers, dict of parts / batch statistics)."""
+    x1, m1, v1 = bn_train(integ, p["AR_BN1/gamma"], p["AR_BN1/beta"])
+    e0 = x1 @ p["AR_EMBEDDING/kernel"] + p["AR_EMBEDDING/bias"]
+    e, m2, v2 = bn_train(e0, p["AR_BN2/gamma"], p["AR_BN2/beta"])
+    h1 = torch.relu(e @ p["AR_CF_DS1/kernel"] + p["AR_CF_DS1/bias"])
+    h2 = torch.relu(h1 @ p["AR_CF_DS2/kernel"] + p["AR_CF_DS2/bias"])
+    pa = torch.softmax(h2 @ p["y_accent/kernel"] + p["y_accent/bias"], -1)
+    l_acc = O.categorical_crossentropy(onehot, pa).mean()
+    total = w_accent * l_acc
+    parts = {"loss_accent": l_acc, "bn1_mean": m1, "bn1_var": v1, "bn2_mean": m2, "bn2_var": v2, "embedding": e}
+    if disc_enable:
+        out, _ = O.disc_head(e, p, onehot, metric_loss, margin)
+        if metric_loss == "circleloss":
+            l_d = O.circle_loss(onehot, out, gamma=O.CIRCLE_GAMMA, margin=margin).mean()
+        else:
+            l_d = O.categorical_crossentropy(onehot, out).mean()
+        parts["loss_disc"] = l_d
+        total = total + w_disc * l_d
+    reg = sum(L2_REG * (p[k] ** 2).sum() for k in l2_keys(disc_enable, metric_loss))
+    parts["reg"] = reg
+    return total + reg, parts
+
+
+def adam_update(p, g, m, v, iterations: int, lr: float):
+    """One Keras-2.2.4 Adam update of a tensor; returns (p, m, v)."""
+    lr_t = lr * (1.0 / (1.0 + ADAM_DECAY * iterations))
+    t = iterations + 1
+    lr_t = lr_t * np.sqrt(1.0 - ADAM_B2 ** t) / (1.0 - ADAM_B1 ** t)
+    m = ADAM_B1 * m + (1 - ADAM_B1) * g
+    v = ADAM_B2 * v + (1 - ADAM_B2) * g * g
+    return p - lr_t * m / (torch.sqrt(v) + ADAM_EPS), m, v
+
+
+def train_step(params: Dict[str, np.ndarray], state: Dict[str, np.ndarray], integ, onehot, *, lr: float, iterations: int,
+               disc_enable: bool, metric_loss: str, margin: float, w_accent: float, w_disc: float
+               ) -> Tuple[Dict[str, np.ndarray], Dict[str, np.ndarray], Dict[str, float], Dict[str, np.ndarray]]:
+    """params: canonical weights (the trainable ones are updated); state: Adam moments `m/<key>`, `v/<key>`.
+    Returns (new params incl. the BN moving statistics, new state, losses, gradients)."""
+    keys = trainable_keys(disc_enable, metric_loss)
+    p = {k: torch.tensor(np.asarray(v, np.float64), requires_grad=(k in keys)) for k, v in params.items()}
+    total, parts = head_loss(p, torch.as_tensor(np.asarray(integ, np.float64)), torch.as_tensor(np.asarray(onehot, np.float64)),
+                             disc_enable=disc_enable, metric_loss=metric_loss, margin=margin, w_accent=w_accent, w_disc=w_disc)
+    grads = torch.autograd.grad(total, [p[k] for k in keys])
+    new_p = {k: np.asarray(v, np.float64).copy() for k, v in params.items()}
+    new_s = dict(state)
+    g_out = {}
+    for k, g in zip(keys, grads):
+        m = torch.as_tensor(np.asarray(state.get("m/" + k, np.zeros_like(new_p[k])), np.float64))
+        v = torch.as_tensor(np.asarray(state.get("v/" + k, np.zeros_like(new_p[k])), np.float64))
+        pk, m, v = adam_update(p[k].detach(), g, m, v, iterations, lr)
+        if k == "y_disc/kernel" and metric_loss == "circleloss":          # unit_norm constraint, axis 0
+            pk = pk / (1e-7 + torch.sqrt((pk ** 2).sum(0, keepdim=True)))
+        new_p[k], new_s["m/" + k], new_s["v/" + k] = pk.numpy(), m.numpy(), v.numpy()
+        g_out[k] = g.numpy()
+    for bn, mk, vk in (("AR_BN1", "bn1_mean", "bn1_var"), ("AR_BN2", "bn2_mean", "bn2_var")):
+        new_p[bn + "/moving_mean"] = BN_MOMENTUM * new_p[bn + "/moving_mean"] + (1 - BN_MOMENTUM) * parts[mk].detach().numpy()
+        new_p[bn + "/moving_variance"] = BN_MOMENTUM * new_p[bn + "/moving_variance"] + (1 - BN_MOMENTUM) * parts[vk].detach().numpy()
+    losses = {k: float(v.detach()) for k, v in parts.items() if k.startswith("loss") or k == "reg"}
+    losses["total"] = float(total.detach())
+    return new_p, new_s, losses, g_out

@@ -52,3 +52,34 @@ def test_loss_vector_allreduce_gloo_world2(tmp_path):
     assert m["count"] == 10 and abs(m["y_ctc_loss_loss"] - stats[:, 2].mean()) < 1e-6
     want_total = 0.01 * stats[:, 0].mean() + 0.6 * stats[:, 1].mean() + 0.01 * stats[:, 2].mean()
     assert abs(m["loss"] - want_total) < 1e-6                # model.py:344-367 weights (Q5)
+
+
+def _grad_worker(rank, world, port, q):
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from aesrc2020_b200.training import HeadTrainer
+    tr = HeadTrainer.__new__(HeadTrainer)                     # only the collective: no device, no model
+    tr.keys, tr.group = ["a", "b"], None
+    g = {"a": torch.full((3, 2), float(rank + 1)), "b": torch.arange(4, dtype=torch.float32) * (rank + 1)}
+    tr._all_reduce(g)
+    q.put((rank, g["a"].tolist(), g["b"].tolist()))
+    dist.destroy_process_group()
+
+
+def test_gradient_all_reduce_is_the_mean_over_replicas():
+    """training.HeadTrainer._all_reduce: ONE flat all-reduce, mean over the replicas (gloo here, NCCL on the GPUs)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 500) + 7
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, a, b in res:
+        assert a == [[1.5, 1.5]] * 3 and b == [0.0, 1.5, 3.0, 4.5]

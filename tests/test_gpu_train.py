@@ -1,0 +1,154 @@
+"""Training mode, first slice: the csrc/train.cu building blocks and one HeadTrainer step against the float64
+autograd oracle (oracle/train_oracle.py, itself pinned by finite differences in tests/test_oracle_train.py)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import norm_err, dev
+from oracle import train_oracle as TO
+
+pytestmark = pytest.mark.gpu
+
+KINDS = [("arcface", 0.3), ("cosface", 0.3), ("sphereface", 1.35), ("softmax", 0.0), ("circleloss", 0.2)]
+
+
+@pytest.mark.parametrize("M,N,K,ta,tb", [(64, 256, 16384, False, False), (16384, 256, 48, True, False), (48, 16384, 256, False, True),
+                                         (7, 5, 3, False, False), (65, 130, 17, True, True), (1, 8, 64, False, False)])
+def test_gemm_all_transposes(cuda_device, M, N, K, ta, tb):
+    from aesrc2020_b200 import training as T
+    rng = np.random.RandomState(M + N)
+    a = rng.randn(K, M) if ta else rng.randn(M, K)
+    b = rng.randn(N, K) if tb else rng.randn(K, N)
+    want = (a.T if ta else a) @ (b.T if tb else b)
+    got = T.gemm(dev(a), dev(b), ta=ta, tb=tb)
+    assert norm_err(got, want) < 5e-6
+    c0 = rng.randn(M, N)
+    out = dev(c0)
+    T.gemm(dev(a), dev(b), ta=ta, tb=tb, alpha=0.5, beta=2.0, out=out)
+    assert norm_err(out, 0.5 * want + 2.0 * c0) < 5e-6
+
+
+def test_bn_train_forward_backward(cuda_device):
+    from aesrc2020_b200 import training as T
+    rng = np.random.RandomState(3)
+    rows, C = 37, 300
+    x = rng.randn(rows, C) * 2 + 0.5
+    g, b = rng.uniform(0.5, 1.5, C), rng.randn(C)
+    mm, mv = rng.randn(C), rng.uniform(0.5, 2, C)
+    dy = rng.randn(rows, C)
+    xt = torch.tensor(x, requires_grad=True)
+    gt, bt = torch.tensor(g, requires_grad=True), torch.tensor(b, requires_grad=True)
+    y, mean, var = TO.bn_train(xt, gt, bt)
+    (y * torch.as_tensor(dy)).sum().backward()
+    mmd, mvd = dev(mm), dev(mv)
+    yd, mean_d, inv_d = T.bn_train_fwd(dev(x), dev(g), dev(b), mmd, mvd)
+    assert norm_err(yd, y.detach()) < 2e-6 and norm_err(mean_d, mean.detach()) < 2e-6
+    assert norm_err(mmd, 0.99 * mm + 0.01 * mean.detach().numpy()) < 2e-6
+    assert norm_err(mvd, 0.99 * mv + 0.01 * var.detach().numpy()) < 2e-6
+    dx, dg, db = T.bn_train_bwd(dev(x), dev(dy), dev(g), mean_d, inv_d)
+    assert norm_err(dx, xt.grad) < 1e-5 and norm_err(dg, gt.grad) < 1e-5 and norm_err(db, bt.grad) < 1e-5
+
+
+@pytest.mark.parametrize("axis", [0, 1])
+def test_l2norm_forward_backward(cuda_device, axis):
+    from aesrc2020_b200 import training as T
+    rng = np.random.RandomState(axis)
+    v = rng.randn(9, 13)
+    u = rng.randn(9, 13)
+    vt = torch.tensor(v, requires_grad=True)
+    vh = vt / torch.sqrt(torch.clamp((vt * vt).sum(1 if axis else 0, keepdim=True), min=1e-12))
+    (vh * torch.as_tensor(u)).sum().backward()
+    vhd, inv = T.l2norm_fwd(dev(v), axis)
+    assert norm_err(vhd, vh.detach()) < 2e-6
+    got = T.l2norm_bwd(vhd, inv, dev(u), axis)
+    assert norm_err(got, vt.grad) < 1e-5
+    acc = dev(np.ones((9, 13)))
+    T.l2norm_bwd(vhd, inv, dev(u), axis, out=acc, beta=1.0)
+    assert norm_err(acc, vt.grad + 1.0) < 1e-5
+
+
+def test_adam_and_unit_norm(cuda_device):
+    from aesrc2020_b200 import training as T
+    rng = np.random.RandomState(8)
+    p0 = rng.randn(40, 8)
+    p, m, v = torch.as_tensor(p0.copy()), torch.zeros(40, 8, dtype=torch.float64), torch.zeros(40, 8, dtype=torch.float64)
+    pd, md, vd = dev(p0), dev(np.zeros((40, 8))), dev(np.zeros((40, 8)))
+    for it in range(5):
+        g = rng.randn(40, 8)
+        p, m, v = TO.adam_update(p, torch.as_tensor(g) + 2 * 1e-4 * p, m, v, it, lr=0.01)
+        T.adam_step(pd, dev(g), md, vd, T.adam_lr_t(0.01, it), l2=1e-4)
+        assert norm_err(pd, p) < 5e-6 and norm_err(md, m) < 5e-6 and norm_err(vd, v) < 5e-6
+    T.unit_norm(pd)
+    assert np.allclose(np.sqrt((pd.cpu().numpy() ** 2).sum(0)), 1.0, atol=1e-6)
+
+
+def _params(kind, D, E=256, n=8, seed=0):
+    rng = np.random.RandomState(seed)
+    p = {"AR_BN1/gamma": rng.uniform(0.7, 1.3, D), "AR_BN1/beta": rng.randn(D) * 0.1, "AR_BN1/moving_mean": rng.randn(D) * 0.1,
+         "AR_BN1/moving_variance": rng.uniform(0.6, 1.4, D),
+         "AR_EMBEDDING/kernel": rng.randn(D, E) / np.sqrt(D), "AR_EMBEDDING/bias": rng.randn(E) * 0.1,
+         "AR_BN2/gamma": rng.uniform(0.7, 1.3, E), "AR_BN2/beta": rng.randn(E) * 0.1, "AR_BN2/moving_mean": rng.randn(E) * 0.1,
+         "AR_BN2/moving_variance": rng.uniform(0.6, 1.4, E),
+         "AR_CF_DS1/kernel": rng.randn(E, 64) / 16, "AR_CF_DS1/bias": rng.randn(64) * 0.1,
+         "AR_CF_DS2/kernel": rng.randn(64, 64) / 8, "AR_CF_DS2/bias": rng.randn(64) * 0.1,
+         "y_accent/kernel": rng.randn(64, n) / 8, "y_accent/bias": rng.randn(n) * 0.1}
+    W = rng.uniform(-0.15, 0.15, (E, n))
+    if kind == "circleloss":
+        W = W / np.sqrt((W ** 2).sum(0, keepdims=True))
+    p[TO.disc_key(kind)] = W
+    return {k: np.asarray(v, np.float32).astype(np.float64) for k, v in p.items()}
+
+
+@pytest.mark.parametrize("kind,margin", KINDS)
+def test_head_trainer_steps_match_the_autograd_oracle(cuda_device, kind, margin):
+    """Three consecutive optimisation steps (gradients, Adam state, BN moving statistics, unit_norm constraint) of
+    HeadTrainer.step_on_features vs oracle.train_oracle.train_step on the same features."""
+    from aesrc2020_b200 import model as mdl, training as T
+    model, _ = mdl.SAR_Net((200, 80, 1), ctc_enable=True, disc_enable=True, res_type="res34", res_filters=32, mto="gvlad",
+                           vlad_clusters=8, ghost_clusters=2, metric_loss=kind, margin=margin)
+    D = 8 * 256
+    params = _params(kind, D, seed=len(kind))
+    for k, v in params.items():
+        model.weights[k] = v.astype(np.float32)
+    tr = T.HeadTrainer(model, lr=0.01)
+    assert abs(tr.w_acc - 0.01) < 1e-12 and abs(tr.w_disc - 0.6) < 1e-12          # model.py:344-367 with CTC + disc
+    rng = np.random.RandomState(11)
+    B = 24
+    lab = rng.randint(0, 8, B)
+    state = {}
+    p_or = dict(params)
+    p_prev = dict(params)
+    for it in range(3):
+        integ = (rng.randn(B, D) * 0.05 + np.eye(8)[lab] @ rng.randn(8, D) * 0.02).astype(np.float32)
+        onehot = np.eye(8, dtype=np.float32)[lab]
+        p_or, state, l_or, g_or = TO.train_step(p_or, state, integ, onehot, lr=0.01, iterations=it, disc_enable=True,
+                                                metric_loss=kind, margin=margin, w_accent=tr.w_acc, w_disc=tr.w_disc)
+        got = tr.step_on_features(dev(integ), dev(onehot))
+        assert abs(got["loss_accent"] - l_or["loss_accent"]) < 1e-4 * max(1, abs(l_or["loss_accent"]))
+        assert abs(got["loss_disc"] - l_or["loss_disc"]) < 2e-4 * max(1, abs(l_or["loss_disc"]))
+        for k in tr.keys:                                  # raw gradients (before the l2 term, which Adam's kernel adds)
+            reg = 2 * TO.L2_REG * p_prev[k] if k in TO.l2_keys(True, kind) else 0.0
+            assert norm_err(tr.last_grads[k], g_or[k] - reg) < 2e-4, (it, k)
+        p_prev = {k: v.copy() for k, v in p_or.items()}
+        for k in tr.keys + ["AR_BN1/moving_mean", "AR_BN1/moving_variance", "AR_BN2/moving_mean", "AR_BN2/moving_variance"]:
+            assert norm_err(tr.p[k], p_or[k]) < 2e-4, (it, k)
+    tr.sync_to_model()
+    assert np.allclose(model.weights["AR_EMBEDDING/kernel"], p_or["AR_EMBEDDING/kernel"], atol=1e-4)
+
+
+def test_train_on_batch_lowers_the_loss_through_the_frozen_encoder(cuda_device):
+    """Keras-like surface: train_on_batch(x) = frozen encoder forward -> head step; 25 steps on one batch reduce the loss,
+    and the updated weights change model.predict."""
+    from aesrc2020_b200 import model as mdl, training as T, utils as us
+    model, _ = mdl.SAR_Net((200, 80, 1), disc_enable=True, res_type="res34", res_filters=32, mto="gvlad", vlad_clusters=8,
+                           ghost_clusters=2, metric_loss="arcface", margin=0.3)
+    x, y = us.synthetic_batch(model.config, 16, seed=3)
+    before = model.predict(x, batch_size=16)[1]
+    tr = T.HeadTrainer(model, lr=0.02)
+    hist = [tr.train_on_batch(x, y)["loss"] for _ in range(25)]
+    assert hist[-1] < 0.7 * hist[0], hist
+    tr.sync_to_model()
+    after = model.predict(x, batch_size=16)[1]
+    assert not np.allclose(before, after)
+    lab = np.argmax(x["x_accent"], -1)
+    assert np.mean(np.argmax(after, -1) == lab) >= np.mean(np.argmax(before, -1) == lab)

@@ -1,0 +1,105 @@
+"""Pins for oracle/train_oracle.py (SURVEY 8f-1 first slice): autograd gradients vs central finite differences for every
+head kind, Keras-style Adam vs torch.optim.Adam driven with the same decayed learning rate, BatchNorm training mode vs
+F.batch_norm, and one whole step reproducing a hand-rolled float64 computation."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import train_oracle as TO, sarnet_oracle as O
+
+KINDS = [("arcface", 0.3), ("cosface", 0.3), ("sphereface", 1.35), ("softmax", 0.0), ("circleloss", 0.2)]
+
+
+def _params(kind, D=24, E=16, n=8, seed=0):
+    rng = np.random.RandomState(seed)
+    p = {"AR_BN1/gamma": rng.uniform(0.7, 1.3, D), "AR_BN1/beta": rng.randn(D) * 0.1, "AR_BN1/moving_mean": rng.randn(D) * 0.1,
+         "AR_BN1/moving_variance": rng.uniform(0.6, 1.4, D),
+         "AR_EMBEDDING/kernel": rng.randn(D, E) / np.sqrt(D), "AR_EMBEDDING/bias": rng.randn(E) * 0.1,
+         "AR_BN2/gamma": rng.uniform(0.7, 1.3, E), "AR_BN2/beta": rng.randn(E) * 0.1, "AR_BN2/moving_mean": rng.randn(E) * 0.1,
+         "AR_BN2/moving_variance": rng.uniform(0.6, 1.4, E),
+         "AR_CF_DS1/kernel": rng.randn(E, 12) / 4, "AR_CF_DS1/bias": rng.randn(12) * 0.1,
+         "AR_CF_DS2/kernel": rng.randn(12, 12) / 3, "AR_CF_DS2/bias": rng.randn(12) * 0.1,
+         "y_accent/kernel": rng.randn(12, n) / 3, "y_accent/bias": rng.randn(n) * 0.1}
+    W = rng.uniform(-0.4, 0.4, (E, n))
+    if kind == "circleloss":
+        W = W / np.sqrt((W ** 2).sum(0, keepdims=True))
+    p[TO.disc_key(kind)] = W
+    return {k: np.asarray(v, np.float64) for k, v in p.items()}
+
+
+@pytest.mark.parametrize("kind,margin", KINDS)
+def test_autograd_gradients_match_finite_differences(kind, margin):
+    B, n = 6, 8
+    rng = np.random.RandomState(3)
+    params = _params(kind)
+    integ = rng.randn(B, 24)
+    onehot = np.eye(n)[rng.randint(0, n, B)]
+    kw = dict(disc_enable=True, metric_loss=kind, margin=margin, w_accent=0.01, w_disc=0.6)
+    _, _, _, grads = TO.train_step(params, {}, integ, onehot, lr=0.01, iterations=0, **kw)
+
+    def loss_of(pp):
+        t = {k: torch.as_tensor(v) for k, v in pp.items()}
+        return float(TO.head_loss(t, torch.as_tensor(integ), torch.as_tensor(onehot), **kw)[0])
+    for k in TO.trainable_keys(True, kind):
+        g = grads[k]
+        idx = [tuple(rng.randint(0, s) for s in g.shape) for _ in range(4)]
+        for i in idx:
+            h = 1e-6
+            pp, pm = {q: v.copy() for q, v in params.items()}, {q: v.copy() for q, v in params.items()}
+            pp[k][i] += h; pm[k][i] -= h
+            fd = (loss_of(pp) - loss_of(pm)) / (2 * h)
+            assert abs(fd - g[i]) <= 1e-6 * max(1.0, abs(fd)) + 2e-8, (kind, k, i, fd, g[i])
+
+
+def test_adam_matches_torch_optim_with_keras_decay():
+    rng = np.random.RandomState(1)
+    p0 = rng.randn(5, 3)
+    pt = torch.tensor(p0.copy(), requires_grad=True)
+    opt = torch.optim.Adam([pt], lr=0.01, betas=(0.9, 0.999), eps=0.0)       # eps handled below
+    p, m, v = torch.as_tensor(p0.copy()), torch.zeros(5, 3, dtype=torch.float64), torch.zeros(5, 3, dtype=torch.float64)
+    for it in range(6):
+        g = torch.as_tensor(rng.randn(5, 3))
+        p, m, v = TO.adam_update(p, g, m, v, it, lr=0.01)
+        # torch: p -= lr * mhat / (sqrt(vhat) + eps) with mhat = m/(1-b1^t), vhat = v/(1-b2^t): identical to Keras' form
+        # when eps = 0; with Keras' eps OUTSIDE the sqrt of the UNcorrected v the two differ at the 1e-7 level
+        for grp in opt.param_groups:
+            grp["lr"] = 0.01 / (1 + TO.ADAM_DECAY * it)
+        pt.grad = g.clone()
+        opt.step()
+        assert float((p - pt.detach()).abs().max()) < 2e-6
+    assert float((p - torch.as_tensor(p0)).abs().max()) > 1e-2                # it moved
+
+
+def test_bn_training_mode_matches_torch():
+    rng = np.random.RandomState(2)
+    x = torch.as_tensor(rng.randn(9, 7) * 2 + 1)
+    g, b = torch.as_tensor(rng.uniform(0.5, 1.5, 7)), torch.as_tensor(rng.randn(7))
+    y, mean, var = TO.bn_train(x, g, b)
+    rm, rv = torch.zeros(7, dtype=torch.float64), torch.ones(7, dtype=torch.float64)
+    want = F.batch_norm(x, rm, rv, g, b, training=True, momentum=0.01, eps=TO.BN_EPS)
+    assert float((y - want).abs().max()) < 1e-12
+    assert float((rm - 0.01 * mean).abs().max()) < 1e-12       # torch's running mean moved by (1 - 0.99) * batch mean
+    # (torch updates the running variance with the UNBIASED estimate; Keras' non-fused path uses the biased one)
+    assert float((rv - (0.99 + 0.01 * var * 9 / 8)).abs().max()) < 1e-12
+
+
+@pytest.mark.parametrize("kind,margin", [("arcface", 0.3), ("circleloss", 0.2)])
+def test_train_step_reduces_the_loss_and_updates_state(kind, margin):
+    rng = np.random.RandomState(5)
+    params = _params(kind, seed=4)
+    B, n = 16, 8
+    lab = rng.randint(0, n, B)
+    integ = rng.randn(B, 24) + np.eye(n)[lab] @ rng.randn(n, 24)           # separable classes
+    onehot = np.eye(n)[lab]
+    kw = dict(disc_enable=True, metric_loss=kind, margin=margin, w_accent=0.01, w_disc=1.0)
+    state, losses = {}, []
+    p = params
+    for it in range(40):
+        p, state, l, _ = TO.train_step(p, state, integ, onehot, lr=0.02, iterations=it, **kw)
+        losses.append(l["total"])
+    assert losses[-1] < 0.6 * losses[0]
+    assert set(state) == {s + k for k in TO.trainable_keys(True, kind) for s in ("m/", "v/")}
+    assert not np.allclose(p["AR_BN1/moving_mean"], params["AR_BN1/moving_mean"])
+    if kind == "circleloss":
+        assert np.allclose(np.sqrt((p["y_disc/kernel"] ** 2).sum(0)), 1.0, atol=1e-6)    # unit_norm constraint
