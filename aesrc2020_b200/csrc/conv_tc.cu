@@ -65,11 +65,14 @@ struct TcParams {
   const __half* res;                     // identity shortcut planes [2][R][Cout] or null
   __half* out_raw; __half* out_act; float* out_dense;
   long long* dbg;                        // optional: clock64 timestamps of CTA 0 (profiling aid)
+  int dbg_it0;                           // first CTA-local item the epilogue stamps cover (chain: a later phase)
   int mma_mask;                          // experiment: which of the 3 hi/lo products to issue (7 = all)
   int act_kind;                          // activated outputs: 0 relu(scale*v+shift), 1 identity, 2 tanh(v)
   unsigned div_rimg_m, div_p_m;          // floor(x / Rimg), floor(x / P) for x < 2^31 as __umulhi(x, m) >> sh (0: divisor is 1)
   int div_rimg_sh, div_p_sh;
   int epi_alias;                         // every CTA owns ONE tile: the epilogue staging lives on top of the (then idle) operand region
+  int nacc_log2;                         // TMEM accumulator stages = 1 << nacc_log2 (2; 4 in the slab kernel's 16-warp thin-tile form)
+  int epi_warps;                         // slab kernel: epilogue warps the launch carries (8 or 16) -> staging bytes
   int stages;                            // generic kernel: depth of the TMA ring (2 or 3)
   int ksplit, ksteps_split, mn_tiles;    // generic kernel, split-K (1-tap GEMMs with a long K): tile = z * mn_tiles + (mt, nt)
   long long dense_zstride;               // elements between the fp32 partial outputs of consecutive K slices
@@ -83,7 +86,7 @@ struct TcParams {
   // planes: it is only ever added in an epilogue (never an MMA operand), so the hi/lo split on write and the re-join
   // on read -- 16 of the ~18 instructions per element a conv2 epilogue spends on it -- are dropped.
   const float* res32;                    // identity shortcut, fp32 (instead of `res`)
-  float* out_raw32;                      // raw sum, fp32 (instead of `out_raw`); needs tma_out
+  float* out_raw32;                      // raw sum, fp32 (instead of `out_raw`)
 };
 // tensor maps of the plane outputs, box = (32 channels, 32 rows, 1 plane), 64B swizzle
 struct OutMaps { CUtensorMap raw, act; };
@@ -139,11 +142,12 @@ __device__ __noinline__ float tanh_precise(float x) { return tanhf(x); }
 template <int MODE, bool CHAIN = false>
 __device__ __forceinline__ void epilogue_item(const TcParams& p, const OutMaps& om, int tile, int c, int it, int quad, int lane,
                                            uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar,
-                                           uint32_t s_bias_u, uint32_t stage_u) {
+                                           uint32_t s_bias_u, uint32_t stage_u, uint64_t* pub_bar = nullptr) {
   const int BN = p.BN;
-  const int as = it & 1;
-  const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-  if (p.dbg && blockIdx.x == 0 && lane == 0 && it < 2 && c < 4) p.dbg[64 + ((it * 4 + c) * 4 + quad) * 4] = clock64();
+  const int as = it & ((1 << p.nacc_log2) - 1);
+  const uint32_t aphase = (uint32_t)(it >> p.nacc_log2) & 1u;
+  const int dit = it - p.dbg_it0;
+  if (p.dbg && blockIdx.x == 0 && lane == 0 && dit >= 0 && dit < 2 && c < 4) p.dbg[64 + ((dit * 4 + c) * 4 + quad) * 8] = clock64();
   const int z = tile / p.mn_tiles, tmn = tile - z * p.mn_tiles;         // K slice (split-K), tile within the M x N grid
   const int mt = tmn / p.n_tiles, nt = tmn - mt * p.n_tiles;
   const int n0 = nt * BN, c0 = c * 32;
@@ -228,9 +232,9 @@ __device__ __forceinline__ void epilogue_item(const TcParams& p, const OutMaps& 
     if (lane == 0) bulk_wait_read0();
     __syncwarp();
   }
-  // profiling aid (sar_tc_conv.dbg, >= 256 int64): CTA 0, per (quadrant, chunk) item of the first two tiles:
+  // profiling aid (sar_tc_conv.dbg, >= 384 int64): CTA 0, per (quadrant, chunk) item of the first two tiles:
   // [item entered | accumulator ready | math + staging done | item finished]
-#define EPI_STAMP(j) if (p.dbg && blockIdx.x == 0 && lane == 0 && it < 2 && c < 4) p.dbg[64 + ((it * 4 + c) * 4 + quad) * 4 + (j)] = clock64();
+#define EPI_STAMP(j) if (p.dbg && blockIdx.x == 0 && lane == 0 && dit >= 0 && dit < 2 && c < 4) p.dbg[64 + ((dit * 4 + c) * 4 + quad) * 8 + (j)] = clock64();
   EPI_STAMP(1)
   if (has_res) {                                     // shortcut pieces -> staging
     if (res32) {                                     // 32 rows x 128 B, piece j of a row in slot j ^ (row & 7)
@@ -370,6 +374,7 @@ __device__ __forceinline__ void epilogue_item(const TcParams& p, const OutMaps& 
       else if (out_raw) { tma_store_3d(&om.raw, rb, cc, cr, 0); tma_store_3d(&om.raw, rb + EPI_PLANE_BYTES, cc, cr, 1); }
       if (out_act) { tma_store_3d(&om.act, ab, cc, cr, 0); tma_store_3d(&om.act, ab + EPI_PLANE_BYTES, cc, cr, 1); }
       bulk_commit();
+      EPI_STAMP(4)
     }
   } else
   // write-out of the plane tiles: every store instruction covers 8 rows x 64 B
@@ -383,7 +388,7 @@ __device__ __forceinline__ void epilogue_item(const TcParams& p, const OutMaps& 
         const bool zero = dr < 0;                       // pad position: the staged values are garbage, store zeros
         const size_t e0 = (size_t)(zero ? -2 - dr : dr) * p.Cout + g_col;
         const uint4 z4 = make_uint4(0, 0, 0, 0);
-        if (out_raw) {
+        if (out_raw && !raw32) {
           *reinterpret_cast<uint4*>(p.out_raw + e0) = zero ? z4 : lds128(rb + off);
           *reinterpret_cast<uint4*>(p.out_raw + e0 + lo_off) = zero ? z4 : lds128(rb + EPI_PLANE_BYTES + off);
         }
@@ -392,6 +397,17 @@ __device__ __forceinline__ void epilogue_item(const TcParams& p, const OutMaps& 
           *reinterpret_cast<uint4*>(p.out_act + e0 + lo_off) = zero ? z4 : lds128(ab + EPI_PLANE_BYTES + off);
         }
       }
+    }
+  }
+  if (!tma_out && out_raw && raw32) {                // fp32 residual stream, generic stores: 4 rows x 128 B per instruction
+    const int d_row = lane >> 3, d_piece = lane & 7;   // (pad rows carry whatever the MMA produced: never an MMA operand)
+#pragma unroll 1
+    for (int i = 0; i < 8; ++i) {
+      const int rl_ = 4 * i + d_row;
+      const long long qq = row0 + rl_;
+      if (qq < p.R)
+        *reinterpret_cast<uint4*>(p.out_raw32 + (size_t)qq * p.Cout + n0 + c0 + 4 * d_piece) =
+            lds128(rb + (uint32_t)rl_ * 128u + ((((uint32_t)d_piece) ^ (uint32_t)(rl_ & 7)) << 4));
     }
   }
   if (out_dense) {                                   // 4 rows x 128 B per store instruction
@@ -409,8 +425,20 @@ __device__ __forceinline__ void epilogue_item(const TcParams& p, const OutMaps& 
   if (CHAIN && p.flag_done) {                        // publish: the rows this item wrote are visible GPU-wide
     if (lane == 0) {
       if (tma_out) { bulk_wait0(); asm volatile("fence.proxy.async;" ::: "memory"); }   // the bulk stores have landed
-      __threadfence();
-      atomicAdd(p.flag_done + mt, 1);
+      EPI_STAMP(5)
+      if (pub_bar) {
+        // hand the tile to the CTA's publisher thread (conv_tc_chain_kernel): this warp's stores are ordered before
+        // the arrive (release.cta; the lanes' stores by the __syncwarp above), the publisher's wait acquires them and
+        // its ONE fence.acq_rel.gpu + counter bump per tile is cumulative over all eight warps' rows.  The warp does
+        // not sit out the ~1.5k-cycle fence.  pub_bar[0..1]: stored (one arrival per item), pub_bar[2..3]: taken by
+        // the publisher -- waited for before slot it & 1 is used again, so neither barrier can run two phases ahead.
+        if (it >= 2) mbar_wait(&pub_bar[2 + as], (uint32_t)((it - 2) >> 1) & 1u);   // publisher took tile it - 2 off this slot
+        mbar_arrive(&pub_bar[as]);
+      } else {
+        __threadfence();
+        EPI_STAMP(6)
+        atomicAdd(p.flag_done + mt, 1);
+      }
     }
   }
   EPI_STAMP(3)
@@ -632,13 +660,13 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   // operand region, which is idle once the tile's last MMA has retired
   uint8_t* epi_own = b_base + (size_t)nb * 2 * sp.bplane_bytes;
   uint8_t* epi_base = p.epi_alias ? smem : epi_own;
-  uint64_t* sfull_bar = reinterpret_cast<uint64_t*>(epi_own + (p.epi_alias ? 0 : EPI_BYTES));
+  uint64_t* sfull_bar = reinterpret_cast<uint64_t*>(epi_own + (p.epi_alias ? 0 : (size_t)p.epi_warps * EPI_WARP_BYTES));
   uint64_t* sempty_bar = sfull_bar + SL_MAX_SLABS;
   uint64_t* bfull_bar = sempty_bar + SL_MAX_SLABS;
   uint64_t* bempty_bar = bfull_bar + SL_MAX_RING;
   uint64_t* tfull_bar = bempty_bar + SL_MAX_RING;
-  uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* rbar = tempty_bar + 2;                                     // [8 warps] shortcut chunk landed
+  uint64_t* tempty_bar = tfull_bar + 4;                                // [4] (2 or 4 accumulator stages in use)
+  uint64_t* rbar = tempty_bar + 4;                                     // [8 warps] shortcut chunk landed
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(rbar + 8);
   float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_base_slot + 2) + 15) & ~uintptr_t(15));   // float4 reads
   float* s_scale = s_bias + p.Cout;
@@ -646,15 +674,16 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int BN = p.BN;
-  const uint32_t tmem_cols = (4 * BN <= 128) ? 128u : (4 * BN <= 256 ? 256u : 512u);
+  const int nacc = 1 << p.nacc_log2;
+  const uint32_t tmem_cols = (2 * nacc * BN <= 128) ? 128u : (2 * nacc * BN <= 256 ? 256u : 512u);
 
   // Short prologue (it is on the critical path of every layer: the previous kernel's CTA must leave the SM before
   // this one starts): the 52 mbarriers are initialised one per lane, TMEM is allocated by the MMA warp, and only
   // the epilogue warps wait for the bias / BN vectors (they are idle until the first accumulator is ready).
   if (warp == WARP_TMA) {
-    constexpr int NBAR = 2 * SL_MAX_SLABS + 2 * SL_MAX_RING + 2 + 2 + 8;       // contiguous from sfull_bar
+    constexpr int NBAR = 2 * SL_MAX_SLABS + 2 * SL_MAX_RING + 4 + 4 + 8;       // contiguous from sfull_bar
     for (int i = lane; i < NBAR; i += 32) {
-      const bool is_tempty = (i == 2 * SL_MAX_SLABS + 2 * SL_MAX_RING + 2) || (i == 2 * SL_MAX_SLABS + 2 * SL_MAX_RING + 3);
+      const bool is_tempty = i >= 2 * SL_MAX_SLABS + 2 * SL_MAX_RING + 4 && i < 2 * SL_MAX_SLABS + 2 * SL_MAX_RING + 8;
       mbar_init(&sfull_bar[i], is_tempty ? 4u * (uint32_t)(p.BN >> 5) : 1u);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -780,8 +809,8 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       int it = 0;
       if (RESIDENT) { mbar_wait(&bfull_bar[0], 0); tc_fence_after(); }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int as = it & 1;
-        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        const int as = it & (nacc - 1);
+        const uint32_t aphase = (uint32_t)(it >> p.nacc_log2) & 1u;
         if (p.dbg && blockIdx.x == 0 && it < 8) p.dbg[it * 4] = clock64();
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
@@ -878,16 +907,29 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 // There is no grid-wide barrier: a 3x3 tile of layer l reads the rows of M tiles m-1, m, m+1 of layer l-1, so the
 // TMA producer waits for those three per-M-tile counters (bumped by the epilogue warps with a release pattern:
 // stores, __syncwarp, __threadfence, atomicAdd; read with ld.acquire + fence.proxy.async before the TMA load).
-// Tiles are dealt to CTAs identically in every phase (tile = blockIdx.x + k * gridDim.x), all CTAs are resident
-// (grid <= #SMs), and dependencies only point to the previous phase: no deadlock.  Neighbouring tiles are never
-// more than one phase apart, which also makes the two-slot rotation of the activation buffers safe.
+// The (phase, tile) items of the whole chain are numbered phase-major and dealt round-robin (item = blockIdx.x +
+// k * gridDim.x), so a phase whose tile count is not a multiple of the grid (160 or 315 tiles on 148 SMs) costs
+// tiles / grid rounds instead of ceil(tiles / grid) -- with a per-phase deal the CTAs holding the extra tile set
+// the pace of the whole chain.  Every CTA walks its items in increasing order, all CTAs are resident (cooperative
+// launch, grid <= #SMs) and an item only waits for items with a smaller number: no deadlock.  An item of phase
+// l + 1 starts after the three M tiles of phase l that read its rows have finished, so the read-after-write
+// flags also order the write-after-read reuse of the two-slot activation buffers.
 // Weights stream through the TMA ring (non-resident form of conv_tc_slab_kernel), epilogue staging has its own
 // 64 KB, the per-item bias / BN vectors a 3 KB per-warp area.
 constexpr int CH_MAX = 12;
+constexpr int CH_DBG_ITEMS = 32, CH_DBG_STRIDE = 8 + CH_DBG_ITEMS * 8;
+// profiling aid: [cta][0] clock64 at start, [1] globaltimer at start, [2] clock64 at exit; per item it < 32 at
+// 8 + it * 8: [0] item number + 1, [1] producer reached the item, [2] dependencies met, [3] first slab landed (MMA warp),
+// [4] all MMAs issued, [5] epilogue warp 0/4 entered chunk 0, [6] chunk 0 published, [7] last chunk published
+#define CH_STAMP(itv, j) if (cp.dbg && (itv) < CH_DBG_ITEMS) cp.dbg[(size_t)blockIdx.x * CH_DBG_STRIDE + 8 + (itv) * 8 + (j)] = clock64();
 struct ChainPhase { CUtensorMap mapA, mapS, mapWm, mapWs; OutMaps om; TcParams p; };
+constexpr int CH_WARP_PUB = SL_WARP_MMA + 1;        // publisher: one fence + counter bump per finished tile
+constexpr int CH_THREADS = SL_THREADS + 32;
 struct ChainParams {
   int n_phases;
+  int publisher;                 // 1: epilogue warps hand finished tiles to the publisher thread; 0: every warp fences itself
   int* flags;                    // [n_phases][m_tiles] counters + [1] CTA exit counter (self-cleaning)
+  long long* dbg;                // optional (descs[0].dbg): per CTA CH_DBG_STRIDE int64 of clock64 stamps, see scripts/chain_dbg.py
   SlabParams sp;
   ChainPhase ph[CH_MAX];
 };
@@ -899,7 +941,7 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 }
 
 template <int KC>
-__global__ void __launch_bounds__(SL_THREADS, 1) conv_tc_chain_kernel(const __grid_constant__ ChainParams cp) {
+__global__ void __launch_bounds__(CH_THREADS, 1) conv_tc_chain_kernel(const __grid_constant__ ChainParams cp) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const SlabParams& sp = cp.sp;
@@ -914,18 +956,20 @@ __global__ void __launch_bounds__(SL_THREADS, 1) conv_tc_chain_kernel(const __gr
   uint64_t* bempty_bar = bfull_bar + SL_MAX_RING;
   uint64_t* tfull_bar = bempty_bar + SL_MAX_RING;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* pub_bar = tempty_bar + 2;                                  // [2] tile it (slot it & 1) stored by all its items, [2] taken
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(pub_bar + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int BN = g0.BN;
   const uint32_t tmem_cols = (4 * BN <= 128) ? 128u : (4 * BN <= 256 ? 256u : 512u);
   const int total_tiles = g0.m_tiles * g0.n_tiles;
+  const int n_items = cp.n_phases * total_tiles;                       // item = phase * total_tiles + tile, dealt round-robin
 
   if (warp == SL_WARP_TMA) {
-    constexpr int NBAR = 2 * SL_MAX_SLABS + 2 * SL_MAX_RING + 2 + 2;
+    constexpr int NBAR = 2 * SL_MAX_SLABS + 2 * SL_MAX_RING + 2 + 2 + 4;
     for (int i = lane; i < NBAR; i += 32) {
-      const bool is_tempty = i >= NBAR - 2;
-      mbar_init(&sfull_bar[i], is_tempty ? 4u * (uint32_t)(BN >> 5) : 1u);
+      const bool per_item = i >= NBAR - 6 && i < NBAR - 2;             // tempty, pub stored: one arrival per epilogue item of a tile
+      mbar_init(&sfull_bar[i], per_item ? 4u * (uint32_t)(BN >> 5) : 1u);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (lane == 0) { prefetch_tmap(&cp.ph[0].mapA); prefetch_tmap(&cp.ph[0].mapWm); }
@@ -940,21 +984,36 @@ __global__ void __launch_bounds__(SL_THREADS, 1) conv_tc_chain_kernel(const __gr
   const uint32_t tmem_base = *tmem_base_slot;
   pdl_wait();
   pdl_trigger();
+  if (cp.dbg && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    cp.dbg[(size_t)blockIdx.x * CH_DBG_STRIDE] = clock64();
+    cp.dbg[(size_t)blockIdx.x * CH_DBG_STRIDE + 1] = (long long)gt;
+  }
 
   if (warp == SL_WARP_TMA) {
     // ===================== TMA producer =====================
     int sb = 0; uint32_t sphase = 0;        // slab ring
     int bs = 0; uint32_t bphase = 0;        // weight ring
-    for (int ph = 0; ph < cp.n_phases; ++ph) {
+    int ph_seen = -1, pit = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int ph = item / total_tiles, tile = item - ph * total_tiles;
       const ChainPhase& P = cp.ph[ph];
       const TcParams& p = P.p;
       const int n_main = p.ntaps * p.chunks_main;
       const int n_chunks = p.chunks_main + p.chunks_sc;
-      if (lane == 0 && ph + 1 < cp.n_phases) { prefetch_tmap(&cp.ph[ph + 1].mapA); prefetch_tmap(&cp.ph[ph + 1].mapWm); }
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      if (ph != ph_seen) {
+        ph_seen = ph;
+        if (lane == 0 && ph + 1 < cp.n_phases) { prefetch_tmap(&cp.ph[ph + 1].mapA); prefetch_tmap(&cp.ph[ph + 1].mapWm); }
+      }
+      {
         const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
         const long long q0 = (long long)mt * TC_BM;
         const int n0 = nt * BN;
+        if (lane == 0) {
+          if (cp.dbg && pit < CH_DBG_ITEMS) cp.dbg[(size_t)blockIdx.x * CH_DBG_STRIDE + 8 + pit * 8] = item + 1;
+          CH_STAMP(pit, 1)
+        }
         if (p.flag_dep) {                    // rows of M tiles mt-1 .. mt+1 of the previous layer must be complete
           const int lo = mt > 0 ? mt - 1 : 0, hi = mt + 1 < p.m_tiles ? mt + 1 : p.m_tiles - 1;
           const long long t0 = clock64();
@@ -964,6 +1023,8 @@ __global__ void __launch_bounds__(SL_THREADS, 1) conv_tc_chain_kernel(const __gr
           asm volatile("fence.proxy.async;" ::: "memory");
           __syncwarp();
         }
+        if (lane == 0) { CH_STAMP(pit, 2) }
+        ++pit;
         for (int c = 0; c < n_chunks; ++c) {
           const bool main = c < p.chunks_main;
           const int kc = main ? p.kc_main : p.kc_sc;
@@ -1016,9 +1077,9 @@ __global__ void __launch_bounds__(SL_THREADS, 1) conv_tc_chain_kernel(const __gr
       int sb = 0; uint32_t sphase = 0;
       int bs = 0; uint32_t bphase = 0;
       int it = 0;
-      for (int ph = 0; ph < cp.n_phases; ++ph) {
-        const TcParams& p = cp.ph[ph].p;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const TcParams& p = cp.ph[item / total_tiles].p;
+        {
           const int as = it & 1;
           const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
           mbar_wait(&tempty_bar[as], aphase ^ 1);
@@ -1029,6 +1090,7 @@ __global__ void __launch_bounds__(SL_THREADS, 1) conv_tc_chain_kernel(const __gr
           for (int c = 0; c < p.chunks_main; ++c) {
             mbar_wait(&sfull_bar[sb], sphase);
             tc_fence_after();
+            if (c == 0) { CH_STAMP(it, 3) }
             uint32_t a_row = a_base0 + (uint32_t)sb * a_slab16 + tap0_16;
 #pragma unroll
             for (int kh = 0; kh < 3; ++kh) {
@@ -1076,28 +1138,47 @@ __global__ void __launch_bounds__(SL_THREADS, 1) conv_tc_chain_kernel(const __gr
             if (c == p.chunks_sc - 1) umma_commit(&tfull_bar[as]);
             if (++sb == sp.nslab) { sb = 0; sphase ^= 1; }
           }
+          CH_STAMP(it, 4)
         }
       }
     }
     __syncwarp();
+  } else if (warp == CH_WARP_PUB) {
+    // ===================== publisher: tile stored by all its epilogue warps -> fence -> counter =====================
+    if (cp.publisher && lane == 0) {
+      int it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int ph = item / total_tiles, tile = item - ph * total_tiles;
+        const TcParams& p = cp.ph[ph].p;
+        mbar_wait(&pub_bar[it & 1], (uint32_t)(it >> 1) & 1u);
+        mbar_arrive(&pub_bar[2 + (it & 1)]);
+        __threadfence();
+        atomicAdd(p.flag_done + tile / p.n_tiles, 4 * (BN >> 5));
+        CH_STAMP(it, 7)
+      }
+    }
   } else {
     // ===================== epilogue warps =====================
     const int quad = warp & 3, group = warp >> 2;
+    uint64_t* const pubp = cp.publisher ? pub_bar : nullptr;
     const uint32_t stage_u = smem_u32(epi_base + (size_t)warp * EPI_WARP_BYTES);
     const uint32_t vec_u = smem_u32(vec_base + (size_t)warp * 384);
     const int nchunks = BN >> 5;
     int it = 0;
-    for (int ph = 0; ph < cp.n_phases; ++ph) {
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int ph = item / total_tiles, tile = item - ph * total_tiles;
       const TcParams& p = cp.ph[ph].p;
       const OutMaps& om = cp.ph[ph].om;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it)
-        for (int c = 0; c < nchunks; ++c)
+      for (int c = 0; c < nchunks; ++c)
           if (((it * nchunks + c) & 1) == group) {
+            if (quad == 0 && lane == 0 && c == 0) { CH_STAMP(it, 5) }
             switch (p.epi_mode) {
-              case 0: epilogue_item<0, true>(p, om, tile, c, it, quad, lane, tmem_base, tfull_bar, tempty_bar, vec_u, stage_u); break;
-              case 3: epilogue_item<3, true>(p, om, tile, c, it, quad, lane, tmem_base, tfull_bar, tempty_bar, vec_u, stage_u); break;
-              default: epilogue_item<-1, true>(p, om, tile, c, it, quad, lane, tmem_base, tfull_bar, tempty_bar, vec_u, stage_u); break;
+              case 0: epilogue_item<0, true>(p, om, tile, c, it, quad, lane, tmem_base, tfull_bar, tempty_bar, vec_u, stage_u, pubp); break;
+              case 3: epilogue_item<3, true>(p, om, tile, c, it, quad, lane, tmem_base, tfull_bar, tempty_bar, vec_u, stage_u, pubp); break;
+              default: epilogue_item<-1, true>(p, om, tile, c, it, quad, lane, tmem_base, tfull_bar, tempty_bar, vec_u, stage_u, pubp); break;
             }
+            if (quad == 0 && lane == 0 && c == 0) { CH_STAMP(it, 6) }
+            if (!cp.publisher && quad == 0 && lane == 0 && c == nchunks - 1) { CH_STAMP(it, 7) }
           }
     }
     if (lane == 0) bulk_wait0();                     // (items of TMA-store layers already waited before publishing)
@@ -1109,6 +1190,7 @@ __global__ void __launch_bounds__(SL_THREADS, 1) conv_tc_chain_kernel(const __gr
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
   }
+  if (cp.dbg && threadIdx.x == 0) cp.dbg[(size_t)blockIdx.x * CH_DBG_STRIDE + 2] = clock64();
   // self-cleaning counters: the last CTA to leave zeroes them for the next launch
   __shared__ int s_last;
   const int nflags = cp.n_phases * g0.m_tiles;
@@ -1118,7 +1200,7 @@ __global__ void __launch_bounds__(SL_THREADS, 1) conv_tc_chain_kernel(const __gr
   }
   __syncthreads();
   if (s_last)
-    for (int i = threadIdx.x; i <= nflags; i += SL_THREADS) cp.flags[i] = 0;
+    for (int i = threadIdx.x; i <= nflags; i += CH_THREADS) cp.flags[i] = 0;
 }
 
 // ------------------------------------------------------------------ host side
@@ -1237,6 +1319,7 @@ static int fill_params(const sar_tc_conv* d, TcParams& p) {
   SAR_REQUIRE(!(p.out_act && p.out_dense), SAR_ERR_BAD_ARG,
               "sar_conv_tc_fwd: out_act and out_dense are the same activated values in two layouts -- request one of them");
 
+  p.nacc_log2 = 1; p.epi_warps = 8;
   p.ksplit = d->ksplit > 1 ? d->ksplit : 1;
   if (p.ksplit > 1) {
     SAR_REQUIRE(d->ntaps == 1 && !d->s && !d->res && !d->out_raw && !d->out_act && d->out_dense && d->act_kind == 1,
@@ -1247,8 +1330,8 @@ static int fill_params(const sar_tc_conv* d, TcParams& p) {
   // plane outputs of an unsplit map leave through TMA stores (SAR_TC_TMA_OUT=0: the LDS -> STG write-out, an A/B aid)
   static const bool tma_ok = !(getenv("SAR_TC_TMA_OUT") && getenv("SAR_TC_TMA_OUT")[0] == '0');
   p.tma_out = (tma_ok && !p.split && !d->out_dense && (d->out_raw || d->out_raw_f32 || d->out_act)) ? 1 : 0;
-  SAR_REQUIRE(!d->out_raw_f32 || p.tma_out, SAR_ERR_UNSUPPORTED,
-              "sar_conv_tc_fwd: out_raw_f32 needs the TMA-store epilogue (unsplit plane outputs, SAR_TC_TMA_OUT unset)");
+  SAR_REQUIRE(!d->out_raw_f32 || (!p.split && !d->out_dense), SAR_ERR_UNSUPPORTED,
+              "sar_conv_tc_fwd: out_raw_f32 needs unsplit plane outputs");
   SAR_REQUIRE(!(p.ksplit > 1) || (!d->res_f32 && !d->out_raw_f32), SAR_ERR_BAD_ARG, "sar_conv_tc_fwd: split-K has no residual stream");
   return SAR_OK;
 }
@@ -1304,9 +1387,18 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
   p.mn_tiles = p.m_tiles * p.n_tiles;
   p.dense_zstride = (long long)d->B * d->H * d->W * d->cout;
   p.epi_alias = ((long long)p.mn_tiles * p.ksplit <= sms) ? 1 : 0;
-  const size_t fixed = 1024 + 1024 + 640 + 3 * (size_t)d->cout * sizeof(float) + (p.epi_alias ? 0 : EPI_BYTES);   // align slack (x2) + barriers + epilogue vectors (+ staging)
-  const size_t budget = 227 * 1024 - fixed;
-  if (slab) {
+  // epilogue mode: the residual-block combinations get compile-time flags (bit 0 identity shortcut, bit 1 raw out)
+  int mode = -1;
+  if (d->out_act && !d->out_dense && d->act_kind == 0 && !p.split && !(d->res_f32 && d->out_raw) && !(d->res && d->out_raw_f32))
+    mode = ((d->res || d->res_f32) ? 1 : 0) | ((d->out_raw || d->out_raw_f32) ? 2 : 0);
+  if (mode == 1) mode = -1;                                            // (no compile-time instance of shortcut-without-raw)
+  static const bool epi16_ok = !(getenv("SAR_TC_EPI16") && getenv("SAR_TC_EPI16")[0] == '0');
+  static const bool epi16_thin_ok = !(getenv("SAR_TC_EPI16_THIN") && getenv("SAR_TC_EPI16_THIN")[0] == '0');
+  size_t fixed = 0, budget = 0;
+  auto plan_slab = [&](int epi_warps) -> bool {          // shared-memory plan of the slab kernel with this many epilogue warps
+    fixed = 1024 + 1024 + 640 + 3 * (size_t)d->cout * sizeof(float) + (p.epi_alias ? 0 : (size_t)epi_warps * EPI_WARP_BYTES);   // align slack (x2) + barriers + epilogue vectors (+ staging)
+    if (fixed + 4096 > 227 * 1024) return false;
+    budget = 227 * 1024 - fixed;
     const int n_ksteps = p.ntaps * p.chunks_main + p.chunks_sc;
     const size_t wres = (size_t)n_ksteps * 2 * sp.bplane_bytes;
     const size_t slab1 = 2 * (size_t)sp.slab_bytes;
@@ -1315,14 +1407,33 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
       sp.nring = 0;
       sp.nslab = (int)((budget - wres) / slab1);
     } else {
+      if (budget < 2 * slab1 + 2 * 2 * (size_t)sp.bplane_bytes) return false;
       sp.resident = 0;
       sp.nslab = 2;
       sp.nring = (int)((budget - 2 * slab1) / (2 * (size_t)sp.bplane_bytes));
       if (sp.nring > SL_MAX_RING) sp.nring = SL_MAX_RING;
-      if (sp.nring < 2) slab = false;
+      if (sp.nring < 2) return false;
     }
     if (sp.nslab > SL_MAX_SLABS) sp.nslab = SL_MAX_SLABS;
+    return true;
+  };
+  if (slab) {
+    // Thin tiles (BN <= 64) of a launch with several tiles per CTA: an epilogue item (tcgen05.ld, convert, split, stage,
+    // store) is ~3.5k cycles of mostly latency per warp while the tile's MMAs take 1-2k, so eight warps (two tiles in
+    // flight) leave the tensor pipe waiting for a free accumulator.  Sixteen warps drain four 32-wide tiles (out of
+    // four TMEM accumulator stages) or two 64-wide ones at a time, when the 128 KB of staging still leaves room for
+    // the slabs and the weights (SAR_TC_EPI16_THIN=0 disables).
+    bool thin16 = epi16_ok && epi16_thin_ok && mode >= 0 && !p.epi_alias && p.BN <= 64 && p.mn_tiles >= 2 * sms;
+    if (thin16 && plan_slab(16) && (sp.resident || sp.nring >= 4)) {
+      p.epi_warps = 16;
+      p.nacc_log2 = (p.BN == 32) ? 2 : 1;
+    } else {
+      thin16 = false;
+      slab = plan_slab(8);
+    }
   }
+  if (!slab) { fixed = 1024 + 1024 + 640 + 3 * (size_t)d->cout * sizeof(float) + (p.epi_alias ? 0 : EPI_BYTES); budget = 227 * 1024 - fixed; }
+  (void)budget;
 
   CUtensorMap mapA, mapS, mapWm, mapWs;
   int rc;
@@ -1342,24 +1453,20 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
   const int grid = tiles < sms ? tiles : sms;
   // 16 epilogue warps when every CTA owns ONE 128-wide tile: its 16 (quadrant, 32-column) items then drain in one
   // round instead of two -- the epilogue of such a launch is a tail nothing overlaps (SAR_TC_EPI16=0 disables)
-  static const bool epi16_ok = !(getenv("SAR_TC_EPI16") && getenv("SAR_TC_EPI16")[0] == '0');
-  auto threads_for = [&](size_t operand_bytes, int mode) {
-    return (epi16_ok && mode >= 0 && p.epi_alias && p.BN >= 128 && operand_bytes >= 2 * (size_t)EPI_BYTES) ? TC_THREADS_MAX : TC_THREADS;
+  auto threads_for = [&](size_t operand_bytes, int mode_) {
+    if (p.epi_warps == 16) return TC_THREADS_MAX;
+    return (epi16_ok && mode_ >= 0 && p.epi_alias && p.BN >= 128 && operand_bytes >= 2 * (size_t)EPI_BYTES) ? TC_THREADS_MAX : TC_THREADS;
   };
   if (slab) {
     const int nb = sp.resident ? (p.ntaps * p.chunks_main + p.chunks_sc) : sp.nring;
     size_t smem = fixed + (size_t)sp.nslab * 2 * sp.slab_bytes + (size_t)nb * 2 * sp.bplane_bytes;
     if (p.epi_alias && smem - fixed < (size_t)EPI_BYTES) smem = fixed + EPI_BYTES;    // aliased staging needs 64 KB of operand region
-    // epilogue mode: the residual-block combinations get compile-time flags (bit 0 identity shortcut, bit 1 raw out)
-    int mode = -1;
     auto launch = [&](auto kern) -> int {
       { const int arc = allow_max_smem(kern, "sar_conv_tc_fwd"); if (arc) return arc; }
       const int m_eff = (mode == 0 || mode == 2 || mode == 3) ? mode : -1;
       launch_k(kern, dim3(grid), dim3(threads_for(smem - fixed, m_eff)), smem, (cudaStream_t)stream, mapA, mapS, mapWm, mapWs, om, p, sp);
       return 0;
     };
-    if (d->out_act && !d->out_dense && d->act_kind == 0 && !p.split && !(d->res_f32 && d->out_raw) && !(d->res && d->out_raw_f32))
-      mode = ((d->res || d->res_f32) ? 1 : 0) | ((d->out_raw || d->out_raw_f32) ? 2 : 0);
     auto pick = [&](auto kc_tag, auto res_tag) -> int {
       constexpr int KCv = decltype(kc_tag)::value;
       constexpr bool RSv = decltype(res_tag)::value;
@@ -1404,6 +1511,10 @@ extern "C" int sar_conv_tc_chain_grid_fwd(const sar_tc_conv* descs, int n, void*
   static_assert(sizeof(ChainParams) < 32000, "ChainParams must fit the kernel parameter space");
   cp.n_phases = n;
   cp.flags = reinterpret_cast<int*>(workspace);
+  // SAR_CHAIN_PUB=0: the round-2a protocol (TMA stores, every epilogue warp waits for its stores and fences) -- A/B aid
+  static const bool use_pub = !(getenv("SAR_CHAIN_PUB") && getenv("SAR_CHAIN_PUB")[0] == '0');
+  cp.publisher = use_pub ? 1 : 0;
+  cp.dbg = reinterpret_cast<long long*>(descs->dbg);      // chain profiling: >= 148 * (8 + 32 * 8) int64 (scripts/chain_dbg.py)
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1457,6 +1568,14 @@ extern "C" int sar_conv_tc_chain_grid_fwd(const sar_tc_conv* descs, int n, void*
     fast_div((unsigned)p.P, &p.div_p_m, &p.div_p_sh);
     p.epi_alias = 0;
     p.dbg = nullptr;
+    {   // SAR_CHAIN_DBG_PHASE=<l>: epilogue_item stamps of CTA 0's first two items of layer l, behind the per-CTA table
+      static const int dbg_ph = getenv("SAR_CHAIN_DBG_PHASE") ? atoi(getenv("SAR_CHAIN_DBG_PHASE")) : -1;
+      if (cp.dbg && i == dbg_ph) {
+        const int tiles_l = m_tiles * (cout / BN), g = tiles_l < sms ? tiles_l : sms;
+        p.dbg = cp.dbg + (size_t)148 * CH_DBG_STRIDE;
+        p.dbg_it0 = (i * tiles_l + g - 1) / g;
+      }
+    }
     p.flag_done = cp.flags + (size_t)i * m_tiles;
     p.flag_dep = i > 0 ? cp.flags + (size_t)(i - 1) * m_tiles : nullptr;
     p.flag_need = 4 * (cout / 32);
@@ -1477,6 +1596,9 @@ extern "C" int sar_conv_tc_chain_grid_fwd(const sar_tc_conv* descs, int n, void*
     } else {
       P.mapS = P.mapA; P.mapWs = P.mapWm;
     }
+    // publisher protocol: generic stores (a bulk store's completion is only visible to the thread that issued it)
+    if (cp.publisher) p.tma_out = 0;
+    SAR_REQUIRE(!d->out_raw_f32 || !p.split, SAR_ERR_UNSUPPORTED, "sar_conv_tc_chain_fwd: out_raw_f32 needs unsplit plane outputs");
     if ((rc = fill_out_maps(d, p, P.mapA, P.om))) return rc;
   }
   const int tiles = g0.m_tiles * (cout / BN);
@@ -1490,10 +1612,10 @@ extern "C" int sar_conv_tc_chain_grid_fwd(const sar_tc_conv* descs, int n, void*
     // leave waiting CTAs resident and their producers unscheduled).  SAR_CHAIN_COOP=0: plain PDL launch (A/B aid).
     static const bool coop = !(getenv("SAR_CHAIN_COOP") && getenv("SAR_CHAIN_COOP")[0] == '0');
     int nblk = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, kern, SL_THREADS, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, kern, CH_THREADS, smem);
     if (nblk * sms < grid) { set_error("sar_conv_tc_chain_fwd: grid of %d CTAs cannot be co-resident (%d per SM x %d SMs)", grid, nblk, sms); return SAR_ERR_UNSUPPORTED; }
-    cudaError_t le = coop ? launch_k_coop(kern, dim3(grid), dim3(SL_THREADS), smem, (cudaStream_t)stream, cp)
-                          : launch_k(kern, dim3(grid), dim3(SL_THREADS), smem, (cudaStream_t)stream, cp);
+    cudaError_t le = coop ? launch_k_coop(kern, dim3(grid), dim3(CH_THREADS), smem, (cudaStream_t)stream, cp)
+                          : launch_k(kern, dim3(grid), dim3(CH_THREADS), smem, (cudaStream_t)stream, cp);
     if (le != cudaSuccess) { set_error("sar_conv_tc_chain_fwd: launch: %s", cudaGetErrorString(le)); return (int)le; }
     return 0;
   };

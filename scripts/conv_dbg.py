@@ -17,7 +17,7 @@ opts = StepOpts(no_chain=True)
 orig = tc.conv_desc
 dbgs = []
 def timed(*a, **k):
-    d = torch.zeros(256, dtype=torch.int64, device="cuda"); dbgs.append(d)
+    d = torch.zeros(512, dtype=torch.int64, device="cuda"); dbgs.append(d)
     return orig(*a, dbg=d, **k)
 rn.forward(xd, opts=opts); torch.cuda.synchronize()
 tc.conv_desc = timed
@@ -33,7 +33,7 @@ for li in layers:
     for it in range(2):
         for c in range(4):
             for q in range(4):
-                o = 64 + ((it * 4 + c) * 4 + q) * 4
+                o = 64 + ((it * 4 + c) * 4 + q) * 8
                 if d[o] == 0: continue
                 e = [d[o + j] - t0 for j in range(4)]
                 print("    item tile %d chunk %d quad %d: entered %6d  acc ready %6d  math done %6d (+%d)  finished %6d (+%d)" % (it, c, q, e[0], e[1], e[2], e[2]-e[1], e[3], e[3]-e[2]))
