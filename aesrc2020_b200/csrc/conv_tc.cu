@@ -744,6 +744,7 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       pdl_trigger();
       int sb = 0; uint32_t sphase = 0;        // slab ring
       int bs = 0; uint32_t bphase = 0;        // weight ring
+      int exp_s = 0, exp_w = 0;               // (SAR_TC_MMAMASK bits 3/4: traffic experiments, wrong results)
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
         const long long q0 = (long long)mt * TC_BM;
@@ -753,6 +754,9 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           const int kc = main ? p.kc_main : p.kc_sc;
           const int rows = main ? sp.slab_rows : TC_BM;
           mbar_wait(&sempty_bar[sb], sphase ^ 1);
+          if ((p.mma_mask & 16) && exp_s >= sp.nslab) {        // experiment: no slab traffic after the first ring fill
+            if (elect_one()) mbar_arrive(&sfull_bar[sb]);
+          } else
           if (elect_one()) {
             const uint32_t dst = smem_u32(slab_base + (size_t)sb * 2 * sp.slab_bytes);
             mbar_expect_tx(&sfull_bar[sb], (uint32_t)(2 * rows * kc * 2));
@@ -767,11 +771,15 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             }
           }
           __syncwarp();
+          ++exp_s;
           if (++sb == sp.nslab) { sb = 0; sphase ^= 1; }
           if (!sp.resident) {
             const CUtensorMap* wm = main ? &mapWm : &mapWs;
             for (int tap = 0; tap < (main ? p.ntaps : 1); ++tap) {
               mbar_wait(&bempty_bar[bs], bphase ^ 1);
+              if ((p.mma_mask & 8) && exp_w++ >= sp.nring) {   // experiment: no weight traffic after the first ring fill
+                if (elect_one()) mbar_arrive(&bfull_bar[bs]);
+              } else
               if (elect_one()) {
                 const uint32_t b_hi = smem_u32(b_base + (size_t)bs * 2 * sp.bplane_bytes);
                 mbar_expect_tx(&bfull_bar[bs], (uint32_t)(2 * BN * kc * 2));
@@ -1280,7 +1288,11 @@ static int fill_params(const sar_tc_conv* d, TcParams& p) {
   p.ntaps = d->ntaps;
   p.kc_main = pick_kc(d->a_ch);
   p.chunks_main = d->a_ch / p.kc_main;
+  // shortcut chunks never wider than the main chunks: the slab / weight-slot sizes follow the widest chunk, and a
+  // 64-wide shortcut chunk on a 32-channel layer (stage 1, block 1: 64-channel stem -> 32) doubled both, which pushed
+  // the layer off the resident-weights form (207 -> ~140 us at B=512)
   p.kc_sc = d->s ? pick_kc(d->s_ch) : 32;
+  if (p.kc_sc > p.kc_main) p.kc_sc = p.kc_main;
   p.chunks_sc = d->s ? d->s_ch / p.kc_sc : 0;
   p.sc_plane = d->s_plane;
   for (int t = 0; t < d->ntaps; ++t) {
@@ -1424,7 +1436,11 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
     // four TMEM accumulator stages) or two 64-wide ones at a time, when the 128 KB of staging still leaves room for
     // the slabs and the weights (SAR_TC_EPI16_THIN=0 disables).
     bool thin16 = epi16_ok && epi16_thin_ok && mode >= 0 && !p.epi_alias && p.BN <= 64 && p.mn_tiles >= 2 * sms;
-    if (thin16 && plan_slab(16) && (sp.resident || sp.nring >= 4)) {
+    // ... and the slab ring still runs a tile ahead: a tile of a projection layer takes chunks_main + chunks_sc slabs,
+    // and with fewer buffers than that + 1 the next tile's first slab waits for this tile's MMAs to retire (TMA
+    // latency exposed on every tile: 5.5k instead of 2.9k cycles per tile on stage 1's projection layer)
+    const int slabs_per_tile = p.chunks_main + p.chunks_sc;
+    if (thin16 && plan_slab(16) && (sp.resident || sp.nring >= 4) && sp.nslab >= (slabs_per_tile > 1 ? slabs_per_tile + 1 : 2)) {
       p.epi_warps = 16;
       p.nacc_log2 = (p.BN == 32) ? 2 : 1;
     } else {
