@@ -34,9 +34,7 @@
 namespace sar {
 
 constexpr int TC_BM = 128;            // output rows per tile (TMEM lanes)
-constexpr int TC_STAGES = 3;
-constexpr int TC_PLANE_BYTES = 16384; // 128 rows x 128 B (kc = 64) per operand plane
-constexpr int TC_STAGE_BYTES = 4 * TC_PLANE_BYTES;
+constexpr int TC_STAGES = 8;          // generic kernel: most ring stages (barrier slots); the launch picks p.stages <= this
 constexpr int TC_THREADS = 320;            // 8 epilogue warps + TMA producer + MMA issuer
 constexpr int TC_THREADS_MAX = 576;        // 16 epilogue warps: one warp per (quadrant, 32-column chunk) of a single 128-wide tile
 // Warp roles.  The SM's schedulers favour the HIGHEST warp id of a sub-partition (wid % 4), so the two
@@ -73,7 +71,8 @@ struct TcParams {
   int epi_alias;                         // every CTA owns ONE tile: the epilogue staging lives on top of the (then idle) operand region
   int nacc_log2;                         // TMEM accumulator stages = 1 << nacc_log2 (2; 4 in the slab kernel's 16-warp thin-tile form)
   int epi_warps;                         // slab kernel: epilogue warps the launch carries (8 or 16) -> staging bytes
-  int stages;                            // generic kernel: depth of the TMA ring (2 or 3)
+  int stages;                            // generic kernel: depth of the TMA ring (2..TC_STAGES: whatever shared memory holds)
+  int stage_bytes, a_plane_bytes;        // generic kernel: one ring stage = [A_hi | A_lo | B_hi ; B_lo], A planes a_plane_bytes apart
   int ksplit, ksteps_split, mn_tiles;    // generic kernel, split-K (1-tap GEMMs with a long K): tile = z * mn_tiles + (mt, nt)
   long long dense_zstride;               // elements between the fp32 partial outputs of consecutive K slices
   // chain kernel (several layers of one stage in ONE persistent launch, see conv_tc_chain_kernel)
@@ -472,7 +471,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   // [stages x 64 KB ring][epilogue staging 64 KB unless aliased onto the ring][barriers][bias | scale | shift]
   const int nepi = (int)(blockDim.x >> 5) - 2;          // epilogue warps (8, or 16 for a single wide tile per CTA)
   const int WARP_TMA = nepi, WARP_MMA = nepi + 1;
-  uint8_t* epi_own = smem + (size_t)p.stages * TC_STAGE_BYTES;
+  uint8_t* epi_own = smem + (size_t)p.stages * p.stage_bytes;
   uint8_t* epi_base = p.epi_alias ? smem : epi_own;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_own + (p.epi_alias ? 0 : EPI_BYTES));
   uint64_t* empty_bar = full_bar + TC_STAGES;
@@ -534,8 +533,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       for (int ks = 0; ks < n_ksteps; ++ks) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one()) {
-          uint8_t* st = smem + stage * TC_STAGE_BYTES;
-          const uint32_t a_hi = smem_u32(st), a_lo = a_hi + TC_PLANE_BYTES, b_hi = a_lo + TC_PLANE_BYTES, b_lo = b_hi + TC_PLANE_BYTES;
+          // stage = [A_hi | A_lo | B_hi ; B_lo]: the lo weight tile sits right behind the hi tile (one 2*BN-row operand)
+          uint8_t* st = smem + (size_t)stage * p.stage_bytes;
+          const uint32_t a_hi = smem_u32(st), a_lo = a_hi + (uint32_t)p.a_plane_bytes, b_hi = a_lo + (uint32_t)p.a_plane_bytes;
+          const uint32_t b_lo = b_hi + (uint32_t)(BN * (ks < n_main ? p.kc_main : p.kc_sc) * 2);
           if (ks < n_main) {
             const int tap = (ch0 + ks) / p.chunks_main, ch = (ch0 + ks) - tap * p.chunks_main;
             const int kc = p.kc_main;
@@ -565,6 +566,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
     // instruction descriptor: D=f32, A=B=f16, K-major both, N=BN, M=128
     const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    const uint32_t idesc_2n = (1u << 4) | ((uint32_t)(BN >> 2) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     int stage = 0; uint32_t phase = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -580,16 +582,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (elect_one()) {
           const int kc = (ks < n_main) ? p.kc_main : p.kc_sc;
           const int row_bytes = kc * 2;
-          uint8_t* st = smem + stage * TC_STAGE_BYTES;
-          const uint32_t a_hi = smem_u32(st), a_lo = a_hi + TC_PLANE_BYTES, b_hi = a_lo + TC_PLANE_BYTES, b_lo = b_hi + TC_PLANE_BYTES;
+          uint8_t* st = smem + (size_t)stage * p.stage_bytes;
+          const uint32_t a_hi = smem_u32(st), a_lo = a_hi + (uint32_t)p.a_plane_bytes, b_hi = a_lo + (uint32_t)p.a_plane_bytes;
           const uint64_t dah = make_desc(a_hi, row_bytes), dal = make_desc(a_lo, row_bytes);
-          const uint64_t dbh = make_desc(b_hi, row_bytes), dbl = make_desc(b_lo, row_bytes);
+          const uint64_t dbh = make_desc(b_hi, row_bytes);
           for (int kk = 0; kk < kc / 16; ++kk) {
             const uint64_t adv = (uint64_t)(kk * 2);       // 32 bytes per UMMA_K=16 halves, in 16-byte units
             const uint32_t first = (ks | kk) ? 1u : 0u;
-            umma_f16(acc0, dah + adv, dbh + adv, idesc, first);
-            umma_f16(acc1, dal + adv, dbh + adv, idesc, first);
-            umma_f16(acc1, dah + adv, dbl + adv, idesc, 1u);
+            umma_f16(acc0, dah + adv, dbh + adv, idesc_2n, first);     // [acc0 | acc1] (+)= A_hi x [B_hi ; B_lo]  (N = 2 BN)
+            umma_f16(acc1, dal + adv, dbh + adv, idesc, 1u);           // acc1 += A_lo x B_hi
           }
           umma_commit(&empty_bar[stage]);                  // frees the smem stage when these MMAs retire
           if (ks == n_ksteps - 1) umma_commit(&tfull_bar[as]);
@@ -1448,8 +1449,33 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
       slab = plan_slab(8);
     }
   }
-  if (!slab) { fixed = 1024 + 1024 + 640 + 3 * (size_t)d->cout * sizeof(float) + (p.epi_alias ? 0 : EPI_BYTES); budget = 227 * 1024 - fixed; }
   (void)budget;
+  size_t smem = 0;                                         // generic kernel: dynamic shared memory
+  if (!slab) {
+    // ring stage sized for this layer's chunk width and N tile (a 32-channel chunk needs a quarter of the 64 KB the
+    // first version reserved), as many stages as shared memory holds: the k-step loop of a strided conv / Dense is
+    // TMA-latency bound (2 stages: ~1.2k cycles per k-step), depth is what hides it.  Wide tiles (64-channel chunks,
+    // BN = 128: 64 KB per stage) would still get only 2 stages next to the epilogue staging: they run 32-channel
+    // chunks instead (twice the k-steps, 4-5 stages in flight).
+    const size_t other = 1024 + (p.epi_alias ? 0 : EPI_BYTES) + 256 + 3 * (size_t)d->cout * sizeof(float);
+    auto stages_for = [&](int kc) { return (int)((227 * 1024 - other) / (size_t)(2 * TC_BM * kc * 2 + 2 * p.BN * kc * 2)); };
+    if (p.kc_main == 64 && stages_for(64) < 4) {
+      p.kc_main = 32; p.chunks_main *= 2;
+      if (d->s) { p.kc_sc = 32; p.chunks_sc = d->s_ch / 32; }
+      if (p.ksplit > 1) p.ksteps_split = p.chunks_main / p.ksplit;
+    }
+    const int kcm = p.kc_main;                             // (kc_sc <= kc_main)
+    p.a_plane_bytes = TC_BM * kcm * 2;
+    p.stage_bytes = 2 * p.a_plane_bytes + 2 * p.BN * kcm * 2;
+    p.stages = stages_for(kcm);
+    if (p.stages > TC_STAGES) p.stages = TC_STAGES;
+    const int n_ksteps_tile = (p.ksplit > 1 ? p.ksteps_split : p.ntaps * p.chunks_main) + p.chunks_sc;
+    if (p.stages > n_ksteps_tile * 2) p.stages = n_ksteps_tile * 2;      // never more than two tiles' worth
+    if (p.epi_alias)                                       // aliased staging (64 KB) lives on the ring
+      while ((size_t)p.stages * p.stage_bytes < (size_t)EPI_BYTES) ++p.stages;
+    SAR_REQUIRE(p.stages >= 2 && p.stages <= TC_STAGES, SAR_ERR_UNSUPPORTED, "sar_conv_tc_fwd: shared-memory plan (stages=%d)", p.stages);
+    smem = other + (size_t)p.stages * p.stage_bytes;
+  }
 
   CUtensorMap mapA, mapS, mapWm, mapWs;
   int rc;
@@ -1498,8 +1524,6 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
     else lrc = sp.resident ? pick(std::integral_constant<int, 32>{}, std::true_type{}) : pick(std::integral_constant<int, 32>{}, std::false_type{});
     if (lrc) return lrc;
   } else {
-    p.stages = p.epi_alias ? 3 : 2;
-    const size_t smem = 1024 + (size_t)p.stages * TC_STAGE_BYTES + (p.epi_alias ? 0 : EPI_BYTES) + 256 + 3 * (size_t)d->cout * sizeof(float);
     { const int arc = allow_max_smem(conv_tc_kernel, "sar_conv_tc_fwd"); if (arc) return arc; }
     launch_k(conv_tc_kernel, dim3(grid), dim3(TC_THREADS), smem, (cudaStream_t)stream, mapA, mapS, mapWm, mapWs, om, p);
   }
