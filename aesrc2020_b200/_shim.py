@@ -74,6 +74,8 @@ SIGNATURES = {
     "sar_head_grad_fwd": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_f, c_f, c_f, c_f, c_f, c_fp, c_fp, c_fp, c_int, C.c_void_p]),
     "sar_adam_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_ll, c_f, c_f, c_f, c_f, c_f, C.c_void_p]),
     "sar_unit_norm_fwd": (c_int, [c_fp, c_int, c_int, C.c_void_p]),
+    "sar_vlad_train_fwd": (c_int, [c_fp] * 7 + [c_int] * 5 + [C.c_void_p]),
+    "sar_vlad_train_bwd": (c_int, [c_fp] * 7 + [c_int] * 5 + [C.c_void_p]),
     "sar_fbank_fwd": (c_int, [c_fp, c_ip, c_fp, c_fp, c_fp, c_int, c_int, c_int, C.c_void_p]),
     "sar_fbank_pcm16_fwd": (c_int, [c_ip, c_ip, c_fp, c_fp, c_fp, c_int, c_int, c_int, C.c_void_p]),
 }

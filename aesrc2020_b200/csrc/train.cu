@@ -10,6 +10,8 @@
 //   sar_head_grad_fwd     softmax + categorical cross-entropy of y_accent and the margin head (SphereFace / CosFace /
 //                         ArcFace / Dense softmax / Circle-Loss): per-sample losses and d loss / d logits, d loss / d cos
 //   sar_adam_fwd          Keras Adam update (+ l2 regulariser gradient, + unit_norm constraint helper)
+//   sar_vlad_train_fwd/bwd  NetVLAD / GhostVLAD pooling in training mode: soft assignments kept, gradients of the centers and of
+//                         the assignment scores (second slice: the pooling layer is trained together with the head)
 //
 // All fp32, CUDA cores, deterministic reduction orders.  This slice is about CORRECT training arithmetic behind the
 // C ABI (checked against float64 autograd, tests/test_gpu_train.py), not yet about speed: the contractions of the head are
@@ -273,6 +275,91 @@ static unsigned blocks_for(long long n, int bs, int cap = 4096) {
   return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
+// ------------------------------------------------------------------ NetVLAD / GhostVLAD in training mode (model.py:82-109, VLAD.py:26-49)
+// One CTA per utterance, everything fp32 on CUDA cores in fixed reduction orders (S <= 128 positions, K+G <= 128).
+//   forward : scores = x Wa + ba -> A = softmax over the K+G clusters (kept for the backward), asum[k] = sum_s A[s,k],
+//             R[k,:] = sum_s A[s,k] x[s,:] - asum[k] c[k,:] for the K real clusters (ghost rows are dropped, VLAD.py:44-45).
+//             The per-cluster K.l2_normalize (VLAD.py:47) is sar_l2norm_fwd on R viewed as (B*K, D).
+//   backward: gR = d loss / d R (from sar_l2norm_bwd).  gA[s,k] = gR[k,:] . (x[s,:] - c[k,:]) (0 for ghosts),
+//             g_scores = A * (gA - sum_k' A gA) (softmax), gc_part[b,k,:] = -asum[b,k] gR[b,k,:] (summed over b by
+//             sar_colsum_fwd); g_Wa = x^T g_scores and g_ba = colsum(g_scores) are the caller's sar_gemm_fwd / sar_colsum_fwd.
+__global__ void __launch_bounds__(256) vlad_train_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wa, const float* __restrict__ ba,
+                                                              const float* __restrict__ centers, float* __restrict__ A_out,
+                                                              float* __restrict__ R_out, float* __restrict__ asum_out, int S, int D, int K, int KG) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ float vsm[];
+  float* As = vsm;                 // [S][KG]
+  float* asum = vsm + S * KG;      // [KG]
+  const int b = blockIdx.x, t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const float* xb = x + (size_t)b * S * D;
+  for (int i = t; i < S * KG; i += 256) {                  // scores: consecutive threads -> consecutive clusters (Wa rows coalesced)
+    const int s_ = i / KG, k = i - s_ * KG;
+    float acc = ba[k];
+    for (int d = 0; d < D; ++d) acc = fmaf(xb[(size_t)s_ * D + d], wa[(size_t)d * KG + k], acc);
+    As[i] = acc;
+  }
+  __syncthreads();
+  for (int s_ = warp; s_ < S; s_ += 8) {                   // softmax of one row per warp (VLAD.py:33-35)
+    float mx = -INFINITY;
+    for (int k = lane; k < KG; k += 32) mx = fmaxf(mx, As[s_ * KG + k]);
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int k = lane; k < KG; k += 32) { const float e = expf(As[s_ * KG + k] - mx); As[s_ * KG + k] = e; sum += e; }
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.f / sum;
+    for (int k = lane; k < KG; k += 32) {
+      const float a = As[s_ * KG + k] * inv;
+      As[s_ * KG + k] = a;
+      A_out[((size_t)b * S + s_) * KG + k] = a;
+    }
+  }
+  __syncthreads();
+  for (int k = t; k < KG; k += 256) {
+    float a = 0.f;
+    for (int s_ = 0; s_ < S; ++s_) a += As[s_ * KG + k];
+    asum[k] = a;
+    if (k < K) asum_out[(size_t)b * K + k] = a;
+  }
+  __syncthreads();
+  for (int i = t; i < K * D; i += 256) {                   // residual sums of the K real clusters
+    const int k = i / D, d = i - k * D;
+    float acc = 0.f;
+    for (int s_ = 0; s_ < S; ++s_) acc = fmaf(As[s_ * KG + k], xb[(size_t)s_ * D + d], acc);
+    R_out[((size_t)b * K + k) * D + d] = acc - asum[k] * centers[(size_t)k * D + d];
+  }
+}
+
+__global__ void __launch_bounds__(256) vlad_train_bwd_kernel(const float* __restrict__ x, const float* __restrict__ A, const float* __restrict__ centers,
+                                                              const float* __restrict__ gR, const float* __restrict__ asum,
+                                                              float* __restrict__ g_scores, float* __restrict__ gc_part, int S, int D, int K, int KG) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ float vsm[];
+  float* gA = vsm;                 // [S][K]
+  const int b = blockIdx.x, t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const float* xb = x + (size_t)b * S * D;
+  const float* gRb = gR + (size_t)b * K * D;
+  for (int i = warp; i < S * K; i += 8) {                  // one (position, cluster) dot product per warp pass
+    const int s_ = i / K, k = i - s_ * K;
+    float acc = 0.f;
+    for (int d = lane; d < D; d += 32) acc = fmaf(gRb[(size_t)k * D + d], xb[(size_t)s_ * D + d] - centers[(size_t)k * D + d], acc);
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) gA[i] = acc;
+  }
+  __syncthreads();
+  for (int s_ = warp; s_ < S; s_ += 8) {                   // softmax backward of one row per warp
+    const float* Ar = A + ((size_t)b * S + s_) * KG;
+    float dot = 0.f;
+    for (int k = lane; k < K; k += 32) dot = fmaf(Ar[k], gA[s_ * K + k], dot);
+    for (int o = 16; o; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    for (int k = lane; k < KG; k += 32)
+      g_scores[((size_t)b * S + s_) * KG + k] = Ar[k] * ((k < K ? gA[s_ * K + k] : 0.f) - dot);
+  }
+  for (int i = t; i < K * D; i += 256)
+    gc_part[(size_t)b * K * D + i] = -asum[(size_t)b * K + i / D] * gRb[i];
+}
+
 }  // namespace sar
 
 extern "C" {
@@ -371,6 +458,30 @@ int sar_unit_norm_fwd(float* w, int D, int n, void* stream) {
   SAR_REQUIRE(w && D > 0 && n > 0, SAR_ERR_BAD_ARG, "sar_unit_norm_fwd: bad argument");
   launch_k(unit_norm_kernel, dim3((n + 63) / 64), dim3(64), 0, (cudaStream_t)stream, w, D, n);
   return check_launch("sar_unit_norm_fwd");
+}
+
+int sar_vlad_train_fwd(const float* x, const float* w_assign, const float* b_assign, const float* centers, float* A, float* R,
+                       float* asum, int B, int S, int D, int K, int G, void* stream) {
+  using namespace sar;
+  SAR_REQUIRE(x && w_assign && b_assign && centers && A && R && asum, SAR_ERR_BAD_ARG, "sar_vlad_train_fwd: null pointer");
+  SAR_REQUIRE(B > 0 && S > 0 && S <= 128 && D > 0 && K > 0 && G >= 0 && K + G <= 128, SAR_ERR_UNSUPPORTED,
+              "sar_vlad_train_fwd: need S <= 128 and K + G <= 128 (S=%d K=%d G=%d)", S, K, G);
+  const size_t smem = ((size_t)S * (K + G) + (K + G)) * sizeof(float);
+  { const int arc = allow_max_smem(vlad_train_fwd_kernel, "sar_vlad_train_fwd"); if (arc) return arc; }
+  launch_k(vlad_train_fwd_kernel, dim3(B), dim3(256), smem, (cudaStream_t)stream, x, w_assign, b_assign, centers, A, R, asum, S, D, K, K + G);
+  return check_launch("sar_vlad_train_fwd");
+}
+
+int sar_vlad_train_bwd(const float* x, const float* A, const float* centers, const float* gR, const float* asum, float* g_scores,
+                       float* gc_part, int B, int S, int D, int K, int G, void* stream) {
+  using namespace sar;
+  SAR_REQUIRE(x && A && centers && gR && asum && g_scores && gc_part, SAR_ERR_BAD_ARG, "sar_vlad_train_bwd: null pointer");
+  SAR_REQUIRE(B > 0 && S > 0 && S <= 128 && D > 0 && K > 0 && G >= 0 && K + G <= 128, SAR_ERR_UNSUPPORTED,
+              "sar_vlad_train_bwd: need S <= 128 and K + G <= 128 (S=%d K=%d G=%d)", S, K, G);
+  const size_t smem = (size_t)S * K * sizeof(float);
+  { const int arc = allow_max_smem(vlad_train_bwd_kernel, "sar_vlad_train_bwd"); if (arc) return arc; }
+  launch_k(vlad_train_bwd_kernel, dim3(B), dim3(256), smem, (cudaStream_t)stream, x, A, centers, gR, asum, g_scores, gc_part, S, D, K, K + G);
+  return check_launch("sar_vlad_train_bwd");
 }
 
 }  // extern "C"

@@ -10,8 +10,13 @@ all-reduced (mean) over the replicas -- the path's first bandwidth-relevant coll
 The encoder in front (ResNet, Bi-GRU, AR_DS, VLAD) is the frozen inference engine and supplies `integ`.
 
 `HeadTrainer(model).train_on_batch(x)` mirrors Keras' `train_on_batch`: returns the weighted total and the per-output
-losses; `fit_generator(generator, steps_per_epoch, epochs)` loops it over utils.data_generator batches.  Not built yet:
-gradients of the encoder kernels (convolutions, Bi-GRU, CTC), i.e. end-to-end training.
+losses; `fit_generator(generator, steps_per_epoch, epochs)` loops it over utils.data_generator batches.
+
+Second slice, `HeadTrainer(model, train_pool=True)`: the NetVLAD / GhostVLAD pooling layer (model.py:82-109, VLAD.py:26-49)
+is trained too -- the frozen encoder ends at AR_DS_LN, `sar_vlad_train_fwd` keeps the soft assignments, and the backward
+(`sar_l2norm_bwd` per cluster, `sar_vlad_train_bwd`, two contractions) yields the gradients of the centers and of the
+assignment Conv2D (kernel, bias; l2(1e-4) regularisers).  Not built yet: gradients of the encoder kernels (convolutions,
+Bi-GRU, LayerNorm, CTC), i.e. end-to-end training.
 """
 from __future__ import annotations
 
@@ -120,6 +125,29 @@ def head_grad(z_acc, c_disc, onehot, head_kind, margin, w_acc, w_disc, s=ops.FAC
     return g_acc, g_disc, losses
 
 
+def vlad_train_fwd(x, w_assign, b_assign, centers, K: int, G: int):
+    """x (B,S,D) -> soft assignments A (B,S,K+G), un-normalised residual sums R (B,K,D), asum (B,K)."""
+    B, S, D = x.shape
+    A = torch.empty((B, S, K + G), device=x.device, dtype=torch.float32)
+    R = torch.empty((B, K, D), device=x.device, dtype=torch.float32)
+    asum = torch.empty((B, K), device=x.device, dtype=torch.float32)
+    check(_shim.lib().sar_vlad_train_fwd(ptr(x), ptr(w_assign), ptr(b_assign), ptr(centers), ptr(A), ptr(R), ptr(asum), B, S, D, K, G,
+                                         stream_ptr()), "sar_vlad_train_fwd")
+    ops._count(1)
+    return A, R, asum
+
+
+def vlad_train_bwd(x, A, centers, gR, asum, K: int, G: int):
+    """-> g_scores (B,S,K+G) = d loss / d assignment scores, gc_part (B,K,D) (sum over B = gradient of the K real centers)."""
+    B, S, D = x.shape
+    g_scores = torch.empty((B, S, K + G), device=x.device, dtype=torch.float32)
+    gc_part = torch.empty((B, K, D), device=x.device, dtype=torch.float32)
+    check(_shim.lib().sar_vlad_train_bwd(ptr(x), ptr(A), ptr(centers), ptr(gR), ptr(asum), ptr(g_scores), ptr(gc_part), B, S, D, K, G,
+                                         stream_ptr()), "sar_vlad_train_bwd")
+    ops._count(1)
+    return g_scores, gc_part
+
+
 def adam_step(p, g, m, v, lr_t, l2=0.0):
     check(_shim.lib().sar_adam_fwd(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), float(lr_t), ADAM_B1, ADAM_B2, ADAM_EPS, float(l2),
                                    stream_ptr()), "sar_adam_fwd")
@@ -141,11 +169,16 @@ def adam_lr_t(lr: float, iterations: int) -> float:
 class HeadTrainer:
     """Fine-tunes the accent head of a SARModel on the device (module docstring)."""
 
-    def __init__(self, model, lr: float = 0.01, group=None):
+    def __init__(self, model, lr: float = 0.01, group=None, train_pool: bool = False):
+        """train_pool: also train the NetVLAD / GhostVLAD pooling layer (assignment Conv2D + centers, model.py:82-109):
+        the frozen encoder then ends at AR_DS_LN and the step differentiates vlad() as well (second slice)."""
         cfg = model.config
         if not cfg.ar_enable:
             raise ValueError("HeadTrainer needs ar_enable=True")
+        if train_pool and cfg.mto not in ("vlad", "gvlad"):
+            raise ValueError("train_pool needs mto='vlad' or 'gvlad' (got %r)" % cfg.mto)
         self.model, self.cfg, self.lr, self.group = model, cfg, float(lr), group
+        self.train_pool = bool(train_pool)
         self.iterations = 0
         self.head_kind = cfg.metric_loss if cfg.disc_enable else None
         self.disc_key = None
@@ -153,6 +186,12 @@ class HeadTrainer:
             self.disc_key = "y_disc/W" if cfg.metric_loss in ("sphereface", "cosface", "arcface") else "y_disc/kernel"
         self.keys: List[str] = list(TRAINABLE) + ([self.disc_key] if self.disc_key else [])
         self.l2 = set(L2_KEYS) | ({"y_disc/kernel"} if (cfg.disc_enable and cfg.metric_loss == "softmax") else set())
+        self.pool_keys: List[str] = []
+        if self.train_pool:
+            pre = cfg.mto
+            self.pool_keys = [pre + "_center_assignment/kernel", pre + "_center_assignment/bias", pre + "_pool/centers"]
+            self.keys += self.pool_keys
+            self.l2 |= set(self.pool_keys[:2])           # l2(1e-4) on the assignment kernel and bias; none on the centers
         lw = cfg.loss_weights()
         self.w_acc, self.w_disc = float(lw.get("y_accent", 0.0)), float(lw.get("y_disc", 0.0))
         dev = torch.device(model.device)
@@ -163,15 +202,25 @@ class HeadTrainer:
         self.v = {k: torch.zeros_like(self.p[k]) for k in self.keys}
         self.last_grads: Dict[str, torch.Tensor] = {}
 
-    # ---- frozen encoder: x_data -> integ (B, K*D | D | 2u)
+    # ---- frozen encoder: x_data -> integ (B, K*D | D | 2u), or (train_pool) the descriptors (B,S,D) in front of vlad()
     def encode(self, x) -> torch.Tensor:
         out = self.model.forward_device(x, want_intermediates=True, graph=False)
-        return out["integration"].contiguous()
+        return out["ar_ds" if self.train_pool else "integration"].contiguous()
 
-    # ---- one step on (integ, onehot) device tensors
+    # ---- one step on (integ | descriptors, onehot) device tensors
     def step_on_features(self, integ: torch.Tensor, onehot: torch.Tensor) -> Dict[str, float]:
         p, cfg = self.p, self.cfg
         B = integ.shape[0]
+        pool = None
+        if self.train_pool:                      # vlad() in training mode: integ = l2norm_k(A^T x - (sum A) c), flattened
+            feat = integ
+            _, S, D = feat.shape
+            K, G = cfg.vlad_clusters, (cfg.ghost_clusters if cfg.mto == "gvlad" else 0)
+            kw_, kb_, kc_ = self.pool_keys
+            A, R, asum = vlad_train_fwd(feat, p[kw_].view(D, K + G), p[kb_], p[kc_], K, G)
+            V, rinv = l2norm_fwd(R.view(B * K, D), 1)
+            integ = V.view(B, K * D)
+            pool = (feat, A, asum, V, rinv, S, D, K, G)
         # forward, training mode
         x1, m1, i1 = bn_train_fwd(integ, p["AR_BN1/gamma"], p["AR_BN1/beta"], p["AR_BN1/moving_mean"], p["AR_BN1/moving_variance"])
         e0 = bias_act(gemm(x1, p["AR_EMBEDDING/kernel"]), p["AR_EMBEDDING/bias"])
@@ -211,7 +260,17 @@ class HeadTrainer:
         g_e0, g["AR_BN2/gamma"], g["AR_BN2/beta"] = bn_train_bwd(e0, g_e, p["AR_BN2/gamma"], m2, i2)
         g["AR_EMBEDDING/kernel"], g["AR_EMBEDDING/bias"] = gemm(x1, g_e0, ta=True), colsum(g_e0)
         g_x1 = gemm(g_e0, p["AR_EMBEDDING/kernel"], tb=True)
-        _, g["AR_BN1/gamma"], g["AR_BN1/beta"] = bn_train_bwd(integ, g_x1, p["AR_BN1/gamma"], m1, i1, want_dx=False)
+        g_integ, g["AR_BN1/gamma"], g["AR_BN1/beta"] = bn_train_bwd(integ, g_x1, p["AR_BN1/gamma"], m1, i1, want_dx=pool is not None)
+        if pool is not None:
+            feat, A, asum, V, rinv, S, D, K, G = pool
+            kw_, kb_, kc_ = self.pool_keys
+            gR = l2norm_bwd(V, rinv, g_integ.view(B * K, D), 1)                       # (B*K, D) = d loss / d R
+            g_scores, gc_part = vlad_train_bwd(feat, A, p[kc_], gR, asum, K, G)
+            g[kw_] = gemm(feat.view(B * S, D), g_scores.view(B * S, K + G), ta=True).view_as(p[kw_])
+            g[kb_] = colsum(g_scores.view(B * S, K + G))
+            gc = torch.zeros_like(p[kc_])                                             # ghost centers: no gradient
+            gc[:K] = colsum(gc_part.view(B, K * D)).view(K, D)
+            g[kc_] = gc
         self._all_reduce(g)
         self.last_grads = g
         # Adam (the l2 regulariser's gradient 2 * 1e-4 * w is added inside the kernel), then the kernel constraint

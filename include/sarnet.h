@@ -323,6 +323,18 @@ int sar_adam_fwd(float* p, const float* g, float* m, float* v, long long n, floa
                  void* stream);
 /* keras.constraints.unit_norm(axis=0) on W (D, n): the Circle-Loss head's kernel constraint (model.py:163). */
 int sar_unit_norm_fwd(float* w, int D, int n, void* stream);
+/* NetVLAD / GhostVLAD pooling in TRAINING mode (model.py:82-109: the 1x1 assignment Conv2D with l2(1e-4) kernel / bias
+ * regularisers; VLAD.py:26-49: softmax over the K+G clusters, residual sums, ghost rows dropped).  x (B,S,D) the frozen
+ * descriptors (AR_DS_LN output), w_assign (D,K+G), b_assign (K+G), centers (K+G,D).  Forward: A (B,S,K+G) soft assignments
+ * (kept for the backward), asum (B,K) = sum_s A, R (B,K,D) = sum_s A[s,k] x[s,:] - asum[k] c[k,:]; the per-cluster
+ * K.l2_normalize (VLAD.py:47) is sar_l2norm_fwd on R viewed as (B*K, D).  Backward, from gR = d loss / d R (sar_l2norm_bwd):
+ * g_scores (B,S,K+G) = d loss / d scores (softmax chained in; g_w_assign = x^T g_scores via sar_gemm_fwd, g_b_assign =
+ * sar_colsum_fwd(g_scores)) and gc_part (B,K,D) = -asum[b,k] gR[b,k,:], whose sum over b (sar_colsum_fwd on (B, K*D)) is the
+ * gradient of the K real centers (ghost centers have none).  S <= 128, K+G <= 128. */
+int sar_vlad_train_fwd(const float* x, const float* w_assign, const float* b_assign, const float* centers, float* A, float* R,
+                       float* asum, int B, int S, int D, int K, int G, void* stream);
+int sar_vlad_train_bwd(const float* x, const float* A, const float* centers, const float* gR, const float* asum, float* g_scores,
+                       float* gc_part, int B, int S, int D, int K, int G, void* stream);
 
 /* ---- feature front-end ------------------------------------------------------------- */
 

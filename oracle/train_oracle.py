@@ -82,6 +82,29 @@ def head_loss(p: Dict[str, torch.Tensor], integ: torch.Tensor, onehot: torch.Ten
     return total + reg, parts
 
 
+# ---- second slice: the NetVLAD / GhostVLAD pooling layer is trained together with the head (frozen encoder below it)
+def pool_keys(mto: str):
+    """Trainable weights of vlad() (model.py:82-109): the 1x1 assignment Conv2D and VladPooling's centers (VLAD.py:17-20)."""
+    return [mto + "_center_assignment/kernel", mto + "_center_assignment/bias", mto + "_pool/centers"]
+
+
+def pool_l2_keys(mto: str):
+    # kernel_regularizer = bias_regularizer = l2(1e-4) on the assignment Conv2D (model.py:87-95); the centers carry none
+    return [mto + "_center_assignment/kernel", mto + "_center_assignment/bias"]
+
+
+def pooled_head_loss(p: Dict[str, torch.Tensor], feat: torch.Tensor, onehot: torch.Tensor, *, mto: str, vlad_clusters: int,
+                     ghost_clusters: int, **kw):
+    """feat (B,S,D) = AR_DS_LN output (frozen encoder) -> vlad() -> the head of head_loss, with the pooling layer's
+    regularisers added."""
+    integ = O.integration(feat, p, feat.shape[-1], mto, vlad_clusters, ghost_clusters)       # model.py:118-139
+    total, parts = head_loss(p, integ, onehot, **kw)
+    reg = sum(L2_REG * (p[k] ** 2).sum() for k in pool_l2_keys(mto))
+    parts["reg"] = parts["reg"] + reg
+    parts["integration"] = integ
+    return total + reg, parts
+
+
 def adam_update(p, g, m, v, iterations: int, lr: float):
     """One Keras-2.2.4 Adam update of a tensor; returns (p, m, v)."""
     lr_t = lr * (1.0 / (1.0 + ADAM_DECAY * iterations))
@@ -93,14 +116,17 @@ def adam_update(p, g, m, v, iterations: int, lr: float):
 
 
 def train_step(params: Dict[str, np.ndarray], state: Dict[str, np.ndarray], integ, onehot, *, lr: float, iterations: int,
-               disc_enable: bool, metric_loss: str, margin: float, w_accent: float, w_disc: float
+               disc_enable: bool, metric_loss: str, margin: float, w_accent: float, w_disc: float, pool: Dict = None
                ) -> Tuple[Dict[str, np.ndarray], Dict[str, np.ndarray], Dict[str, float], Dict[str, np.ndarray]]:
     """params: canonical weights (the trainable ones are updated); state: Adam moments `m/<key>`, `v/<key>`.
+    `pool` = dict(mto=, vlad_clusters=, ghost_clusters=): `integ` is then the (B,S,D) descriptor tensor in front of
+    vlad() and the pooling layer's weights are trained too (pooled_head_loss).
     Returns (new params incl. the BN moving statistics, new state, losses, gradients)."""
-    keys = trainable_keys(disc_enable, metric_loss)
+    keys = trainable_keys(disc_enable, metric_loss) + (pool_keys(pool["mto"]) if pool else [])
     p = {k: torch.tensor(np.asarray(v, np.float64), requires_grad=(k in keys)) for k, v in params.items()}
-    total, parts = head_loss(p, torch.as_tensor(np.asarray(integ, np.float64)), torch.as_tensor(np.asarray(onehot, np.float64)),
-                             disc_enable=disc_enable, metric_loss=metric_loss, margin=margin, w_accent=w_accent, w_disc=w_disc)
+    kw = dict(disc_enable=disc_enable, metric_loss=metric_loss, margin=margin, w_accent=w_accent, w_disc=w_disc)
+    x_in, y_in = torch.as_tensor(np.asarray(integ, np.float64)), torch.as_tensor(np.asarray(onehot, np.float64))
+    total, parts = pooled_head_loss(p, x_in, y_in, **pool, **kw) if pool else head_loss(p, x_in, y_in, **kw)
     grads = torch.autograd.grad(total, [p[k] for k in keys])
     new_p = {k: np.asarray(v, np.float64).copy() for k, v in params.items()}
     new_s = dict(state)

@@ -171,3 +171,93 @@ def test_train_on_batch_lowers_the_loss_through_the_frozen_encoder(cuda_device):
     assert not np.allclose(before, after)
     lab = np.argmax(x["x_accent"], -1)
     assert np.mean(np.argmax(after, -1) == lab) >= np.mean(np.argmax(before, -1) == lab)
+
+
+@pytest.mark.parametrize("mto,G", [("gvlad", 2), ("vlad", 0)])
+def test_vlad_training_kernels_match_autograd(cuda_device, mto, G):
+    """sar_vlad_train_fwd / sar_vlad_train_bwd (+ the per-cluster l2norm) vs torch autograd on oracle.vlad (float64)."""
+    from aesrc2020_b200 import training as T
+    from oracle import sarnet_oracle as O
+    rng = np.random.RandomState(5 + G)
+    B, S, D, K = 6, 13, 256, 8
+    x = rng.randn(B, S, D) * 0.7
+    wa = rng.randn(D, K + G) * 0.1
+    ba = rng.randn(K + G) * 0.1
+    c = rng.randn(K + G, D) * 0.5
+    u = rng.randn(B, K * D)
+    p = {mto + "_center_assignment/kernel": torch.tensor(wa.reshape(1, 1, D, K + G), requires_grad=True),
+         mto + "_center_assignment/bias": torch.tensor(ba, requires_grad=True),
+         mto + "_pool/centers": torch.tensor(c, requires_grad=True)}
+    want = O.integration(torch.as_tensor(x), p, D, mto, K, G)
+    (want * torch.as_tensor(u)).sum().backward()
+    xd, cd = dev(x), dev(c)
+    A, R, asum = T.vlad_train_fwd(xd, dev(wa), dev(ba), cd, K, G)
+    assert abs(float(A.sum()) - B * S) < 1e-3 and norm_err(asum, A[:, :, :K].sum(1)) < 1e-6
+    V, rinv = T.l2norm_fwd(R.view(B * K, D), 1)
+    assert norm_err(V.view(B, K * D), want.detach()) < 2e-6
+    gR = T.l2norm_bwd(V, rinv, dev(u).view(B * K, D), 1)
+    g_scores, gc_part = T.vlad_train_bwd(xd, A, cd, gR, asum, K, G)
+    g_wa = T.gemm(xd.view(B * S, D), g_scores.view(B * S, K + G), ta=True)
+    g_ba = T.colsum(g_scores.view(B * S, K + G))
+    g_c = T.colsum(gc_part.view(B, K * D)).view(K, D)
+    assert norm_err(g_wa, p[mto + "_center_assignment/kernel"].grad.reshape(D, K + G)) < 2e-5
+    assert norm_err(g_ba, p[mto + "_center_assignment/bias"].grad) < 2e-5
+    assert norm_err(g_c, p[mto + "_pool/centers"].grad[:K]) < 2e-5
+    assert float(p[mto + "_pool/centers"].grad[K:].abs().max()) == 0.0 if G else True
+
+
+def test_head_trainer_with_pooling_layer_matches_the_oracle(cuda_device):
+    """Second slice: HeadTrainer(train_pool=True).step_on_features on AR_DS_LN descriptors vs train_oracle.train_step(pool=...):
+    losses, every gradient (head + assignment Conv2D + centers) and the parameters after two Adam steps."""
+    from aesrc2020_b200 import model as mdl, training as T
+    K, G, Dh = 8, 2, 256
+    model, _ = mdl.SAR_Net((200, 80, 1), ctc_enable=True, disc_enable=True, res_type="res34", res_filters=32, mto="gvlad",
+                           vlad_clusters=K, ghost_clusters=G, metric_loss="arcface", margin=0.3)
+    params = _params("arcface", K * Dh, seed=9)
+    rng = np.random.RandomState(21)
+    params["gvlad_center_assignment/kernel"] = (rng.randn(1, 1, Dh, K + G) * 0.1).astype(np.float32).astype(np.float64)
+    params["gvlad_center_assignment/bias"] = (rng.randn(K + G) * 0.1).astype(np.float32).astype(np.float64)
+    params["gvlad_pool/centers"] = (rng.randn(K + G, Dh) * 0.3).astype(np.float32).astype(np.float64)
+    for k, v in params.items():
+        model.weights[k] = v.astype(np.float32)
+    tr = T.HeadTrainer(model, lr=0.01, train_pool=True)
+    assert set(TO.pool_keys("gvlad")) <= set(tr.keys)
+    B, S = 16, 12
+    lab = rng.randint(0, 8, B)
+    pool = dict(mto="gvlad", vlad_clusters=K, ghost_clusters=G)
+    state, p_or, p_prev = {}, dict(params), dict(params)
+    l2k = set(TO.l2_keys(True, "arcface")) | set(TO.pool_l2_keys("gvlad"))
+    for it in range(2):
+        feat = (rng.randn(B, S, Dh) * 0.5 + (np.eye(8)[lab] @ rng.randn(8, Dh))[:, None, :] * 0.3).astype(np.float32)
+        onehot = np.eye(8, dtype=np.float32)[lab]
+        p_or, state, l_or, g_or = TO.train_step(p_or, state, feat, onehot, lr=0.01, iterations=it, disc_enable=True,
+                                                metric_loss="arcface", margin=0.3, w_accent=tr.w_acc, w_disc=tr.w_disc, pool=pool)
+        got = tr.step_on_features(dev(feat), dev(onehot))
+        assert abs(got["loss_accent"] - l_or["loss_accent"]) < 1e-4 * max(1, abs(l_or["loss_accent"]))
+        assert abs(got["loss_disc"] - l_or["loss_disc"]) < 2e-4 * max(1, abs(l_or["loss_disc"]))
+        for k in tr.keys:
+            if k in ("AR_BN1/beta", "AR_EMBEDDING/bias"):
+                continue                                   # exactly-zero data gradients (see the test above)
+            want = g_or[k] - (2 * TO.L2_REG * p_prev[k] if k in l2k else 0.0)
+            got_k = tr.last_grads[k].cpu().numpy().astype(np.float64)
+            err = float(np.max(np.abs(got_k - want)) / max(np.max(np.abs(want)), 1e-6))
+            assert err < 5e-4, (it, k, err)
+        p_prev = {k: v.copy() for k, v in p_or.items()}
+        for k in TO.pool_keys("gvlad") + ["AR_EMBEDDING/kernel", "y_disc/W"]:
+            assert norm_err(tr.p[k], p_or[k]) < 2e-3, (it, k)
+    tr.sync_to_model()
+    assert model.weights["gvlad_center_assignment/kernel"].shape == (1, 1, Dh, K + G)
+
+
+def test_train_on_batch_with_pooling_layer_lowers_the_loss(cuda_device):
+    from aesrc2020_b200 import model as mdl, training as T, utils as us
+    model, _ = mdl.SAR_Net((200, 80, 1), disc_enable=True, res_type="res34", res_filters=32, mto="gvlad", vlad_clusters=8,
+                           ghost_clusters=2, metric_loss="arcface", margin=0.3)
+    x, y = us.synthetic_batch(model.config, 16, seed=3)
+    c0 = model.weights["gvlad_pool/centers"].copy()
+    tr = T.HeadTrainer(model, lr=0.02, train_pool=True)
+    hist = [tr.train_on_batch(x, y)["loss"] for _ in range(25)]
+    assert hist[-1] < 0.7 * hist[0], hist
+    tr.sync_to_model()
+    assert not np.allclose(c0[:8], model.weights["gvlad_pool/centers"][:8])
+    assert np.array_equal(c0[8:], model.weights["gvlad_pool/centers"][8:])       # ghost centers never move

@@ -103,3 +103,37 @@ def test_train_step_reduces_the_loss_and_updates_state(kind, margin):
     assert not np.allclose(p["AR_BN1/moving_mean"], params["AR_BN1/moving_mean"])
     if kind == "circleloss":
         assert np.allclose(np.sqrt((p["y_disc/kernel"] ** 2).sum(0)), 1.0, atol=1e-6)    # unit_norm constraint
+
+
+@pytest.mark.parametrize("mto,G", [("gvlad", 2), ("vlad", 0)])
+def test_pooled_gradients_match_finite_differences(mto, G):
+    """Second slice: vlad() (model.py:82-109, VLAD.py:26-49) in front of the head -- autograd gradients of the assignment
+    Conv2D, its bias and the centers vs central finite differences; ghost centers get exactly zero."""
+    B, S, Dd, K, n = 5, 7, 6, 4, 8
+    rng = np.random.RandomState(12)
+    params = _params("arcface", D=K * Dd)
+    params[mto + "_center_assignment/kernel"] = rng.randn(1, 1, Dd, K + G) * 0.5
+    params[mto + "_center_assignment/bias"] = rng.randn(K + G) * 0.1
+    params[mto + "_pool/centers"] = rng.randn(K + G, Dd) * 0.5
+    feat = rng.randn(B, S, Dd)
+    onehot = np.eye(n)[rng.randint(0, n, B)]
+    kw = dict(disc_enable=True, metric_loss="arcface", margin=0.3, w_accent=0.01, w_disc=0.6)
+    pool = dict(mto=mto, vlad_clusters=K, ghost_clusters=G)
+    _, state, losses, grads = TO.train_step(params, {}, feat, onehot, lr=0.01, iterations=0, pool=pool, **kw)
+    assert set(TO.pool_keys(mto)) <= set(grads) and "m/" + mto + "_pool/centers" in state
+
+    def loss_of(pp):
+        t = {k: torch.as_tensor(v) for k, v in pp.items()}
+        return float(TO.pooled_head_loss(t, torch.as_tensor(feat), torch.as_tensor(onehot), **pool, **kw)[0])
+    assert abs(loss_of(params) - losses["total"]) < 1e-12
+    for k in TO.pool_keys(mto) + ["AR_EMBEDDING/kernel", "AR_BN1/gamma"]:
+        g = grads[k]
+        for _ in range(5):
+            i = tuple(rng.randint(0, s_) for s_ in g.shape)
+            h = 1e-6
+            pp, pm = {q: v.copy() for q, v in params.items()}, {q: v.copy() for q, v in params.items()}
+            pp[k][i] += h; pm[k][i] -= h
+            fd = (loss_of(pp) - loss_of(pm)) / (2 * h)
+            assert abs(fd - g[i]) <= 2e-6 * max(1.0, abs(fd)) + 2e-8, (k, i, fd, g[i])
+    if G:
+        assert np.all(grads[mto + "_pool/centers"][K:] == 0.0)                 # VLAD.py:44-45 drops the ghost rows
