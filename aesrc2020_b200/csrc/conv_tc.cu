@@ -81,6 +81,7 @@ struct TcParams {
   int flag_need;                         // items per M tile = 4 * Cout / 32
   int epi_mode;                          // epilogue mode of this layer (-1, 0, 2, 3)
   int tma_out;                           // plane outputs of an unsplit map leave through TMA stores (see epilogue_item)
+  int pair;                              // conv_tc_pair_kernel: the accumulator-drained arrivals go to the LEADER CTA's barrier
   // The residual stream between the blocks of a stage as ONE fp32 plane [R][Cout] (flat-pad rows) instead of hi/lo
   // planes: it is only ever added in an epilogue (never an MMA operand), so the hi/lo split on write and the re-join
   // on read -- 16 of the ~18 instructions per element a conv2 epilogue spends on it -- are dropped.
@@ -285,7 +286,10 @@ __device__ __forceinline__ void epilogue_item(const TcParams& p, const OutMaps& 
     if (g == 3) {                                    // the chunk has left TMEM: hand the accumulator back
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) {
+        if (p.pair) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[as]), 0));   // the pair's MMA issuer is CTA 0
+        else mbar_arrive(&tempty_bar[as]);
+      }
     }
     const uint32_t vec = s_bias_u + (uint32_t)((CHAIN ? 0 : n0 + c0) + 8 * g) * 4u;   // bias | scale | shift, vstride bytes apart
     float v[8];
@@ -908,6 +912,212 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) { p.dbg[62] = t_entry; p.dbg[63] = clock64(); }
 }
 
+// ------------------------------------------------------------------ the pair kernel (3x3 stride 1, cta_group::2)
+// conv_tc_slab_kernel's non-resident form on CTA PAIRS: a cluster of two CTAs (one TPC) owns two vertically adjacent
+// M tiles (256 output rows) of one N tile.  Each CTA loads the halo'd A slab of ITS 128 rows and only HALF of every
+// weight tile (rows [BN/2 * rank, BN/2 * rank + BN/2) of B_hi and of B_lo); the leader issues M = 256
+// tcgen05.mma.cta_group::2 instructions that read both CTAs' shared memory and write each CTA's 128 accumulator rows
+// into its own tensor memory.  Per SM the weight stream -- the larger part of the L2 -> shared-memory traffic of the
+// stage 2-4 layers (590 KB of a 662 KB tile in stage 3) -- is halved.
+// Per k16 step the hi/lo products are three N = BN instructions (the [B_hi ; B_lo] 2N trick of the slab kernel would
+// put all of B_hi in one CTA and all of B_lo in the other, and the A_lo x B_hi product needs B_hi from both):
+//   acc0 (+)= A_hi x B_hi,  acc1 (+)= A_hi x B_lo,  acc1 += A_lo x B_hi.
+// Protocol (CUTLASS' 2-SM pipeline): "full" barriers live in the leader -- its producer posts the bytes of BOTH CTAs'
+// loads, both CTAs' TMA loads complete on it; "empty" / "accumulator ready" arrive in both CTAs through multicast
+// tcgen05.commit; "accumulator drained" collects the epilogue warps of both CTAs on the leader's barrier.
+template <int EPI_MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EPI_MODE >= 0 ? TC_THREADS_MAX : TC_THREADS, 1)
+conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapWh,
+                    const __grid_constant__ OutMaps om, const TcParams p, const SlabParams sp) {
+  constexpr int KC = 64;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int nepi = (int)(blockDim.x >> 5) - 2;
+  const int WARP_TMA = nepi, WARP_MMA = nepi + 1;
+  const int BN = p.BN;
+  const uint32_t bhalf = (uint32_t)(BN / 2) * KC * 2;                  // bytes of my half of one weight plane tile
+  uint8_t* slab_base = smem;                                           // [nslab][2 planes][slab_bytes]
+  uint8_t* b_base = smem + (size_t)sp.nslab * 2 * sp.slab_bytes;       // [nring][B_hi half | B_lo half]
+  uint8_t* epi_own = b_base + (size_t)sp.nring * 2 * bhalf;
+  uint8_t* epi_base = p.epi_alias ? smem : epi_own;
+  uint64_t* sfull_bar = reinterpret_cast<uint64_t*>(epi_own + (p.epi_alias ? 0 : (size_t)p.epi_warps * EPI_WARP_BYTES));
+  uint64_t* sempty_bar = sfull_bar + SL_MAX_SLABS;
+  uint64_t* bfull_bar = sempty_bar + SL_MAX_SLABS;
+  uint64_t* bempty_bar = bfull_bar + SL_MAX_RING;
+  uint64_t* tfull_bar = bempty_bar + SL_MAX_RING;
+  uint64_t* tempty_bar = tfull_bar + 4;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tempty_bar + 4 + 8);
+  float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_base_slot + 2) + 15) & ~uintptr_t(15));
+  float* s_scale = s_bias + p.Cout;
+  float* s_shift = s_scale + p.Cout;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const uint32_t tmem_cols = (4 * BN <= 128) ? 128u : (4 * BN <= 256 ? 256u : 512u);   // 2 stages x (acc0, acc1)
+
+  if (warp == WARP_TMA) {
+    constexpr int NBAR = 2 * SL_MAX_SLABS + 2 * SL_MAX_RING + 4 + 4;
+    for (int i = lane; i < NBAR; i += 32) {
+      const bool is_tempty = i >= 2 * SL_MAX_SLABS + 2 * SL_MAX_RING + 4;
+      mbar_init(&sfull_bar[i], is_tempty ? 2u * 4u * (uint32_t)(BN >> 5) : 1u);      // drained: both CTAs' epilogue items
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (lane == 0) { prefetch_tmap(&mapA); prefetch_tmap(&mapWh); }
+  }
+  if (warp == WARP_MMA) {                       // the same warp id in both CTAs
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                           // both CTAs' barriers are initialised before anything crosses over
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+  if (warp < nepi) {
+    for (int i = threadIdx.x; i < p.Cout; i += nepi * 32) {
+      s_bias[i] = p.bias ? p.bias[i] : 0.f;
+      s_scale[i] = p.act_scale ? p.act_scale[i] : 1.f;
+      s_shift[i] = p.act_shift ? p.act_shift[i] : 0.f;
+    }
+    named_bar_sync(1, nepi * 32);
+  }
+
+  const int pairs_m = (p.m_tiles + 1) >> 1;
+  const int total_pairs = pairs_m * p.n_tiles;
+  const int ncl = (int)(gridDim.x >> 1), cl = (int)(blockIdx.x >> 1);
+
+  if (warp == WARP_TMA) {
+    // ===================== TMA producer (both CTAs) =====================
+    pdl_wait();
+    pdl_trigger();
+    int sb = 0; uint32_t sphase = 0;
+    int bs = 0; uint32_t bphase = 0;
+    for (int pr = cl; pr < total_pairs; pr += ncl) {
+      const int pm = pr / p.n_tiles, nt = pr - pm * p.n_tiles;
+      const int mt = 2 * pm + (int)rank;                   // (an odd tail's second tile lies past the tensor: zero fill)
+      const long long q0 = (long long)mt * TC_BM;
+      const int n0 = nt * BN + (int)rank * (BN / 2);       // my half of the weight rows
+      for (int c = 0; c < p.chunks_main; ++c) {
+        mbar_wait(&sempty_bar[sb], sphase ^ 1);
+        if (elect_one()) {
+          const uint32_t dst = smem_u32(slab_base + (size_t)sb * 2 * sp.slab_bytes);
+          if (leader) mbar_expect_tx(&sfull_bar[sb], 2u * (uint32_t)(2 * sp.slab_rows * KC * 2));
+          const uint32_t bar = mapa_u32(smem_u32(&sfull_bar[sb]), 0);
+          const int row0 = (int)(q0 - sp.lead);
+          tma_load_3d_2sm(&mapA, dst, bar, c * KC, row0, 0);
+          tma_load_3d_2sm(&mapA, dst + sp.slab_bytes, bar, c * KC, row0, 1);
+        }
+        __syncwarp();
+        if (++sb == sp.nslab) { sb = 0; sphase ^= 1; }
+        for (int tap = 0; tap < 9; ++tap) {
+          const int kofs = (tap * p.chunks_main + c) * KC;
+          mbar_wait(&bempty_bar[bs], bphase ^ 1);
+          if (elect_one()) {
+            const uint32_t b_hi = smem_u32(b_base + (size_t)bs * 2 * bhalf);
+            if (leader) mbar_expect_tx(&bfull_bar[bs], 2u * 2u * bhalf);
+            const uint32_t bar = mapa_u32(smem_u32(&bfull_bar[bs]), 0);
+            tma_load_3d_2sm(&mapWh, b_hi, bar, kofs, n0, 0);
+            tma_load_3d_2sm(&mapWh, b_hi + bhalf, bar, kofs, n0, 1);
+          }
+          __syncwarp();
+          if (++bs == sp.nring) { bs = 0; bphase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == WARP_MMA) {
+    // ===================== MMA issuer: one elected lane of the LEADER =====================
+    if (leader && elect_one()) {
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);   // M = 256 over the pair
+      constexpr uint32_t ROWB = KC * 2, ROW16 = ROWB >> 4;
+      constexpr uint32_t DHI = ((8 * ROWB) >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t a_base0 = ((smem_u32(slab_base) & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t a_slab16 = (uint32_t)(2 * sp.slab_bytes) >> 4, a_lo16 = (uint32_t)sp.slab_bytes >> 4;
+      const uint32_t b_base0 = ((smem_u32(b_base) & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t b_slot16 = (2u * bhalf) >> 4, b_lo16 = bhalf >> 4;
+      const uint32_t p_row16 = (uint32_t)p.P * ROW16;
+      const uint32_t tap0_16 = (uint32_t)(sp.lead - p.P - 1) * ROW16;
+      int sb = 0; uint32_t sphase = 0;
+      int bs = 0; uint32_t bphase = 0;
+      int it = 0;
+      for (int pr = cl; pr < total_pairs; pr += ncl, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait_cluster(&tempty_bar[as], aphase ^ 1);   // drained by the epilogue warps of BOTH CTAs
+        tc_fence_after();
+        const uint32_t acc0 = tmem_base + (uint32_t)(as * 2 * BN);
+        const uint32_t acc1 = acc0 + (uint32_t)BN;
+        uint32_t acc_on = 0;
+        for (int c = 0; c < p.chunks_main; ++c) {
+          mbar_wait_cluster(&sfull_bar[sb], sphase);
+          tc_fence_after();
+          uint32_t a_row = a_base0 + (uint32_t)sb * a_slab16 + tap0_16;
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+              mbar_wait_cluster(&bfull_bar[bs], bphase);
+              tc_fence_after();
+              const uint32_t b0 = b_base0 + (uint32_t)bs * b_slot16;
+              const uint32_t a0 = a_row + (uint32_t)kw * ROW16;
+#pragma unroll
+              for (int kk = 0; kk < KC / 16; ++kk) {
+                const uint64_t dah = ((uint64_t)DHI << 32) | (a0 + 2u * kk), dal = ((uint64_t)DHI << 32) | (a0 + a_lo16 + 2u * kk);
+                const uint64_t dbh = ((uint64_t)DHI << 32) | (b0 + 2u * kk), dbl = ((uint64_t)DHI << 32) | (b0 + b_lo16 + 2u * kk);
+                umma_f16_2sm(acc0, dah, dbh, idesc, acc_on);          // acc0 (+)= A_hi x B_hi
+                umma_f16_2sm(acc1, dah, dbl, idesc, acc_on);          // acc1 (+)= A_hi x B_lo
+                umma_f16_2sm(acc1, dal, dbh, idesc, 1u);              // acc1  += A_lo x B_hi
+                acc_on = 1u;
+              }
+              umma_commit_2sm(&bempty_bar[bs]);
+              if (++bs == sp.nring) { bs = 0; bphase ^= 1; }
+            }
+            a_row += p_row16;
+          }
+          umma_commit_2sm(&sempty_bar[sb]);
+          if (c == p.chunks_main - 1) umma_commit_2sm(&tfull_bar[as]);
+          if (++sb == sp.nslab) { sb = 0; sphase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue warps (both CTAs, each drains its own 128 accumulator rows) =====================
+    pdl_wait();
+    const int quad = warp & 3, group = warp >> 2, ngroups = nepi >> 2;
+    const uint32_t stage_u = smem_u32(epi_base + (size_t)warp * EPI_WARP_BYTES);
+    const uint32_t s_bias_u = smem_u32(s_bias);
+    const int nchunks = BN >> 5;
+    int it = 0, item = 0;
+    for (int pr = cl; pr < total_pairs; pr += ncl, ++it) {
+      const int pm = pr / p.n_tiles, nt = pr - pm * p.n_tiles;
+      const int mt = 2 * pm + (int)rank;
+      for (int c = 0; c < nchunks; ++c, ++item) {
+        if (item % ngroups != group) continue;
+        if (mt < p.m_tiles) {
+          epilogue_item<EPI_MODE>(p, om, mt * p.n_tiles + nt, c, it, quad, lane, tmem_base, tfull_bar, tempty_bar, s_bias_u, stage_u);
+        } else {                                  // the tile past an odd tail: nothing to store, the barrier protocol still runs
+          const int as = it & 1;
+          mbar_wait(&tfull_bar[as], (uint32_t)(it >> 1) & 1u);
+          tc_fence_after();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[as]), 0));
+        }
+      }
+    }
+    if (p.tma_out && lane == 0) bulk_wait0();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                           // the peer's tensor memory / shared memory are in use until both are done
+  if (warp == WARP_MMA) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
+  }
+}
+
 // ------------------------------------------------------------------ the chain kernel
 // All stride-1 3x3 convolutions of one ResNet stage (conv2 of the first block, then conv1/conv2 of every further
 // block) as ONE persistent launch.  At small batches a stage-3/4 layer has fewer tiles than the chip has SMs and
@@ -1499,6 +1709,47 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
     if (p.epi_warps == 16) return TC_THREADS_MAX;
     return (epi16_ok && mode_ >= 0 && p.epi_alias && p.BN >= 128 && operand_bytes >= 2 * (size_t)EPI_BYTES) ? TC_THREADS_MAX : TC_THREADS;
   };
+  // CTA pairs (conv_tc_pair_kernel): the multi-round layers whose weights stream through the ring (stages 2-4 at large
+  // batches) -- every SM then fetches half of each weight tile.  SAR_TC_PAIR=0 disables, =2 forces it for every eligible layer.
+  static const int pair_env = getenv("SAR_TC_PAIR") ? atoi(getenv("SAR_TC_PAIR")) : 1;
+  if (slab && pair_env && !sp.resident && p.kc_main == 64 && p.chunks_sc == 0 && p.epi_warps == 8 && p.m_tiles >= 2 && (sms & 1) == 0 &&
+      (pair_env == 2 || (long long)p.mn_tiles >= 2LL * sms)) {
+    const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
+    const int ncl = pairs < sms / 2 ? pairs : sms / 2;
+    TcParams q = p;
+    SlabParams sq = sp;
+    q.pair = 1; q.nacc_log2 = 1;
+    q.epi_alias = (pairs <= ncl) ? 1 : 0;
+    const size_t fixed_p = 1024 + 1024 + 640 + 3 * (size_t)d->cout * sizeof(float) + (q.epi_alias ? 0 : (size_t)EPI_BYTES);
+    const size_t slab1 = 2 * (size_t)sp.slab_bytes, bstage = (size_t)p.BN * 64 * 2;      // [B_hi half | B_lo half] of one k-step
+    sq.resident = 0;
+    for (sq.nslab = (p.chunks_main >= 2) ? 3 : 2; sq.nslab >= 2; --sq.nslab) {       // a third slab only if >= 6 weight stages remain
+      const long long left = (long long)227 * 1024 - (long long)fixed_p - (long long)(sq.nslab * slab1);
+      sq.nring = left > 0 ? (int)(left / (long long)bstage) : 0;
+      if (sq.nring > SL_MAX_RING) sq.nring = SL_MAX_RING;
+      if (sq.nring >= 6 || sq.nslab == 2) break;
+    }
+    if (sq.nring >= 4) {
+      CUtensorMap mapWh;
+      if ((rc = make_map(&mapWh, d->w, d->cout, ktot, 2, 64, p.BN / 2))) return rc;
+      size_t smem_p = fixed_p + sq.nslab * slab1 + (size_t)sq.nring * bstage;
+      if (q.epi_alias && smem_p - fixed_p < (size_t)EPI_BYTES) smem_p = fixed_p + EPI_BYTES;
+      auto launch_p = [&](auto kern) -> int {
+        { const int arc = allow_max_smem(kern, "sar_conv_tc_fwd(pair)"); if (arc) return arc; }
+        launch_k(kern, dim3(2 * ncl), dim3(TC_THREADS), smem_p, (cudaStream_t)stream, mapA, mapWh, om, q, sq);
+        return 0;
+      };
+      int lrc;
+      switch (mode) {
+        case 0: lrc = launch_p(conv_tc_pair_kernel<0>); break;
+        case 2: lrc = launch_p(conv_tc_pair_kernel<2>); break;
+        case 3: lrc = launch_p(conv_tc_pair_kernel<3>); break;
+        default: lrc = launch_p(conv_tc_pair_kernel<-1>); break;
+      }
+      if (lrc) return lrc;
+      return check_launch("sar_conv_tc_fwd(pair)");
+    }
+  }
   if (slab) {
     const int nb = sp.resident ? (p.ntaps * p.chunks_main + p.chunks_sc) : sp.nring;
     size_t smem = fixed + (size_t)sp.nslab * 2 * sp.slab_bytes + (size_t)nb * 2 * sp.bplane_bytes;
