@@ -927,8 +927,9 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 // tcgen05.commit; "accumulator drained" collects the epilogue warps of both CTAs on the leader's barrier.
 template <int EPI_MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EPI_MODE >= 0 ? TC_THREADS_MAX : TC_THREADS, 1)
-conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapWh,
-                    const __grid_constant__ OutMaps om, const TcParams p, const SlabParams sp) {
+conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapS,
+                    const __grid_constant__ CUtensorMap mapWh, const __grid_constant__ OutMaps om, const TcParams p,
+                    const SlabParams sp) {
   constexpr int KC = 64;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -963,7 +964,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       mbar_init(&sfull_bar[i], is_tempty ? 2u * 4u * (uint32_t)(BN >> 5) : 1u);      // drained: both CTAs' epilogue items
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    if (lane == 0) { prefetch_tmap(&mapA); prefetch_tmap(&mapWh); }
+    if (lane == 0) { prefetch_tmap(&mapA); prefetch_tmap(&mapWh); if (p.chunks_sc) prefetch_tmap(&mapS); }
   }
   if (warp == WARP_MMA) {                       // the same warp id in both CTAs
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(tmem_cols));
@@ -1024,6 +1025,30 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           if (++bs == sp.nring) { bs = 0; bphase ^= 1; }
         }
       }
+      // 1x1 projection shortcut (kc_sc == 64): my 128 rows of the shortcut operand, one tap, no halo; one weight k-step
+      for (int c = 0; c < p.chunks_sc; ++c) {
+        mbar_wait(&sempty_bar[sb], sphase ^ 1);
+        if (elect_one()) {
+          const uint32_t dst = smem_u32(slab_base + (size_t)sb * 2 * sp.slab_bytes);
+          if (leader) mbar_expect_tx(&sfull_bar[sb], 2u * (uint32_t)(2 * TC_BM * KC * 2));
+          const uint32_t bar = mapa_u32(smem_u32(&sfull_bar[sb]), 0);
+          tma_load_3d_2sm(&mapS, dst, bar, c * KC, (int)q0, p.sc_plane);
+          tma_load_3d_2sm(&mapS, dst + sp.slab_bytes, bar, c * KC, (int)q0, p.sc_plane + 1);
+        }
+        __syncwarp();
+        if (++sb == sp.nslab) { sb = 0; sphase ^= 1; }
+        mbar_wait(&bempty_bar[bs], bphase ^ 1);
+        if (elect_one()) {
+          const uint32_t b_hi = smem_u32(b_base + (size_t)bs * 2 * bhalf);
+          if (leader) mbar_expect_tx(&bfull_bar[bs], 2u * 2u * bhalf);
+          const uint32_t bar = mapa_u32(smem_u32(&bfull_bar[bs]), 0);
+          const int kofs = (9 * p.chunks_main + c) * KC;
+          tma_load_3d_2sm(&mapWh, b_hi, bar, kofs, n0, 0);
+          tma_load_3d_2sm(&mapWh, b_hi + bhalf, bar, kofs, n0, 1);
+        }
+        __syncwarp();
+        if (++bs == sp.nring) { bs = 0; bphase ^= 1; }
+      }
     }
   } else if (warp == WARP_MMA) {
     // ===================== MMA issuer: one elected lane of the LEADER =====================
@@ -1075,7 +1100,28 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             a_row += p_row16;
           }
           umma_commit_2sm(&sempty_bar[sb]);
-          if (c == p.chunks_main - 1) umma_commit_2sm(&tfull_bar[as]);
+          if (p.chunks_sc == 0 && c == p.chunks_main - 1) umma_commit_2sm(&tfull_bar[as]);
+          if (++sb == sp.nslab) { sb = 0; sphase ^= 1; }
+        }
+        for (int c = 0; c < p.chunks_sc; ++c) {           // 1x1 projection shortcut: one tap, rows from slab row 0
+          mbar_wait_cluster(&sfull_bar[sb], sphase);
+          tc_fence_after();
+          mbar_wait_cluster(&bfull_bar[bs], bphase);
+          tc_fence_after();
+          const uint32_t a0 = a_base0 + (uint32_t)sb * a_slab16;
+          const uint32_t b0 = b_base0 + (uint32_t)bs * b_slot16;
+#pragma unroll
+          for (int kk = 0; kk < KC / 16; ++kk) {
+            const uint64_t dah = ((uint64_t)DHI << 32) | (a0 + 2u * kk), dal = ((uint64_t)DHI << 32) | (a0 + a_lo16 + 2u * kk);
+            const uint64_t dbh = ((uint64_t)DHI << 32) | (b0 + 2u * kk), dbl = ((uint64_t)DHI << 32) | (b0 + b_lo16 + 2u * kk);
+            umma_f16_2sm(acc0, dah, dbh, idesc, 1u);
+            umma_f16_2sm(acc1, dah, dbl, idesc, 1u);
+            umma_f16_2sm(acc1, dal, dbh, idesc, 1u);
+          }
+          umma_commit_2sm(&bempty_bar[bs]);
+          if (++bs == sp.nring) { bs = 0; bphase ^= 1; }
+          umma_commit_2sm(&sempty_bar[sb]);
+          if (c == p.chunks_sc - 1) umma_commit_2sm(&tfull_bar[as]);
           if (++sb == sp.nslab) { sb = 0; sphase ^= 1; }
         }
       }
@@ -1712,8 +1758,10 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
   // CTA pairs (conv_tc_pair_kernel): the multi-round layers whose weights stream through the ring (stages 2-4 at large
   // batches) -- every SM then fetches half of each weight tile.  SAR_TC_PAIR=0 disables, =2 forces it for every eligible layer.
   static const int pair_env = getenv("SAR_TC_PAIR") ? atoi(getenv("SAR_TC_PAIR")) : 1;
-  if (slab && pair_env && !sp.resident && p.kc_main == 64 && p.chunks_sc == 0 && p.epi_warps == 8 && p.m_tiles >= 2 && (sms & 1) == 0 &&
-      (pair_env == 2 || (long long)p.mn_tiles >= 2LL * sms)) {
+  // (64-channel layers -- stage 2 -- are epilogue-bound at this tile size: coupling two CTAs' accumulator hand-back
+  // made their shortcut layers 13 % slower, so pairs start at 128 input channels)
+  if (slab && pair_env && !sp.resident && p.kc_main == 64 && (p.chunks_sc == 0 || p.kc_sc == 64) && p.epi_warps == 8 && p.m_tiles >= 2 &&
+      (sms & 1) == 0 && (pair_env == 2 || ((long long)p.mn_tiles >= 2LL * sms && p.chunks_main >= 2))) {
     const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
     const int ncl = pairs < sms / 2 ? pairs : sms / 2;
     TcParams q = p;
@@ -1734,9 +1782,12 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
       if ((rc = make_map(&mapWh, d->w, d->cout, ktot, 2, 64, p.BN / 2))) return rc;
       size_t smem_p = fixed_p + sq.nslab * slab1 + (size_t)sq.nring * bstage;
       if (q.epi_alias && smem_p - fixed_p < (size_t)EPI_BYTES) smem_p = fixed_p + EPI_BYTES;
+      // 16 epilogue warps when every CTA owns ONE 128-wide tile (its 16 items then drain in one round), as in the slab kernel
+      const bool wide = epi16_ok && mode >= 0 && q.epi_alias && p.BN >= 128 && smem_p - fixed_p >= 2 * (size_t)EPI_BYTES;
+      if (wide) q.epi_warps = 16;
       auto launch_p = [&](auto kern) -> int {
         { const int arc = allow_max_smem(kern, "sar_conv_tc_fwd(pair)"); if (arc) return arc; }
-        launch_k(kern, dim3(2 * ncl), dim3(TC_THREADS), smem_p, (cudaStream_t)stream, mapA, mapWh, om, q, sq);
+        launch_k(kern, dim3(2 * ncl), dim3(wide ? TC_THREADS_MAX : TC_THREADS), smem_p, (cudaStream_t)stream, mapA, mapS, mapWh, om, q, sq);
         return 0;
       };
       int lrc;

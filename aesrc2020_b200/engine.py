@@ -127,6 +127,10 @@ class ResNetTC:
         import os as _os
         # stages whose stride-1 layers run as one persistent chain launch (SAR_CHAIN_STAGES="" disables)
         self.chain_stages = {int(x) for x in _os.environ.get("SAR_CHAIN_STAGES", "2,3,4").split(",") if x.strip()}
+        # ... but only while a layer has few tiles per SM: the chain removes per-layer launch / prologue / epilogue tails
+        # (B=64: conv segment 0.527 -> 0.495 ms), at large batches those are amortised and the per-layer kernels are
+        # faster (weights resident or CTA pairs; B=512: 3.17 -> 2.72 ms without chains).  Items = 128 x 64 tiles.
+        self.chain_max_items = int(_os.environ.get("SAR_CHAIN_MAX_ITEMS", str(3 * 148)))
         # residual stream between identity-shortcut blocks as one fp32 plane (SAR_RAW32=0: hi/lo planes, an A/B aid)
         self.raw32 = _os.environ.get("SAR_RAW32", "1") != "0" and _os.environ.get("SAR_TC_TMA_OUT", "1") != "0"
 
@@ -210,7 +214,8 @@ class ResNetTC:
         def emit(desc, chainable):
             # lanes run concurrently on separate streams: a chain launch (CTAs spinning on tile counters of CTAs of
             # the SAME launch) needs its whole grid resident, which two lanes sharing the SMs cannot promise
-            if chainable and stage in self.chain_stages and not opts.no_chain:
+            items = -(-(desc.B * (desc.H + 1) * (desc.W + 1)) // 128) * max(1, desc.cout // 64)
+            if chainable and stage in self.chain_stages and not opts.no_chain and items <= self.chain_max_items:
                 pending.append(desc)
             else:
                 flush()
