@@ -750,52 +750,68 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       int sb = 0; uint32_t sphase = 0;        // slab ring
       int bs = 0; uint32_t bphase = 0;        // weight ring
       int exp_s = 0, exp_w = 0;               // (SAR_TC_MMAMASK bits 3/4: traffic experiments, wrong results)
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+      // One "step" = one slab (a 64/32-channel chunk of a tile) and the weight tiles of its taps.  The slab of step k+1
+      // is requested after the first three weight tiles of step k, not after all nine (the weight ring lets this warp
+      // run only nring taps ahead of the MMAs, so a slab requested behind the last tap is requested late).  Measured
+      // at B=512: neutral to -1 % on the streamed-weight layers (stage 2: 683 -> 678 us) -- the slab was not what the
+      // ~0.9k cycles between two tiles wait for.
+      auto issue_slab = [&](int tile, int c) {
+        const int mt = tile / p.n_tiles;
         const long long q0 = (long long)mt * TC_BM;
-        const int n0 = nt * BN;
-        for (int c = 0; c < n_chunks; ++c) {
-          const bool main = c < p.chunks_main;
-          const int kc = main ? p.kc_main : p.kc_sc;
-          const int rows = main ? sp.slab_rows : TC_BM;
-          mbar_wait(&sempty_bar[sb], sphase ^ 1);
-          if ((p.mma_mask & 16) && exp_s >= sp.nslab) {        // experiment: no slab traffic after the first ring fill
-            if (elect_one()) mbar_arrive(&sfull_bar[sb]);
-          } else
-          if (elect_one()) {
-            const uint32_t dst = smem_u32(slab_base + (size_t)sb * 2 * sp.slab_bytes);
-            mbar_expect_tx(&sfull_bar[sb], (uint32_t)(2 * rows * kc * 2));
-            if (main) {
-              const int row0 = (int)(q0 - sp.lead);
-              tma_load_3d(&mapA, dst, &sfull_bar[sb], c * kc, row0, 0);
-              tma_load_3d(&mapA, dst + sp.slab_bytes, &sfull_bar[sb], c * kc, row0, 1);
-            } else {
-              const int ch = c - p.chunks_main;
-              tma_load_3d(&mapS, dst, &sfull_bar[sb], ch * kc, (int)q0, p.sc_plane);
-              tma_load_3d(&mapS, dst + sp.slab_bytes, &sfull_bar[sb], ch * kc, (int)q0, p.sc_plane + 1);
-            }
-          }
-          __syncwarp();
-          ++exp_s;
-          if (++sb == sp.nslab) { sb = 0; sphase ^= 1; }
-          if (!sp.resident) {
-            const CUtensorMap* wm = main ? &mapWm : &mapWs;
-            for (int tap = 0; tap < (main ? p.ntaps : 1); ++tap) {
-              mbar_wait(&bempty_bar[bs], bphase ^ 1);
-              if ((p.mma_mask & 8) && exp_w++ >= sp.nring) {   // experiment: no weight traffic after the first ring fill
-                if (elect_one()) mbar_arrive(&bfull_bar[bs]);
-              } else
-              if (elect_one()) {
-                const uint32_t b_hi = smem_u32(b_base + (size_t)bs * 2 * sp.bplane_bytes);
-                mbar_expect_tx(&bfull_bar[bs], (uint32_t)(2 * BN * kc * 2));
-                tma_load_3d(wm, b_hi, &bfull_bar[bs], kofs_of(c, tap), n0, 0);
-                tma_load_3d(wm, b_hi + (uint32_t)(BN * kc * 2), &bfull_bar[bs], kofs_of(c, tap), n0, 1);   // [B_hi ; B_lo] adjacent
-              }
-              __syncwarp();
-              if (++bs == sp.nring) { bs = 0; bphase ^= 1; }
-            }
+        const bool main = c < p.chunks_main;
+        const int kc = main ? p.kc_main : p.kc_sc;
+        const int rows = main ? sp.slab_rows : TC_BM;
+        mbar_wait(&sempty_bar[sb], sphase ^ 1);
+        if ((p.mma_mask & 16) && exp_s >= sp.nslab) {        // experiment: no slab traffic after the first ring fill
+          if (elect_one()) mbar_arrive(&sfull_bar[sb]);
+        } else
+        if (elect_one()) {
+          const uint32_t dst = smem_u32(slab_base + (size_t)sb * 2 * sp.slab_bytes);
+          mbar_expect_tx(&sfull_bar[sb], (uint32_t)(2 * rows * kc * 2));
+          if (main) {
+            const int row0 = (int)(q0 - sp.lead);
+            tma_load_3d(&mapA, dst, &sfull_bar[sb], c * kc, row0, 0);
+            tma_load_3d(&mapA, dst + sp.slab_bytes, &sfull_bar[sb], c * kc, row0, 1);
+          } else {
+            const int ch = c - p.chunks_main;
+            tma_load_3d(&mapS, dst, &sfull_bar[sb], ch * kc, (int)q0, p.sc_plane);
+            tma_load_3d(&mapS, dst + sp.slab_bytes, &sfull_bar[sb], ch * kc, (int)q0, p.sc_plane + 1);
           }
         }
+        __syncwarp();
+        ++exp_s;
+        if (++sb == sp.nslab) { sb = 0; sphase ^= 1; }
+      };
+      auto issue_weight = [&](int tile, int c, int tap) {
+        const int nt = tile - (tile / p.n_tiles) * p.n_tiles;
+        const int n0 = nt * BN;
+        const bool main = c < p.chunks_main;
+        const int kc = main ? p.kc_main : p.kc_sc;
+        const CUtensorMap* wm = main ? &mapWm : &mapWs;
+        mbar_wait(&bempty_bar[bs], bphase ^ 1);
+        if ((p.mma_mask & 8) && exp_w++ >= sp.nring) {       // experiment: no weight traffic after the first ring fill
+          if (elect_one()) mbar_arrive(&bfull_bar[bs]);
+        } else
+        if (elect_one()) {
+          const uint32_t b_hi = smem_u32(b_base + (size_t)bs * 2 * sp.bplane_bytes);
+          mbar_expect_tx(&bfull_bar[bs], (uint32_t)(2 * BN * kc * 2));
+          tma_load_3d(wm, b_hi, &bfull_bar[bs], kofs_of(c, tap), n0, 0);
+          tma_load_3d(wm, b_hi + (uint32_t)(BN * kc * 2), &bfull_bar[bs], kofs_of(c, tap), n0, 1);   // [B_hi ; B_lo] adjacent
+        }
+        __syncwarp();
+        if (++bs == sp.nring) { bs = 0; bphase ^= 1; }
+      };
+      int tile = blockIdx.x, c = 0;
+      if (tile < total_tiles) issue_slab(tile, 0);
+      while (tile < total_tiles) {
+        int ntile = tile, nc = c + 1;
+        if (nc == n_chunks) { nc = 0; ntile = tile + (int)gridDim.x; }
+        const int ntaps = sp.resident ? 0 : (c < p.chunks_main ? p.ntaps : 1);
+        const int early = ntaps < 3 ? ntaps : 3;
+        for (int tap = 0; tap < early; ++tap) issue_weight(tile, c, tap);
+        if (ntile < total_tiles) issue_slab(ntile, nc);
+        for (int tap = early; tap < ntaps; ++tap) issue_weight(tile, c, tap);
+        tile = ntile; c = nc;
       }
     }
   } else if (warp == WARP_MMA) {
@@ -994,61 +1010,57 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     pdl_trigger();
     int sb = 0; uint32_t sphase = 0;
     int bs = 0; uint32_t bphase = 0;
-    for (int pr = cl; pr < total_pairs; pr += ncl) {
-      const int pm = pr / p.n_tiles, nt = pr - pm * p.n_tiles;
-      const int mt = 2 * pm + (int)rank;                   // (an odd tail's second tile lies past the tensor: zero fill)
+    const int n_chunks = p.chunks_main + p.chunks_sc;
+    // (step order as in conv_tc_slab_kernel: the next step's slab goes out after three weight tiles of this one)
+    auto issue_slab = [&](int pr, int c) {
+      const int pm = pr / p.n_tiles;
+      const int mt = 2 * pm + (int)rank;                     // (an odd tail's second tile lies past the tensor: zero fill)
       const long long q0 = (long long)mt * TC_BM;
-      const int n0 = nt * BN + (int)rank * (BN / 2);       // my half of the weight rows
-      for (int c = 0; c < p.chunks_main; ++c) {
-        mbar_wait(&sempty_bar[sb], sphase ^ 1);
-        if (elect_one()) {
-          const uint32_t dst = smem_u32(slab_base + (size_t)sb * 2 * sp.slab_bytes);
-          if (leader) mbar_expect_tx(&sfull_bar[sb], 2u * (uint32_t)(2 * sp.slab_rows * KC * 2));
-          const uint32_t bar = mapa_u32(smem_u32(&sfull_bar[sb]), 0);
+      const bool main = c < p.chunks_main;
+      mbar_wait(&sempty_bar[sb], sphase ^ 1);
+      if (elect_one()) {
+        const uint32_t dst = smem_u32(slab_base + (size_t)sb * 2 * sp.slab_bytes);
+        if (leader) mbar_expect_tx(&sfull_bar[sb], 2u * (uint32_t)(2 * (main ? sp.slab_rows : TC_BM) * KC * 2));
+        const uint32_t bar = mapa_u32(smem_u32(&sfull_bar[sb]), 0);
+        if (main) {
           const int row0 = (int)(q0 - sp.lead);
           tma_load_3d_2sm(&mapA, dst, bar, c * KC, row0, 0);
           tma_load_3d_2sm(&mapA, dst + sp.slab_bytes, bar, c * KC, row0, 1);
-        }
-        __syncwarp();
-        if (++sb == sp.nslab) { sb = 0; sphase ^= 1; }
-        for (int tap = 0; tap < 9; ++tap) {
-          const int kofs = (tap * p.chunks_main + c) * KC;
-          mbar_wait(&bempty_bar[bs], bphase ^ 1);
-          if (elect_one()) {
-            const uint32_t b_hi = smem_u32(b_base + (size_t)bs * 2 * bhalf);
-            if (leader) mbar_expect_tx(&bfull_bar[bs], 2u * 2u * bhalf);
-            const uint32_t bar = mapa_u32(smem_u32(&bfull_bar[bs]), 0);
-            tma_load_3d_2sm(&mapWh, b_hi, bar, kofs, n0, 0);
-            tma_load_3d_2sm(&mapWh, b_hi + bhalf, bar, kofs, n0, 1);
-          }
-          __syncwarp();
-          if (++bs == sp.nring) { bs = 0; bphase ^= 1; }
+        } else {                                             // 1x1 projection shortcut (kc_sc == 64): my 128 rows, no halo
+          const int ch = c - p.chunks_main;
+          tma_load_3d_2sm(&mapS, dst, bar, ch * KC, (int)q0, p.sc_plane);
+          tma_load_3d_2sm(&mapS, dst + sp.slab_bytes, bar, ch * KC, (int)q0, p.sc_plane + 1);
         }
       }
-      // 1x1 projection shortcut (kc_sc == 64): my 128 rows of the shortcut operand, one tap, no halo; one weight k-step
-      for (int c = 0; c < p.chunks_sc; ++c) {
-        mbar_wait(&sempty_bar[sb], sphase ^ 1);
-        if (elect_one()) {
-          const uint32_t dst = smem_u32(slab_base + (size_t)sb * 2 * sp.slab_bytes);
-          if (leader) mbar_expect_tx(&sfull_bar[sb], 2u * (uint32_t)(2 * TC_BM * KC * 2));
-          const uint32_t bar = mapa_u32(smem_u32(&sfull_bar[sb]), 0);
-          tma_load_3d_2sm(&mapS, dst, bar, c * KC, (int)q0, p.sc_plane);
-          tma_load_3d_2sm(&mapS, dst + sp.slab_bytes, bar, c * KC, (int)q0, p.sc_plane + 1);
-        }
-        __syncwarp();
-        if (++sb == sp.nslab) { sb = 0; sphase ^= 1; }
-        mbar_wait(&bempty_bar[bs], bphase ^ 1);
-        if (elect_one()) {
-          const uint32_t b_hi = smem_u32(b_base + (size_t)bs * 2 * bhalf);
-          if (leader) mbar_expect_tx(&bfull_bar[bs], 2u * 2u * bhalf);
-          const uint32_t bar = mapa_u32(smem_u32(&bfull_bar[bs]), 0);
-          const int kofs = (9 * p.chunks_main + c) * KC;
-          tma_load_3d_2sm(&mapWh, b_hi, bar, kofs, n0, 0);
-          tma_load_3d_2sm(&mapWh, b_hi + bhalf, bar, kofs, n0, 1);
-        }
-        __syncwarp();
-        if (++bs == sp.nring) { bs = 0; bphase ^= 1; }
+      __syncwarp();
+      if (++sb == sp.nslab) { sb = 0; sphase ^= 1; }
+    };
+    auto issue_weight = [&](int pr, int c, int tap) {
+      const int nt = pr - (pr / p.n_tiles) * p.n_tiles;
+      const int n0 = nt * BN + (int)rank * (BN / 2);         // my half of the weight rows
+      const int kofs = (c < p.chunks_main ? tap * p.chunks_main + c : 9 * p.chunks_main + (c - p.chunks_main)) * KC;
+      mbar_wait(&bempty_bar[bs], bphase ^ 1);
+      if (elect_one()) {
+        const uint32_t b_hi = smem_u32(b_base + (size_t)bs * 2 * bhalf);
+        if (leader) mbar_expect_tx(&bfull_bar[bs], 2u * 2u * bhalf);
+        const uint32_t bar = mapa_u32(smem_u32(&bfull_bar[bs]), 0);
+        tma_load_3d_2sm(&mapWh, b_hi, bar, kofs, n0, 0);
+        tma_load_3d_2sm(&mapWh, b_hi + bhalf, bar, kofs, n0, 1);
       }
+      __syncwarp();
+      if (++bs == sp.nring) { bs = 0; bphase ^= 1; }
+    };
+    int pr = cl, c = 0;
+    if (pr < total_pairs) issue_slab(pr, 0);
+    while (pr < total_pairs) {
+      int npr = pr, nc = c + 1;
+      if (nc == n_chunks) { nc = 0; npr = pr + ncl; }
+      const int ntaps = c < p.chunks_main ? 9 : 1;
+      const int early = ntaps < 3 ? ntaps : 3;
+      for (int tap = 0; tap < early; ++tap) issue_weight(pr, c, tap);
+      if (npr < total_pairs) issue_slab(npr, nc);
+      for (int tap = early; tap < ntaps; ++tap) issue_weight(pr, c, tap);
+      pr = npr; c = nc;
     }
   } else if (warp == WARP_MMA) {
     // ===================== MMA issuer: one elected lane of the LEADER =====================
