@@ -75,7 +75,8 @@ SIGNATURES = {
     "sar_adam_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_ll, c_f, c_f, c_f, c_f, c_f, C.c_void_p]),
     "sar_unit_norm_fwd": (c_int, [c_fp, c_int, c_int, C.c_void_p]),
     "sar_vlad_train_fwd": (c_int, [c_fp] * 7 + [c_int] * 5 + [C.c_void_p]),
-    "sar_vlad_train_bwd": (c_int, [c_fp] * 7 + [c_int] * 5 + [C.c_void_p]),
+    "sar_vlad_train_bwd": (c_int, [c_fp] * 8 + [c_int] * 5 + [C.c_void_p]),
+    "sar_ln_train_bwd": (c_int, [c_fp] * 5 + [c_int, c_int, c_f, c_int, C.c_void_p]),
     "sar_fbank_fwd": (c_int, [c_fp, c_ip, c_fp, c_fp, c_fp, c_int, c_int, c_int, C.c_void_p]),
     "sar_fbank_pcm16_fwd": (c_int, [c_ip, c_ip, c_fp, c_fp, c_fp, c_int, c_int, c_int, C.c_void_p]),
 }

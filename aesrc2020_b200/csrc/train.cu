@@ -119,7 +119,7 @@ __global__ void bias_act_kernel(const float* __restrict__ x, const float* __rest
   pdl_trigger();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float v = x[i] + (b ? b[i % C] : 0.f);
-    y[i] = relu ? fmaxf(v, 0.f) : v;
+    y[i] = relu == 1 ? fmaxf(v, 0.f) : (relu == 2 ? tanhf(v) : v);
   }
 }
 __global__ void relu_bwd_kernel(const float* __restrict__ g, const float* __restrict__ h, float* __restrict__ out, long long n) {
@@ -332,7 +332,8 @@ __global__ void __launch_bounds__(256) vlad_train_fwd_kernel(const float* __rest
 
 __global__ void __launch_bounds__(256) vlad_train_bwd_kernel(const float* __restrict__ x, const float* __restrict__ A, const float* __restrict__ centers,
                                                               const float* __restrict__ gR, const float* __restrict__ asum,
-                                                              float* __restrict__ g_scores, float* __restrict__ gc_part, int S, int D, int K, int KG) {
+                                                              float* __restrict__ g_scores, float* __restrict__ gc_part, float* __restrict__ g_x,
+                                                              int S, int D, int K, int KG) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ float vsm[];
@@ -358,6 +359,55 @@ __global__ void __launch_bounds__(256) vlad_train_bwd_kernel(const float* __rest
   }
   for (int i = t; i < K * D; i += 256)
     gc_part[(size_t)b * K * D + i] = -asum[(size_t)b * K + i / D] * gRb[i];
+  // the residual-sum path of d loss / d x: g_x[s,:] = sum_k A[s,k] gR[k,:]  (the score path, g_scores Wa^T, is the
+  // caller's sar_gemm_fwd with beta = 1)
+  if (g_x)
+    for (int i = t; i < S * D; i += 256) {
+      const int s_ = i / D, d = i - s_ * D;
+      const float* Ar = A + ((size_t)b * S + s_) * KG;
+      float acc = 0.f;
+      for (int k = 0; k < K; ++k) acc = fmaf(Ar[k], gRb[(size_t)k * D + d], acc);
+      g_x[((size_t)b * S + s_) * D + d] = acc;
+    }
+}
+
+// ------------------------------------------------------------------ LayerNormalization (+ the tanh in front of it) backward
+// Row per warp.  y (rows, C) is the LN INPUT (= tanh(pre) when `tanh_in`), g_z = d loss / d LN output.
+//   xhat = (y - mean) * inv,  inv = 1 / sqrt(var + eps) (biased variance, eps = 1e-14: keras_layer_normalization)
+//   g_y = inv * (gamma g_z - mean(gamma g_z) - xhat * mean(gamma g_z xhat));   g_pre = g_y * (1 - y^2) if tanh_in
+// also writes gz_xhat = g_z * xhat (column sums = d loss / d gamma; d loss / d beta = column sums of g_z).
+__global__ void __launch_bounds__(256) ln_train_bwd_kernel(const float* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ g_z,
+                                                            float* __restrict__ g_pre, float* __restrict__ gz_xhat, int rows, int C, float eps,
+                                                            int tanh_in) {
+  pdl_wait();
+  pdl_trigger();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + warp;
+  if (r >= rows) return;
+  const float* yr = y + (size_t)r * C;
+  const float* gr = g_z + (size_t)r * C;
+  float s1 = 0.f;
+  for (int c = lane; c < C; c += 32) s1 += yr[c];
+  for (int o = 16; o; o >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+  const float mean = s1 / C;
+  float s2 = 0.f;
+  for (int c = lane; c < C; c += 32) { const float dlt = yr[c] - mean; s2 = fmaf(dlt, dlt, s2); }
+  for (int o = 16; o; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  const float inv = rsqrtf(s2 / C + eps);
+  float a1 = 0.f, a2 = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float xh = (yr[c] - mean) * inv, gg = gamma[c] * gr[c];
+    a1 += gg; a2 = fmaf(gg, xh, a2);
+  }
+  for (int o = 16; o; o >>= 1) { a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o); }
+  a1 /= C; a2 /= C;
+  for (int c = lane; c < C; c += 32) {
+    const float yv = yr[c], xh = (yv - mean) * inv;
+    float gy = inv * (gamma[c] * gr[c] - a1 - xh * a2);
+    if (tanh_in) gy *= 1.f - yv * yv;
+    g_pre[(size_t)r * C + c] = gy;
+    gz_xhat[(size_t)r * C + c] = gr[c] * xh;
+  }
 }
 
 }  // namespace sar
@@ -397,8 +447,9 @@ int sar_bn_train_bwd(const float* x, const float* dy, const float* gamma, const 
 int sar_bias_act_fwd(const float* x, const float* bias, float* y, long long rows, int C, int act, void* stream) {
   using namespace sar;
   SAR_REQUIRE(x && y, SAR_ERR_BAD_ARG, "sar_bias_act_fwd: null pointer");
-  SAR_REQUIRE(rows > 0 && C > 0 && (act == SAR_ACT_NONE || act == SAR_ACT_RELU), SAR_ERR_BAD_ARG, "sar_bias_act_fwd: bad argument");
-  launch_k(bias_act_kernel, dim3(blocks_for(rows * C, 256)), dim3(256), 0, (cudaStream_t)stream, x, bias, y, rows * C, C, act == SAR_ACT_RELU ? 1 : 0);
+  SAR_REQUIRE(rows > 0 && C > 0 && (act == SAR_ACT_NONE || act == SAR_ACT_RELU || act == SAR_ACT_TANH), SAR_ERR_BAD_ARG, "sar_bias_act_fwd: bad argument");
+  launch_k(bias_act_kernel, dim3(blocks_for(rows * C, 256)), dim3(256), 0, (cudaStream_t)stream, x, bias, y, rows * C, C,
+           act == SAR_ACT_RELU ? 1 : (act == SAR_ACT_TANH ? 2 : 0));
   return check_launch("sar_bias_act_fwd");
 }
 
@@ -472,15 +523,24 @@ int sar_vlad_train_fwd(const float* x, const float* w_assign, const float* b_ass
   return check_launch("sar_vlad_train_fwd");
 }
 
+int sar_ln_train_bwd(const float* y, const float* gamma, const float* g_z, float* g_pre, float* gz_xhat, int rows, int C, float eps,
+                     int tanh_in, void* stream) {
+  using namespace sar;
+  SAR_REQUIRE(y && gamma && g_z && g_pre && gz_xhat && rows > 0 && C > 0, SAR_ERR_BAD_ARG, "sar_ln_train_bwd: bad argument");
+  launch_k(ln_train_bwd_kernel, dim3((rows + 7) / 8), dim3(256), 0, (cudaStream_t)stream, y, gamma, g_z, g_pre, gz_xhat, rows, C, eps,
+           tanh_in ? 1 : 0);
+  return check_launch("sar_ln_train_bwd");
+}
+
 int sar_vlad_train_bwd(const float* x, const float* A, const float* centers, const float* gR, const float* asum, float* g_scores,
-                       float* gc_part, int B, int S, int D, int K, int G, void* stream) {
+                       float* gc_part, float* g_x, int B, int S, int D, int K, int G, void* stream) {
   using namespace sar;
   SAR_REQUIRE(x && A && centers && gR && asum && g_scores && gc_part, SAR_ERR_BAD_ARG, "sar_vlad_train_bwd: null pointer");
   SAR_REQUIRE(B > 0 && S > 0 && S <= 128 && D > 0 && K > 0 && G >= 0 && K + G <= 128, SAR_ERR_UNSUPPORTED,
               "sar_vlad_train_bwd: need S <= 128 and K + G <= 128 (S=%d K=%d G=%d)", S, K, G);
   const size_t smem = (size_t)S * K * sizeof(float);
   { const int arc = allow_max_smem(vlad_train_bwd_kernel, "sar_vlad_train_bwd"); if (arc) return arc; }
-  launch_k(vlad_train_bwd_kernel, dim3(B), dim3(256), smem, (cudaStream_t)stream, x, A, centers, gR, asum, g_scores, gc_part, S, D, K, K + G);
+  launch_k(vlad_train_bwd_kernel, dim3(B), dim3(256), smem, (cudaStream_t)stream, x, A, centers, gR, asum, g_scores, gc_part, g_x, S, D, K, K + G);
   return check_launch("sar_vlad_train_bwd");
 }
 

@@ -15,8 +15,12 @@ losses; `fit_generator(generator, steps_per_epoch, epochs)` loops it over utils.
 Second slice, `HeadTrainer(model, train_pool=True)`: the NetVLAD / GhostVLAD pooling layer (model.py:82-109, VLAD.py:26-49)
 is trained too -- the frozen encoder ends at AR_DS_LN, `sar_vlad_train_fwd` keeps the soft assignments, and the backward
 (`sar_l2norm_bwd` per cluster, `sar_vlad_train_bwd`, two contractions) yields the gradients of the centers and of the
-assignment Conv2D (kernel, bias; l2(1e-4) regularisers).  Not built yet: gradients of the encoder kernels (convolutions,
-Bi-GRU, LayerNorm, CTC), i.e. end-to-end training.
+assignment Conv2D (kernel, bias; l2(1e-4) regularisers).
+
+Third slice, `HeadTrainer(model, train_ds=True)`: AR_DS (Dense + tanh) and AR_DS_LN are trained as well -- the whole accent
+branch above the shared CRNN encoder (model.py:275-296).  The frozen encoder ends at CRNN_LN; `sar_vlad_train_bwd` also returns
+d loss / d descriptors, `sar_ln_train_bwd` differentiates LayerNormalization together with the tanh in front of it.
+Not built yet: gradients of the shared encoder (convolutions, Bi-GRU, CTC branch), i.e. end-to-end training.
 """
 from __future__ import annotations
 
@@ -74,9 +78,9 @@ def bn_train_bwd(x, dy, gamma, mean, inv, want_dx=True):
     return dx, dg, db
 
 
-def bias_act(x, bias, relu=False):
+def bias_act(x, bias, relu=False, tanh=False):
     y = torch.empty_like(x)
-    check(_shim.lib().sar_bias_act_fwd(ptr(x), ptr(bias), ptr(y), x.shape[0], x.shape[1], 1 if relu else 0, stream_ptr()),
+    check(_shim.lib().sar_bias_act_fwd(ptr(x), ptr(bias), ptr(y), x.shape[0], x.shape[1], 1 if relu else (2 if tanh else 0), stream_ptr()),
           "sar_bias_act_fwd")
     ops._count(1)
     return y
@@ -137,15 +141,30 @@ def vlad_train_fwd(x, w_assign, b_assign, centers, K: int, G: int):
     return A, R, asum
 
 
-def vlad_train_bwd(x, A, centers, gR, asum, K: int, G: int):
-    """-> g_scores (B,S,K+G) = d loss / d assignment scores, gc_part (B,K,D) (sum over B = gradient of the K real centers)."""
+def vlad_train_bwd(x, A, centers, gR, asum, K: int, G: int, want_gx: bool = False):
+    """-> g_scores (B,S,K+G) = d loss / d assignment scores, gc_part (B,K,D) (sum over B = gradient of the K real centers)
+    [, g_x (B,S,D): the residual-sum path of d loss / d x; the caller adds g_scores Wa^T]."""
     B, S, D = x.shape
     g_scores = torch.empty((B, S, K + G), device=x.device, dtype=torch.float32)
     gc_part = torch.empty((B, K, D), device=x.device, dtype=torch.float32)
-    check(_shim.lib().sar_vlad_train_bwd(ptr(x), ptr(A), ptr(centers), ptr(gR), ptr(asum), ptr(g_scores), ptr(gc_part), B, S, D, K, G,
-                                         stream_ptr()), "sar_vlad_train_bwd")
+    g_x = torch.empty((B, S, D), device=x.device, dtype=torch.float32) if want_gx else None
+    check(_shim.lib().sar_vlad_train_bwd(ptr(x), ptr(A), ptr(centers), ptr(gR), ptr(asum), ptr(g_scores), ptr(gc_part), ptr(g_x),
+                                         B, S, D, K, G, stream_ptr()), "sar_vlad_train_bwd")
     ops._count(1)
-    return g_scores, gc_part
+    return (g_scores, gc_part, g_x) if want_gx else (g_scores, gc_part)
+
+
+LN_EPS = 1e-14                              # keras_layer_normalization: K.epsilon() ** 2
+
+
+def ln_train_bwd(y, gamma, g_z, tanh_in: bool):
+    """Backward of LayerNormalization (optionally with the tanh that produced its input y): -> (g_pre, g_z * xhat)."""
+    rows, C = y.shape
+    g_pre, gzx = torch.empty_like(y), torch.empty_like(y)
+    check(_shim.lib().sar_ln_train_bwd(ptr(y), ptr(gamma), ptr(g_z), ptr(g_pre), ptr(gzx), rows, C, LN_EPS, int(tanh_in), stream_ptr()),
+          "sar_ln_train_bwd")
+    ops._count(1)
+    return g_pre, gzx
 
 
 def adam_step(p, g, m, v, lr_t, l2=0.0):
@@ -169,16 +188,20 @@ def adam_lr_t(lr: float, iterations: int) -> float:
 class HeadTrainer:
     """Fine-tunes the accent head of a SARModel on the device (module docstring)."""
 
-    def __init__(self, model, lr: float = 0.01, group=None, train_pool: bool = False):
+    def __init__(self, model, lr: float = 0.01, group=None, train_pool: bool = False, train_ds: bool = False):
         """train_pool: also train the NetVLAD / GhostVLAD pooling layer (assignment Conv2D + centers, model.py:82-109):
-        the frozen encoder then ends at AR_DS_LN and the step differentiates vlad() as well (second slice)."""
+        the frozen encoder then ends at AR_DS_LN and the step differentiates vlad() as well (second slice).
+        train_ds (implies train_pool): also train AR_DS (Dense + tanh, l2 regularisers) and AR_DS_LN (model.py:275-276):
+        the whole accent branch above the shared CRNN encoder; the frozen encoder ends at CRNN_LN (third slice)."""
         cfg = model.config
         if not cfg.ar_enable:
             raise ValueError("HeadTrainer needs ar_enable=True")
+        train_pool = bool(train_pool or train_ds)
         if train_pool and cfg.mto not in ("vlad", "gvlad"):
             raise ValueError("train_pool needs mto='vlad' or 'gvlad' (got %r)" % cfg.mto)
         self.model, self.cfg, self.lr, self.group = model, cfg, float(lr), group
         self.train_pool = bool(train_pool)
+        self.train_ds = bool(train_ds)
         self.iterations = 0
         self.head_kind = cfg.metric_loss if cfg.disc_enable else None
         self.disc_key = None
@@ -192,6 +215,11 @@ class HeadTrainer:
             self.pool_keys = [pre + "_center_assignment/kernel", pre + "_center_assignment/bias", pre + "_pool/centers"]
             self.keys += self.pool_keys
             self.l2 |= set(self.pool_keys[:2])           # l2(1e-4) on the assignment kernel and bias; none on the centers
+        self.ds_keys: List[str] = []
+        if self.train_ds:
+            self.ds_keys = ["AR_DS/kernel", "AR_DS/bias", "AR_DS_LN/gamma", "AR_DS_LN/beta"]
+            self.keys += self.ds_keys
+            self.l2 |= set(self.ds_keys[:2])             # DS(hidden_dim, 'tanh'): l2(1e-4) on kernel and bias (model.py:35-42)
         lw = cfg.loss_weights()
         self.w_acc, self.w_disc = float(lw.get("y_accent", 0.0)), float(lw.get("y_disc", 0.0))
         dev = torch.device(model.device)
@@ -205,13 +233,20 @@ class HeadTrainer:
     # ---- frozen encoder: x_data -> integ (B, K*D | D | 2u), or (train_pool) the descriptors (B,S,D) in front of vlad()
     def encode(self, x) -> torch.Tensor:
         out = self.model.forward_device(x, want_intermediates=True, graph=False)
-        return out["ar_ds" if self.train_pool else "integration"].contiguous()
+        return out["crnn" if self.train_ds else ("ar_ds" if self.train_pool else "integration")].contiguous()
 
     # ---- one step on (integ | descriptors, onehot) device tensors
     def step_on_features(self, integ: torch.Tensor, onehot: torch.Tensor) -> Dict[str, float]:
         p, cfg = self.p, self.cfg
         B = integ.shape[0]
-        pool = None
+        pool = ds = None
+        if self.train_ds:                        # AR_DS -> AR_DS_LN on the frozen encoder's CRNN_LN output (B,S,2u)
+            crnn = integ
+            _, S0, C0 = crnn.shape
+            yds = bias_act(gemm(crnn.view(B * S0, C0), p["AR_DS/kernel"]), p["AR_DS/bias"], tanh=True)
+            zds = ops.layernorm(yds, p["AR_DS_LN/gamma"], p["AR_DS_LN/beta"])
+            ds = (crnn.view(B * S0, C0), yds)
+            integ = zds.view(B, S0, -1)
         if self.train_pool:                      # vlad() in training mode: integ = l2norm_k(A^T x - (sum A) c), flattened
             feat = integ
             _, S, D = feat.shape
@@ -265,7 +300,15 @@ class HeadTrainer:
             feat, A, asum, V, rinv, S, D, K, G = pool
             kw_, kb_, kc_ = self.pool_keys
             gR = l2norm_bwd(V, rinv, g_integ.view(B * K, D), 1)                       # (B*K, D) = d loss / d R
-            g_scores, gc_part = vlad_train_bwd(feat, A, p[kc_], gR, asum, K, G)
+            if ds is not None:
+                g_scores, gc_part, g_feat = vlad_train_bwd(feat, A, p[kc_], gR, asum, K, G, want_gx=True)
+                gemm(g_scores.view(B * S, K + G), p[kw_].view(D, K + G), tb=True, out=g_feat.view(B * S, D), beta=1.0)
+                x_ds, yds = ds
+                g_pre, gzx = ln_train_bwd(yds, p["AR_DS_LN/gamma"], g_feat.view(B * S, D), tanh_in=True)
+                g["AR_DS_LN/gamma"], g["AR_DS_LN/beta"] = colsum(gzx), colsum(g_feat.view(B * S, D))
+                g["AR_DS/kernel"], g["AR_DS/bias"] = gemm(x_ds, g_pre, ta=True), colsum(g_pre)
+            else:
+                g_scores, gc_part = vlad_train_bwd(feat, A, p[kc_], gR, asum, K, G)
             g[kw_] = gemm(feat.view(B * S, D), g_scores.view(B * S, K + G), ta=True).view_as(p[kw_])
             g[kb_] = colsum(g_scores.view(B * S, K + G))
             gc = torch.zeros_like(p[kc_])                                             # ghost centers: no gradient

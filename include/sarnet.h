@@ -302,7 +302,7 @@ int sar_bn_train_fwd(const float* x, const float* gamma, const float* beta, floa
                      float* save_mean, float* save_invstd, int rows, int C, float eps, float momentum, void* stream);
 int sar_bn_train_bwd(const float* x, const float* dy, const float* gamma, const float* save_mean, const float* save_invstd,
                      float* dx /* may be NULL */, float* dgamma, float* dbeta, int rows, int C, void* stream);
-/* y = act(x + bias) on (rows, C), act in {SAR_ACT_NONE, SAR_ACT_RELU}; out = g * (h > 0); out (C) = column sums of g (rows, C). */
+/* y = act(x + bias) on (rows, C), act in {SAR_ACT_NONE, SAR_ACT_RELU, SAR_ACT_TANH}; out = g * (h > 0); out (C) = column sums of g (rows, C). */
 int sar_bias_act_fwd(const float* x, const float* bias, float* y, long long rows, int C, int act, void* stream);
 int sar_relu_bwd(const float* g, const float* h, float* out, long long n, void* stream);
 int sar_colsum_fwd(const float* g, float* out, int rows, int C, void* stream);
@@ -334,7 +334,14 @@ int sar_unit_norm_fwd(float* w, int D, int n, void* stream);
 int sar_vlad_train_fwd(const float* x, const float* w_assign, const float* b_assign, const float* centers, float* A, float* R,
                        float* asum, int B, int S, int D, int K, int G, void* stream);
 int sar_vlad_train_bwd(const float* x, const float* A, const float* centers, const float* gR, const float* asum, float* g_scores,
-                       float* gc_part, int B, int S, int D, int K, int G, void* stream);
+                       float* gc_part, float* g_x /* may be NULL: (B,S,D) = sum_k A[s,k] gR[k,:], the residual-sum path of d loss / d x;
+                       the score path g_scores w_assign^T is one sar_gemm_fwd with beta = 1 */,
+                       int B, int S, int D, int K, int G, void* stream);
+/* Backward of LN(tanh(.)) = DS(..., 'tanh') -> LayerNormalization (model.py:32-42, the AR_DS / AR_DS_LN pair): y (rows, C) is the
+ * LN input (= tanh(pre) when tanh_in), g_z = d loss / d LN output; g_pre = d loss / d pre (or d loss / d y when !tanh_in);
+ * gz_xhat = g_z * xhat, whose column sums are d loss / d gamma (d loss / d beta = column sums of g_z).  eps = 1e-14. */
+int sar_ln_train_bwd(const float* y, const float* gamma, const float* g_z, float* g_pre, float* gz_xhat, int rows, int C, float eps,
+                     int tanh_in, void* stream);
 
 /* ---- feature front-end ------------------------------------------------------------- */
 

@@ -261,3 +261,82 @@ def test_train_on_batch_with_pooling_layer_lowers_the_loss(cuda_device):
     tr.sync_to_model()
     assert not np.allclose(c0[:8], model.weights["gvlad_pool/centers"][:8])
     assert np.array_equal(c0[8:], model.weights["gvlad_pool/centers"][8:])       # ghost centers never move
+
+
+def test_ln_tanh_backward_matches_autograd(cuda_device):
+    from aesrc2020_b200 import training as T
+    rng = np.random.RandomState(4)
+    rows, C = 37, 256
+    pre = rng.randn(rows, C) * 0.8
+    gamma, beta = rng.uniform(0.5, 1.5, C), rng.randn(C) * 0.1
+    gz = rng.randn(rows, C)
+    for tanh_in in (True, False):
+        pt = torch.tensor(pre, requires_grad=True)
+        gt, bt = torch.tensor(gamma, requires_grad=True), torch.tensor(beta, requires_grad=True)
+        y = torch.tanh(pt) if tanh_in else pt
+        mu = y.mean(-1, keepdim=True)
+        z = (y - mu) / torch.sqrt(((y - mu) ** 2).mean(-1, keepdim=True) + 1e-14) * gt + bt
+        (z * torch.as_tensor(gz)).sum().backward()
+        g_pre, gzx = T.ln_train_bwd(dev(y.detach().numpy()), dev(gamma), dev(gz), tanh_in)
+        assert norm_err(g_pre, pt.grad) < 2e-5
+        assert norm_err(T.colsum(gzx), gt.grad) < 2e-5 and norm_err(T.colsum(dev(gz)), bt.grad) < 2e-6
+
+
+def test_head_trainer_third_slice_matches_the_oracle(cuda_device):
+    """HeadTrainer(train_ds=True).step_on_features on CRNN_LN features vs train_oracle.train_step(pool=dict(train_ds=True)):
+    AR_DS / AR_DS_LN / pooling / head gradients and the parameters after two Adam steps."""
+    from aesrc2020_b200 import model as mdl, training as T
+    K, G, Dh = 8, 2, 256
+    model, _ = mdl.SAR_Net((200, 80, 1), ctc_enable=True, disc_enable=True, res_type="res34", res_filters=32, mto="gvlad",
+                           vlad_clusters=K, ghost_clusters=G, metric_loss="cosface", margin=0.3)
+    params = _params("cosface", K * Dh, seed=13)
+    rng = np.random.RandomState(31)
+    f32 = lambda a: np.asarray(a, np.float32).astype(np.float64)
+    params["gvlad_center_assignment/kernel"] = f32(rng.randn(1, 1, Dh, K + G) * 0.1)
+    params["gvlad_center_assignment/bias"] = f32(rng.randn(K + G) * 0.1)
+    params["gvlad_pool/centers"] = f32(rng.randn(K + G, Dh) * 0.3)
+    params["AR_DS/kernel"] = f32(rng.randn(2 * Dh, Dh) / np.sqrt(2 * Dh))
+    params["AR_DS/bias"] = f32(rng.randn(Dh) * 0.1)
+    params["AR_DS_LN/gamma"] = f32(rng.uniform(0.7, 1.3, Dh))
+    params["AR_DS_LN/beta"] = f32(rng.randn(Dh) * 0.1)
+    for k, v in params.items():
+        model.weights[k] = v.astype(np.float32)
+    tr = T.HeadTrainer(model, lr=0.01, train_ds=True)
+    assert tr.train_pool and set(TO.DS_KEYS) <= set(tr.keys)
+    B, S = 12, 10
+    lab = rng.randint(0, 8, B)
+    pool = dict(mto="gvlad", vlad_clusters=K, ghost_clusters=G, train_ds=True)
+    state, p_or, p_prev = {}, dict(params), dict(params)
+    l2k = set(TO.l2_keys(True, "cosface")) | set(TO.pool_l2_keys("gvlad")) | {"AR_DS/kernel", "AR_DS/bias"}
+    for it in range(2):
+        crnn = (rng.randn(B, S, 2 * Dh) + (np.eye(8)[lab] @ rng.randn(8, 2 * Dh))[:, None, :] * 0.5).astype(np.float32)
+        onehot = np.eye(8, dtype=np.float32)[lab]
+        p_or, state, l_or, g_or = TO.train_step(p_or, state, crnn, onehot, lr=0.01, iterations=it, disc_enable=True,
+                                                metric_loss="cosface", margin=0.3, w_accent=tr.w_acc, w_disc=tr.w_disc, pool=pool)
+        got = tr.step_on_features(dev(crnn), dev(onehot))
+        assert abs(got["loss_disc"] - l_or["loss_disc"]) < 2e-4 * max(1, abs(l_or["loss_disc"]))
+        for k in tr.keys:
+            if k in ("AR_BN1/beta", "AR_EMBEDDING/bias"):
+                continue
+            want = g_or[k] - (2 * TO.L2_REG * p_prev[k] if k in l2k else 0.0)
+            got_k = tr.last_grads[k].cpu().numpy().astype(np.float64)
+            err = float(np.max(np.abs(got_k - want)) / max(np.max(np.abs(want)), 1e-6))
+            assert err < 1e-3, (it, k, err)
+        p_prev = {k: v.copy() for k, v in p_or.items()}
+        for k in TO.DS_KEYS + TO.pool_keys("gvlad"):
+            assert norm_err(tr.p[k], p_or[k]) < 2e-3, (it, k)
+
+
+def test_train_on_batch_third_slice_lowers_the_loss(cuda_device):
+    from aesrc2020_b200 import model as mdl, training as T, utils as us
+    model, _ = mdl.SAR_Net((200, 80, 1), disc_enable=True, res_type="res34", res_filters=32, mto="gvlad", vlad_clusters=8,
+                           ghost_clusters=2, metric_loss="arcface", margin=0.3)
+    x, y = us.synthetic_batch(model.config, 16, seed=3)
+    w0 = model.weights["AR_DS/kernel"].copy()
+    tr = T.HeadTrainer(model, lr=0.02, train_ds=True)
+    hist = [tr.train_on_batch(x, y)["loss"] for _ in range(25)]
+    assert hist[-1] < 0.7 * hist[0], hist
+    tr.sync_to_model()
+    assert not np.allclose(w0, model.weights["AR_DS/kernel"])
+    out = model.predict(x, batch_size=16)                   # the inference engine rebuilds with the trained weights
+    assert np.all(np.isfinite(out[0]))

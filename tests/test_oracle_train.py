@@ -137,3 +137,39 @@ def test_pooled_gradients_match_finite_differences(mto, G):
             assert abs(fd - g[i]) <= 2e-6 * max(1.0, abs(fd)) + 2e-8, (k, i, fd, g[i])
     if G:
         assert np.all(grads[mto + "_pool/centers"][K:] == 0.0)                 # VLAD.py:44-45 drops the ghost rows
+
+
+def test_third_slice_gradients_match_finite_differences():
+    """Third slice: AR_DS (Dense + tanh) -> AR_DS_LN -> vlad() -> head on the CRNN_LN output: autograd vs finite differences
+    for the Dense kernel / bias and the LayerNormalization gamma / beta."""
+    B, S, C0, Dd, K, G, n = 4, 5, 10, 6, 4, 2, 8
+    rng = np.random.RandomState(17)
+    params = _params("arcface", D=K * Dd)
+    params["gvlad_center_assignment/kernel"] = rng.randn(1, 1, Dd, K + G) * 0.5
+    params["gvlad_center_assignment/bias"] = rng.randn(K + G) * 0.1
+    params["gvlad_pool/centers"] = rng.randn(K + G, Dd) * 0.5
+    params["AR_DS/kernel"] = rng.randn(C0, Dd) * 0.4
+    params["AR_DS/bias"] = rng.randn(Dd) * 0.1
+    params["AR_DS_LN/gamma"] = rng.uniform(0.7, 1.3, Dd)
+    params["AR_DS_LN/beta"] = rng.randn(Dd) * 0.1
+    x = rng.randn(B, S, C0)
+    onehot = np.eye(n)[rng.randint(0, n, B)]
+    kw = dict(disc_enable=True, metric_loss="arcface", margin=0.3, w_accent=0.01, w_disc=0.6)
+    pool = dict(mto="gvlad", vlad_clusters=K, ghost_clusters=G, train_ds=True)
+    _, state, losses, grads = TO.train_step(params, {}, x, onehot, lr=0.01, iterations=0, pool=pool, **kw)
+    assert set(TO.DS_KEYS) <= set(grads)
+
+    def loss_of(pp):
+        t = {k: torch.as_tensor(v) for k, v in pp.items()}
+        return float(TO.pooled_head_loss(t, torch.as_tensor(x), torch.as_tensor(onehot), **pool, **kw)[0])
+    for k in TO.DS_KEYS + ["gvlad_pool/centers"]:
+        g = grads[k]
+        for _ in range(5):
+            i = tuple(rng.randint(0, s_) for s_ in g.shape)
+            if k == "gvlad_pool/centers":
+                i = (rng.randint(0, K),) + i[1:]
+            h = 1e-6
+            pp, pm = {q: v.copy() for q, v in params.items()}, {q: v.copy() for q, v in params.items()}
+            pp[k][i] += h; pm[k][i] -= h
+            fd = (loss_of(pp) - loss_of(pm)) / (2 * h)
+            assert abs(fd - g[i]) <= 2e-6 * max(1.0, abs(fd)) + 2e-8, (k, i, fd, g[i])
