@@ -525,6 +525,41 @@ def fbank_bench(runner, steps, peaks):
     return roof, e2e_pcm
 
 
+# ====================================================================================== training slice
+def train_slice_bench(dev, rank, world, B=64, steps=10):
+    """one optimisation step of the accent branch above the frozen shared encoder --
+    training.HeadTrainer(train_ds=True).train_on_batch: encoder forward, AR_DS / AR_DS_LN / GhostVLAD / embedding / classifier /
+    ArcFace forward + backward in training mode, ONE flat gradient all-reduce over the ranks, Keras Adam.  Weak scaling."""
+    import torch.distributed as tdist
+    from aesrc2020_b200 import model as mdl, training as T, utils as us
+    with contextlib.redirect_stdout(io.StringIO()):
+        model, _ = mdl.SAR_Net((500, 80, 1), **dict(CONFIGS["cfg2"]["kw"]))
+    x, y = us.synthetic_batch(model.config, B, seed=100 + rank)
+    tr = T.HeadTrainer(model, lr=0.01, train_ds=True)
+    xd = {k: model._to_device(k, v) for k, v in x.items()}
+    for _ in range(3):
+        tr.train_on_batch(xd, y)
+    torch.cuda.synchronize()
+    if world > 1:
+        tdist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        last = tr.train_on_batch(xd, y)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+        ms = float(t.item())
+    return {"workload": "accent branch above the frozen CRNN encoder (AR_DS .. y_accent / y_disc), B=%d/GPU, fwd + bwd + Adam" % B,
+            "ms_per_step": ms, "value": world * B / (ms * 1e-3), "unit": "utt/s (training, partial graph)",
+            "trainable_parameters": int(sum(tr.p[k].numel() for k in tr.keys)), "allreduce_bytes_per_step": 4 * int(sum(tr.p[k].numel() for k in tr.keys)) if world > 1 else 0,
+            "loss": float(last["loss"]), "scaling": "weak",
+            "note": "eager launches (no CUDA graph), includes the frozen encoder's inference forward; gradients of the shared encoder are not built"}
+
+
 # ====================================================================================== strong scaling
 def strong_scaling(dev, rank, world, peaks, global_b=4096, micro=512, reps=2):
     """configs[4]: global B=4096, split contiguously over the ranks (dist.shard_slice), every rank runs its share as
@@ -676,7 +711,7 @@ def main():
     R.close()
 
     # ---------------------------------------------------------------- the other north-star configurations
-    extra, strong, roofline_vlad = None, None, None
+    extra, strong, roofline_vlad, train_slice = None, None, None, None
     if not quick:
         extra = {}
         vlad_in_graph = {64: vlad_ms} if (vlad_ms and args.config == "cfg2" and B == 64) else {}
@@ -696,6 +731,10 @@ def main():
             strong = strong_scaling(dev, rank, world, peaks)
         except Exception as ex:
             strong = {"error": "%s: %s" % (type(ex).__name__, ex)}
+        try:
+            train_slice = train_slice_bench(dev, rank, world)
+        except Exception as ex:
+            train_slice = {"error": "%s: %s" % (type(ex).__name__, ex)}
         if rank == 0:
             try:
                 roofline_vlad = vlad_roofline(dev, peaks, vlad_ms_in_graph=vlad_in_graph)
@@ -747,6 +786,8 @@ def main():
         line["sustained"] = sustained
     if roofline_vlad:
         line["roofline_vlad"] = roofline_vlad
+    if train_slice:
+        line["train_slice"] = train_slice
     if roofline_fbank:
         line["roofline_fbank"] = roofline_fbank
     if e2e_pcm:
