@@ -131,6 +131,50 @@ def test_many_tiles_persistent_loop(cuda_device):
     _case(48, 125, 20, 32, 32, 1)                     # 48*126*21/128 = 993 tiles
 
 
+PAIR_CASES = [
+    # (B, H, W, Cin, Cout, kwargs): shapes conv_tc_pair_kernel accepts (>= 2 M tiles, 64-wide chunks, streamed weights)
+    (4, 13, 10, 128, 128, dict(dense=True)),                       # 5 M tiles: the odd tail's second tile lies past the tensor
+    (4, 13, 10, 128, 128, dict(residual=True)),                    # identity shortcut rows in the epilogue
+    (4, 13, 10, 128, 128, dict(proj=(64, 2))),                     # 1x1 / s2 projection shortcut chunks (s3b1)
+    (3, 9, 7, 256, 256, dict(residual=True, dense=True)),          # two N tiles, stage 4
+    (3, 9, 7, 256, 256, dict(proj=(128, 2))),                      # s4b1
+    (2, 13, 10, 128, 128, dict(out_split=True)),                   # phase-split outputs for a strided consumer
+    (40, 31, 12, 256, 256, dict(residual=True)),                   # 130 x 2 pairs > 74 clusters: multi-round, own epilogue staging
+]
+
+
+@pytest.mark.skipif(__import__("os").environ.get("SAR_TC_PAIR") != "2", reason="inner half of test_cta_pair_kernel_forced")
+@pytest.mark.parametrize("i", range(len(PAIR_CASES)))
+def test_pair_inner(cuda_device, i):
+    """Runs only inside test_cta_pair_kernel_forced's child process (SAR_TC_PAIR=2 is read once per process)."""
+    B, H, W, Cin, Cout, kw = PAIR_CASES[i]
+    names = []
+    try:
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            _case(B, H, W, Cin, Cout, 1, **kw)
+        names = [e.key for e in prof.key_averages()]
+    except ImportError:
+        _case(B, H, W, Cin, Cout, 1, **kw)
+    if names:                       # CUPTI saw this process' launches: the CTA-pair kernel must be among them
+        assert any("conv_tc_pair_kernel" in n for n in names), names
+
+
+def test_cta_pair_kernel_forced(cuda_device):
+    """conv_tc_pair_kernel (tcgen05.mma.cta_group::2, M = 256 over a CTA pair, each SM streams half of every weight tile)
+    is chosen by the library only for layers with >= 2 tiles per SM (B >= 256 shards; covered end to end by
+    test_full_size_batch_matches_oracle_on_a_slice).  Here it is FORCED (SAR_TC_PAIR=2) onto small layers in a child
+    process and every case is compared with the float64 oracle: odd tile tails, identity and projection shortcuts,
+    two N tiles, phase-split outputs, multi-round persistent loop."""
+    import os, subprocess, sys
+    env = dict(os.environ, SAR_TC_PAIR="2")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_conv_tc.py"), "-q", "-x", "-m", "gpu",
+                        "-k", "test_pair_inner", "-p", "no:cacheprovider"], env=env, cwd=root, capture_output=True, text=True, timeout=220)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "%d passed" % len(PAIR_CASES) in r.stdout, r.stdout[-1000:]
+
+
 @pytest.mark.parametrize("T,B,F0", [(500, 3, 64), (300, 2, 64), (37, 1, 64), (7, 2, 64), (801, 1, 64), (200, 150, 64),
                                     (200, 2, 32), (37, 1, 16)])
 def test_stem_pool_matches_oracle(cuda_device, T, B, F0):
