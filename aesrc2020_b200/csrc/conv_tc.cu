@@ -79,7 +79,7 @@ struct TcParams {
   int* flag_done;                        // [m_tiles] epilogue items finished per M tile of THIS layer (or null)
   const int* flag_dep;                   // [m_tiles] the same counters of the layer this one reads (or null)
   int flag_need;                         // items per M tile = 4 * Cout / 32
-  int epi_mode;                          // epilogue mode of this layer (-1, 0, 2, 3)
+  int epi_mode;                          // epilogue mode of this layer (-1, 0, 2, 3, 4)
   int tma_out;                           // plane outputs of an unsplit map leave through TMA stores (see epilogue_item)
   int pair;                              // conv_tc_pair_kernel: the accumulator-drained arrivals go to the LEADER CTA's barrier
   // The residual stream between the blocks of a stage as ONE fp32 plane [R][Cout] (flat-pad rows) instead of hi/lo
@@ -136,6 +136,8 @@ __device__ __noinline__ float tanh_precise(float x) { return tanhf(x); }
 // MODE < 0: every output option is a run-time flag.  MODE >= 0 fixes the combination at compile time (the hot
 // residual-block cases; the per-round flag tests were ~25 % of the executed instructions):
 //   bit 0 = identity shortcut, bit 1 = raw planes out, the activated planes (BN->ReLU) are always written.
+//   MODE 4 = the stage-ending conv2: fp32 shortcut stream in, raw hi/lo PLANES out (the next stage's projection operand)
+//   + activated planes, both phase-split for the strided consumers (generic stores, shortcut row held in registers).
 // CHAIN (conv_tc_chain_kernel): the bias / BN vectors of the item's 32 columns are staged from global memory into a
 // per-warp area (s_bias_u, 32 floats apart), shortcut rows are read with ld.global.cg (another CTA wrote them
 // during this very kernel), and the finished item is published in the layer's per-M-tile counter.
@@ -152,9 +154,9 @@ __device__ __forceinline__ void epilogue_item(const TcParams& p, const OutMaps& 
   const int mt = tmn / p.n_tiles, nt = tmn - mt * p.n_tiles;
   const int n0 = nt * BN, c0 = c * 32;
   const long long row0 = (long long)mt * TC_BM + quad * 32;
-  const bool res32 = p.res32 != nullptr, raw32 = p.out_raw32 != nullptr;
-  const bool has_res = MODE < 0 ? (p.res != nullptr || res32) : ((MODE & 1) != 0);
-  const bool out_raw = MODE < 0 ? (p.out_raw != nullptr || raw32) : ((MODE & 2) != 0);
+  const bool res32 = MODE == 4 ? true : p.res32 != nullptr, raw32 = MODE == 4 ? false : p.out_raw32 != nullptr;
+  const bool has_res = MODE < 0 ? (p.res != nullptr || res32) : (MODE == 4 || (MODE & 1) != 0);
+  const bool out_raw = MODE < 0 ? (p.out_raw != nullptr || raw32) : (MODE == 4 || (MODE & 2) != 0);
   const bool out_act = MODE < 0 ? (p.out_act != nullptr) : true;
   const bool out_dense = MODE < 0 ? (p.out_dense != nullptr) : false;
   const int act_kind = MODE < 0 ? p.act_kind : 0;
@@ -224,7 +226,7 @@ __device__ __forceinline__ void epilogue_item(const TcParams& p, const OutMaps& 
   // TMA-store path (plane outputs of an unsplit map): the staging tiles ARE the 64B-swizzled boxes of the output
   // tensor maps (slot = piece ^ ((row >> 1) & 3) is CU_TENSOR_MAP_SWIZZLE_64B for 64-byte rows), so the write-out
   // is one cp.async.bulk.tensor store per plane instead of an LDS -> STG loop; pad rows are staged as zeros.
-  const bool tma_out = p.tma_out != 0;
+  const bool tma_out = MODE == 4 ? false : p.tma_out != 0;
   const bool zrow = tma_out && drow_p < 0;
   mbar_wait(&tfull_bar[as], aphase);
   tc_fence_after();
@@ -261,7 +263,7 @@ __device__ __forceinline__ void epilogue_item(const TcParams& p, const OutMaps& 
   // takes its whole shortcut row into registers
   // ... and the mirror case, hi/lo plane shortcut in, fp32 raw sum out (the first block of a stage with an identity
   // shortcut on the stem's planes: res18 with 64 filters).  (The host routes both combinations to MODE -1.)
-  const bool res_to_regs = MODE < 0 && has_res && out_raw && (res32 != raw32);
+  const bool res_to_regs = MODE == 4 || (MODE < 0 && has_res && out_raw && (res32 != raw32));
   uint4 rrow[8];
   if (res_to_regs) {
     if (res32) {
@@ -277,7 +279,7 @@ __device__ __forceinline__ void epilogue_item(const TcParams& p, const OutMaps& 
     __syncwarp();
   }
   const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 2 * BN + c0);
-#pragma unroll 2
+#pragma unroll(MODE == 4 ? 4 : 2)
   for (int g = 0; g < 4; ++g) {                      // 8 columns per round
     uint32_t r0[8], r1[8];
     tmem_ld8(tbase + (uint32_t)(8 * g), r0);
@@ -1452,6 +1454,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_tc_chain_kernel(const __gr
             switch (p.epi_mode) {
               case 0: epilogue_item<0, true>(p, om, tile, c, it, quad, lane, tmem_base, tfull_bar, tempty_bar, vec_u, stage_u, pubp); break;
               case 3: epilogue_item<3, true>(p, om, tile, c, it, quad, lane, tmem_base, tfull_bar, tempty_bar, vec_u, stage_u, pubp); break;
+              case 4: epilogue_item<4, true>(p, om, tile, c, it, quad, lane, tmem_base, tfull_bar, tempty_bar, vec_u, stage_u, pubp); break;
               default: epilogue_item<-1, true>(p, om, tile, c, it, quad, lane, tmem_base, tfull_bar, tempty_bar, vec_u, stage_u, pubp); break;
             }
             if (quad == 0 && lane == 0 && c == 0) { CH_STAMP(it, 6) }
@@ -1673,6 +1676,9 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
   if (d->out_act && !d->out_dense && d->act_kind == 0 && !p.split && !(d->res_f32 && d->out_raw) && !(d->res && d->out_raw_f32))
     mode = ((d->res || d->res_f32) ? 1 : 0) | ((d->out_raw || d->out_raw_f32) ? 2 : 0);
   if (mode == 1) mode = -1;                                            // (no compile-time instance of shortcut-without-raw)
+  static const bool mode4_ok = !(getenv("SAR_TC_MODE4") && getenv("SAR_TC_MODE4")[0] == '0');
+  if (mode4_ok && p.split && d->out_act && d->out_raw && d->res_f32 && !d->res && !d->out_raw_f32 && !d->out_dense && d->act_kind == 0)
+    mode = 4;                                                          // the stage-ending conv2 (see epilogue_item)
   static const bool epi16_ok = !(getenv("SAR_TC_EPI16") && getenv("SAR_TC_EPI16")[0] == '0');
   static const bool epi16_thin_ok = !(getenv("SAR_TC_EPI16_THIN") && getenv("SAR_TC_EPI16_THIN")[0] == '0');
   size_t fixed = 0, budget = 0;
@@ -1807,6 +1813,7 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
         case 0: lrc = launch_p(conv_tc_pair_kernel<0>); break;
         case 2: lrc = launch_p(conv_tc_pair_kernel<2>); break;
         case 3: lrc = launch_p(conv_tc_pair_kernel<3>); break;
+        case 4: lrc = launch_p(conv_tc_pair_kernel<4>); break;
         default: lrc = launch_p(conv_tc_pair_kernel<-1>); break;
       }
       if (lrc) return lrc;
@@ -1819,7 +1826,7 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
     if (p.epi_alias && smem - fixed < (size_t)EPI_BYTES) smem = fixed + EPI_BYTES;    // aliased staging needs 64 KB of operand region
     auto launch = [&](auto kern) -> int {
       { const int arc = allow_max_smem(kern, "sar_conv_tc_fwd"); if (arc) return arc; }
-      const int m_eff = (mode == 0 || mode == 2 || mode == 3) ? mode : -1;
+      const int m_eff = (mode == 0 || mode == 2 || mode == 3 || mode == 4) ? mode : -1;
       launch_k(kern, dim3(grid), dim3(threads_for(smem - fixed, m_eff)), smem, (cudaStream_t)stream, mapA, mapS, mapWm, mapWs, om, p, sp);
       return 0;
     };
@@ -1830,6 +1837,7 @@ extern "C" int sar_conv_tc_fwd(const sar_tc_conv* d, void* stream) {
         case 0: return launch(conv_tc_slab_kernel<KCv, RSv, 0>);
         case 2: return launch(conv_tc_slab_kernel<KCv, RSv, 2>);
         case 3: return launch(conv_tc_slab_kernel<KCv, RSv, 3>);
+        case 4: return launch(conv_tc_slab_kernel<KCv, RSv, 4>);
         default: return launch(conv_tc_slab_kernel<KCv, RSv, -1>);
       }
     };
@@ -1938,6 +1946,9 @@ extern "C" int sar_conv_tc_chain_grid_fwd(const sar_tc_conv* descs, int n, void*
       const int m = ((d->res || d->res_f32) ? 1 : 0) | ((d->out_raw || d->out_raw_f32) ? 2 : 0);
       if ((m == 0 || m == 3) && !(d->res_f32 && d->out_raw) && !(d->res && d->out_raw_f32)) p.epi_mode = m;
     }
+    if (p.split && d->out_act && d->out_raw && d->res_f32 && !d->res && !d->out_raw_f32 && !d->out_dense && d->act_kind == 0 &&
+        !(getenv("SAR_TC_MODE4") && getenv("SAR_TC_MODE4")[0] == '0'))
+      p.epi_mode = 4;
     const int ktot = 9 * d->a_ch + (d->s ? d->s_ch : 0);
     int rc;
     if ((rc = make_map(&P.mapA, d->a, d->a_rows, d->a_ch, d->a_planes, p.kc_main, sp.slab_rows))) return rc;

@@ -176,6 +176,16 @@ def vlad_algorithmic_work(B, S, D, K, G, e=ACT_BYTES):
     return 4.0 * B * S * D * (K + G), e * B * S * D + 4.0 * B * K * D + 4.0 * (2 * (K + G) * D + (K + G))
 
 
+def workload_config(cfgd, B, T, plan, in_bytes, rotate, world):
+    """The `config` object of the JSON line -- built by the SAME function for both arms (`--impl ours` / `--impl reference`),
+    so the driver's same-config check compares equal dicts; arm-specific details live in other keys of the line."""
+    act_mb = conv_algorithmic_work(plan, B, ACT_BYTES)[1] / 1e6 * 2 / 3
+    return {"workload": cfgd["workload"], "per_gpu_batch": B, "frames": T, "seq_len": plan.seq_len,
+            "l2": "inputs rotate over %d distinct batches (%.0f MB > 126 MB L2); activations %.0f MB/step"
+                  % (rotate, rotate * in_bytes / 1e6, act_mb),
+            "parallelism": "dp%d (batch-sharded, 1 all-reduce of 8 floats/step)" % world}
+
+
 def conv_roofline(plan, B, conv_ms, step_ms, peaks):
     F, Bt, nconv = conv_algorithmic_work(plan, B, ACT_BYTES)
     t = conv_ms * 1e-3
@@ -604,13 +614,18 @@ def run_reference(args, cfgd):
     cfg = SARConfig(input_shape=(cfgd["T"], 80, 1), **cfgd["kw"])
     w = W.init_weights(cfg, 1234)
     Bs = min(args.ref_batch, cfgd["B"])
-    x, _ = us.synthetic_batch(cfg, Bs, seed=2020)
-    fwd = lambda: O.sar_net_forward(w, x, **cfg.model_kwargs(), dtype=torch.float32)
-    for _ in range(max(1, min(args.warmup, 2))):
-        fwd()
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    # the same rotation over distinct synthetic batches as the GPU arm (seeds as in StepRunner); each timed step is a
+    # Bs-utterance sample of one of them
+    nrot = max(1, args.rotate)
+    xs = [us.synthetic_batch(cfg, Bs, seed=2020 + i)[0] for i in range(nrot)]
+    in_bytes = sum(np.asarray(v).nbytes for v in us.synthetic_batch(cfg, 1, seed=1)[0].values()) * cfgd["B"]
+    fwd = lambda i: O.sar_net_forward(w, xs[i % nrot], **cfg.model_kwargs(), dtype=torch.float32)
+    for i in range(max(1, min(args.warmup, 2))):
+        fwd(i)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        fwd()
+    for i in range(args.steps):
+        fwd(i)
     dt = (time.perf_counter() - t0) / args.steps
     v = Bs / dt
     sample = ("%d of the %d utterances of one step per timed step, throughput normalised per utterance (torch-CPU fp32 "
@@ -619,10 +634,10 @@ def run_reference(args, cfgd):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": cfgd["workload"], "per_gpu_batch": cfgd["B"], "frames": cfgd["T"],
-                   "note": "reference arm = torch-CPU restatement of the Keras forward (oracle port, kind 'port'); the literal "
-                           "Keras/TF graph is not runnable in this image; each timed step is a %d-utterance sample of the "
-                           "%d-utterance batch" % (Bs, cfgd["B"])},
+        "config": workload_config(cfgd, cfgd["B"], cfgd["T"], cfg.plan(), in_bytes, args.rotate, world),
+        "note": "reference arm = torch-CPU restatement of the Keras forward (oracle port, kind 'port'); the literal "
+                "Keras/TF graph is not runnable in this image; each timed step is a %d-utterance sample of the "
+                "%d-utterance batch, throughput normalised per utterance" % (Bs, cfgd["B"]),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -771,11 +786,8 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16x2 (fp16 hi+lo split operands, fp32 accumulate; fp32 elsewhere)", "data": "synthetic",
-        "config": {"workload": cfgd["workload"], "per_gpu_batch": B, "frames": T, "seq_len": plan.seq_len,
-                   "l2": "inputs rotate over %d distinct batches (%.0f MB > 126 MB L2); activations %.0f MB/step"
-                         % (args.rotate, args.rotate * in_bytes / 1e6, roof["algorithmic_mb_per_step"] * 2 / 3),
-                   "parallelism": "dp%d (batch-sharded, 1 all-reduce of 8 floats/step)" % world,
-                   "pipeline": "%d independent step(s) in flight (one stream + CUDA graph + buffer set each)" % (1 if args.eager else args.pipeline)},
+        "config": workload_config(cfgd, B, T, plan, in_bytes, args.rotate, world),
+        "pipeline": "%d independent step(s) in flight (one stream + CUDA graph + buffer set each)" % (1 if args.eager else args.pipeline),
         "e2e": e2e, "gpu_launches": launches, "gpu_launches_per_step": launches_per_step, "roofline": roof, "clocks": clocks,
         "wall_s": None,
     }

@@ -140,6 +140,7 @@ PAIR_CASES = [
     (3, 9, 7, 256, 256, dict(proj=(128, 2))),                      # s4b1
     (2, 13, 10, 128, 128, dict(out_split=True)),                   # phase-split outputs for a strided consumer
     (40, 31, 12, 256, 256, dict(residual=True)),                   # 130 x 2 pairs > 74 clusters: multi-round, own epilogue staging
+    (4, 32, 5, 128, 128, dict(res32_split=True)),                  # stage-ending conv2: fp32 shortcut in, split planes out (MODE 4)
 ]
 
 
@@ -148,14 +149,15 @@ PAIR_CASES = [
 def test_pair_inner(cuda_device, i):
     """Runs only inside test_cta_pair_kernel_forced's child process (SAR_TC_PAIR=2 is read once per process)."""
     B, H, W, Cin, Cout, kw = PAIR_CASES[i]
+    run = (lambda: _res32_case(B, H, W, Cin, True, True)) if kw.get("res32_split") else (lambda: _case(B, H, W, Cin, Cout, 1, **kw))
     names = []
     try:
         from torch.profiler import profile, ProfilerActivity
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
-            _case(B, H, W, Cin, Cout, 1, **kw)
+            run()
         names = [e.key for e in prof.key_averages()]
     except ImportError:
-        _case(B, H, W, Cin, Cout, 1, **kw)
+        run()
     if names:                       # CUPTI saw this process' launches: the CTA-pair kernel must be among them
         assert any("conv_tc_pair_kernel" in n for n in names), names
 
@@ -319,12 +321,19 @@ def test_vlad_tc_unsupported_shapes_are_refused(cuda_device):
 
 @pytest.mark.parametrize("B,H,W,C,res_in,split_out", [(2, 11, 10, 64, True, False), (3, 25, 20, 32, True, False),
                                                        (2, 6, 3, 256, True, False), (2, 7, 5, 128, False, False),
-                                                       (48, 125, 20, 32, True, False), (2, 13, 10, 64, True, True)])
+                                                       (48, 125, 20, 32, True, False), (2, 13, 10, 64, True, True),
+                                                       (48, 125, 20, 32, True, True), (3, 32, 5, 128, True, True),
+                                                       (24, 63, 10, 64, True, True)])
 def test_residual_stream_as_one_fp32_plane(cuda_device, B, H, W, C, res_in, split_out):
+    _res32_case(B, H, W, C, res_in, split_out)
+
+
+def _res32_case(B, H, W, C, res_in, split_out):
     """res_f32 / out_raw_f32 (sar_tc_conv): the identity shortcut read from, and the raw sum written to, ONE fp32 plane of
     flat-pad rows instead of hi/lo planes -- same values as the planes form (the stream is only added, never an MMA
-    operand).  Covers the compile-time epilogue modes (res + raw + act), the generic one (raw32 in, split planes out: a
-    stage-ending conv2) and a many-tile persistent launch."""
+    operand).  Covers the compile-time epilogue modes (res + raw + act), the stage-ending conv2 (fp32 shortcut in, phase-split
+    raw + activated planes out: epilogue MODE 4, at the stage-1 / 2 / 3 geometries incl. the 16-warp thin form) and many-tile
+    persistent launches."""
     from aesrc2020_b200 import tc
     rng = np.random.RandomState(H * 31 + C)
     x = _f32(rng.randn(B, H, W, C))
