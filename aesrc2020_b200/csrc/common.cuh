@@ -82,6 +82,16 @@ constexpr size_t SAR_MAX_DYN_SMEM = 227 * 1024;
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// NaN-propagating max / ReLU (max.NaN.f32): fmaxf returns the non-NaN operand, which would turn an fp16 overflow of the
+// tensor-core operand planes (|x| >= 65504 -> inf in the hi plane, inf - inf = NaN in the accumulator) into silent zeros
+// at the next ReLU / max-pool.  With these the NaN reaches the model outputs, where the host checks for it (model._finite).
+__device__ __forceinline__ float fmax_nan(float a, float b) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ float relu_nan(float a) { return fmax_nan(a, 0.f); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

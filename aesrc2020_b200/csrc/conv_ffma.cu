@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(256) conv_ffma_kernel(ConvP p) {
         if (p.pre_scale) {
 #pragma unroll
           for (int i = 0; i < 8; ++i)
-            a_reg[i] = fmaxf(fmaf(a_reg[i], __ldg(p.pre_scale + ci + i), __ldg(p.pre_shift + ci + i)), 0.f);
+            a_reg[i] = relu_nan(fmaf(a_reg[i], __ldg(p.pre_scale + ci + i), __ldg(p.pre_shift + ci + i)));
         }
       } else {
 #pragma unroll
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(256) conv_ffma_kernel(ConvP p) {
           int hi = hi0 + r, wi = wi0 + s;
           if (hi >= 0 && hi < p.H && wi >= 0 && wi < p.W) {
             v = __ldg(p.x + (((size_t)an * p.H + hi) * p.W + wi) * p.Cin + ci);
-            if (p.pre_scale) v = fmaxf(fmaf(v, __ldg(p.pre_scale + ci), __ldg(p.pre_shift + ci)), 0.f);
+            if (p.pre_scale) v = relu_nan(fmaf(v, __ldg(p.pre_scale + ci), __ldg(p.pre_shift + ci)));
           }
         }
         a_reg[i] = v;
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(256) conv_ffma_kernel(ConvP p) {
       if (p.bias) v += __ldg(p.bias + n);
       if (p.residual) v += __ldg(p.residual + (size_t)m * p.Cout + n);
       if (p.post_scale) v = fmaf(v, __ldg(p.post_scale + n), __ldg(p.post_shift + n));
-      if (p.act == SAR_ACT_RELU) v = fmaxf(v, 0.f);
+      if (p.act == SAR_ACT_RELU) v = relu_nan(v);
       else if (p.act == SAR_ACT_TANH) v = tanhf(v);
       acc[i][j] = v;
     }

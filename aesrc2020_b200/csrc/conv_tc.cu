@@ -35,6 +35,14 @@ namespace sar {
 
 constexpr int TC_BM = 128;            // output rows per tile (TMEM lanes)
 constexpr int TC_STAGES = 8;          // generic kernel: most ring stages (barrier slots); the launch picks p.stages <= this
+// -DSAR_BIASFOLD: the MODE 0 epilogue (conv1 of a block: only relu(bn(.)) leaves the item) finds the conv bias folded into
+// the BN shift, relu(s acc + (s b + t)), and skips the bias add + its two shared-memory loads per 8 columns.  Same-box A/B
+// (scripts/ab_so.sh, 3 runs each): conv segment 0.4865 vs 0.4878 ms at B=64, 2.75 vs 2.73 ms at B=512 -- neutral, so off.
+#ifdef SAR_BIASFOLD
+constexpr bool TC_BIASFOLD = true;
+#else
+constexpr bool TC_BIASFOLD = false;
+#endif
 constexpr int TC_THREADS = 320;            // 8 epilogue warps + TMA producer + MMA issuer
 constexpr int TC_THREADS_MAX = 576;        // 16 epilogue warps: one warp per (quadrant, 32-column chunk) of a single 128-wide tile
 // Warp roles.  The SM's schedulers favour the HIGHEST warp id of a sub-partition (wid % 4), so the two
@@ -198,7 +206,8 @@ __device__ __forceinline__ void epilogue_item(const TcParams& p, const OutMaps& 
     const int col = n0 + c0 + lane;
     const float bv = p.bias ? __ldg(p.bias + col) : 0.f;
     const float sv = p.act_scale ? __ldg(p.act_scale + col) : 1.f;
-    const float tv = p.act_shift ? __ldg(p.act_shift + col) : 0.f;
+    float tv = p.act_shift ? __ldg(p.act_shift + col) : 0.f;
+    if (MODE == 0 && TC_BIASFOLD) tv = fmaf(bv, sv, tv);            // MODE 0: only relu(bn(.)) leaves the item -- the bias rides in the shift
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_bias_u + (uint32_t)lane * 4u), "f"(bv) : "memory");
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_bias_u + 128u + (uint32_t)lane * 4u), "f"(sv) : "memory");
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_bias_u + 256u + (uint32_t)lane * 4u), "f"(tv) : "memory");
@@ -295,7 +304,10 @@ __device__ __forceinline__ void epilogue_item(const TcParams& p, const OutMaps& 
     }
     const uint32_t vec = s_bias_u + (uint32_t)((CHAIN ? 0 : n0 + c0) + 8 * g) * 4u;   // bias | scale | shift, vstride bytes apart
     float v[8];
-    {
+    if (MODE == 0 && TC_BIASFOLD) {                  // relu(s (acc + b) + t) = relu(s acc + (s b + t)): the staging code folded b
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = fmaf(__uint_as_float(r1[e]), TC_LO_INV, __uint_as_float(r0[e]));
+    } else {
       const uint4 b0 = lds128(vec), b1 = lds128(vec + 16);
       const float bb[8] = {__uint_as_float(b0.x), __uint_as_float(b0.y), __uint_as_float(b0.z), __uint_as_float(b0.w),
                            __uint_as_float(b1.x), __uint_as_float(b1.y), __uint_as_float(b1.z), __uint_as_float(b1.w)};
@@ -350,7 +362,7 @@ __device__ __forceinline__ void epilogue_item(const TcParams& p, const OutMaps& 
         const float tt[8] = {__uint_as_float(t0.x), __uint_as_float(t0.y), __uint_as_float(t0.z), __uint_as_float(t0.w),
                              __uint_as_float(t1.x), __uint_as_float(t1.y), __uint_as_float(t1.z), __uint_as_float(t1.w)};
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = fmaxf(fmaf(v[e], ss[e], tt[e]), 0.f);
+        for (int e = 0; e < 8; ++e) v[e] = relu_nan(fmaf(v[e], ss[e], tt[e]));
       } else if (act_kind == 2) {                  // Dense(..., activation='tanh'), model.py:35-42
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] = tanh_precise(v[e]);
@@ -712,6 +724,7 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       s_bias[i] = p.bias ? p.bias[i] : 0.f;
       s_scale[i] = p.act_scale ? p.act_scale[i] : 1.f;
       s_shift[i] = p.act_shift ? p.act_shift[i] : 0.f;
+      if (EPI_MODE == 0 && TC_BIASFOLD) s_shift[i] = fmaf(s_bias[i], s_scale[i], s_shift[i]);      // MODE 0 epilogue: bias folded into the BN shift
     }
     named_bar_sync(1, nepi * 32);
   }
@@ -998,6 +1011,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       s_bias[i] = p.bias ? p.bias[i] : 0.f;
       s_scale[i] = p.act_scale ? p.act_scale[i] : 1.f;
       s_shift[i] = p.act_shift ? p.act_shift[i] : 0.f;
+      if (EPI_MODE == 0 && TC_BIASFOLD) s_shift[i] = fmaf(s_bias[i], s_scale[i], s_shift[i]);      // MODE 0 epilogue: bias folded into the BN shift
     }
     named_bar_sync(1, nepi * 32);
   }

@@ -27,7 +27,7 @@ __global__ void maxpool_kernel(const float* __restrict__ x, float* __restrict__ 
         int wi = wo * stride - pad_l + dw;
         if (wi < 0 || wi >= W) continue;
         float4 v = __ldg(reinterpret_cast<const float4*>(x + (((size_t)n * H + hi) * W + wi) * C) + c4);
-        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+        m.x = fmax_nan(m.x, v.x); m.y = fmax_nan(m.y, v.y); m.z = fmax_nan(m.z, v.z); m.w = fmax_nan(m.w, v.w);
       }
     }
     reinterpret_cast<float4*>(out + (size_t)pix * C)[c4] = m;
@@ -48,7 +48,7 @@ __global__ void affine_relu_kernel(const float* __restrict__ x, const float* __r
     float4 s = __ldg(reinterpret_cast<const float4*>(scale) + c4);
     float4 b = __ldg(reinterpret_cast<const float4*>(shift) + c4);
     v.x = fmaf(v.x, s.x, b.x); v.y = fmaf(v.y, s.y, b.y); v.z = fmaf(v.z, s.z, b.z); v.w = fmaf(v.w, s.w, b.w);
-    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    if (relu) { v.x = relu_nan(v.x); v.y = relu_nan(v.y); v.z = relu_nan(v.z); v.w = relu_nan(v.w); }
     reinterpret_cast<float4*>(out)[i] = v;
   }
 }

@@ -124,10 +124,10 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(HeadP p) {
     for (int d = t; d < p.D; d += HEAD_THREADS) x[d] = __ldg(p.emb + (size_t)b * p.D + d);
     __syncthreads();
     matvec_parts<false>(x, p.D, p.w1, p.H1, 1.f, pacc, psq, h1, nullptr, t);
-    for (int j = t; j < p.H1; j += HEAD_THREADS) h1[j] = fmaxf(h1[j] + __ldg(p.b1 + j), 0.f);
+    for (int j = t; j < p.H1; j += HEAD_THREADS) h1[j] = relu_nan(h1[j] + __ldg(p.b1 + j));
     __syncthreads();
     matvec_parts<false>(h1, p.H1, p.w2, p.H2, 1.f, pacc, psq, h2, nullptr, t);
-    for (int j = t; j < p.H2; j += HEAD_THREADS) h2[j] = fmaxf(h2[j] + __ldg(p.b2 + j), 0.f);
+    for (int j = t; j < p.H2; j += HEAD_THREADS) h2[j] = relu_nan(h2[j] + __ldg(p.b2 + j));
     __syncthreads();
     matvec_parts<false>(h2, p.H2, p.w3, n, 1.f, pacc, psq, h1, nullptr, t);      // h1[0..n) = logits - bias
     if (t < 32) {

@@ -65,7 +65,7 @@ __global__ void planes_pack_kernel(const float* __restrict__ x, const float* __r
     }
     if (relu) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+      for (int j = 0; j < 8; ++j) v[j] = relu_nan(v[j]);
     }
     long long row, R; int plane0;
     plane_addr(g, n, h, w, row, R, plane0);
@@ -117,8 +117,8 @@ __global__ void maxpool_planes_kernel(const float* __restrict__ x, __half* __res
         if (wi < 0 || wi >= Win) continue;
         const float4* src = reinterpret_cast<const float4*>(x + (((size_t)n * Hin + hi) * Win + wi) * g.C + c);
         float4 a = __ldg(src), b = __ldg(src + 1);
-        v[0] = fmaxf(v[0], a.x); v[1] = fmaxf(v[1], a.y); v[2] = fmaxf(v[2], a.z); v[3] = fmaxf(v[3], a.w);
-        v[4] = fmaxf(v[4], b.x); v[5] = fmaxf(v[5], b.y); v[6] = fmaxf(v[6], b.z); v[7] = fmaxf(v[7], b.w);
+        v[0] = fmax_nan(v[0], a.x); v[1] = fmax_nan(v[1], a.y); v[2] = fmax_nan(v[2], a.z); v[3] = fmax_nan(v[3], a.w);
+        v[4] = fmax_nan(v[4], b.x); v[5] = fmax_nan(v[5], b.y); v[6] = fmax_nan(v[6], b.z); v[7] = fmax_nan(v[7], b.w);
       }
     }
     long long row, R; int plane0;

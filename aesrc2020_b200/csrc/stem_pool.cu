@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(SP_THREADS, 2) stem_pool_kernel(StemP p) {
       const int ch = 16 * cg + c;
       const float b = __ldg(p.bias + ch), s = __ldg(p.scale + ch), sh = __ldg(p.shift + ch);
 #pragma unroll
-      for (int px = 0; px < 4; ++px) acc[px][c] = fmaxf(fmaf(acc[px][c] + b, s, sh), 0.f);
+      for (int px = 0; px < 4; ++px) acc[px][c] = relu_nan(fmaf(acc[px][c] + b, s, sh));
     }
 #pragma unroll
     for (int px = 0; px < 4; ++px)
@@ -132,8 +132,8 @@ __global__ void __launch_bounds__(SP_THREADS, 2) stem_pool_kernel(StemP p) {
         if (wc < 0 || wc >= p.Wc) continue;
         const float4* src = reinterpret_cast<const float4*>(c_s + ((size_t)r * p.Wc + wc) * F0 + 8 * c8);
         const float4 v0 = src[0], v1 = src[1];
-        m[0] = fmaxf(m[0], v0.x); m[1] = fmaxf(m[1], v0.y); m[2] = fmaxf(m[2], v0.z); m[3] = fmaxf(m[3], v0.w);
-        m[4] = fmaxf(m[4], v1.x); m[5] = fmaxf(m[5], v1.y); m[6] = fmaxf(m[6], v1.z); m[7] = fmaxf(m[7], v1.w);
+        m[0] = fmax_nan(m[0], v0.x); m[1] = fmax_nan(m[1], v0.y); m[2] = fmax_nan(m[2], v0.z); m[3] = fmax_nan(m[3], v0.w);
+        m[4] = fmax_nan(m[4], v1.x); m[5] = fmax_nan(m[5], v1.y); m[6] = fmax_nan(m[6], v1.z); m[7] = fmax_nan(m[7], v1.w);
       }
     }
     uint32_t hh[4], ll[4];

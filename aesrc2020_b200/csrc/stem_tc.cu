@@ -288,10 +288,10 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const StemTcP p)
         float4 mx = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int k = 0; k < 9; ++k) {
-          mx.x = fmaxf(mx.x, fmaf(v[k].x, sc4.x, sh4.x));
-          mx.y = fmaxf(mx.y, fmaf(v[k].y, sc4.y, sh4.y));
-          mx.z = fmaxf(mx.z, fmaf(v[k].z, sc4.z, sh4.z));
-          mx.w = fmaxf(mx.w, fmaf(v[k].w, sc4.w, sh4.w));
+          mx.x = fmax_nan(mx.x, fmaf(v[k].x, sc4.x, sh4.x));
+          mx.y = fmax_nan(mx.y, fmaf(v[k].y, sc4.y, sh4.y));
+          mx.z = fmax_nan(mx.z, fmaf(v[k].z, sc4.z, sh4.z));
+          mx.w = fmax_nan(mx.w, fmaf(v[k].w, sc4.w, sh4.w));
         }
         const __half2 h01 = __floats2half2_rn(mx.x, mx.y), h23 = __floats2half2_rn(mx.z, mx.w);
         const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);

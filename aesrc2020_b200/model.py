@@ -451,7 +451,7 @@ class SARModel:
             torch.cuda.current_stream().synchronize()
             off = 0
             for i, o in enumerate(outs):
-                chunks[i].append(self._pinned_out[off:off + o.numel()].view(o.shape).numpy().copy())
+                chunks[i].append(self._finite(self._pinned_out[off:off + o.numel()].view(o.shape).numpy().copy()))
                 off += o.numel()
         cat = (lambda c: torch.cat(c, 0)) if on_device else (lambda c: np.concatenate(c, 0))
         res = [cat(c) for c in chunks]
@@ -558,7 +558,17 @@ class SARModel:
         if self.config.ctc_enable and bool((views[-1] != 0).any()):
             raise SarnetError("CTC: infeasible or out-of-range label sequence in batch "
                               "(Not enough time for target transition sequence)")
-        return [v.numpy().copy() for v in views[:len(self._outputs)]]
+        return [self._finite(v.numpy().copy()) for v in views[:len(self._outputs)]]
+
+    @staticmethod
+    def _finite(a: np.ndarray) -> np.ndarray:
+        """The tensor-core operand planes are fp16 hi/lo pairs: an activation with |x| >= 65504 becomes inf in the hi plane
+        and NaN one layer later, and reaches the outputs as NaN.  The hot kernels carry no range check; the (tiny) host
+        copy of the outputs does, so a saturated batch fails loudly instead of returning garbage."""
+        if a.size <= (1 << 20) and a.dtype.kind == "f" and not np.isfinite(a).all():
+            raise SarnetError("non-finite model output: the inputs are non-finite, or an activation left the fp16 range of the "
+                              "tensor-core operand planes (|x| >= 65504); rescale the features (utils.feat_norm yields [0, 1])")
+        return a
 
     def predict_generator(self, generator, steps=None, max_queue_size=10, workers=1, use_multiprocessing=False, verbose=0,
                           prefetch: bool = False):

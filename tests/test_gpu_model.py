@@ -465,3 +465,20 @@ def test_predict_generator_prefetch_ring_matches_predict(cuda_device):
     got = model.predict_generator(us.data_generator(lst, seed=9, **kw), steps=6, prefetch=True, max_queue_size=2)
     for i in range(len(got)):
         assert np.allclose(got[i], np.concatenate([r[i] for r in ref_batches], 0), rtol=2e-4, atol=1e-6), i
+
+
+def test_activation_overflow_fails_loudly(cuda_device):
+    """The tensor-core operand planes are fp16 hi/lo pairs (|x| < 65504).  Features far outside the [0, 1] range
+    utils.feat_norm produces saturate them; the outputs turn NaN and predict / predict_generator raise instead of
+    returning them (the in-range batch before and after is unaffected)."""
+    from aesrc2020_b200 import _shim
+    model, x, _ = build("cfg2_gvlad_arcface")
+    good = model.predict(x, batch_size=len(x["x_data"]))
+    bad = dict(x, x_data=x["x_data"] * np.float32(3e6))
+    with pytest.raises(_shim.SarnetError, match="non-finite"):
+        model.predict(bad, batch_size=len(x["x_data"]))
+    with pytest.raises(_shim.SarnetError, match="non-finite"):
+        model.predict_generator(iter([x, bad, x]))
+    again = model.predict(x, batch_size=len(x["x_data"]))
+    for a, b in zip(good, again):
+        assert np.array_equal(a, b)
