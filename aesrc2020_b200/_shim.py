@@ -68,6 +68,8 @@ SIGNATURES = {
     "sar_bn_train_bwd": (c_int, [c_fp] * 8 + [c_int, c_int, C.c_void_p]),
     "sar_bias_act_fwd": (c_int, [c_fp, c_fp, c_fp, c_ll, c_int, c_int, C.c_void_p]),
     "sar_relu_bwd": (c_int, [c_fp, c_fp, c_fp, c_ll, C.c_void_p]),
+    "sar_gru_gate_fwd": (c_int, [c_fp] * 10 + [c_int] * 6 + [C.c_void_p]),
+    "sar_gru_gate_bwd": (c_int, [c_fp] * 10 + [c_int] * 6 + [C.c_void_p]),
     "sar_colsum_fwd": (c_int, [c_fp, c_fp, c_int, c_int, C.c_void_p]),
     "sar_l2norm_fwd": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_int, C.c_void_p]),
     "sar_l2norm_bwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_f, C.c_void_p]),

@@ -10,6 +10,7 @@
 //   sar_head_grad_fwd     softmax + categorical cross-entropy of y_accent and the margin head (SphereFace / CosFace /
 //                         ArcFace / Dense softmax / Circle-Loss): per-sample losses and d loss / d logits, d loss / d cos
 //   sar_adam_fwd          Keras Adam update (+ l2 regulariser gradient, + unit_norm constraint helper)
+//   sar_gru_gate_fwd/bwd  one time step of CuDNNGRU in training mode (gates kept) and its backward (fourth slice: CNN_LIN, CRNN)
 //   sar_vlad_train_fwd/bwd  NetVLAD / GhostVLAD pooling in training mode: soft assignments kept, gradients of the centers and of
 //                         the assignment scores (second slice: the pooling layer is trained together with the head)
 //
@@ -410,6 +411,57 @@ __global__ void __launch_bounds__(256) ln_train_bwd_kernel(const float* __restri
   }
 }
 
+// ------------------------------------------------------------------ CuDNNGRU in training mode (fourth slice): one time step
+// Gate arithmetic of one step of one direction (model.py:44-50; reset_after form, gate order z|r|h):
+//   a = xp[b, t, :] (= x W + b_i) and hu = h_prev U (+ b_r added here);  z = s(a_z + hu_z), r = s(a_r + hu_r),
+//   hh = tanh(a_h + r * hu_h),  h' = z h_prev + (1 - z) hh.  The step's z, r, hh and hu_h (+ bias) are kept for the backward.
+__global__ void gru_gate_fwd_kernel(const float* __restrict__ xp, const float* __restrict__ hu, const float* __restrict__ b_r,
+                                    const float* __restrict__ h_prev, float* __restrict__ z_s, float* __restrict__ r_s,
+                                    float* __restrict__ hh_s, float* __restrict__ hph_s, float* __restrict__ h_new,
+                                    float* __restrict__ out, int B, int S, int u, int t, int out_stride, int out_off) {
+  pdl_wait();
+  pdl_trigger();
+  const long long n = (long long)B * u;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / u), j = (int)(i - (long long)b * u);
+    const float* a = xp + ((size_t)b * S + t) * 3 * u;
+    const float* hb = hu + (size_t)b * 3 * u;
+    const float z = sigmoidf_(a[j] + hb[j] + b_r[j]);
+    const float r = sigmoidf_(a[u + j] + hb[u + j] + b_r[u + j]);
+    const float hph = hb[2 * u + j] + b_r[2 * u + j];
+    const float hh = tanhf(a[2 * u + j] + r * hph);
+    const float hp = h_prev[i];
+    const float hn = z * hp + (1.f - z) * hh;
+    z_s[i] = z; r_s[i] = r; hh_s[i] = hh; hph_s[i] = hph; h_new[i] = hn;
+    if (out) out[((size_t)b * S + t) * out_stride + out_off + j] = hn;
+  }
+}
+// ... and its backward: dh = g_out[b, t, off + j] + dh_rec[b, j] is d loss / d h'.  Writes d loss / d a into d_xp[b, t, :]
+// (the input-projection pre-activations), d loss / d hu into d_hu (B, 3u), and dh * z into dh_prev (the caller adds
+// d_hu U^T with one GEMM).
+__global__ void gru_gate_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__ dh_rec, const float* __restrict__ z_s,
+                                    const float* __restrict__ r_s, const float* __restrict__ hh_s, const float* __restrict__ hph_s,
+                                    const float* __restrict__ h_prev, float* __restrict__ d_xp, float* __restrict__ d_hu,
+                                    float* __restrict__ dh_prev, int B, int S, int u, int t, int out_stride, int out_off) {
+  pdl_wait();
+  pdl_trigger();
+  const long long n = (long long)B * u;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / u), j = (int)(i - (long long)b * u);
+    float dh = dh_rec ? dh_rec[i] : 0.f;
+    if (g_out) dh += g_out[((size_t)b * S + t) * out_stride + out_off + j];
+    const float z = z_s[i], r = r_s[i], hh = hh_s[i], hph = hph_s[i], hp = h_prev[i];
+    const float d_ah = dh * (1.f - z) * (1.f - hh * hh);          // through tanh
+    const float d_az = dh * (hp - hh) * z * (1.f - z);            // through the update gate
+    const float d_ar = d_ah * hph * r * (1.f - r);                // through the reset gate
+    float* da = d_xp + ((size_t)b * S + t) * 3 * u;
+    float* dhu = d_hu + (size_t)b * 3 * u;
+    da[j] = d_az; da[u + j] = d_ar; da[2 * u + j] = d_ah;
+    dhu[j] = d_az; dhu[u + j] = d_ar; dhu[2 * u + j] = d_ah * r;
+    dh_prev[i] = dh * z;
+  }
+}
+
 }  // namespace sar
 
 extern "C" {
@@ -458,6 +510,29 @@ int sar_relu_bwd(const float* g, const float* h, float* out, long long n, void* 
   SAR_REQUIRE(g && h && out && n > 0, SAR_ERR_BAD_ARG, "sar_relu_bwd: bad argument");
   launch_k(relu_bwd_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, (cudaStream_t)stream, g, h, out, n);
   return check_launch("sar_relu_bwd");
+}
+
+int sar_gru_gate_fwd(const float* xp, const float* hu, const float* b_r, const float* h_prev, float* z, float* r, float* hh,
+                     float* hph, float* h_new, float* out, int B, int S, int u, int t, int out_stride, int out_off, void* stream) {
+  using namespace sar;
+  SAR_REQUIRE(xp && hu && b_r && h_prev && z && r && hh && hph && h_new, SAR_ERR_BAD_ARG, "sar_gru_gate_fwd: null pointer");
+  SAR_REQUIRE(B > 0 && S > 0 && u > 0 && t >= 0 && t < S && (!out || (out_off >= 0 && out_off + u <= out_stride)), SAR_ERR_BAD_ARG,
+              "sar_gru_gate_fwd: bad argument");
+  launch_k(gru_gate_fwd_kernel, dim3(blocks_for((long long)B * u, 256)), dim3(256), 0, (cudaStream_t)stream, xp, hu, b_r, h_prev, z, r,
+           hh, hph, h_new, out, B, S, u, t, out_stride, out_off);
+  return check_launch("sar_gru_gate_fwd");
+}
+
+int sar_gru_gate_bwd(const float* g_out, const float* dh_rec, const float* z, const float* r, const float* hh, const float* hph,
+                     const float* h_prev, float* d_xp, float* d_hu, float* dh_prev, int B, int S, int u, int t, int out_stride,
+                     int out_off, void* stream) {
+  using namespace sar;
+  SAR_REQUIRE(z && r && hh && hph && h_prev && d_xp && d_hu && dh_prev && (g_out || dh_rec), SAR_ERR_BAD_ARG, "sar_gru_gate_bwd: null pointer");
+  SAR_REQUIRE(B > 0 && S > 0 && u > 0 && t >= 0 && t < S && (!g_out || (out_off >= 0 && out_off + u <= out_stride)), SAR_ERR_BAD_ARG,
+              "sar_gru_gate_bwd: bad argument");
+  launch_k(gru_gate_bwd_kernel, dim3(blocks_for((long long)B * u, 256)), dim3(256), 0, (cudaStream_t)stream, g_out, dh_rec, z, r, hh, hph,
+           h_prev, d_xp, d_hu, dh_prev, B, S, u, t, out_stride, out_off);
+  return check_launch("sar_gru_gate_bwd");
 }
 
 int sar_colsum_fwd(const float* g, float* out, int rows, int C, void* stream) {

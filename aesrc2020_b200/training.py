@@ -20,7 +20,11 @@ assignment Conv2D (kernel, bias; l2(1e-4) regularisers).
 Third slice, `HeadTrainer(model, train_ds=True)`: AR_DS (Dense + tanh) and AR_DS_LN are trained as well -- the whole accent
 branch above the shared CRNN encoder (model.py:275-296).  The frozen encoder ends at CRNN_LN; `sar_vlad_train_bwd` also returns
 d loss / d descriptors, `sar_ln_train_bwd` differentiates LayerNormalization together with the tanh in front of it.
-Not built yet: gradients of the shared encoder (convolutions, Bi-GRU, CTC branch), i.e. end-to-end training.
+Fourth slice, `HeadTrainer(model, train_crnn=True)`: CNN_LIN (Dense + tanh) -> CNN_LIN_LN -> CRNN (Bidirectional CuDNNGRU) ->
+CRNN_LN are trained too (model.py:252-256) -- everything above the ResNet on the accent path.  The Bi-GRU runs in training
+mode as one GEMM + `sar_gru_gate_fwd` per time step (gates kept) and is differentiated by back-propagation through time
+(`sar_gru_gate_bwd` + one GEMM per step, the weight gradients as three GEMMs over all steps).
+Not built yet: gradients of the ResNet convolutions and of the CTC branch, i.e. end-to-end multi-task training.
 """
 from __future__ import annotations
 
@@ -167,6 +171,56 @@ def ln_train_bwd(y, gamma, g_z, tanh_in: bool):
     return g_pre, gzx
 
 
+def gru_dir_fwd(x_rows, B: int, S: int, W, U, bias, reverse: bool, out, off: int):
+    """One direction of CuDNNGRU in training mode (model.py:44-50): the input projection is one GEMM, every time step one
+    GEMM (h_prev U) + `sar_gru_gate_fwd`.  Writes h_t into out[:, t, off:off+u]; returns what the backward needs."""
+    u = U.shape[0]
+    dev = x_rows.device
+    xp = bias_act(gemm(x_rows, W), bias[:3 * u])                              # (B*S, 3u) = x W + b_i
+    hseq = torch.zeros((S + 1, B, u), device=dev, dtype=torch.float32)        # hseq[k]: state before processing step k
+    z, r, hh, hph = (torch.empty((S, B, u), device=dev, dtype=torch.float32) for _ in range(4))
+    b_r = bias[3 * u:]
+    lib = _shim.lib()
+    for k in range(S):
+        t = S - 1 - k if reverse else k
+        hu = gemm(hseq[k], U)
+        check(lib.sar_gru_gate_fwd(ptr(xp), ptr(hu), ptr(b_r), ptr(hseq[k]), ptr(z[k]), ptr(r[k]), ptr(hh[k]), ptr(hph[k]),
+                                   ptr(hseq[k + 1]), ptr(out), B, S, u, t, out.shape[-1], off, stream_ptr()), "sar_gru_gate_fwd")
+    ops._count(S)
+    return dict(hseq=hseq, z=z, r=r, hh=hh, hph=hph, x_rows=x_rows, reverse=reverse, off=off)
+
+
+def gru_dir_bwd(g_out, saved, B: int, S: int, W, U, g_x=None):
+    """Back-propagation through time of gru_dir_fwd: g_out (B,S,2u) = d loss / d layer output.  Returns the gradients of
+    (kernel, recurrent_kernel, bias (6u)) and accumulates d loss / d x into g_x (B*S, Din)."""
+    u = U.shape[0]
+    dev = g_out.device
+    hseq, reverse, off = saved["hseq"], saved["reverse"], saved["off"]
+    d_xp = torch.empty((B * S, 3 * u), device=dev, dtype=torch.float32)
+    d_hu = torch.empty((S, B, 3 * u), device=dev, dtype=torch.float32)
+    lib = _shim.lib()
+    dh = None
+    for k in range(S - 1, -1, -1):
+        t = S - 1 - k if reverse else k
+        dh_prev = torch.empty((B, u), device=dev, dtype=torch.float32)
+        check(lib.sar_gru_gate_bwd(ptr(g_out), ptr(dh) if dh is not None else None, ptr(saved["z"][k]), ptr(saved["r"][k]),
+                                   ptr(saved["hh"][k]), ptr(saved["hph"][k]), ptr(hseq[k]), ptr(d_xp), ptr(d_hu[k]), ptr(dh_prev),
+                                   B, S, u, t, g_out.shape[-1], off, stream_ptr()), "sar_gru_gate_bwd")
+        if k > 0:
+            gemm(d_hu[k], U, tb=True, out=dh_prev, beta=1.0)                    # + d_hu U^T
+        dh = dh_prev
+    ops._count(S)
+    x_rows = saved["x_rows"]
+    gW = gemm(x_rows, d_xp, ta=True)
+    gU = gemm(hseq[:S].view(S * B, u), d_hu.view(S * B, 3 * u), ta=True)
+    gb = torch.cat([colsum(d_xp), colsum(d_hu.view(S * B, 3 * u))])
+    if g_x is None:
+        g_x = gemm(d_xp, W, tb=True)
+    else:
+        gemm(d_xp, W, tb=True, out=g_x, beta=1.0)
+    return gW, gU, gb, g_x
+
+
 def adam_step(p, g, m, v, lr_t, l2=0.0):
     check(_shim.lib().sar_adam_fwd(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), float(lr_t), ADAM_B1, ADAM_B2, ADAM_EPS, float(l2),
                                    stream_ptr()), "sar_adam_fwd")
@@ -188,20 +242,26 @@ def adam_lr_t(lr: float, iterations: int) -> float:
 class HeadTrainer:
     """Fine-tunes the accent head of a SARModel on the device (module docstring)."""
 
-    def __init__(self, model, lr: float = 0.01, group=None, train_pool: bool = False, train_ds: bool = False):
+    def __init__(self, model, lr: float = 0.01, group=None, train_pool: bool = False, train_ds: bool = False,
+                 train_crnn: bool = False):
         """train_pool: also train the NetVLAD / GhostVLAD pooling layer (assignment Conv2D + centers, model.py:82-109):
         the frozen encoder then ends at AR_DS_LN and the step differentiates vlad() as well (second slice).
         train_ds (implies train_pool): also train AR_DS (Dense + tanh, l2 regularisers) and AR_DS_LN (model.py:275-276):
-        the whole accent branch above the shared CRNN encoder; the frozen encoder ends at CRNN_LN (third slice)."""
+        the whole accent branch above the shared CRNN encoder; the frozen encoder ends at CRNN_LN (third slice).
+        train_crnn (implies train_ds): also train CNN_LIN (Dense + tanh) -> CNN_LIN_LN -> CRNN (Bidirectional CuDNNGRU, back-
+        propagation through time) -> CRNN_LN (model.py:252-256): everything above the ResNet on the accent path; the
+        frozen encoder is the ResNet alone (fourth slice)."""
         cfg = model.config
         if not cfg.ar_enable:
             raise ValueError("HeadTrainer needs ar_enable=True")
+        train_ds = bool(train_ds or train_crnn)
         train_pool = bool(train_pool or train_ds)
         if train_pool and cfg.mto not in ("vlad", "gvlad"):
             raise ValueError("train_pool needs mto='vlad' or 'gvlad' (got %r)" % cfg.mto)
         self.model, self.cfg, self.lr, self.group = model, cfg, float(lr), group
         self.train_pool = bool(train_pool)
         self.train_ds = bool(train_ds)
+        self.train_crnn = bool(train_crnn)
         self.iterations = 0
         self.head_kind = cfg.metric_loss if cfg.disc_enable else None
         self.disc_key = None
@@ -220,6 +280,13 @@ class HeadTrainer:
             self.ds_keys = ["AR_DS/kernel", "AR_DS/bias", "AR_DS_LN/gamma", "AR_DS_LN/beta"]
             self.keys += self.ds_keys
             self.l2 |= set(self.ds_keys[:2])             # DS(hidden_dim, 'tanh'): l2(1e-4) on kernel and bias (model.py:35-42)
+        self.crnn_keys: List[str] = []
+        if self.train_crnn:
+            gk = ["CRNN/%s/%s" % (d, w) for d in ("forward", "backward") for w in ("kernel", "recurrent_kernel", "bias")]
+            self.crnn_keys = ["CNN_LIN/kernel", "CNN_LIN/bias", "CNN_LIN_LN/gamma", "CNN_LIN_LN/beta"] + gk + ["CRNN_LN/gamma", "CRNN_LN/beta"]
+            self.keys += self.crnn_keys
+            # DS: l2(1e-4) on kernel and bias; BIGRU: kernel_regularizer + bias_regularizer, none on the recurrent kernel (model.py:35-50)
+            self.l2 |= {"CNN_LIN/kernel", "CNN_LIN/bias"} | {k for k in gk if not k.endswith("recurrent_kernel")}
         lw = cfg.loss_weights()
         self.w_acc, self.w_disc = float(lw.get("y_accent", 0.0)), float(lw.get("y_disc", 0.0))
         dev = torch.device(model.device)
@@ -233,13 +300,29 @@ class HeadTrainer:
     # ---- frozen encoder: x_data -> integ (B, K*D | D | 2u), or (train_pool) the descriptors (B,S,D) in front of vlad()
     def encode(self, x) -> torch.Tensor:
         out = self.model.forward_device(x, want_intermediates=True, graph=False)
+        if self.train_crnn:                       # CNN2SEQ (model.py:252): the ResNet's (B,H,W,C) map as (B, S, Cc) rows
+            plan = self.cfg.plan()
+            raw = out["resnet_raw"]
+            return raw.reshape(raw.shape[0], plan.seq_len, plan.cout).contiguous()
         return out["crnn" if self.train_ds else ("ar_ds" if self.train_pool else "integration")].contiguous()
 
     # ---- one step on (integ | descriptors, onehot) device tensors
     def step_on_features(self, integ: torch.Tensor, onehot: torch.Tensor) -> Dict[str, float]:
         p, cfg = self.p, self.cfg
         B = integ.shape[0]
-        pool = ds = None
+        pool = ds = rn = None
+        if self.train_crnn:                      # CNN_LIN -> CNN_LIN_LN -> CRNN -> CRNN_LN on the frozen ResNet's sequence (B,S,Cc)
+            _, Sr, Cr = integ.shape
+            x0 = integ.view(B * Sr, Cr)
+            y_lin = bias_act(gemm(x0, p["CNN_LIN/kernel"]), p["CNN_LIN/bias"], tanh=True)
+            z_lin = ops.layernorm(y_lin, p["CNN_LIN_LN/gamma"], p["CNN_LIN_LN/beta"])
+            u = p["CRNN/forward/recurrent_kernel"].shape[0]
+            gru_out = torch.empty((B, Sr, 2 * u), device=integ.device, dtype=torch.float32)
+            sv = [gru_dir_fwd(z_lin, B, Sr, p["CRNN/%s/kernel" % d], p["CRNN/%s/recurrent_kernel" % d], p["CRNN/%s/bias" % d],
+                              d == "backward", gru_out, i * u) for i, d in enumerate(("forward", "backward"))]
+            crnn_rows = ops.layernorm(gru_out.view(B * Sr, 2 * u), p["CRNN_LN/gamma"], p["CRNN_LN/beta"])
+            rn = (x0, y_lin, z_lin, gru_out, sv, Sr)
+            integ = crnn_rows.view(B, Sr, 2 * u)
         if self.train_ds:                        # AR_DS -> AR_DS_LN on the frozen encoder's CRNN_LN output (B,S,2u)
             crnn = integ
             _, S0, C0 = crnn.shape
@@ -307,6 +390,20 @@ class HeadTrainer:
                 g_pre, gzx = ln_train_bwd(yds, p["AR_DS_LN/gamma"], g_feat.view(B * S, D), tanh_in=True)
                 g["AR_DS_LN/gamma"], g["AR_DS_LN/beta"] = colsum(gzx), colsum(g_feat.view(B * S, D))
                 g["AR_DS/kernel"], g["AR_DS/bias"] = gemm(x_ds, g_pre, ta=True), colsum(g_pre)
+                if rn is not None:               # ... and on through CRNN_LN, the Bi-GRU (BPTT), CNN_LIN_LN and CNN_LIN
+                    x0, y_lin, z_lin, gru_out, sv, Sr = rn
+                    u2 = gru_out.shape[-1]
+                    g_crnn = gemm(g_pre, p["AR_DS/kernel"], tb=True)                    # (B*S, 2u) = d loss / d CRNN_LN output
+                    g_gru, gzx2 = ln_train_bwd(gru_out.view(B * Sr, u2), p["CRNN_LN/gamma"], g_crnn, tanh_in=False)
+                    g["CRNN_LN/gamma"], g["CRNN_LN/beta"] = colsum(gzx2), colsum(g_crnn)
+                    g_zlin = None
+                    for d, s_ in zip(("forward", "backward"), sv):
+                        gW, gU, gb, g_zlin = gru_dir_bwd(g_gru.view(B, Sr, u2), s_, B, Sr, p["CRNN/%s/kernel" % d],
+                                                         p["CRNN/%s/recurrent_kernel" % d], g_x=g_zlin)
+                        g["CRNN/%s/kernel" % d], g["CRNN/%s/recurrent_kernel" % d], g["CRNN/%s/bias" % d] = gW, gU, gb
+                    g_pl, gzx1 = ln_train_bwd(y_lin, p["CNN_LIN_LN/gamma"], g_zlin, tanh_in=True)
+                    g["CNN_LIN_LN/gamma"], g["CNN_LIN_LN/beta"] = colsum(gzx1), colsum(g_zlin)
+                    g["CNN_LIN/kernel"], g["CNN_LIN/bias"] = gemm(x0, g_pl, ta=True), colsum(g_pl)
             else:
                 g_scores, gc_part = vlad_train_bwd(feat, A, p[kc_], gR, asum, K, G)
             g[kw_] = gemm(feat.view(B * S, D), g_scores.view(B * S, K + G), ta=True).view_as(p[kw_])

@@ -82,15 +82,21 @@ def load_peaks():
         return {"hbm_gbs": 6650.0, "tflops": 1400.0, "tflops_burst": 1590.0, "source": "fallback (B200_PROFILING.md)"}
 
 
-def build_id() -> str:
-    """Hash of the CUDA sources: ties committed ncu figures (profiles/*.json) to the build they were taken on."""
+def build_id(files=None) -> str:
+    """Hash of the CUDA sources (all of them, or the named ones): ties committed ncu figures (profiles/*.json) to the
+    build they were taken on."""
     h = hashlib.sha1()
     d = os.path.join(ROOT, "aesrc2020_b200", "csrc")
     for fn in sorted(os.listdir(d)):
-        if fn.endswith((".cu", ".cuh")):
+        if fn.endswith((".cu", ".cuh")) and (files is None or fn in files):
             with open(os.path.join(d, fn), "rb") as f:
                 h.update(fn.encode() + f.read())
     return h.hexdigest()[:12]
+
+
+def conv_build_id() -> str:
+    """The sources the residual-block convolution kernels are compiled from (roofline.traffic is tied to these)."""
+    return build_id(("conv_tc.cu", "tc_common.cuh", "common.cuh"))
 
 
 class ClockSampler:
@@ -769,17 +775,17 @@ def main():
     try:                                                # DRAM bytes per launch from the committed ncu pass of THIS build
         with open(os.path.join(ROOT, "profiles", "r2_conv_traffic.json")) as f:
             tj = json.load(f)
-        if tj.get("build_id") == build_id() and args.config == "cfg2" and B == tj.get("B"):
+        if tj.get("build_id") == conv_build_id() and args.config == "cfg2" and B == tj.get("B"):
             traffic, traffic_src = tj["traffic_bytes_per_launch"], tj.get("source")
     except Exception:
         pass
     roof.update({"traffic": traffic,
-                 "traffic_unit": "bytes/launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu; null unless profiles/r2_conv_traffic.json was taken on this build: %s)" % (traffic_src or build_id()),
+                 "traffic_unit": "bytes/launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu; null unless profiles/r2_conv_traffic.json was taken on this build of the conv sources: %s)" % (traffic_src or conv_build_id()),
                  "kernel": "residual-block conv (%d launches/step for thin-ResNet34)" % roof["launches_per_step"],
                  "timing": "external CUDA events (graph event-record nodes) around the block-conv launches of the single-stream "
                            "step graph, read after each of K replays run right after the value region",
                  "peak_source": peaks["source"] + ", sustained bf16 for a kernel timed inside a long step",
-                 "build_id": build_id()})
+                 "build_id": build_id(), "conv_build_id": conv_build_id()})
     launches = launches_per_step * args.steps
 
     line = {

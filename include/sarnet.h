@@ -306,6 +306,16 @@ int sar_bn_train_bwd(const float* x, const float* dy, const float* gamma, const 
 int sar_bias_act_fwd(const float* x, const float* bias, float* y, long long rows, int C, int act, void* stream);
 int sar_relu_bwd(const float* g, const float* h, float* out, long long n, void* stream);
 int sar_colsum_fwd(const float* g, float* out, int rows, int C, void* stream);
+/* One time step of one direction of CuDNNGRU in TRAINING mode (model.py:44-50; reset_after, gates z|r|h) and its backward.
+ * xp (B,S,3u) = x W + b_i (batch-major), hu (B,3u) = h_prev U, b_r (3u); z, r, hh, hph (B,u) are this step's saved gates
+ * (hph = hu_h + b_r_h), h_new (B,u), out (B,S,out_stride) receives h_new at [b, t, out_off + j] (NULL: not stored).
+ * Backward: dh = g_out[b,t,out_off+j] + dh_rec[b,j] (either may be NULL); d_xp[b,t,:] = d loss / d (x W + b_i),
+ * d_hu (B,3u) = d loss / d (h_prev U + b_r), dh_prev = dh * z (the caller adds d_hu U^T).  fp32, CUDA cores. */
+int sar_gru_gate_fwd(const float* xp, const float* hu, const float* b_r, const float* h_prev, float* z, float* r, float* hh,
+                     float* hph, float* h_new, float* out, int B, int S, int u, int t, int out_stride, int out_off, void* stream);
+int sar_gru_gate_bwd(const float* g_out, const float* dh_rec, const float* z, const float* r, const float* hh, const float* hph,
+                     const float* h_prev, float* d_xp, float* d_hu, float* dh_prev, int B, int S, int u, int t, int out_stride,
+                     int out_off, void* stream);
 /* K.l2_normalize of every row (axis 1) or column (axis 0) of v (rows, D): out = v / sqrt(max(|v|^2, 1e-12)), inv_norm per
  * vector; backward: out = beta * out + (u - vhat (vhat . u)) * inv_norm, u = d loss / d vhat.  (losses.py:30-33, model.py:162) */
 int sar_l2norm_fwd(const float* v, float* out, float* inv_norm, int rows, int D, int axis, void* stream);

@@ -94,17 +94,27 @@ def pool_l2_keys(mto: str):
 
 
 DS_KEYS = ["AR_DS/kernel", "AR_DS/bias", "AR_DS_LN/gamma", "AR_DS_LN/beta"]       # third slice (model.py:275-276)
+# fourth slice (model.py:252-256): CNN_LIN -> CNN_LIN_LN -> CRNN (Bidirectional CuDNNGRU) -> CRNN_LN
+GRU_KEYS = ["CRNN/%s/%s" % (d, w) for d in ("forward", "backward") for w in ("kernel", "recurrent_kernel", "bias")]
+CRNN_KEYS = ["CNN_LIN/kernel", "CNN_LIN/bias", "CNN_LIN_LN/gamma", "CNN_LIN_LN/beta"] + GRU_KEYS + ["CRNN_LN/gamma", "CRNN_LN/beta"]
+# DS: l2(1e-4) on kernel and bias; BIGRU: kernel_regularizer and bias_regularizer, none on the recurrent kernel (model.py:35-50)
+CRNN_L2_KEYS = ["CNN_LIN/kernel", "CNN_LIN/bias"] + [k for k in GRU_KEYS if not k.endswith("recurrent_kernel")]
 
 
 def pooled_head_loss(p: Dict[str, torch.Tensor], feat: torch.Tensor, onehot: torch.Tensor, *, mto: str, vlad_clusters: int,
-                     ghost_clusters: int, train_ds: bool = False, **kw):
+                     ghost_clusters: int, train_ds: bool = False, train_crnn: bool = False, **kw):
     """feat (B,S,D) = AR_DS_LN output (frozen encoder) -> vlad() -> the head of head_loss, with the pooling layer's
     regularisers added.  train_ds: feat is the CRNN_LN output (B,S,2u) instead and AR_DS (Dense + tanh, l2 regularisers on
     kernel and bias) -> AR_DS_LN run in front of vlad() (model.py:275-276)."""
     reg_ds = 0.0
+    if train_crnn:           # feat is the frozen ResNet's sequence (B,S,Cc): model.py:252-256 in front of the accent branch
+        feat = O.layernorm(O.dense(feat, p, "CNN_LIN", "tanh"), p, "CNN_LIN_LN")
+        feat = O.layernorm(O.bigru(feat, p, "CRNN"), p, "CRNN_LN")
+        reg_ds = reg_ds + sum(L2_REG * (p[k] ** 2).sum() for k in CRNN_L2_KEYS)
+        train_ds = True
     if train_ds:
         feat = O.layernorm(O.dense(feat, p, "AR_DS", "tanh"), p, "AR_DS_LN")
-        reg_ds = L2_REG * ((p["AR_DS/kernel"] ** 2).sum() + (p["AR_DS/bias"] ** 2).sum())
+        reg_ds = reg_ds + L2_REG * ((p["AR_DS/kernel"] ** 2).sum() + (p["AR_DS/bias"] ** 2).sum())
     integ = O.integration(feat, p, feat.shape[-1], mto, vlad_clusters, ghost_clusters)       # model.py:118-139
     total, parts = head_loss(p, integ, onehot, **kw)
     reg = sum(L2_REG * (p[k] ** 2).sum() for k in pool_l2_keys(mto)) + reg_ds
@@ -131,7 +141,8 @@ def train_step(params: Dict[str, np.ndarray], state: Dict[str, np.ndarray], inte
     vlad() and the pooling layer's weights are trained too (pooled_head_loss).
     Returns (new params incl. the BN moving statistics, new state, losses, gradients)."""
     keys = trainable_keys(disc_enable, metric_loss) + (pool_keys(pool["mto"]) if pool else []) + \
-        (DS_KEYS if (pool and pool.get("train_ds")) else [])
+        (DS_KEYS if (pool and (pool.get("train_ds") or pool.get("train_crnn"))) else []) + \
+        (CRNN_KEYS if (pool and pool.get("train_crnn")) else [])
     p = {k: torch.tensor(np.asarray(v, np.float64), requires_grad=(k in keys)) for k, v in params.items()}
     kw = dict(disc_enable=disc_enable, metric_loss=metric_loss, margin=margin, w_accent=w_accent, w_disc=w_disc)
     x_in, y_in = torch.as_tensor(np.asarray(integ, np.float64)), torch.as_tensor(np.asarray(onehot, np.float64))

@@ -25,7 +25,7 @@ SAR_CHAIN_STAGES="0" timeout 600 ncu --set full --cache-control none --clock-con
     -k regex:"conv_tc_pair_kernel" -s 24 -c 2 -f -o $OUT/${TAG}_pair_full_b512 python bench.py --eager --pipeline 1 --steps 1 --warmup 1 --no-cpu-baseline --batch 512 > $OUT/${TAG}_pair_full.out 2>&1
 echo "ncu full pair rc=$?"
 SAR_CHAIN_STAGES="0" timeout 600 ncu --set full --cache-control none --clock-control none --import-source on \
-    -k regex:"slab_kernel<32, true, 0>|slab_kernel<.int.32, .bool.1, .int.0>" -s 2 -c 1 -f -o $OUT/${TAG}_slab_s1_full_b512 python bench.py --eager --pipeline 1 --steps 1 --warmup 1 --no-cpu-baseline --batch 512 > $OUT/${TAG}_slab_s1_full.out 2>&1
+    --kernel-name-base demangled -k regex:"conv_tc_slab_kernel<32, 1, 0>|conv_tc_slab_kernel<.int.32, .bool.1, .int.0>" -c 1 -f -o $OUT/${TAG}_slab_s1_full_b512 python bench.py --eager --pipeline 1 --steps 1 --warmup 1 --no-cpu-baseline --batch 512 > $OUT/${TAG}_slab_s1_full.out 2>&1
 echo "ncu full slab rc=$?"
 for tool in memcheck synccheck racecheck; do
   timeout 600 compute-sanitizer --tool $tool --print-limit 1000 --log-file $OUT/sanitize/${TAG}_${tool}_step.log --error-exitcode 3 python scripts/sanitize_step.py > $OUT/sanitize/${TAG}_${tool}_step.out 2>&1
@@ -37,3 +37,6 @@ for tool in memcheck synccheck racecheck; do
 done
 for f in $OUT/sanitize/${TAG}_*.log; do echo "== $f"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|Invalid|hazard|Barrier error|    at " $f | sed "s/by thread.*//" | sort | uniq -c | sort -rn | head -8; done
 ls -la $OUT/*.ncu-rep
+# DRAM bytes per residual-block conv launch of THIS build -> the file bench.py's roofline.traffic reads (copy it to profiles/r2_conv_traffic.json)
+python scripts/summarize_launches.py $OUT/${TAG}_launches_eager_traffic.csv --align --traffic-json $OUT/${TAG}_conv_traffic.json \
+    --build-id $(python -c "import bench; print(bench.conv_build_id())") --B 64 | tail -3

@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from helpers import norm_err, dev
-from oracle import train_oracle as TO
+from oracle import train_oracle as TO, sarnet_oracle as O
 
 pytestmark = pytest.mark.gpu
 
@@ -339,4 +339,87 @@ def test_train_on_batch_third_slice_lowers_the_loss(cuda_device):
     tr.sync_to_model()
     assert not np.allclose(w0, model.weights["AR_DS/kernel"])
     out = model.predict(x, batch_size=16)                   # the inference engine rebuilds with the trained weights
+    assert np.all(np.isfinite(out[0]))
+
+
+def test_gru_training_step_kernels_match_autograd(cuda_device):
+    """sar_gru_gate_fwd / sar_gru_gate_bwd through training.gru_dir_fwd / gru_dir_bwd (one GEMM + one gate kernel per time
+    step, BPTT) vs float64 autograd through the oracle's CuDNNGRU restatement, both directions, ragged sizes."""
+    from aesrc2020_b200 import training as T
+    rng = np.random.RandomState(5)
+    B, S, Din, u = 5, 7, 24, 16
+    f32 = lambda a: np.asarray(a, np.float32)
+    x = f32(rng.randn(B, S, Din))
+    gout = f32(rng.randn(B, S, 2 * u))
+    for di, (dname, reverse) in enumerate((("forward", False), ("backward", True))):
+        W, U, b = f32(rng.randn(Din, 3 * u) * 0.3), f32(rng.randn(u, 3 * u) * 0.3), f32(rng.randn(6 * u) * 0.2)
+        tx, tW, tU, tb = (torch.tensor(a.astype(np.float64), requires_grad=True) for a in (x, W, U, b))
+        o, _ = O.gru_direction(tx, tW, tU, tb, reverse)
+        (o * torch.tensor(gout[:, :, di * u:(di + 1) * u].astype(np.float64))).sum().backward()
+        out = torch.zeros((B, S, 2 * u), device="cuda")
+        sv = T.gru_dir_fwd(dev(x).view(B * S, Din), B, S, dev(W), dev(U), dev(b), reverse, out, di * u)
+        assert norm_err(out[:, :, di * u:(di + 1) * u], o.detach()) < 1e-5
+        gW, gU, gb, gx = T.gru_dir_bwd(dev(gout), sv, B, S, dev(W), dev(U))
+        for name, got, want in (("kernel", gW, tW.grad), ("recurrent", gU, tU.grad), ("bias", gb, tb.grad),
+                                ("x", gx.view(B, S, Din), tx.grad)):
+            assert norm_err(got, want) < 2e-5, (dname, name, norm_err(got, want))
+
+
+def test_head_trainer_fourth_slice_matches_the_oracle(cuda_device):
+    """HeadTrainer(train_crnn=True).step_on_features on the frozen ResNet's sequence vs
+    train_oracle.train_step(pool=dict(train_crnn=True)): gradients of CNN_LIN / CNN_LIN_LN / both CRNN directions / CRNN_LN
+    (and of everything above) and the parameters after two Adam steps."""
+    from aesrc2020_b200 import model as mdl, training as T
+    K, G, Dh = 8, 2, 256
+    model, _ = mdl.SAR_Net((200, 80, 1), ctc_enable=False, disc_enable=True, res_type="res34", res_filters=32, mto="gvlad",
+                           vlad_clusters=K, ghost_clusters=G, metric_loss="arcface", margin=0.3)
+    Cc = model.config.plan().cout
+    params = _params("arcface", K * Dh, seed=17)
+    rng = np.random.RandomState(37)
+    f32 = lambda a: np.asarray(a, np.float32).astype(np.float64)
+    params["gvlad_center_assignment/kernel"] = f32(rng.randn(1, 1, Dh, K + G) * 0.1)
+    params["gvlad_center_assignment/bias"] = f32(rng.randn(K + G) * 0.1)
+    params["gvlad_pool/centers"] = f32(rng.randn(K + G, Dh) * 0.3)
+    for k in TO.DS_KEYS + TO.CRNN_KEYS:
+        params[k] = f32(model.weights[k])
+    for k, v in params.items():
+        model.weights[k] = v.astype(np.float32)
+    tr = T.HeadTrainer(model, lr=0.01, train_crnn=True)
+    assert tr.train_ds and tr.train_pool and set(TO.CRNN_KEYS) <= set(tr.keys)
+    B, S = 6, 9
+    lab = rng.randint(0, 8, B)
+    pool = dict(mto="gvlad", vlad_clusters=K, ghost_clusters=G, train_crnn=True)
+    state, p_or, p_prev = {}, dict(params), dict(params)
+    l2k = set(TO.l2_keys(True, "arcface")) | set(TO.pool_l2_keys("gvlad")) | {"AR_DS/kernel", "AR_DS/bias"} | set(TO.CRNN_L2_KEYS)
+    for it in range(2):
+        seq = np.maximum(rng.randn(B, S, Cc) + (np.eye(8)[lab] @ rng.randn(8, Cc))[:, None, :] * 0.5, 0).astype(np.float32)
+        onehot = np.eye(8, dtype=np.float32)[lab]
+        p_or, state, l_or, g_or = TO.train_step(p_or, state, seq, onehot, lr=0.01, iterations=it, disc_enable=True,
+                                                metric_loss="arcface", margin=0.3, w_accent=tr.w_acc, w_disc=tr.w_disc, pool=pool)
+        got = tr.step_on_features(dev(seq), dev(onehot))
+        assert abs(got["loss_disc"] - l_or["loss_disc"]) < 2e-4 * max(1, abs(l_or["loss_disc"]))
+        for k in tr.keys:
+            if k in ("AR_BN1/beta", "AR_EMBEDDING/bias"):
+                continue
+            want = g_or[k] - (2 * TO.L2_REG * p_prev[k] if k in l2k else 0.0)
+            got_k = tr.last_grads[k].cpu().numpy().astype(np.float64)
+            err = float(np.max(np.abs(got_k - want)) / max(np.max(np.abs(want)), 1e-6))
+            assert err < 2e-3, (it, k, err)
+        p_prev = {k: v.copy() for k, v in p_or.items()}
+        for k in TO.CRNN_KEYS:
+            assert norm_err(tr.p[k], p_or[k]) < 2e-3, (it, k)
+
+
+def test_train_on_batch_fourth_slice_lowers_the_loss(cuda_device):
+    from aesrc2020_b200 import model as mdl, training as T, utils as us
+    model, _ = mdl.SAR_Net((200, 80, 1), disc_enable=True, res_type="res34", res_filters=32, mto="gvlad", vlad_clusters=8,
+                           ghost_clusters=2, metric_loss="arcface", margin=0.3)
+    x, y = us.synthetic_batch(model.config, 16, seed=3)
+    w0 = model.weights["CRNN/forward/recurrent_kernel"].copy()
+    tr = T.HeadTrainer(model, lr=0.01, train_crnn=True)
+    hist = [tr.train_on_batch(x, y)["loss"] for _ in range(20)]
+    assert hist[-1] < 0.7 * hist[0], hist
+    tr.sync_to_model()
+    assert not np.allclose(w0, model.weights["CRNN/forward/recurrent_kernel"])
+    out = model.predict(x, batch_size=16)
     assert np.all(np.isfinite(out[0]))

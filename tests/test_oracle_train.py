@@ -173,3 +173,56 @@ def test_third_slice_gradients_match_finite_differences():
             pp[k][i] += h; pm[k][i] -= h
             fd = (loss_of(pp) - loss_of(pm)) / (2 * h)
             assert abs(fd - g[i]) <= 2e-6 * max(1.0, abs(fd)) + 2e-8, (k, i, fd, g[i])
+
+
+def _crnn_params(rng, params, Cc, u):
+    params["CNN_LIN/kernel"] = rng.randn(Cc, u) * 0.4
+    params["CNN_LIN/bias"] = rng.randn(u) * 0.1
+    params["CNN_LIN_LN/gamma"] = rng.uniform(0.7, 1.3, u)
+    params["CNN_LIN_LN/beta"] = rng.randn(u) * 0.1
+    for d in ("forward", "backward"):
+        params["CRNN/%s/kernel" % d] = rng.randn(u, 3 * u) * 0.4
+        params["CRNN/%s/recurrent_kernel" % d] = rng.randn(u, 3 * u) * 0.4
+        params["CRNN/%s/bias" % d] = rng.randn(6 * u) * 0.1
+    params["CRNN_LN/gamma"] = rng.uniform(0.7, 1.3, 2 * u)
+    params["CRNN_LN/beta"] = rng.randn(2 * u) * 0.1
+    return params
+
+
+def test_fourth_slice_gradients_match_finite_differences():
+    """Fourth slice: CNN_LIN (Dense + tanh) -> CNN_LIN_LN -> CRNN (Bidirectional CuDNNGRU: back-propagation through time in
+    both directions) -> CRNN_LN -> the accent branch, on the frozen ResNet's sequence: autograd vs central differences for
+    every new trainable tensor (kernel, recurrent kernel and the 6u bias of both directions, the LayerNormalizations)."""
+    B, S, Cc, u, Dd, K, G, n = 3, 6, 7, 5, 6, 4, 2, 8
+    rng = np.random.RandomState(23)
+    params = _params("arcface", D=K * Dd)
+    params["gvlad_center_assignment/kernel"] = rng.randn(1, 1, Dd, K + G) * 0.5
+    params["gvlad_center_assignment/bias"] = rng.randn(K + G) * 0.1
+    params["gvlad_pool/centers"] = rng.randn(K + G, Dd) * 0.5
+    params["AR_DS/kernel"] = rng.randn(2 * u, Dd) * 0.4
+    params["AR_DS/bias"] = rng.randn(Dd) * 0.1
+    params["AR_DS_LN/gamma"] = rng.uniform(0.7, 1.3, Dd)
+    params["AR_DS_LN/beta"] = rng.randn(Dd) * 0.1
+    _crnn_params(rng, params, Cc, u)
+    x = rng.randn(B, S, Cc)
+    onehot = np.eye(n)[rng.randint(0, n, B)]
+    kw = dict(disc_enable=True, metric_loss="arcface", margin=0.3, w_accent=0.01, w_disc=0.6)
+    pool = dict(mto="gvlad", vlad_clusters=K, ghost_clusters=G, train_crnn=True)
+    _, state, losses, grads = TO.train_step(params, {}, x, onehot, lr=0.01, iterations=0, pool=pool, **kw)
+    assert set(TO.CRNN_KEYS) | set(TO.DS_KEYS) <= set(grads)
+
+    def loss_of(pp):
+        t = {k: torch.as_tensor(v) for k, v in pp.items()}
+        return float(TO.pooled_head_loss(t, torch.as_tensor(x), torch.as_tensor(onehot), **pool, **kw)[0])
+    for k in TO.CRNN_KEYS + ["AR_DS/kernel"]:
+        g = grads[k]
+        for _ in range(4):
+            i = tuple(rng.randint(0, s_) for s_ in g.shape)
+            h = 1e-6
+            pp, pm = {q: v.copy() for q, v in params.items()}, {q: v.copy() for q, v in params.items()}
+            pp[k][i] += h; pm[k][i] -= h
+            fd = (loss_of(pp) - loss_of(pm)) / (2 * h)
+            assert abs(fd - g[i]) <= 2e-6 * max(1.0, abs(fd)) + 2e-8, (k, i, fd, g[i])
+    # the regularisers: l2 on the Dense and on the GRU's input kernel / bias, none on the recurrent kernels
+    assert all(k in TO.CRNN_L2_KEYS for k in ("CRNN/forward/kernel", "CRNN/backward/bias", "CNN_LIN/bias"))
+    assert not any(k.endswith("recurrent_kernel") for k in TO.CRNN_L2_KEYS)
