@@ -543,15 +543,16 @@ def fbank_bench(runner, steps, peaks):
 
 # ====================================================================================== training slice
 def train_slice_bench(dev, rank, world, B=64, steps=10):
-    """one optimisation step of the accent branch above the frozen shared encoder --
-    training.HeadTrainer(train_ds=True).train_on_batch: encoder forward, AR_DS / AR_DS_LN / GhostVLAD / embedding / classifier /
-    ArcFace forward + backward in training mode, ONE flat gradient all-reduce over the ranks, Keras Adam.  Weak scaling."""
+    """one optimisation step of everything above the frozen ResNet on the accent path --
+    training.HeadTrainer(train_crnn=True).train_on_batch: ResNet inference forward, then CNN_LIN / CNN_LIN_LN / CRNN Bi-GRU
+    (BPTT) / CRNN_LN / AR_DS / AR_DS_LN / GhostVLAD / embedding / classifier / ArcFace forward + backward in training mode,
+    ONE flat gradient all-reduce over the ranks, Keras Adam.  Weak scaling."""
     import torch.distributed as tdist
     from aesrc2020_b200 import model as mdl, training as T, utils as us
     with contextlib.redirect_stdout(io.StringIO()):
         model, _ = mdl.SAR_Net((500, 80, 1), **dict(CONFIGS["cfg2"]["kw"]))
     x, y = us.synthetic_batch(model.config, B, seed=100 + rank)
-    tr = T.HeadTrainer(model, lr=0.01, train_ds=True)
+    tr = T.HeadTrainer(model, lr=0.01, train_crnn=True)
     xd = {k: model._to_device(k, v) for k, v in x.items()}
     for _ in range(3):
         tr.train_on_batch(xd, y)
@@ -569,11 +570,11 @@ def train_slice_bench(dev, rank, world, B=64, steps=10):
         t = torch.tensor([ms], device=dev)
         tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
         ms = float(t.item())
-    return {"workload": "accent branch above the frozen CRNN encoder (AR_DS .. y_accent / y_disc), B=%d/GPU, fwd + bwd + Adam" % B,
+    return {"workload": "everything above the frozen ResNet on the accent path (CNN_LIN, CRNN Bi-GRU with BPTT, AR_DS .. y_accent / y_disc), B=%d/GPU, fwd + bwd + Adam" % B,
             "ms_per_step": ms, "value": world * B / (ms * 1e-3), "unit": "utt/s (training, partial graph)",
             "trainable_parameters": int(sum(tr.p[k].numel() for k in tr.keys)), "allreduce_bytes_per_step": 4 * int(sum(tr.p[k].numel() for k in tr.keys)) if world > 1 else 0,
             "loss": float(last["loss"]), "scaling": "weak",
-            "note": "eager launches (no CUDA graph), includes the frozen encoder's inference forward; gradients of the shared encoder are not built"}
+            "note": "eager launches (no CUDA graph; the Bi-GRU is one GEMM + one gate kernel per time step and direction, fp32 CUDA cores), includes the frozen ResNet's inference forward; gradients of the ResNet and of the CTC branch are not built"}
 
 
 # ====================================================================================== strong scaling

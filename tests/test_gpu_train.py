@@ -406,8 +406,10 @@ def test_head_trainer_fourth_slice_matches_the_oracle(cuda_device):
             err = float(np.max(np.abs(got_k - want)) / max(np.max(np.abs(want)), 1e-6))
             assert err < 2e-3, (it, k, err)
         p_prev = {k: v.copy() for k, v in p_or.items()}
+        # Adam's first steps move every element by ~lr * sign(g): the few elements whose fp32 gradient is within rounding of
+        # zero can take the other sign (a 2 * lr difference each), so the parameters get a looser bound than the gradients
         for k in TO.CRNN_KEYS:
-            assert norm_err(tr.p[k], p_or[k]) < 2e-3, (it, k)
+            assert norm_err(tr.p[k], p_or[k]) < 8e-3, (it, k)
 
 
 def test_train_on_batch_fourth_slice_lowers_the_loss(cuda_device):
