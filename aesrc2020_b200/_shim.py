@@ -62,6 +62,7 @@ SIGNATURES = {
     "sar_labels_pack_fwd": (c_int, [c_ip, c_int, c_fp, c_ip, c_ip, c_int, c_int, c_fp, c_ip, c_ip, c_ip, c_int, C.c_void_p]),
     "sar_ctc_greedy_fwd": (c_int, [c_fp, c_int, c_ip, c_int, c_ip, c_ip, c_int, c_int, c_int, C.c_void_p]),
     "sar_ctc_ld_fwd": (c_int, [c_fp, c_int, c_fp, c_ip, c_ip, c_fp, c_fp, c_ip, c_int, c_int, c_int, c_int, C.c_void_p]),
+    "sar_ctc_grad_fwd": (c_int, [c_fp, c_int, c_fp, c_ip, c_ip, c_fp, c_fp, c_ip, c_int, c_int, c_int, c_int, C.c_float, C.c_void_p]),
     "sar_loss_reduce_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, C.c_void_p]),
     "sar_gemm_fwd": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_f, c_f, C.c_void_p]),
     "sar_bn_train_fwd": (c_int, [c_fp] * 8 + [c_int, c_int, c_f, c_f, C.c_void_p]),

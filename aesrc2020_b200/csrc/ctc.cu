@@ -112,6 +112,145 @@ __global__ void __launch_bounds__(CTC_THREADS) ctc_kernel(const float* __restric
   }
 }
 
+// ------------------------------------------------------------------ training mode: d loss / d logits (fifth slice)
+// ctc_kernel plus the beta recursion and the gradient of  loss_b = -log P(labels | q)  with respect to the PRE-softmax
+// ctc_pred logits a, through K.ctc_batch_cost's double normalisation (model.py:62-71):
+//   p = softmax(a),  u = log(p + 1e-7),  q = softmax(u) = (p + 1e-7) / Z;
+//   d loss / d u[t,k] = q[t,k] - gamma[t,k],   gamma[t,k] = sum_{s: ext[s] = k} alpha_t(s) beta_t(s) / (P q[t,k])   (Graves 2006)
+//   d loss / d p[t,j] = (q[t,j] - gamma[t,j]) / (p[t,j] + 1e-7),   d loss / d a[t,i] = p_i (dL/dp_i - sum_j p_j dL/dp_j).
+// One CTA per utterance; alpha of every frame stays in shared memory, frames are finished from the last to the first as
+// beta becomes available.  grad (B,S,C) receives scale * d loss_b / d a (frames >= in_len and rejected utterances: zeros).
+__global__ void __launch_bounds__(CTC_THREADS) ctc_grad_kernel(const float* __restrict__ logits, const float* __restrict__ labels,
+                                                                const int* __restrict__ in_len, const int* __restrict__ lab_len,
+                                                                float* __restrict__ loss, float* __restrict__ grad,
+                                                                int* __restrict__ status, int S, int C, int ld, int Lmax, float scale) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ __align__(16) float sm[];
+  const int NE = 2 * Lmax + 1;
+  float* lq = sm;                               // [S][NE]
+  float* al = lq + (size_t)S * NE;              // [S][NE]
+  float* beta = al + (size_t)S * NE;            // [2][NE]
+  float* stat = beta + 2 * NE;                  // [S][2]: row max, 1 / sum exp
+  float* gam = stat + 2 * S;                    // [C]
+  float* red = gam + C;                         // [32] block reduction scratch
+  int* ext = reinterpret_cast<int*>(red + 32);  // [NE]
+  __shared__ int bad;
+  __shared__ float s_ll;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int b = blockIdx.x;
+  const int T = in_len[b], L = lab_len[b];
+  float* gb = grad + (size_t)b * S * C;
+  if (t == 0) bad = 0;
+  __syncthreads();
+  const bool malformed = (T < 0 || T > S || L < 0 || L > Lmax);
+  const int blank = C - 1;
+  const int n = malformed ? 0 : 2 * L + 1;
+  for (int s = t; s < n; s += CTC_THREADS) {
+    int v = blank;
+    if (s & 1) {
+      v = (int)labels[(size_t)b * Lmax + (s >> 1)];
+      if (v < 0 || v >= blank) { bad = 1; v = 0; }
+    }
+    ext[s] = v;
+  }
+  __syncthreads();
+  for (int f = warp; f < S && !malformed; f += CTC_THREADS / 32) {
+    const float* row = logits + ((size_t)b * S + f) * ld;
+    float m = -INFINITY;
+    for (int c = lane; c < C; c += 32) m = fmaxf(m, __ldg(row + c));
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int c = lane; c < C; c += 32) sum += expf(__ldg(row + c) - m);
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    float z = 0.f;
+    for (int c = lane; c < C; c += 32) z += expf(__ldg(row + c) - m) * inv + CTC_EPS;
+    z = warp_sum(z);
+    if (lane == 0) { stat[2 * f] = m; stat[2 * f + 1] = inv; }
+    const float logz = logf(z);
+    if (f < T)
+      for (int s = lane; s < n; s += 32) lq[(size_t)f * NE + s] = logf(expf(__ldg(row + ext[s]) - m) * inv + CTC_EPS) - logz;
+  }
+  __syncthreads();
+  // ---- alpha, every frame kept
+  for (int s = t; s < n; s += CTC_THREADS) al[s] = (s < 2 && T > 0) ? lq[s] : -INFINITY;
+  __syncthreads();
+  for (int f = 1; f < T && !malformed; ++f) {
+    const float* a0 = al + (size_t)(f - 1) * NE;
+    for (int s = t; s < n; s += CTC_THREADS) {
+      const float x0 = a0[s];
+      const float x1 = (s >= 1) ? a0[s - 1] : -INFINITY;
+      const float x2 = (s >= 2 && (s & 1) && ext[s] != ext[s - 2]) ? a0[s - 2] : -INFINITY;
+      al[(size_t)f * NE + s] = lse3(x0, x1, x2) + lq[(size_t)f * NE + s];
+    }
+    __syncthreads();
+  }
+  if (t == 0) {
+    float ll = -INFINITY;
+    if (!malformed && T > 0) {
+      const float* aT = al + (size_t)(T - 1) * NE;
+      ll = (n > 1) ? lse2(aT[n - 1], aT[n - 2]) : aT[0];
+    }
+    const int st = (malformed || bad) ? 2 : ((ll == -INFINITY) ? 1 : 0);
+    loss[b] = malformed ? INFINITY : -ll;
+    if (status) status[b] = st;
+    s_ll = (st == 0) ? ll : -INFINITY;
+  }
+  __syncthreads();
+  const float ll = s_ll;
+  const bool ok = ll != -INFINITY;
+  // ---- frames past the utterance (or all frames of a rejected one): zero gradient
+  for (int f = ok ? T : 0; f < S; ++f)
+    for (int c = t; c < C; c += CTC_THREADS) gb[(size_t)f * C + c] = 0.f;
+  if (!ok) return;
+  // ---- beta (emission included, like alpha) from the last frame down; each frame's gradient as soon as its beta is known
+  const float Zc = 1.f + (float)C * CTC_EPS;    // sum_c (p_c + eps) up to rounding; the exact per-frame Z is recomputed below
+  (void)Zc;
+  float* b0 = beta;
+  float* b1 = beta + NE;
+  for (int f = T - 1; f >= 0; --f) {
+    for (int s = t; s < n; s += CTC_THREADS) {
+      float v;
+      if (f == T - 1) v = (s >= n - 2) ? lq[(size_t)f * NE + s] : -INFINITY;
+      else {
+        const float x0 = b1[s];
+        const float x1 = (s + 1 < n) ? b1[s + 1] : -INFINITY;
+        const float x2 = (s + 2 < n && (s & 1) && ext[s + 2] != ext[s]) ? b1[s + 2] : -INFINITY;
+        v = lse3(x0, x1, x2) + lq[(size_t)f * NE + s];
+      }
+      b0[s] = v;
+    }
+    for (int c = t; c < C; c += CTC_THREADS) gam[c] = 0.f;
+    __syncthreads();
+    for (int s = t; s < n; s += CTC_THREADS) {
+      const float lg = al[(size_t)f * NE + s] + b0[s] - lq[(size_t)f * NE + s] - ll;
+      if (lg > -80.f) atomicAdd(&gam[ext[s]], expf(lg));
+    }
+    __syncthreads();
+    const float* row = logits + ((size_t)b * S + f) * ld;
+    const float m = stat[2 * f], inv = stat[2 * f + 1];
+    // pass 1: Z and sum_j p_j dL/dp_j need q, which needs Z: Z first
+    float z = 0.f;
+    for (int c = t; c < C; c += CTC_THREADS) z += expf(__ldg(row + c) - m) * inv + CTC_EPS;
+    z = block_sum(z, red);
+    const float invz = 1.f / z;
+    float dot = 0.f;
+    for (int c = t; c < C; c += CTC_THREADS) {
+      const float pc = expf(__ldg(row + c) - m) * inv;
+      dot += pc * ((pc + CTC_EPS) * invz - gam[c]) / (pc + CTC_EPS);
+    }
+    dot = block_sum(dot, red);
+    for (int c = t; c < C; c += CTC_THREADS) {
+      const float pc = expf(__ldg(row + c) - m) * inv;
+      const float dp = ((pc + CTC_EPS) * invz - gam[c]) / (pc + CTC_EPS);
+      gb[(size_t)f * C + c] = scale * pc * (dp - dot);
+    }
+    __syncthreads();
+    float* tmp = b0; b0 = b1; b1 = tmp;
+  }
+}
+
 // Greedy CTC decode (K.ctc_decode(..., greedy=True), model.py:385-389 -> tf.nn.ctc_greedy_decoder with
 // merge_repeated=True): per frame the FIRST maximum over the C classes (softmax is monotone, so the pre-softmax
 // logits give the same path), then collapse repeats and drop blanks (blank = C-1).  One CTA per utterance: a warp
@@ -185,4 +324,18 @@ extern "C" int sar_ctc_ld_fwd(const float* logits, int ld, const float* labels, 
   { const int arc = allow_max_smem(ctc_kernel, "sar_ctc_fwd"); if (arc) return arc; }
   launch_k(ctc_kernel, dim3(B), dim3(CTC_THREADS), smem, (cudaStream_t)stream, logits, labels, in_len, lab_len, loss, probs, status, S, C, ld, Lmax);
   return check_launch("sar_ctc_fwd");
+}
+
+extern "C" int sar_ctc_grad_fwd(const float* logits, int ld, const float* labels, const int* in_len, const int* lab_len,
+                                float* loss, float* grad, int* status, int B, int S, int C, int Lmax, float scale, void* stream) {
+  using namespace sar;
+  SAR_REQUIRE(logits && labels && in_len && lab_len && loss && grad, SAR_ERR_BAD_ARG, "sar_ctc_grad_fwd: null pointer");
+  SAR_REQUIRE(B > 0 && S > 0 && C > 1 && Lmax > 0 && ld >= C, SAR_ERR_BAD_ARG, "sar_ctc_grad_fwd: bad dimension");
+  const int NE = 2 * Lmax + 1;
+  const size_t smem = sizeof(float) * (2 * (size_t)S * NE + 2 * NE + 2 * (size_t)S + C + 32) + sizeof(int) * NE;
+  SAR_REQUIRE(smem <= 227 * 1024, SAR_ERR_UNSUPPORTED, "sar_ctc_grad_fwd: S*(2*Lmax+1) too large for shared memory (%zu B)", smem);
+  { const int arc = allow_max_smem(ctc_grad_kernel, "sar_ctc_grad_fwd"); if (arc) return arc; }
+  launch_k(ctc_grad_kernel, dim3(B), dim3(CTC_THREADS), smem, (cudaStream_t)stream, logits, labels, in_len, lab_len, loss, grad, status,
+           S, C, ld, Lmax, scale);
+  return check_launch("sar_ctc_grad_fwd");
 }

@@ -24,7 +24,10 @@ Fourth slice, `HeadTrainer(model, train_crnn=True)`: CNN_LIN (Dense + tanh) -> C
 CRNN_LN are trained too (model.py:252-256) -- everything above the ResNet on the accent path.  The Bi-GRU runs in training
 mode as one GEMM + `sar_gru_gate_fwd` per time step (gates kept) and is differentiated by back-propagation through time
 (`sar_gru_gate_bwd` + one GEMM per step, the weight gradients as three GEMMs over all steps).
-Not built yet: gradients of the ResNet convolutions and of the CTC branch, i.e. end-to-end multi-task training.
+Fifth slice, `HeadTrainer(model, train_ctc=True)`: the CTC branch -- CTC_BIGRU -> CTC_BIGRU_LN -> CTC_DS -> CTC_DS_LN -> ctc_pred ->
+K.ctc_batch_cost (model.py:261-269, 62-71; `sar_ctc_grad_fwd`: alpha-beta recursion, gradient through the double normalisation) --
+is trained together with the accent branch, their gradients joining at CRNN_LN: multi-task training of everything above the ResNet.
+Not built yet: gradients of the ResNet convolutions (stem, residual blocks), i.e. end-to-end training.
 """
 from __future__ import annotations
 
@@ -221,6 +224,22 @@ def gru_dir_bwd(g_out, saved, B: int, S: int, W, U, g_x=None):
     return gW, gU, gb, g_x
 
 
+def ctc_grad(logits, labels, in_len, lab_len, scale: float, classes=None):
+    """sar_ctc_grad_fwd: K.ctc_batch_cost per utterance and scale * d loss_b / d (pre-softmax ctc_pred logits) (B,S,C)."""
+    B, S, ld = logits.shape
+    Cc = int(classes) if classes else ld
+    labels = labels.to(torch.float32).contiguous()
+    in_len = in_len.reshape(-1).to(torch.int32).contiguous()
+    lab_len = lab_len.reshape(-1).to(torch.int32).contiguous()
+    loss = torch.empty((B,), device=logits.device, dtype=torch.float32)
+    status = torch.empty((B,), device=logits.device, dtype=torch.int32)
+    grad = torch.empty((B, S, Cc), device=logits.device, dtype=torch.float32)
+    check(_shim.lib().sar_ctc_grad_fwd(ptr(logits), ld, ptr(labels), ptr(in_len), ptr(lab_len), ptr(loss), ptr(grad), ptr(status),
+                                       B, S, Cc, labels.shape[1], float(scale), stream_ptr()), "sar_ctc_grad_fwd")
+    ops._count(1)
+    return loss, grad, status
+
+
 def adam_step(p, g, m, v, lr_t, l2=0.0):
     check(_shim.lib().sar_adam_fwd(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), float(lr_t), ADAM_B1, ADAM_B2, ADAM_EPS, float(l2),
                                    stream_ptr()), "sar_adam_fwd")
@@ -243,17 +262,23 @@ class HeadTrainer:
     """Fine-tunes the accent head of a SARModel on the device (module docstring)."""
 
     def __init__(self, model, lr: float = 0.01, group=None, train_pool: bool = False, train_ds: bool = False,
-                 train_crnn: bool = False):
+                 train_crnn: bool = False, train_ctc: bool = False):
         """train_pool: also train the NetVLAD / GhostVLAD pooling layer (assignment Conv2D + centers, model.py:82-109):
         the frozen encoder then ends at AR_DS_LN and the step differentiates vlad() as well (second slice).
         train_ds (implies train_pool): also train AR_DS (Dense + tanh, l2 regularisers) and AR_DS_LN (model.py:275-276):
         the whole accent branch above the shared CRNN encoder; the frozen encoder ends at CRNN_LN (third slice).
         train_crnn (implies train_ds): also train CNN_LIN (Dense + tanh) -> CNN_LIN_LN -> CRNN (Bidirectional CuDNNGRU, back-
         propagation through time) -> CRNN_LN (model.py:252-256): everything above the ResNet on the accent path; the
-        frozen encoder is the ResNet alone (fourth slice)."""
+        frozen encoder is the ResNet alone (fourth slice).
+        train_ctc (implies train_crnn; needs ctc_enable): the CTC branch as well -- CTC_BIGRU -> CTC_BIGRU_LN -> CTC_DS (Dense +
+        tanh) -> CTC_DS_LN -> ctc_pred -> K.ctc_batch_cost (model.py:261-269, 62-71), its gradient joining the accent
+        branch's at CRNN_LN: multi-task training of everything above the ResNet (fifth slice)."""
         cfg = model.config
         if not cfg.ar_enable:
             raise ValueError("HeadTrainer needs ar_enable=True")
+        if train_ctc and not cfg.ctc_enable:
+            raise ValueError("train_ctc needs a model built with ctc_enable=True")
+        train_crnn = bool(train_crnn or train_ctc)
         train_ds = bool(train_ds or train_crnn)
         train_pool = bool(train_pool or train_ds)
         if train_pool and cfg.mto not in ("vlad", "gvlad"):
@@ -262,6 +287,7 @@ class HeadTrainer:
         self.train_pool = bool(train_pool)
         self.train_ds = bool(train_ds)
         self.train_crnn = bool(train_crnn)
+        self.train_ctc = bool(train_ctc)
         self.iterations = 0
         self.head_kind = cfg.metric_loss if cfg.disc_enable else None
         self.disc_key = None
@@ -287,8 +313,16 @@ class HeadTrainer:
             self.keys += self.crnn_keys
             # DS: l2(1e-4) on kernel and bias; BIGRU: kernel_regularizer + bias_regularizer, none on the recurrent kernel (model.py:35-50)
             self.l2 |= {"CNN_LIN/kernel", "CNN_LIN/bias"} | {k for k in gk if not k.endswith("recurrent_kernel")}
+        self.ctc_keys: List[str] = []
+        if self.train_ctc:
+            gk = ["CTC_BIGRU/%s/%s" % (d, w) for d in ("forward", "backward") for w in ("kernel", "recurrent_kernel", "bias")]
+            self.ctc_keys = gk + ["CTC_BIGRU_LN/gamma", "CTC_BIGRU_LN/beta", "CTC_DS/kernel", "CTC_DS/bias", "CTC_DS_LN/gamma",
+                                  "CTC_DS_LN/beta", "ctc_pred/kernel", "ctc_pred/bias"]
+            self.keys += self.ctc_keys
+            self.l2 |= {"CTC_DS/kernel", "CTC_DS/bias", "ctc_pred/kernel", "ctc_pred/bias"} | {k for k in gk if not k.endswith("recurrent_kernel")}
         lw = cfg.loss_weights()
         self.w_acc, self.w_disc = float(lw.get("y_accent", 0.0)), float(lw.get("y_disc", 0.0))
+        self.w_ctc = float(lw.get("y_ctc_loss", 0.0))
         dev = torch.device(model.device)
         put = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
         bn_stats = [b + s for b in ("AR_BN1", "AR_BN2") for s in ("/moving_mean", "/moving_variance")]
@@ -307,9 +341,12 @@ class HeadTrainer:
         return out["crnn" if self.train_ds else ("ar_ds" if self.train_pool else "integration")].contiguous()
 
     # ---- one step on (integ | descriptors, onehot) device tensors
-    def step_on_features(self, integ: torch.Tensor, onehot: torch.Tensor) -> Dict[str, float]:
+    def step_on_features(self, integ: torch.Tensor, onehot: torch.Tensor, ctc=None) -> Dict[str, float]:
+        """`ctc` (train_ctc): (x_ctc_label (B,Lmax), x_ctc_in_len (B,1), x_ctc_out_len (B,1)) device tensors."""
         p, cfg = self.p, self.cfg
         B = integ.shape[0]
+        g_ctc: Dict[str, torch.Tensor] = {}
+        g_crnn_ctc = loss_ctc = None
         pool = ds = rn = None
         if self.train_crnn:                      # CNN_LIN -> CNN_LIN_LN -> CRNN -> CRNN_LN on the frozen ResNet's sequence (B,S,Cc)
             _, Sr, Cr = integ.shape
@@ -323,6 +360,35 @@ class HeadTrainer:
             crnn_rows = ops.layernorm(gru_out.view(B * Sr, 2 * u), p["CRNN_LN/gamma"], p["CRNN_LN/beta"])
             rn = (x0, y_lin, z_lin, gru_out, sv, Sr)
             integ = crnn_rows.view(B, Sr, 2 * u)
+            if self.train_ctc:                   # the whole CTC branch, forward and backward, down to d loss / d CRNN_LN output
+                if ctc is None:
+                    raise ValueError("train_ctc needs the CTC inputs (x_ctc_label, x_ctc_in_len, x_ctc_out_len)")
+                uc = p["CTC_BIGRU/forward/recurrent_kernel"].shape[0]
+                ago = torch.empty((B, Sr, 2 * uc), device=integ.device, dtype=torch.float32)
+                svc = [gru_dir_fwd(crnn_rows, B, Sr, p["CTC_BIGRU/%s/kernel" % d], p["CTC_BIGRU/%s/recurrent_kernel" % d],
+                                   p["CTC_BIGRU/%s/bias" % d], d == "backward", ago, i * uc) for i, d in enumerate(("forward", "backward"))]
+                a1 = ops.layernorm(ago.view(B * Sr, 2 * uc), p["CTC_BIGRU_LN/gamma"], p["CTC_BIGRU_LN/beta"])
+                y2 = bias_act(gemm(a1, p["CTC_DS/kernel"]), p["CTC_DS/bias"], tanh=True)
+                a2 = ops.layernorm(y2, p["CTC_DS_LN/gamma"], p["CTC_DS_LN/beta"])
+                logits = bias_act(gemm(a2, p["ctc_pred/kernel"]), p["ctc_pred/bias"])
+                Cb = logits.shape[-1]
+                loss_b, g_log, status = ctc_grad(logits.view(B, Sr, Cb), ctc[0], ctc[1], ctc[2], self.w_ctc / B)
+                if bool((status != 0).any()):
+                    raise _shim.SarnetError("CTC: infeasible or out-of-range label sequence in batch")
+                loss_ctc = loss_b
+                g_log = g_log.view(B * Sr, Cb)
+                g_ctc["ctc_pred/kernel"], g_ctc["ctc_pred/bias"] = gemm(a2, g_log, ta=True), colsum(g_log)
+                g_a2 = gemm(g_log, p["ctc_pred/kernel"], tb=True)
+                g_p2, gzx = ln_train_bwd(y2, p["CTC_DS_LN/gamma"], g_a2, tanh_in=True)
+                g_ctc["CTC_DS_LN/gamma"], g_ctc["CTC_DS_LN/beta"] = colsum(gzx), colsum(g_a2)
+                g_ctc["CTC_DS/kernel"], g_ctc["CTC_DS/bias"] = gemm(a1, g_p2, ta=True), colsum(g_p2)
+                g_a1 = gemm(g_p2, p["CTC_DS/kernel"], tb=True)
+                g_ago, gzx = ln_train_bwd(ago.view(B * Sr, 2 * uc), p["CTC_BIGRU_LN/gamma"], g_a1, tanh_in=False)
+                g_ctc["CTC_BIGRU_LN/gamma"], g_ctc["CTC_BIGRU_LN/beta"] = colsum(gzx), colsum(g_a1)
+                for d, s_ in zip(("forward", "backward"), svc):
+                    gW, gU, gb, g_crnn_ctc = gru_dir_bwd(g_ago.view(B, Sr, 2 * uc), s_, B, Sr, p["CTC_BIGRU/%s/kernel" % d],
+                                                         p["CTC_BIGRU/%s/recurrent_kernel" % d], g_x=g_crnn_ctc)
+                    g_ctc["CTC_BIGRU/%s/kernel" % d], g_ctc["CTC_BIGRU/%s/recurrent_kernel" % d], g_ctc["CTC_BIGRU/%s/bias" % d] = gW, gU, gb
         if self.train_ds:                        # AR_DS -> AR_DS_LN on the frozen encoder's CRNN_LN output (B,S,2u)
             crnn = integ
             _, S0, C0 = crnn.shape
@@ -393,7 +459,10 @@ class HeadTrainer:
                 if rn is not None:               # ... and on through CRNN_LN, the Bi-GRU (BPTT), CNN_LIN_LN and CNN_LIN
                     x0, y_lin, z_lin, gru_out, sv, Sr = rn
                     u2 = gru_out.shape[-1]
-                    g_crnn = gemm(g_pre, p["AR_DS/kernel"], tb=True)                    # (B*S, 2u) = d loss / d CRNN_LN output
+                    if g_crnn_ctc is not None:                                          # + the CTC branch's share
+                        g_crnn = gemm(g_pre, p["AR_DS/kernel"], tb=True, out=g_crnn_ctc, beta=1.0)
+                    else:
+                        g_crnn = gemm(g_pre, p["AR_DS/kernel"], tb=True)                # (B*S, 2u) = d loss / d CRNN_LN output
                     g_gru, gzx2 = ln_train_bwd(gru_out.view(B * Sr, u2), p["CRNN_LN/gamma"], g_crnn, tanh_in=False)
                     g["CRNN_LN/gamma"], g["CRNN_LN/beta"] = colsum(gzx2), colsum(g_crnn)
                     g_zlin = None
@@ -411,6 +480,7 @@ class HeadTrainer:
             gc = torch.zeros_like(p[kc_])                                             # ghost centers: no gradient
             gc[:K] = colsum(gc_part.view(B, K * D)).view(K, D)
             g[kc_] = gc
+        g.update(g_ctc)
         self._all_reduce(g)
         self.last_grads = g
         # Adam (the l2 regulariser's gradient 2 * 1e-4 * w is added inside the kernel), then the kernel constraint
@@ -426,6 +496,9 @@ class HeadTrainer:
         if kind:
             out["loss_disc"] = lm[1]
             total += self.w_disc * lm[1]
+        if loss_ctc is not None:
+            out["loss_ctc"] = float(loss_ctc.mean().item())
+            total += self.w_ctc * out["loss_ctc"]
         out["loss"] = total                        # data terms (Keras adds the regulariser terms to the reported total)
         return out
 
@@ -450,7 +523,10 @@ class HeadTrainer:
         if onehot is None:
             raise ValueError("train_on_batch needs the accent labels (x_accent, or y['y_accent'])")
         onehot = self.model._to_device("x_accent", onehot).contiguous()
-        return self.step_on_features(self.encode(xd), onehot)
+        ctc = None
+        if self.train_ctc:
+            ctc = tuple(self.model._to_device(k, xd[k]).contiguous() for k in ("x_ctc_label", "x_ctc_in_len", "x_ctc_out_len"))
+        return self.step_on_features(self.encode(xd), onehot, ctc)
 
     def fit_generator(self, generator, steps_per_epoch: int, epochs: int = 1, verbose: int = 0):
         """train.py:38-44 shape: `epochs` x `steps_per_epoch` batches of (inputs, targets) from the generator."""

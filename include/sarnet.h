@@ -269,6 +269,11 @@ int sar_ctc_fwd(const float* logits, const float* labels, const int* in_len, con
  * its output columns to a multiple of 32 (1000 -> 1024); only the first C columns of a row are classes. */
 int sar_ctc_ld_fwd(const float* logits, int ld, const float* labels, const int* in_len, const int* lab_len,
                    float* loss, float* probs, int* status, int B, int S, int C, int Lmax, void* stream);
+/* Training mode (model.py:62-71 under compile(), model.py:187-201): the same loss plus grad (B,S,C) = scale * d loss_b / d logits
+ * (alpha-beta recursion; through q = softmax(log(softmax(logits) + 1e-7))); frames >= in_len and utterances with status != 0
+ * get zero gradient. */
+int sar_ctc_grad_fwd(const float* logits, int ld, const float* labels, const int* in_len, const int* lab_len,
+                     float* loss, float* grad, int* status, int B, int S, int C, int Lmax, float scale, void* stream);
 
 /* Greedy CTC decode of the ctc_pred posteriors from PRE-softmax logits (rows `ld` >= C floats apart).
  * Replaces: ctc_pred() = K.ctc_decode(pred, input_len, greedy=True) (model.py:385-389; tf.nn.ctc_greedy_decoder with

@@ -99,19 +99,45 @@ GRU_KEYS = ["CRNN/%s/%s" % (d, w) for d in ("forward", "backward") for w in ("ke
 CRNN_KEYS = ["CNN_LIN/kernel", "CNN_LIN/bias", "CNN_LIN_LN/gamma", "CNN_LIN_LN/beta"] + GRU_KEYS + ["CRNN_LN/gamma", "CRNN_LN/beta"]
 # DS: l2(1e-4) on kernel and bias; BIGRU: kernel_regularizer and bias_regularizer, none on the recurrent kernel (model.py:35-50)
 CRNN_L2_KEYS = ["CNN_LIN/kernel", "CNN_LIN/bias"] + [k for k in GRU_KEYS if not k.endswith("recurrent_kernel")]
+# fifth slice (model.py:261-269): CTC_BIGRU -> CTC_BIGRU_LN -> CTC_DS -> CTC_DS_LN -> ctc_pred -> K.ctc_batch_cost
+CTC_GRU_KEYS = ["CTC_BIGRU/%s/%s" % (d, w) for d in ("forward", "backward") for w in ("kernel", "recurrent_kernel", "bias")]
+CTC_KEYS = CTC_GRU_KEYS + ["CTC_BIGRU_LN/gamma", "CTC_BIGRU_LN/beta", "CTC_DS/kernel", "CTC_DS/bias", "CTC_DS_LN/gamma", "CTC_DS_LN/beta",
+                           "ctc_pred/kernel", "ctc_pred/bias"]
+CTC_L2_KEYS = ["CTC_DS/kernel", "CTC_DS/bias", "ctc_pred/kernel", "ctc_pred/bias"] + [k for k in CTC_GRU_KEYS if not k.endswith("recurrent_kernel")]
+
+
+def ctc_loss_autograd(probs, labels, in_len, lab_len):
+    """K.ctc_batch_cost (O.ctc_batch_cost: q = softmax(log(p + 1e-7)), blank = C-1) in a form autograd can differentiate:
+    torch's own CTC on log q (O.ctc_batch_cost's explicit lattice takes logsumexp over all -inf states, whose gradient is
+    NaN; the two forwards agree -- tests/test_oracle_kats.py).  Returns the (B,) losses."""
+    B, S, C = probs.shape
+    logq = torch.log_softmax(torch.log(probs + O.K_EPS), dim=-1).transpose(0, 1)           # (S,B,C)
+    il = torch.as_tensor(np.asarray(in_len).reshape(-1), dtype=torch.long)
+    ll = torch.as_tensor(np.asarray(lab_len).reshape(-1), dtype=torch.long)
+    lab = torch.as_tensor(np.asarray(labels), dtype=torch.long)
+    return torch.nn.functional.ctc_loss(logq, lab, il, ll, blank=C - 1, reduction="none", zero_infinity=False)
 
 
 def pooled_head_loss(p: Dict[str, torch.Tensor], feat: torch.Tensor, onehot: torch.Tensor, *, mto: str, vlad_clusters: int,
-                     ghost_clusters: int, train_ds: bool = False, train_crnn: bool = False, **kw):
+                     ghost_clusters: int, train_ds: bool = False, train_crnn: bool = False, train_ctc: bool = False, ctc=None,
+                     w_ctc: float = 0.0, **kw):
     """feat (B,S,D) = AR_DS_LN output (frozen encoder) -> vlad() -> the head of head_loss, with the pooling layer's
     regularisers added.  train_ds: feat is the CRNN_LN output (B,S,2u) instead and AR_DS (Dense + tanh, l2 regularisers on
     kernel and bias) -> AR_DS_LN run in front of vlad() (model.py:275-276)."""
     reg_ds = 0.0
+    train_crnn = train_crnn or train_ctc
     if train_crnn:           # feat is the frozen ResNet's sequence (B,S,Cc): model.py:252-256 in front of the accent branch
         feat = O.layernorm(O.dense(feat, p, "CNN_LIN", "tanh"), p, "CNN_LIN_LN")
         feat = O.layernorm(O.bigru(feat, p, "CRNN"), p, "CRNN_LN")
         reg_ds = reg_ds + sum(L2_REG * (p[k] ** 2).sum() for k in CRNN_L2_KEYS)
         train_ds = True
+    ctc_term = ctc_losses = None
+    if train_ctc:            # ctc = (labels (B,Lmax), in_len, lab_len): the ASR branch on the CRNN_LN output (model.py:261-269)
+        asr = O.layernorm(O.bigru(feat, p, "CTC_BIGRU"), p, "CTC_BIGRU_LN")
+        asr = O.layernorm(O.dense(asr, p, "CTC_DS", "tanh"), p, "CTC_DS_LN")
+        ctc_losses = ctc_loss_autograd(O.dense(asr, p, "ctc_pred", "softmax"), *ctc)
+        ctc_term = w_ctc * ctc_losses.mean()
+        reg_ds = reg_ds + sum(L2_REG * (p[k] ** 2).sum() for k in CTC_L2_KEYS)
     if train_ds:
         feat = O.layernorm(O.dense(feat, p, "AR_DS", "tanh"), p, "AR_DS_LN")
         reg_ds = reg_ds + L2_REG * ((p["AR_DS/kernel"] ** 2).sum() + (p["AR_DS/bias"] ** 2).sum())
@@ -120,6 +146,9 @@ def pooled_head_loss(p: Dict[str, torch.Tensor], feat: torch.Tensor, onehot: tor
     reg = sum(L2_REG * (p[k] ** 2).sum() for k in pool_l2_keys(mto)) + reg_ds
     parts["reg"] = parts["reg"] + reg
     parts["integration"] = integ
+    if ctc_term is not None:
+        parts["loss_ctc"] = ctc_losses.mean()
+        total = total + ctc_term
     return total + reg, parts
 
 
@@ -141,8 +170,8 @@ def train_step(params: Dict[str, np.ndarray], state: Dict[str, np.ndarray], inte
     vlad() and the pooling layer's weights are trained too (pooled_head_loss).
     Returns (new params incl. the BN moving statistics, new state, losses, gradients)."""
     keys = trainable_keys(disc_enable, metric_loss) + (pool_keys(pool["mto"]) if pool else []) + \
-        (DS_KEYS if (pool and (pool.get("train_ds") or pool.get("train_crnn"))) else []) + \
-        (CRNN_KEYS if (pool and pool.get("train_crnn")) else [])
+        (DS_KEYS if (pool and (pool.get("train_ds") or pool.get("train_crnn") or pool.get("train_ctc"))) else []) + \
+        (CRNN_KEYS if (pool and (pool.get("train_crnn") or pool.get("train_ctc"))) else []) + (CTC_KEYS if (pool and pool.get("train_ctc")) else [])
     p = {k: torch.tensor(np.asarray(v, np.float64), requires_grad=(k in keys)) for k, v in params.items()}
     kw = dict(disc_enable=disc_enable, metric_loss=metric_loss, margin=margin, w_accent=w_accent, w_disc=w_disc)
     x_in, y_in = torch.as_tensor(np.asarray(integ, np.float64)), torch.as_tensor(np.asarray(onehot, np.float64))

@@ -425,3 +425,88 @@ def test_train_on_batch_fourth_slice_lowers_the_loss(cuda_device):
     assert not np.allclose(w0, model.weights["CRNN/forward/recurrent_kernel"])
     out = model.predict(x, batch_size=16)
     assert np.all(np.isfinite(out[0]))
+
+
+@pytest.mark.parametrize("B,S,C,Lmax,ld", [(5, 12, 9, 4, 9), (3, 75, 1000, 72, 1024), (4, 21, 33, 6, 64)])
+def test_ctc_gradient_kernel_matches_autograd(cuda_device, B, S, C, Lmax, ld):
+    """sar_ctc_grad_fwd (alpha-beta recursion, gradient through q = softmax(log(softmax(a) + 1e-7))) vs float64 autograd
+    of the oracle's CTC: losses and d loss / d logits, ragged input / label lengths, repeated labels, padded rows
+    (ld > C: the tensor-core ctc_pred layout), frames past in_len get zero gradient."""
+    from aesrc2020_b200 import training as T
+    rng = np.random.RandomState(B * 100 + S)
+    logits = (rng.randn(B, S, ld) * 2).astype(np.float32)
+    lab_len = rng.randint(1, Lmax + 1, B)
+    in_len = np.array([rng.randint(min(S, 2 * l + 1), S + 1) for l in lab_len])
+    labels = np.zeros((B, Lmax), np.float32)
+    for b in range(B):
+        labels[b, :lab_len[b]] = rng.randint(0, C - 1, lab_len[b])
+        if lab_len[b] >= 2:
+            labels[b, 1] = labels[b, 0]                      # a repeat: needs the blank between
+    scale = 0.37
+    ta = torch.tensor(logits[:, :, :C].astype(np.float64), requires_grad=True)
+    lo = TO.ctc_loss_autograd(torch.softmax(ta, -1), labels, in_len, lab_len)
+    (scale * lo.sum()).backward()
+    loss, grad, status = T.ctc_grad(dev(logits), dev(labels), torch.from_numpy(in_len.astype(np.int32)).cuda(),
+                                    torch.from_numpy(lab_len.astype(np.int32)).cuda(), scale, classes=C)
+    assert int(status.abs().max()) == 0
+    assert norm_err(loss, lo.detach()) < 1e-5
+    assert norm_err(grad, ta.grad) < 5e-5, norm_err(grad, ta.grad)
+    for b in range(B):
+        assert float(grad[b, in_len[b]:].abs().sum()) == 0.0
+
+
+def test_head_trainer_fifth_slice_multitask_matches_the_oracle(cuda_device):
+    """HeadTrainer(train_ctc=True): CTC branch + accent branch above the frozen ResNet, one step vs
+    train_oracle.train_step(pool=dict(train_ctc=True, ctc=..., w_ctc=...)): every gradient, the three losses."""
+    from aesrc2020_b200 import model as mdl, training as T
+    K, G, Dh = 8, 2, 256
+    model, _ = mdl.SAR_Net((200, 80, 1), ctc_enable=True, disc_enable=True, res_type="res34", res_filters=32, mto="gvlad",
+                           vlad_clusters=K, ghost_clusters=G, metric_loss="arcface", margin=0.3, bpe_classes=50, max_ctc_len=6)
+    Cc = model.config.plan().cout
+    params = _params("arcface", K * Dh, seed=19)
+    rng = np.random.RandomState(41)
+    f32 = lambda a: np.asarray(a, np.float32).astype(np.float64)
+    params["gvlad_center_assignment/kernel"] = f32(rng.randn(1, 1, Dh, K + G) * 0.1)
+    params["gvlad_center_assignment/bias"] = f32(rng.randn(K + G) * 0.1)
+    params["gvlad_pool/centers"] = f32(rng.randn(K + G, Dh) * 0.3)
+    for k in TO.DS_KEYS + TO.CRNN_KEYS + TO.CTC_KEYS:
+        params[k] = f32(model.weights[k])
+    for k, v in params.items():
+        model.weights[k] = v.astype(np.float32)
+    tr = T.HeadTrainer(model, lr=0.01, train_ctc=True)
+    assert tr.train_crnn and set(TO.CTC_KEYS) <= set(tr.keys) and tr.w_ctc > 0
+    B, S = 5, 13
+    lab = rng.randint(0, 8, B)
+    labels = rng.randint(0, 49, (B, 6)).astype(np.float32)
+    lab_len = rng.randint(1, 7, (B, 1)).astype(np.int32)
+    in_len = np.full((B, 1), S, np.int32)
+    pool = dict(mto="gvlad", vlad_clusters=K, ghost_clusters=G, train_ctc=True, ctc=(labels, in_len, lab_len), w_ctc=tr.w_ctc)
+    l2k = set(TO.l2_keys(True, "arcface")) | set(TO.pool_l2_keys("gvlad")) | {"AR_DS/kernel", "AR_DS/bias"} | set(TO.CRNN_L2_KEYS) | set(TO.CTC_L2_KEYS)
+    seq = np.maximum(rng.randn(B, S, Cc) + (np.eye(8)[lab] @ rng.randn(8, Cc))[:, None, :] * 0.5, 0).astype(np.float32)
+    onehot = np.eye(8, dtype=np.float32)[lab]
+    p_or, state, l_or, g_or = TO.train_step(dict(params), {}, seq, onehot, lr=0.01, iterations=0, disc_enable=True,
+                                            metric_loss="arcface", margin=0.3, w_accent=tr.w_acc, w_disc=tr.w_disc, pool=pool)
+    got = tr.step_on_features(dev(seq), dev(onehot), (dev(labels), torch.from_numpy(in_len).cuda(), torch.from_numpy(lab_len).cuda()))
+    assert abs(got["loss_ctc"] - l_or["loss_ctc"]) < 2e-4 * max(1, abs(l_or["loss_ctc"]))
+    assert abs(got["loss_disc"] - l_or["loss_disc"]) < 2e-4 * max(1, abs(l_or["loss_disc"]))
+    for k in tr.keys:
+        if k in ("AR_BN1/beta", "AR_EMBEDDING/bias"):
+            continue
+        want = g_or[k] - (2 * TO.L2_REG * params[k] if k in l2k else 0.0)
+        got_k = tr.last_grads[k].cpu().numpy().astype(np.float64)
+        err = float(np.max(np.abs(got_k - want)) / max(np.max(np.abs(want)), 1e-6))
+        assert err < 2e-3, (k, err)
+
+
+def test_train_on_batch_fifth_slice_lowers_both_losses(cuda_device):
+    from aesrc2020_b200 import model as mdl, training as T, utils as us
+    model, _ = mdl.SAR_Net((200, 80, 1), ctc_enable=True, disc_enable=True, res_type="res34", res_filters=32, mto="gvlad",
+                           vlad_clusters=8, ghost_clusters=2, metric_loss="arcface", margin=0.3)
+    x, y = us.synthetic_batch(model.config, 12, seed=5)
+    tr = T.HeadTrainer(model, lr=0.01, train_ctc=True)
+    hist = [tr.train_on_batch(x, y) for _ in range(20)]
+    assert hist[-1]["loss_ctc"] < 0.8 * hist[0]["loss_ctc"], [h["loss_ctc"] for h in hist]
+    assert hist[-1]["loss_disc"] < hist[0]["loss_disc"], [h["loss_disc"] for h in hist]
+    tr.sync_to_model()
+    outs = model.predict(x, batch_size=12)
+    assert all(np.all(np.isfinite(o)) for o in outs)

@@ -226,3 +226,59 @@ def test_fourth_slice_gradients_match_finite_differences():
     # the regularisers: l2 on the Dense and on the GRU's input kernel / bias, none on the recurrent kernels
     assert all(k in TO.CRNN_L2_KEYS for k in ("CRNN/forward/kernel", "CRNN/backward/bias", "CNN_LIN/bias"))
     assert not any(k.endswith("recurrent_kernel") for k in TO.CRNN_L2_KEYS)
+
+
+def test_fifth_slice_ctc_branch_gradients_match_finite_differences():
+    """Fifth slice: the CTC branch (CTC_BIGRU -> LN -> CTC_DS -> LN -> ctc_pred -> K.ctc_batch_cost) trained with the accent
+    branch above the frozen ResNet.  The differentiable CTC (torch's own on log q) equals the oracle's explicit lattice;
+    autograd of the multi-task total vs central differences for every CTC-branch tensor and for the shared CRNN below."""
+    from oracle import sarnet_oracle as O
+    B, S, Cc, u, Dd, K, G, n, C, Lmax = 3, 7, 6, 4, 6, 4, 2, 8, 9, 3
+    rng = np.random.RandomState(29)
+    params = _params("arcface", D=K * Dd)
+    params["gvlad_center_assignment/kernel"] = rng.randn(1, 1, Dd, K + G) * 0.5
+    params["gvlad_center_assignment/bias"] = rng.randn(K + G) * 0.1
+    params["gvlad_pool/centers"] = rng.randn(K + G, Dd) * 0.5
+    params["AR_DS/kernel"] = rng.randn(2 * u, Dd) * 0.4
+    params["AR_DS/bias"] = rng.randn(Dd) * 0.1
+    params["AR_DS_LN/gamma"] = rng.uniform(0.7, 1.3, Dd)
+    params["AR_DS_LN/beta"] = rng.randn(Dd) * 0.1
+    _crnn_params(rng, params, Cc, u)
+    for d in ("forward", "backward"):
+        params["CTC_BIGRU/%s/kernel" % d] = rng.randn(2 * u, 3 * u) * 0.4
+        params["CTC_BIGRU/%s/recurrent_kernel" % d] = rng.randn(u, 3 * u) * 0.4
+        params["CTC_BIGRU/%s/bias" % d] = rng.randn(6 * u) * 0.1
+    params["CTC_BIGRU_LN/gamma"] = rng.uniform(0.7, 1.3, 2 * u)
+    params["CTC_BIGRU_LN/beta"] = rng.randn(2 * u) * 0.1
+    params["CTC_DS/kernel"] = rng.randn(2 * u, u) * 0.4
+    params["CTC_DS/bias"] = rng.randn(u) * 0.1
+    params["CTC_DS_LN/gamma"] = rng.uniform(0.7, 1.3, u)
+    params["CTC_DS_LN/beta"] = rng.randn(u) * 0.1
+    params["ctc_pred/kernel"] = rng.randn(u, C) * 0.6
+    params["ctc_pred/bias"] = rng.randn(C) * 0.1
+    x = rng.randn(B, S, Cc)
+    onehot = np.eye(n)[rng.randint(0, n, B)]
+    labels = np.array([[1, 1, 4], [0, 7, 0], [5, 0, 0]], np.float64)          # a repeated label, ragged lengths
+    in_len, lab_len = np.array([[7], [6], [4]]), np.array([[3], [2], [1]])
+    # the differentiable CTC is the oracle's CTC
+    pr = torch.softmax(torch.as_tensor(rng.randn(B, S, C)), -1)
+    a = TO.ctc_loss_autograd(pr, labels, in_len, lab_len)
+    b = O.ctc_batch_cost(torch.as_tensor(labels), pr, torch.as_tensor(in_len), torch.as_tensor(lab_len)).reshape(-1)
+    assert torch.allclose(a, b, rtol=1e-10, atol=1e-10)
+    kw = dict(disc_enable=True, metric_loss="arcface", margin=0.3, w_accent=0.01, w_disc=0.6)
+    pool = dict(mto="gvlad", vlad_clusters=K, ghost_clusters=G, train_ctc=True, ctc=(labels, in_len, lab_len), w_ctc=0.3)
+    _, state, losses, grads = TO.train_step(params, {}, x, onehot, lr=0.01, iterations=0, pool=pool, **kw)
+    assert set(TO.CTC_KEYS) | set(TO.CRNN_KEYS) <= set(grads) and losses["loss_ctc"] > 0
+
+    def loss_of(pp):
+        t = {k: torch.as_tensor(v) for k, v in pp.items()}
+        return float(TO.pooled_head_loss(t, torch.as_tensor(x), torch.as_tensor(onehot), **pool, **kw)[0])
+    for k in TO.CTC_KEYS + ["CRNN/forward/recurrent_kernel", "CRNN_LN/gamma", "CNN_LIN/kernel"]:
+        g = grads[k]
+        for _ in range(3):
+            i = tuple(rng.randint(0, s_) for s_ in g.shape)
+            h = 1e-6
+            pp, pm = {q: v.copy() for q, v in params.items()}, {q: v.copy() for q, v in params.items()}
+            pp[k][i] += h; pm[k][i] -= h
+            fd = (loss_of(pp) - loss_of(pm)) / (2 * h)
+            assert abs(fd - g[i]) <= 2e-6 * max(1.0, abs(fd)) + 2e-8, (k, i, fd, g[i])
