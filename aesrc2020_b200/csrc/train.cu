@@ -11,6 +11,7 @@
 //                         ArcFace / Dense softmax / Circle-Loss): per-sample losses and d loss / d logits, d loss / d cos
 //   sar_adam_fwd          Keras Adam update (+ l2 regulariser gradient, + unit_norm constraint helper)
 //   sar_gru_gate_fwd/bwd  one time step of CuDNNGRU in training mode (gates kept) and its backward (fourth slice: CNN_LIN, CRNN)
+//   sar_conv2d_bwd_data / _bwd_weight, sar_maxpool2d_bwd, sar_axpy_fwd   the ResNet's backward (sixth slice; correctness-first fp32)
 //   sar_vlad_train_fwd/bwd  NetVLAD / GhostVLAD pooling in training mode: soft assignments kept, gradients of the centers and of
 //                         the assignment scores (second slice: the pooling layer is trained together with the head)
 //
@@ -462,6 +463,114 @@ __global__ void gru_gate_bwd_kernel(const float* __restrict__ g_out, const float
   }
 }
 
+// ------------------------------------------------------------------ convolution / pooling backward (sixth slice: the ResNet)
+// Correctness-first fp32 kernels for NHWC maps with HWIO kernels and TF-SAME leading pads (pad_t, pad_l), any stride.
+// d loss / d x[b,h,w,ci] = sum_{kh,kw,co} dy[b,ho,wo,co] w[kh,kw,ci,co] over the (kh,kw) with h = ho*stride + kh - pad_t (same in w).
+// One thread per dx element, the taps and output channels walked in a fixed order.
+__global__ void conv2d_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx, int B, int H, int W,
+                                       int Cin, int Ho, int Wo, int Cout, int kh, int kw, int stride, int pad_t, int pad_l, float beta) {
+  pdl_wait();
+  pdl_trigger();
+  const long long n = (long long)B * H * W * Cin;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Cin);
+    long long r = i / Cin;
+    const int x_ = (int)(r % W); r /= W;
+    const int y_ = (int)(r % H);
+    const int b = (int)(r / H);
+    float acc = 0.f;
+    for (int a = 0; a < kh; ++a) {
+      const int hn = y_ + pad_t - a;
+      if (hn < 0 || hn % stride) continue;
+      const int ho = hn / stride;
+      if (ho >= Ho) continue;
+      for (int c = 0; c < kw; ++c) {
+        const int wn = x_ + pad_l - c;
+        if (wn < 0 || wn % stride) continue;
+        const int wo = wn / stride;
+        if (wo >= Wo) continue;
+        const float* g = dy + (((size_t)b * Ho + ho) * Wo + wo) * Cout;
+        const float* wr = w + ((size_t)(a * kw + c) * Cin + ci) * Cout;
+        for (int co = 0; co < Cout; ++co) acc = fmaf(__ldg(g + co), __ldg(wr + co), acc);
+      }
+    }
+    dx[i] = acc + (beta != 0.f ? beta * dx[i] : 0.f);
+  }
+}
+// d loss / d w[kh,kw,ci,co] = sum_{b,ho,wo} x[b, ho*stride+kh-pad_t, wo*stride+kw-pad_l, ci] dy[b,ho,wo,co]: the output positions are
+// split into gridDim.y chunks, chunk z writes its partial sums to part[z][kh*kw*Cin*Cout] (summed by sar_colsum_fwd: fixed order).
+__global__ void conv2d_bwd_weight_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ part, int B, int H,
+                                         int W, int Cin, int Ho, int Wo, int Cout, int kh, int kw, int stride, int pad_t, int pad_l) {
+  pdl_wait();
+  pdl_trigger();
+  const long long nw = (long long)kh * kw * Cin * Cout;
+  const long long npos = (long long)B * Ho * Wo;
+  const long long per = (npos + gridDim.y - 1) / gridDim.y;
+  const long long p0 = blockIdx.y * per, p1 = (p0 + per < npos) ? p0 + per : npos;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nw; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Cout);
+    long long r = i / Cout;
+    const int ci = (int)(r % Cin); r /= Cin;
+    const int c = (int)(r % kw);
+    const int a = (int)(r / kw);
+    float acc = 0.f;
+    for (long long q = p0; q < p1; ++q) {
+      const int wo = (int)(q % Wo);
+      const long long t = q / Wo;
+      const int ho = (int)(t % Ho);
+      const int b = (int)(t / Ho);
+      const int hi = ho * stride + a - pad_t, wi = wo * stride + c - pad_l;
+      if (hi < 0 || hi >= H || wi < 0 || wi >= W) continue;
+      acc = fmaf(__ldg(x + (((size_t)b * H + hi) * W + wi) * Cin + ci), __ldg(dy + (size_t)q * Cout + co), acc);
+    }
+    part[(size_t)blockIdx.y * nw + i] = acc;
+  }
+}
+// MaxPooling2D backward: one thread per INPUT element; it collects dy of every window whose (first) maximum it is.
+__global__ void maxpool2d_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, int B, int H, int W,
+                                     int C, int Ho, int Wo, int k, int stride, int pad_t, int pad_l) {
+  pdl_wait();
+  pdl_trigger();
+  const long long n = (long long)B * H * W * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % C);
+    long long r = i / C;
+    const int x_ = (int)(r % W); r /= W;
+    const int y_ = (int)(r % H);
+    const int b = (int)(r / H);
+    const float me = x[i];
+    float acc = 0.f;
+    for (int ho = 0; ho < Ho; ++ho) {
+      const int h0 = ho * stride - pad_t;
+      if (y_ < h0 || y_ >= h0 + k) continue;
+      for (int wo = 0; wo < Wo; ++wo) {
+        const int w0 = wo * stride - pad_l;
+        if (x_ < w0 || x_ >= w0 + k) continue;
+        // am I the first maximum of this window (row-major scan, padded cells never win)?
+        bool win = true;
+        for (int a = 0; a < k && win; ++a) {
+          const int hi = h0 + a;
+          if (hi < 0 || hi >= H) continue;
+          for (int c = 0; c < k; ++c) {
+            const int wi = w0 + c;
+            if (wi < 0 || wi >= W) continue;
+            const float v = __ldg(x + (((size_t)b * H + hi) * W + wi) * C + ch);
+            const bool before = (hi < y_) || (hi == y_ && wi < x_);
+            if (v > me || (before && v == me)) { win = false; break; }
+          }
+        }
+        if (win) acc += __ldg(dy + (((size_t)b * Ho + ho) * Wo + wo) * C + ch);
+      }
+    }
+    dx[i] = acc;
+  }
+}
+__global__ void axpy_kernel(const float* __restrict__ x, float* __restrict__ y, float alpha, long long n) {
+  pdl_wait();
+  pdl_trigger();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] = fmaf(alpha, x[i], y[i]);
+}
+
 }  // namespace sar
 
 extern "C" {
@@ -533,6 +642,45 @@ int sar_gru_gate_bwd(const float* g_out, const float* dh_rec, const float* z, co
   launch_k(gru_gate_bwd_kernel, dim3(blocks_for((long long)B * u, 256)), dim3(256), 0, (cudaStream_t)stream, g_out, dh_rec, z, r, hh, hph,
            h_prev, d_xp, d_hu, dh_prev, B, S, u, t, out_stride, out_off);
   return check_launch("sar_gru_gate_bwd");
+}
+
+int sar_conv2d_bwd_data(const float* dy, const float* w_hwio, float* dx, int B, int H, int W, int Cin, int Ho, int Wo, int Cout, int kh,
+                        int kw, int stride, int pad_t, int pad_l, float beta, void* stream) {
+  using namespace sar;
+  SAR_REQUIRE(dy && w_hwio && dx, SAR_ERR_BAD_ARG, "sar_conv2d_bwd_data: null pointer");
+  SAR_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Ho > 0 && Wo > 0 && Cout > 0 && kh > 0 && kw > 0 && stride > 0 && pad_t >= 0 && pad_l >= 0,
+              SAR_ERR_BAD_ARG, "sar_conv2d_bwd_data: bad dimension");
+  launch_k(conv2d_bwd_data_kernel, dim3(blocks_for((long long)B * H * W * Cin, 256, 1 << 16)), dim3(256), 0, (cudaStream_t)stream, dy, w_hwio, dx,
+           B, H, W, Cin, Ho, Wo, Cout, kh, kw, stride, pad_t, pad_l, beta);
+  return check_launch("sar_conv2d_bwd_data");
+}
+
+int sar_conv2d_bwd_weight(const float* x, const float* dy, float* partial, int chunks, int B, int H, int W, int Cin, int Ho, int Wo, int Cout,
+                          int kh, int kw, int stride, int pad_t, int pad_l, void* stream) {
+  using namespace sar;
+  SAR_REQUIRE(x && dy && partial, SAR_ERR_BAD_ARG, "sar_conv2d_bwd_weight: null pointer");
+  SAR_REQUIRE(chunks > 0 && chunks <= 65535 && B > 0 && H > 0 && W > 0 && Cin > 0 && Ho > 0 && Wo > 0 && Cout > 0 && kh > 0 && kw > 0 && stride > 0,
+              SAR_ERR_BAD_ARG, "sar_conv2d_bwd_weight: bad dimension");
+  launch_k(conv2d_bwd_weight_kernel, dim3(blocks_for((long long)kh * kw * Cin * Cout, 128, 4096), chunks), dim3(128), 0, (cudaStream_t)stream, x, dy,
+           partial, B, H, W, Cin, Ho, Wo, Cout, kh, kw, stride, pad_t, pad_l);
+  return check_launch("sar_conv2d_bwd_weight");
+}
+
+int sar_maxpool2d_bwd(const float* x, const float* dy, float* dx, int B, int H, int W, int C, int Ho, int Wo, int k, int stride, int pad_t,
+                      int pad_l, void* stream) {
+  using namespace sar;
+  SAR_REQUIRE(x && dy && dx && B > 0 && H > 0 && W > 0 && C > 0 && Ho > 0 && Wo > 0 && k > 0 && stride > 0, SAR_ERR_BAD_ARG,
+              "sar_maxpool2d_bwd: bad argument");
+  launch_k(maxpool2d_bwd_kernel, dim3(blocks_for((long long)B * H * W * C, 256, 1 << 16)), dim3(256), 0, (cudaStream_t)stream, x, dy, dx, B, H, W, C,
+           Ho, Wo, k, stride, pad_t, pad_l);
+  return check_launch("sar_maxpool2d_bwd");
+}
+
+int sar_axpy_fwd(const float* x, float* y, float alpha, long long n, void* stream) {
+  using namespace sar;
+  SAR_REQUIRE(x && y && n > 0, SAR_ERR_BAD_ARG, "sar_axpy_fwd: bad argument");
+  launch_k(axpy_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, (cudaStream_t)stream, x, y, alpha, n);
+  return check_launch("sar_axpy_fwd");
 }
 
 int sar_colsum_fwd(const float* g, float* out, int rows, int C, void* stream) {

@@ -27,7 +27,9 @@ mode as one GEMM + `sar_gru_gate_fwd` per time step (gates kept) and is differen
 Fifth slice, `HeadTrainer(model, train_ctc=True)`: the CTC branch -- CTC_BIGRU -> CTC_BIGRU_LN -> CTC_DS -> CTC_DS_LN -> ctc_pred ->
 K.ctc_batch_cost (model.py:261-269, 62-71; `sar_ctc_grad_fwd`: alpha-beta recursion, gradient through the double normalisation) --
 is trained together with the accent branch, their gradients joining at CRNN_LN: multi-task training of everything above the ResNet.
-Not built yet: gradients of the ResNet convolutions (stem, residual blocks), i.e. end-to-end training.
+Sixth slice, `HeadTrainer(model, train_resnet=True[, train_ctc=True])`: the ResNet as well (training_resnet.py: training-mode
+BatchNormalization, convolution / max-pool backward) -- the whole model trains end to end, as `fit_generator` does in the
+reference (train.py:38-44).  This last slice is correctness-first fp32 CUDA-core code, not yet the tensor-core backward.
 """
 from __future__ import annotations
 
@@ -262,7 +264,7 @@ class HeadTrainer:
     """Fine-tunes the accent head of a SARModel on the device (module docstring)."""
 
     def __init__(self, model, lr: float = 0.01, group=None, train_pool: bool = False, train_ds: bool = False,
-                 train_crnn: bool = False, train_ctc: bool = False):
+                 train_crnn: bool = False, train_ctc: bool = False, train_resnet: bool = False):
         """train_pool: also train the NetVLAD / GhostVLAD pooling layer (assignment Conv2D + centers, model.py:82-109):
         the frozen encoder then ends at AR_DS_LN and the step differentiates vlad() as well (second slice).
         train_ds (implies train_pool): also train AR_DS (Dense + tanh, l2 regularisers) and AR_DS_LN (model.py:275-276):
@@ -272,13 +274,16 @@ class HeadTrainer:
         frozen encoder is the ResNet alone (fourth slice).
         train_ctc (implies train_crnn; needs ctc_enable): the CTC branch as well -- CTC_BIGRU -> CTC_BIGRU_LN -> CTC_DS (Dense +
         tanh) -> CTC_DS_LN -> ctc_pred -> K.ctc_batch_cost (model.py:261-269, 62-71), its gradient joining the accent
-        branch's at CRNN_LN: multi-task training of everything above the ResNet (fifth slice)."""
+        branch's at CRNN_LN: multi-task training of everything above the ResNet (fifth slice).
+        train_resnet (implies train_crnn): the ResNet too, in training mode (batch-statistic BatchNormalization) with its
+        backward (training_resnet.ResNetTrainer) -- nothing is frozen: the whole model trains end to end (sixth slice;
+        with train_ctc: the reference's full multi-task fit)."""
         cfg = model.config
         if not cfg.ar_enable:
             raise ValueError("HeadTrainer needs ar_enable=True")
         if train_ctc and not cfg.ctc_enable:
             raise ValueError("train_ctc needs a model built with ctc_enable=True")
-        train_crnn = bool(train_crnn or train_ctc)
+        train_crnn = bool(train_crnn or train_ctc or train_resnet)
         train_ds = bool(train_ds or train_crnn)
         train_pool = bool(train_pool or train_ds)
         if train_pool and cfg.mto not in ("vlad", "gvlad"):
@@ -288,6 +293,7 @@ class HeadTrainer:
         self.train_ds = bool(train_ds)
         self.train_crnn = bool(train_crnn)
         self.train_ctc = bool(train_ctc)
+        self.train_resnet = bool(train_resnet)
         self.iterations = 0
         self.head_kind = cfg.metric_loss if cfg.disc_enable else None
         self.disc_key = None
@@ -313,6 +319,13 @@ class HeadTrainer:
             self.keys += self.crnn_keys
             # DS: l2(1e-4) on kernel and bias; BIGRU: kernel_regularizer + bias_regularizer, none on the recurrent kernel (model.py:35-50)
             self.l2 |= {"CNN_LIN/kernel", "CNN_LIN/bias"} | {k for k in gk if not k.endswith("recurrent_kernel")}
+        self.resnet_keys: List[str] = []
+        res_stats: List[str] = []
+        if self.train_resnet:
+            from .training_resnet import ResNetTrainer
+            self.resnet_keys, res_l2, res_stats = ResNetTrainer.param_keys(cfg)
+            self.keys += self.resnet_keys
+            self.l2 |= set(res_l2)
         self.ctc_keys: List[str] = []
         if self.train_ctc:
             gk = ["CTC_BIGRU/%s/%s" % (d, w) for d in ("forward", "backward") for w in ("kernel", "recurrent_kernel", "bias")]
@@ -326,13 +339,20 @@ class HeadTrainer:
         dev = torch.device(model.device)
         put = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
         bn_stats = [b + s for b in ("AR_BN1", "AR_BN2") for s in ("/moving_mean", "/moving_variance")]
-        self.p: Dict[str, torch.Tensor] = {k: put(model.weights[k]) for k in self.keys + bn_stats}
+        self.p: Dict[str, torch.Tensor] = {k: put(model.weights[k]) for k in self.keys + bn_stats + res_stats}
+        self.resnet_tr = None
+        if self.train_resnet:
+            from .training_resnet import ResNetTrainer
+            self.resnet_tr = ResNetTrainer(cfg, self.p)
         self.m = {k: torch.zeros_like(self.p[k]) for k in self.keys}
         self.v = {k: torch.zeros_like(self.p[k]) for k in self.keys}
         self.last_grads: Dict[str, torch.Tensor] = {}
 
     # ---- frozen encoder: x_data -> integ (B, K*D | D | 2u), or (train_pool) the descriptors (B,S,D) in front of vlad()
     def encode(self, x) -> torch.Tensor:
+        if self.train_resnet:                     # nothing is frozen: the step starts from the features themselves
+            xd = self.model._as_dict(x)
+            return self.model._to_device("x_data", xd["x_data"]).contiguous()
         out = self.model.forward_device(x, want_intermediates=True, graph=False)
         if self.train_crnn:                       # CNN2SEQ (model.py:252): the ResNet's (B,H,W,C) map as (B, S, Cc) rows
             plan = self.cfg.plan()
@@ -348,6 +368,11 @@ class HeadTrainer:
         g_ctc: Dict[str, torch.Tensor] = {}
         g_crnn_ctc = loss_ctc = None
         pool = ds = rn = None
+        res_shape = None
+        if self.train_resnet:                    # ResNet in training mode; CNN2SEQ (model.py:252): (B,H,W,C) -> (B, H*W, C)
+            fmap = self.resnet_tr.forward(integ)
+            res_shape = fmap.shape
+            integ = fmap.view(B, res_shape[1] * res_shape[2], res_shape[3])
         if self.train_crnn:                      # CNN_LIN -> CNN_LIN_LN -> CRNN -> CRNN_LN on the frozen ResNet's sequence (B,S,Cc)
             _, Sr, Cr = integ.shape
             x0 = integ.view(B * Sr, Cr)
@@ -473,6 +498,9 @@ class HeadTrainer:
                     g_pl, gzx1 = ln_train_bwd(y_lin, p["CNN_LIN_LN/gamma"], g_zlin, tanh_in=True)
                     g["CNN_LIN_LN/gamma"], g["CNN_LIN_LN/beta"] = colsum(gzx1), colsum(g_zlin)
                     g["CNN_LIN/kernel"], g["CNN_LIN/bias"] = gemm(x0, g_pl, ta=True), colsum(g_pl)
+                    if res_shape is not None:    # ... and through the whole ResNet
+                        g_x0 = gemm(g_pl, p["CNN_LIN/kernel"], tb=True)
+                        g.update(self.resnet_tr.backward(g_x0.view(res_shape)))
             else:
                 g_scores, gc_part = vlad_train_bwd(feat, A, p[kc_], gR, asum, K, G)
             g[kw_] = gemm(feat.view(B * S, D), g_scores.view(B * S, K + G), ta=True).view_as(p[kw_])

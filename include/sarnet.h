@@ -311,6 +311,20 @@ int sar_bn_train_bwd(const float* x, const float* dy, const float* gamma, const 
 int sar_bias_act_fwd(const float* x, const float* bias, float* y, long long rows, int C, int act, void* stream);
 int sar_relu_bwd(const float* g, const float* h, float* out, long long n, void* stream);
 int sar_colsum_fwd(const float* g, float* out, int rows, int C, void* stream);
+/* Backward of Conv2D / MaxPooling2D on NHWC fp32 maps (resnet.py in training mode; HWIO kernels, TF-SAME leading pads, any stride):
+ *   sar_conv2d_bwd_data:   dx (B,H,W,Cin) = beta * dx + d loss / d x from dy (B,Ho,Wo,Cout)
+ *   sar_conv2d_bwd_weight: partial (chunks, kh*kw*Cin*Cout): the output positions split into `chunks` ranges, one partial
+ *                          d loss / d w per range (sum them with sar_colsum_fwd: deterministic order)
+ *   sar_maxpool2d_bwd:     dx = dy routed to the first maximum of every window (padded cells never win)
+ *   sar_axpy_fwd:          y += alpha * x  (gradient accumulation where two paths meet: Add(), resnet.py:89)
+ * Correctness-first CUDA-core kernels (fixed summation orders), not tensor-core code. */
+int sar_conv2d_bwd_data(const float* dy, const float* w_hwio, float* dx, int B, int H, int W, int Cin, int Ho, int Wo, int Cout, int kh,
+                        int kw, int stride, int pad_t, int pad_l, float beta, void* stream);
+int sar_conv2d_bwd_weight(const float* x, const float* dy, float* partial, int chunks, int B, int H, int W, int Cin, int Ho, int Wo, int Cout,
+                          int kh, int kw, int stride, int pad_t, int pad_l, void* stream);
+int sar_maxpool2d_bwd(const float* x, const float* dy, float* dx, int B, int H, int W, int C, int Ho, int Wo, int k, int stride, int pad_t,
+                      int pad_l, void* stream);
+int sar_axpy_fwd(const float* x, float* y, float alpha, long long n, void* stream);
 /* One time step of one direction of CuDNNGRU in TRAINING mode (model.py:44-50; reset_after, gates z|r|h) and its backward.
  * xp (B,S,3u) = x W + b_i (batch-major), hu (B,3u) = h_prev U, b_r (3u); z, r, hh, hph (B,u) are this step's saved gates
  * (hph = hu_h + b_r_h), h_new (B,u), out (B,S,out_stride) receives h_new at [b, t, out_off + j] (NULL: not stored).

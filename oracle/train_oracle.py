@@ -106,6 +106,21 @@ CTC_KEYS = CTC_GRU_KEYS + ["CTC_BIGRU_LN/gamma", "CTC_BIGRU_LN/beta", "CTC_DS/ke
 CTC_L2_KEYS = ["CTC_DS/kernel", "CTC_DS/bias", "ctc_pred/kernel", "ctc_pred/bias"] + [k for k in CTC_GRU_KEYS if not k.endswith("recurrent_kernel")]
 
 
+def resnet_train(x, p, res_type: str, filters: int):
+    """O.resnet (resnet.py:170-201) in TRAINING mode: every BatchNormalization of the ResNet normalises with the batch
+    statistics of its input (biased variance over batch and positions, eps 1e-3) -- the only difference to inference."""
+    def bn_batch(t, pp, prefix):
+        mean = t.mean(dim=(0, 1, 2))
+        var = ((t - mean) ** 2).mean(dim=(0, 1, 2))
+        return (t - mean) / torch.sqrt(var + BN_EPS) * pp[prefix + "/gamma"] + pp[prefix + "/beta"]
+    keep = O.batchnorm
+    O.batchnorm = bn_batch
+    try:
+        return O.resnet(x, p, res_type, filters)
+    finally:
+        O.batchnorm = keep
+
+
 def ctc_loss_autograd(probs, labels, in_len, lab_len):
     """K.ctc_batch_cost (O.ctc_batch_cost: q = softmax(log(p + 1e-7)), blank = C-1) in a form autograd can differentiate:
     torch's own CTC on log q (O.ctc_batch_cost's explicit lattice takes logsumexp over all -inf states, whose gradient is
@@ -120,11 +135,17 @@ def ctc_loss_autograd(probs, labels, in_len, lab_len):
 
 def pooled_head_loss(p: Dict[str, torch.Tensor], feat: torch.Tensor, onehot: torch.Tensor, *, mto: str, vlad_clusters: int,
                      ghost_clusters: int, train_ds: bool = False, train_crnn: bool = False, train_ctc: bool = False, ctc=None,
-                     w_ctc: float = 0.0, **kw):
+                     w_ctc: float = 0.0, train_resnet=None, extra_keys=(), extra_l2=(), **kw):
     """feat (B,S,D) = AR_DS_LN output (frozen encoder) -> vlad() -> the head of head_loss, with the pooling layer's
     regularisers added.  train_ds: feat is the CRNN_LN output (B,S,2u) instead and AR_DS (Dense + tanh, l2 regularisers on
     kernel and bias) -> AR_DS_LN run in front of vlad() (model.py:275-276)."""
     reg_ds = 0.0
+    reg_res = 0.0
+    if train_resnet:         # dict(res_type=, filters=): feat is x_data (B,T,80,1); the ResNet trains too (sixth slice), then CNN2SEQ
+        fmap = resnet_train(feat, p, train_resnet["res_type"], train_resnet["filters"])
+        feat = fmap.reshape(fmap.shape[0], fmap.shape[1] * fmap.shape[2], fmap.shape[3])
+        reg_res = sum(L2_REG * (p[k] ** 2).sum() for k in extra_l2)       # l2(1e-4) on every conv kernel (resnet.py:36,56,86,116)
+        train_crnn = True
     train_crnn = train_crnn or train_ctc
     if train_crnn:           # feat is the frozen ResNet's sequence (B,S,Cc): model.py:252-256 in front of the accent branch
         feat = O.layernorm(O.dense(feat, p, "CNN_LIN", "tanh"), p, "CNN_LIN_LN")
@@ -143,7 +164,7 @@ def pooled_head_loss(p: Dict[str, torch.Tensor], feat: torch.Tensor, onehot: tor
         reg_ds = reg_ds + L2_REG * ((p["AR_DS/kernel"] ** 2).sum() + (p["AR_DS/bias"] ** 2).sum())
     integ = O.integration(feat, p, feat.shape[-1], mto, vlad_clusters, ghost_clusters)       # model.py:118-139
     total, parts = head_loss(p, integ, onehot, **kw)
-    reg = sum(L2_REG * (p[k] ** 2).sum() for k in pool_l2_keys(mto)) + reg_ds
+    reg = sum(L2_REG * (p[k] ** 2).sum() for k in pool_l2_keys(mto)) + reg_ds + reg_res
     parts["reg"] = parts["reg"] + reg
     parts["integration"] = integ
     if ctc_term is not None:
@@ -170,8 +191,8 @@ def train_step(params: Dict[str, np.ndarray], state: Dict[str, np.ndarray], inte
     vlad() and the pooling layer's weights are trained too (pooled_head_loss).
     Returns (new params incl. the BN moving statistics, new state, losses, gradients)."""
     keys = trainable_keys(disc_enable, metric_loss) + (pool_keys(pool["mto"]) if pool else []) + \
-        (DS_KEYS if (pool and (pool.get("train_ds") or pool.get("train_crnn") or pool.get("train_ctc"))) else []) + \
-        (CRNN_KEYS if (pool and (pool.get("train_crnn") or pool.get("train_ctc"))) else []) + (CTC_KEYS if (pool and pool.get("train_ctc")) else [])
+        (DS_KEYS if (pool and (pool.get("train_ds") or pool.get("train_crnn") or pool.get("train_ctc") or pool.get("train_resnet"))) else []) + \
+        (CRNN_KEYS if (pool and (pool.get("train_crnn") or pool.get("train_ctc") or pool.get("train_resnet"))) else []) + list(pool.get("extra_keys", ()) if pool else ()) + (CTC_KEYS if (pool and pool.get("train_ctc")) else [])
     p = {k: torch.tensor(np.asarray(v, np.float64), requires_grad=(k in keys)) for k, v in params.items()}
     kw = dict(disc_enable=disc_enable, metric_loss=metric_loss, margin=margin, w_accent=w_accent, w_disc=w_disc)
     x_in, y_in = torch.as_tensor(np.asarray(integ, np.float64)), torch.as_tensor(np.asarray(onehot, np.float64))

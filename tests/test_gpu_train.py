@@ -511,3 +511,123 @@ def test_train_on_batch_fifth_slice_lowers_both_losses(cuda_device):
     tr.sync_to_model()
     outs = model.predict(x, batch_size=12)
     assert all(np.all(np.isfinite(o)) for o in outs)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,stride", [(2, 9, 8, 5, 7, 3, 1), (2, 9, 8, 5, 7, 3, 2), (3, 10, 7, 4, 6, 3, 2), (2, 8, 6, 8, 16, 1, 2),
+                                                     (2, 20, 16, 1, 6, 7, 2), (1, 5, 4, 32, 32, 3, 1)])
+def test_conv_backward_kernels_match_autograd(cuda_device, B, H, W, Cin, Cout, k, stride):
+    """sar_conv2d_bwd_data / sar_conv2d_bwd_weight vs float64 autograd of the oracle's TF-SAME (k > 1) / VALID (1x1 shortcut)
+    Conv2D: strides 1 and 2, even and odd sizes (asymmetric SAME pads), the 7x7 stem, accumulation into dx (beta = 1)."""
+    from aesrc2020_b200 import training_resnet as TR
+    from aesrc2020_b200.config import ConvSpec, same_pad
+    rng = np.random.RandomState(B + H * 3 + k)
+    x = rng.randn(B, H, W, Cin).astype(np.float32)
+    w = (rng.randn(k, k, Cin, Cout) * 0.3).astype(np.float32)
+    pad = "same" if k > 1 else "valid"
+    if pad == "same":
+        Ho, pt, _ = same_pad(H, k, stride)
+        Wo, pl, _ = same_pad(W, k, stride)
+    else:
+        Ho, Wo, pt, pl = (H - 1) // stride + 1, (W - 1) // stride + 1, 0, 0
+    tx, tw = torch.tensor(x.astype(np.float64), requires_grad=True), torch.tensor(w.astype(np.float64), requires_grad=True)
+    y = O.conv2d(tx, tw, None, stride, pad)
+    assert tuple(y.shape) == (B, Ho, Wo, Cout)
+    gy = rng.randn(B, Ho, Wo, Cout).astype(np.float32)
+    (y * torch.tensor(gy.astype(np.float64))).sum().backward()
+    spec = ConvSpec(name="t", kh=k, kw=k, stride=stride, cin=Cin, cout=Cout, hin=H, win=W, hout=Ho, wout=Wo, pad_t=pt, pad_l=pl,
+                    pre_bn=None, post_bn=None)
+    dx = TR.conv_bwd_data(spec, dev(gy), dev(w), B)
+    assert norm_err(dx, tx.grad) < 1e-5
+    base = rng.randn(B, H, W, Cin).astype(np.float32)
+    dx2 = TR.conv_bwd_data(spec, dev(gy), dev(w), B, dx=dev(base), beta=1.0)
+    assert norm_err(dx2, tx.grad + torch.tensor(base.astype(np.float64))) < 1e-5
+    dw = TR.conv_bwd_weight(spec, dev(x), dev(gy), B)
+    assert norm_err(dw, tw.grad) < 1e-5
+
+
+@pytest.mark.parametrize("B,H,W,C", [(2, 9, 8, 5), (2, 10, 7, 3), (1, 50, 40, 8)])
+def test_maxpool_backward_matches_autograd(cuda_device, B, H, W, C):
+    from aesrc2020_b200 import training_resnet as TR, ops
+    from aesrc2020_b200.config import same_pad
+    rng = np.random.RandomState(H)
+    x = rng.randn(B, H, W, C).astype(np.float32)
+    Ho, pt, _ = same_pad(H, 3, 2)
+    Wo, pl, _ = same_pad(W, 3, 2)
+    tx = torch.tensor(x.astype(np.float64), requires_grad=True)
+    y = O.maxpool_same(tx)
+    gy = rng.randn(B, Ho, Wo, C).astype(np.float32)
+    (y * torch.tensor(gy.astype(np.float64))).sum().backward()
+    dx = TR.maxpool_bwd(dev(x), dev(gy), 3, 2, pt, pl)
+    assert norm_err(dx, tx.grad) < 1e-6
+
+
+def test_whole_model_training_step_matches_the_oracle(cuda_device):
+    """HeadTrainer(train_resnet=True): NOTHING frozen -- ResNet (training-mode BN) + CNN_LIN + CRNN + accent branch, one
+    optimisation step vs the float64 autograd oracle: every gradient of the model and the accent / margin losses."""
+    import warnings
+    from aesrc2020_b200 import model as mdl, training as T
+    from aesrc2020_b200.training_resnet import ResNetTrainer
+    K, G = 8, 2
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model, _ = mdl.SAR_Net((100, 80, 1), ctc_enable=False, disc_enable=True, res_type="res18", res_filters=8, mto="gvlad",
+                               vlad_clusters=K, ghost_clusters=G, metric_loss="arcface", margin=0.3)
+    cfg = model.config
+    rng = np.random.RandomState(43)
+    for k in list(model.weights):                     # biases / betas away from zero
+        if k.endswith("/bias") or k.endswith("/beta"):
+            model.weights[k] = (model.weights[k] + rng.randn(*model.weights[k].shape) * 0.05).astype(np.float32)
+    params = {k: np.asarray(v, np.float32).astype(np.float64) for k, v in model.weights.items()}
+    rkeys, rl2, _ = ResNetTrainer.param_keys(cfg)
+    tr = T.HeadTrainer(model, lr=0.01, train_resnet=True)
+    assert set(rkeys) <= set(tr.keys) and tr.train_crnn
+    B = 4
+    lab = rng.randint(0, 8, B)
+    x = rng.rand(B, 100, 80, 1).astype(np.float32)
+    onehot = np.eye(8, dtype=np.float32)[lab]
+    pool = dict(mto="gvlad", vlad_clusters=K, ghost_clusters=G, train_resnet=dict(res_type="res18", filters=8),
+                extra_keys=tuple(rkeys), extra_l2=tuple(rl2))
+    l2k = set(TO.l2_keys(True, "arcface")) | set(TO.pool_l2_keys("gvlad")) | {"AR_DS/kernel", "AR_DS/bias"} | set(TO.CRNN_L2_KEYS) | set(rl2)
+    p_or, state, l_or, g_or = TO.train_step(dict(params), {}, x, onehot, lr=0.01, iterations=0, disc_enable=True,
+                                            metric_loss="arcface", margin=0.3, w_accent=tr.w_acc, w_disc=tr.w_disc, pool=pool)
+    got = tr.step_on_features(dev(x), dev(onehot))
+    assert abs(got["loss_disc"] - l_or["loss_disc"]) < 5e-4 * max(1, abs(l_or["loss_disc"]))
+    worst = {}
+    for k in tr.keys:
+        if k in ("AR_BN1/beta", "AR_EMBEDDING/bias"):
+            continue
+        want = g_or[k] - (2 * TO.L2_REG * params[k] if k in l2k else 0.0)
+        got_k = tr.last_grads[k].cpu().numpy().astype(np.float64)
+        if k.startswith("resnet/") and k.endswith("/bias"):
+            # a constant added in front of a batch-statistic BN is removed by its mean: the true gradient of EVERY conv bias
+            # of the ResNet is zero in training mode (float64: ~1e-17).  fp32 leaves rounding noise: bound it by the scale of
+            # the same convolution's kernel gradient
+            scale = float(np.max(np.abs(g_or[k[:-5] + "/kernel"])))
+            assert float(np.max(np.abs(want))) < 1e-9 * max(scale, 1.0), (k, float(np.max(np.abs(want))))
+            worst[k] = float(np.max(np.abs(got_k))) / max(scale, 1e-6) * 5.0          # passes below 1e-3 of the kernel gradient
+            continue
+        worst[k] = float(np.max(np.abs(got_k - want)) / max(np.max(np.abs(want)), 1e-6))
+    bad = {k: round(v, 5) for k, v in worst.items() if v > 5e-3}
+    assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:12]
+
+
+def test_whole_model_training_lowers_the_loss(cuda_device):
+    import warnings
+    from aesrc2020_b200 import model as mdl, training as T, utils as us
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model, _ = mdl.SAR_Net((100, 80, 1), ctc_enable=True, disc_enable=True, res_type="res18", res_filters=8, mto="gvlad",
+                               vlad_clusters=8, ghost_clusters=2, metric_loss="arcface", margin=0.3, bpe_classes=40, max_ctc_len=4)
+    x, y = us.synthetic_batch(model.config, 8, seed=7)
+    w0 = model.weights["resnet/s2b1/conv1/kernel"].copy()
+    m0 = model.weights["resnet/stem_bn/moving_mean"].copy()
+    tr = T.HeadTrainer(model, lr=0.005, train_resnet=True, train_ctc=True)      # the reference's full multi-task fit
+    hist = [tr.train_on_batch(x, y) for _ in range(15)]
+    assert hist[-1]["loss"] < 0.8 * hist[0]["loss"], [h["loss"] for h in hist]
+    tr.sync_to_model()
+    assert not np.allclose(w0, model.weights["resnet/s2b1/conv1/kernel"])
+    assert not np.allclose(m0, model.weights["resnet/stem_bn/moving_mean"])      # BN moving averages follow the batches
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        outs = model.predict(x, batch_size=8)
+    assert all(np.all(np.isfinite(o)) for o in outs)

@@ -282,3 +282,45 @@ def test_fifth_slice_ctc_branch_gradients_match_finite_differences():
             pp[k][i] += h; pm[k][i] -= h
             fd = (loss_of(pp) - loss_of(pm)) / (2 * h)
             assert abs(fd - g[i]) <= 2e-6 * max(1.0, abs(fd)) + 2e-8, (k, i, fd, g[i])
+
+
+def test_sixth_slice_resnet_training_gradients_match_finite_differences():
+    """Sixth slice: the ResNet in training mode (batch-statistic BN) under the rest of the model: autograd of the total vs
+    central differences for conv kernels / biases / BN parameters of the stem, a plain block, a strided block with its
+    projection shortcut, and the final BN."""
+    from aesrc2020_b200.config import SARConfig
+    from aesrc2020_b200 import weights as W
+    from aesrc2020_b200.training_resnet import ResNetTrainer
+    K, G, n = 4, 2, 8
+    cfg = SARConfig(input_shape=(40, 80, 1), ctc_enable=False, ar_enable=True, disc_enable=True, res_type="res18", res_filters=4,
+                    hidden_dim=6, mto="gvlad", vlad_clusters=K, ghost_clusters=G, metric_loss="arcface", margin=0.3)
+    w = W.init_weights(cfg, 3)
+    rng = np.random.RandomState(31)
+    params = {k: np.asarray(v, np.float64) for k, v in w.items()}
+    for k in params:                                  # biases / betas away from zero so that every term is exercised
+        if k.endswith("/bias") or k.endswith("/beta"):
+            params[k] = params[k] + rng.randn(*params[k].shape) * 0.1
+    rkeys, rl2, _ = ResNetTrainer.param_keys(cfg)
+    B = 3
+    x = rng.rand(B, 40, 80, 1)
+    onehot = np.eye(n)[rng.randint(0, n, B)]
+    kw = dict(disc_enable=True, metric_loss="arcface", margin=0.3, w_accent=0.01, w_disc=0.6)
+    pool = dict(mto="gvlad", vlad_clusters=K, ghost_clusters=G, train_resnet=dict(res_type="res18", filters=4),
+                extra_keys=tuple(rkeys), extra_l2=tuple(rl2))
+    _, state, losses, grads = TO.train_step(params, {}, x, onehot, lr=0.01, iterations=0, pool=pool, **kw)
+    assert set(rkeys) <= set(grads)
+
+    def loss_of(pp):
+        t = {k: torch.as_tensor(v) for k, v in pp.items()}
+        return float(TO.pooled_head_loss(t, torch.as_tensor(x), torch.as_tensor(onehot), **pool, **kw)[0])
+    probe = ["resnet/stem/kernel", "resnet/stem_bn/gamma", "resnet/s1b2/conv1/kernel", "resnet/s1b2/bn1/beta", "resnet/s2b1/conv1/kernel",
+             "resnet/s2b1/short/kernel", "resnet/s2b1/short/bias", "resnet/s4b2/conv2/bias", "resnet/final_bn/gamma", "CNN_LIN/kernel"]
+    for k in probe:
+        g = grads[k]
+        for _ in range(3):
+            i = tuple(rng.randint(0, s_) for s_ in g.shape)
+            h = 1e-6
+            pp, pm = {q: v.copy() for q, v in params.items()}, {q: v.copy() for q, v in params.items()}
+            pp[k][i] += h; pm[k][i] -= h
+            fd = (loss_of(pp) - loss_of(pm)) / (2 * h)
+            assert abs(fd - g[i]) <= 5e-6 * max(1.0, abs(fd)) + 5e-8, (k, i, fd, g[i])
