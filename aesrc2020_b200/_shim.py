@@ -69,6 +69,9 @@ SIGNATURES = {
     "sar_bn_train_bwd": (c_int, [c_fp] * 8 + [c_int, c_int, C.c_void_p]),
     "sar_bias_act_fwd": (c_int, [c_fp, c_fp, c_fp, c_ll, c_int, c_int, C.c_void_p]),
     "sar_relu_bwd": (c_int, [c_fp, c_fp, c_fp, c_ll, C.c_void_p]),
+    "sar_colsum_rows_fwd": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_fp, C.c_void_p]),
+    "sar_bn_train_rows_fwd": (c_int, [c_fp] * 8 + [c_int, c_int, C.c_float, C.c_float, c_int, c_fp, C.c_void_p]),
+    "sar_bn_train_rows_bwd": (c_int, [c_fp] * 8 + [c_int, c_int, c_int, c_fp, C.c_void_p]),
     "sar_conv2d_bwd_data": (c_int, [c_fp, c_fp, c_fp] + [c_int] * 12 + [C.c_float, C.c_void_p]),
     "sar_conv2d_bwd_weight": (c_int, [c_fp, c_fp, c_fp] + [c_int] * 13 + [C.c_void_p]),
     "sar_maxpool2d_bwd": (c_int, [c_fp, c_fp, c_fp] + [c_int] * 10 + [C.c_void_p]),

@@ -69,6 +69,51 @@ __global__ void __launch_bounds__(256) gemm_kernel(const float* __restrict__ A, 
     }
 }
 
+// Skinny GEMM, M <= 32 rows, A not transposed: the per-time-step products of the GRU (h U, d_hu U^T with M = batch) and the
+// embedding Dense at small batches.  The 64 x 64 tiles of gemm_kernel leave all but a few CTAs idle there and pay one
+// global-memory round trip per 16 k-values (2-3 us each).  Here a CTA owns 32 output columns, lane = column, the 8 warps
+// split K; every lane keeps its M accumulators in registers, A values are warp-broadcast loads, B is read coalesced
+// (tb = 0: row k across the lanes) or as one contiguous row per lane (tb = 1).  The warps' partial sums are added in warp
+// order: a fixed summation order.
+template <int MR>
+__global__ void __launch_bounds__(256) gemm_skinny_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
+                                                          int M, int N, int K, int tb, float alpha, float beta) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ float red[8][MR][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + lane;
+  const int per = (K + 7) / 8;
+  const int k0 = warp * per, k1 = min(K, k0 + per);
+  float acc[MR];
+#pragma unroll
+  for (int m = 0; m < MR; ++m) acc[m] = 0.f;
+  if (n < N) {
+    const float* bp = tb ? B + (size_t)n * K : B + n;
+    const size_t bstep = tb ? 1 : (size_t)N;
+#pragma unroll 4
+    for (int k = k0; k < k1; ++k) {
+      const float bv = __ldg(bp + (size_t)k * bstep);
+#pragma unroll
+      for (int m = 0; m < MR; ++m)
+        if (m < M) acc[m] = fmaf(__ldg(A + (size_t)m * K + k), bv, acc[m]);
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < MR; ++m) red[warp][m][lane] = acc[m];
+  __syncthreads();
+  for (int i = threadIdx.x; i < MR * 32; i += 256) {
+    const int m = i >> 5, l = i & 31, gn = blockIdx.x * 32 + l;
+    if (m < M && gn < N) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += red[w][m][l];
+      float* c = C + (size_t)m * N + gn;
+      *c = alpha * t + (beta != 0.f ? beta * *c : 0.f);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ BatchNormalization, training mode, (rows, C)
 // one thread per channel, rows walked in a fixed order (coalesced across channels)
 __global__ void bn_train_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -139,6 +184,82 @@ __global__ void colsum_kernel(const float* __restrict__ g, float* __restrict__ o
   float s = 0.f;
   for (int r = 0; r < rows; ++r) s += g[(size_t)r * C + c];
   out[c] = s;
+}
+
+// ------------------------------------------------------------------ row-parallel column reductions (maps with many rows)
+// The one-thread-per-channel kernels above walk `rows` serially: fine for the head (rows = batch), 65 % of a whole-model
+// training step once the ResNet's BatchNormalizations (rows = B*H*W up to 10^5..10^6) use them.  Here the rows are split into
+// gridDim.y chunks; a block = 32 channels x 8 row lanes; partial sums go to part[chunk][c] and are added in chunk order by
+// col_final_kernel -- still a fixed summation order, independent of scheduling.
+//   mode 0: s1 = sum a            mode 1: s1 = sum (a - mean)^2            mode 2: s1 = sum b, s2 = sum b * (a - mean) * inv
+__global__ void __launch_bounds__(256) col_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ mean,
+                                                          const float* __restrict__ inv, float* __restrict__ part1, float* __restrict__ part2,
+                                                          int rows, int C, int mode) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ float sh1[8][33], sh2[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  const int per = (rows + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
+  float s1 = 0.f, s2 = 0.f;
+  if (c < C) {
+    const float m = mode ? mean[c] : 0.f, iv = mode == 2 ? inv[c] : 0.f;
+    for (int r = r0 + ty; r < r1; r += 8) {
+      const float v = a[(size_t)r * C + c];
+      if (mode == 0) s1 += v;
+      else if (mode == 1) { const float d = v - m; s1 = fmaf(d, d, s1); }
+      else { const float d = b[(size_t)r * C + c]; s1 += d; s2 = fmaf(d, (v - m) * iv, s2); }
+    }
+  }
+  sh1[ty][tx] = s1; sh2[ty][tx] = s2;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { t1 += sh1[k][tx]; t2 += sh2[k][tx]; }
+    part1[(size_t)blockIdx.y * C + c] = t1;
+    if (mode == 2) part2[(size_t)blockIdx.y * C + c] = t2;
+  }
+}
+__global__ void col_final_kernel(const float* __restrict__ part, int nch, int C, float scale, float* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int k = 0; k < nch; ++k) s += part[(size_t)k * C + c];
+  out[c] = s * scale;
+}
+__global__ void bn_stats_finish_kernel(const float* __restrict__ mean, const float* __restrict__ var, float* __restrict__ save_invstd,
+                                       float* __restrict__ mov_mean, float* __restrict__ mov_var, int C, float eps, float momentum) {
+  pdl_wait();
+  pdl_trigger();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  save_invstd[c] = 1.0f / sqrtf(var[c] + eps);
+  if (mov_mean) mov_mean[c] = momentum * mov_mean[c] + (1.f - momentum) * mean[c];
+  if (mov_var) mov_var[c] = momentum * mov_var[c] + (1.f - momentum) * var[c];
+}
+__global__ void bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ inv,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y, long long n, int C) {
+  pdl_wait();
+  pdl_trigger();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    y[i] = (x[i] - mean[c]) * inv[c] * gamma[c] + beta[c];
+  }
+}
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ mean,
+                                    const float* __restrict__ inv, const float* __restrict__ gamma, const float* __restrict__ dgamma,
+                                    const float* __restrict__ dbeta, float* __restrict__ dx, long long n, int C, float inv_rows) {
+  pdl_wait();
+  pdl_trigger();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const float xh = (x[i] - mean[c]) * inv[c];
+    dx[i] = gamma[c] * inv[c] * (dy[i] - dbeta[c] * inv_rows - xh * dgamma[c] * inv_rows);
+  }
 }
 
 // ------------------------------------------------------------------ K.l2_normalize (eps 1e-12 under the root) and backward
@@ -497,34 +618,62 @@ __global__ void conv2d_bwd_data_kernel(const float* __restrict__ dy, const float
     dx[i] = acc + (beta != 0.f ? beta * dx[i] : 0.f);
   }
 }
-// d loss / d w[kh,kw,ci,co] = sum_{b,ho,wo} x[b, ho*stride+kh-pad_t, wo*stride+kw-pad_l, ci] dy[b,ho,wo,co]: the output positions are
-// split into gridDim.y chunks, chunk z writes its partial sums to part[z][kh*kw*Cin*Cout] (summed by sar_colsum_fwd: fixed order).
-__global__ void conv2d_bwd_weight_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ part, int B, int H,
-                                         int W, int Cin, int Ho, int Wo, int Cout, int kh, int kw, int stride, int pad_t, int pad_l) {
+// d loss / d w[kh,kw,ci,co] = sum_{b,ho,wo} x[b, ho*stride+kh-pad_t, wo*stride+kw-pad_l, ci] dy[b,ho,wo,co]: a GEMM per tap,
+// [Cin x positions] x [positions x Cout].  Block = one tap, a 32 x 32 (ci, co) tile and one of gridDim.y position chunks;
+// 32 positions at a time are staged in shared memory (the shifted x rows, zero outside the map), thread (ty, tx) owns a
+// 2 x 2 patch of the tile.  Chunk z writes its partial sums to part[z][kh*kw*Cin*Cout] (summed by sar_colsum_fwd: fixed order).
+__global__ void __launch_bounds__(256) conv2d_bwd_weight_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ part,
+                                                                int B, int H, int W, int Cin, int Ho, int Wo, int Cout, int kh, int kw,
+                                                                int stride, int pad_t, int pad_l) {
   pdl_wait();
   pdl_trigger();
+  __shared__ float xs[32][33], ds[32][33];
+  const int ct_o = (Cout + 31) / 32, ct_i = (Cin + 31) / 32;
+  int t = blockIdx.x;
+  const int co0 = (t % ct_o) * 32; t /= ct_o;
+  const int ci0 = (t % ct_i) * 32; t /= ct_i;
+  const int c = t % kw, a = t / kw;
   const long long nw = (long long)kh * kw * Cin * Cout;
   const long long npos = (long long)B * Ho * Wo;
   const long long per = (npos + gridDim.y - 1) / gridDim.y;
   const long long p0 = blockIdx.y * per, p1 = (p0 + per < npos) ? p0 + per : npos;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nw; i += (long long)gridDim.x * blockDim.x) {
-    const int co = (int)(i % Cout);
-    long long r = i / Cout;
-    const int ci = (int)(r % Cin); r /= Cin;
-    const int c = (int)(r % kw);
-    const int a = (int)(r / kw);
-    float acc = 0.f;
-    for (long long q = p0; q < p1; ++q) {
-      const int wo = (int)(q % Wo);
-      const long long t = q / Wo;
-      const int ho = (int)(t % Ho);
-      const int b = (int)(t / Ho);
-      const int hi = ho * stride + a - pad_t, wi = wo * stride + c - pad_l;
-      if (hi < 0 || hi >= H || wi < 0 || wi >= W) continue;
-      acc = fmaf(__ldg(x + (((size_t)b * H + hi) * W + wi) * Cin + ci), __ldg(dy + (size_t)q * Cout + co), acc);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int lr = threadIdx.x >> 5, lc = threadIdx.x & 31;       // loader role: row lr (+8k) of the 32-position slab, channel lc
+  float acc[2][2] = {};
+  for (long long q0 = p0; q0 < p1; q0 += 32) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = lr + 8 * k;
+      const long long q = q0 + r;
+      float xv = 0.f, dv = 0.f;
+      if (q < p1) {
+        const int wo = (int)(q % Wo);
+        const long long u = q / Wo;
+        const int ho = (int)(u % Ho);
+        const int b = (int)(u / Ho);
+        const int hi = ho * stride + a - pad_t, wi = wo * stride + c - pad_l;
+        if (hi >= 0 && hi < H && wi >= 0 && wi < W && ci0 + lc < Cin) xv = __ldg(x + (((size_t)b * H + hi) * W + wi) * Cin + ci0 + lc);
+        if (co0 + lc < Cout) dv = __ldg(dy + (size_t)q * Cout + co0 + lc);
+      }
+      xs[r][lc] = xv; ds[r][lc] = dv;
     }
-    part[(size_t)blockIdx.y * nw + i] = acc;
+    __syncthreads();
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) {
+      const float x0 = xs[r][2 * ty], x1 = xs[r][2 * ty + 1], d0 = ds[r][2 * tx], d1 = ds[r][2 * tx + 1];
+      acc[0][0] = fmaf(x0, d0, acc[0][0]); acc[0][1] = fmaf(x0, d1, acc[0][1]);
+      acc[1][0] = fmaf(x1, d0, acc[1][0]); acc[1][1] = fmaf(x1, d1, acc[1][1]);
+    }
+    __syncthreads();
   }
+  float* out = part + (size_t)blockIdx.y * nw + (size_t)(a * kw + c) * Cin * Cout;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int ci = ci0 + 2 * ty + i, co = co0 + 2 * tx + j;
+      if (ci < Cin && co < Cout) out[(size_t)ci * Cout + co] = acc[i][j];
+    }
 }
 // MaxPooling2D backward: one thread per INPUT element; it collects dy of every window whose (first) maximum it is.
 __global__ void maxpool2d_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, int B, int H, int W,
@@ -580,6 +729,13 @@ int sar_gemm_fwd(const float* A, const float* B, float* C, int M, int N, int K, 
   using namespace sar;
   SAR_REQUIRE(A && B && C, SAR_ERR_BAD_ARG, "sar_gemm_fwd: null pointer");
   SAR_REQUIRE(M > 0 && N > 0 && K > 0, SAR_ERR_BAD_ARG, "sar_gemm_fwd: non-positive dimension");
+  if (!trans_a && M <= 32 && K >= 64) {          // skinny: the GRU's per-step products, the embedding Dense at small batches
+    if (M <= 16)
+      launch_k(gemm_skinny_kernel<16>, dim3((N + 31) / 32), dim3(256), 0, (cudaStream_t)stream, A, B, C, M, N, K, trans_b ? 1 : 0, alpha, beta);
+    else
+      launch_k(gemm_skinny_kernel<32>, dim3((N + 31) / 32), dim3(256), 0, (cudaStream_t)stream, A, B, C, M, N, K, trans_b ? 1 : 0, alpha, beta);
+    return check_launch("sar_gemm_fwd(skinny)");
+  }
   launch_k(gemm_kernel, dim3((N + TG - 1) / TG, (M + TG - 1) / TG), dim3(256), 0, (cudaStream_t)stream, A, B, C, M, N, K, trans_a ? 1 : 0,
            trans_b ? 1 : 0, alpha, beta);
   return check_launch("sar_gemm_fwd");
@@ -603,6 +759,54 @@ int sar_bn_train_bwd(const float* x, const float* dy, const float* gamma, const 
   launch_k(bn_train_bwd_kernel, dim3((C + 127) / 128), dim3(128), 0, (cudaStream_t)stream, x, dy, gamma, save_mean, save_invstd, dx,
            dgamma, dbeta, rows, C);
   return check_launch("sar_bn_train_bwd");
+}
+
+// Row-parallel forms of sar_colsum_fwd / sar_bn_train_fwd / sar_bn_train_bwd for maps with many rows (the ResNet in training
+// mode): `nch` row chunks, `ws` = caller-owned scratch of (2 * nch + 2) * C floats.  Same results up to fp32 summation order
+// (fixed, chunk by chunk).
+int sar_colsum_rows_fwd(const float* g, float* out, int rows, int C, int nch, float* ws, void* stream) {
+  using namespace sar;
+  SAR_REQUIRE(g && out && ws && rows > 0 && C > 0 && nch > 0 && nch <= 65535, SAR_ERR_BAD_ARG, "sar_colsum_rows_fwd: bad argument");
+  launch_k(col_partial_kernel, dim3((C + 31) / 32, nch), dim3(256), 0, (cudaStream_t)stream, g, (const float*)nullptr, (const float*)nullptr,
+           (const float*)nullptr, ws, (float*)nullptr, rows, C, 0);
+  launch_k(col_final_kernel, dim3((C + 127) / 128), dim3(128), 0, (cudaStream_t)stream, (const float*)ws, nch, C, 1.0f, out);
+  return check_launch("sar_colsum_rows_fwd");
+}
+
+int sar_bn_train_rows_fwd(const float* x, const float* gamma, const float* beta, float* moving_mean, float* moving_var, float* y,
+                          float* save_mean, float* save_invstd, int rows, int C, float eps, float momentum, int nch, float* ws,
+                          void* stream) {
+  using namespace sar;
+  SAR_REQUIRE(x && gamma && beta && y && save_mean && save_invstd && ws, SAR_ERR_BAD_ARG, "sar_bn_train_rows_fwd: null pointer");
+  SAR_REQUIRE(rows > 0 && C > 0 && nch > 0 && nch <= 65535, SAR_ERR_BAD_ARG, "sar_bn_train_rows_fwd: bad dimension");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* var = ws + (size_t)2 * nch * C;
+  const dim3 gp((C + 31) / 32, nch), gc((C + 127) / 128);
+  launch_k(col_partial_kernel, gp, dim3(256), 0, st, x, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, ws, (float*)nullptr, rows, C, 0);
+  launch_k(col_final_kernel, gc, dim3(128), 0, st, (const float*)ws, nch, C, 1.0f / rows, save_mean);
+  launch_k(col_partial_kernel, gp, dim3(256), 0, st, x, (const float*)nullptr, (const float*)save_mean, (const float*)nullptr, ws, (float*)nullptr, rows, C, 1);
+  launch_k(col_final_kernel, gc, dim3(128), 0, st, (const float*)ws, nch, C, 1.0f / rows, var);
+  launch_k(bn_stats_finish_kernel, gc, dim3(128), 0, st, (const float*)save_mean, (const float*)var, save_invstd, moving_mean, moving_var, C, eps, momentum);
+  launch_k(bn_apply_kernel, dim3(blocks_for((long long)rows * C, 256, 1 << 16)), dim3(256), 0, st, x, (const float*)save_mean, (const float*)save_invstd,
+           gamma, beta, y, (long long)rows * C, C);
+  return check_launch("sar_bn_train_rows_fwd");
+}
+
+int sar_bn_train_rows_bwd(const float* x, const float* dy, const float* gamma, const float* save_mean, const float* save_invstd,
+                          float* dx, float* dgamma, float* dbeta, int rows, int C, int nch, float* ws, void* stream) {
+  using namespace sar;
+  SAR_REQUIRE(x && dy && gamma && save_mean && save_invstd && dgamma && dbeta && ws, SAR_ERR_BAD_ARG, "sar_bn_train_rows_bwd: null pointer");
+  SAR_REQUIRE(rows > 0 && C > 0 && nch > 0 && nch <= 65535, SAR_ERR_BAD_ARG, "sar_bn_train_rows_bwd: bad dimension");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* p2 = ws + (size_t)nch * C;
+  const dim3 gp((C + 31) / 32, nch), gc((C + 127) / 128);
+  launch_k(col_partial_kernel, gp, dim3(256), 0, st, x, dy, save_mean, save_invstd, ws, p2, rows, C, 2);
+  launch_k(col_final_kernel, gc, dim3(128), 0, st, (const float*)ws, nch, C, 1.0f, dbeta);
+  launch_k(col_final_kernel, gc, dim3(128), 0, st, (const float*)p2, nch, C, 1.0f, dgamma);
+  if (dx)
+    launch_k(bn_bwd_apply_kernel, dim3(blocks_for((long long)rows * C, 256, 1 << 16)), dim3(256), 0, st, x, dy, save_mean, save_invstd, gamma,
+             (const float*)dgamma, (const float*)dbeta, dx, (long long)rows * C, C, 1.0f / rows);
+  return check_launch("sar_bn_train_rows_bwd");
 }
 
 int sar_bias_act_fwd(const float* x, const float* bias, float* y, long long rows, int C, int act, void* stream) {
@@ -661,8 +865,10 @@ int sar_conv2d_bwd_weight(const float* x, const float* dy, float* partial, int c
   SAR_REQUIRE(x && dy && partial, SAR_ERR_BAD_ARG, "sar_conv2d_bwd_weight: null pointer");
   SAR_REQUIRE(chunks > 0 && chunks <= 65535 && B > 0 && H > 0 && W > 0 && Cin > 0 && Ho > 0 && Wo > 0 && Cout > 0 && kh > 0 && kw > 0 && stride > 0,
               SAR_ERR_BAD_ARG, "sar_conv2d_bwd_weight: bad dimension");
-  launch_k(conv2d_bwd_weight_kernel, dim3(blocks_for((long long)kh * kw * Cin * Cout, 128, 4096), chunks), dim3(128), 0, (cudaStream_t)stream, x, dy,
-           partial, B, H, W, Cin, Ho, Wo, Cout, kh, kw, stride, pad_t, pad_l);
+  const long long tiles = (long long)kh * kw * ((Cin + 31) / 32) * ((Cout + 31) / 32);
+  SAR_REQUIRE(tiles < (1ll << 31), SAR_ERR_UNSUPPORTED, "sar_conv2d_bwd_weight: too many tiles");
+  launch_k(conv2d_bwd_weight_kernel, dim3((unsigned)tiles, chunks), dim3(256), 0, (cudaStream_t)stream, x, dy, partial, B, H, W, Cin, Ho, Wo,
+           Cout, kh, kw, stride, pad_t, pad_l);
   return check_launch("sar_conv2d_bwd_weight");
 }
 

@@ -65,11 +65,25 @@ def gemm(a, b, *, ta=False, tb=False, alpha=1.0, beta=0.0, out=None):
     return out
 
 
+ROWS_PARALLEL = 2048        # more rows than this: the row-parallel kernels (the ResNet's maps: rows = B*H*W)
+
+
+def _row_chunks(rows: int, C: int, dev):
+    nch = max(1, min(256, rows // 512))
+    return nch, torch.empty(((2 * nch + 2) * C,), device=dev, dtype=torch.float32)
+
+
 def bn_train_fwd(x, gamma, beta, mov_mean=None, mov_var=None):
     rows, C = x.shape
     y = torch.empty_like(x)
     mean = torch.empty((C,), device=x.device, dtype=torch.float32)
     inv = torch.empty((C,), device=x.device, dtype=torch.float32)
+    if rows > ROWS_PARALLEL:
+        nch, ws = _row_chunks(rows, C, x.device)
+        check(_shim.lib().sar_bn_train_rows_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(mov_mean), ptr(mov_var), ptr(y), ptr(mean), ptr(inv),
+                                                rows, C, BN_EPS, BN_MOMENTUM, nch, ptr(ws), stream_ptr()), "sar_bn_train_rows_fwd")
+        ops._count(6)
+        return y, mean, inv
     check(_shim.lib().sar_bn_train_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(mov_mean), ptr(mov_var), ptr(y), ptr(mean), ptr(inv),
                                        rows, C, BN_EPS, BN_MOMENTUM, stream_ptr()), "sar_bn_train_fwd")
     ops._count(1)
@@ -81,6 +95,12 @@ def bn_train_bwd(x, dy, gamma, mean, inv, want_dx=True):
     dx = torch.empty_like(x) if want_dx else None
     dg = torch.empty((C,), device=x.device, dtype=torch.float32)
     db = torch.empty((C,), device=x.device, dtype=torch.float32)
+    if rows > ROWS_PARALLEL:
+        nch, ws = _row_chunks(rows, C, x.device)
+        check(_shim.lib().sar_bn_train_rows_bwd(ptr(x), ptr(dy), ptr(gamma), ptr(mean), ptr(inv), ptr(dx), ptr(dg), ptr(db), rows, C, nch,
+                                                ptr(ws), stream_ptr()), "sar_bn_train_rows_bwd")
+        ops._count(4)
+        return dx, dg, db
     check(_shim.lib().sar_bn_train_bwd(ptr(x), ptr(dy), ptr(gamma), ptr(mean), ptr(inv), ptr(dx), ptr(dg), ptr(db), rows, C,
                                        stream_ptr()), "sar_bn_train_bwd")
     ops._count(1)
@@ -104,6 +124,11 @@ def relu_bwd(g, h):
 
 def colsum(g):
     out = torch.empty((g.shape[1],), device=g.device, dtype=torch.float32)
+    if g.shape[0] > ROWS_PARALLEL:
+        nch, ws = _row_chunks(g.shape[0], g.shape[1], g.device)
+        check(_shim.lib().sar_colsum_rows_fwd(ptr(g), ptr(out), g.shape[0], g.shape[1], nch, ptr(ws), stream_ptr()), "sar_colsum_rows_fwd")
+        ops._count(2)
+        return out
     check(_shim.lib().sar_colsum_fwd(ptr(g), ptr(out), g.shape[0], g.shape[1], stream_ptr()), "sar_colsum_fwd")
     ops._count(1)
     return out

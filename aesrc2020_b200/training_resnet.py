@@ -24,6 +24,12 @@ from . import training as T
 
 
 def conv_bwd_data(spec, dy, w, B, dx=None, beta=0.0):
+    if (spec.stride == 1 and beta == 0.0 and dx is None and spec.kh == spec.kw and spec.kh % 2 == 1
+            and spec.pad_t == spec.kh // 2 and spec.pad_l == spec.kw // 2 and spec.hin == spec.hout and spec.win == spec.wout):
+        # stride-1 SAME: d loss / d x is the forward convolution of dy with the kernel rotated by 180 degrees and its channel axes
+        # swapped -- the implicit-GEMM forward kernel (sar_conv2d_fwd) is ~15x faster than the direct gradient kernel
+        wf = w.flip(0, 1).permute(0, 1, 3, 2).contiguous()
+        return ops.conv2d(dy, wf, None, stride=1, pad_t=spec.pad_t, pad_l=spec.pad_l, out_hw=(spec.hin, spec.win))
     if dx is None:
         dx = torch.empty((B, spec.hin, spec.win, spec.cin), device=dy.device, dtype=torch.float32)
     check(_shim.lib().sar_conv2d_bwd_data(ptr(dy), ptr(w), ptr(dx), B, spec.hin, spec.win, spec.cin, spec.hout, spec.wout, spec.cout,
@@ -35,7 +41,7 @@ def conv_bwd_data(spec, dy, w, B, dx=None, beta=0.0):
 
 def conv_bwd_weight(spec, x, dy, B):
     npos = B * spec.hout * spec.wout
-    chunks = max(1, min(64, npos // 256))
+    chunks = max(1, min(128, npos // 512))
     nw = spec.kh * spec.kw * spec.cin * spec.cout
     part = torch.empty((chunks, nw), device=dy.device, dtype=torch.float32)
     check(_shim.lib().sar_conv2d_bwd_weight(ptr(x), ptr(dy), ptr(part), chunks, B, spec.hin, spec.win, spec.cin, spec.hout, spec.wout,

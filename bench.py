@@ -24,6 +24,8 @@ Printed JSON (rank 0, ONE line):
                  configs[3] shard (NetVLAD+CosFace, 256/GPU), configs[4] shard (512/GPU): value / single_stream /
                  e2e / conv roofline each
   strong         configs[4] strong scaling: global B=4096 split over the N ranks, micro-batched (512/step)
+  train_slice    SURVEY 8f-1: one optimisation step of everything above the frozen ResNet (accent path), B=64/GPU
+  train_full     SURVEY 8f-1: one optimisation step of the WHOLE model, multi-task (correctness-first ResNet backward), B=16/GPU
   cpu_baseline   the oracle's torch-CPU fp32 restatement of the Keras forward on the host cores (bounded sample)
 `--impl reference` times that CPU restatement as the reference arm (the literal Keras/TF graph cannot run here: no
 tensorflow/keras in the image and CuDNNGRU has no CPU kernel).  `--quick` skips extra_configs / strong / sustained.
@@ -577,6 +579,43 @@ def train_slice_bench(dev, rank, world, B=64, steps=10):
             "note": "eager launches (no CUDA graph; the Bi-GRU is one GEMM + one gate kernel per time step and direction, fp32 CUDA cores), includes the frozen ResNet's inference forward; gradients of the ResNet and of the CTC branch are not built"}
 
 
+def train_full_bench(dev, rank, world, B=16, steps=2):
+    """SURVEY 8f-1, complete but correctness-first: one optimisation step of the WHOLE model (configs[4] graph: ResNet in training
+    mode + CRNN + CTC branch + GhostVLAD + Circle-Loss), training.HeadTrainer(train_resnet=True, train_ctc=True).  The ResNet's
+    backward is fp32 CUDA-core code (training_resnet.py), so this number says what the slice costs today, not what B200 can do."""
+    import torch.distributed as tdist
+    from aesrc2020_b200 import model as mdl, training as T, utils as us
+    with contextlib.redirect_stdout(io.StringIO()):
+        model, _ = mdl.SAR_Net((500, 80, 1), **dict(CONFIGS["cfg5"]["kw"]))
+    x, y = us.synthetic_batch(model.config, B, seed=300 + rank)
+    tr = T.HeadTrainer(model, lr=0.005, train_resnet=True, train_ctc=True)
+    xd = {k: model._to_device(k, v) for k, v in x.items()}
+    first = tr.train_on_batch(xd, y)
+    torch.cuda.synchronize()
+    if world > 1:
+        tdist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        last = tr.train_on_batch(xd, y)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+        ms = float(t.item())
+    npar = int(sum(tr.p[k].numel() for k in tr.keys))
+    return {"workload": "whole model, nothing frozen (configs[4] graph: thin-ResNet34 in training mode + CRNN + CTC branch + GhostVLAD + Circle-Loss), "
+                        "B=%d/GPU x 500 frames, fwd + bwd + Adam" % B,
+            "ms_per_step": ms, "value": world * B / (ms * 1e-3), "unit": "utt/s (training, whole graph)", "trainable_parameters": npar,
+            "allreduce_bytes_per_step": 4 * npar if world > 1 else 0, "loss_first": float(first["loss"]), "loss_last": float(last["loss"]),
+            "scaling": "weak",
+            "note": "correctness-first: the ResNet's training forward / backward are fp32 CUDA-core kernels (row-parallel BN statistics, "
+                    "smem-tiled weight gradients, data gradients through the implicit-GEMM forward kernel), eager launches; parity with the "
+                    "float64 autograd oracle is tested, tensor-core speed is not the claim"}
+
+
 # ====================================================================================== strong scaling
 def strong_scaling(dev, rank, world, peaks, global_b=4096, micro=512, reps=2):
     """configs[4]: global B=4096, split contiguously over the ranks (dist.shard_slice), every rank runs its share as
@@ -733,7 +772,7 @@ def main():
     R.close()
 
     # ---------------------------------------------------------------- the other north-star configurations
-    extra, strong, roofline_vlad, train_slice = None, None, None, None
+    extra, strong, roofline_vlad, train_slice, train_full = None, None, None, None, None
     if not quick:
         extra = {}
         vlad_in_graph = {64: vlad_ms} if (vlad_ms and args.config == "cfg2" and B == 64) else {}
@@ -757,6 +796,11 @@ def main():
             train_slice = train_slice_bench(dev, rank, world)
         except Exception as ex:
             train_slice = {"error": "%s: %s" % (type(ex).__name__, ex)}
+        try:
+            train_full = train_full_bench(dev, rank, world)
+        except Exception as ex:
+            train_full = {"error": "%s: %s" % (type(ex).__name__, ex)}
+            torch.cuda.empty_cache()
         if rank == 0:
             try:
                 roofline_vlad = vlad_roofline(dev, peaks, vlad_ms_in_graph=vlad_in_graph)
@@ -807,6 +851,7 @@ def main():
         line["roofline_vlad"] = roofline_vlad
     if train_slice:
         line["train_slice"] = train_slice
+        line["train_full"] = train_full
     if roofline_fbank:
         line["roofline_fbank"] = roofline_fbank
     if e2e_pcm:

@@ -307,6 +307,14 @@ int sar_bn_train_fwd(const float* x, const float* gamma, const float* beta, floa
                      float* save_mean, float* save_invstd, int rows, int C, float eps, float momentum, void* stream);
 int sar_bn_train_bwd(const float* x, const float* dy, const float* gamma, const float* save_mean, const float* save_invstd,
                      float* dx /* may be NULL */, float* dgamma, float* dbeta, int rows, int C, void* stream);
+/* Row-parallel forms for maps with many rows (the ResNet's BatchNormalizations in training mode, conv bias gradients): the rows
+ * are reduced in `nch` chunks with a fixed summation order; `ws` = caller-owned scratch of (2 * nch + 2) * C floats. */
+int sar_colsum_rows_fwd(const float* g, float* out, int rows, int C, int nch, float* ws, void* stream);
+int sar_bn_train_rows_fwd(const float* x, const float* gamma, const float* beta, float* moving_mean, float* moving_var, float* y,
+                          float* save_mean, float* save_invstd, int rows, int C, float eps, float momentum, int nch, float* ws,
+                          void* stream);
+int sar_bn_train_rows_bwd(const float* x, const float* dy, const float* gamma, const float* save_mean, const float* save_invstd,
+                          float* dx /* may be NULL */, float* dgamma, float* dbeta, int rows, int C, int nch, float* ws, void* stream);
 /* y = act(x + bias) on (rows, C), act in {SAR_ACT_NONE, SAR_ACT_RELU, SAR_ACT_TANH}; out = g * (h > 0); out (C) = column sums of g (rows, C). */
 int sar_bias_act_fwd(const float* x, const float* bias, float* y, long long rows, int C, int act, void* stream);
 int sar_relu_bwd(const float* g, const float* h, float* out, long long n, void* stream);
