@@ -1,4 +1,6 @@
-"""Training mode, first slice: one optimisation step of the reference's accent head on the device.
+"""Training mode: optimisation steps of the reference's model on the device, built slice by slice from the
+accent head down to the ResNet -- `HeadTrainer(model, train_resnet=True, train_ctc=True)` trains the WHOLE model, the other
+flags freeze everything below the chosen layer (fine-tuning above the frozen inference engine).
 
 What the reference does with the path is `train_model.fit_generator(...)` (train.py:38-44) on a model compiled with
 `Adam(lr, decay=2e-4)` (model.py:187-201).  This module builds the first slice of that: the layers AFTER
