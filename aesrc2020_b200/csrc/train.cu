@@ -69,21 +69,21 @@ __global__ void __launch_bounds__(256) gemm_kernel(const float* __restrict__ A, 
     }
 }
 
-// Skinny GEMM, M <= 32 rows, A not transposed: the per-time-step products of the GRU (h U, d_hu U^T with M = batch) and the
+// Skinny GEMM, M <= 64 rows, A not transposed: the per-time-step products of the GRU (h U, d_hu U^T with M = batch) and the
 // embedding Dense at small batches.  The 64 x 64 tiles of gemm_kernel leave all but a few CTAs idle there and pay one
 // global-memory round trip per 16 k-values (2-3 us each).  Here a CTA owns 32 output columns, lane = column, the 8 warps
 // split K; every lane keeps its M accumulators in registers, A values are warp-broadcast loads, B is read coalesced
 // (tb = 0: row k across the lanes) or as one contiguous row per lane (tb = 1).  The warps' partial sums are added in warp
-// order: a fixed summation order.
-template <int MR>
-__global__ void __launch_bounds__(256) gemm_skinny_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
+// order: a fixed summation order.  (M <= 32: 8 warps; M <= 64: 4 warps, the partial sums must fit 48 KB of shared memory.)
+template <int MR, int NW>
+__global__ void __launch_bounds__(NW * 32) gemm_skinny_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
                                                           int M, int N, int K, int tb, float alpha, float beta) {
   pdl_wait();
   pdl_trigger();
-  __shared__ float red[8][MR][33];
+  __shared__ float red[NW][MR][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + lane;
-  const int per = (K + 7) / 8;
+  const int per = (K + NW - 1) / NW;
   const int k0 = warp * per, k1 = min(K, k0 + per);
   float acc[MR];
 #pragma unroll
@@ -102,12 +102,12 @@ __global__ void __launch_bounds__(256) gemm_skinny_kernel(const float* __restric
 #pragma unroll
   for (int m = 0; m < MR; ++m) red[warp][m][lane] = acc[m];
   __syncthreads();
-  for (int i = threadIdx.x; i < MR * 32; i += 256) {
+  for (int i = threadIdx.x; i < MR * 32; i += NW * 32) {
     const int m = i >> 5, l = i & 31, gn = blockIdx.x * 32 + l;
     if (m < M && gn < N) {
       float t = 0.f;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) t += red[w][m][l];
+      for (int w = 0; w < NW; ++w) t += red[w][m][l];
       float* c = C + (size_t)m * N + gn;
       *c = alpha * t + (beta != 0.f ? beta * *c : 0.f);
     }
@@ -729,11 +729,13 @@ int sar_gemm_fwd(const float* A, const float* B, float* C, int M, int N, int K, 
   using namespace sar;
   SAR_REQUIRE(A && B && C, SAR_ERR_BAD_ARG, "sar_gemm_fwd: null pointer");
   SAR_REQUIRE(M > 0 && N > 0 && K > 0, SAR_ERR_BAD_ARG, "sar_gemm_fwd: non-positive dimension");
-  if (!trans_a && M <= 32 && K >= 64) {          // skinny: the GRU's per-step products, the embedding Dense at small batches
-    if (M <= 16)
-      launch_k(gemm_skinny_kernel<16>, dim3((N + 31) / 32), dim3(256), 0, (cudaStream_t)stream, A, B, C, M, N, K, trans_b ? 1 : 0, alpha, beta);
-    else
-      launch_k(gemm_skinny_kernel<32>, dim3((N + 31) / 32), dim3(256), 0, (cudaStream_t)stream, A, B, C, M, N, K, trans_b ? 1 : 0, alpha, beta);
+  if (!trans_a && M <= 64 && K >= 64) {          // skinny: the GRU's per-step products, the embedding Dense at small batches
+    const dim3 g((N + 31) / 32);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int tb_ = trans_b ? 1 : 0;
+    if (M <= 16) launch_k(gemm_skinny_kernel<16, 8>, g, dim3(256), 0, st, A, B, C, M, N, K, tb_, alpha, beta);
+    else if (M <= 32) launch_k(gemm_skinny_kernel<32, 8>, g, dim3(256), 0, st, A, B, C, M, N, K, tb_, alpha, beta);
+    else launch_k(gemm_skinny_kernel<64, 4>, g, dim3(128), 0, st, A, B, C, M, N, K, tb_, alpha, beta);
     return check_launch("sar_gemm_fwd(skinny)");
   }
   launch_k(gemm_kernel, dim3((N + TG - 1) / TG, (M + TG - 1) / TG), dim3(256), 0, (cudaStream_t)stream, A, B, C, M, N, K, trans_a ? 1 : 0,

@@ -15,7 +15,8 @@ KINDS = [("arcface", 0.3), ("cosface", 0.3), ("sphereface", 1.35), ("softmax", 0
 @pytest.mark.parametrize("M,N,K,ta,tb", [(64, 256, 16384, False, False), (16384, 256, 48, True, False), (48, 16384, 256, False, True),
                                          (7, 5, 3, False, False), (65, 130, 17, True, True), (1, 8, 64, False, False),
                                          (16, 768, 256, False, False), (16, 256, 768, False, True), (12, 250, 16385, False, False),
-                                         (32, 77, 100, False, True), (17, 40, 64, False, False)])       # skinny kernel (M <= 32, A not transposed)
+                                         (32, 77, 100, False, True), (17, 40, 64, False, False), (64, 768, 256, False, False),
+                                         (64, 256, 768, False, True), (33, 70, 129, False, True)])       # skinny kernel (M <= 64, A not transposed)
 def test_gemm_all_transposes(cuda_device, M, N, K, ta, tb):
     from aesrc2020_b200 import training as T
     rng = np.random.RandomState(M + N)
