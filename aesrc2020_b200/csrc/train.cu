@@ -729,7 +729,9 @@ int sar_gemm_fwd(const float* A, const float* B, float* C, int M, int N, int K, 
   using namespace sar;
   SAR_REQUIRE(A && B && C, SAR_ERR_BAD_ARG, "sar_gemm_fwd: null pointer");
   SAR_REQUIRE(M > 0 && N > 0 && K > 0, SAR_ERR_BAD_ARG, "sar_gemm_fwd: non-positive dimension");
-  if (!trans_a && M <= 64 && K >= 64) {          // skinny: the GRU's per-step products, the embedding Dense at small batches
+  // skinny: the GRU's per-step products, the embedding Dense at small batches.  (M in (32, 64] has a 4-warp instance, measured
+  // SLOWER than the tiled kernel at M = 64 -- 85 vs 49 us per h U product: 64 broadcast loads per k-value -- so it is not dispatched)
+  if (!trans_a && M <= 32 && K >= 64) {
     const dim3 g((N + 31) / 32);
     cudaStream_t st = (cudaStream_t)stream;
     const int tb_ = trans_b ? 1 : 0;

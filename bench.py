@@ -591,6 +591,7 @@ def train_full_bench(dev, rank, world, B=16, steps=2):
     tr = T.HeadTrainer(model, lr=0.005, train_resnet=True, train_ctc=True)
     xd = {k: model._to_device(k, v) for k, v in x.items()}
     first = tr.train_on_batch(xd, y)
+    tr.train_on_batch(xd, y)                          # second warm-up step: the caching allocator still grows during the first two
     torch.cuda.synchronize()
     if world > 1:
         tdist.barrier()
