@@ -689,10 +689,13 @@ __global__ void maxpool2d_bwd_kernel(const float* __restrict__ x, const float* _
     const int b = (int)(r / H);
     const float me = x[i];
     float acc = 0.f;
-    for (int ho = 0; ho < Ho; ++ho) {
+    // windows covering me: ho with ho*stride - pad_t <= y_ < ho*stride - pad_t + k (same along w)
+    const int ho_lo = max(0, (y_ + pad_t - k + stride) / stride), ho_hi = min(Ho - 1, (y_ + pad_t) / stride);
+    const int wo_lo = max(0, (x_ + pad_l - k + stride) / stride), wo_hi = min(Wo - 1, (x_ + pad_l) / stride);
+    for (int ho = ho_lo; ho <= ho_hi; ++ho) {
       const int h0 = ho * stride - pad_t;
       if (y_ < h0 || y_ >= h0 + k) continue;
-      for (int wo = 0; wo < Wo; ++wo) {
+      for (int wo = wo_lo; wo <= wo_hi; ++wo) {
         const int w0 = wo * stride - pad_l;
         if (x_ < w0 || x_ >= w0 + k) continue;
         // am I the first maximum of this window (row-major scan, padded cells never win)?

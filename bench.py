@@ -25,7 +25,7 @@ Printed JSON (rank 0, ONE line):
                  e2e / conv roofline each
   strong         configs[4] strong scaling: global B=4096 split over the N ranks, micro-batched (512/step)
   train_slice    SURVEY 8f-1: one optimisation step of everything above the frozen ResNet (accent path), B=64/GPU
-  train_full     SURVEY 8f-1: one optimisation step of the WHOLE model, multi-task (correctness-first ResNet backward), B=16/GPU
+  train_full     SURVEY 8f-1: one optimisation step of the WHOLE model, multi-task (correctness-first ResNet backward), B=64/GPU
   cpu_baseline   the oracle's torch-CPU fp32 restatement of the Keras forward on the host cores (bounded sample)
 `--impl reference` times that CPU restatement as the reference arm (the literal Keras/TF graph cannot run here: no
 tensorflow/keras in the image and CuDNNGRU has no CPU kernel).  `--quick` skips extra_configs / strong / sustained.
@@ -579,7 +579,7 @@ def train_slice_bench(dev, rank, world, B=64, steps=10):
             "note": "eager launches (no CUDA graph; the Bi-GRU is one GEMM + one gate kernel per time step and direction, fp32 CUDA cores), includes the frozen ResNet's inference forward; gradients of the ResNet and of the CTC branch are not built"}
 
 
-def train_full_bench(dev, rank, world, B=16, steps=2):
+def train_full_bench(dev, rank, world, B=64, steps=2):
     """SURVEY 8f-1, complete but correctness-first: one optimisation step of the WHOLE model (configs[4] graph: ResNet in training
     mode + CRNN + CTC branch + GhostVLAD + Circle-Loss), training.HeadTrainer(train_resnet=True, train_ctc=True).  The ResNet's
     backward is fp32 CUDA-core code (training_resnet.py), so this number says what the slice costs today, not what B200 can do."""
