@@ -1,5 +1,7 @@
-/* sarnet.h -- C ABI of libsarnet_sm100.so, the B200 (sm_100a) forward engine for the
- * speech-accent-recognition network of pika-online/AESRC2020.
+/* sarnet.h -- C ABI of libsarnet_sm100.so, the B200 (sm_100a) engine for the
+ * speech-accent-recognition network of pika-online/AESRC2020: the inference forward path on
+ * tcgen05 tensor-core kernels, and the training-mode forward / backward kernels (fp32,
+ * correctness-first; the "training mode" section near the end).
  *
  * The reference has NO native/FFI interface (it is Keras-on-TensorFlow Python); its
  * boundary for this path is the Python call surface of model.py / resnet.py / VLAD.py /
