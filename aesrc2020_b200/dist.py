@@ -119,6 +119,29 @@ class DataParallelModel:
             res.append(full if isinstance(o, torch.Tensor) else full.cpu().numpy())
         return res if isinstance(local, list) else res[0]
 
+    def _shard_batches(self, generator):
+        """multi_gpu_model's split (model.py:193-194): every global batch the generator yields is cut into contiguous
+        per-replica shards; this rank keeps its own."""
+        rank, world = self._rank_world()
+        for item in generator:
+            x, y = item if isinstance(item, tuple) else (item, None)
+            xd = self.model._as_dict(x)
+            n = len(xd["x_data"])
+            sl = shard_slice(n, rank, world)
+            yield shard_inputs(xd, rank, world), (None if y is None else {k: v[sl] for k, v in y.items()})
+
+    def train_on_batch(self, x, y=None):
+        return next(self.fit_batches([(x, y)]))
+
+    def fit_batches(self, batches):
+        for xs, ys in self._shard_batches(batches):
+            yield self.model.train_on_batch(xs, ys)
+
+    def fit_generator(self, generator, steps_per_epoch, epochs=1, **kw):
+        """train.py:38-44 on the data-parallel model: every rank trains on its shard of each global batch, the gradients are
+        all-reduced (mean) inside training.HeadTrainer -- the synchronous data parallelism of multi_gpu_model."""
+        return self.model.fit_generator(self._shard_batches(generator), steps_per_epoch, epochs, **kw)
+
     def evaluate(self, x, y=None, batch_size=32):
         rank, world = self._rank_world()
         xs = shard_inputs(self.model._as_dict(x), rank, world)

@@ -4,8 +4,8 @@ Kept verbatim from the reference: `SAR_Net(...)` keyword set and `(model, train_
 return (model.py:204-224,371); the returned model's `predict / get_layer / load_weights /
 save_weights / summary`; helper names `build, compile, integration, vlad, disc_loss,
 ctc_module, ctc_lambda_func, sub_model, ctc_pred` and the layer factories `SQUEEZE, EXPAND,
-BN, LN, DS, BIGRU, DP` (model.py:23-53).  Forward-only: `lr` is accepted and ignored, and
-`compile` wires the data-parallel wrapper instead of an optimiser.
+BN, LN, DS, BIGRU, DP` (model.py:23-53).  `compile` keeps `lr` for `fit_generator` / `train_on_batch` (training.HeadTrainer:
+Keras' Adam(lr, decay=2e-4), model.py:197) and wires the data-parallel wrapper for gpus > 1.
 
 Tensors at this surface: numpy arrays (host, as in Keras) or CUDA torch tensors.  predict()
 with host arrays does the H2D copy from pinned memory, runs the kernels, and copies the
@@ -272,6 +272,8 @@ class SARModel:
         # concurrent micro-batch lanes per step (engine.forward_lanes); 0 = automatic (see _lanes_for)
         self.lanes = int(os.environ.get("SAR_LANES", "0"))
         self._pipe = None              # predict_generator's staging slots (see _pipe_state)
+        self.lr = 0.01                 # compile(): Adam(lr, decay=2e-4), model.py:197
+        self._trainer = None           # training.HeadTrainer over the whole model, built by the first training call
 
     # -- Keras-like surface
     @property
@@ -620,6 +622,58 @@ class SARModel:
         res = [np.concatenate(c, 0) for c in chunks] if n else [np.zeros((0,), np.float32) for _ in chunks]
         return res[0] if len(res) == 1 else res
 
+    # -- training surface (train.py:38-44): the whole model, nothing frozen
+    def trainer(self, group=None):
+        """The training.HeadTrainer behind train_on_batch / fit_generator: every layer trains (ResNet with batch-statistic
+        BatchNormalization, CRNN, accent branch, and the CTC branch when ctc_enable), Adam(self.lr, decay=2e-4)."""
+        if self._trainer is None:
+            cfg = self.config
+            if not cfg.ar_enable or cfg.mto not in ("vlad", "gvlad") or cfg.bn_dim:
+                raise SarnetError("training is built for ar_enable=True with mto='vlad' | 'gvlad' and bn_dim=0 "
+                                  "(got ar_enable=%s, mto=%r, bn_dim=%s)" % (cfg.ar_enable, cfg.mto, cfg.bn_dim))
+            from .training import HeadTrainer
+            self._trainer = HeadTrainer(self, lr=self.lr, group=group, train_resnet=True, train_ctc=bool(cfg.ctc_enable))
+        return self._trainer
+
+    def train_on_batch(self, x, y=None):
+        """Keras Model.train_on_batch: one optimisation step; returns {'loss', 'loss_accent', 'loss_disc'[, 'loss_ctc']}.
+        The inference weights follow at the end of fit_generator (or trainer().sync_to_model())."""
+        return self.trainer().train_on_batch(x, y)
+
+    def fit_generator(self, generator, steps_per_epoch, epochs=1, verbose=1, callbacks=None, validation_data=None,
+                      max_queue_size=10, workers=1, use_multiprocessing=False, initial_epoch=0, **kw):
+        """Keras Model.fit_generator as train.py:38-44 calls it: `epochs - initial_epoch` epochs of `steps_per_epoch` batches
+        of (inputs, targets) from `generator` (utils.data_generator).  After every epoch the trained weights are written
+        back into the model (so a callback's `model.save(...)`, train.py:31-35, stores them), `validation_data` =
+        (inputs, targets) is evaluated with the inference engine (`val_*` entries), and every object in `callbacks` that
+        has `on_epoch_end(epoch, logs)` is called (duck-typed: Keras itself is not a dependency).  A callback may stop the
+        run by setting `model.stop_training = True` (what EarlyStopping does).  Returns the list of per-epoch logs."""
+        tr = self.trainer()
+        it = iter(generator)
+        history = []
+        self.stop_training = False
+        for epoch in range(int(initial_epoch), int(epochs)):
+            acc = []
+            for _ in range(int(steps_per_epoch)):
+                item = next(it)
+                xb, yb = item if isinstance(item, tuple) else (item, None)
+                acc.append(tr.train_on_batch(xb, yb))
+            logs = {k: float(np.mean([a[k] for a in acc])) for k in acc[0]}
+            tr.sync_to_model()
+            if validation_data is not None:
+                vx, vy = validation_data[0], (validation_data[1] if len(validation_data) > 1 else None)
+                for k, v in self.evaluate(vx, vy).items():
+                    logs["val_" + k] = float(v)
+            history.append(logs)
+            if verbose:
+                print("Epoch %d/%d - %s" % (epoch + 1, epochs, " - ".join("%s: %.4f" % kv for kv in logs.items())))
+            for cb in (callbacks or []):
+                if hasattr(cb, "on_epoch_end"):
+                    cb.on_epoch_end(epoch, logs)
+            if self.stop_training:
+                break
+        return history
+
     def evaluate(self, x, y: Optional[Dict[str, ArrayLike]] = None, batch_size=32, group=None):
         """Keras-style evaluate: batch-mean losses, accuracies and the weighted total
         (model.py:344-367).  With torch.distributed initialised the 8-float loss vector is
@@ -650,8 +704,11 @@ def build(inputs, outputs, raw=None, name="model"):
 
 
 def compile(model, gpus, lr=None, loss=None, loss_weights=None, metrics=None):
-    """model.py:187-201.  Forward-only: no optimiser.  gpus>1 returns the data-parallel view
-    (one process per GPU under torchrun; batch sharded by rank; loss vector all-reduced)."""
+    """model.py:187-201: Adam(lr, decay=2e-4) is what fit_generator / train_on_batch use (training.HeadTrainer).  gpus>1
+    returns the data-parallel view (one process per GPU under torchrun; batch sharded by rank; loss vector and, in
+    training, the gradients all-reduced)."""
+    if lr is not None:
+        model.lr = float(lr)
     if gpus > 1:
         from .dist import DataParallelModel
         return DataParallelModel(model, gpus)

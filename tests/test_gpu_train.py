@@ -639,3 +639,47 @@ def test_whole_model_training_lowers_the_loss(cuda_device):
         warnings.simplefilter("ignore")
         outs = model.predict(x, batch_size=8)
     assert all(np.all(np.isfinite(o)) for o in outs)
+
+
+def test_fit_generator_mirrors_train_py(cuda_device, tmp_path):
+    """train.py:25-44 end to end on the mirrored surface: utils.data_generator -> train_model.fit_generator(steps_per_epoch,
+    epochs, callbacks=[a Callback that saves '%03d.h5' every epoch], validation_data) -> the saved checkpoint, loaded back through
+    SAR_Net(raw_model=...), predicts what the trained model predicts.  Whole model, multi-task (CTC + accent), nothing frozen."""
+    import warnings
+    from aesrc2020_b200 import model as mdl, utils as us
+    kw = dict(ctc_enable=True, ar_enable=True, disc_enable=True, res_type="res18", res_filters=8, mto="gvlad", vlad_clusters=8,
+              ghost_clusters=2, metric_loss="arcface", margin=0.3, bpe_classes=40, max_ctc_len=4)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model, train_model = mdl.SAR_Net((100, 80, 1), lr=0.004, **kw)
+    cfg = model.config
+    rng = np.random.RandomState(11)
+    lst = ["u%d" % i for i in range(16)]
+    data = {u: rng.rand(int(n), 80).astype(np.float32) for u, n in zip(lst, rng.randint(60, 100, size=16))}
+    acc = {u: int(rng.randint(0, 8)) for u in lst}
+    trans = {u: [int(v) for v in rng.randint(3, 38, size=rng.randint(1, 4))] for u in lst}
+    gkw = dict(ctc_enable=True, ar_enable=True, disc_enable=True, batch_size=8, data_dct=data, accent_dct=acc, trans_dct=trans,
+               max_input_len=100, max_ctc_len=4, encoder_len=cfg.plan().seq_len, accent_classes=8)
+    dev_x, dev_y = next(us.data_generator(lst, seed=3, **gkw))
+
+    saved = []
+
+    class evaluation:                                    # train.py:31-35
+        def on_epoch_end(self, epoch, logs=None):
+            p = str(tmp_path / ("%03d.h5" % epoch))
+            model.save(p)
+            saved.append((p, dict(logs)))
+
+    hist = train_model.fit_generator(generator=us.data_generator(lst, seed=1, **gkw), steps_per_epoch=4, epochs=3, callbacks=[evaluation()],
+                                     initial_epoch=0, validation_data=(dev_x, dev_y), max_queue_size=20, verbose=0)
+    assert len(hist) == 3 and len(saved) == 3
+    assert hist[-1]["loss"] < hist[0]["loss"], [h["loss"] for h in hist]
+    assert any(k.startswith("val_") for k in hist[0]) and all(np.isfinite(v) for h in hist for v in h.values())
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m2, _ = mdl.SAR_Net((100, 80, 1), seed=77, raw_model=saved[-1][0], **kw)
+        want = model.predict(dev_x, batch_size=8)
+        got = m2.predict(dev_x, batch_size=8)
+    for g, w in zip(got, want):
+        g, w = (g.cpu().numpy() if hasattr(g, "cpu") else g), (w.cpu().numpy() if hasattr(w, "cpu") else w)
+        assert np.array_equal(g, w)
