@@ -367,6 +367,7 @@ class HeadTrainer:
         put = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
         bn_stats = [b + s for b in ("AR_BN1", "AR_BN2") for s in ("/moving_mean", "/moving_variance")]
         self.p: Dict[str, torch.Tensor] = {k: put(model.weights[k]) for k in self.keys + bn_stats + res_stats}
+        self.stat_keys: List[str] = bn_stats + res_stats       # BN moving averages: per-replica updates, averaged over the ranks
         self.resnet_tr = None
         if self.train_resnet:
             from .training_resnet import ResNetTrainer
@@ -544,6 +545,7 @@ class HeadTrainer:
             adam_step(p[k], g[k], self.m[k], self.v[k], lr_t, l2=L2_REG if k in self.l2 else 0.0)
         if kind == "circleloss":
             unit_norm(p[self.disc_key])
+        self._sync_stats()
         self.iterations += 1
         lm = losses.mean(0).tolist()
         out = {"loss_accent": lm[0]}
@@ -556,6 +558,21 @@ class HeadTrainer:
             total += self.w_ctc * out["loss_ctc"]
         out["loss"] = total                        # data terms (Keras adds the regulariser terms to the reported total)
         return out
+
+    def _sync_stats(self):
+        """Every replica updates the BN moving averages with ITS shard's statistics; the mean over the replicas keeps the ranks'
+        inference weights identical (Keras' multi_gpu_model towers share one set of variables)."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+            return
+        flat = torch.cat([self.p[k].reshape(-1) for k in self.stat_keys])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+        flat /= dist.get_world_size(self.group)
+        off = 0
+        for k in self.stat_keys:
+            n = self.p[k].numel()
+            self.p[k].copy_(flat[off:off + n].view_as(self.p[k]))
+            off += n
 
     def _all_reduce(self, grads: Dict[str, torch.Tensor]):
         """Mean of the replicas' gradients: ONE flat all-reduce (NCCL over NVLink when initialised)."""
