@@ -83,3 +83,31 @@ def test_gradient_all_reduce_is_the_mean_over_replicas():
         p.join(timeout=60)
     for rank, a, b in res:
         assert a == [[1.5, 1.5]] * 3 and b == [0.0, 1.5, 3.0, 4.5]
+
+
+def test_data_parallel_fit_shards_every_global_batch_like_multi_gpu_model():
+    """dist.DataParallelModel._shard_batches (the generator fit_generator trains on when gpus > 1): every (inputs, targets)
+    batch is cut into the contiguous per-replica slices of multi_gpu_model (model.py:193-194); the slices of all ranks tile
+    the global batch, inputs and targets stay aligned.  Host logic only (no device, no process group: rank/world stubbed)."""
+    class _Model:
+        @staticmethod
+        def _as_dict(x):
+            return dict(x)
+
+    n = 11
+    x = {"x_data": np.arange(n * 3, dtype=np.float32).reshape(n, 3), "x_accent": np.arange(n)[:, None].astype(np.float32)}
+    y = {"y_accent": np.arange(n)[:, None].astype(np.float32) + 100}
+    for world in (1, 2, 4):
+        seen_x, seen_y = [], []
+        for rank in range(world):
+            dp = sdist.DataParallelModel(_Model(), world)
+            dp._rank_world = lambda r=rank, w=world: (r, w)
+            (xs, ys), = list(dp._shard_batches([(x, y)]))
+            assert len(xs["x_data"]) == len(xs["x_accent"]) == len(ys["y_accent"])
+            assert np.array_equal(ys["y_accent"][:, 0] - 100, xs["x_accent"][:, 0])      # inputs and targets of the same utterances
+            seen_x.append(xs["x_data"]); seen_y.append(ys["y_accent"])
+        assert np.array_equal(np.concatenate(seen_x), x["x_data"]) and np.array_equal(np.concatenate(seen_y), y["y_accent"])
+    dp = sdist.DataParallelModel(_Model(), 2)
+    dp._rank_world = lambda: (1, 2)
+    (xs, ys), = list(dp._shard_batches([x]))                  # a generator that yields inputs only
+    assert ys is None and len(xs["x_data"]) == n - n // 2
