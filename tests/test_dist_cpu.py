@@ -65,12 +65,18 @@ def _grad_worker(rank, world, port, q):
     tr.keys, tr.group = ["a", "b"], None
     g = {"a": torch.full((3, 2), float(rank + 1)), "b": torch.arange(4, dtype=torch.float32) * (rank + 1)}
     tr._all_reduce(g)
+    # ... and the BN moving averages every replica updated with its own shard's statistics
+    tr.stat_keys, tr.p = ["bn/moving_mean", "bn/moving_variance"], {"bn/moving_mean": torch.full((3,), float(rank)),
+                                                                    "bn/moving_variance": torch.full((3,), 2.0 + 2 * rank)}
+    tr._sync_stats()
+    assert tr.p["bn/moving_mean"].tolist() == [0.5] * 3 and tr.p["bn/moving_variance"].tolist() == [3.0] * 3
     q.put((rank, g["a"].tolist(), g["b"].tolist()))
     dist.destroy_process_group()
 
 
 def test_gradient_all_reduce_is_the_mean_over_replicas():
-    """training.HeadTrainer._all_reduce: ONE flat all-reduce, mean over the replicas (gloo here, NCCL on the GPUs)."""
+    """training.HeadTrainer._all_reduce: ONE flat all-reduce, mean over the replicas (gloo here, NCCL on the GPUs); _sync_stats:
+    the BN moving averages are averaged too (asserted inside the workers)."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
