@@ -7,7 +7,10 @@ lives in the un-vendored, un-pinned dependency `python_speech_features`
 published algorithm (sigproc.preemphasis / framesig / powspec and
 base.get_filterbanks).  `feat_norm` is sklearn's MinMaxScaler, which IS
 importable here and is cross-checked in tests/test_oracle_fbank.py.
-Parity status for this file: unpinned for psf, pinned for MinMaxScaler.
+Parity status for this file: unpinned for psf itself (no copy of the package or of its outputs is available offline);
+its stages are cross-checked against independent implementations in tests/test_oracle_fbank.py -- framing + rectangular
+window + |rfft_512|^2 / 512 against torch.stft, the mel scale and filter placement against torchaudio's HTK filterbank --
+and MinMaxScaler is pinned against sklearn.
 """
 from __future__ import annotations
 

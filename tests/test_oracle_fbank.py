@@ -78,3 +78,58 @@ def test_data_loader_oracle_matches_sklearn_and_reference_contract():
     assert x["x_ctc_in_len"].reshape(-1).tolist() == [13] * 5 and x["x_ctc_in_len"].shape == (5, 1)
     assert x["x_accent"].argmax(1).tolist() == [0, 1, 2, 3, 4] and x["x_accent"].sum() == 5
     assert set(y) == {"y_ctc_loss", "y_accent", "y_disc", "y_disc_bn"}
+
+
+def test_power_spectrum_matches_torch_stft():
+    """Independent implementation of the framing + rectangular window + |rfft_512|^2 / 512 stage: torch.stft.  (stft centres the
+    400-sample window in its 512-sample buffer -- a 56-sample shift that changes only the phase -- and frames the signal it is
+    given, so the pre-emphasised signal is offered with 56 leading zeros and psf's zero padding at the end.)"""
+    import torch
+    from oracle import fbank_oracle as F
+    rng = np.random.RandomState(0)
+    for n in (16000, 16123, 399, 401):
+        sig = rng.randn(n)
+        pre = np.append(sig[0], sig[1:] - 0.97 * sig[:-1])
+        nf = F.num_frames(n)
+        padlen = (nf - 1) * 160 + 400
+        buf = np.concatenate([np.zeros(56), pre, np.zeros(padlen - n + 56)])
+        st = torch.stft(torch.from_numpy(buf), n_fft=512, hop_length=160, win_length=400, window=torch.ones(400, dtype=torch.float64),
+                        center=False, return_complex=True)
+        pspec_t = (st.abs() ** 2 / 512).T.numpy()[:nf]                      # (frames, 257)
+        fb = F.get_filterbanks(80, 512, 16000)
+        want = pspec_t @ fb.T
+        got = F.fbank(sig)
+        assert got.shape == (nf, 80)
+        assert np.allclose(got, np.where(want == 0, np.finfo(float).eps, want), rtol=1e-9, atol=1e-12)
+
+
+def test_mel_scale_matches_torchaudio_htk():
+    """The mel <-> Hz maps (2595 log10(1 + f/700)) and the 82 filter edge frequencies against torchaudio's HTK mel scale; the
+    oracle's FFT-bin edges are psf's floor((nfft + 1) f / sr) of exactly those frequencies, and every triangular filter peaks
+    within one bin of torchaudio's continuous triangle of the same index."""
+    import torch
+    import torchaudio.functional as AF
+    from oracle import fbank_oracle as F
+    hz = np.array([0.0, 100.0, 440.0, 1000.0, 4000.0, 8000.0])
+    m = F.hz2mel(hz)
+    assert np.allclose(m, 2595.0 * np.log10(1 + hz / 700.0)) and np.allclose(F.mel2hz(m), hz)
+    ta = AF.melscale_fbanks(n_freqs=257, f_min=0.0, f_max=8000.0, n_mels=80, sample_rate=16000, norm=None, mel_scale="htk").numpy()  # (257, 80)
+    fb = F.get_filterbanks(80, 512, 16000)                                   # (80, 257)
+    assert fb.shape == ta.T.shape
+    # psf's floor()ed bin edges collapse where the mel spacing is finer than an FFT bin: at nfilt = 80 / nfft = 512 filter 2 is
+    # EMPTY (its three edges fall on bins 1, 2, 2), so that feature is identically eps -- a property of the reference's front-end
+    # the device kernel reproduces
+    empty = [j for j in range(80) if not fb[j].any()]
+    assert empty == [2]
+    live = np.array([j for j in range(80) if j not in empty])
+    pk_o, pk_t = fb.argmax(1), ta.argmax(0)
+    assert np.all(np.abs(pk_o[live] - pk_t[live]) <= 1), (pk_o, pk_t)
+    edges_hz = F.mel2hz(np.linspace(F.hz2mel(0.0), F.hz2mel(8000.0), 82))
+    bins = np.floor((512 + 1) * edges_hz / 16000)
+    for j in live:                                                           # support of filter j = [bin_j, bin_{j+2}]
+        nz = np.nonzero(fb[j])[0]
+        assert nz.min() >= bins[j] and nz.max() <= bins[j + 2]
+    # torchaudio's own edge frequencies (all_freqs where a triangle starts) agree with the oracle's to a fraction of a bin
+    f_axis = np.linspace(0, 8000, 257)
+    starts_t = np.array([f_axis[np.nonzero(ta[:, j])[0].min()] for j in range(80)])
+    assert np.all(np.abs(starts_t - edges_hz[:80]) <= 2 * (8000 / 256))
