@@ -612,7 +612,16 @@ __global__ void conv2d_bwd_data_kernel(const float* __restrict__ dy, const float
         if (wo >= Wo) continue;
         const float* g = dy + (((size_t)b * Ho + ho) * Wo + wo) * Cout;
         const float* wr = w + ((size_t)(a * kw + c) * Cin + ci) * Cout;
-        for (int co = 0; co < Cout; ++co) acc = fmaf(__ldg(g + co), __ldg(wr + co), acc);
+        if ((Cout & 3) == 0) {                       // rows of dy and of w[kh,kw,ci,:] are 16-byte aligned
+          const float4* g4 = reinterpret_cast<const float4*>(g);
+          const float4* w4 = reinterpret_cast<const float4*>(wr);
+          for (int co = 0; co < Cout / 4; ++co) {
+            const float4 gv = __ldg(g4 + co), wv = __ldg(w4 + co);
+            acc = fmaf(gv.x, wv.x, acc); acc = fmaf(gv.y, wv.y, acc); acc = fmaf(gv.z, wv.z, acc); acc = fmaf(gv.w, wv.w, acc);
+          }
+        } else {
+          for (int co = 0; co < Cout; ++co) acc = fmaf(__ldg(g + co), __ldg(wr + co), acc);
+        }
       }
     }
     dx[i] = acc + (beta != 0.f ? beta * dx[i] : 0.f);
@@ -672,6 +681,65 @@ __global__ void __launch_bounds__(256) conv2d_bwd_weight_kernel(const float* __r
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const int ci = ci0 + 2 * ty + i, co = co0 + 2 * tx + j;
+      if (ci < Cin && co < Cout) out[(size_t)ci * Cout + co] = acc[i][j];
+    }
+}
+// The same for layers with >= 64 input and output channels: a 64 x 64 (ci, co) tile, 16 positions per slab, thread (ty, tx) owns
+// a 4 x 4 patch -- 16 FMAs per 8 shared-memory loads instead of 4 per 4.
+__global__ void __launch_bounds__(256) conv2d_bwd_weight64_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ part,
+                                                                  int B, int H, int W, int Cin, int Ho, int Wo, int Cout, int kh, int kw,
+                                                                  int stride, int pad_t, int pad_l) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ float xs[16][68], ds[16][68];
+  const int ct_o = (Cout + 63) / 64, ct_i = (Cin + 63) / 64;
+  int t = blockIdx.x;
+  const int co0 = (t % ct_o) * 64; t /= ct_o;
+  const int ci0 = (t % ct_i) * 64; t /= ct_i;
+  const int c = t % kw, a = t / kw;
+  const long long nw = (long long)kh * kw * Cin * Cout;
+  const long long npos = (long long)B * Ho * Wo;
+  const long long per = (npos + gridDim.y - 1) / gridDim.y;
+  const long long p0 = blockIdx.y * per, p1 = (p0 + per < npos) ? p0 + per : npos;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int lr = threadIdx.x >> 6, lc = threadIdx.x & 63;       // loader role: row lr (+4k) of the 16-position slab, channel lc
+  float acc[4][4] = {};
+  for (long long q0 = p0; q0 < p1; q0 += 16) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = lr + 4 * k;
+      const long long q = q0 + r;
+      float xv = 0.f, dv = 0.f;
+      if (q < p1) {
+        const int wo = (int)(q % Wo);
+        const long long u = q / Wo;
+        const int ho = (int)(u % Ho);
+        const int b = (int)(u / Ho);
+        const int hi = ho * stride + a - pad_t, wi = wo * stride + c - pad_l;
+        if (hi >= 0 && hi < H && wi >= 0 && wi < W && ci0 + lc < Cin) xv = __ldg(x + (((size_t)b * H + hi) * W + wi) * Cin + ci0 + lc);
+        if (co0 + lc < Cout) dv = __ldg(dy + (size_t)q * Cout + co0 + lc);
+      }
+      xs[r][lc] = xv; ds[r][lc] = dv;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int r = 0; r < 16; ++r) {
+      const float4 xv = *reinterpret_cast<const float4*>(&xs[r][4 * ty]);
+      const float4 dv = *reinterpret_cast<const float4*>(&ds[r][4 * tx]);
+      const float xa[4] = {xv.x, xv.y, xv.z, xv.w}, da[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xa[i], da[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* out = part + (size_t)blockIdx.y * nw + (size_t)(a * kw + c) * Cin * Cout;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ci = ci0 + 4 * ty + i, co = co0 + 4 * tx + j;
       if (ci < Cin && co < Cout) out[(size_t)ci * Cout + co] = acc[i][j];
     }
 }
@@ -872,6 +940,12 @@ int sar_conv2d_bwd_weight(const float* x, const float* dy, float* partial, int c
   SAR_REQUIRE(x && dy && partial, SAR_ERR_BAD_ARG, "sar_conv2d_bwd_weight: null pointer");
   SAR_REQUIRE(chunks > 0 && chunks <= 65535 && B > 0 && H > 0 && W > 0 && Cin > 0 && Ho > 0 && Wo > 0 && Cout > 0 && kh > 0 && kw > 0 && stride > 0,
               SAR_ERR_BAD_ARG, "sar_conv2d_bwd_weight: bad dimension");
+  if (Cin >= 64 && Cout >= 64) {
+    const long long tiles = (long long)kh * kw * ((Cin + 63) / 64) * ((Cout + 63) / 64);
+    launch_k(conv2d_bwd_weight64_kernel, dim3((unsigned)tiles, chunks), dim3(256), 0, (cudaStream_t)stream, x, dy, partial, B, H, W, Cin, Ho, Wo,
+             Cout, kh, kw, stride, pad_t, pad_l);
+    return check_launch("sar_conv2d_bwd_weight");
+  }
   const long long tiles = (long long)kh * kw * ((Cin + 31) / 32) * ((Cout + 31) / 32);
   SAR_REQUIRE(tiles < (1ll << 31), SAR_ERR_UNSUPPORTED, "sar_conv2d_bwd_weight: too many tiles");
   launch_k(conv2d_bwd_weight_kernel, dim3((unsigned)tiles, chunks), dim3(256), 0, (cudaStream_t)stream, x, dy, partial, B, H, W, Cin, Ho, Wo,

@@ -522,7 +522,8 @@ def test_train_on_batch_fifth_slice_lowers_both_losses(cuda_device):
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout,k,stride", [(2, 9, 8, 5, 7, 3, 1), (2, 9, 8, 5, 7, 3, 2), (3, 10, 7, 4, 6, 3, 2), (2, 8, 6, 8, 16, 1, 2),
-                                                     (2, 20, 16, 1, 6, 7, 2), (1, 5, 4, 32, 32, 3, 1)])
+                                                     (2, 20, 16, 1, 6, 7, 2), (1, 5, 4, 32, 32, 3, 1), (3, 9, 5, 64, 128, 3, 1),
+                                                     (2, 11, 6, 70, 65, 3, 2), (2, 8, 6, 128, 256, 1, 2)])
 def test_conv_backward_kernels_match_autograd(cuda_device, B, H, W, Cin, Cout, k, stride):
     """sar_conv2d_bwd_data / sar_conv2d_bwd_weight vs float64 autograd of the oracle's TF-SAME (k > 1) / VALID (1x1 shortcut)
     Conv2D: strides 1 and 2, even and odd sizes (asymmetric SAME pads), the 7x7 stem, accumulation into dx (beta = 1)."""
