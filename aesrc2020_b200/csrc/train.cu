@@ -23,7 +23,10 @@
 namespace sar {
 
 // ------------------------------------------------------------------ small fp32 GEMM, row-major, optional transposes
-constexpr int TG = 64, TGK = 16;
+constexpr int TG = 64, TGK = 32;
+// 64 x 64 tile per CTA, 32 k-values per round; the next round's global loads are issued (into registers) before the current
+// round's FMAs, so the ~1 us round trip overlaps the math -- the GRU's per-step products (K = 256 / 768 on 4-12 CTAs) are
+// round-trip bound: 16-value rounds without prefetch cost 2.3 us each.
 __global__ void __launch_bounds__(256) gemm_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
                                                     int M, int N, int K, int ta, int tb, float alpha, float beta) {
   pdl_wait();
@@ -31,20 +34,41 @@ __global__ void __launch_bounds__(256) gemm_kernel(const float* __restrict__ A, 
   __shared__ float As[TGK][TG + 4], Bs[TGK][TG + 4];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int m0 = blockIdx.y * TG, n0 = blockIdx.x * TG;
-  float acc[4][4] = {};
-  for (int k0 = 0; k0 < K; k0 += TGK) {
-    for (int i = threadIdx.x; i < TG * TGK; i += 256) {
+  constexpr int PER = TG * TGK / 256;                       // elements of each operand tile per thread (8)
+  float ra[PER], rb[PER];
+  auto load_tile = [&](int k0) {
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const int i = threadIdx.x + 256 * j;
       // A tile: element (m, k) = ta ? A[k][m] : A[m][k]; index so that consecutive threads read consecutive addresses
       int m, k;
       if (ta) { m = i % TG; k = i / TG; } else { k = i % TGK; m = i / TGK; }
       const int gm = m0 + m, gk = k0 + k;
-      As[k][m] = (gm < M && gk < K) ? (ta ? A[(size_t)gk * M + gm] : A[(size_t)gm * K + gk]) : 0.f;
+      ra[j] = (gm < M && gk < K) ? (ta ? A[(size_t)gk * M + gm] : A[(size_t)gm * K + gk]) : 0.f;
       int n, kb;
       if (tb) { kb = i % TGK; n = i / TGK; } else { n = i % TG; kb = i / TG; }
       const int gn = n0 + n, gkb = k0 + kb;
-      Bs[kb][n] = (gn < N && gkb < K) ? (tb ? B[(size_t)gn * K + gkb] : B[(size_t)gkb * N + gn]) : 0.f;
+      rb[j] = (gn < N && gkb < K) ? (tb ? B[(size_t)gn * K + gkb] : B[(size_t)gkb * N + gn]) : 0.f;
     }
+  };
+  auto store_tile = [&]() {
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const int i = threadIdx.x + 256 * j;
+      int m, k;
+      if (ta) { m = i % TG; k = i / TG; } else { k = i % TGK; m = i / TGK; }
+      As[k][m] = ra[j];
+      int n, kb;
+      if (tb) { kb = i % TGK; n = i / TGK; } else { n = i % TG; kb = i / TG; }
+      Bs[kb][n] = rb[j];
+    }
+  };
+  float acc[4][4] = {};
+  load_tile(0);
+  for (int k0 = 0; k0 < K; k0 += TGK) {
+    store_tile();
     __syncthreads();
+    if (k0 + TGK < K) load_tile(k0 + TGK);
 #pragma unroll
     for (int k = 0; k < TGK; ++k) {
       float a[4], b[4];
