@@ -83,6 +83,7 @@ SIGNATURES = {
     "sar_l2norm_bwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_f, C.c_void_p]),
     "sar_head_grad_fwd": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_f, c_f, c_f, c_f, c_f, c_fp, c_fp, c_fp, c_int, C.c_void_p]),
     "sar_adam_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_ll, c_f, c_f, c_f, c_f, c_f, C.c_void_p]),
+    "sar_adam_dev_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_ll, c_fp, c_f, c_f, c_f, c_f, C.c_void_p]),
     "sar_unit_norm_fwd": (c_int, [c_fp, c_int, c_int, C.c_void_p]),
     "sar_vlad_train_fwd": (c_int, [c_fp] * 7 + [c_int] * 5 + [C.c_void_p]),
     "sar_vlad_train_bwd": (c_int, [c_fp] * 8 + [c_int] * 5 + [C.c_void_p]),

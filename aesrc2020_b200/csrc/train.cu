@@ -405,6 +405,21 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     p[i] -= lr_t * mi / (sqrtf(vi) + eps);
   }
 }
+// the same with lr_t read from device memory: a captured CUDA graph of the training step is replayed with a new step size
+// (Adam's bias correction and Keras' decay change lr_t every iteration; a kernel ARGUMENT would be frozen into the graph)
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                long long n, const float* __restrict__ lr_t_p, float b1, float b2, float eps, float l2) {
+  pdl_wait();
+  pdl_trigger();
+  const float lr_t = *lr_t_p;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float ge = fmaf(2.f * l2, p[i], g[i]);
+    const float mi = b1 * m[i] + (1.f - b1) * ge;
+    const float vi = b2 * v[i] + (1.f - b2) * ge * ge;
+    m[i] = mi; v[i] = vi;
+    p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
 // keras.constraints.unit_norm(axis=0): W[:, j] /= (1e-7 + ||W[:, j]||), W (D, n)
 __global__ void unit_norm_kernel(float* __restrict__ w, int D, int n) {
   pdl_wait();
@@ -1036,6 +1051,14 @@ int sar_adam_fwd(float* p, const float* g, float* m, float* v, long long n, floa
   SAR_REQUIRE(p && g && m && v && n > 0, SAR_ERR_BAD_ARG, "sar_adam_fwd: bad argument");
   launch_k(adam_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, n, lr_t, beta1, beta2, eps, l2);
   return check_launch("sar_adam_fwd");
+}
+
+int sar_adam_dev_fwd(float* p, const float* g, float* m, float* v, long long n, const float* lr_t, float beta1, float beta2, float eps,
+                     float l2, void* stream) {
+  using namespace sar;
+  SAR_REQUIRE(p && g && m && v && lr_t && n > 0, SAR_ERR_BAD_ARG, "sar_adam_dev_fwd: bad argument");
+  launch_k(adam_dev_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, n, lr_t, beta1, beta2, eps, l2);
+  return check_launch("sar_adam_dev_fwd");
 }
 
 int sar_unit_norm_fwd(float* w, int D, int n, void* stream) {

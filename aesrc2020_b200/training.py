@@ -275,6 +275,13 @@ def adam_step(p, g, m, v, lr_t, l2=0.0):
     ops._count(1)
 
 
+def adam_step_dev(p, g, m, v, lr_dev, l2=0.0):
+    """adam_step with lr_t in a one-element device tensor (graph replay, see HeadTrainer.train_on_batch)."""
+    check(_shim.lib().sar_adam_dev_fwd(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), ptr(lr_dev), ADAM_B1, ADAM_B2, ADAM_EPS, float(l2),
+                                       stream_ptr()), "sar_adam_dev_fwd")
+    ops._count(1)
+
+
 def unit_norm(w):
     check(_shim.lib().sar_unit_norm_fwd(ptr(w), w.shape[0], w.shape[1], stream_ptr()), "sar_unit_norm_fwd")
     ops._count(1)
@@ -375,6 +382,16 @@ class HeadTrainer:
         self.m = {k: torch.zeros_like(self.p[k]) for k in self.keys}
         self.v = {k: torch.zeros_like(self.p[k]) for k in self.keys}
         self.last_grads: Dict[str, torch.Tensor] = {}
+        # CUDA-graph replay of the step (train_on_batch): after two eager steps of a batch shape the whole step -- forward,
+        # backward, Adam -- is captured once and replayed; lr_t travels through a device scalar.  Single process only (the
+        # gradient all-reduce stays eager); SAR_TRAIN_GRAPH=0 disables.
+        import os as _os
+        self.use_graph = _os.environ.get("SAR_TRAIN_GRAPH", "1") != "0"
+        self._graphs: Dict = {}
+        self._eager_count: Dict = {}
+        self._lr_dev = None            # set while a step is being captured
+        self._defer = False            # capture: no host synchronisation inside the step
+        self._last = None              # (losses, loss_ctc, status) device tensors of the last step
 
     # ---- frozen encoder: x_data -> integ (B, K*D | D | 2u), or (train_pool) the descriptors (B,S,D) in front of vlad()
     def encode(self, x) -> torch.Tensor:
@@ -394,7 +411,7 @@ class HeadTrainer:
         p, cfg = self.p, self.cfg
         B = integ.shape[0]
         g_ctc: Dict[str, torch.Tensor] = {}
-        g_crnn_ctc = loss_ctc = None
+        g_crnn_ctc = loss_ctc = ctc_status = None
         pool = ds = rn = None
         res_shape = None
         if self.train_resnet:                    # ResNet in training mode; CNN2SEQ (model.py:252): (B,H,W,C) -> (B, H*W, C)
@@ -426,7 +443,8 @@ class HeadTrainer:
                 logits = bias_act(gemm(a2, p["ctc_pred/kernel"]), p["ctc_pred/bias"])
                 Cb = logits.shape[-1]
                 loss_b, g_log, status = ctc_grad(logits.view(B, Sr, Cb), ctc[0], ctc[1], ctc[2], self.w_ctc / B)
-                if bool((status != 0).any()):
+                ctc_status = status
+                if not self._defer and bool((status != 0).any()):
                     raise _shim.SarnetError("CTC: infeasible or out-of-range label sequence in batch")
                 loss_ctc = loss_b
                 g_log = g_log.view(B * Sr, Cb)
@@ -540,17 +558,29 @@ class HeadTrainer:
         self._all_reduce(g)
         self.last_grads = g
         # Adam (the l2 regulariser's gradient 2 * 1e-4 * w is added inside the kernel), then the kernel constraint
-        lr_t = adam_lr_t(self.lr, self.iterations)
-        for k in self.keys:
-            adam_step(p[k], g[k], self.m[k], self.v[k], lr_t, l2=L2_REG if k in self.l2 else 0.0)
+        if self._lr_dev is not None:               # being captured: the step size is read from device memory at replay time
+            for k in self.keys:
+                adam_step_dev(p[k], g[k], self.m[k], self.v[k], self._lr_dev, l2=L2_REG if k in self.l2 else 0.0)
+        else:
+            lr_t = adam_lr_t(self.lr, self.iterations)
+            for k in self.keys:
+                adam_step(p[k], g[k], self.m[k], self.v[k], lr_t, l2=L2_REG if k in self.l2 else 0.0)
         if kind == "circleloss":
             unit_norm(p[self.disc_key])
         self._sync_stats()
+        self._last = (losses, loss_ctc, ctc_status)
+        if self._defer:
+            return {}
         self.iterations += 1
+        return self._report()
+
+    def _report(self) -> Dict[str, float]:
+        """Host copy of the last step's losses (the step's only synchronisation)."""
+        losses, loss_ctc, _ = self._last
         lm = losses.mean(0).tolist()
         out = {"loss_accent": lm[0]}
         total = self.w_acc * lm[0]
-        if kind:
+        if self.head_kind:
             out["loss_disc"] = lm[1]
             total += self.w_disc * lm[1]
         if loss_ctc is not None:
@@ -558,6 +588,50 @@ class HeadTrainer:
             total += self.w_ctc * out["loss_ctc"]
         out["loss"] = total                        # data terms (Keras adds the regulariser terms to the reported total)
         return out
+
+    # ---- the step as a replayed CUDA graph
+    def _distributed(self) -> bool:
+        import torch.distributed as dist
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def step_graphed(self, feats: torch.Tensor, onehot: torch.Tensor, ctc=None) -> Dict[str, float]:
+        """step_on_features through a CUDA graph: the first two steps of a batch shape run eagerly (they also raise every
+        kernel's shared-memory limit and fill the allocator), the third is captured -- ~2 k launches become one replay.
+        Inputs are copied into the graph's static buffers, lr_t into its device scalar.  Bitwise the eager step (tested)."""
+        if not self.use_graph or self._distributed():
+            return self.step_on_features(feats, onehot, ctc)
+        key = (tuple(feats.shape), tuple(onehot.shape), None if ctc is None else tuple(tuple(c.shape) for c in ctc))
+        st = self._graphs.get(key)
+        if st is None:
+            n = self._eager_count.get(key, 0)
+            if n < 2:
+                self._eager_count[key] = n + 1
+                return self.step_on_features(feats, onehot, ctc)
+            st = {"feats": feats.clone(), "onehot": onehot.clone(), "ctc": None if ctc is None else tuple(c.clone() for c in ctc),
+                  "lr": torch.zeros((1,), device=feats.device, dtype=torch.float32), "graph": torch.cuda.CUDAGraph()}
+            torch.cuda.synchronize()
+            self._lr_dev, self._defer = st["lr"], True
+            try:
+                with torch.cuda.graph(st["graph"]):
+                    self.step_on_features(st["feats"], st["onehot"], st["ctc"])
+            finally:
+                self._lr_dev, self._defer = None, False
+            st["last"], st["grads"] = self._last, self.last_grads
+            self._graphs[key] = st
+        st["feats"].copy_(feats)
+        st["onehot"].copy_(onehot)
+        if ctc is not None:
+            for d, c in zip(st["ctc"], ctc):
+                d.copy_(c)
+        st["lr"].fill_(adam_lr_t(self.lr, self.iterations))
+        st["graph"].replay()
+        self.iterations += 1
+        self._last, self.last_grads = st["last"], st["grads"]
+        status = self._last[2]
+        if status is not None and bool((status != 0).any()):
+            raise _shim.SarnetError("CTC: infeasible or out-of-range label sequence in batch (the step was applied with a zero "
+                                    "CTC gradient for the rejected utterances)")
+        return self._report()
 
     def _sync_stats(self):
         """Every replica updates the BN moving averages with ITS shard's statistics; the mean over the replicas keeps the ranks'
@@ -598,7 +672,7 @@ class HeadTrainer:
         ctc = None
         if self.train_ctc:
             ctc = tuple(self.model._to_device(k, xd[k]).contiguous() for k in ("x_ctc_label", "x_ctc_in_len", "x_ctc_out_len"))
-        return self.step_on_features(self.encode(xd), onehot, ctc)
+        return self.step_graphed(self.encode(xd), onehot, ctc)
 
     def fit_generator(self, generator, steps_per_epoch: int, epochs: int = 1, verbose: int = 0):
         """train.py:38-44 shape: `epochs` x `steps_per_epoch` batches of (inputs, targets) from the generator."""

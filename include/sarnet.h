@@ -360,6 +360,10 @@ int sar_head_grad_fwd(const float* z_accent, const float* c_disc, const float* o
  * p -= lr_t m / (sqrt(v) + eps).  lr_t = lr / (1 + decay * iterations) * sqrt(1 - beta2^t) / (1 - beta1^t) is the caller's. */
 int sar_adam_fwd(float* p, const float* g, float* m, float* v, long long n, float lr_t, float beta1, float beta2, float eps, float l2,
                  void* stream);
+/* The same update with the step size read from DEVICE memory (`lr_t`, one float): lets a captured CUDA graph of the whole
+ * training step be replayed while lr_t changes every iteration (bias correction, decay). */
+int sar_adam_dev_fwd(float* p, const float* g, float* m, float* v, long long n, const float* lr_t, float beta1, float beta2, float eps,
+                     float l2, void* stream);
 /* keras.constraints.unit_norm(axis=0) on W (D, n): the Circle-Loss head's kernel constraint (model.py:163). */
 int sar_unit_norm_fwd(float* w, int D, int n, void* stream);
 /* NetVLAD / GhostVLAD pooling in TRAINING mode (model.py:82-109: the 1x1 assignment Conv2D with l2(1e-4) kernel / bias

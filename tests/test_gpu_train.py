@@ -684,3 +684,33 @@ def test_fit_generator_mirrors_train_py(cuda_device, tmp_path):
     for g, w in zip(got, want):
         g, w = (g.cpu().numpy() if hasattr(g, "cpu") else g), (w.cpu().numpy() if hasattr(w, "cpu") else w)
         assert np.array_equal(g, w)
+
+
+@pytest.mark.parametrize("flags", [dict(train_ds=True), dict(train_resnet=True, train_ctc=True)])
+def test_graph_replay_of_the_training_step_is_bitwise_the_eager_step(cuda_device, flags):
+    """train_on_batch captures the step (forward, backward, Adam with lr_t from device memory) as a CUDA graph after two
+    eager steps and replays it: over 6 steps on DIFFERENT batches the losses and every parameter / Adam moment / BN moving
+    average are bitwise those of a trainer that never leaves eager mode."""
+    import warnings
+    from aesrc2020_b200 import model as mdl, training as T, utils as us
+    kw = dict(ctc_enable=True, disc_enable=True, res_type="res18", res_filters=8, mto="gvlad", vlad_clusters=8, ghost_clusters=2,
+              metric_loss="arcface", margin=0.3, bpe_classes=40, max_ctc_len=4)
+    runs = []
+    for use_graph in (False, True):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            model, _ = mdl.SAR_Net((100, 80, 1), seed=21, **kw)
+            tr = T.HeadTrainer(model, lr=0.004, **flags)
+            tr.use_graph = use_graph
+            hist = []
+            for i in range(6):
+                x, y = us.synthetic_batch(model.config, 6, seed=400 + i)
+                hist.append(tr.train_on_batch(x, y))
+        assert (len(tr._graphs) == 1) == use_graph and tr.iterations == 6
+        runs.append((hist, {k: v.clone() for k, v in tr.p.items()}, {k: v.clone() for k, v in tr.m.items()}))
+    (h0, p0, m0), (h1, p1, m1) = runs
+    assert h0 == h1, (h0, h1)
+    for k in p0:
+        assert torch.equal(p0[k], p1[k]), k
+    for k in m0:
+        assert torch.equal(m0[k], m1[k]), k
