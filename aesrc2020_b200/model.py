@@ -628,9 +628,9 @@ class SARModel:
         BatchNormalization, CRNN, accent branch, and the CTC branch when ctc_enable), Adam(self.lr, decay=2e-4)."""
         if self._trainer is None:
             cfg = self.config
-            if not cfg.ar_enable or cfg.mto not in ("vlad", "gvlad") or cfg.bn_dim:
-                raise SarnetError("training is built for ar_enable=True with mto='vlad' | 'gvlad' and bn_dim=0 "
-                                  "(got ar_enable=%s, mto=%r, bn_dim=%s)" % (cfg.ar_enable, cfg.mto, cfg.bn_dim))
+            if not cfg.ar_enable or cfg.bn_dim:
+                raise SarnetError("training is built for ar_enable=True and bn_dim=0 (got ar_enable=%s, bn_dim=%s)"
+                                  % (cfg.ar_enable, cfg.bn_dim))
             from .training import HeadTrainer
             self._trainer = HeadTrainer(self, lr=self.lr, group=group, train_resnet=True, train_ctc=bool(cfg.ctc_enable))
         return self._trainer

@@ -205,7 +205,8 @@ def ln_train_bwd(y, gamma, g_z, tanh_in: bool):
 
 def gru_dir_fwd(x_rows, B: int, S: int, W, U, bias, reverse: bool, out, off: int):
     """One direction of CuDNNGRU in training mode (model.py:44-50): the input projection is one GEMM, every time step one
-    GEMM (h_prev U) + `sar_gru_gate_fwd`.  Writes h_t into out[:, t, off:off+u]; returns what the backward needs."""
+    GEMM (h_prev U) + `sar_gru_gate_fwd`.  Writes h_t into out[:, t, off:off+u] (`out` None: return_sequences=False, the final
+    state is saved["hseq"][S]); returns what the backward needs."""
     u = U.shape[0]
     dev = x_rows.device
     xp = bias_act(gemm(x_rows, W), bias[:3 * u])                              # (B*S, 3u) = x W + b_i
@@ -217,27 +218,29 @@ def gru_dir_fwd(x_rows, B: int, S: int, W, U, bias, reverse: bool, out, off: int
         t = S - 1 - k if reverse else k
         hu = gemm(hseq[k], U)
         check(lib.sar_gru_gate_fwd(ptr(xp), ptr(hu), ptr(b_r), ptr(hseq[k]), ptr(z[k]), ptr(r[k]), ptr(hh[k]), ptr(hph[k]),
-                                   ptr(hseq[k + 1]), ptr(out), B, S, u, t, out.shape[-1], off, stream_ptr()), "sar_gru_gate_fwd")
+                                   ptr(hseq[k + 1]), ptr(out), B, S, u, t, out.shape[-1] if out is not None else 0, off, stream_ptr()),
+              "sar_gru_gate_fwd")
     ops._count(S)
     return dict(hseq=hseq, z=z, r=r, hh=hh, hph=hph, x_rows=x_rows, reverse=reverse, off=off)
 
 
-def gru_dir_bwd(g_out, saved, B: int, S: int, W, U, g_x=None):
-    """Back-propagation through time of gru_dir_fwd: g_out (B,S,2u) = d loss / d layer output.  Returns the gradients of
-    (kernel, recurrent_kernel, bias (6u)) and accumulates d loss / d x into g_x (B*S, Din)."""
+def gru_dir_bwd(g_out, saved, B: int, S: int, W, U, g_x=None, dh_last=None):
+    """Back-propagation through time of gru_dir_fwd: g_out (B,S,2u) = d loss / d layer output (None for
+    return_sequences=False), dh_last (B,u) = d loss / d final state.  Returns the gradients of (kernel, recurrent_kernel,
+    bias (6u)) and accumulates d loss / d x into g_x (B*S, Din)."""
     u = U.shape[0]
-    dev = g_out.device
+    dev = saved["hseq"].device
     hseq, reverse, off = saved["hseq"], saved["reverse"], saved["off"]
     d_xp = torch.empty((B * S, 3 * u), device=dev, dtype=torch.float32)
     d_hu = torch.empty((S, B, 3 * u), device=dev, dtype=torch.float32)
     lib = _shim.lib()
-    dh = None
+    dh = dh_last
     for k in range(S - 1, -1, -1):
         t = S - 1 - k if reverse else k
         dh_prev = torch.empty((B, u), device=dev, dtype=torch.float32)
         check(lib.sar_gru_gate_bwd(ptr(g_out), ptr(dh) if dh is not None else None, ptr(saved["z"][k]), ptr(saved["r"][k]),
                                    ptr(saved["hh"][k]), ptr(saved["hph"][k]), ptr(hseq[k]), ptr(d_xp), ptr(d_hu[k]), ptr(dh_prev),
-                                   B, S, u, t, g_out.shape[-1], off, stream_ptr()), "sar_gru_gate_bwd")
+                                   B, S, u, t, g_out.shape[-1] if g_out is not None else 0, off, stream_ptr()), "sar_gru_gate_bwd")
         if k > 0:
             gemm(d_hu[k], U, tb=True, out=dh_prev, beta=1.0)                    # + d_hu U^T
         dh = dh_prev
@@ -320,8 +323,8 @@ class HeadTrainer:
         train_crnn = bool(train_crnn or train_ctc or train_resnet)
         train_ds = bool(train_ds or train_crnn)
         train_pool = bool(train_pool or train_ds)
-        if train_pool and cfg.mto not in ("vlad", "gvlad"):
-            raise ValueError("train_pool needs mto='vlad' or 'gvlad' (got %r)" % cfg.mto)
+        if train_pool and cfg.mto not in ("avg", "bigru", "vlad", "gvlad"):
+            raise ValueError("train_pool needs mto in avg | bigru | vlad | gvlad (got %r)" % cfg.mto)
         self.model, self.cfg, self.lr, self.group = model, cfg, float(lr), group
         self.train_pool = bool(train_pool)
         self.train_ds = bool(train_ds)
@@ -338,9 +341,13 @@ class HeadTrainer:
         self.pool_keys: List[str] = []
         if self.train_pool:
             pre = cfg.mto
-            self.pool_keys = [pre + "_center_assignment/kernel", pre + "_center_assignment/bias", pre + "_pool/centers"]
-            self.keys += self.pool_keys
-            self.l2 |= set(self.pool_keys[:2])           # l2(1e-4) on the assignment kernel and bias; none on the centers
+            if pre in ("vlad", "gvlad"):
+                self.pool_keys = [pre + "_center_assignment/kernel", pre + "_center_assignment/bias", pre + "_pool/centers"]
+                self.l2 |= set(self.pool_keys[:2])       # l2(1e-4) on the assignment kernel and bias; none on the centers
+            elif pre == "bigru":                         # integration(): BIGRU(hidden_dim, seq=False, name="AR_MERGE"), model.py:118-123
+                self.pool_keys = ["AR_MERGE/%s/%s" % (d, w) for d in ("forward", "backward") for w in ("kernel", "recurrent_kernel", "bias")]
+                self.l2 |= {k for k in self.pool_keys if not k.endswith("recurrent_kernel")}
+            self.keys += self.pool_keys                  # (avg: GlobalAveragePooling1D has no weights)
         self.ds_keys: List[str] = []
         if self.train_ds:
             self.ds_keys = ["AR_DS/kernel", "AR_DS/bias", "AR_DS_LN/gamma", "AR_DS_LN/beta"]
@@ -387,6 +394,7 @@ class HeadTrainer:
         # gradient all-reduce stays eager); SAR_TRAIN_GRAPH=0 disables.
         import os as _os
         self.use_graph = _os.environ.get("SAR_TRAIN_GRAPH", "1") != "0"
+        self._avg_E: Dict = {}          # mto='avg': the (B*S, B) averaging matrices
         self._graphs: Dict = {}
         self._eager_count: Dict = {}
         self._lr_dev = None            # set while a step is being captured
@@ -467,7 +475,7 @@ class HeadTrainer:
             zds = ops.layernorm(yds, p["AR_DS_LN/gamma"], p["AR_DS_LN/beta"])
             ds = (crnn.view(B * S0, C0), yds)
             integ = zds.view(B, S0, -1)
-        if self.train_pool:                      # vlad() in training mode: integ = l2norm_k(A^T x - (sum A) c), flattened
+        if self.train_pool and cfg.mto in ("vlad", "gvlad"):   # vlad() in training mode: integ = l2norm_k(A^T x - (sum A) c), flattened
             feat = integ
             _, S, D = feat.shape
             K, G = cfg.vlad_clusters, (cfg.ghost_clusters if cfg.mto == "gvlad" else 0)
@@ -475,7 +483,26 @@ class HeadTrainer:
             A, R, asum = vlad_train_fwd(feat, p[kw_].view(D, K + G), p[kb_], p[kc_], K, G)
             V, rinv = l2norm_fwd(R.view(B * K, D), 1)
             integ = V.view(B, K * D)
-            pool = (feat, A, asum, V, rinv, S, D, K, G)
+            pool = ("vlad", feat, A, asum, V, rinv, S, D, K, G)
+        elif self.train_pool and cfg.mto == "bigru":           # AR_MERGE: Bi-GRU with return_sequences=False (the reference's default mto)
+            feat = integ
+            _, S, D = feat.shape
+            rows = feat.reshape(B * S, D)
+            svm = [gru_dir_fwd(rows, B, S, p["AR_MERGE/%s/kernel" % d], p["AR_MERGE/%s/recurrent_kernel" % d], p["AR_MERGE/%s/bias" % d],
+                               d == "backward", None, 0) for d in ("forward", "backward")]
+            integ = torch.cat([s_["hseq"][S] for s_ in svm], dim=1)             # concat(final forward state, final backward state)
+            pool = ("bigru", svm, S, D, svm[0]["hseq"].shape[-1])
+        elif self.train_pool:                                   # avg: GlobalAveragePooling1D as a GEMM with the (B*S, B) averaging matrix
+            feat = integ
+            _, S, D = feat.shape
+            E = self._avg_E.get((B, S))               # built once per shape, in an eager step (never inside a graph capture)
+            if E is None:
+                E = torch.zeros((B, S, B), device=feat.device, dtype=torch.float32)
+                ib = torch.arange(B, device=feat.device)
+                E[ib, :, ib] = 1.0 / S
+                E = self._avg_E[(B, S)] = E.view(B * S, B)
+            integ = gemm(E, feat.reshape(B * S, D), ta=True)
+            pool = ("avg", E, S, D)
         # forward, training mode
         x1, m1, i1 = bn_train_fwd(integ, p["AR_BN1/gamma"], p["AR_BN1/beta"], p["AR_BN1/moving_mean"], p["AR_BN1/moving_variance"])
         e0 = bias_act(gemm(x1, p["AR_EMBEDDING/kernel"]), p["AR_EMBEDDING/bias"])
@@ -517,12 +544,31 @@ class HeadTrainer:
         g_x1 = gemm(g_e0, p["AR_EMBEDDING/kernel"], tb=True)
         g_integ, g["AR_BN1/gamma"], g["AR_BN1/beta"] = bn_train_bwd(integ, g_x1, p["AR_BN1/gamma"], m1, i1, want_dx=pool is not None)
         if pool is not None:
-            feat, A, asum, V, rinv, S, D, K, G = pool
-            kw_, kb_, kc_ = self.pool_keys
-            gR = l2norm_bwd(V, rinv, g_integ.view(B * K, D), 1)                       # (B*K, D) = d loss / d R
+            g_feat = None
+            if pool[0] == "vlad":
+                _, feat, A, asum, V, rinv, S, D, K, G = pool
+                kw_, kb_, kc_ = self.pool_keys
+                gR = l2norm_bwd(V, rinv, g_integ.view(B * K, D), 1)                   # (B*K, D) = d loss / d R
+                if ds is not None:
+                    g_scores, gc_part, g_feat = vlad_train_bwd(feat, A, p[kc_], gR, asum, K, G, want_gx=True)
+                    gemm(g_scores.view(B * S, K + G), p[kw_].view(D, K + G), tb=True, out=g_feat.view(B * S, D), beta=1.0)
+                else:
+                    g_scores, gc_part = vlad_train_bwd(feat, A, p[kc_], gR, asum, K, G)
+                g[kw_] = gemm(feat.view(B * S, D), g_scores.view(B * S, K + G), ta=True).view_as(p[kw_])
+                g[kb_] = colsum(g_scores.view(B * S, K + G))
+                gc = torch.zeros_like(p[kc_])                                         # ghost centers: no gradient
+                gc[:K] = colsum(gc_part.view(B, K * D)).view(K, D)
+                g[kc_] = gc
+            elif pool[0] == "bigru":
+                _, svm, S, D, um = pool
+                for i, (d, s_) in enumerate(zip(("forward", "backward"), svm)):
+                    gW, gU, gb, g_feat = gru_dir_bwd(None, s_, B, S, p["AR_MERGE/%s/kernel" % d], p["AR_MERGE/%s/recurrent_kernel" % d],
+                                                     g_x=g_feat, dh_last=g_integ[:, i * um:(i + 1) * um].contiguous())
+                    g["AR_MERGE/%s/kernel" % d], g["AR_MERGE/%s/recurrent_kernel" % d], g["AR_MERGE/%s/bias" % d] = gW, gU, gb
+            else:
+                _, E, S, D = pool
+                g_feat = gemm(E, g_integ)                                             # every frame gets 1/S of its utterance's gradient
             if ds is not None:
-                g_scores, gc_part, g_feat = vlad_train_bwd(feat, A, p[kc_], gR, asum, K, G, want_gx=True)
-                gemm(g_scores.view(B * S, K + G), p[kw_].view(D, K + G), tb=True, out=g_feat.view(B * S, D), beta=1.0)
                 x_ds, yds = ds
                 g_pre, gzx = ln_train_bwd(yds, p["AR_DS_LN/gamma"], g_feat.view(B * S, D), tanh_in=True)
                 g["AR_DS_LN/gamma"], g["AR_DS_LN/beta"] = colsum(gzx), colsum(g_feat.view(B * S, D))
@@ -547,13 +593,6 @@ class HeadTrainer:
                     if res_shape is not None:    # ... and through the whole ResNet
                         g_x0 = gemm(g_pl, p["CNN_LIN/kernel"], tb=True)
                         g.update(self.resnet_tr.backward(g_x0.view(res_shape)))
-            else:
-                g_scores, gc_part = vlad_train_bwd(feat, A, p[kc_], gR, asum, K, G)
-            g[kw_] = gemm(feat.view(B * S, D), g_scores.view(B * S, K + G), ta=True).view_as(p[kw_])
-            g[kb_] = colsum(g_scores.view(B * S, K + G))
-            gc = torch.zeros_like(p[kc_])                                             # ghost centers: no gradient
-            gc[:K] = colsum(gc_part.view(B, K * D)).view(K, D)
-            g[kc_] = gc
         g.update(g_ctc)
         self._all_reduce(g)
         self.last_grads = g

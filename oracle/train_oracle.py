@@ -83,13 +83,26 @@ def head_loss(p: Dict[str, torch.Tensor], integ: torch.Tensor, onehot: torch.Ten
 
 
 # ---- second slice: the NetVLAD / GhostVLAD pooling layer is trained together with the head (frozen encoder below it)
+MERGE_KEYS = ["AR_MERGE/%s/%s" % (d, w) for d in ("forward", "backward") for w in ("kernel", "recurrent_kernel", "bias")]
+
+
 def pool_keys(mto: str):
-    """Trainable weights of vlad() (model.py:82-109): the 1x1 assignment Conv2D and VladPooling's centers (VLAD.py:17-20)."""
+    """Trainable weights of integration() (model.py:118-139): vlad / gvlad -- the 1x1 assignment Conv2D and VladPooling's centers
+    (model.py:82-109, VLAD.py:17-20); bigru -- the AR_MERGE Bi-GRU (return_sequences=False); avg -- none."""
+    if mto == "bigru":
+        return list(MERGE_KEYS)
+    if mto == "avg":
+        return []
     return [mto + "_center_assignment/kernel", mto + "_center_assignment/bias", mto + "_pool/centers"]
 
 
 def pool_l2_keys(mto: str):
-    # kernel_regularizer = bias_regularizer = l2(1e-4) on the assignment Conv2D (model.py:87-95); the centers carry none
+    # vlad: kernel_regularizer = bias_regularizer = l2(1e-4) on the assignment Conv2D (model.py:87-95), the centers carry none;
+    # bigru: BIGRU's kernel and bias regularisers (model.py:44-50), none on the recurrent kernel
+    if mto == "bigru":
+        return [k for k in MERGE_KEYS if not k.endswith("recurrent_kernel")]
+    if mto == "avg":
+        return []
     return [mto + "_center_assignment/kernel", mto + "_center_assignment/bias"]
 
 

@@ -714,3 +714,50 @@ def test_graph_replay_of_the_training_step_is_bitwise_the_eager_step(cuda_device
         assert torch.equal(p0[k], p1[k]), k
     for k in m0:
         assert torch.equal(m0[k], m1[k]), k
+
+
+@pytest.mark.parametrize("mto", ["bigru", "avg"])
+def test_reference_default_integration_trains(cuda_device, mto):
+    """train.py's own defaults: MANY_TO_ONE = 'bigru' (AR_MERGE Bi-GRU, final states), METRIC_LOSS = 'softmax', CTC + accent +
+    disc -- and 'avg'.  One step of HeadTrainer(train_ds=True) on CRNN_LN features vs the float64 autograd oracle (every gradient),
+    then the whole model (train_resnet + train_ctc) through train_on_batch incl. the graph replay: the loss falls."""
+    import warnings
+    from aesrc2020_b200 import model as mdl, training as T, utils as us
+    kw = dict(ctc_enable=True, disc_enable=True, res_type="res18", res_filters=8, mto=mto, metric_loss="softmax", margin=0.3,
+              bpe_classes=40, max_ctc_len=4)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model, _ = mdl.SAR_Net((100, 80, 1), seed=5, **kw)
+    rng = np.random.RandomState(3)
+    for k in list(model.weights):
+        if k.endswith("/bias") or k.endswith("/beta"):
+            model.weights[k] = (model.weights[k] + rng.randn(*model.weights[k].shape) * 0.05).astype(np.float32)
+    params = {k: np.asarray(v, np.float32).astype(np.float64) for k, v in model.weights.items()}
+    tr = T.HeadTrainer(model, lr=0.01, train_ds=True)
+    assert set(TO.pool_keys(mto)) <= set(tr.keys)
+    B, S = 6, 9
+    lab = rng.randint(0, 8, B)
+    crnn = (rng.randn(B, S, 512) + (np.eye(8)[lab] @ rng.randn(8, 512))[:, None, :] * 0.5).astype(np.float32)
+    onehot = np.eye(8, dtype=np.float32)[lab]
+    pool = dict(mto=mto, vlad_clusters=0, ghost_clusters=0, train_ds=True)
+    l2k = set(TO.l2_keys(True, "softmax")) | set(TO.pool_l2_keys(mto)) | {"AR_DS/kernel", "AR_DS/bias"}
+    _, _, l_or, g_or = TO.train_step(dict(params), {}, crnn, onehot, lr=0.01, iterations=0, disc_enable=True, metric_loss="softmax",
+                                     margin=0.3, w_accent=tr.w_acc, w_disc=tr.w_disc, pool=pool)
+    got = tr.step_on_features(dev(crnn), dev(onehot))
+    assert abs(got["loss_disc"] - l_or["loss_disc"]) < 2e-4 * max(1, abs(l_or["loss_disc"]))
+    for k in tr.keys:
+        # zero-gradient keys (a per-channel constant in front of a batch-statistic BN): AR_BN1/beta, AR_EMBEDDING/bias, and with
+        # average pooling AR_DS_LN/beta too (it shifts every frame, hence the mean, by the same vector -- AR_BN1 removes it)
+        if k in ("AR_BN1/beta", "AR_EMBEDDING/bias") or (mto == "avg" and k == "AR_DS_LN/beta"):
+            continue
+        want = g_or[k] - (2 * TO.L2_REG * params[k] if k in l2k else 0.0)
+        got_k = tr.last_grads[k].cpu().numpy().astype(np.float64)
+        err = float(np.max(np.abs(got_k - want)) / max(np.max(np.abs(want)), 1e-6))
+        assert err < 2e-3, (k, err)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model2, train_model = mdl.SAR_Net((100, 80, 1), seed=5, lr=0.004, **kw)
+        x, y = us.synthetic_batch(model2.config, 8, seed=9)
+        hist = [train_model.train_on_batch(x, y) for _ in range(12)]
+    assert min(h["loss"] for h in hist[-3:]) < 0.85 * hist[0]["loss"], [round(h["loss"], 3) for h in hist]
+    assert len(model2.trainer()._graphs) == 1

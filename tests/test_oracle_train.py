@@ -324,3 +324,40 @@ def test_sixth_slice_resnet_training_gradients_match_finite_differences():
             pp[k][i] += h; pm[k][i] -= h
             fd = (loss_of(pp) - loss_of(pm)) / (2 * h)
             assert abs(fd - g[i]) <= 5e-6 * max(1.0, abs(fd)) + 5e-8, (k, i, fd, g[i])
+
+
+@pytest.mark.parametrize("mto", ["bigru", "avg"])
+def test_bigru_and_avg_integration_gradients_match_finite_differences(mto):
+    """integration() with mto = 'bigru' (AR_MERGE: Bi-GRU with return_sequences=False -- train.py's default MANY_TO_ONE) and
+    'avg' (GlobalAveragePooling1D) under AR_DS -> AR_DS_LN -> head: autograd vs central differences."""
+    B, S, C0, Dd, n = 4, 5, 7, 6, 8
+    um = 3
+    rng = np.random.RandomState(37)
+    params = _params("softmax", D=(2 * um if mto == "bigru" else Dd))
+    params["AR_DS/kernel"] = rng.randn(C0, Dd) * 0.4
+    params["AR_DS/bias"] = rng.randn(Dd) * 0.1
+    params["AR_DS_LN/gamma"] = rng.uniform(0.7, 1.3, Dd)
+    params["AR_DS_LN/beta"] = rng.randn(Dd) * 0.1
+    for d in ("forward", "backward"):
+        params["AR_MERGE/%s/kernel" % d] = rng.randn(Dd, 3 * um) * 0.4
+        params["AR_MERGE/%s/recurrent_kernel" % d] = rng.randn(um, 3 * um) * 0.4
+        params["AR_MERGE/%s/bias" % d] = rng.randn(6 * um) * 0.1
+    x = rng.randn(B, S, C0)
+    onehot = np.eye(n)[rng.randint(0, n, B)]
+    kw = dict(disc_enable=True, metric_loss="softmax", margin=0.0, w_accent=0.01, w_disc=0.6)
+    pool = dict(mto=mto, vlad_clusters=0, ghost_clusters=0, train_ds=True)
+    _, state, losses, grads = TO.train_step(params, {}, x, onehot, lr=0.01, iterations=0, pool=pool, **kw)
+    assert set(TO.pool_keys(mto)) | set(TO.DS_KEYS) <= set(grads)
+
+    def loss_of(pp):
+        t = {k: torch.as_tensor(v) for k, v in pp.items()}
+        return float(TO.pooled_head_loss(t, torch.as_tensor(x), torch.as_tensor(onehot), **pool, **kw)[0])
+    for k in TO.pool_keys(mto) + TO.DS_KEYS:
+        g = grads[k]
+        for _ in range(4):
+            i = tuple(rng.randint(0, s_) for s_ in g.shape)
+            h = 1e-6
+            pp, pm = {q: v.copy() for q, v in params.items()}, {q: v.copy() for q, v in params.items()}
+            pp[k][i] += h; pm[k][i] -= h
+            fd = (loss_of(pp) - loss_of(pm)) / (2 * h)
+            assert abs(fd - g[i]) <= 2e-6 * max(1.0, abs(fd)) + 2e-8, (k, i, fd, g[i])
