@@ -162,3 +162,52 @@ def test_model_load_weights_accepts_a_keras_named_npz(tmp_path, capsys):
     assert not np.array_equal(o.weights["resnet/stem/kernel"], m.weights["resnet/stem/kernel"])
     o.load_weights(p)
     assert all(np.array_equal(o.weights[k], m.weights[k]) for k in m.weights)
+
+
+def test_fit_generator_host_loop_epochs_callbacks_and_early_stop():
+    """model.fit_generator's host logic (train.py:38-44) with the device trainer stubbed out: `epochs - initial_epoch` epochs of
+    `steps_per_epoch` batches, (inputs, targets) tuples split, per-epoch weight sync BEFORE the callbacks run (so a callback's
+    model.save stores trained weights), mean logs, duck-typed callbacks, `model.stop_training` ends the run."""
+    from aesrc2020_b200 import model as mdl, weights as W
+    from aesrc2020_b200.config import SARConfig
+    cfg = SARConfig(input_shape=(100, 80, 1), ctc_enable=False, ar_enable=True, disc_enable=True, res_type="res18", res_filters=32,
+                    mto="bigru", metric_loss="softmax")
+    model = mdl.SARModel(cfg, W.init_weights(cfg, 1))
+    events = []
+
+    class FakeTrainer:
+        def __init__(self):
+            self.n = 0
+
+        def train_on_batch(self, x, y):
+            self.n += 1
+            events.append(("step", x["x_data"], None if y is None else y["y_accent"]))
+            return {"loss": 10.0 / self.n, "loss_accent": 1.0}
+
+        def sync_to_model(self):
+            events.append(("sync",))
+
+    model._trainer = FakeTrainer()
+
+    def gen():
+        i = 0
+        while True:
+            i += 1
+            yield ({"x_data": i}, {"y_accent": -i}) if i % 2 else {"x_data": i}          # tuples and bare input dicts
+
+    class Stopper:
+        def on_epoch_end(self, epoch, logs):
+            events.append(("cb", epoch, round(logs["loss"], 4)))
+            if epoch == 2:
+                model.stop_training = True
+
+    hist = model.fit_generator(gen(), steps_per_epoch=3, epochs=5, callbacks=[Stopper(), object()], initial_epoch=1, verbose=0)
+    assert len(hist) == 2                                                    # epochs 1 and 2, then stopped
+    steps = [e for e in events if e[0] == "step"]
+    assert [s[1] for s in steps] == [1, 2, 3, 4, 5, 6] and [s[2] for s in steps] == [-1, None, -3, None, -5, None]
+    assert abs(hist[0]["loss"] - np.mean([10.0, 5.0, 10.0 / 3])) < 1e-12 and hist[0]["loss_accent"] == 1.0
+    kinds = [e[0] for e in events]
+    assert kinds == ["step"] * 3 + ["sync", "cb"] + ["step"] * 3 + ["sync", "cb"]          # sync precedes the callbacks
+    assert [e[1] for e in events if e[0] == "cb"] == [1, 2]
+    # compile() keeps the learning rate for the optimiser (model.py:187-201)
+    assert mdl.compile(model, 1, lr=0.003) is model and model.lr == 0.003
