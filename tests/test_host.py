@@ -211,3 +211,25 @@ def test_fit_generator_host_loop_epochs_callbacks_and_early_stop():
     assert [e[1] for e in events if e[0] == "cb"] == [1, 2]
     # compile() keeps the learning rate for the optimiser (model.py:187-201)
     assert mdl.compile(model, 1, lr=0.003) is model and model.lr == 0.003
+
+
+def test_resnet_trainer_parameter_inventory_matches_the_weights():
+    """training_resnet.ResNetTrainer.param_keys (host logic): every ResNet weight of weights.init_weights is either trainable or
+    a BN moving statistic, exactly once; the l2 regulariser sits on the conv kernels only (resnet.py:36,56,86,116); the
+    first block of thin-ResNet34 carries its projection shortcut; HeadTrainer's key sets for the other slices exist in the weights."""
+    from aesrc2020_b200 import weights as W
+    from aesrc2020_b200.config import SARConfig
+    from aesrc2020_b200.training_resnet import ResNetTrainer
+    from oracle import train_oracle as TO
+    for res_type, f in (("res18", 64), ("res34", 32)):
+        cfg = SARConfig(input_shape=(200, 80, 1), ctc_enable=True, ar_enable=True, disc_enable=True, res_type=res_type, res_filters=f,
+                        mto="bigru", metric_loss="softmax")
+        w = W.init_weights(cfg, 1)
+        keys, l2, stats = ResNetTrainer.param_keys(cfg)
+        res = sorted(k for k in w if k.startswith("resnet/"))
+        assert sorted(keys + stats) == res and len(set(keys + stats)) == len(keys + stats)
+        assert all(k.endswith("/kernel") for k in l2) and set(l2) == {k for k in keys if k.endswith("/kernel")}
+        assert all(k.endswith(("/moving_mean", "/moving_variance")) for k in stats)
+        assert ("resnet/s1b1/short/kernel" in keys) == (res_type == "res34")
+        for k in TO.DS_KEYS + TO.CRNN_KEYS + TO.CTC_KEYS + TO.pool_keys("bigru"):
+            assert k in w, k
